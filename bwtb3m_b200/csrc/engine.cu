@@ -1,0 +1,425 @@
+// Engine: owns the device text and results, runs K1..K7 on one stream, exports the C ABI of
+// include/b3m.h.  Host orchestration only; all arithmetic is in the kernels.
+#include "engine.h"
+#include "scan.cuh"
+#include <string.h>
+#include <algorithm>
+
+namespace b3m {
+
+// ------------------------------------------------------------------------------------------
+struct PhaseTimer {
+	Stream & st;
+	cudaEvent_t ev[16];
+	int n = 0;
+	explicit PhaseTimer(Stream & s) : st(s) { for (auto & e : ev) B3M_CUDA(cudaEventCreate(&e)); }
+	~PhaseTimer() { for (auto & e : ev) cudaEventDestroy(e); }
+	void mark() { B3M_CUDA(cudaEventRecord(ev[n++], st.s)); }
+	float ms(int a, int b) { float t = 0; cudaEventElapsedTime(&t, ev[a], ev[b]); return t; }
+};
+
+Engine::Engine(int dev, void * stream) : device(dev) {
+	B3M_CUDA(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	B3M_CUDA(cudaGetDeviceProperties(&prop, device));
+	st.sms = prop.multiProcessorCount;
+	if (stream) { st.s = (cudaStream_t)stream; own_stream = false; }
+	else { B3M_CUDA(cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking)); own_stream = true; }
+	// keep freed blocks in the pool: repeated builds do not go back to the driver allocator
+	cudaMemPool_t pool;
+	B3M_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+	uint64_t thr = ~0ull;
+	B3M_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+	B3M_CUDA(cudaMallocHost((void **)&pinned, 4096));
+}
+
+Engine::~Engine() {
+	cudaSetDevice(device);
+	cudaStreamSynchronize(st.s);
+	raw.release(); codes.release(); bwt.release(); prerank.release(); sa.release(); isa.release(); dict.release();
+	d_hist.release(); d_special.release();
+	cudaStreamSynchronize(st.s);
+	if (pinned) cudaFreeHost(pinned);
+	if (own_stream) cudaStreamDestroy(st.s);
+}
+
+void Engine::reset_results() {
+	bwt.release(); prerank.release(); sa.release(); isa.release(); dict.release();
+	have_results = false;
+}
+
+// K1 ---------------------------------------------------------------------------------------
+void Engine::load(const void * input, uint64_t nbytes, int itype, bool on_device) {
+	B3M_CUDA(cudaSetDevice(device));
+	B3M_REQUIRE(itype >= 0 && itype <= 3, "unknown input type");
+	reset_results();
+	codes.release(); raw.release();
+	inputtype = itype;
+	PhaseTimer pt(st);
+	pt.mark();
+	const uint8_t * d_in = nullptr;
+	auto stage = [&](uint64_t off, uint64_t len, uint64_t pad) {
+		raw.alloc(st, len + pad + 16);
+		if (pad) B3M_CUDA(cudaMemsetAsync(raw.get() + len, 0, pad + 16, st.s));
+		B3M_CUDA(cudaMemcpyAsync(raw.get(), (const uint8_t *)input + off, len,
+		                         on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st.s));
+		d_in = raw.get();
+	};
+	auto peek = [&](uint64_t off, uint64_t len, uint8_t * dst) {
+		if (on_device) {
+			B3M_CUDA(cudaMemcpyAsync(pinned, (const uint8_t *)input + off, len, cudaMemcpyDeviceToHost, st.s));
+			B3M_CUDA(cudaStreamSynchronize(st.s));
+			memcpy(dst, pinned, len);
+		} else memcpy(dst, (const uint8_t *)input + off, len);
+	};
+	d_hist.alloc(st, 256);
+	memset(hist, 0, sizeof(hist));
+	T = DevText();
+	uint64_t hcodes[256];
+	if (itype == B3M_INPUT_PAC || itype == B3M_INPUT_PACTERM) {
+		B3M_REQUIRE(nbytes >= 2, "pac file too short");
+		uint8_t last;
+		peek(nbytes - 1, 1, &last);
+		B3M_REQUIRE(last < 4, "pac file: bad count byte");
+		uint64_t const l = (nbytes - 2) * 4 + last; // BWA fa2pac layout
+		B3M_REQUIRE(l > 0, "empty input");
+		if (on_device) d_in = (const uint8_t *)input; else stage(0, nbytes, 0);
+		codes.alloc(st, l + 16);
+		k1_unpack_pac(st, d_in, l, codes.get(), d_hist.get());
+		B3M_CUDA(cudaMemcpyAsync(pinned, d_hist.get(), 256 * 8, cudaMemcpyDeviceToHost, st.s));
+		B3M_CUDA(cudaStreamSynchronize(st.s));
+		memcpy(hcodes, pinned, sizeof(hcodes));
+		T.ntext = l; T.sigma = 4; T.keybits = 2;
+		if (itype == B3M_INPUT_PACTERM) {
+			T.has_term = 1; T.n = l + 1;
+			hist[0] = 1;
+			for (int c = 0; c < 4; ++c) { hist[c + 1] = hcodes[c]; code2sym[c] = (uint8_t)(c + 1); }
+		} else {
+			T.has_term = 0; T.n = l;
+			for (int c = 0; c < 4; ++c) { hist[c] = hcodes[c]; code2sym[c] = (uint8_t)c; }
+		}
+		for (int c = 0; c < 4; ++c) codehist[c] = hcodes[c];
+		decode_bytes = nbytes + l;
+	} else {
+		uint64_t nsym;
+		if (itype == B3M_INPUT_COMPACTSTREAM) {
+			// [layout unpinned, SURVEY 8c] 4 big-endian uint64: bits, n, words, words; then the bit stream
+			B3M_REQUIRE(nbytes >= 32, "compact file too short");
+			uint8_t hdr[16];
+			peek(0, 16, hdr);
+			uint64_t b = 0, n = 0;
+			for (int i = 0; i < 8; ++i) { b = (b << 8) | hdr[i]; n = (n << 8) | hdr[8 + i]; }
+			B3M_REQUIRE(b >= 1 && b <= 8, "compact file: unsupported bits per symbol");
+			B3M_REQUIRE((n * b + 7) / 8 <= nbytes - 32, "compact file: truncated");
+			B3M_REQUIRE(n > 0, "empty input");
+			stage(32, nbytes - 32, 8);
+			codes.alloc(st, n + 16);
+			k1_unpack_compact(st, d_in, n, (unsigned)b, codes.get(), d_hist.get());
+			nsym = n;
+		} else {
+			B3M_REQUIRE(nbytes > 0, "empty input");
+			if (on_device) d_in = (const uint8_t *)input; else stage(0, nbytes, 0);
+			codes.alloc(st, nbytes + 16);
+			k1_hist_bytes(st, d_in, nbytes, d_hist.get());
+			nsym = nbytes;
+		}
+		B3M_CUDA(cudaMemcpyAsync(pinned, d_hist.get(), 256 * 8, cudaMemcpyDeviceToHost, st.s));
+		B3M_CUDA(cudaStreamSynchronize(st.s));
+		memcpy(hist, pinned, sizeof(hist));
+		// dense, order preserving alphabet
+		uint8_t lut[256];
+		memset(lut, 0, sizeof(lut));
+		uint32_t sigma = 0;
+		for (int s = 0; s < 256; ++s) if (hist[s]) { lut[s] = (uint8_t)sigma; code2sym[sigma] = (uint8_t)s; codehist[sigma] = hist[s]; ++sigma; }
+		memcpy(pinned, lut, 256);
+		DevBuf<uint8_t> dlut(st, 256);
+		B3M_CUDA(cudaMemcpyAsync(dlut.get(), pinned, 256, cudaMemcpyHostToDevice, st.s));
+		const uint8_t * src = (itype == B3M_INPUT_COMPACTSTREAM) ? (const uint8_t *)codes.get() : d_in;
+		k1_map_bytes(st, src, nsym, dlut.get(), codes.get());
+		B3M_CUDA(cudaStreamSynchronize(st.s)); // pinned staging buffer is reused below
+		T.ntext = nsym; T.n = nsym; T.sigma = sigma; T.has_term = 0;
+		T.keybits = sigma <= 4 ? 2 : (sigma <= 16 ? 4 : 8);
+		decode_bytes = 3 * nsym;
+	}
+	B3M_REQUIRE(T.n < 0xFFFFFFF0ull, "inputs of 2^32 symbols or more are not supported yet");
+	T.codes = codes.get();
+	raw.release();
+	pt.mark();
+	B3M_CUDA(cudaStreamSynchronize(st.s));
+	ms_decode = pt.ms(0, 1);
+	loaded = true;
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_sample_ranks(const uint32_t * __restrict__ rank, uint64_t ntext, uint64_t rate, uint32_t shift, uint64_t ns, uint32_t * __restrict__ out) {
+	uint64_t const q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= ns) return;
+	uint64_t const p = q * rate;
+	out[q] = p < ntext ? rank[p] + shift : 0u; // p == ntext: the terminator suffix has rank 0
+}
+
+__global__ void __launch_bounds__(256)
+k_pairs(const uint32_t * __restrict__ prerank, uint64_t ns, uint64_t rate, unsigned long long * __restrict__ pairs) {
+	uint64_t const q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= ns) return;
+	pairs[2 * q] = prerank[q];
+	pairs[2 * q + 1] = q * rate;
+}
+
+__global__ void __launch_bounds__(256)
+k_fill_u64(unsigned long long * p, uint64_t n, unsigned long long v) {
+	uint64_t const i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) p[i] = v;
+}
+
+static uint64_t choose_preisarate(uint64_t n, int sms) {
+	// enough independent LF chains to fill every SM (2048 threads each) a few times over,
+	// but chains of at least 64 steps
+	uint64_t const want = (uint64_t)sms * 2048 * 2;
+	uint64_t r = 64;
+	while (r < (1u << 18) && n / r > want) r <<= 1;
+	return r;
+}
+
+void Engine::make_dict(uint32_t exc_pos, uint32_t exc_code, uint32_t exc_lf) {
+	int const flavour = T.sigma <= 4 ? 2 : 8;
+	size_t const bytes = dict_bytes(flavour, T.n, T.sigma);
+	dict.alloc(st, bytes);
+	k4_build_dict(st, bwt.get(), T.n, flavour, T.sigma, dict.get());
+	D = DevDict();
+	D.flavour = flavour; D.n = T.n; D.lines = dict.get(); D.sigma = T.sigma;
+	uint64_t acc = T.has_term ? 1 : 0;
+	for (uint32_t c = 0; c < 257; ++c) { D.C[c] = (uint32_t)acc; if (c < T.sigma) acc += codehist[c]; }
+	D.exc_pos = exc_pos; D.exc_code = exc_code; D.exc_lf = exc_lf;
+	dict_bytes_moved = T.n + bytes;
+}
+
+void Engine::build(b3m_build_params const & p) {
+	B3M_CUDA(cudaSetDevice(device));
+	B3M_REQUIRE(loaded, "no input loaded");
+	B3M_REQUIRE(p.numblocks >= 1, "numblocks must be >= 1");
+	auto pow2 = [](uint64_t v) { return v && !(v & (v - 1)); };
+	B3M_REQUIRE(pow2(p.sasamplingrate) && pow2(p.isasamplingrate), "sampling rates must be powers of two");
+	reset_results();
+	params = p;
+	prerate = p.preisarate ? p.preisarate : (p.bwtonly ? 64 : choose_preisarate(T.n, st.sms));
+	B3M_REQUIRE(pow2(prerate), "preisarate must be a power of two");
+	npre = div_up(T.n, prerate);
+	sortstats = SortStats(); walkstats = WalkStats();
+	gap_lf_steps = gap_chains = merge_bytes = extract_bytes = 0; max_lcpnext = 0;
+	ms_sort = ms_extract = ms_dict = ms_gap = ms_merge = ms_walk = 0;
+	numblocks = std::min<uint64_t>(p.numblocks, T.n);
+
+	PhaseTimer pt(st);
+	pt.mark(); // 0
+	d_special.alloc(st, 4);
+	B3M_CUDA(cudaMemsetAsync(d_special.get(), 0xff, 16, st.s));
+	bwt.alloc(st, T.n + 16);
+	prerank.alloc(st, npre);
+	uint32_t exc_pos = 0xffffffffu;
+	if (numblocks == 1) {
+		uint64_t const W = T.ntext;
+		DevBuf<uint32_t> dsa(st, W), drank(st, W);
+		k2_suffix_sort(st, T, 0, W, T.has_term ? 0 : 1, 0, dsa.get(), drank.get(), &sortstats);
+		pt.mark(); // 1
+		uint64_t const shift = T.has_term ? 1 : 0;
+		k3_extract_bwt(st, T, 0, dsa.get(), W, bwt.get(), shift, d_special.get());
+		if (T.has_term) // rank 0 is the terminator suffix; its predecessor is the last base
+			B3M_CUDA(cudaMemcpyAsync(bwt.get(), T.codes + T.ntext - 1, 1, cudaMemcpyDeviceToDevice, st.s));
+		B3M_LAUNCH(st, k_sample_ranks, (unsigned)div_up(npre, 256), 256, 0, (const uint32_t *)drank.get(), T.ntext, prerate,
+		           (uint32_t)shift, npre, prerank.get());
+		extract_bytes = W * (4 + 32 + 1) + npre * 36;
+		if (T.has_term) {
+			B3M_CUDA(cudaMemcpyAsync(pinned, d_special.get(), 16, cudaMemcpyDeviceToHost, st.s));
+			B3M_CUDA(cudaStreamSynchronize(st.s));
+			exc_pos = ((uint32_t *)pinned)[0];
+			B3M_REQUIRE(exc_pos != 0xffffffffu, "internal: terminator row not found");
+		}
+		pt.mark(); // 2
+		ms_sort = -1; // filled below
+	} else {
+		build_blocks(pt, &exc_pos); // marks 1 (leaves+merges split inside) and 2
+	}
+	root_exc_pos = exc_pos;
+	make_dict(exc_pos, 0, 0);
+	pt.mark(); // 3
+	nsa = nisa = 0;
+	if (!p.bwtonly) {
+		nsa = div_up(T.n, p.sasamplingrate);
+		nisa = div_up(T.n, p.isasamplingrate);
+		sa.alloc(st, nsa); isa.alloc(st, nisa);
+		B3M_LAUNCH(st, k_fill_u64, (unsigned)div_up(nsa, 256), 256, 0, (unsigned long long *)sa.get(), nsa, ~0ull);
+		B3M_LAUNCH(st, k_fill_u64, (unsigned)div_up(nisa, 256), 256, 0, (unsigned long long *)isa.get(), nisa, ~0ull);
+		k7_walk(st, D, prerank.get(), npre, prerate, T.n, p.sasamplingrate, p.isasamplingrate, sa.get(), isa.get(), &walkstats);
+	}
+	pt.mark(); // 4
+	B3M_CUDA(cudaStreamSynchronize(st.s));
+	if (numblocks == 1) { ms_sort = pt.ms(0, 1); ms_extract = pt.ms(1, 2); }
+	ms_dict = pt.ms(2, 3);
+	ms_walk = pt.ms(3, 4);
+	ms_total = pt.ms(0, 4);
+	have_results = true;
+}
+
+void Engine::fetch(uint8_t * h_bwt, uint64_t * h_pairs, uint64_t * h_sa, uint64_t * h_isa) {
+	B3M_CUDA(cudaSetDevice(device));
+	B3M_REQUIRE(have_results, "no results");
+	if (h_bwt) {
+		DevBuf<uint8_t> out(st, T.n + 16), dlut(st, 256);
+		uint8_t lut[256];
+		memset(lut, 0, 256);
+		for (uint32_t c = 0; c < T.sigma; ++c) lut[c] = code2sym[c];
+		B3M_CUDA(cudaMemcpyAsync(dlut.get(), lut, 256, cudaMemcpyHostToDevice, st.s));
+		k1_map_bytes(st, bwt.get(), T.n, dlut.get(), out.get());
+		if (T.has_term) B3M_CUDA(cudaMemsetAsync(out.get() + root_exc_pos, 0, 1, st.s));
+		B3M_CUDA(cudaMemcpyAsync(h_bwt, out.get(), T.n, cudaMemcpyDeviceToHost, st.s));
+		B3M_CUDA(cudaStreamSynchronize(st.s));
+	}
+	if (h_pairs) {
+		DevBuf<uint64_t> pairs(st, 2 * npre);
+		B3M_LAUNCH(st, k_pairs, (unsigned)div_up(npre, 256), 256, 0, (const uint32_t *)prerank.get(), npre, prerate,
+		           (unsigned long long *)pairs.get());
+		B3M_CUDA(cudaMemcpyAsync(h_pairs, pairs.get(), 16 * npre, cudaMemcpyDeviceToHost, st.s));
+		B3M_CUDA(cudaStreamSynchronize(st.s));
+	}
+	if (h_sa && nsa) B3M_CUDA(cudaMemcpyAsync(h_sa, sa.get(), 8 * nsa, cudaMemcpyDeviceToHost, st.s));
+	if (h_isa && nisa) B3M_CUDA(cudaMemcpyAsync(h_isa, isa.get(), 8 * nisa, cudaMemcpyDeviceToHost, st.s));
+	B3M_CUDA(cudaStreamSynchronize(st.s));
+}
+
+void Engine::info(b3m_info * o) {
+	memset(o, 0, sizeof(*o));
+	o->n = T.n; o->sigma = T.sigma + (T.has_term ? 1 : 0); o->numblocks = numblocks;
+	o->preisarate = prerate; o->npreisa = npre;
+	o->sasamplingrate = params.sasamplingrate; o->nsa = nsa;
+	o->isasamplingrate = params.isasamplingrate; o->nisa = nisa;
+	memcpy(o->hist, hist, sizeof(hist));
+	o->sort_rounds = sortstats.rounds; o->radix_passes = sortstats.radix_passes; o->radix_bytes = sortstats.radix_bytes;
+	o->sort_active_sum = sortstats.active_sum; o->sort_other_bytes = sortstats.other_bytes;
+	o->gap_lf_steps = gap_lf_steps; o->walk_lf_steps = walkstats.steps; o->walk_chains = walkstats.chains; o->gap_chains = gap_chains;
+	o->merge_bytes = merge_bytes; o->extract_bytes = extract_bytes; o->dict_bytes = dict_bytes_moved; o->decode_bytes = decode_bytes;
+	o->launches = st.launches; o->max_lcpnext = max_lcpnext;
+	o->ms_decode = ms_decode; o->ms_sort = ms_sort; o->ms_extract = ms_extract; o->ms_dict = ms_dict;
+	o->ms_gap = ms_gap; o->ms_merge = ms_merge; o->ms_walk = ms_walk; o->ms_total = ms_total;
+}
+
+__global__ void __launch_bounds__(256)
+k_pick_starts(const uint32_t * __restrict__ prerank, uint64_t npre, uint64_t nchains, uint32_t * __restrict__ start) {
+	uint64_t const q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= nchains) return;
+	start[q] = prerank[(q * npre) / nchains];
+}
+
+void Engine::lf_bench(uint64_t nchains, uint64_t steps, float * ms, uint64_t * checksum) {
+	B3M_CUDA(cudaSetDevice(device));
+	B3M_REQUIRE(have_results, "no results");
+	B3M_REQUIRE(nchains >= 1, "nchains must be >= 1");
+	DevBuf<uint32_t> start(st, nchains), out(st, nchains);
+	B3M_LAUNCH(st, k_pick_starts, (unsigned)div_up(nchains, 256), 256, 0, (const uint32_t *)prerank.get(), npre, nchains, start.get());
+	PhaseTimer pt(st);
+	pt.mark();
+	k7_lfbench(st, D, start.get(), nchains, steps, out.get());
+	pt.mark();
+	std::vector<uint32_t> h(nchains);
+	B3M_CUDA(cudaMemcpyAsync(h.data(), out.get(), 4 * nchains, cudaMemcpyDeviceToHost, st.s));
+	B3M_CUDA(cudaStreamSynchronize(st.s));
+	*ms = pt.ms(0, 1);
+	uint64_t cs = 0;
+	for (uint64_t i = 0; i < nchains; ++i) cs = cs * 1000003ull + h[i];
+	if (checksum) *checksum = cs;
+}
+
+} // namespace b3m
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+using b3m::Engine;
+
+struct b3m_engine {
+	Engine * e;
+	std::string err;
+};
+
+static void set_err(char * err, size_t errlen, const char * msg) {
+	if (err && errlen) { strncpy(err, msg, errlen - 1); err[errlen - 1] = 0; }
+}
+
+#define B3M_GUARD(h, body)                                                   \
+	if (!(h)) return 1;                                                      \
+	try { body; (h)->err.clear(); return 0; }                                \
+	catch (std::exception const & ex) { (h)->err = ex.what(); return 2; }    \
+	catch (...) { (h)->err = "unknown error"; return 3; }
+
+extern "C" {
+
+const char * b3m_version(void) { return "b3m-b200 0.1 (sm_100a)"; }
+
+int b3m_parse_inputtype(const char * name) {
+	if (!name) return -1;
+	if (!strcmp(name, "bytestream")) return B3M_INPUT_BYTESTREAM;
+	if (!strcmp(name, "compactstream")) return B3M_INPUT_COMPACTSTREAM;
+	if (!strcmp(name, "pac")) return B3M_INPUT_PAC;
+	if (!strcmp(name, "pacterm")) return B3M_INPUT_PACTERM;
+	return -1;
+}
+
+int b3m_engine_create(int device, void * cuda_stream, b3m_engine ** out, char * err, size_t errlen) {
+	if (!out) return 1;
+	*out = nullptr;
+	try {
+		int ndev = 0;
+		cudaError_t const ce = cudaGetDeviceCount(&ndev);
+		if (ce != cudaSuccess || ndev <= 0)
+			throw b3m::Error(std::string("no CUDA device available (") + cudaGetErrorString(ce) + "); this library has no CPU fallback");
+		if (device < 0 || device >= ndev) throw b3m::Error("bad device ordinal");
+		b3m_engine * h = new b3m_engine();
+		h->e = new Engine(device, cuda_stream);
+		*out = h;
+		return 0;
+	} catch (std::exception const & ex) { set_err(err, errlen, ex.what()); return 2; }
+	catch (...) { set_err(err, errlen, "unknown error"); return 3; }
+}
+
+void b3m_engine_destroy(b3m_engine * h) {
+	if (!h) return;
+	delete h->e;
+	delete h;
+}
+
+const char * b3m_engine_last_error(const b3m_engine * h) { return h ? h->err.c_str() : "null engine"; }
+
+int b3m_engine_load_host(b3m_engine * h, const void * input, uint64_t nbytes, int inputtype) {
+	B3M_GUARD(h, h->e->load(input, nbytes, inputtype, false));
+}
+int b3m_engine_load_device(b3m_engine * h, const void * d_input, uint64_t nbytes, int inputtype) {
+	B3M_GUARD(h, h->e->load(d_input, nbytes, inputtype, true));
+}
+int b3m_engine_build(b3m_engine * h, const b3m_build_params * p) {
+	B3M_GUARD(h, { if (!p) throw b3m::Error("null params"); h->e->build(*p); });
+}
+int b3m_engine_info(b3m_engine * h, b3m_info * info) {
+	B3M_GUARD(h, { if (!info) throw b3m::Error("null info"); h->e->info(info); });
+}
+int b3m_engine_fetch(b3m_engine * h, uint8_t * bwt, uint64_t * preisa_pairs, uint64_t * sa, uint64_t * isa) {
+	B3M_GUARD(h, h->e->fetch(bwt, preisa_pairs, sa, isa));
+}
+int b3m_engine_device_results(b3m_engine * h, const void ** d_bwt_codes, const void ** d_preisa_rank,
+                              const void ** d_sa, const void ** d_isa) {
+	B3M_GUARD(h, {
+		if (!h->e->have_results) throw b3m::Error("no results");
+		if (d_bwt_codes) *d_bwt_codes = h->e->bwt.get();
+		if (d_preisa_rank) *d_preisa_rank = h->e->prerank.get();
+		if (d_sa) *d_sa = h->e->sa.get();
+		if (d_isa) *d_isa = h->e->isa.get();
+	});
+}
+int b3m_engine_lf_bench(b3m_engine * h, uint64_t nchains, uint64_t steps, float * ms, uint64_t * checksum) {
+	B3M_GUARD(h, { float t = 0; h->e->lf_bench(nchains, steps, &t, checksum); if (ms) *ms = t; });
+}
+int b3m_engine_sync(b3m_engine * h) {
+	B3M_GUARD(h, { B3M_CUDA(cudaSetDevice(h->e->device)); B3M_CUDA(cudaStreamSynchronize(h->e->st.s)); });
+}
+
+} // extern "C"

@@ -1,0 +1,58 @@
+// Engine class behind the C ABI (include/b3m.h).
+#pragma once
+#include "../../include/b3m.h"
+#include "kernels.h"
+
+namespace b3m {
+
+struct PhaseTimer;
+
+struct Engine {
+	int device = 0;
+	Stream st;
+	bool own_stream = true;
+	uint8_t * pinned = nullptr; // 4 KiB pinned staging area for small copies
+
+	// input
+	bool loaded = false;
+	int inputtype = 0;
+	DevBuf<uint8_t> raw, codes;
+	DevBuf<uint64_t> d_hist;
+	DevText T;
+	uint64_t hist[256];      // reference symbol -> count
+	uint64_t codehist[256];  // dense code -> count (terminator excluded)
+	uint8_t code2sym[256];
+
+	// results of the last build
+	bool have_results = false;
+	b3m_build_params params{};
+	uint64_t numblocks = 1;
+	uint64_t prerate = 0, npre = 0, nsa = 0, nisa = 0;
+	DevBuf<uint8_t> bwt;        // n dense codes (terminator row holds code 0, see root_exc_pos)
+	DevBuf<uint32_t> prerank;   // rank of positions 0, prerate, 2*prerate, ...
+	DevBuf<uint64_t> sa, isa;
+	DevBuf<uint8_t> dict;
+	DevBuf<uint32_t> d_special;
+	DevDict D;
+	uint32_t root_exc_pos = 0xffffffffu;
+
+	// statistics
+	SortStats sortstats;
+	WalkStats walkstats;
+	uint64_t gap_lf_steps = 0, gap_chains = 0, merge_bytes = 0, extract_bytes = 0, dict_bytes_moved = 0, decode_bytes = 0;
+	uint64_t max_lcpnext = 0;
+	float ms_decode = 0, ms_sort = 0, ms_extract = 0, ms_dict = 0, ms_gap = 0, ms_merge = 0, ms_walk = 0, ms_total = 0;
+
+	Engine(int dev, void * stream);
+	~Engine();
+	void reset_results();
+	void load(const void * input, uint64_t nbytes, int itype, bool on_device);
+	void build(b3m_build_params const & p);
+	void build_blocks(PhaseTimer & pt, uint32_t * exc_pos);
+	void make_dict(uint32_t exc_pos, uint32_t exc_code, uint32_t exc_lf);
+	void fetch(uint8_t * h_bwt, uint64_t * h_pairs, uint64_t * h_sa, uint64_t * h_isa);
+	void info(b3m_info * o);
+	void lf_bench(uint64_t nchains, uint64_t steps, float * ms, uint64_t * checksum);
+};
+
+} // namespace b3m

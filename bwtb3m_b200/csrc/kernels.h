@@ -1,0 +1,76 @@
+// Internal (C++) interface between the engine and the CUDA stages K1..K7.
+// Replaces, stage by stage, the libmaus2 code reached from
+// /root/reference/src/bwtb3m.cpp:62-63 (BwtMergeSort::computeBwt); see DESIGN.md.
+#pragma once
+#include "common.cuh"
+
+namespace b3m {
+
+// ---- device text -------------------------------------------------------------------------
+// Dense symbol codes 0..sigma-1, one byte per symbol.  For pacterm the unique terminator is
+// implicit: it sits at position ntext (n = ntext+1) and is smaller than every code.
+struct DevText {
+	const uint8_t * codes = nullptr;
+	uint64_t ntext = 0;     // stored symbols
+	uint64_t n = 0;         // BWT length (ntext, or ntext+1 with implicit terminator)
+	uint32_t sigma = 0;     // number of distinct codes
+	int has_term = 0;       // pacterm
+	unsigned keybits = 8;   // bits per code inside sort keys (2, 4 or 8)
+};
+
+// ---- K1 ---------------------------------------------------------------------------------
+void k1_hist_bytes(Stream & st, const uint8_t * d_in, uint64_t nbytes, uint64_t * d_hist256);
+void k1_map_bytes(Stream & st, const uint8_t * d_in, uint64_t n, const uint8_t * d_lut256, uint8_t * d_out);
+void k1_unpack_pac(Stream & st, const uint8_t * d_pac, uint64_t l, uint8_t * d_out, uint64_t * d_hist256);
+void k1_unpack_compact(Stream & st, const uint8_t * d_words, uint64_t n, unsigned b, uint8_t * d_out, uint64_t * d_hist256);
+
+// ---- K2 ---------------------------------------------------------------------------------
+struct SortStats {
+	uint64_t rounds = 0;          // prefix doubling rounds including round 0
+	uint64_t radix_passes = 0;
+	uint64_t radix_bytes = 0;     // algorithmic bytes of all radix passes
+	uint64_t active_sum = 0;      // sum over rounds of records entering the round
+	uint64_t other_bytes = 0;     // key extraction, flagging, rank scatter, compaction
+};
+
+// Sorts the W suffixes that start at text positions wstart+i, 0 <= i < W.
+// circular != 0: W == ntext, wstart == 0, indices wrap (terminator-free whole text).
+// circular == 0: the end of the window is a sentinel smaller than every symbol; text positions
+//                wrap modulo ntext when text_wraps != 0.
+// sa[k] = window-relative start of the k-th smallest suffix; rank = inverse permutation.
+void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W, int circular, int text_wraps,
+                    uint32_t * sa, uint32_t * rank, SortStats * stats);
+
+// ---- K3 ---------------------------------------------------------------------------------
+// bwt[k + shift] = code preceding suffix sa[k] (text position wstart+sa[k]); the suffix at text
+// position 0 of a terminated text gets code 0 and its output index is written to *d_termrank.
+void k3_extract_bwt(Stream & st, DevText const & T, uint64_t wstart, const uint32_t * sa, uint64_t m,
+                    uint8_t * bwt, uint64_t shift, uint32_t * d_special);
+
+// ---- K4 / K7 ----------------------------------------------------------------------------
+// Rank dictionary, 2-bit flavour: 64-byte lines = 4 x uint32 cumulative counts + 48 bytes
+// (192 symbols x 2 bit).  Byte flavour: 128 symbols per block, 256 x uint32 counts + 128 bytes.
+struct DevDict {
+	int flavour = 0;              // 2 or 8
+	uint64_t n = 0;               // symbols
+	const void * lines = nullptr; // flavour 2: uint4[4*nlines]; flavour 8: see rankdict.cuh
+	uint64_t nlines = 0;
+	uint32_t sigma = 0;           // number of codes
+	uint32_t C[257];              // C[c] = # symbols with code < c (exception position excluded)
+	uint32_t exc_pos = 0xffffffffu; // position whose stored symbol must not be counted
+	uint32_t exc_code = 0;        // code stored at exc_pos
+	uint32_t exc_lf = 0;          // LF target when a walk stands on exc_pos (terminator row -> 0)
+};
+size_t dict_bytes(int flavour, uint64_t n, uint32_t sigma);
+void k4_build_dict(Stream & st, const uint8_t * bwt, uint64_t n, int flavour, uint32_t sigma, void * lines);
+
+struct WalkStats { uint64_t steps = 0; uint64_t chains = 0; };
+// K7: from every anchor (rank, pos) walk LF towards smaller positions for `len` steps,
+// sampling SA by rank and ISA by position.  pos_off: value added to a text position before it
+// is reported (0), n: BWT length.
+void k7_walk(Stream & st, DevDict const & D, const uint32_t * anchor_rank, uint64_t nanchors, uint64_t arate,
+             uint64_t n, uint64_t sarate, uint64_t isarate, uint64_t * sa_out, uint64_t * isa_out, WalkStats * ws);
+// LF-steps/s instrument (restates bwttestdecodespeed.cpp:82-96 for many chains)
+void k7_lfbench(Stream & st, DevDict const & D, const uint32_t * start_rank, uint64_t nchains, uint64_t steps, uint32_t * out_rank);
+
+} // namespace b3m

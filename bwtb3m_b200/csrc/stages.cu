@@ -1,0 +1,392 @@
+// K1 (input decoding + histogram), K3 (BWT extraction), K4 (rank dictionary build),
+// K7 (sampled SA/ISA LF walk).  See kernels.h for the reference code each one replaces.
+#include "kernels.h"
+#include "rankdict.cuh"
+#include "scan.cuh"
+
+namespace b3m {
+
+// ------------------------------------------------------------------------------------------
+// K1: replaces the libmaus2 input wrappers {Byte,Pac,PacTerm,Compact}InputTypes
+// (/root/reference/src/checkbwt.cpp:254-270) and the symbol histogram pass.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_hist_bytes(const uint8_t * __restrict__ in, uint64_t n, unsigned long long * __restrict__ hist) {
+	__shared__ uint32_t sh[256];
+	sh[threadIdx.x] = 0;
+	__syncthreads();
+	uint64_t const nvec = n / 16;
+	const uint4 * v = reinterpret_cast<const uint4 *>(in);
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (uint64_t)gridDim.x * blockDim.x) {
+		uint4 const q = ld_stream_u4(v + i);
+		uint32_t const w[4] = {q.x, q.y, q.z, q.w};
+		#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+			atomicAdd(&sh[w[k] & 255u], 1u);
+			atomicAdd(&sh[(w[k] >> 8) & 255u], 1u);
+			atomicAdd(&sh[(w[k] >> 16) & 255u], 1u);
+			atomicAdd(&sh[w[k] >> 24], 1u);
+		}
+	}
+	if (blockIdx.x == 0)
+		for (uint64_t i = nvec * 16 + threadIdx.x; i < n; i += blockDim.x) atomicAdd(&sh[in[i]], 1u);
+	__syncthreads();
+	if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}
+
+void k1_hist_bytes(Stream & st, const uint8_t * d_in, uint64_t nbytes, uint64_t * d_hist256) {
+	B3M_CUDA(cudaMemsetAsync(d_hist256, 0, 256 * sizeof(uint64_t), st.s));
+	if (!nbytes) return;
+	// one CTA handles at most 2^32/16 vectors between flushes of its 32-bit shared counters
+	uint64_t want = div_up(nbytes / 16 + 1, 256 * 64);
+	unsigned grid = (unsigned)(want < (uint64_t)st.sms * 8 ? (want ? want : 1) : (uint64_t)st.sms * 8);
+	B3M_LAUNCH(st, k_hist_bytes, grid, 256, 0, d_in, nbytes, (unsigned long long *)d_hist256);
+}
+
+__global__ void __launch_bounds__(256) k_map_bytes(const uint8_t * __restrict__ in, uint64_t n, const uint8_t * __restrict__ lut, uint8_t * __restrict__ out) {
+	__shared__ uint8_t sl[256];
+	sl[threadIdx.x] = lut[threadIdx.x];
+	__syncthreads();
+	uint64_t const nvec = n / 16;
+	const uint4 * v = reinterpret_cast<const uint4 *>(in);
+	uint4 * o = reinterpret_cast<uint4 *>(out);
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (uint64_t)gridDim.x * blockDim.x) {
+		uint4 const q = ld_stream_u4(v + i);
+		uint32_t w[4] = {q.x, q.y, q.z, q.w};
+		#pragma unroll
+		for (int k = 0; k < 4; ++k)
+			w[k] = (uint32_t)sl[w[k] & 255u] | ((uint32_t)sl[(w[k] >> 8) & 255u] << 8) |
+			       ((uint32_t)sl[(w[k] >> 16) & 255u] << 16) | ((uint32_t)sl[w[k] >> 24] << 24);
+		o[i] = make_uint4(w[0], w[1], w[2], w[3]);
+	}
+	if (blockIdx.x == 0)
+		for (uint64_t i = nvec * 16 + threadIdx.x; i < n; i += blockDim.x) out[i] = sl[in[i]];
+}
+
+void k1_map_bytes(Stream & st, const uint8_t * d_in, uint64_t n, const uint8_t * d_lut256, uint8_t * d_out) {
+	if (!n) return;
+	uint64_t want = div_up(n / 16 + 1, 256 * 8);
+	unsigned grid = (unsigned)(want < (uint64_t)st.sms * 16 ? (want ? want : 1) : (uint64_t)st.sms * 16);
+	B3M_LAUNCH(st, k_map_bytes, grid, 256, 0, d_in, n, d_lut256, d_out);
+}
+
+// pac: 2 bit/symbol, MSB first inside each byte (BWA fa2pac layout).
+// One thread expands 4 pac bytes into 16 one-byte codes (one 128-bit store).
+__global__ void __launch_bounds__(256) k_unpack_pac(const uint8_t * __restrict__ pac, uint64_t l, uint8_t * __restrict__ out,
+                                                    unsigned long long * __restrict__ hist) {
+	__shared__ uint32_t sh[4];
+	if (threadIdx.x < 4) sh[threadIdx.x] = 0;
+	__syncthreads();
+	uint64_t const ngroups = div_up(l, 16);
+	uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+	for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += (uint64_t)gridDim.x * blockDim.x) {
+		uint64_t const first = g * 16;
+		uint32_t const cnt = (l - first) < 16 ? (uint32_t)(l - first) : 16u;
+		uint32_t const nb = (cnt + 3) / 4;
+		uint32_t bytes[4] = {0, 0, 0, 0};
+		if (nb == 4) {
+			uint32_t const w = *reinterpret_cast<const uint32_t *>(pac + g * 4);
+			bytes[0] = w & 255u; bytes[1] = (w >> 8) & 255u; bytes[2] = (w >> 16) & 255u; bytes[3] = w >> 24;
+		} else {
+			for (uint32_t b = 0; b < nb; ++b) bytes[b] = pac[g * 4 + b];
+		}
+		uint32_t w[4];
+		#pragma unroll
+		for (int b = 0; b < 4; ++b) {
+			uint32_t const x = bytes[b];
+			w[b] = ((x >> 6) & 3u) | (((x >> 4) & 3u) << 8) | (((x >> 2) & 3u) << 16) | ((x & 3u) << 24);
+		}
+		if (cnt == 16) {
+			*reinterpret_cast<uint4 *>(out + first) = make_uint4(w[0], w[1], w[2], w[3]);
+			#pragma unroll
+			for (int b = 0; b < 4; ++b) {
+				// count codes 1,2,3 via bit tricks on the four bytes; code 0 = 4 - others
+				uint32_t const lo = w[b] & 0x01010101u, hi = (w[b] >> 1) & 0x01010101u;
+				uint32_t const n3 = __popc(lo & hi), n1 = __popc(lo & ~hi), n2 = __popc(hi & ~lo);
+				c1 += n1; c2 += n2; c3 += n3; c0 += 4 - n1 - n2 - n3;
+			}
+		} else {
+			for (uint32_t k = 0; k < cnt; ++k) {
+				uint32_t const c = (w[k >> 2] >> (8 * (k & 3))) & 3u;
+				out[first + k] = (uint8_t)c;
+				c0 += (c == 0); c1 += (c == 1); c2 += (c == 2); c3 += (c == 3);
+			}
+		}
+	}
+	c0 = __reduce_add_sync(0xffffffffu, c0); c1 = __reduce_add_sync(0xffffffffu, c1);
+	c2 = __reduce_add_sync(0xffffffffu, c2); c3 = __reduce_add_sync(0xffffffffu, c3);
+	if ((threadIdx.x & 31) == 0) { atomicAdd(&sh[0], c0); atomicAdd(&sh[1], c1); atomicAdd(&sh[2], c2); atomicAdd(&sh[3], c3); }
+	__syncthreads();
+	if (threadIdx.x < 4 && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}
+
+void k1_unpack_pac(Stream & st, const uint8_t * d_pac, uint64_t l, uint8_t * d_out, uint64_t * d_hist256) {
+	B3M_CUDA(cudaMemsetAsync(d_hist256, 0, 256 * sizeof(uint64_t), st.s));
+	if (!l) return;
+	uint64_t want = div_up(div_up(l, 16), 256 * 8);
+	unsigned grid = (unsigned)(want < (uint64_t)st.sms * 16 ? (want ? want : 1) : (uint64_t)st.sms * 16);
+	B3M_LAUNCH(st, k_unpack_pac, grid, 256, 0, d_pac, l, d_out, (unsigned long long *)d_hist256);
+}
+
+// compactstream payload: b-bit symbols, MSB first, in a big-endian bit stream [layout unpinned,
+// SURVEY 8c]; one thread per symbol (b <= 8).
+__global__ void __launch_bounds__(256) k_unpack_compact(const uint8_t * __restrict__ d, uint64_t n, unsigned b, uint8_t * __restrict__ out,
+                                                        unsigned long long * __restrict__ hist) {
+	__shared__ uint32_t sh[256];
+	sh[threadIdx.x] = 0;
+	__syncthreads();
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+		uint64_t const bit = i * b;
+		uint64_t const byte = bit >> 3;
+		uint32_t const two = ((uint32_t)d[byte] << 8) | (uint32_t)d[byte + 1]; // one pad byte is guaranteed by the loader
+		uint32_t const v = (two >> (16 - (bit & 7) - b)) & ((1u << b) - 1u);
+		out[i] = (uint8_t)v;
+		atomicAdd(&sh[v], 1u);
+	}
+	__syncthreads();
+	if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}
+
+void k1_unpack_compact(Stream & st, const uint8_t * d_words, uint64_t n, unsigned b, uint8_t * d_out, uint64_t * d_hist256) {
+	B3M_CUDA(cudaMemsetAsync(d_hist256, 0, 256 * sizeof(uint64_t), st.s));
+	if (!n) return;
+	uint64_t want = div_up(n, 256 * 16);
+	unsigned grid = (unsigned)(want < (uint64_t)st.sms * 16 ? (want ? want : 1) : (uint64_t)st.sms * 16);
+	B3M_LAUNCH(st, k_unpack_compact, grid, 256, 0, d_words, n, b, d_out, (unsigned long long *)d_hist256);
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: L[k] = T[(SA[k]-1) mod n]   (/root/reference/src/lcpbit.cpp:3668-3669)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_extract_bwt(const uint8_t * __restrict__ codes, uint64_t ntext, int has_term, uint64_t wstart, int text_wraps,
+              const uint32_t * __restrict__ sa, uint64_t m, uint8_t * __restrict__ bwt, uint64_t shift, uint32_t * __restrict__ special) {
+	uint64_t const k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= m) return;
+	uint32_t const i = sa[k];
+	uint64_t p = wstart + i;
+	if (text_wraps && p >= ntext) p -= ntext;
+	uint8_t c;
+	if (p == 0) {
+		if (has_term) { c = 0; special[0] = (uint32_t)(k + shift); } // predecessor is the terminator
+		else c = codes[ntext - 1];
+	} else c = codes[p - 1];
+	if (i == 0) special[1] = (uint32_t)(k + shift);                   // rank of the block-start suffix
+	bwt[k + shift] = c;
+}
+
+void k3_extract_bwt(Stream & st, DevText const & T, uint64_t wstart, const uint32_t * sa, uint64_t m,
+                    uint8_t * bwt, uint64_t shift, uint32_t * d_special) {
+	if (!m) return;
+	B3M_LAUNCH(st, k_extract_bwt, (unsigned)div_up(m, 256), 256, 0, T.codes, T.ntext, T.has_term, wstart,
+	           T.has_term ? 0 : 1, sa, m, bwt, shift, d_special);
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: dictionary build
+// ------------------------------------------------------------------------------------------
+size_t dict_bytes(int flavour, uint64_t n, uint32_t sigma) {
+	if (flavour == 2) return (size_t)(n / D2_SYMS + 1) * 64;
+	return (size_t)(n / D8_SYMS + 1) * (4u * d8_spad(sigma) + D8_SYMS);
+}
+
+// one thread packs one 64-byte line and leaves the line's own symbol counts in the counter slot
+__global__ void __launch_bounds__(128) k_dict2_pack(const uint8_t * __restrict__ bwt, uint64_t n, uint4 * __restrict__ lines, uint64_t nlines) {
+	uint64_t const line = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (line >= nlines) return;
+	uint64_t const first = line * D2_SYMS;
+	uint64_t w[6] = {0, 0, 0, 0, 0, 0};
+	uint32_t cnt[4] = {0, 0, 0, 0};
+	uint32_t const have = first >= n ? 0u : ((n - first) < D2_SYMS ? (uint32_t)(n - first) : D2_SYMS);
+	if (have == D2_SYMS) {
+		const uint4 * src = reinterpret_cast<const uint4 *>(bwt + first); // 192*line is 16-byte aligned
+		#pragma unroll
+		for (int q = 0; q < 12; ++q) {
+			uint4 const v = __ldg(src + q);
+			uint32_t const x[4] = {v.x, v.y, v.z, v.w};
+			uint64_t acc = 0;
+			#pragma unroll
+			for (int k = 0; k < 4; ++k) {
+				uint32_t const y = x[k] & 0x03030303u;
+				// gather the four 2-bit codes of this word into 8 contiguous bits
+				uint32_t const z = (y | (y >> 6) | (y >> 12) | (y >> 18)) & 0xffu;
+				acc |= (uint64_t)z << (8 * k);
+			}
+			w[q >> 1] |= acc << (32 * (q & 1));
+		}
+	} else {
+		for (uint32_t j = 0; j < have; ++j) w[j >> 5] |= (uint64_t)(bwt[first + j] & 3u) << (2 * (j & 31));
+	}
+	#pragma unroll
+	for (int k = 0; k < 6; ++k) {
+		uint32_t const valid = have > 32u * k ? ((have - 32u * k) < 32u ? have - 32u * k : 32u) : 0u;
+		uint64_t const pm = valid >= 32u ? ~0ull : ((1ull << (2 * valid)) - 1ull);
+		#pragma unroll
+		for (uint32_t c = 0; c < 4; ++c) cnt[c] += popc_code2(w[k], c, pm);
+	}
+	uint4 * lp = lines + line * 4;
+	lp[0] = make_uint4(cnt[0], cnt[1], cnt[2], cnt[3]);
+	lp[1] = make_uint4((uint32_t)w[0], (uint32_t)(w[0] >> 32), (uint32_t)w[1], (uint32_t)(w[1] >> 32));
+	lp[2] = make_uint4((uint32_t)w[2], (uint32_t)(w[2] >> 32), (uint32_t)w[3], (uint32_t)(w[3] >> 32));
+	lp[3] = make_uint4((uint32_t)w[4], (uint32_t)(w[4] >> 32), (uint32_t)w[5], (uint32_t)(w[5] >> 32));
+}
+
+// flavour 8: one warp per 128-symbol block: local counts by warp match, symbols copied
+__global__ void __launch_bounds__(256) k_dict8_pack(const uint8_t * __restrict__ bwt, uint64_t n, uint8_t * __restrict__ base,
+                                                    uint32_t stride, uint32_t spad, uint64_t nblocks) {
+	__shared__ uint32_t cnt[8][256];
+	unsigned const w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	uint64_t const blk = (uint64_t)blockIdx.x * 8 + w;
+	if (blk >= nblocks) return; // whole warp leaves together
+	for (uint32_t c = lane; c < 256; c += 32) cnt[w][c] = 0;
+	__syncwarp();
+	uint64_t const first = blk * D8_SYMS + 4ull * lane;
+	uint32_t word = 0;
+	uint32_t nb = 0;
+	if (first < n) {
+		nb = (n - first) < 4 ? (uint32_t)(n - first) : 4u;
+		if (nb == 4) word = *reinterpret_cast<const uint32_t *>(bwt + first);
+		else for (uint32_t k = 0; k < nb; ++k) word |= (uint32_t)bwt[first + k] << (8 * k);
+	}
+	#pragma unroll
+	for (uint32_t k = 0; k < 4; ++k) {
+		bool const valid = k < nb;
+		uint32_t const c = (word >> (8 * k)) & 255u;
+		unsigned const peers = __match_any_sync(0xffffffffu, valid ? c : 0xffffffffu);
+		if (valid && (peers & lanemask_lt()) == 0) cnt[w][c] += __popc(peers);
+		__syncwarp();
+	}
+	uint8_t * bp = base + blk * stride;
+	for (uint32_t c = lane; c < spad; c += 32) reinterpret_cast<uint32_t *>(bp)[c] = cnt[w][c];
+	reinterpret_cast<uint32_t *>(bp + 4u * spad)[lane] = word;
+}
+
+constexpr uint32_t D8_CHUNK = 256; // blocks per chunk in the column scans
+__global__ void __launch_bounds__(256) k_dict8_chunksum(const uint8_t * __restrict__ base, uint32_t stride, uint32_t spad, uint64_t nblocks,
+                                                        uint32_t * __restrict__ chunktot) {
+	uint32_t const c = threadIdx.x;
+	if (c >= spad) return;
+	uint64_t const b0 = (uint64_t)blockIdx.x * D8_CHUNK;
+	uint64_t const b1 = b0 + D8_CHUNK < nblocks ? b0 + D8_CHUNK : nblocks;
+	uint32_t s = 0;
+	for (uint64_t b = b0; b < b1; ++b) s += reinterpret_cast<const uint32_t *>(base + b * stride)[c];
+	chunktot[(uint64_t)blockIdx.x * spad + c] = s;
+}
+__global__ void __launch_bounds__(256) k_dict8_chunkscan(uint32_t * __restrict__ chunktot, uint32_t spad, uint64_t nchunks) {
+	uint32_t const c = threadIdx.x;
+	if (c >= spad) return;
+	uint32_t run = 0;
+	for (uint64_t k = 0; k < nchunks; ++k) { uint32_t const t = chunktot[k * spad + c]; chunktot[k * spad + c] = run; run += t; }
+}
+__global__ void __launch_bounds__(256) k_dict8_apply(uint8_t * __restrict__ base, uint32_t stride, uint32_t spad, uint64_t nblocks,
+                                                     const uint32_t * __restrict__ chunktot) {
+	uint32_t const c = threadIdx.x;
+	if (c >= spad) return;
+	uint64_t const b0 = (uint64_t)blockIdx.x * D8_CHUNK;
+	uint64_t const b1 = b0 + D8_CHUNK < nblocks ? b0 + D8_CHUNK : nblocks;
+	uint32_t run = chunktot[(uint64_t)blockIdx.x * spad + c];
+	for (uint64_t b = b0; b < b1; ++b) {
+		uint32_t * p = reinterpret_cast<uint32_t *>(base + b * stride) + c;
+		uint32_t const t = *p; *p = run; run += t;
+	}
+}
+
+void k4_build_dict(Stream & st, const uint8_t * bwt, uint64_t n, int flavour, uint32_t sigma, void * lines) {
+	if (flavour == 2) {
+		uint64_t const nlines = n / D2_SYMS + 1;
+		uint4 * L = reinterpret_cast<uint4 *>(lines);
+		B3M_LAUNCH(st, k_dict2_pack, (unsigned)div_up(nlines, 128), 128, 0, bwt, n, L, nlines);
+		scan_apply<OpSum4>(st, nlines,
+			[=] __device__(uint64_t i) -> uint4 { return L[i * 4]; },
+			[=] __device__(uint64_t i, uint4 excl, uint4) { L[i * 4] = excl; });
+		return;
+	}
+	uint32_t const spad = d8_spad(sigma);
+	uint32_t const stride = 4u * spad + D8_SYMS;
+	uint64_t const nblocks = n / D8_SYMS + 1;
+	uint8_t * base = reinterpret_cast<uint8_t *>(lines);
+	B3M_LAUNCH(st, k_dict8_pack, (unsigned)div_up(nblocks, 8), 256, 0, bwt, n, base, stride, spad, nblocks);
+	uint64_t const nchunks = div_up(nblocks, D8_CHUNK);
+	DevBuf<uint32_t> chunktot(st, nchunks * spad);
+	B3M_LAUNCH(st, k_dict8_chunksum, (unsigned)nchunks, 256, 0, (const uint8_t *)base, stride, spad, nblocks, chunktot.get());
+	B3M_LAUNCH(st, k_dict8_chunkscan, 1, 256, 0, chunktot.get(), spad, nchunks);
+	B3M_LAUNCH(st, k_dict8_apply, (unsigned)nchunks, 256, 0, base, stride, spad, nblocks, (const uint32_t *)chunktot.get());
+}
+
+// ------------------------------------------------------------------------------------------
+// K7: sampled SA / ISA by LF walk from the anchors; one chain per thread
+// (in-repo twin of the reference loop: /root/reference/src/hwtPreIsaToIsa.cpp:114-161;
+//  `curpos=(curpos+n-1)%n; currank=LF(currank)`, `ISA[curpos/rate]=currank`).
+// SA is sampled by rank, ISA by position.
+// ------------------------------------------------------------------------------------------
+struct CTable { uint32_t c[257]; };
+
+__device__ __forceinline__ uint32_t lf_step(DictView const & D, CTable const & C, uint32_t exc_lf, uint32_t r) {
+	if (r == D.exc_pos) return exc_lf;
+	if (D.flavour == 2) { uint32_t s; return dict_lf2(D, C.c, r, &s); }
+	uint32_t const s = dict_symbol(D, r);
+	return C.c[s] + dict_rank(D, s, r);
+}
+
+__global__ void __launch_bounds__(256)
+k_walk(DictView D, CTable C, uint32_t exc_lf, const uint32_t * __restrict__ anchor_rank, uint64_t nanchors, uint64_t arate, uint64_t n,
+       uint32_t samask, uint32_t sashift, uint32_t isamask, uint32_t isashift,
+       unsigned long long * __restrict__ sa_out, unsigned long long * __restrict__ isa_out) {
+	uint64_t const q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= nanchors) return;
+	uint32_t r = anchor_rank[q];
+	uint64_t p = q * arate;
+	uint64_t steps = q ? arate : n - (nanchors - 1) * arate;
+	while (steps--) {
+		if ((p & isamask) == 0) isa_out[p >> isashift] = r;
+		if ((r & samask) == 0) sa_out[r >> sashift] = p;
+		p = p ? p - 1 : n - 1;
+		r = lf_step(D, C, exc_lf, r);
+	}
+}
+
+__global__ void __launch_bounds__(256)
+k_lfbench(DictView D, CTable C, uint32_t exc_lf, const uint32_t * __restrict__ start, uint64_t nchains, uint64_t steps, uint32_t * __restrict__ out) {
+	uint64_t const q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= nchains) return;
+	uint32_t r = start[q];
+	for (uint64_t s = 0; s < steps; ++s) r = lf_step(D, C, exc_lf, r);
+	out[q] = r;
+}
+
+static DictView make_view(DevDict const & D) {
+	DictView v;
+	v.base = reinterpret_cast<const uint8_t *>(D.lines);
+	v.flavour = (uint32_t)D.flavour;
+	v.spad = d8_spad(D.sigma);
+	v.stride = D.flavour == 2 ? 64u : 4u * v.spad + D8_SYMS;
+	v.exc_pos = D.exc_pos;
+	v.exc_code = D.exc_code;
+	return v;
+}
+
+static unsigned ilog2_exact(uint64_t v) {
+	B3M_REQUIRE(v && !(v & (v - 1)), "sampling rates must be powers of two"); // hwtPreIsaToIsa.cpp:90-97
+	unsigned s = 0;
+	while ((1ull << s) < v) ++s;
+	return s;
+}
+
+void k7_walk(Stream & st, DevDict const & D, const uint32_t * anchor_rank, uint64_t nanchors, uint64_t arate,
+             uint64_t n, uint64_t sarate, uint64_t isarate, uint64_t * sa_out, uint64_t * isa_out, WalkStats * ws) {
+	if (!nanchors) return;
+	CTable C;
+	for (int i = 0; i < 257; ++i) C.c[i] = D.C[i];
+	B3M_LAUNCH(st, k_walk, (unsigned)div_up(nanchors, 256), 256, 0, make_view(D), C, D.exc_lf, anchor_rank, nanchors, arate, n,
+	           (uint32_t)(sarate - 1), ilog2_exact(sarate), (uint32_t)(isarate - 1), ilog2_exact(isarate),
+	           (unsigned long long *)sa_out, (unsigned long long *)isa_out);
+	if (ws) { ws->steps += n; ws->chains += nanchors; }
+}
+
+void k7_lfbench(Stream & st, DevDict const & D, const uint32_t * start_rank, uint64_t nchains, uint64_t steps, uint32_t * out_rank) {
+	if (!nchains) return;
+	CTable C;
+	for (int i = 0; i < 257; ++i) C.c[i] = D.C[i];
+	B3M_LAUNCH(st, k_lfbench, (unsigned)div_up(nchains, 256), 256, 0, make_view(D), C, D.exc_lf, start_rank, nchains, steps, out_rank);
+}
+
+} // namespace b3m

@@ -1,0 +1,99 @@
+"""Host-side mirror of the engine-level C ABI (include/b3m.h): one Engine per GPU."""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import INPUT_TYPES, BuildParams, Info, lib
+
+
+class B3MError(RuntimeError):
+    pass
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class Engine:
+    """Drives K1..K7 on one GPU through libb3m.so.  Mirrors the argument meaning of the
+    reference's BwtMergeSortOptions (/root/reference/src/bwtb3m.cpp:43-56)."""
+
+    def __init__(self, device=0, stream=None):
+        self._lib = lib()
+        h = C.c_void_p()
+        err = C.create_string_buffer(1024)
+        rc = self._lib.b3m_engine_create(device, C.c_void_p(stream) if stream else None, C.byref(h), err, 1024)
+        if rc != 0:
+            raise B3MError(err.value.decode() or "b3m_engine_create failed (%d)" % rc)
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.b3m_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise B3MError(self._lib.b3m_engine_last_error(self._h).decode())
+
+    def load_host(self, data, inputtype="bytestream"):
+        """data: bytes-like or uint8 numpy array holding the input FILE contents."""
+        a = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, dtype=np.uint8)
+        self._keep = a
+        self._check(self._lib.b3m_engine_load_host(self._h, C.c_void_p(a.ctypes.data), a.size, INPUT_TYPES[inputtype]))
+
+    def load_host_ptr(self, ptr, nbytes, inputtype="bytestream"):
+        self._check(self._lib.b3m_engine_load_host(self._h, C.c_void_p(ptr), nbytes, INPUT_TYPES[inputtype]))
+
+    def load_device(self, dptr, nbytes, inputtype="bytestream"):
+        self._check(self._lib.b3m_engine_load_device(self._h, C.c_void_p(dptr), nbytes, INPUT_TYPES[inputtype]))
+
+    def build(self, numblocks=1, preisarate=0, sasamplingrate=32, isasamplingrate=262144, bwtonly=False,
+              largelcpthres=16384):
+        p = BuildParams(numblocks, preisarate, sasamplingrate, isasamplingrate, 1 if bwtonly else 0, largelcpthres)
+        self._check(self._lib.b3m_engine_build(self._h, C.byref(p)))
+
+    def info(self):
+        i = Info()
+        self._check(self._lib.b3m_engine_info(self._h, C.byref(i)))
+        d = {k: getattr(i, k) for k, _ in Info._fields_ if k != "hist"}
+        d["hist"] = {s: int(c) for s, c in enumerate(i.hist) if c}
+        return d
+
+    def fetch(self, bwt=True, preisa=True, sa=True, isa=True, out=None):
+        """Returns dict with numpy arrays; `out` may hold preallocated (e.g. pinned) arrays."""
+        i = self.info()
+        out = dict(out or {})
+        res = {}
+        if bwt:
+            res["bwt"] = out.get("bwt") if out.get("bwt") is not None else np.empty(i["n"], dtype=np.uint8)
+        if preisa:
+            res["preisa"] = out.get("preisa") if out.get("preisa") is not None else np.empty((i["npreisa"], 2), dtype=np.uint64)
+        if sa and i["nsa"]:
+            res["sa"] = out.get("sa") if out.get("sa") is not None else np.empty(i["nsa"], dtype=np.uint64)
+        if isa and i["nisa"]:
+            res["isa"] = out.get("isa") if out.get("isa") is not None else np.empty(i["nisa"], dtype=np.uint64)
+        self._check(self._lib.b3m_engine_fetch(self._h, _ptr(res.get("bwt")), _ptr(res.get("preisa")), _ptr(res.get("sa")),
+                                               _ptr(res.get("isa"))))
+        return res
+
+    def fetch_ptrs(self, bwt_ptr, preisa_ptr, sa_ptr, isa_ptr):
+        self._check(self._lib.b3m_engine_fetch(self._h, C.c_void_p(bwt_ptr) if bwt_ptr else None,
+                                               C.c_void_p(preisa_ptr) if preisa_ptr else None,
+                                               C.c_void_p(sa_ptr) if sa_ptr else None,
+                                               C.c_void_p(isa_ptr) if isa_ptr else None))
+
+    def lf_bench(self, nchains, steps):
+        ms = C.c_float(0)
+        cs = C.c_uint64(0)
+        self._check(self._lib.b3m_engine_lf_bench(self._h, nchains, steps, C.byref(ms), C.byref(cs)))
+        return float(ms.value), int(cs.value)
+
+    def sync(self):
+        self._check(self._lib.b3m_engine_sync(self._h))

@@ -1,0 +1,166 @@
+/*
+ * b3m.h -- C ABI of the B200-native BWT-by-balanced-block-merging engine (libb3m.so).
+ *
+ * This is the drop-in boundary for the hot path of gt1/bwtb3m.  The reference has no FFI layer:
+ * its seam is one C++ static call into libmaus2,
+ *     libmaus2::suffixsort::bwtb3m::BwtMergeSort::computeBwt(options,&std::cerr)
+ *         (/root/reference/src/bwtb3m.cpp:62-63)
+ * plus the process-level contract (key=value command line, output files).  Every entry point
+ * below names the reference interface it replaces.  Plain C types only: pointers, sizes, fixed
+ * width integers.  No exception crosses this boundary; every call returns 0 on success and a
+ * non-zero code on failure with a message in the caller's buffer (file-level calls) or in
+ * b3m_engine_last_error() (engine calls).  There is no CPU fallback: without a CUDA device the
+ * calls fail.
+ */
+#ifndef B3M_H
+#define B3M_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* input types kept from the reference's option `inputtype`
+ * (/root/reference/src/bwtb3m.cpp:43; BwtMergeSortOptions::parseInputType,
+ *  /root/reference/src/checkbwt.cpp:254-270); lz4 and utf-8 are out of scope. */
+#define B3M_INPUT_BYTESTREAM 0
+#define B3M_INPUT_COMPACTSTREAM 1
+#define B3M_INPUT_PAC 2
+#define B3M_INPUT_PACTERM 3
+
+const char * b3m_version(void);
+
+/* returns B3M_INPUT_* or -1 (replaces BwtMergeSortOptions::parseInputType) */
+int b3m_parse_inputtype(const char * name);
+
+/* ------------------------------------------------------------------------------------------
+ * File level: the reference's three library calls on this path.
+ * ---------------------------------------------------------------------------------------- */
+
+/* Mirrors libmaus2::suffixsort::bwtb3m::BwtMergeSortOptions as constructed from the command
+ * line (/root/reference/src/bwtb3m.cpp:43-56,62): same names, meaning and defaults. */
+typedef struct b3m_options {
+	const char * fn;              /* input file (positional argument 0) */
+	const char * inputtype;       /* "bytestream" (default) | "compactstream" | "pac" | "pacterm" */
+	const char * outputfilename;  /* default: tmpprefix + ".bwt" */
+	uint64_t sasamplingrate;      /* default 32 */
+	uint64_t isasamplingrate;     /* default 262144 */
+	uint64_t mem;                 /* memory target, default 2 GiB; bounds the block size */
+	uint64_t numthreads;          /* host threads (file encoding); default: logical CPUs */
+	int bwtonly;                  /* 1: only .bwt + .preisa (+.preisa.meta) */
+	const char * tmpprefix;       /* prefix for temporary files */
+	const char * sparsetmpprefix; /* accepted for compatibility (gap arrays live in HBM) */
+	int copyinputtomemory;        /* accepted for compatibility (input is always staged in HBM) */
+	uint64_t largelcpthres;       /* default 16384 */
+	int verbose;
+	/* additions of this implementation */
+	int device;                   /* CUDA device ordinal, default 0 */
+	uint64_t numblocks;           /* 0: derive from mem (one block if it fits); >0: force */
+} b3m_options;
+
+/* Mirrors libmaus2::suffixsort::bwtb3m::BwtMergeSortResult
+ * (/root/reference/src/checkbwt.cpp:39-53): the names of the files written. */
+typedef struct b3m_result {
+	char textfn[1024];
+	char bwtfn[1024];
+	char histfn[1024];
+	char preisafn[1024];
+	char metafn[1024];
+	char safn[1024];   /* empty when bwtonly */
+	char isafn[1024];  /* empty when bwtonly */
+	uint64_t n;        /* BWT length (pacterm: bases + 1) */
+	uint64_t numblocks;
+	double seconds_total;
+	double seconds_device;
+} b3m_result;
+
+void b3m_options_init(b3m_options * o);
+
+/* replaces BwtMergeSort::computeBwt(options, logstr)  (/root/reference/src/bwtb3m.cpp:63) */
+int b3m_compute_bwt(const b3m_options * o, b3m_result * res, char * err, size_t errlen);
+
+/* replaces BwtComputeSSA::computeSSA(bwt,sasamplingrate,isasamplingrate,tmpfilenamebase,
+ * copyinputtomemory,numthreads,maxsortmem,maxtmpfiles,logstr,ref_isa_fn,ref_sa_fn)
+ * (/root/reference/src/bwtcomputessa.cpp:39-51): .bwt + .preisa -> .sa + .isa */
+int b3m_compute_ssa(const char * bwtfn, uint64_t sasamplingrate, uint64_t isasamplingrate,
+                    const char * tmpprefix, int copyinputtomemory, uint64_t numthreads,
+                    uint64_t maxsortmem, uint64_t maxtmpfiles, int verbose,
+                    const char * ref_isa_fn, const char * ref_sa_fn, int device,
+                    char * err, size_t errlen);
+
+/* replaces libmaus2::fm::MausFmToBwaConversion::rewrite(in,outbwt,outsa,numthreads)
+ * (/root/reference/src/bwtb3mtobwa.cpp:29) */
+int b3m_to_bwa(const char * inbwt, const char * outbwt, const char * outsa, char * err, size_t errlen);
+
+/* ------------------------------------------------------------------------------------------
+ * Engine level: the same path on caller-owned host or device buffers.  One engine per GPU and
+ * per host thread; the engine owns its device memory and enqueues everything on one stream.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct b3m_engine b3m_engine;
+
+/* cuda_stream: a cudaStream_t to enqueue on, or NULL for an engine-owned stream */
+int b3m_engine_create(int device, void * cuda_stream, b3m_engine ** out, char * err, size_t errlen);
+void b3m_engine_destroy(b3m_engine * e);
+const char * b3m_engine_last_error(const b3m_engine * e);
+
+/* K1: stage + decode the input (the bytes of the input file) and build the symbol histogram.
+ * Replaces the {Byte,Compact,Pac,PacTerm}InputTypes readers (/root/reference/src/checkbwt.cpp:260-266). */
+int b3m_engine_load_host(b3m_engine * e, const void * input, uint64_t nbytes, int inputtype);
+int b3m_engine_load_device(b3m_engine * e, const void * d_input, uint64_t nbytes, int inputtype);
+
+typedef struct b3m_build_params {
+	uint64_t numblocks;        /* >= 1 */
+	uint64_t preisarate;       /* spacing of the (rank,pos) anchors, power of two; 0: choose */
+	uint64_t sasamplingrate;   /* power of two */
+	uint64_t isasamplingrate;  /* power of two */
+	int bwtonly;
+	uint64_t largelcpthres;
+} b3m_build_params;
+
+/* K2..K7: block sort -> gap arrays -> merge -> final BWT, anchors, sampled SA/ISA; results stay
+ * in HBM until fetched.  Replaces BwtMergeSortTemplate<InputTypes>::computeBwt. */
+int b3m_engine_build(b3m_engine * e, const b3m_build_params * p);
+
+typedef struct b3m_info {
+	uint64_t n;            /* BWT length */
+	uint64_t sigma;        /* distinct symbols (terminator included) */
+	uint64_t numblocks;
+	uint64_t preisarate, npreisa;
+	uint64_t sasamplingrate, nsa;
+	uint64_t isasamplingrate, nisa;
+	uint64_t hist[256];    /* symbol -> count, reference symbol space */
+	/* counters the roofline report is computed from */
+	uint64_t sort_rounds, radix_passes, radix_bytes, sort_active_sum, sort_other_bytes;
+	uint64_t gap_lf_steps, walk_lf_steps, walk_chains, gap_chains;
+	uint64_t merge_bytes, extract_bytes, dict_bytes, decode_bytes;
+	uint64_t launches;     /* kernels launched since the engine was created */
+	uint64_t max_lcpnext;
+	/* device time per phase of the last build, milliseconds (CUDA events on the engine stream) */
+	float ms_decode, ms_sort, ms_extract, ms_dict, ms_gap, ms_merge, ms_walk, ms_total;
+} b3m_info;
+int b3m_engine_info(b3m_engine * e, b3m_info * info);
+
+/* D2H of the results; any pointer may be NULL.  bwt: n symbols in the reference's symbol space;
+ * preisa_pairs: 2*npreisa uint64 (rank,pos); sa: nsa uint64 (SA[k*sasamplingrate]);
+ * isa: nisa uint64 (ISA[k*isasamplingrate]). */
+int b3m_engine_fetch(b3m_engine * e, uint8_t * bwt, uint64_t * preisa_pairs, uint64_t * sa, uint64_t * isa);
+
+/* device pointers of the results (valid until the next load/build): bwt codes are dense ranks,
+ * see b3m_engine_info; for the multi-GPU orchestration and device-resident benchmarks. */
+int b3m_engine_device_results(b3m_engine * e, const void ** d_bwt_codes, const void ** d_preisa_rank,
+                              const void ** d_sa, const void ** d_isa);
+
+/* LF-steps/s instrument on the dictionary of the last build: nchains dependent LF chains of
+ * `steps` steps each, started at evenly spaced sampled ranks; returns elapsed device ms.
+ * Restates /root/reference/src/bwttestdecodespeed.cpp:82-96 for thousands of chains. */
+int b3m_engine_lf_bench(b3m_engine * e, uint64_t nchains, uint64_t steps, float * ms, uint64_t * checksum);
+
+/* wait for the engine's stream */
+int b3m_engine_sync(b3m_engine * e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,116 @@
+"""GPU parity, single block: the CUDA path (through the C ABI, host buffers) against the CPU
+oracle on the same seeded inputs; bit-exact BWT, anchors, sampled SA and ISA."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+KATS = [
+    (b"abbab#", b"bb#aba", [2, 5, 4, 1, 3, 0]),
+    (b"banana", b"nnbaaa", [3, 2, 5, 1, 4, 0]),
+    (b"mississippi", b"pssmipissii", [4, 3, 10, 8, 2, 9, 7, 1, 6, 5, 0]),
+    (b"ACGTACGTTGCA", b"CATGAATCCGTG", [1, 4, 7, 9, 2, 5, 8, 11, 10, 6, 3, 0]),
+]
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from bwtb3m_b200 import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def run(eng, data, inputtype, **kw):
+    eng.load_host(data, inputtype)
+    eng.build(**kw)
+    return eng.fetch(), eng.info()
+
+
+@pytest.mark.parametrize("text,bwt,isa", KATS)
+def test_kat_bytestream(eng, text, bwt, isa):
+    res, info = run(eng, text, "bytestream", preisarate=1, sasamplingrate=1, isasamplingrate=1)
+    assert res["bwt"].tobytes() == bwt
+    assert res["preisa"][:, 0].tolist() == isa
+    assert res["isa"].tolist() == isa
+    sa = [0] * len(isa)
+    for p, r in enumerate(isa):
+        sa[r] = p
+    assert res["sa"].tolist() == sa
+
+
+def test_kat_pacterm(eng):
+    res, info = run(eng, bytes([0x1B, 0xE4, 0x00, 0x00]), "pacterm", preisarate=1, sasamplingrate=1, isasamplingrate=1)
+    assert info["n"] == 9
+    assert res["bwt"].tolist() == [1, 2, 0, 3, 1, 4, 2, 4, 3]
+    assert res["sa"].tolist() == [8, 7, 0, 6, 1, 5, 2, 4, 3]
+    assert res["isa"][0] == 2
+    assert info["hist"] == {0: 1, 1: 2, 2: 2, 3: 2, 4: 2}
+
+
+@pytest.mark.parametrize("seed,n,sigma", [(1, 1000, 4), (2, 70001, 4), (3, 30000, 256), (4, 5000, 2), (5, 20000, 20),
+                                          (6, 300000, 4), (7, 1, 4), (8, 2, 4), (9, 17, 3)])
+def test_random_bytestream_vs_oracle(eng, oracle, seed, n, sigma):
+    rng = np.random.default_rng(seed)
+    t = rng.integers(0, sigma, size=n, dtype=np.uint8)
+    if n == 2:
+        t[:] = [1, 0]
+    sa = oracle.sa_circular(t)
+    bwt, isa = oracle.bwt_from_sa(t, sa)
+    res, info = run(eng, t, "bytestream", preisarate=64, sasamplingrate=32, isasamplingrate=128)
+    assert np.array_equal(res["bwt"], bwt)
+    assert np.array_equal(res["preisa"][:, 0], isa[::64].astype(np.uint64))
+    assert np.array_equal(res["preisa"][:, 1], np.arange(0, n, 64, dtype=np.uint64))
+    assert np.array_equal(res["sa"], sa[::32].astype(np.uint64))
+    assert np.array_equal(res["isa"], isa[::128].astype(np.uint64))
+
+
+@pytest.mark.parametrize("seed,l", [(11, 8), (12, 1001), (13, 65536), (14, 250003), (15, 3), (16, 16), (17, 15)])
+@pytest.mark.parametrize("itype", ["pac", "pacterm"])
+def test_random_pac_vs_oracle(eng, oracle, seed, l, itype):
+    rng = np.random.default_rng(seed)
+    bases = rng.integers(0, 4, size=l, dtype=np.uint8)
+    if itype == "pac" and l == 16:
+        bases[0] = (bases[1] + 1) % 4  # keep the text primitive
+    pac = oracle.encode_pac(bases)
+    t = oracle.decode_pac(pac.tobytes(), term=(itype == "pacterm"))
+    n = t.size
+    sa = oracle.sa_circular(t)
+    bwt, isa = oracle.bwt_from_sa(t, sa)
+    res, info = run(eng, pac, itype, preisarate=16, sasamplingrate=4, isasamplingrate=8)
+    assert info["n"] == n
+    assert np.array_equal(res["bwt"], bwt)
+    assert np.array_equal(res["preisa"][:, 0], isa[::16].astype(np.uint64))
+    assert np.array_equal(res["sa"], sa[::4].astype(np.uint64))
+    assert np.array_equal(res["isa"], isa[::8].astype(np.uint64))
+
+
+def test_repetitive_many_rounds(eng, oracle):
+    """Mutated copies: LCPs in the hundreds force many prefix-doubling rounds."""
+    rng = np.random.default_rng(21)
+    base = rng.integers(0, 4, size=3000, dtype=np.uint8)
+    parts = []
+    for c in range(8):
+        x = base.copy()
+        pos = rng.integers(0, x.size, size=3)
+        x[pos] = (x[pos] + 1) % 4
+        parts.append(x)
+    t = np.concatenate(parts)
+    sa = oracle.sa_circular(t)
+    bwt, isa = oracle.bwt_from_sa(t, sa)
+    res, info = run(eng, t, "bytestream", preisarate=64, sasamplingrate=32, isasamplingrate=64)
+    assert info["sort_rounds"] >= 6
+    assert np.array_equal(res["bwt"], bwt)
+    assert np.array_equal(res["sa"], sa[::32].astype(np.uint64))
+    assert np.array_equal(res["isa"], isa[::64].astype(np.uint64))
+
+
+def test_checkbwt_property_8mbp(eng, oracle):
+    """BASELINE config 1 size (8 Mbp ACGT bytestream, bwtonly=1): the restated checkbwt verifier
+    (LF-walk against the circularly reversed text) accepts the GPU BWT + anchors."""
+    rng = np.random.default_rng(1)
+    t = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=8_000_000)]
+    res, info = run(eng, t, "bytestream", bwtonly=True)
+    assert info["preisarate"] == 64 and info["nsa"] == 0
+    rc, checked = oracle.checkbwt(t, res["bwt"], res["preisa"], numthreads=8)
+    assert rc == 1 and checked == t.size
