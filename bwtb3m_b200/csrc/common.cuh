@@ -6,6 +6,8 @@
 #include <string>
 #include <stdexcept>
 #include <vector>
+#include <map>
+#include <iterator>
 
 namespace b3m {
 
@@ -26,11 +28,81 @@ struct Error : std::runtime_error {
 		if (!(cond)) throw ::b3m::Error(std::string(msg) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
 	} while (0)
 
-// Per-engine launch context: the stream every kernel goes to, and counters the bench reports.
+// Device memory arena: a few large cudaMalloc slabs carved by a host-side first-fit free list.
+// Every user of the arena enqueues on the engine's single stream, so a block may be handed out
+// again as soon as it is freed (stream order protects it).  Measured reason: cudaMallocAsync
+// stalled the host for 100-600 ms at unpredictable points of a 1 Gbp build.
+struct Arena {
+	struct Slab { char * base; size_t size; std::map<size_t, size_t> free_; };
+	std::vector<Slab> slabs;
+	std::map<void *, std::pair<int, size_t>> live; // ptr -> (slab, size)
+	size_t in_use = 0, peak = 0, capacity = 0;
+	static size_t round_up(size_t b) { return (b + 511) & ~(size_t)511; }
+	~Arena() { release_all(); }
+	void release_all() {
+		for (auto & s : slabs) cudaFree(s.base);
+		slabs.clear(); live.clear(); in_use = 0; capacity = 0;
+	}
+	void add_slab(size_t bytes) {
+		Slab s; s.size = round_up(bytes);
+		cudaError_t const e = cudaMalloc((void **)&s.base, s.size);
+		if (e != cudaSuccess) { cudaGetLastError(); throw Error(std::string("out of device memory allocating ") + std::to_string(s.size >> 20) + " MiB: " + cudaGetErrorString(e)); }
+		s.free_[0] = s.size;
+		capacity += s.size;
+		slabs.push_back(std::move(s));
+	}
+	// make sure one slab can hold `bytes` more; only reshapes the arena when nothing is live
+	void reserve(size_t bytes) {
+		bytes = round_up(bytes);
+		for (auto & s : slabs) for (auto & f : s.free_) if (f.second >= bytes) return;
+		if (live.empty()) release_all();
+		add_slab(bytes);
+	}
+	void * alloc(size_t bytes) {
+		if (!bytes) return nullptr;
+		bytes = round_up(bytes);
+		for (int pass = 0; pass < 2; ++pass) {
+			for (size_t si = 0; si < slabs.size(); ++si) {
+				auto & fl = slabs[si].free_;
+				for (auto it = fl.begin(); it != fl.end(); ++it) {
+					if (it->second >= bytes) {
+						size_t const off = it->first, sz = it->second;
+						fl.erase(it);
+						if (sz > bytes) fl[off + bytes] = sz - bytes;
+						void * p = slabs[si].base + off;
+						live[p] = std::make_pair((int)si, bytes);
+						in_use += bytes; if (in_use > peak) peak = in_use;
+						return p;
+					}
+				}
+			}
+			size_t const grow = bytes > ((size_t)1 << 30) ? bytes : ((size_t)1 << 30);
+			add_slab(grow);
+		}
+		throw Error("arena allocation failed");
+	}
+	void free(void * p) {
+		if (!p) return;
+		auto it = live.find(p);
+		if (it == live.end()) return;
+		int const si = it->second.first; size_t sz = it->second.second;
+		size_t off = (size_t)((char *)p - slabs[si].base);
+		live.erase(it);
+		in_use -= sz;
+		auto & fl = slabs[si].free_;
+		auto nx = fl.lower_bound(off);
+		if (nx != fl.end() && off + sz == nx->first) { sz += nx->second; nx = fl.erase(nx); }
+		if (nx != fl.begin()) { auto pv = std::prev(nx); if (pv->first + pv->second == off) { off = pv->first; sz += pv->second; fl.erase(pv); } }
+		fl[off] = sz;
+	}
+};
+
+// Per-engine launch context: the stream every kernel goes to, the arena, and counters the bench reports.
 struct Stream {
 	cudaStream_t s = nullptr;
 	uint64_t launches = 0;      // kernels launched by this library (bench: "gpu_launches")
 	int sms = 148;              // multiprocessor count of the device
+	Arena * arena = nullptr;
 };
 
 #define B3M_LAUNCH(st, kernel, grid, block, smem, ...)                                            \
@@ -40,29 +112,29 @@ struct Stream {
 		B3M_CUDA(cudaGetLastError());                                                             \
 	} while (0)
 
-// Stream-ordered device buffer (cudaMallocAsync from the device's default pool).
+// Arena-backed device buffer.
 template <typename T>
 struct DevBuf {
 	T * p = nullptr;
 	size_t n = 0;
-	cudaStream_t s = nullptr;
+	Arena * a = nullptr;
 	DevBuf() {}
 	DevBuf(Stream & st, size_t count) { alloc(st, count); }
 	DevBuf(DevBuf const &) = delete;
 	DevBuf & operator=(DevBuf const &) = delete;
-	DevBuf(DevBuf && o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; o.n = 0; }
+	DevBuf(DevBuf && o) noexcept : p(o.p), n(o.n), a(o.a) { o.p = nullptr; o.n = 0; }
 	DevBuf & operator=(DevBuf && o) noexcept {
-		if (this != &o) { release(); p = o.p; n = o.n; s = o.s; o.p = nullptr; o.n = 0; }
+		if (this != &o) { release(); p = o.p; n = o.n; a = o.a; o.p = nullptr; o.n = 0; }
 		return *this;
 	}
 	~DevBuf() { release(); }
 	void alloc(Stream & st, size_t count) {
 		release();
-		s = st.s; n = count;
-		if (count) B3M_CUDA(cudaMallocAsync((void **)&p, count * sizeof(T), s));
+		a = st.arena; n = count;
+		if (count) p = (T *)a->alloc(count * sizeof(T));
 	}
 	void release() {
-		if (p) { cudaFreeAsync(p, s); p = nullptr; n = 0; }
+		if (p) { a->free(p); p = nullptr; n = 0; }
 	}
 	T * get() const { return p; }
 	size_t bytes() const { return n * sizeof(T); }

@@ -25,11 +25,7 @@ Engine::Engine(int dev, void * stream) : device(dev) {
 	st.sms = prop.multiProcessorCount;
 	if (stream) { st.s = (cudaStream_t)stream; own_stream = false; }
 	else { B3M_CUDA(cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking)); own_stream = true; }
-	// keep freed blocks in the pool: repeated builds do not go back to the driver allocator
-	cudaMemPool_t pool;
-	B3M_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-	uint64_t thr = ~0ull;
-	B3M_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+	st.arena = &arena;
 	B3M_CUDA(cudaMallocHost((void **)&pinned, 4096));
 }
 
@@ -39,6 +35,7 @@ Engine::~Engine() {
 	raw.release(); codes.release(); bwt.release(); prerank.release(); sa.release(); isa.release(); dict.release();
 	d_hist.release(); d_special.release();
 	cudaStreamSynchronize(st.s);
+	arena.release_all();
 	if (pinned) cudaFreeHost(pinned);
 	if (own_stream) cudaStreamDestroy(st.s);
 }
@@ -53,8 +50,13 @@ void Engine::load(const void * input, uint64_t nbytes, int itype, bool on_device
 	B3M_CUDA(cudaSetDevice(device));
 	B3M_REQUIRE(itype >= 0 && itype <= 3, "unknown input type");
 	reset_results();
-	codes.release(); raw.release();
+	codes.release(); raw.release(); d_hist.release(); d_special.release();
 	inputtype = itype;
+	// one slab for the whole build: text + BWT + suffix/rank arrays + sort buffers (HBM layout)
+	{
+		uint64_t const nsym_est = (itype == B3M_INPUT_PAC || itype == B3M_INPUT_PACTERM) ? nbytes * 4 : nbytes;
+		arena.reserve((size_t)(nsym_est * 30 + nbytes + (64u << 20)));
+	}
 	PhaseTimer pt(st);
 	pt.mark();
 	const uint8_t * d_in = nullptr;

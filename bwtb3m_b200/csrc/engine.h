@@ -9,6 +9,7 @@ struct PhaseTimer;
 
 struct Engine {
 	int device = 0;
+	Arena arena;
 	Stream st;
 	bool own_stream = true;
 	uint8_t * pinned = nullptr; // 4 KiB pinned staging area for small copies

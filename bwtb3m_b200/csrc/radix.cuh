@@ -1,10 +1,16 @@
-// LSD radix sort on records held as NA parallel uint32 arrays (structure of arrays).
-// One pass = upsweep (per-tile digit histogram) -> exclusive scan -> downsweep (stable rank in
-// shared memory with warp match/ballot, reorder through shared memory, coalesced scatter).
-// No CTA waits on another CTA, so a pass cannot hang.
+// LSD radix sort on records held as NA parallel uint32 arrays (structure of arrays), 8-bit
+// digits, one kernel per digit ("onesweep"): each CTA takes the next tile from a ticket counter,
+// ranks its records stably in shared memory (8 ballots per record find equal digits inside a
+// warp), obtains its global offsets by decoupled look-back over the tile status words of its
+// predecessors, reorders through shared memory and writes coalesced runs.
 //
-// Algorithmic HBM bytes per pass and record: 4 (upsweep key read)
-// + 4*NA (downsweep read) + 4*NA (downsweep write).
+// Why not __match_any_sync: MATCH runs on the ADU pipe; a first version measured 98% ADU
+// utilisation and 7% of HBM peak (profiles/r01_radix_match_any.txt).
+// Forward progress: tickets are handed out in launch order, so every predecessor of a tile is
+// already resident or finished when the tile starts to look back.
+//
+// Algorithmic HBM bytes per pass and record: 4*NA read + 4*NA write, plus one
+// 4-byte key read per radix_sort_bits() call for the digit histograms.
 #pragma once
 #include "common.cuh"
 #include "scan.cuh"
@@ -16,128 +22,190 @@ constexpr int RADIX_WARPS = RADIX_THREADS / 32;
 constexpr int RADIX_ITEMS = 16;
 constexpr int RADIX_TILE = RADIX_THREADS * RADIX_ITEMS; // 4096 records
 constexpr int RADIX_BINS = 256;
+constexpr int RADIX_MAXDIG = 4;
 
 template <int NA>
 struct RadixRec {
 	uint32_t * a[NA];
 };
 
-// warp-aggregated shared-memory histogram update; returns rank of this lane among equal digits
-// that precede it in the warp plus the running count before this round.
-__device__ __forceinline__ uint32_t warp_rank_digit(uint32_t * wcnt, uint32_t d, bool valid) {
-	unsigned const peers = __match_any_sync(0xffffffffu, valid ? d : 0xffffffffu);
-	uint32_t before = 0;
-	if (valid) before = wcnt[d];
-	__syncwarp();
-	unsigned const lt = lanemask_lt();
-	if (valid && (peers & lt) == 0) wcnt[d] = before + __popc(peers);
-	__syncwarp();
-	return before + __popc(peers & lt);
+// lanes holding the same 8-bit digit
+__device__ __forceinline__ unsigned warp_peers8(uint32_t d) {
+	unsigned peers = 0xffffffffu;
+	#pragma unroll
+	for (int b = 0; b < 8; ++b) {
+		bool const bit = (d >> b) & 1u;
+		unsigned const m = __ballot_sync(0xffffffffu, bit);
+		peers &= bit ? m : ~m;
+	}
+	return peers;
 }
 
-__global__ void __launch_bounds__(RADIX_THREADS)
-k_radix_upsweep(const uint32_t * __restrict__ key, uint64_t n, int shift, uint32_t mask,
-                uint32_t * __restrict__ counts, uint32_t ntiles) {
-	__shared__ uint32_t wcnt[RADIX_WARPS][RADIX_BINS];
-	unsigned const w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	for (int i = threadIdx.x; i < RADIX_WARPS * RADIX_BINS; i += RADIX_THREADS) (&wcnt[0][0])[i] = 0;
+// ---- digit histograms of one key array: up to 4 digits in one read -----------------------
+__global__ void __launch_bounds__(256)
+k_radix_hist(const uint32_t * __restrict__ key, uint64_t n, int bit_lo, int ndig, uint32_t lastmask,
+             unsigned long long * __restrict__ ghist /* [ndig][256] */) {
+	__shared__ uint32_t sh[RADIX_MAXDIG][RADIX_BINS];
+	for (int i = threadIdx.x; i < RADIX_MAXDIG * RADIX_BINS; i += blockDim.x) (&sh[0][0])[i] = 0;
 	__syncthreads();
-	uint64_t const chunk = (uint64_t)blockIdx.x * RADIX_TILE + (uint64_t)w * (32 * RADIX_ITEMS);
-	uint32_t k[RADIX_ITEMS];
-	#pragma unroll
-	for (int j = 0; j < RADIX_ITEMS; ++j) {
-		uint64_t const i = chunk + j * 32 + lane;
-		k[j] = (i < n) ? key[i] : 0u;
-	}
-	#pragma unroll
-	for (int j = 0; j < RADIX_ITEMS; ++j) {
-		uint64_t const i = chunk + j * 32 + lane;
-		warp_rank_digit(wcnt[w], (k[j] >> shift) & mask, i < n);
+	uint64_t const stride = (uint64_t)gridDim.x * blockDim.x;
+	unsigned const lane = threadIdx.x & 31;
+	for (uint64_t b0 = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); b0 < n; b0 += stride) {
+		uint64_t const i = b0 + lane;
+		bool const valid = i < n;
+		uint32_t const k = valid ? (key[i] >> bit_lo) : 0u;
+		unsigned const vmask = __ballot_sync(0xffffffffu, valid);
+		for (int d = 0; d < ndig; ++d) {
+			uint32_t const dg = (k >> (8 * d)) & (d == ndig - 1 ? lastmask : 255u);
+			// a digit that is constant across the warp (high bits of small keys) is aggregated
+			uint32_t const d0 = __shfl_sync(0xffffffffu, dg, 0);
+			if (__all_sync(0xffffffffu, !valid || dg == d0)) { if (lane == 0) atomicAdd(&sh[d][d0], (uint32_t)__popc(vmask)); }
+			else if (valid) atomicAdd(&sh[d][dg], 1u);
+		}
 	}
 	__syncthreads();
-	for (int d = threadIdx.x; d < RADIX_BINS; d += RADIX_THREADS) {
-		uint32_t s = 0;
-		#pragma unroll
-		for (int ww = 0; ww < RADIX_WARPS; ++ww) s += wcnt[ww][d];
-		counts[(uint64_t)d * ntiles + blockIdx.x] = s;
+	for (int i = threadIdx.x; i < ndig * RADIX_BINS; i += blockDim.x)
+		if ((&sh[0][0])[i]) atomicAdd(&ghist[i], (unsigned long long)(&sh[0][0])[i]);
+}
+
+// exclusive scan of each digit's histogram; skip[d] = 1 when one bin holds every record
+__global__ void __launch_bounds__(256)
+k_radix_hist_scan(const unsigned long long * __restrict__ ghist, int ndig, uint64_t n, uint32_t * __restrict__ base /* [ndig][256] */,
+                  uint32_t * __restrict__ skip) {
+	for (int d = 0; d < ndig; ++d) {
+		uint32_t const c = (uint32_t)ghist[d * RADIX_BINS + threadIdx.x];
+		uint32_t total;
+		uint32_t const incl = block_scan_inclusive<OpSum>(c, &total);
+		base[d * RADIX_BINS + threadIdx.x] = incl - c;
+		if ((uint64_t)c == n) skip[d] = 1;
+		__syncthreads();
 	}
 }
+
+// status word: bits 63..62 = flag (0 empty, 1 aggregate of this tile, 2 inclusive prefix), low 32 bits = count
+constexpr unsigned long long RADIX_FLAG_AGG = 1ull << 62;
+constexpr unsigned long long RADIX_FLAG_INC = 2ull << 62;
 
 template <int NA>
-__global__ void __launch_bounds__(RADIX_THREADS)
-k_radix_downsweep(RadixRec<NA> in, RadixRec<NA> out, int ka, uint64_t n, int shift, uint32_t mask,
-                  const uint32_t * __restrict__ offsets, uint32_t ntiles) {
+struct RadixPassArgs {
+	const uint32_t * in[NA];   // in[0] is the array that holds the digit
+	uint32_t * out[NA];
+};
+
+template <int NA>
+__global__ void __launch_bounds__(RADIX_THREADS, 3)
+k_radix_onesweep(RadixPassArgs<NA> A, uint64_t n, int shift, uint32_t mask, const uint32_t * __restrict__ base /* [256] */,
+                 unsigned long long * __restrict__ status /* [ntiles][256] */, uint32_t * __restrict__ ticket) {
 	__shared__ uint32_t wcnt[RADIX_WARPS][RADIX_BINS];
 	__shared__ uint32_t gbase[RADIX_BINS];
-	__shared__ uint32_t stage[RADIX_TILE];
+	__shared__ uint32_t skey[RADIX_TILE];
+	__shared__ uint32_t sval[RADIX_TILE];
+	__shared__ uint32_t s_tile;
 	unsigned const w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
 	for (int i = threadIdx.x; i < RADIX_WARPS * RADIX_BINS; i += RADIX_THREADS) (&wcnt[0][0])[i] = 0;
 	__syncthreads();
-	uint64_t const tbase = (uint64_t)blockIdx.x * RADIX_TILE;
+	uint32_t const tile = s_tile;
+	uint64_t const tbase = (uint64_t)tile * RADIX_TILE;
 	uint64_t const chunk = tbase + (uint64_t)w * (32 * RADIX_ITEMS);
 	uint32_t const nvalid = (n - tbase) < (uint64_t)RADIX_TILE ? (uint32_t)(n - tbase) : (uint32_t)RADIX_TILE;
 
 	uint32_t k[RADIX_ITEMS];
-	uint32_t slot[RADIX_ITEMS];
 	#pragma unroll
 	for (int j = 0; j < RADIX_ITEMS; ++j) {
 		uint64_t const i = chunk + j * 32 + lane;
-		k[j] = (i < n) ? in.a[ka][i] : 0xffffffffu;
+		k[j] = (i < n) ? A.in[0][i] : 0xffffffffu;
 	}
+	// stable rank inside the warp; records past n take the last bin and, being last in tile
+	// order, rank behind every real record
+	uint16_t slot[RADIX_ITEMS];
+	uint32_t * mycnt = wcnt[w];
+	unsigned const lt = lanemask_lt();
 	#pragma unroll
 	for (int j = 0; j < RADIX_ITEMS; ++j) {
 		uint64_t const i = chunk + j * 32 + lane;
-		// records past n take the last bin; being last in tile order they rank after every real record
-		uint32_t const d = (i < n) ? ((k[j] >> shift) & mask) : (RADIX_BINS - 1);
-		slot[j] = warp_rank_digit(wcnt[w], d, true);
+		uint32_t const d = (i < n) ? ((k[j] >> shift) & mask) : (uint32_t)(RADIX_BINS - 1);
+		unsigned const peers = warp_peers8(d);
+		uint32_t const before = mycnt[d];
+		__syncwarp();
+		if ((peers & lt) == 0) mycnt[d] = before + __popc(peers);
+		__syncwarp();
+		slot[j] = (uint16_t)(before + __popc(peers & lt));
 	}
 	__syncthreads();
-	// per digit: exclusive scan over warps, then over digits
+	// per digit (thread d <-> bin d): scan over warps, publish the tile aggregate, scan over digits
 	{
-		uint32_t const d = threadIdx.x; // RADIX_THREADS == RADIX_BINS
+		uint32_t const d = threadIdx.x;
 		uint32_t s = 0;
 		#pragma unroll
 		for (int ww = 0; ww < RADIX_WARPS; ++ww) { uint32_t const t = wcnt[ww][d]; wcnt[ww][d] = s; s += t; }
+		// invalid records were counted in the last bin: they are not part of the global count
+		uint32_t const cnt = (d == RADIX_BINS - 1) ? s - (RADIX_TILE - nvalid) : s;
+		volatile unsigned long long * st = status + (uint64_t)tile * RADIX_BINS + d;
+		*st = (tile == 0 ? RADIX_FLAG_INC : RADIX_FLAG_AGG) | cnt;
 		uint32_t total;
 		uint32_t const incl = block_scan_inclusive<OpSum>(s, &total);
 		uint32_t const dstart = incl - s;
 		#pragma unroll
 		for (int ww = 0; ww < RADIX_WARPS; ++ww) wcnt[ww][d] += dstart;
-		gbase[d] = offsets[(uint64_t)d * ntiles + blockIdx.x] - dstart;
+		// decoupled look-back
+		uint32_t excl = 0;
+		if (tile > 0) {
+			int64_t t = (int64_t)tile - 1;
+			while (true) {
+				unsigned long long const v = *(volatile unsigned long long *)(status + (uint64_t)t * RADIX_BINS + d);
+				if ((v >> 62) == 0) continue;
+				excl += (uint32_t)v;
+				if ((v >> 62) == 2) break;
+				--t;
+			}
+			*st = RADIX_FLAG_INC | (unsigned long long)(excl + cnt);
+		}
+		gbase[d] = base[d] + excl - dstart;
 	}
 	__syncthreads();
 	#pragma unroll
 	for (int j = 0; j < RADIX_ITEMS; ++j) {
 		uint64_t const i = chunk + j * 32 + lane;
-		uint32_t const d = (i < n) ? ((k[j] >> shift) & mask) : (RADIX_BINS - 1);
-		slot[j] += wcnt[w][d];
-		stage[slot[j]] = k[j];
+		uint32_t const d = (i < n) ? ((k[j] >> shift) & mask) : (uint32_t)(RADIX_BINS - 1);
+		slot[j] = (uint16_t)(slot[j] + wcnt[w][d]);
+		skey[slot[j]] = k[j];
+	}
+	// payload loads are issued before the barrier so that they overlap the key scatter
+	uint32_t v[NA > 1 ? RADIX_ITEMS : 1];
+	if (NA > 1) {
+		#pragma unroll
+		for (int j = 0; j < RADIX_ITEMS; ++j) {
+			uint64_t const i = chunk + j * 32 + lane;
+			v[j] = (i < n) ? A.in[1][i] : 0u;
+		}
 	}
 	__syncthreads();
-	uint32_t gpos[RADIX_ITEMS];
 	#pragma unroll
 	for (int j = 0; j < RADIX_ITEMS; ++j) {
 		uint32_t const s = j * RADIX_THREADS + threadIdx.x;
 		if (s < nvalid) {
-			uint32_t const kk = stage[s];
-			gpos[j] = gbase[(kk >> shift) & mask] + s;
-			out.a[ka][gpos[j]] = kk;
+			uint32_t const kk = skey[s];
+			A.out[0][gbase[(kk >> shift) & mask] + s] = kk;
 		}
 	}
 	#pragma unroll
-	for (int a = 0; a < NA; ++a) {
-		if (a == ka) continue;
-		__syncthreads();
-		#pragma unroll
-		for (int j = 0; j < RADIX_ITEMS; ++j) {
-			uint64_t const i = chunk + j * 32 + lane;
-			if (i < n) stage[slot[j]] = in.a[a][i];
+	for (int a = 1; a < NA; ++a) {
+		if (a > 1) {
+			__syncthreads();
+			#pragma unroll
+			for (int j = 0; j < RADIX_ITEMS; ++j) {
+				uint64_t const i = chunk + j * 32 + lane;
+				v[j] = (i < n) ? A.in[a][i] : 0u;
+			}
 		}
+		#pragma unroll
+		for (int j = 0; j < RADIX_ITEMS; ++j) sval[slot[j]] = v[j];
 		__syncthreads();
 		#pragma unroll
 		for (int j = 0; j < RADIX_ITEMS; ++j) {
 			uint32_t const s = j * RADIX_THREADS + threadIdx.x;
-			if (s < nvalid) out.a[a][gpos[j]] = stage[s];
+			if (s < nvalid) A.out[a][gbase[(skey[s] >> shift) & mask] + s] = sval[s];
 		}
 	}
 }
@@ -148,22 +216,43 @@ struct RadixStats {
 };
 
 // Sorts records by bits [bit_lo, bit_hi) of array ka (stable).  `cur` and `alt` are ping-pong
-// buffers; on return *swapped tells whether the result lives in alt.
+// buffers; on return `cur` names the arrays that hold the result.
 template <int NA>
 void radix_sort_bits(Stream & st, RadixRec<NA> & cur, RadixRec<NA> & alt, int ka, uint64_t n,
                      int bit_lo, int bit_hi, RadixStats * rs) {
 	if (n == 0 || bit_hi <= bit_lo) return;
 	uint32_t const ntiles = (uint32_t)div_up(n, RADIX_TILE);
-	DevBuf<uint32_t> counts(st, (size_t)ntiles * RADIX_BINS);
-	for (int shift = bit_lo; shift < bit_hi; shift += 8) {
-		int const bits = (bit_hi - shift) < 8 ? (bit_hi - shift) : 8;
-		uint32_t const mask = (1u << bits) - 1u;
-		B3M_LAUNCH(st, k_radix_upsweep, ntiles, RADIX_THREADS, 0, cur.a[ka], n, shift, mask, counts.get(), ntiles);
-		scan_exclusive_inplace<OpSum>(st, counts.get(), (uint64_t)ntiles * RADIX_BINS);
-		B3M_LAUNCH(st, (k_radix_downsweep<NA>), ntiles, RADIX_THREADS, 0, cur, alt, ka, n, shift, mask,
-		           (const uint32_t *)counts.get(), ntiles);
-		RadixRec<NA> t = cur; cur = alt; alt = t;
-		if (rs) { rs->passes++; rs->bytes += n * (4ull + 8ull * NA); }
+	DevBuf<unsigned long long> status(st, (size_t)ntiles * RADIX_BINS);
+	for (int lo = bit_lo; lo < bit_hi; lo += 8 * RADIX_MAXDIG) {
+		int const hi = (bit_hi - lo) > 8 * RADIX_MAXDIG ? lo + 8 * RADIX_MAXDIG : bit_hi;
+		int const ndig = (hi - lo + 7) / 8;
+		int const lastbits = (hi - lo) - 8 * (ndig - 1);
+		uint32_t const lastmask = (1u << lastbits) - 1u;
+		DevBuf<unsigned long long> ghist(st, RADIX_MAXDIG * RADIX_BINS);
+		DevBuf<uint32_t> base(st, RADIX_MAXDIG * RADIX_BINS + 8 + RADIX_MAXDIG);
+		uint32_t * skip = base.get() + RADIX_MAXDIG * RADIX_BINS;
+		uint32_t * ticket = skip + 4;
+		B3M_CUDA(cudaMemsetAsync(ghist.get(), 0, ghist.bytes(), st.s));
+		B3M_CUDA(cudaMemsetAsync(skip, 0, (8 + RADIX_MAXDIG) * sizeof(uint32_t), st.s));
+		uint64_t const want = div_up(n, 256 * 16);
+		unsigned const hgrid = (unsigned)(want < (uint64_t)st.sms * 8 ? want : (uint64_t)st.sms * 8);
+		B3M_LAUNCH(st, k_radix_hist, hgrid, 256, 0, (const uint32_t *)cur.a[ka], n, lo, ndig, lastmask, ghist.get());
+		B3M_LAUNCH(st, k_radix_hist_scan, 1, 256, 0, (const unsigned long long *)ghist.get(), ndig, n, base.get(), skip);
+		if (rs) rs->bytes += 4ull * n;
+		uint32_t hskip[4];
+		B3M_CUDA(cudaMemcpyAsync(hskip, skip, sizeof(hskip), cudaMemcpyDeviceToHost, st.s));
+		B3M_CUDA(cudaStreamSynchronize(st.s));
+		for (int d = 0; d < ndig; ++d) {
+			if (hskip[d]) continue; // every record has the same digit: the pass would be the identity
+			B3M_CUDA(cudaMemsetAsync(status.get(), 0, status.bytes(), st.s));
+			RadixPassArgs<NA> A;
+			A.in[0] = cur.a[ka]; A.out[0] = alt.a[ka];
+			for (int a = 0, o = 1; a < NA; ++a) if (a != ka) { A.in[o] = cur.a[a]; A.out[o] = alt.a[a]; ++o; }
+			B3M_LAUNCH(st, (k_radix_onesweep<NA>), ntiles, RADIX_THREADS, 0, A, n, lo + 8 * d,
+			           (d == ndig - 1 ? lastmask : 255u), (const uint32_t *)(base.get() + d * RADIX_BINS), status.get(), ticket + d);
+			RadixRec<NA> t = cur; cur = alt; alt = t;
+			if (rs) { rs->passes++; rs->bytes += n * 8ull * NA; }
+		}
 	}
 }
 

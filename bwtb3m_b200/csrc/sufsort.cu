@@ -9,6 +9,8 @@
 #include "kernels.h"
 #include "radix.cuh"
 #include "scan.cuh"
+#include <time.h>
+#include <stdlib.h>
 
 namespace b3m {
 
@@ -57,6 +59,13 @@ k_gather_ahead(const uint32_t * __restrict__ aidx, uint64_t na, const uint32_t *
 	key2[a] = k;
 }
 
+static double wall_ms() {
+	struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+	return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+static bool trace_on() { static int t = -1; if (t < 0) t = getenv("B3M_TRACE") ? 1 : 0; return t == 1; }
+#define TRACE(msg) do { if (trace_on()) { cudaStreamSynchronize(st.s); double t_ = wall_ms(); fprintf(stderr, "[T] %-28s %9.3f ms\n", msg, t_ - t_last); t_last = wall_ms(); } } while (0)
+
 static uint32_t fetch_u32(Stream & st, const uint32_t * d) {
 	uint32_t h = 0;
 	B3M_CUDA(cudaMemcpyAsync(&h, d, sizeof(uint32_t), cudaMemcpyDeviceToHost, st.s));
@@ -73,6 +82,7 @@ void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W,
 	uint64_t const nshort = circular ? 0 : (W < (uint64_t)(k0 - 1) ? W : (uint64_t)(k0 - 1));
 	TextView v{T.codes, T.ntext, wstart, W, circular, text_wraps};
 	SortStats S;
+	double t_last = wall_ms();
 
 	DevBuf<uint32_t> scalar(st, 4);
 	uint32_t * d_total = scalar.get();
@@ -84,10 +94,13 @@ void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W,
 		// sa doubles as the first index buffer
 		RadixRec<2> cur{{key0.get(), sa}}, alt{{key1.get(), idx1.get()}};
 		unsigned const grid = (unsigned)div_up(W, 256);
+		TRACE("r0 alloc");
 		B3M_LAUNCH(st, k_make_keys, grid, 256, 0, v, bits, k0, nshort, cur.a[0], cur.a[1]);
 		S.other_bytes += W * (1ull + 8ull);
 		RadixStats rs;
+		TRACE("r0 make_keys");
 		radix_sort_bits<2>(st, cur, alt, 0, W, 0, 32, &rs);
+		TRACE("r0 radix");
 		S.radix_passes += rs.passes; S.radix_bytes += rs.bytes; S.active_sum += W; S.rounds = 1;
 		const uint32_t * skey = cur.a[0];
 		const uint32_t * sidx = cur.a[1];
@@ -110,6 +123,7 @@ void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W,
 				if (sa != sidx) sa[k] = i;
 			});
 		S.other_bytes += W * (8ull + 8ull + 4ull + 4ull + 4ull);
+		TRACE("r0 heads+rank scatter");
 		// compaction of suffixes whose group has more than one member
 		B3M_CUDA(cudaMemsetAsync(d_total, 0, 4, st.s));
 		// two passes: count, then allocate and fill
@@ -122,6 +136,7 @@ void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W,
 			[=] __device__(uint64_t k, uint32_t excl, uint32_t v0) { if (k + 1 == Wm) *d_total = excl + v0; });
 		na = fetch_u32(st, d_total);
 		S.other_bytes += W * 8ull;
+		TRACE("r0 count active");
 		if (na) {
 			for (int b = 0; b < 6; ++b) pool[b].alloc(st, na);
 			uint32_t * agrp = pool[0].get();
@@ -133,7 +148,9 @@ void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W,
 				});
 			S.other_bytes += W * 8ull + na * 8ull;
 		}
+		TRACE("r0 compact");
 	}
+	TRACE("r0 free");
 
 	// ---------------- doubling rounds ----------------
 	uint32_t * bufs[6];
@@ -146,11 +163,13 @@ void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W,
 		unsigned const grid = (unsigned)div_up(na, 256);
 		B3M_LAUNCH(st, k_gather_ahead, grid, 256, 0, (const uint32_t *)bufs[1], na, (const uint32_t *)rank, h, W, circular, bufs[2]);
 		S.other_bytes += na * (4ull + 32ull + 4ull);
+		TRACE("rN gather");
 		RadixRec<3> cur{{bufs[0], bufs[2], bufs[1]}}, alt{{bufs[3], bufs[4], bufs[5]}};
 		RadixStats rs;
 		radix_sort_bits<3>(st, cur, alt, 1, na, 0, bw, &rs); // rank ahead (minor key)
 		radix_sort_bits<3>(st, cur, alt, 0, na, 0, bw, &rs); // group (major key)
 		S.radix_passes += rs.passes; S.radix_bytes += rs.bytes; S.active_sum += na; S.rounds++;
+		TRACE("rN radix");
 		const uint32_t * sg = cur.a[0];
 		const uint32_t * sk = cur.a[1];
 		const uint32_t * si = cur.a[2];
@@ -188,6 +207,7 @@ void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W,
 			});
 		S.other_bytes += na * (2 * 8ull + 8ull);
 		uint64_t const nn = fetch_u32(st, d_total);
+		TRACE("rN split+compact");
 		// next round: grp = alt[1], idx = alt[2]; everything else is free
 		uint32_t * nb[6] = {alt.a[1], alt.a[2], cur.a[0], cur.a[1], cur.a[2], alt.a[0]};
 		for (int b = 0; b < 6; ++b) bufs[b] = nb[b];
