@@ -6,7 +6,7 @@ NVFLAGS := -std=c++17 -O3 -lineinfo --extended-lambda $(ARCH) -ccbin $(CXX) -Xco
 CSRC := bwtb3m_b200/csrc
 OBJS := $(CSRC)/engine.o $(CSRC)/sufsort.o $(CSRC)/stages.o $(CSRC)/blocks.o $(CSRC)/hostapi.o
 LIB  := bwtb3m_b200/libb3m.so
-BINS := bin/bwtb3m bin/bwtb3mtobwa bin/bwtcomputessa bin/bwtb3mdecoderl bin/checkbwt
+BINS := $(patsubst cli/%.cpp,bin/%,$(wildcard cli/*.cpp))
 
 all: $(LIB) $(BINS) oracle
 

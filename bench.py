@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- measures BASELINE.json's metric (input Mbp/s of the BWT + sampled SA/ISA build).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl ours|reference]
+
+A step = one pass of the hot path (K1 decode -> K2 sort -> K3 extract -> [K5 gap, K6 merge] ->
+K4 dictionary -> K7 SA/ISA walk) over one synthetic input.  `value`: inputs already resident in
+HBM; `e2e`: the same through the C ABI with pinned HOST buffers (H2D of the input file bytes,
+D2H of BWT + anchors + SA + ISA inside the timed region).  The CPU oracle is executed only for
+the `cpu_baseline` leg and by `--impl reference`.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "input Mbp/s BWT+SSA build"
+UNIT = "Mbp/s"
+
+
+def build_params(workload):
+    # cfg1 is the reference's CPU-runnable BWT-only case; the others build the full sampled SA/ISA
+    if workload == "cfg1":
+        return dict(sasamplingrate=32, isasamplingrate=262144, bwtonly=True)
+    return dict(sasamplingrate=32, isasamplingrate=262144, bwtonly=False)
+
+
+def config_dict(args, n, itype, extra=None):
+    from bwtb3m_b200.workloads import CONFIGS
+    d = {
+        "workload": "%s: %s" % (args.workload, CONFIGS[args.workload][3]),
+        "n_symbols": int(n),
+        "inputtype": itype,
+        "sasamplingrate": 32,
+        "isasamplingrate": 262144,
+        "bwtonly": 1 if args.workload == "cfg1" else 0,
+        "scale": args.scale,
+        "l2": "flushed between timed steps (256 MiB write)",
+    }
+    if extra:
+        d.update(extra)
+    return d
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks and throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.samples.append(line.strip())
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        busy = sorted(sm)[len(sm) // 2:]  # the upper half of the samples = under load
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_oracle_run(itype, filebytes, nsyms_limit, params, threads):
+    """Times the CPU oracle (restated reference algorithm) on a prefix of the workload."""
+    from oracle import oracle as orc
+    orc.build()
+    if itype in ("pac", "pacterm"):
+        from bwtb3m_b200.workloads import pac_file_from_packed
+        pac = pac_file_from_packed(filebytes, nsyms_limit)  # prefix of the workload as its own .pac file
+        t0 = time.perf_counter()
+        t = orc.decode_pac(pac.tobytes(), term=(itype == "pacterm"))
+    else:
+        t0 = time.perf_counter()
+        t = np.ascontiguousarray(filebytes[:nsyms_limit])
+    n = t.size
+    nblocks = orc.default_numblocks(n, 2 << 30, threads)  # reference defaults: mem=2 GiB
+    rate = 64 if params["bwtonly"] else 4096  # anchors every 4096 positions keep all host threads busy in the SSA walk
+    bwt, pp, st = orc.b3m(t, nblocks=nblocks, rate=rate, nthreads=threads)
+    if not params["bwtonly"]:
+        orc.ssa(bwt, pp, params["sasamplingrate"], params["isasamplingrate"], nthreads=threads)
+    dt = time.perf_counter() - t0
+    return dt, n, nblocks
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  gt1/bwtb3m cannot be
+    built here (libmaus2 is absent), so this arm times the oracle port, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from bwtb3m_b200 import workloads
+    from oracle import oracle as orc
+    itype, data, nsym = workloads.make(args.workload, args.scale)
+    params = build_params(args.workload)
+    threads = os.cpu_count() or 1
+    sample = min(nsym, args.ref_sample)
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_oracle_run(itype, data, sample, params, threads)
+    tot, syms = 0.0, 0
+    for _ in range(args.steps):
+        dt, n, nblocks = cpu_oracle_run(itype, data, sample, params, threads)
+        tot += dt
+        syms += sample
+    v = syms / tot / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": config_dict(args, nsym, itype),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "first %d symbols of the workload per step, %d blocks; restated reference (libmaus2 unavailable)" % (sample, nblocks)},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from bwtb3m_b200 import Engine, workloads
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        from bwtb3m_b200 import multigpu
+        return multigpu.bench_main(args, METRIC, UNIT, config_dict, build_params, ClockSampler, measured_peak_gbs)
+
+    torch.cuda.set_device(local)
+    itype, data, nsym = workloads.make(args.workload, args.scale)
+    params = build_params(args.workload)
+    host_in = torch.from_numpy(data).pin_memory()
+    dev_in = host_in.cuda(non_blocking=False)
+    stream = torch.cuda.Stream()
+    eng = Engine(local, stream.cuda_stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def step_device():
+        eng.load_device(dev_in.data_ptr(), dev_in.numel(), itype)
+        eng.build(numblocks=args.numblocks, **params)
+
+    with torch.cuda.stream(stream):
+        for _ in range(max(args.warmup, 3)):
+            step_device()
+        info = eng.info()
+        # ---- value: device-resident input, CUDA events on the engine's stream ----
+        sampler = ClockSampler(local)
+        sampler.start()
+        time.sleep(0.15)
+        torch.cuda.synchronize()
+        l0 = eng.info()["launches"]
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for k in range(args.steps):
+            flush.fill_(k & 0xFF)
+            ev[k][0].record(stream)
+            step_device()
+            ev[k][1].record(stream)
+        torch.cuda.synchronize()
+        total_ms = sum(a.elapsed_time(b) for a, b in ev)
+        l1 = eng.info()["launches"]
+        time.sleep(0.1)
+        sampler.stop()
+        info = eng.info()
+
+        # ---- e2e: pinned host input -> results in pinned host buffers, wall clock ----
+        n = info["n"]
+        out = {
+            "bwt": torch.empty(n, dtype=torch.uint8).pin_memory(),
+            "preisa": torch.empty(2 * info["npreisa"], dtype=torch.int64).pin_memory(),
+            "sa": torch.empty(max(info["nsa"], 1), dtype=torch.int64).pin_memory(),
+            "isa": torch.empty(max(info["nisa"], 1), dtype=torch.int64).pin_memory(),
+        }
+
+        def step_e2e():
+            eng.load_host_ptr(host_in.data_ptr(), host_in.numel(), itype)
+            eng.build(numblocks=args.numblocks, **params)
+            eng.fetch_ptrs(out["bwt"].data_ptr(), out["preisa"].data_ptr(),
+                           out["sa"].data_ptr() if info["nsa"] else 0, out["isa"].data_ptr() if info["nisa"] else 0)
+
+        step_e2e()
+        torch.cuda.synchronize()
+        e2e_s = 0.0
+        for k in range(args.steps):
+            flush.fill_(k & 0xFF)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            step_e2e()
+            torch.cuda.synchronize()
+            e2e_s += time.perf_counter() - t0
+        h2d = int(host_in.numel())
+        d2h = int(n + 16 * info["npreisa"] + 8 * info["nsa"] + 8 * info["nisa"])
+
+        # ---- roofline of the dominant kernel: per-kernel CUDA events, separate profiled steps ----
+        eng.set_profile(True)
+        for k in range(3):
+            flush.fill_(k)
+            step_device()
+        kt = eng.kernel_times()
+        eng.set_profile(False)
+        lf_ms, _ = eng.lf_bench(1 << 20, 256)
+
+    peak, peak_src = measured_peak_gbs()
+    dom = max(kt.items(), key=lambda kv: kv[1]["ms"]) if kt else (None, None)
+    roof = None
+    if dom[0]:
+        name, r = dom
+        achieved = r["bytes"] / (r["ms"] * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                tj = json.load(open(tp))
+                if tj.get("kernel") == name and tj.get("workload") == args.workload and args.scale == 1.0:
+                    traffic = tj.get("dram_bytes_per_launch")
+            except Exception:
+                pass
+        roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "launches_timed": r["launches"],
+                "avg_launch_ms": r["ms"] / r["launches"], "algorithmic_bytes_per_launch": r["bytes"] / r["launches"],
+                "share_of_step": r["ms"] / sum(x["ms"] for x in kt.values())}
+
+    # ---- CPU baseline: the oracle port on this box's host cores ----
+    threads = os.cpu_count() or 1
+    cpu = None
+    if not args.no_cpu:
+        sample = min(nsym, args.cpu_sample)
+        dt, nn, nblocks = cpu_oracle_run(itype, data, sample, params, threads)
+        cpu = {"value": sample / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port", "seconds": dt,
+               "sample": "first %d symbols of the workload, %d blocks, full pipeline; restated reference (libmaus2 unavailable)" % (sample, nblocks)}
+
+    total_s = total_ms * 1e-3
+    line = {
+        "metric": METRIC, "value": nsym * args.steps / total_s / 1e6, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": config_dict(args, nsym, itype, {"numblocks": info["numblocks"], "preisarate": info["preisarate"]}),
+        "clocks": sampler.summary(),
+        "e2e": {"value": nsym * args.steps / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1e3 * e2e_s / args.steps},
+        "gpu_launches": int(l1 - l0),
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "phases_ms": {k[3:]: round(info[k], 4) for k in info if k.startswith("ms_")},
+        "counters": {k: info[k] for k in ("sort_rounds", "radix_passes", "radix_bytes", "sort_active_sum", "walk_lf_steps",
+                                          "walk_chains", "gap_lf_steps", "max_lcpnext")},
+        "kernels_ms_per_step": {k: round(v["ms"] / 3, 4) for k, v in kt.items()},
+        "lf_steps_per_s": (1 << 20) * 256 / (lf_ms * 1e-3),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only; invalid as a bench value)")
+    ap.add_argument("--numblocks", type=int, default=1)
+    ap.add_argument("--cpu-sample", type=int, default=48_000_000, help="symbols of the workload the cpu_baseline leg processes")
+    ap.add_argument("--ref-sample", type=int, default=8_000_000, help="symbols per step of --impl reference")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

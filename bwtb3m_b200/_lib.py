@@ -53,7 +53,8 @@ EXPORTS = [
     "b3m_version", "b3m_parse_inputtype", "b3m_options_init", "b3m_compute_bwt", "b3m_compute_ssa", "b3m_to_bwa",
     "b3m_engine_create", "b3m_engine_destroy", "b3m_engine_last_error", "b3m_engine_load_host",
     "b3m_engine_load_device", "b3m_engine_build", "b3m_engine_info", "b3m_engine_fetch",
-    "b3m_engine_device_results", "b3m_engine_lf_bench", "b3m_engine_sync",
+    "b3m_engine_device_results", "b3m_engine_lf_bench", "b3m_engine_sync", "b3m_engine_set_profile",
+    "b3m_engine_kernel_times",
 ]
 
 _lib = None
@@ -82,6 +83,8 @@ def lib():
     L.b3m_engine_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.b3m_engine_lf_bench.argtypes = [vp, u64, u64, C.POINTER(C.c_float), u64p]
     L.b3m_engine_sync.argtypes = [vp]
+    L.b3m_engine_set_profile.argtypes = [vp, C.c_int]
+    L.b3m_engine_kernel_times.argtypes = [vp, C.c_char_p, C.c_size_t]
     if hasattr(L, "b3m_options_init"):
         L.b3m_options_init.argtypes = [C.POINTER(Options)]
         L.b3m_options_init.restype = None

@@ -97,13 +97,46 @@ struct Arena {
 	}
 };
 
+// Opt-in per-kernel timing (CUDA events on the launching stream) for the roofline report.
+struct KernelTimes {
+	struct Rec { std::string name; uint64_t bytes; cudaEvent_t a, b; };
+	bool on = false;
+	std::vector<Rec> recs;
+	std::vector<cudaEvent_t> spare;
+	cudaEvent_t get() {
+		cudaEvent_t e;
+		if (!spare.empty()) { e = spare.back(); spare.pop_back(); return e; }
+		cudaEventCreate(&e);
+		return e;
+	}
+	void clear() { for (auto & r : recs) { spare.push_back(r.a); spare.push_back(r.b); } recs.clear(); }
+	~KernelTimes() { clear(); for (auto e : spare) cudaEventDestroy(e); }
+};
+
 // Per-engine launch context: the stream every kernel goes to, the arena, and counters the bench reports.
 struct Stream {
 	cudaStream_t s = nullptr;
 	uint64_t launches = 0;      // kernels launched by this library (bench: "gpu_launches")
 	int sms = 148;              // multiprocessor count of the device
 	Arena * arena = nullptr;
+	KernelTimes kt;
 };
+
+// launch + (when profiling is switched on) bracket with events; `bytes` = algorithmic HBM bytes
+#define B3M_LAUNCH_T(st, label, bytes_, kernel, grid, block, smem, ...)                           \
+	do {                                                                                          \
+		if ((st).kt.on) {                                                                         \
+			::b3m::KernelTimes::Rec r_{label, (uint64_t)(bytes_), (st).kt.get(), (st).kt.get()};   \
+			cudaEventRecord(r_.a, (st).s);                                                        \
+			kernel<<<(grid), (block), (smem), (st).s>>>(__VA_ARGS__);                             \
+			cudaEventRecord(r_.b, (st).s);                                                        \
+			(st).kt.recs.push_back(r_);                                                           \
+		} else {                                                                                  \
+			kernel<<<(grid), (block), (smem), (st).s>>>(__VA_ARGS__);                             \
+		}                                                                                         \
+		++(st).launches;                                                                          \
+		B3M_CUDA(cudaGetLastError());                                                             \
+	} while (0)
 
 #define B3M_LAUNCH(st, kernel, grid, block, smem, ...)                                            \
 	do {                                                                                          \

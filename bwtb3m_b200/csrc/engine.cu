@@ -4,6 +4,8 @@
 #include "scan.cuh"
 #include <string.h>
 #include <algorithm>
+#include <map>
+#include <tuple>
 
 namespace b3m {
 
@@ -348,9 +350,9 @@ static void set_err(char * err, size_t errlen, const char * msg) {
 	if (err && errlen) { strncpy(err, msg, errlen - 1); err[errlen - 1] = 0; }
 }
 
-#define B3M_GUARD(h, body)                                                   \
+#define B3M_GUARD(h, ...)                                                    \
 	if (!(h)) return 1;                                                      \
-	try { body; (h)->err.clear(); return 0; }                                \
+	try { __VA_ARGS__; (h)->err.clear(); return 0; }                                \
 	catch (std::exception const & ex) { (h)->err = ex.what(); return 2; }    \
 	catch (...) { (h)->err = "unknown error"; return 3; }
 
@@ -419,6 +421,30 @@ int b3m_engine_device_results(b3m_engine * h, const void ** d_bwt_codes, const v
 }
 int b3m_engine_lf_bench(b3m_engine * h, uint64_t nchains, uint64_t steps, float * ms, uint64_t * checksum) {
 	B3M_GUARD(h, { float t = 0; h->e->lf_bench(nchains, steps, &t, checksum); if (ms) *ms = t; });
+}
+int b3m_engine_set_profile(b3m_engine * h, int on) {
+	B3M_GUARD(h, { h->e->st.kt.clear(); h->e->st.kt.on = on != 0; });
+}
+int b3m_engine_kernel_times(b3m_engine * h, char * buf, size_t buflen) {
+	B3M_GUARD(h, {
+		B3M_CUDA(cudaSetDevice(h->e->device));
+		B3M_CUDA(cudaStreamSynchronize(h->e->st.s));
+		std::map<std::string, std::tuple<uint64_t, double, uint64_t>> agg;
+		for (auto & r : h->e->st.kt.recs) {
+			float ms = 0; cudaEventElapsedTime(&ms, r.a, r.b);
+			auto & t = agg[r.name];
+			std::get<0>(t) += 1; std::get<1>(t) += ms; std::get<2>(t) += r.bytes;
+		}
+		h->e->st.kt.clear();
+		std::string out;
+		for (auto & kv : agg) {
+			char line[256];
+			snprintf(line, sizeof(line), "%s %llu %.6f %llu\n", kv.first.c_str(), (unsigned long long)std::get<0>(kv.second),
+			         std::get<1>(kv.second), (unsigned long long)std::get<2>(kv.second));
+			out += line;
+		}
+		if (buf && buflen) { strncpy(buf, out.c_str(), buflen - 1); buf[buflen - 1] = 0; }
+	});
 }
 int b3m_engine_sync(b3m_engine * h) {
 	B3M_GUARD(h, { B3M_CUDA(cudaSetDevice(h->e->device)); B3M_CUDA(cudaStreamSynchronize(h->e->st.s)); });

@@ -236,7 +236,7 @@ void radix_sort_bits(Stream & st, RadixRec<NA> & cur, RadixRec<NA> & alt, int ka
 		B3M_CUDA(cudaMemsetAsync(skip, 0, (8 + RADIX_MAXDIG) * sizeof(uint32_t), st.s));
 		uint64_t const want = div_up(n, 256 * 16);
 		unsigned const hgrid = (unsigned)(want < (uint64_t)st.sms * 8 ? want : (uint64_t)st.sms * 8);
-		B3M_LAUNCH(st, k_radix_hist, hgrid, 256, 0, (const uint32_t *)cur.a[ka], n, lo, ndig, lastmask, ghist.get());
+		B3M_LAUNCH_T(st, "radix_hist", 4ull * n, k_radix_hist, hgrid, 256, 0, (const uint32_t *)cur.a[ka], n, lo, ndig, lastmask, ghist.get());
 		B3M_LAUNCH(st, k_radix_hist_scan, 1, 256, 0, (const unsigned long long *)ghist.get(), ndig, n, base.get(), skip);
 		if (rs) rs->bytes += 4ull * n;
 		uint32_t hskip[4];
@@ -248,7 +248,8 @@ void radix_sort_bits(Stream & st, RadixRec<NA> & cur, RadixRec<NA> & alt, int ka
 			RadixPassArgs<NA> A;
 			A.in[0] = cur.a[ka]; A.out[0] = alt.a[ka];
 			for (int a = 0, o = 1; a < NA; ++a) if (a != ka) { A.in[o] = cur.a[a]; A.out[o] = alt.a[a]; ++o; }
-			B3M_LAUNCH(st, (k_radix_onesweep<NA>), ntiles, RADIX_THREADS, 0, A, n, lo + 8 * d,
+			B3M_LAUNCH_T(st, NA == 2 ? "radix_onesweep<2>" : (NA == 3 ? "radix_onesweep<3>" : "radix_onesweep"), n * 8ull * NA,
+			           (k_radix_onesweep<NA>), ntiles, RADIX_THREADS, 0, A, n, lo + 8 * d,
 			           (d == ndig - 1 ? lastmask : 255u), (const uint32_t *)(base.get() + d * RADIX_BINS), status.get(), ticket + d);
 			RadixRec<NA> t = cur; cur = alt; alt = t;
 			if (rs) { rs->passes++; rs->bytes += n * 8ull * NA; }

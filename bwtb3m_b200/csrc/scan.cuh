@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile(uint64_t n, In in, O
 }
 
 template <typename Op, typename In, typename Out>
-void scan_apply(Stream & st, uint64_t n, In in, Out out);
+void scan_apply(Stream & st, uint64_t n, In in, Out out, const char * label = nullptr, uint64_t bytes = 0);
 
 // exclusive scan of an array in place
 template <typename Op>
@@ -139,7 +139,7 @@ void scan_exclusive_inplace(Stream & st, typename Op::T * a, uint64_t n) {
 }
 
 template <typename Op, typename In, typename Out>
-void scan_apply(Stream & st, uint64_t n, In in, Out out) {
+void scan_apply(Stream & st, uint64_t n, In in, Out out, const char * label, uint64_t bytes) {
 	typedef typename Op::T T;
 	if (n == 0) return;
 	uint64_t const ntiles = div_up(n, SCAN_TILE);
@@ -150,7 +150,8 @@ void scan_apply(Stream & st, uint64_t n, In in, Out out) {
 	DevBuf<T> partial(st, ntiles);
 	B3M_LAUNCH(st, (k_scan_reduce<Op, In>), (unsigned)ntiles, SCAN_THREADS, 0, n, in, partial.get());
 	scan_exclusive_inplace<Op>(st, partial.get(), ntiles);
-	B3M_LAUNCH(st, (k_scan_tile<Op, In, Out>), (unsigned)ntiles, SCAN_THREADS, 0, n, in, out, (const T *)partial.get());
+	if (label) B3M_LAUNCH_T(st, label, bytes, (k_scan_tile<Op, In, Out>), (unsigned)ntiles, SCAN_THREADS, 0, n, in, out, (const T *)partial.get());
+	else B3M_LAUNCH(st, (k_scan_tile<Op, In, Out>), (unsigned)ntiles, SCAN_THREADS, 0, n, in, out, (const T *)partial.get());
 }
 
 } // namespace b3m

@@ -177,7 +177,7 @@ k_extract_bwt(const uint8_t * __restrict__ codes, uint64_t ntext, int has_term, 
 void k3_extract_bwt(Stream & st, DevText const & T, uint64_t wstart, const uint32_t * sa, uint64_t m,
                     uint8_t * bwt, uint64_t shift, uint32_t * d_special) {
 	if (!m) return;
-	B3M_LAUNCH(st, k_extract_bwt, (unsigned)div_up(m, 256), 256, 0, T.codes, T.ntext, T.has_term, wstart,
+	B3M_LAUNCH_T(st, "extract_bwt", m * 37ull, k_extract_bwt, (unsigned)div_up(m, 256), 256, 0, T.codes, T.ntext, T.has_term, wstart,
 	           T.has_term ? 0 : 1, sa, m, bwt, shift, d_special);
 }
 
@@ -376,7 +376,7 @@ void k7_walk(Stream & st, DevDict const & D, const uint32_t * anchor_rank, uint6
 	if (!nanchors) return;
 	CTable C;
 	for (int i = 0; i < 257; ++i) C.c[i] = D.C[i];
-	B3M_LAUNCH(st, k_walk, (unsigned)div_up(nanchors, 256), 256, 0, make_view(D), C, D.exc_lf, anchor_rank, nanchors, arate, n,
+	B3M_LAUNCH_T(st, "lf_walk", n * 64ull, k_walk, (unsigned)div_up(nanchors, 256), 256, 0, make_view(D), C, D.exc_lf, anchor_rank, nanchors, arate, n,
 	           (uint32_t)(sarate - 1), ilog2_exact(sarate), (uint32_t)(isarate - 1), ilog2_exact(isarate),
 	           (unsigned long long *)sa_out, (unsigned long long *)isa_out);
 	if (ws) { ws->steps += n; ws->chains += nanchors; }

@@ -95,7 +95,7 @@ void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W,
 		RadixRec<2> cur{{key0.get(), sa}}, alt{{key1.get(), idx1.get()}};
 		unsigned const grid = (unsigned)div_up(W, 256);
 		TRACE("r0 alloc");
-		B3M_LAUNCH(st, k_make_keys, grid, 256, 0, v, bits, k0, nshort, cur.a[0], cur.a[1]);
+		B3M_LAUNCH_T(st, "make_keys", W * 9ull, k_make_keys, grid, 256, 0, v, bits, k0, nshort, cur.a[0], cur.a[1]);
 		S.other_bytes += W * (1ull + 8ull);
 		RadixStats rs;
 		TRACE("r0 make_keys");
@@ -121,7 +121,7 @@ void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W,
 				uint32_t const i = sidx[k];
 				rank[i] = head;
 				if (sa != sidx) sa[k] = i;
-			});
+			}, "heads_rank_scatter", W * 48ull);
 		S.other_bytes += W * (8ull + 8ull + 4ull + 4ull + 4ull);
 		TRACE("r0 heads+rank scatter");
 		// compaction of suffixes whose group has more than one member
@@ -161,7 +161,7 @@ void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W,
 	while (na) {
 		if (circular && h >= W) break; // non-primitive text: ties stay in current order (unpinned)
 		unsigned const grid = (unsigned)div_up(na, 256);
-		B3M_LAUNCH(st, k_gather_ahead, grid, 256, 0, (const uint32_t *)bufs[1], na, (const uint32_t *)rank, h, W, circular, bufs[2]);
+		B3M_LAUNCH_T(st, "gather_ahead", na * 40ull, k_gather_ahead, grid, 256, 0, (const uint32_t *)bufs[1], na, (const uint32_t *)rank, h, W, circular, bufs[2]);
 		S.other_bytes += na * (4ull + 32ull + 4ull);
 		TRACE("rN gather");
 		RadixRec<3> cur{{bufs[0], bufs[2], bufs[1]}}, alt{{bufs[3], bufs[4], bufs[5]}};

@@ -95,5 +95,18 @@ class Engine:
         self._check(self._lib.b3m_engine_lf_bench(self._h, nchains, steps, C.byref(ms), C.byref(cs)))
         return float(ms.value), int(cs.value)
 
+    def set_profile(self, on=True):
+        self._check(self._lib.b3m_engine_set_profile(self._h, 1 if on else 0))
+
+    def kernel_times(self):
+        """{name: {"launches": L, "ms": total ms, "bytes": algorithmic bytes}} since the last call."""
+        buf = C.create_string_buffer(1 << 16)
+        self._check(self._lib.b3m_engine_kernel_times(self._h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, cnt, ms, nbytes = line.rsplit(" ", 3)
+            out[name] = {"launches": int(cnt), "ms": float(ms), "bytes": int(nbytes)}
+        return out
+
     def sync(self):
         self._check(self._lib.b3m_engine_sync(self._h))

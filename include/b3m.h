@@ -160,6 +160,13 @@ int b3m_engine_lf_bench(b3m_engine * e, uint64_t nchains, uint64_t steps, float 
 /* wait for the engine's stream */
 int b3m_engine_sync(b3m_engine * e);
 
+/* Opt-in per-kernel timing for the roofline report: when on, the heavy kernels of the next
+ * builds are bracketed with CUDA events on the engine's stream.  b3m_engine_kernel_times()
+ * writes one line per kernel name, "name launches total_ms algorithmic_bytes\n", and clears
+ * the records. */
+int b3m_engine_set_profile(b3m_engine * e, int on);
+int b3m_engine_kernel_times(b3m_engine * e, char * buf, size_t buflen);
+
 #ifdef __cplusplus
 }
 #endif
