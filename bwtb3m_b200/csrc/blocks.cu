@@ -1,4 +1,396 @@
+// Multi-block path: block partition + bounded LCP (A4), leaf sorting with look-ahead, gt bits,
+// anchors (A5), z-ranks, K5 gap arrays by backward search (A7), K6 gap-driven merge (A8).
+// Replaces BwtMergeSortTemplate<InputTypes>::computeBwt's block / merge-tree stages reached from
+// /root/reference/src/bwtb3m.cpp:62-63 (libmaus2, absent); the identities every kernel
+// implements are SURVEY.md Appendix A.1-A.4 (brute-force checked there, restated on the CPU in
+// oracle/b3m_oracle.c: leaf_build, node_merge).
 #include "engine.h"
+#include "rankdict.cuh"
+#include "scan.cuh"
+#include <string.h>
+#include <algorithm>
+
 namespace b3m {
-void Engine::build_blocks(PhaseTimer &, uint32_t *) { throw Error("numblocks > 1 not implemented yet"); }
+
+// ------------------------------------------------------------------------------------------
+// circular text access; the implicit terminator of pacterm (position ntext) is a unique symbol
+// smaller than every code
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int text_sym(TextRef const & t, uint64_t p) {
+	return (t.has_term && p == t.ntext) ? -1 : (int)t.codes[p];
 }
+
+// lexicographic comparison of the rotations starting at a and b
+__device__ int cmp_rot(TextRef const & t, uint64_t a, uint64_t b) {
+	if (a == b) return 0;
+	for (uint64_t k = 0; k < t.n; ++k) {
+		int const x = text_sym(t, a), y = text_sym(t, b);
+		if (x != y) return x < y ? -1 : 1;
+		a = (a + 1 == t.n) ? 0 : a + 1;
+		b = (b + 1 == t.n) ? 0 : b + 1;
+	}
+	return 0;
+}
+
+// A4: lcpnext = max over i in [s,e), i != ep, of LCP(rot(i), rot(ep)), each LCP bounded by cap
+__global__ void __launch_bounds__(256)
+k_lcpnext(TextRef t, uint64_t s, uint64_t e, uint64_t ep, uint64_t cap, uint64_t skip_below, unsigned long long * __restrict__ out) {
+	uint64_t const i = s + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	uint64_t l = 0;
+	if (i < e && i != ep) {
+		uint64_t a = i, b = ep;
+		while (l < cap) {
+			int const x = text_sym(t, a), y = text_sym(t, b);
+			if (x != y || x < 0) break;
+			++l;
+			a = (a + 1 == t.n) ? 0 : a + 1;
+			b = (b + 1 == t.n) ? 0 : b + 1;
+		}
+		if (l < skip_below) l = 0;
+	}
+	// warp maximum, one atomic per warp
+	uint32_t lo = (uint32_t)l, hi = (uint32_t)(l >> 32);
+	uint32_t const mhi = __reduce_max_sync(0xffffffffu, hi);
+	lo = (hi == mhi) ? lo : 0u;
+	uint32_t const mlo = __reduce_max_sync(0xffffffffu, lo);
+	if ((threadIdx.x & 31) == 0) {
+		unsigned long long const m = ((unsigned long long)mhi << 32) | mlo;
+		if (m) atomicMax(out, m);
+	}
+}
+
+// leaf: block BWT from the block's own suffixes in sorted order; the block-start suffix gets
+// the placeholder code 0 (bwtterm of the reference) and its row is recorded
+__global__ void __launch_bounds__(256)
+k_leaf_emit(const uint8_t * __restrict__ codes, uint64_t s, const uint32_t * __restrict__ bsa, uint64_t mt, uint32_t shift,
+            uint8_t * __restrict__ L, uint32_t * __restrict__ special) {
+	uint64_t const k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= mt) return;
+	uint32_t const i = bsa[k];
+	uint8_t c = 0;
+	if (i == 0) special[0] = (uint32_t)k + shift; else c = codes[s + i - 1];
+	L[k + shift] = c;
+}
+
+// leaf: gt bits relative to the block start (Appendix A.3) and the (rank,pos) anchors
+__global__ void __launch_bounds__(256)
+k_leaf_gt_samples(const uint32_t * __restrict__ brank, uint64_t mt, uint32_t shift, uint64_t s, uint64_t ratemask, uint32_t rateshift,
+                  uint8_t * __restrict__ gt, uint32_t * __restrict__ prerank) {
+	uint64_t const i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= mt) return;
+	uint32_t const r = brank[i], r0 = brank[0];
+	gt[s + i] = r > r0;
+	uint64_t const p = s + i;
+	if ((p & ratemask) == 0) prerank[p >> rateshift] = r + shift;
+}
+
+// number of suffixes of one leaf that are smaller than rot(z), for the start point z of every chain
+__global__ void __launch_bounds__(128)
+k_zrank(TextRef t, const uint32_t * __restrict__ bsa, uint64_t mt, uint64_t s, uint64_t a1, uint64_t chl, uint64_t r1, uint64_t nch,
+        uint32_t * __restrict__ out) {
+	uint64_t const c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= nch) return;
+	uint64_t zhi = a1 + (c + 1) * chl;
+	if (zhi > r1) zhi = r1;
+	uint64_t const z = zhi == t.n ? 0 : zhi;
+	uint64_t lo = 0, hi = mt;
+	while (lo < hi) {
+		uint64_t const mid = (lo + hi) >> 1;
+		if (cmp_rot(t, s + bsa[mid], z) < 0) lo = mid + 1; else hi = mid;
+	}
+	out[c] += (uint32_t)lo;
+}
+
+// gt_R[r1] = [rot(r1) > rot(a1)] decided directly (oracle node_merge)
+__global__ void k_gt_top(TextRef t, uint64_t r1, uint64_t a1, uint32_t * __restrict__ special) {
+	special[2] = cmp_rot(t, r1 == t.n ? 0 : r1, a1) > 0 ? 1u : 0u;
+}
+
+// histogram of a text range (any alignment)
+__global__ void __launch_bounds__(256)
+k_hist_range(const uint8_t * __restrict__ in, uint64_t n, unsigned long long * __restrict__ hist) {
+	__shared__ uint32_t sh[256];
+	sh[threadIdx.x] = 0;
+	__syncthreads();
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) atomicAdd(&sh[in[i]], 1u);
+	__syncthreads();
+	if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: gap array.  One backward-search chain per thread over R's text, right to left
+// (Appendix A.2):  r <- C_A[c] + rank_c(L_A, r) + [c == T[a1-1] and gt_R[j]],  G[r]++ .
+// ------------------------------------------------------------------------------------------
+struct CTab { uint32_t c[257]; };
+
+__global__ void __launch_bounds__(256)
+k_gap(DictView D, CTab C, TextRef t, uint64_t a1, uint64_t r1, uint64_t chl, uint64_t nch, const uint32_t * __restrict__ r0,
+      const uint8_t * __restrict__ gt_in /* indexed by text position */, uint8_t * __restrict__ gt_out /* indexed by position - a1 */,
+      const uint32_t * __restrict__ special, uint32_t isa_a0, uint64_t ratemask, uint32_t rateshift,
+      uint32_t * __restrict__ G, uint32_t * __restrict__ rsamp /* indexed by position / rate */) {
+	uint64_t const c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= nch) return;
+	uint64_t const zlo = a1 + c * chl;
+	uint64_t zhi = zlo + chl;
+	if (zhi > r1) zhi = r1;
+	uint32_t const lastA = t.codes[a1 - 1];
+	uint32_t r = r0[c];
+	for (uint64_t j = zhi; j > zlo; --j) {
+		uint64_t const p = j - 1;
+		if (t.has_term && p == t.ntext) r = 0; // the terminator suffix is smaller than every suffix of A
+		else {
+			uint32_t const g = (j < r1) ? gt_in[j] : special[2];
+			uint32_t const c0 = t.codes[p];
+			r = C.c[c0] + dict_rank(D, c0, r) + ((c0 == lastA && g) ? 1u : 0u);
+		}
+		atomicAdd(&G[r], 1u);
+		gt_out[p - a1] = r > isa_a0; // Appendix A.3
+		if ((p & ratemask) == 0) rsamp[p >> rateshift] = r;
+	}
+}
+
+// ------------------------------------------------------------------------------------------
+// K6: merge by the gap array (Appendix A.4): exclusive scan of G, then for every k the G[k]
+// symbols of L_R followed by L_A[k]; G is left holding its inclusive prefix sums.
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t BIG_GAP = 512;
+struct BigGap { uint32_t src, dst, len; };
+
+__global__ void __launch_bounds__(256)
+k_copy_big(const BigGap * __restrict__ list, const uint32_t * __restrict__ count, const uint8_t * __restrict__ LR, uint8_t * __restrict__ M) {
+	uint32_t const n = *count;
+	for (uint32_t e = blockIdx.y; e < n; e += gridDim.y) {
+		BigGap const g = list[e];
+		for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < g.len; i += (uint64_t)gridDim.x * blockDim.x)
+			M[(uint64_t)g.dst + i] = LR[(uint64_t)g.src + i];
+	}
+}
+
+__global__ void __launch_bounds__(256)
+k_merge_samples(uint32_t * __restrict__ prerank, uint64_t qA0, uint64_t qA1, uint64_t qR1, const uint32_t * __restrict__ Sincl,
+                const uint32_t * __restrict__ rsamp) {
+	uint64_t const q = qA0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= qR1) return;
+	uint32_t const k = prerank[q];
+	prerank[q] = q < qA1 ? k + Sincl[k] : k + rsamp[q];
+}
+
+// ------------------------------------------------------------------------------------------
+struct EventAccum {
+	Stream & st;
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+	explicit EventAccum(Stream & s) : st(s) {}
+	~EventAccum() { for (auto & p : ev) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); } }
+	void begin() { cudaEvent_t a, b; B3M_CUDA(cudaEventCreate(&a)); B3M_CUDA(cudaEventCreate(&b)); B3M_CUDA(cudaEventRecord(a, st.s)); ev.push_back({a, b}); }
+	void end() { B3M_CUDA(cudaEventRecord(ev.back().second, st.s)); }
+	float total() { float t = 0; for (auto & p : ev) { float x = 0; cudaEventElapsedTime(&x, p.first, p.second); t += x; } return t; }
+};
+
+static TextRef text_ref(DevText const & T) { return TextRef{T.codes, T.ntext, T.n, T.has_term}; }
+
+static unsigned ilog2u(uint64_t v) { unsigned s = 0; while ((1ull << s) < v) ++s; return s; }
+
+uint32_t Engine::fetch_special(int slot) {
+	B3M_CUDA(cudaMemcpyAsync(pinned, d_special.get() + slot, 4, cudaMemcpyDeviceToHost, st.s));
+	B3M_CUDA(cudaStreamSynchronize(st.s));
+	return *(uint32_t *)pinned;
+}
+
+// A4 + A5: one leaf.  Sorts the block's suffixes with lcpnext+1 look-ahead symbols and emits
+// the block BWT into L (m codes), the gt bits and the anchors of the block.
+void Engine::leaf_build(BlockLeaf & leaf, uint64_t s, uint64_t m, uint8_t * L, uint32_t * term_pos, SortStats * ss) {
+	TextRef const t = text_ref(T);
+	uint64_t const e = s + m;
+	bool const has_termsuffix = T.has_term && e == T.n;     // the block holds the terminator suffix
+	uint64_t const mt = has_termsuffix ? m - 1 : m;         // suffixes that start with a stored symbol
+	uint32_t const shift = has_termsuffix ? 1 : 0;
+	uint64_t W = mt;
+	if (!has_termsuffix) {
+		// bounded first, exact only when the bound was hit (large-LCP escape, largelcpthres)
+		uint64_t const ep = e == T.n ? 0 : e;
+		uint64_t const cap = params.largelcpthres ? params.largelcpthres : 16384;
+		DevBuf<unsigned long long> dl(st, 1);
+		uint64_t lcpnext = 0;
+		for (int pass = 0; pass < 2; ++pass) {
+			B3M_CUDA(cudaMemsetAsync(dl.get(), 0, 8, st.s));
+			B3M_LAUNCH(st, k_lcpnext, (unsigned)div_up(m, 256), 256, 0, t, s, e, ep, pass ? T.n : cap, pass ? cap : 0, dl.get());
+			B3M_CUDA(cudaMemcpyAsync(pinned, dl.get(), 8, cudaMemcpyDeviceToHost, st.s));
+			B3M_CUDA(cudaStreamSynchronize(st.s));
+			lcpnext = std::max<uint64_t>(lcpnext, *(unsigned long long *)pinned);
+			if (lcpnext < cap) break;
+			++large_lcp_blocks;
+		}
+		max_lcpnext = std::max(max_lcpnext, lcpnext);
+		W = m + lcpnext + 1;
+		if (T.has_term) W = std::min(W, T.ntext - s); // the terminator ends every comparison
+	}
+	leaf.s = s; leaf.mt = mt;
+	if (mt) {
+		DevBuf<uint32_t> wrank(st, W);
+		{
+			DevBuf<uint32_t> wsa(st, W);
+			k2_suffix_sort(st, T, s, W, 0, T.has_term ? 0 : 1, wsa.get(), wrank.get(), ss);
+			leaf.sa.alloc(st, mt);
+			// keep the block's own suffixes, in order; wrank becomes the block-local rank by position
+			const uint32_t * sa = wsa.get();
+			uint32_t * bsa = leaf.sa.get();
+			uint32_t * br = wrank.get();
+			uint64_t const mtl = mt;
+			if (W == mt) {
+				B3M_CUDA(cudaMemcpyAsync(bsa, sa, 4 * mt, cudaMemcpyDeviceToDevice, st.s));
+			} else {
+				scan_apply<OpSum>(st, W,
+					[=] __device__(uint64_t k) -> uint32_t { return sa[k] < mtl ? 1u : 0u; },
+					[=] __device__(uint64_t k, uint32_t excl, uint32_t v) { if (v) { uint32_t const i = sa[k]; bsa[excl] = i; br[i] = excl; } });
+			}
+		}
+		B3M_LAUNCH(st, k_leaf_emit, (unsigned)div_up(mt, 256), 256, 0, T.codes, s, (const uint32_t *)leaf.sa.get(), mt, shift, L, d_special.get());
+		B3M_LAUNCH(st, k_leaf_gt_samples, (unsigned)div_up(mt, 256), 256, 0, (const uint32_t *)wrank.get(), mt, shift, s, prerate - 1, ilog2u(prerate),
+		           gt.get(), prerank.get());
+		extract_bytes += mt * (4 + 32 + 1 + 4 + 1);
+	}
+	if (has_termsuffix) {
+		// rank 0 is the terminator suffix; its predecessor is the last base (or it is the block start)
+		uint32_t const zero = 0;
+		if (mt) B3M_CUDA(cudaMemcpyAsync(L, T.codes + T.ntext - 1, 1, cudaMemcpyDeviceToDevice, st.s));
+		else {
+			B3M_CUDA(cudaMemsetAsync(L, 0, 1, st.s));
+			B3M_CUDA(cudaMemsetAsync(d_special.get(), 0, 4, st.s));
+		}
+		B3M_CUDA(cudaMemsetAsync(gt.get() + T.ntext, 0, 1, st.s));
+		if ((T.ntext & (prerate - 1)) == 0) B3M_CUDA(cudaMemcpyAsync(prerank.get() + T.ntext / prerate, &zero, 4, cudaMemcpyHostToDevice, st.s));
+	}
+	*term_pos = fetch_special(0);
+	if (!has_termsuffix) leaf.keep = true; else leaf.sa.release(); // the last block is never a left part
+}
+
+// A7 + A8: merge node A = [a0,a1) (left) with R = [a1,r1) (right) into M.
+void Engine::node_merge(BlockNode & A, BlockNode & R, std::vector<BlockLeaf> & leaves, BlockNode & M, EventAccum & tgap, EventAccum & tmerge) {
+	TextRef const t = text_ref(T);
+	uint64_t const a0 = A.a0, a1 = A.a1, r1 = R.a1;
+	uint64_t const na = a1 - a0, nr = r1 - a1;
+	B3M_REQUIRE(R.a0 == a1, "internal: merge of non-adjacent nodes");
+	int const flavour = T.sigma <= 4 ? 2 : 8;
+
+	tgap.begin();
+	// rank dictionary over L_A; the placeholder of A's block-start row is excluded from counts
+	DevBuf<uint8_t> dlines(st, dict_bytes(flavour, na, T.sigma));
+	k4_build_dict(st, A.L.get(), na, flavour, T.sigma, dlines.get());
+	DictView D;
+	D.base = dlines.get(); D.flavour = (uint32_t)flavour; D.spad = d8_spad(T.sigma);
+	D.stride = flavour == 2 ? 64u : 4u * D.spad + D8_SYMS;
+	D.exc_pos = A.term; D.exc_code = 0;
+	// C_A counted over A's text (Appendix A.2)
+	CTab C;
+	{
+		DevBuf<unsigned long long> dh(st, 256);
+		B3M_CUDA(cudaMemsetAsync(dh.get(), 0, 256 * 8, st.s));
+		unsigned const grid = (unsigned)std::min<uint64_t>(div_up(na, 256 * 64), (uint64_t)st.sms * 8);
+		B3M_LAUNCH(st, k_hist_range, grid ? grid : 1, 256, 0, T.codes + a0, na, dh.get());
+		B3M_CUDA(cudaMemcpyAsync(pinned, dh.get(), 256 * 8, cudaMemcpyDeviceToHost, st.s));
+		B3M_CUDA(cudaStreamSynchronize(st.s));
+		uint64_t acc = 0;
+		for (int c = 0; c < 257; ++c) { C.c[c] = (uint32_t)acc; if (c < 256) acc += ((unsigned long long *)pinned)[c]; }
+	}
+	// chains: R's text is split into nch pieces; the start rank of each piece is the sum of the
+	// z-ranks of A's leaves
+	uint64_t nch = std::min<uint64_t>(std::max<uint64_t>(nr / 64, 1), (uint64_t)st.sms * 2048 * 2);
+	uint64_t const chl = div_up(nr, nch);
+	nch = div_up(nr, chl);
+	DevBuf<uint32_t> r0(st, nch);
+	B3M_CUDA(cudaMemsetAsync(r0.get(), 0, 4 * nch, st.s));
+	for (auto & lf : leaves)
+		if (lf.keep && lf.s >= a0 && lf.s < a1 && lf.mt)
+			B3M_LAUNCH(st, k_zrank, (unsigned)div_up(nch, 128), 128, 0, t, (const uint32_t *)lf.sa.get(), lf.mt, lf.s, a1, chl, r1, nch, r0.get());
+	if (!(T.has_term && r1 == T.n)) B3M_LAUNCH(st, k_gt_top, 1, 1, 0, t, r1, a1, d_special.get());
+	DevBuf<uint32_t> G(st, na + 1);
+	DevBuf<uint8_t> gtnew(st, nr);
+	B3M_CUDA(cudaMemsetAsync(G.get(), 0, 4 * (na + 1), st.s));
+	B3M_LAUNCH_T(st, "gap_chains", nr * 128ull, k_gap, (unsigned)div_up(nch, 256), 256, 0, D, C, t, a1, r1, chl, nch, (const uint32_t *)r0.get(),
+	             (const uint8_t *)gt.get(), gtnew.get(), (const uint32_t *)d_special.get(), A.term, prerate - 1, ilog2u(prerate), G.get(), rsamp.get());
+	B3M_CUDA(cudaMemcpyAsync(gt.get() + a1, gtnew.get(), nr, cudaMemcpyDeviceToDevice, st.s));
+	gap_lf_steps += nr; gap_chains += nch;
+	tgap.end();
+
+	tmerge.begin();
+	// the stale placeholder of R becomes the true seam symbol T[a1-1] (Appendix A.4)
+	B3M_CUDA(cudaMemcpyAsync(R.L.get() + R.term, T.codes + a1 - 1, 1, cudaMemcpyDeviceToDevice, st.s));
+	M.a0 = a0; M.a1 = r1;
+	M.L.alloc(st, na + nr + 16);
+	DevBuf<BigGap> big(st, nr / BIG_GAP + 2);
+	uint32_t * bigcount = d_special.get() + 3;
+	B3M_CUDA(cudaMemsetAsync(bigcount, 0, 4, st.s));
+	{
+		uint32_t * g = G.get();
+		const uint8_t * LA = A.L.get();
+		const uint8_t * LR = R.L.get();
+		uint8_t * LM = M.L.get();
+		BigGap * bl = big.get();
+		uint64_t const nal = na;
+		scan_apply<OpSum>(st, na + 1,
+			[=] __device__(uint64_t k) -> uint32_t { return g[k]; },
+			[=] __device__(uint64_t k, uint32_t excl, uint32_t v) {
+				uint64_t const o = k + excl;
+				if (v <= BIG_GAP) { for (uint32_t x = 0; x < v; ++x) LM[o + x] = LR[excl + x]; }
+				else { uint32_t const e = atomicAdd(bigcount, 1u); bl[e] = BigGap{excl, (uint32_t)o, v}; }
+				if (k < nal) LM[o + v] = LA[k];
+				g[k] = excl + v;
+			}, "merge_scatter", 8ull * (na + 1) + 2ull * (na + nr));
+		B3M_LAUNCH(st, k_copy_big, dim3((unsigned)st.sms, 64), 256, 0, (const BigGap *)bl, (const uint32_t *)bigcount, LR, LM);
+	}
+	// anchors and the row of the merged node's block-start suffix move by the same rank maps
+	uint64_t const qA0 = div_up(a0, prerate), qA1 = div_up(a1, prerate), qR1 = div_up(r1, prerate);
+	if (qR1 > qA0)
+		B3M_LAUNCH(st, k_merge_samples, (unsigned)div_up(qR1 - qA0, 256), 256, 0, prerank.get(), qA0, qA1, qR1, (const uint32_t *)G.get(), (const uint32_t *)rsamp.get());
+	B3M_CUDA(cudaMemcpyAsync(pinned, G.get() + A.term, 4, cudaMemcpyDeviceToHost, st.s));
+	B3M_CUDA(cudaStreamSynchronize(st.s));
+	M.term = A.term + *(uint32_t *)pinned;
+	merge_bytes += 8ull * (na + 1) + 2ull * (na + nr);
+	tmerge.end();
+	A.L.release(); R.L.release();
+}
+
+void Engine::build_tree(std::vector<BlockLeaf> & leaves, uint64_t lo, uint64_t hi, uint64_t bs, BlockNode & out,
+                        EventAccum & tsort, EventAccum & tgap, EventAccum & tmerge) {
+	if (hi - lo == 1) {
+		uint64_t const s = lo * bs, e = std::min(s + bs, T.n);
+		out.a0 = s; out.a1 = e;
+		out.L.alloc(st, e - s + 16);
+		tsort.begin();
+		leaf_build(leaves[lo], s, e - s, out.L.get(), &out.term, &sortstats);
+		tsort.end();
+		return;
+	}
+	uint64_t const mid = (lo + hi) / 2;
+	BlockNode A, R;
+	build_tree(leaves, lo, mid, bs, A, tsort, tgap, tmerge);
+	build_tree(leaves, mid, hi, bs, R, tsort, tgap, tmerge);
+	node_merge(A, R, leaves, out, tgap, tmerge);
+}
+
+void Engine::build_blocks(PhaseTimer & pt, uint32_t * exc_pos) {
+	uint64_t const bs = div_up(T.n, numblocks);
+	numblocks = div_up(T.n, bs);
+	B3M_REQUIRE(numblocks >= 2, "internal: build_blocks needs at least two blocks");
+	gt.alloc(st, T.n);
+	rsamp.alloc(st, npre);
+	std::vector<BlockLeaf> leaves(numblocks);
+	EventAccum tsort(st), tgap(st), tmerge(st);
+	BlockNode root;
+	sortstats = SortStats();
+	build_tree(leaves, 0, numblocks, bs, root, tsort, tgap, tmerge);
+	leaves.clear();
+	gt.release(); rsamp.release();
+	// root: the remaining placeholder is the row of suffix 0 (Appendix A.4)
+	if (T.has_term) *exc_pos = root.term;
+	else {
+		B3M_CUDA(cudaMemcpyAsync(root.L.get() + root.term, T.codes + T.n - 1, 1, cudaMemcpyDeviceToDevice, st.s));
+		*exc_pos = 0xffffffffu;
+	}
+	bwt = std::move(root.L);
+	B3M_CUDA(cudaStreamSynchronize(st.s));
+	ms_sort = tsort.total(); ms_gap = tgap.total(); ms_merge = tmerge.total(); ms_extract = 0;
+	(void)pt;
+}
+
+} // namespace b3m

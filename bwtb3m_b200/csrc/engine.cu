@@ -10,15 +10,6 @@
 namespace b3m {
 
 // ------------------------------------------------------------------------------------------
-struct PhaseTimer {
-	Stream & st;
-	cudaEvent_t ev[16];
-	int n = 0;
-	explicit PhaseTimer(Stream & s) : st(s) { for (auto & e : ev) B3M_CUDA(cudaEventCreate(&e)); }
-	~PhaseTimer() { for (auto & e : ev) cudaEventDestroy(e); }
-	void mark() { B3M_CUDA(cudaEventRecord(ev[n++], st.s)); }
-	float ms(int a, int b) { float t = 0; cudaEventElapsedTime(&t, ev[a], ev[b]); return t; }
-};
 
 Engine::Engine(int dev, void * stream) : device(dev) {
 	B3M_CUDA(cudaSetDevice(device));
@@ -211,13 +202,13 @@ void Engine::build(b3m_build_params const & p) {
 	B3M_REQUIRE(pow2(prerate), "preisarate must be a power of two");
 	npre = div_up(T.n, prerate);
 	sortstats = SortStats(); walkstats = WalkStats();
-	gap_lf_steps = gap_chains = merge_bytes = extract_bytes = 0; max_lcpnext = 0;
+	gap_lf_steps = gap_chains = merge_bytes = extract_bytes = 0; max_lcpnext = large_lcp_blocks = 0;
 	ms_sort = ms_extract = ms_dict = ms_gap = ms_merge = ms_walk = 0;
 	numblocks = std::min<uint64_t>(p.numblocks, T.n);
 
 	PhaseTimer pt(st);
 	pt.mark(); // 0
-	d_special.alloc(st, 4);
+	d_special.alloc(st, 8);
 	B3M_CUDA(cudaMemsetAsync(d_special.get(), 0xff, 16, st.s));
 	bwt.alloc(st, T.n + 16);
 	prerank.alloc(st, npre);
@@ -243,7 +234,8 @@ void Engine::build(b3m_build_params const & p) {
 		pt.mark(); // 2
 		ms_sort = -1; // filled below
 	} else {
-		build_blocks(pt, &exc_pos); // marks 1 (leaves+merges split inside) and 2
+		build_blocks(pt, &exc_pos);
+		pt.mark(); pt.mark(); // 1, 2: the phases are timed inside build_blocks
 	}
 	root_exc_pos = exc_pos;
 	make_dict(exc_pos, 0, 0);

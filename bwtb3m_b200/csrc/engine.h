@@ -5,7 +5,30 @@
 
 namespace b3m {
 
-struct PhaseTimer;
+struct PhaseTimer {
+	Stream & st;
+	cudaEvent_t ev[16];
+	int n = 0;
+	explicit PhaseTimer(Stream & s) : st(s) { for (auto & e : ev) B3M_CUDA(cudaEventCreate(&e)); }
+	~PhaseTimer() { for (auto & e : ev) cudaEventDestroy(e); }
+	void mark() { B3M_CUDA(cudaEventRecord(ev[n++], st.s)); }
+	float ms(int a, int b) { float t = 0; cudaEventElapsedTime(&t, ev[a], ev[b]); return t; }
+};
+struct EventAccum;
+
+// one leaf of the merge tree: the block's own suffixes in sorted order (kept for z-ranks)
+struct BlockLeaf {
+	uint64_t s = 0, mt = 0;
+	bool keep = false;
+	DevBuf<uint32_t> sa; // block-relative start positions
+};
+// a node of the merge tree over the text range [a0,a1): its BWT with a placeholder (code 0) at
+// row `term`, the rank of the suffix starting at a0 (the reference's bwtterm row)
+struct BlockNode {
+	uint64_t a0 = 0, a1 = 0;
+	uint32_t term = 0;
+	DevBuf<uint8_t> L;
+};
 
 struct Engine {
 	int device = 0;
@@ -34,6 +57,8 @@ struct Engine {
 	DevBuf<uint64_t> sa, isa;
 	DevBuf<uint8_t> dict;
 	DevBuf<uint32_t> d_special;
+	DevBuf<uint8_t> gt;         // multi-block: gt[i] = [rot(i) > rot(start of i's current node)]
+	DevBuf<uint32_t> rsamp;     // multi-block: r(j) at the anchors of the right part of a merge
 	DevDict D;
 	uint32_t root_exc_pos = 0xffffffffu;
 
@@ -41,7 +66,7 @@ struct Engine {
 	SortStats sortstats;
 	WalkStats walkstats;
 	uint64_t gap_lf_steps = 0, gap_chains = 0, merge_bytes = 0, extract_bytes = 0, dict_bytes_moved = 0, decode_bytes = 0;
-	uint64_t max_lcpnext = 0;
+	uint64_t max_lcpnext = 0, large_lcp_blocks = 0;
 	float ms_decode = 0, ms_sort = 0, ms_extract = 0, ms_dict = 0, ms_gap = 0, ms_merge = 0, ms_walk = 0, ms_total = 0;
 
 	Engine(int dev, void * stream);
@@ -50,6 +75,11 @@ struct Engine {
 	void load(const void * input, uint64_t nbytes, int itype, bool on_device);
 	void build(b3m_build_params const & p);
 	void build_blocks(PhaseTimer & pt, uint32_t * exc_pos);
+	void build_tree(std::vector<BlockLeaf> & leaves, uint64_t lo, uint64_t hi, uint64_t bs, BlockNode & out,
+	                EventAccum & tsort, EventAccum & tgap, EventAccum & tmerge);
+	void leaf_build(BlockLeaf & leaf, uint64_t s, uint64_t m, uint8_t * L, uint32_t * term_pos, SortStats * ss);
+	void node_merge(BlockNode & A, BlockNode & R, std::vector<BlockLeaf> & leaves, BlockNode & M, EventAccum & tgap, EventAccum & tmerge);
+	uint32_t fetch_special(int slot);
 	void make_dict(uint32_t exc_pos, uint32_t exc_code, uint32_t exc_lf);
 	void fetch(uint8_t * h_bwt, uint64_t * h_pairs, uint64_t * h_sa, uint64_t * h_isa);
 	void info(b3m_info * o);

@@ -18,6 +18,13 @@ struct DevText {
 	unsigned keybits = 8;   // bits per code inside sort keys (2, 4 or 8)
 };
 
+// what the block-level kernels need to read the circular text
+struct TextRef {
+	const uint8_t * codes;
+	uint64_t ntext, n;
+	int has_term;
+};
+
 // ---- K1 ---------------------------------------------------------------------------------
 void k1_hist_bytes(Stream & st, const uint8_t * d_in, uint64_t nbytes, uint64_t * d_hist256);
 void k1_map_bytes(Stream & st, const uint8_t * d_in, uint64_t n, const uint8_t * d_lut256, uint8_t * d_out);

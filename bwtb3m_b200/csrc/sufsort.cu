@@ -214,7 +214,11 @@ void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W,
 		na = nn;
 		h *= 2;
 	}
-	if (stats) *stats = S;
+	if (stats) { // accumulated over the leaves of a multi-block build
+		stats->rounds = stats->rounds > S.rounds ? stats->rounds : S.rounds;
+		stats->radix_passes += S.radix_passes; stats->radix_bytes += S.radix_bytes;
+		stats->active_sum += S.active_sum; stats->other_bytes += S.other_bytes;
+	}
 }
 
 } // namespace b3m
