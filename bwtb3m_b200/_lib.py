@@ -54,7 +54,8 @@ EXPORTS = [
     "b3m_engine_create", "b3m_engine_destroy", "b3m_engine_last_error", "b3m_engine_load_host",
     "b3m_engine_load_device", "b3m_engine_build", "b3m_engine_info", "b3m_engine_fetch",
     "b3m_engine_device_results", "b3m_engine_lf_bench", "b3m_engine_sync", "b3m_engine_set_profile",
-    "b3m_engine_kernel_times",
+    "b3m_engine_kernel_times", "b3m_engine_write_bwt", "b3m_engine_fetch_runs", "b3m_engine_ssa_from_bwt",
+    "b3m_bwt_length", "b3m_bwt_decode", "b3m_bwt_encode_host",
 ]
 
 _lib = None
@@ -85,7 +86,13 @@ def lib():
     L.b3m_engine_sync.argtypes = [vp]
     L.b3m_engine_set_profile.argtypes = [vp, C.c_int]
     L.b3m_engine_kernel_times.argtypes = [vp, C.c_char_p, C.c_size_t]
-    if hasattr(L, "b3m_options_init"):
+    L.b3m_engine_write_bwt.argtypes = [vp, C.c_char_p]
+    L.b3m_engine_fetch_runs.argtypes = [vp, vp, vp, u64, u64p]
+    L.b3m_engine_ssa_from_bwt.argtypes = [vp, vp, u64, vp, u64, u64, u64]
+    L.b3m_bwt_length.argtypes = [C.c_char_p, u64p, C.c_char_p, C.c_size_t]
+    L.b3m_bwt_decode.argtypes = [C.c_char_p, vp, u64, u64, C.c_char_p, C.c_size_t]
+    L.b3m_bwt_encode_host.argtypes = [C.c_char_p, vp, u64, C.c_char_p, C.c_size_t]
+    if True:
         L.b3m_options_init.argtypes = [C.POINTER(Options)]
         L.b3m_options_init.restype = None
         L.b3m_compute_bwt.argtypes = [C.POINTER(Options), C.POINTER(Result), C.c_char_p, C.c_size_t]

@@ -34,6 +34,7 @@ Engine::~Engine() {
 }
 
 void Engine::reset_results() {
+	ssa_only = false;
 	bwt.release(); prerank.release(); sa.release(); isa.release(); dict.release();
 	have_results = false;
 }
@@ -261,14 +262,10 @@ void Engine::build(b3m_build_params const & p) {
 void Engine::fetch(uint8_t * h_bwt, uint64_t * h_pairs, uint64_t * h_sa, uint64_t * h_isa) {
 	B3M_CUDA(cudaSetDevice(device));
 	B3M_REQUIRE(have_results, "no results");
+	B3M_REQUIRE(!(ssa_only && (h_bwt || h_pairs)), "the engine holds sampled SA/ISA only (computed from an existing BWT)");
 	if (h_bwt) {
-		DevBuf<uint8_t> out(st, T.n + 16), dlut(st, 256);
-		uint8_t lut[256];
-		memset(lut, 0, 256);
-		for (uint32_t c = 0; c < T.sigma; ++c) lut[c] = code2sym[c];
-		B3M_CUDA(cudaMemcpyAsync(dlut.get(), lut, 256, cudaMemcpyHostToDevice, st.s));
-		k1_map_bytes(st, bwt.get(), T.n, dlut.get(), out.get());
-		if (T.has_term) B3M_CUDA(cudaMemsetAsync(out.get() + root_exc_pos, 0, 1, st.s));
+		DevBuf<uint8_t> out;
+		symbols_device(out);
 		B3M_CUDA(cudaMemcpyAsync(h_bwt, out.get(), T.n, cudaMemcpyDeviceToHost, st.s));
 		B3M_CUDA(cudaStreamSynchronize(st.s));
 	}
@@ -298,6 +295,115 @@ void Engine::info(b3m_info * o) {
 	o->launches = st.launches; o->max_lcpnext = max_lcpnext;
 	o->ms_decode = ms_decode; o->ms_sort = ms_sort; o->ms_extract = ms_extract; o->ms_dict = ms_dict;
 	o->ms_gap = ms_gap; o->ms_merge = ms_merge; o->ms_walk = ms_walk; o->ms_total = ms_total;
+}
+
+// ------------------------------------------------------------------------------------------
+// bwtcomputessa path: sampled SA/ISA from an existing BWT and (rank,pos) anchors
+// (replaces BwtComputeSSA::computeSSA, /root/reference/src/bwtcomputessa.cpp:51; the walk is
+//  /root/reference/src/hwtPreIsaToIsa.cpp:79,114-161: anchors sorted by position, each walks
+//  back to its predecessor)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_find_byte(const uint8_t * __restrict__ s, uint64_t n, uint32_t v, uint32_t * __restrict__ out) {
+	uint64_t const i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n && s[i] == v) *out = (uint32_t)i;
+}
+
+void Engine::ssa_from_bwt(const uint8_t * h_bwt, uint64_t n, const uint64_t * h_pairs, uint64_t npairs, uint64_t sarate, uint64_t isarate) {
+	B3M_CUDA(cudaSetDevice(device));
+	B3M_REQUIRE(n > 0 && n < 0xFFFFFFF0ull, "BWT length out of range");
+	B3M_REQUIRE(npairs > 0, "no (rank,pos) anchors: the .preisa file is empty");
+	auto pow2 = [](uint64_t v) { return v && !(v & (v - 1)); };
+	B3M_REQUIRE(pow2(sarate) && pow2(isarate), "sampling rates must be powers of two");
+	reset_results();
+	codes.release(); raw.release(); d_hist.release(); d_special.release();
+	loaded = false;
+	arena.reserve((size_t)(n * 4 + 16 * npairs + (64u << 20)));
+	PhaseTimer pt(st);
+	pt.mark();
+	raw.alloc(st, n + 16);
+	B3M_CUDA(cudaMemcpyAsync(raw.get(), h_bwt, n, cudaMemcpyHostToDevice, st.s));
+	d_hist.alloc(st, 256);
+	d_special.alloc(st, 8);
+	k1_hist_bytes(st, raw.get(), n, d_hist.get());
+	B3M_CUDA(cudaMemcpyAsync(pinned, d_hist.get(), 256 * 8, cudaMemcpyDeviceToHost, st.s));
+	B3M_CUDA(cudaStreamSynchronize(st.s));
+	memcpy(hist, pinned, sizeof(hist));
+	// dense codes; a symbol that occurs once (pacterm's terminator) is kept out of a 4-symbol
+	// alphabet so that the 2-bit dictionary can be used
+	int distinct = 0, unique_sym = -1;
+	for (int c = 0; c < 256; ++c) if (hist[c]) { ++distinct; if (hist[c] == 1 && unique_sym < 0) unique_sym = c; }
+	bool const use_exc = distinct == 5 && unique_sym >= 0;
+	uint8_t lut[256];
+	memset(lut, 0, sizeof(lut));
+	uint32_t sigma = 0;
+	uint64_t acc = 0, csym[257];
+	for (int c = 0; c < 256; ++c) { csym[c] = acc; acc += hist[c]; }
+	D = DevDict();
+	for (int c = 0; c < 256; ++c) if (hist[c] && !(use_exc && c == unique_sym)) { lut[c] = (uint8_t)sigma; code2sym[sigma] = (uint8_t)c; D.C[sigma] = (uint32_t)csym[c]; ++sigma; }
+	for (uint32_t c = sigma; c < 257; ++c) D.C[c] = (uint32_t)n;
+	uint32_t exc_pos = 0xffffffffu;
+	if (use_exc) {
+		B3M_CUDA(cudaMemsetAsync(d_special.get(), 0xff, 4, st.s));
+		B3M_LAUNCH(st, k_find_byte, (unsigned)div_up(n, 256), 256, 0, (const uint8_t *)raw.get(), n, (uint32_t)unique_sym, d_special.get());
+		exc_pos = fetch_special(0);
+		B3M_REQUIRE(exc_pos != 0xffffffffu, "internal: unique symbol not found");
+	}
+	T = DevText();
+	T.n = n; T.ntext = n; T.sigma = sigma; T.has_term = 0; T.keybits = 8;
+	bwt.alloc(st, n + 16);
+	{
+		memcpy(pinned, lut, 256);
+		DevBuf<uint8_t> dlut(st, 256);
+		B3M_CUDA(cudaMemcpyAsync(dlut.get(), pinned, 256, cudaMemcpyHostToDevice, st.s));
+		k1_map_bytes(st, raw.get(), n, dlut.get(), bwt.get());
+		B3M_CUDA(cudaStreamSynchronize(st.s));
+	}
+	raw.release();
+	int const flavour = sigma <= 4 ? 2 : 8;
+	size_t const bytes = dict_bytes(flavour, n, sigma);
+	dict.alloc(st, bytes);
+	k4_build_dict(st, bwt.get(), n, flavour, sigma, dict.get());
+	D.flavour = flavour; D.n = n; D.lines = dict.get(); D.sigma = sigma;
+	D.exc_pos = exc_pos; D.exc_code = 0; D.exc_lf = use_exc ? (uint32_t)csym[unique_sym] : 0;
+	dict_bytes_moved = n + bytes;
+	pt.mark();
+	// anchors sorted by position; each walks back to its predecessor
+	std::vector<std::pair<uint64_t, uint64_t>> A(npairs);
+	for (uint64_t k = 0; k < npairs; ++k) {
+		A[k] = std::make_pair(h_pairs[2 * k + 1], h_pairs[2 * k]);
+		B3M_REQUIRE(A[k].first < n && A[k].second < n, "anchor out of range in .preisa");
+	}
+	std::sort(A.begin(), A.end());
+	std::vector<uint32_t> ar(npairs);
+	std::vector<uint64_t> ap(npairs), as(npairs);
+	for (uint64_t k = 0; k < npairs; ++k) {
+		uint64_t const prev = A[(k + npairs - 1) % npairs].first;
+		uint64_t todo = (A[k].first + n - prev) % n;
+		if (todo == 0) todo = npairs == 1 ? n : 0;
+		ar[k] = (uint32_t)A[k].second; ap[k] = A[k].first; as[k] = todo;
+	}
+	DevBuf<uint32_t> dar(st, npairs);
+	DevBuf<uint64_t> dap(st, npairs), das(st, npairs);
+	B3M_CUDA(cudaMemcpyAsync(dar.get(), ar.data(), 4 * npairs, cudaMemcpyHostToDevice, st.s));
+	B3M_CUDA(cudaMemcpyAsync(dap.get(), ap.data(), 8 * npairs, cudaMemcpyHostToDevice, st.s));
+	B3M_CUDA(cudaMemcpyAsync(das.get(), as.data(), 8 * npairs, cudaMemcpyHostToDevice, st.s));
+	params = b3m_build_params();
+	params.sasamplingrate = sarate; params.isasamplingrate = isarate;
+	nsa = div_up(n, sarate); nisa = div_up(n, isarate);
+	sa.alloc(st, nsa); isa.alloc(st, nisa);
+	B3M_LAUNCH(st, k_fill_u64, (unsigned)div_up(nsa, 256), 256, 0, (unsigned long long *)sa.get(), nsa, ~0ull);
+	B3M_LAUNCH(st, k_fill_u64, (unsigned)div_up(nisa, 256), 256, 0, (unsigned long long *)isa.get(), nisa, ~0ull);
+	walkstats = WalkStats();
+	k7_walk_anchors(st, D, dar.get(), dap.get(), das.get(), npairs, n, sarate, isarate, sa.get(), isa.get(), &walkstats);
+	pt.mark();
+	B3M_CUDA(cudaStreamSynchronize(st.s));
+	ms_dict = pt.ms(0, 1); ms_walk = pt.ms(1, 2); ms_total = pt.ms(0, 2);
+	ms_decode = ms_sort = ms_extract = ms_gap = ms_merge = 0;
+	npre = 0; prerate = 0; numblocks = 0;
+	root_exc_pos = 0xffffffffu;
+	ssa_only = true;
+	have_results = true;
 }
 
 __global__ void __launch_bounds__(256)
@@ -410,6 +516,15 @@ int b3m_engine_device_results(b3m_engine * h, const void ** d_bwt_codes, const v
 		if (d_sa) *d_sa = h->e->sa.get();
 		if (d_isa) *d_isa = h->e->isa.get();
 	});
+}
+int b3m_engine_write_bwt(b3m_engine * h, const char * bwtfn) {
+	B3M_GUARD(h, { if (!bwtfn) throw b3m::Error("null file name"); h->e->write_bwt(bwtfn); });
+}
+int b3m_engine_fetch_runs(b3m_engine * h, uint8_t * syms, uint64_t * lens, uint64_t cap, uint64_t * nruns) {
+	B3M_GUARD(h, h->e->fetch_runs(syms, lens, cap, nruns));
+}
+int b3m_engine_ssa_from_bwt(b3m_engine * h, const uint8_t * bwt, uint64_t n, const uint64_t * pairs, uint64_t npairs, uint64_t sarate, uint64_t isarate) {
+	B3M_GUARD(h, { if (!bwt || !pairs) throw b3m::Error("null argument"); h->e->ssa_from_bwt(bwt, n, pairs, npairs, sarate, isarate); });
 }
 int b3m_engine_lf_bench(b3m_engine * h, uint64_t nchains, uint64_t steps, float * ms, uint64_t * checksum) {
 	B3M_GUARD(h, { float t = 0; h->e->lf_bench(nchains, steps, &t, checksum); if (ms) *ms = t; });

@@ -49,6 +49,7 @@ struct Engine {
 
 	// results of the last build
 	bool have_results = false;
+	bool ssa_only = false;     // results come from ssa_from_bwt: only sa/isa can be fetched
 	b3m_build_params params{};
 	uint64_t numblocks = 1;
 	uint64_t prerate = 0, npre = 0, nsa = 0, nisa = 0;
@@ -80,6 +81,14 @@ struct Engine {
 	void leaf_build(BlockLeaf & leaf, uint64_t s, uint64_t m, uint8_t * L, uint32_t * term_pos, SortStats * ss);
 	void node_merge(BlockNode & A, BlockNode & R, std::vector<BlockLeaf> & leaves, BlockNode & M, EventAccum & tgap, EventAccum & tmerge);
 	uint32_t fetch_special(int slot);
+	// K8 / output side
+	uint64_t rl_bytes = 0, rl_nruns = 0;
+	void symbols_device(DevBuf<uint8_t> & out);
+	uint64_t rl_runs(const uint8_t * s, DevBuf<uint32_t> & start);
+	void write_bwt(const char * fn);
+	void fetch_runs(uint8_t * h_sym, uint64_t * h_len, uint64_t cap, uint64_t * nruns_out);
+	// sampled SA/ISA from an existing BWT and (rank,pos) anchors (bwtcomputessa path)
+	void ssa_from_bwt(const uint8_t * h_bwt, uint64_t n, const uint64_t * h_pairs, uint64_t npairs, uint64_t sarate, uint64_t isarate);
 	void make_dict(uint32_t exc_pos, uint32_t exc_code, uint32_t exc_lf);
 	void fetch(uint8_t * h_bwt, uint64_t * h_pairs, uint64_t * h_sa, uint64_t * h_isa);
 	void info(b3m_info * o);

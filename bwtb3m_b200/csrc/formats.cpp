@@ -217,22 +217,30 @@ static void serialise_table(std::vector<uint8_t> & o, HuffCode const & h) {
 
 static const char RL_MAGIC[8] = {'B', '3', 'M', 'R', 'L', '0', '1', 0};
 
-void rl_write_container(std::string const & fn, RlHeader const & h, const uint64_t * payload, uint64_t nwords,
-                        const uint64_t * block_word_off, const uint64_t * block_sym_off) {
+struct RlContainerWriter::Impl {
+	File f;
+	RlHeader h;
+	uint64_t hdbytes = 0, paybytes = 0;
+	Impl(std::string const & fn, RlHeader const & hh) : f(fn, "wb"), h(hh) {}
+};
+RlContainerWriter::RlContainerWriter(std::string const & fn, RlHeader const & h) : impl(new Impl(fn, h)) {
 	std::vector<uint8_t> hd(RL_MAGIC, RL_MAGIC + 8);
 	put_be64(hd, h.n); put_be64(hd, h.nruns); put_be64(hd, h.runs_per_block); put_be64(hd, h.nblocks);
 	serialise_table(hd, h.sym);
 	serialise_table(hd, h.len);
 	while (hd.size() % 8) hd.push_back(0);
+	impl->f.write(hd.data(), hd.size());
+	impl->hdbytes = hd.size();
+}
+RlContainerWriter::~RlContainerWriter() {}
+void RlContainerWriter::payload(const void * bytes, size_t nbytes) { impl->f.write(bytes, nbytes); impl->paybytes += nbytes; }
+void RlContainerWriter::finish(const uint64_t * block_word_off, const uint64_t * block_sym_off) {
 	std::vector<uint8_t> idx;
-	idx.reserve(16 * h.nblocks + 8);
-	for (uint64_t b = 0; b < h.nblocks; ++b) { put_be64(idx, block_word_off[b]); put_be64(idx, block_sym_off[b]); }
-	put_be64(idx, hd.size() + 8 * nwords);
-	File f(fn, "wb");
-	f.write(hd.data(), hd.size());
-	f.write(payload, 8 * nwords);
-	f.write(idx.data(), idx.size());
-	f.close();
+	idx.reserve(16 * impl->h.nblocks + 8);
+	for (uint64_t b = 0; b < impl->h.nblocks; ++b) { put_be64(idx, block_word_off[b]); put_be64(idx, block_sym_off[b]); }
+	put_be64(idx, impl->hdbytes + impl->paybytes);
+	impl->f.write(idx.data(), idx.size());
+	impl->f.close();
 }
 
 static inline unsigned bitlen64(uint64_t v) { unsigned b = 0; while (v) { ++b; v >>= 1; } return b; }
@@ -271,7 +279,9 @@ void rl_encode_host(std::string const & fn, const uint8_t * syms, uint64_t n) {
 		}
 		bw.align64();
 	}
-	rl_write_container(fn, h, (const uint64_t *)payload.data(), payload.size() / 8, woff.data(), soff.data());
+	RlContainerWriter wr(fn, h);
+	wr.payload(payload.data(), payload.size());
+	wr.finish(woff.data(), soff.data());
 }
 
 // ---- reader -----------------------------------------------------------------------------------

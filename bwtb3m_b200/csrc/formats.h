@@ -75,9 +75,18 @@ struct RlHeader {
 	HuffCode sym, len;
 };
 
-// writer used by the device encoder (K8): the payload words are already encoded
-void rl_write_container(std::string const & fn, RlHeader const & h, const uint64_t * payload_words_be, uint64_t nwords,
-                        const uint64_t * block_word_off, const uint64_t * block_sym_off);
+// writer used by the device encoder (K8) and the host encoder: header, then the already encoded
+// payload in any number of pieces, then the block index
+class RlContainerWriter {
+public:
+	RlContainerWriter(std::string const & fn, RlHeader const & h);
+	~RlContainerWriter();
+	void payload(const void * bytes, size_t nbytes);
+	void finish(const uint64_t * block_word_off, const uint64_t * block_sym_off);
+private:
+	struct Impl;
+	std::unique_ptr<Impl> impl;
+};
 
 // host encoder (tools and tests; same bytes as the device encoder)
 void rl_encode_host(std::string const & fn, const uint8_t * syms, uint64_t n);

@@ -1,0 +1,302 @@
+// File-level C ABI (include/b3m.h): the reference's three library calls on this path,
+//   BwtMergeSort::computeBwt              /root/reference/src/bwtb3m.cpp:62-63
+//   BwtComputeSSA::computeSSA             /root/reference/src/bwtcomputessa.cpp:39-51
+//   MausFmToBwaConversion::rewrite        /root/reference/src/bwtb3mtobwa.cpp:29
+// Host orchestration and file formats only; every step of the hot path runs in the CUDA engine.
+#include "engine.h"
+#include "formats.h"
+#include <string.h>
+#include <time.h>
+#include <unistd.h>
+#include <algorithm>
+#include <thread>
+
+using namespace b3m;
+
+namespace {
+
+double now_sec() {
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+void set_err(char * err, size_t errlen, const char * msg) {
+	if (err && errlen) { strncpy(err, msg, errlen - 1); err[errlen - 1] = 0; }
+}
+
+std::string clip_off(std::string const & s, std::string const & suffix) {
+	if (s.size() >= suffix.size() && s.compare(s.size() - suffix.size(), suffix.size(), suffix) == 0) return s.substr(0, s.size() - suffix.size());
+	return s;
+}
+
+void copy_name(char * dst, std::string const & s) {
+	strncpy(dst, s.c_str(), 1023);
+	dst[1023] = 0;
+}
+
+// pinned host buffer holding a whole file
+struct PinnedFile {
+	uint8_t * p = nullptr;
+	uint64_t n = 0;
+	explicit PinnedFile(std::string const & fn) {
+		n = file_size(fn);
+		if (cudaMallocHost((void **)&p, n ? n : 1) != cudaSuccess) { cudaGetLastError(); throw Error("cannot allocate pinned host memory for " + fn); }
+		FILE * f = fopen(fn.c_str(), "rb");
+		if (!f) { cudaFreeHost(p); throw IoError("cannot open " + fn + " for reading"); }
+		size_t const got = fread(p, 1, n, f);
+		fclose(f);
+		if (got != n) { cudaFreeHost(p); throw IoError("short read on " + fn); }
+	}
+	~PinnedFile() { if (p) cudaFreeHost(p); }
+};
+
+void check_device_available() {
+	int ndev = 0;
+	cudaError_t const ce = cudaGetDeviceCount(&ndev);
+	if (ce != cudaSuccess || ndev <= 0)
+		throw Error(std::string("no CUDA device available (") + cudaGetErrorString(ce) + "); this library has no CPU fallback");
+}
+
+// bytes of device memory one suffix of a block costs while the block is sorted (text, suffix
+// array, ranks, radix ping-pong buffers; DESIGN.md "HBM layout")
+constexpr uint64_t BYTES_PER_SUFFIX = 30;
+
+} // namespace
+
+extern "C" {
+
+void b3m_options_init(b3m_options * o) {
+	if (!o) return;
+	memset(o, 0, sizeof(*o));
+	o->inputtype = "bytestream";
+	o->sasamplingrate = 32;          // BwtMergeSortOptions::getDefaultSaSamplingRate, README.md:40
+	o->isasamplingrate = 262144;     // getDefaultIsaSamplingRate, README.md:41
+	o->mem = 0;                      // 0: bounded by the free device memory (the reference's 2 GiB is a host RAM target)
+	long const nc = sysconf(_SC_NPROCESSORS_ONLN);
+	o->numthreads = nc > 0 ? (uint64_t)nc : 1;
+	o->bwtonly = 0;
+	o->copyinputtomemory = 0;
+	o->largelcpthres = 16384;
+	o->verbose = 0;
+	o->device = 0;
+	o->numblocks = 0;
+}
+
+int b3m_compute_bwt(const b3m_options * o, b3m_result * res, char * err, size_t errlen) {
+	try {
+		if (!o || !res) throw Error("null argument");
+		if (!o->fn || !*o->fn) throw Error("no input file name");
+		double const t0 = now_sec();
+		memset(res, 0, sizeof(*res));
+		int const itype = b3m_parse_inputtype(o->inputtype ? o->inputtype : "bytestream");
+		if (itype < 0) throw Error(std::string("unknown input type ") + (o->inputtype ? o->inputtype : "(null)") + " (lz4 and utf-8 are not supported by this implementation)");
+		std::string const tmpprefix = (o->tmpprefix && *o->tmpprefix) ? o->tmpprefix : "bwtb3m_tmp";
+		std::string const bwtfn = (o->outputfilename && *o->outputfilename) ? o->outputfilename : tmpprefix + ".bwt";
+		std::string const prefix = clip_off(bwtfn, ".bwt");
+		check_device_available();
+		if (!file_exists(o->fn)) throw IoError(std::string("input file ") + o->fn + " does not exist");
+		bool const verbose = o->verbose != 0;
+
+		PinnedFile in(o->fn);
+		if (verbose) fprintf(stderr, "[V] read %llu bytes from %s in %.3f s\n", (unsigned long long)in.n, o->fn, now_sec() - t0);
+		Engine e(o->device, nullptr);
+		e.load(in.p, in.n, itype, false);
+		uint64_t const n = e.T.n;
+
+		// block size: the whole text is one block when its working set fits the memory target;
+		// mem=0 means the free device memory (SURVEY 3.1 step 3 for the reference's rule)
+		size_t freeb = 0, totalb = 0;
+		B3M_CUDA(cudaMemGetInfo(&freeb, &totalb));
+		uint64_t const avail = (uint64_t)freeb + e.arena.capacity - e.arena.in_use;
+		uint64_t target = o->mem ? std::min<uint64_t>(o->mem, avail) : avail;
+		uint64_t numblocks = o->numblocks;
+		if (!numblocks) {
+			uint64_t const per_block = std::max<uint64_t>(target / BYTES_PER_SUFFIX, 1);
+			numblocks = std::max<uint64_t>(1, (n + per_block - 1) / per_block);
+		}
+		b3m_build_params p;
+		memset(&p, 0, sizeof(p));
+		p.numblocks = numblocks;
+		p.preisarate = 0;
+		p.sasamplingrate = o->sasamplingrate ? o->sasamplingrate : 32;
+		p.isasamplingrate = o->isasamplingrate ? o->isasamplingrate : 262144;
+		p.bwtonly = o->bwtonly;
+		p.largelcpthres = o->largelcpthres ? o->largelcpthres : 16384;
+		if (verbose) fprintf(stderr, "[V] n=%llu sigma=%u numblocks=%llu (memory target %llu MiB)\n", (unsigned long long)n, e.T.sigma + (e.T.has_term ? 1 : 0),
+		                     (unsigned long long)numblocks, (unsigned long long)(target >> 20));
+		e.build(p);
+		b3m_info info;
+		e.info(&info);
+		if (verbose)
+			fprintf(stderr, "[V] device: decode %.3f ms, sort %.3f ms, extract %.3f ms, gap %.3f ms, merge %.3f ms, dict %.3f ms, walk %.3f ms\n",
+			        info.ms_decode, info.ms_sort, info.ms_extract, info.ms_gap, info.ms_merge, info.ms_dict, info.ms_walk);
+
+		// outputs: .bwt, .hist, then either .preisa(+.meta) or .sa/.isa
+		double const t1 = now_sec();
+		e.write_bwt(bwtfn.c_str());
+		write_hist(prefix + ".hist", info.hist);
+		copy_name(res->textfn, o->fn);
+		copy_name(res->bwtfn, bwtfn);
+		copy_name(res->histfn, prefix + ".hist");
+		if (o->bwtonly) {
+			std::vector<uint64_t> pairs(2 * info.npreisa);
+			e.fetch(nullptr, pairs.data(), nullptr, nullptr);
+			write_preisa(prefix + ".preisa", pairs.data(), info.npreisa, info.preisarate);
+			copy_name(res->preisafn, prefix + ".preisa");
+			copy_name(res->metafn, prefix + ".preisa.meta");
+		} else {
+			// the reference removes its .preisa files in this mode (ChangeLog 0.0.49)
+			std::vector<uint64_t> sa(info.nsa), isa(info.nisa);
+			e.fetch(nullptr, nullptr, sa.data(), isa.data());
+			write_sampled(prefix + ".sa", info.sasamplingrate, sa.data(), info.nsa);
+			write_sampled(prefix + ".isa", info.isasamplingrate, isa.data(), info.nisa);
+			copy_name(res->safn, prefix + ".sa");
+			copy_name(res->isafn, prefix + ".isa");
+		}
+		if (verbose) fprintf(stderr, "[V] wrote %s (%llu runs, %llu payload bytes) and siblings in %.3f s\n", bwtfn.c_str(),
+		                     (unsigned long long)e.rl_nruns, (unsigned long long)e.rl_bytes, now_sec() - t1);
+		res->n = n;
+		res->numblocks = info.numblocks;
+		res->seconds_device = 1e-3 * (info.ms_decode + info.ms_total);
+		res->seconds_total = now_sec() - t0;
+		return 0;
+	} catch (std::exception const & ex) { set_err(err, errlen, ex.what()); return 2; }
+	catch (...) { set_err(err, errlen, "unknown error"); return 3; }
+}
+
+int b3m_compute_ssa(const char * bwtfn, uint64_t sasamplingrate, uint64_t isasamplingrate, const char * tmpprefix, int copyinputtomemory,
+                    uint64_t numthreads, uint64_t maxsortmem, uint64_t maxtmpfiles, int verbose, const char * ref_isa_fn, const char * ref_sa_fn,
+                    int device, char * err, size_t errlen) {
+	(void)tmpprefix; (void)copyinputtomemory; (void)maxsortmem; (void)maxtmpfiles; // no external memory is needed: the BWT lives in HBM
+	try {
+		if (!bwtfn || !*bwtfn) throw Error("no .bwt file name");
+		check_device_available();
+		double const t0 = now_sec();
+		std::string const prefix = clip_off(bwtfn, ".bwt");
+		std::string const preisafn = prefix + ".preisa";
+		if (!file_exists(bwtfn)) throw IoError(std::string(bwtfn) + " does not exist");
+		if (!file_exists(preisafn)) throw IoError(preisafn + " does not exist (run bwtb3m with bwtonly=1 first)");
+		if (!numthreads) numthreads = 1;
+		std::vector<uint8_t> const L = RlDecoder::decodeAll(std::vector<std::string>(1, bwtfn), numthreads);
+		std::vector<uint64_t> const pairs = read_preisa(preisafn);
+		if (verbose) fprintf(stderr, "[V] decoded %llu symbols, %llu anchors in %.3f s\n", (unsigned long long)L.size(), (unsigned long long)(pairs.size() / 2), now_sec() - t0);
+		Engine e(device, nullptr);
+		e.ssa_from_bwt(L.data(), L.size(), pairs.data(), pairs.size() / 2, sasamplingrate ? sasamplingrate : 32, isasamplingrate ? isasamplingrate : 32);
+		std::vector<uint64_t> sa(e.nsa), isa(e.nisa);
+		e.fetch(nullptr, nullptr, sa.data(), isa.data());
+		for (auto v : sa) if (v == ~0ull) throw Error("sampled suffix array is incomplete: the anchors do not cover the text");   // hwtPreIsaToIsa.cpp:166-167
+		for (auto v : isa) if (v == ~0ull) throw Error("sampled inverse suffix array is incomplete: the anchors do not cover the text");
+		write_sampled(prefix + ".sa", e.params.sasamplingrate, sa.data(), sa.size());
+		write_sampled(prefix + ".isa", e.params.isasamplingrate, isa.data(), isa.size());
+		// optional comparison with reference files (ref_isa / ref_sa arguments of the reference tool)
+		auto compare = [&](const char * fn, std::vector<uint64_t> const & mine, uint64_t rate, const char * what) {
+			if (!fn || !*fn) return;
+			uint64_t r = 0; std::vector<uint64_t> v;
+			read_sampled(fn, &r, &v);
+			if (r != rate || v != mine) throw Error(std::string("sampled ") + what + " differs from reference file " + fn);
+			if (verbose) fprintf(stderr, "[V] sampled %s equals %s\n", what, fn);
+		};
+		compare(ref_sa_fn, sa, e.params.sasamplingrate, "suffix array");
+		compare(ref_isa_fn, isa, e.params.isasamplingrate, "inverse suffix array");
+		if (verbose) fprintf(stderr, "[V] dictionary %.3f ms, walk %.3f ms, total %.3f s\n", e.ms_dict, e.ms_walk, now_sec() - t0);
+		return 0;
+	} catch (std::exception const & ex) { set_err(err, errlen, ex.what()); return 2; }
+	catch (...) { set_err(err, errlen, "unknown error"); return 3; }
+}
+
+// BWA's on-disk formats (public bwt_dump_bwt / bwt_dump_sa):
+//   .bwt: primary, L2[1..4], then ceil(seq_len/16) uint32 words, 16 symbols per word, symbol i
+//         at bits (15-(i&15))*2, the terminator row removed
+//   .sa : primary, L2[1..4], sa_intv, seq_len, then SA[k*sa_intv] for k = 1..floor(seq_len/sa_intv)
+int b3m_to_bwa(const char * inbwt, const char * outbwt, const char * outsa, char * err, size_t errlen) {
+	try {
+		if (!inbwt || !outbwt || !outsa) throw Error("null argument");
+		std::string const prefix = clip_off(inbwt, ".bwt");
+		std::string const safn = prefix + ".sa";
+		if (!file_exists(inbwt)) throw IoError(std::string(inbwt) + " does not exist");
+		if (!file_exists(safn)) throw IoError(safn + " does not exist (bwtb3m must run with bwtonly=0, or run bwtcomputessa)");
+		unsigned const nthreads = std::max(1u, std::thread::hardware_concurrency());
+		std::vector<uint8_t> const L = RlDecoder::decodeAll(std::vector<std::string>(1, inbwt), nthreads);
+		uint64_t const n = L.size();
+		if (n < 2) throw Error("BWT too short for a BWA index");
+		uint64_t sarate = 0; std::vector<uint64_t> sa;
+		read_sampled(safn, &sarate, &sa);
+		uint64_t const seq_len = n - 1;
+		uint64_t primary = ~0ull, cnt[5] = {0, 0, 0, 0, 0};
+		for (uint64_t i = 0; i < n; ++i) {
+			if (L[i] > 4) throw Error("bwtb3mtobwa needs a pacterm BWT (symbols 0..4)");
+			cnt[L[i]]++;
+			if (L[i] == 0) primary = i;
+		}
+		if (cnt[0] != 1) throw Error("bwtb3mtobwa needs exactly one terminator symbol in the BWT");
+		uint64_t L2[5]; L2[0] = 0;
+		for (int c = 0; c < 4; ++c) L2[c + 1] = L2[c] + cnt[c + 1];
+		uint64_t const nw = (seq_len + 15) >> 4;
+		std::vector<uint32_t> wds(nw ? nw : 1, 0);
+		// pack in parallel: rows before the primary keep their index, rows after it move up by one
+		{
+			std::vector<std::thread> th;
+			for (unsigned t = 0; t < nthreads; ++t) th.emplace_back([&, t]() {
+				uint64_t const w0 = nw * t / nthreads, w1 = nw * (t + 1) / nthreads;
+				for (uint64_t w = w0; w < w1; ++w) {
+					uint32_t v = 0;
+					for (uint64_t k = w << 4; k < std::min<uint64_t>((w + 1) << 4, seq_len); ++k) {
+						uint64_t const i = k < primary ? k : k + 1;
+						v |= (uint32_t)(L[i] - 1) << ((15 - (k & 15)) << 1);
+					}
+					wds[w] = v;
+				}
+			});
+			for (auto & x : th) x.join();
+		}
+		{
+			std::vector<uint8_t> o(40 + 4 * nw);
+			memcpy(o.data(), &primary, 8); memcpy(o.data() + 8, L2 + 1, 32); memcpy(o.data() + 40, wds.data(), 4 * nw);
+			write_file(outbwt, o.data(), o.size());
+		}
+		{
+			uint64_t const n_sa = (seq_len + sarate) / sarate;
+			if (sa.size() < n_sa) throw Error("sampled suffix array " + safn + " is too short");
+			std::vector<uint8_t> o(56 + 8 * (n_sa - 1));
+			memcpy(o.data(), &primary, 8); memcpy(o.data() + 8, L2 + 1, 32); memcpy(o.data() + 40, &sarate, 8); memcpy(o.data() + 48, &seq_len, 8);
+			if (n_sa > 1) memcpy(o.data() + 56, sa.data() + 1, 8 * (n_sa - 1));
+			write_file(outsa, o.data(), o.size());
+		}
+		return 0;
+	} catch (std::exception const & ex) { set_err(err, errlen, ex.what()); return 2; }
+	catch (...) { set_err(err, errlen, "unknown error"); return 3; }
+}
+
+// reader entry points for bindings that do not want to link C++: decode a .bwt into memory
+int b3m_bwt_length(const char * bwtfn, uint64_t * n, char * err, size_t errlen) {
+	try {
+		if (!bwtfn || !n) throw Error("null argument");
+		*n = RlDecoder::getLength(std::string(bwtfn));
+		return 0;
+	} catch (std::exception const & ex) { set_err(err, errlen, ex.what()); return 2; }
+	catch (...) { set_err(err, errlen, "unknown error"); return 3; }
+}
+
+int b3m_bwt_decode(const char * bwtfn, uint8_t * out, uint64_t cap, uint64_t numthreads, char * err, size_t errlen) {
+	try {
+		if (!bwtfn || !out) throw Error("null argument");
+		std::vector<uint8_t> const L = RlDecoder::decodeAll(std::vector<std::string>(1, bwtfn), numthreads ? numthreads : 1);
+		if (L.size() > cap) throw Error("output buffer too small");
+		memcpy(out, L.data(), L.size());
+		return 0;
+	} catch (std::exception const & ex) { set_err(err, errlen, ex.what()); return 2; }
+	catch (...) { set_err(err, errlen, "unknown error"); return 3; }
+}
+
+// host encoder of the same container (tools/tests; the product path encodes on the device)
+int b3m_bwt_encode_host(const char * bwtfn, const uint8_t * syms, uint64_t n, char * err, size_t errlen) {
+	try {
+		if (!bwtfn || (!syms && n)) throw Error("null argument");
+		rl_encode_host(bwtfn, syms, n);
+		return 0;
+	} catch (std::exception const & ex) { set_err(err, errlen, ex.what()); return 2; }
+	catch (...) { set_err(err, errlen, "unknown error"); return 3; }
+}
+
+} // extern "C"

@@ -344,6 +344,25 @@ k_walk(DictView D, CTable C, uint32_t exc_lf, const uint32_t * __restrict__ anch
 	}
 }
 
+// anchors at arbitrary positions (bwtcomputessa: whatever the .preisa file holds)
+__global__ void __launch_bounds__(256)
+k_walk_anchors(DictView D, CTable C, uint32_t exc_lf, const uint32_t * __restrict__ anchor_rank, const unsigned long long * __restrict__ anchor_pos,
+               const unsigned long long * __restrict__ anchor_steps, uint64_t nanchors, uint64_t n,
+               uint32_t samask, uint32_t sashift, uint32_t isamask, uint32_t isashift,
+               unsigned long long * __restrict__ sa_out, unsigned long long * __restrict__ isa_out) {
+	uint64_t const q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= nanchors) return;
+	uint32_t r = anchor_rank[q];
+	uint64_t p = anchor_pos[q];
+	uint64_t steps = anchor_steps[q];
+	while (steps--) {
+		if ((p & isamask) == 0) isa_out[p >> isashift] = r;
+		if ((r & samask) == 0) sa_out[r >> sashift] = p;
+		p = p ? p - 1 : n - 1;
+		r = lf_step(D, C, exc_lf, r);
+	}
+}
+
 __global__ void __launch_bounds__(256)
 k_lfbench(DictView D, CTable C, uint32_t exc_lf, const uint32_t * __restrict__ start, uint64_t nchains, uint64_t steps, uint32_t * __restrict__ out) {
 	uint64_t const q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -377,6 +396,18 @@ void k7_walk(Stream & st, DevDict const & D, const uint32_t * anchor_rank, uint6
 	CTable C;
 	for (int i = 0; i < 257; ++i) C.c[i] = D.C[i];
 	B3M_LAUNCH_T(st, "lf_walk", n * 64ull, k_walk, (unsigned)div_up(nanchors, 256), 256, 0, make_view(D), C, D.exc_lf, anchor_rank, nanchors, arate, n,
+	           (uint32_t)(sarate - 1), ilog2_exact(sarate), (uint32_t)(isarate - 1), ilog2_exact(isarate),
+	           (unsigned long long *)sa_out, (unsigned long long *)isa_out);
+	if (ws) { ws->steps += n; ws->chains += nanchors; }
+}
+
+void k7_walk_anchors(Stream & st, DevDict const & D, const uint32_t * anchor_rank, const uint64_t * anchor_pos, const uint64_t * anchor_steps,
+                     uint64_t nanchors, uint64_t n, uint64_t sarate, uint64_t isarate, uint64_t * sa_out, uint64_t * isa_out, WalkStats * ws) {
+	if (!nanchors) return;
+	CTable C;
+	for (int i = 0; i < 257; ++i) C.c[i] = D.C[i];
+	B3M_LAUNCH_T(st, "lf_walk", n * 64ull, k_walk_anchors, (unsigned)div_up(nanchors, 256), 256, 0, make_view(D), C, D.exc_lf, anchor_rank,
+	           (const unsigned long long *)anchor_pos, (const unsigned long long *)anchor_steps, nanchors, n,
 	           (uint32_t)(sarate - 1), ilog2_exact(sarate), (uint32_t)(isarate - 1), ilog2_exact(isarate),
 	           (unsigned long long *)sa_out, (unsigned long long *)isa_out);
 	if (ws) { ws->steps += n; ws->chains += nanchors; }

@@ -89,6 +89,31 @@ class Engine:
                                                C.c_void_p(sa_ptr) if sa_ptr else None,
                                                C.c_void_p(isa_ptr) if isa_ptr else None))
 
+    def write_bwt(self, fn):
+        """K8: device-side run-length Huffman encoding of the BWT of the last build into `fn`."""
+        import os
+        self._check(self._lib.b3m_engine_write_bwt(self._h, os.fsencode(fn)))
+
+    def fetch_runs(self):
+        """(symbols uint8, lengths uint64) of the runs of the BWT."""
+        n = C.c_uint64(0)
+        self._check(self._lib.b3m_engine_fetch_runs(self._h, None, None, 0, C.byref(n)))
+        syms = np.empty(n.value, dtype=np.uint8)
+        lens = np.empty(n.value, dtype=np.uint64)
+        self._check(self._lib.b3m_engine_fetch_runs(self._h, _ptr(syms), _ptr(lens), n.value, C.byref(n)))
+        return syms, lens
+
+    def ssa_from_bwt(self, bwt, preisa_pairs, sasamplingrate=32, isasamplingrate=32):
+        """K4 + K7 on an existing BWT (bwtcomputessa path); returns (sa, isa) samples."""
+        b = np.ascontiguousarray(bwt, dtype=np.uint8)
+        pp = np.ascontiguousarray(preisa_pairs, dtype=np.uint64).ravel()
+        self._check(self._lib.b3m_engine_ssa_from_bwt(self._h, _ptr(b), b.size, _ptr(pp), pp.size // 2, sasamplingrate, isasamplingrate))
+        i = self.info()
+        sa = np.empty(i["nsa"], dtype=np.uint64)
+        isa = np.empty(i["nisa"], dtype=np.uint64)
+        self._check(self._lib.b3m_engine_fetch(self._h, None, None, _ptr(sa), _ptr(isa)))
+        return sa, isa
+
     def lf_bench(self, nchains, steps):
         ms = C.c_float(0)
         cs = C.c_uint64(0)

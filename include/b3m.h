@@ -94,6 +94,16 @@ int b3m_compute_ssa(const char * bwtfn, uint64_t sasamplingrate, uint64_t isasam
  * (/root/reference/src/bwtb3mtobwa.cpp:29) */
 int b3m_to_bwa(const char * inbwt, const char * outbwt, const char * outsa, char * err, size_t errlen);
 
+/* Reader of the .bwt container for bindings that cannot link C++: replaces
+ * libmaus2::huffman::RLDecoder::getLength (/root/reference/src/hwtPreIsaToIsa.cpp:53) and a full
+ * RLDecoder::decode() loop (/root/reference/src/bwtb3mdecoderl.cpp:27-46). */
+int b3m_bwt_length(const char * bwtfn, uint64_t * n, char * err, size_t errlen);
+int b3m_bwt_decode(const char * bwtfn, uint8_t * out, uint64_t cap, uint64_t numthreads, char * err, size_t errlen);
+/* Host writer of the same container from a symbol array (replaces RLEncoderStd::encode + flush,
+ * /root/reference/src/lcpbit.cpp:3677-3681); a tool for tests and converters -- the build path
+ * b3m_compute_bwt encodes on the device and never calls it. */
+int b3m_bwt_encode_host(const char * bwtfn, const uint8_t * syms, uint64_t n, char * err, size_t errlen);
+
 /* ------------------------------------------------------------------------------------------
  * Engine level: the same path on caller-owned host or device buffers.  One engine per GPU and
  * per host thread; the engine owns its device memory and enqueues everything on one stream.
@@ -151,6 +161,18 @@ int b3m_engine_fetch(b3m_engine * e, uint8_t * bwt, uint64_t * preisa_pairs, uin
  * see b3m_engine_info; for the multi-GPU orchestration and device-resident benchmarks. */
 int b3m_engine_device_results(b3m_engine * e, const void ** d_bwt_codes, const void ** d_preisa_rank,
                               const void ** d_sa, const void ** d_isa);
+
+/* K8: run-length + Huffman encode the BWT of the last build on the device and write the .bwt
+ * container (replaces the RLEncoder output stage of computeBwt). */
+int b3m_engine_write_bwt(b3m_engine * e, const char * bwtfn);
+/* The run stream (symbol, length) of the BWT, for a reference-side binding that feeds
+ * libmaus2's own RLEncoderStd::encodeRun (/root/reference/src/lcpbit.cpp:728-745).  With both
+ * pointers NULL only *nruns is returned. */
+int b3m_engine_fetch_runs(b3m_engine * e, uint8_t * syms, uint64_t * lens, uint64_t cap, uint64_t * nruns);
+/* K4 + K7 on an existing BWT: sampled SA/ISA from n symbols and npairs (rank,pos) anchors
+ * (engine half of b3m_compute_ssa); fetch with b3m_engine_fetch(e, NULL, NULL, sa, isa). */
+int b3m_engine_ssa_from_bwt(b3m_engine * e, const uint8_t * bwt, uint64_t n, const uint64_t * preisa_pairs, uint64_t npairs,
+                            uint64_t sasamplingrate, uint64_t isasamplingrate);
 
 /* LF-steps/s instrument on the dictionary of the last build: nchains dependent LF chains of
  * `steps` steps each, started at evenly spaced sampled ranks; returns elapsed device ms.
