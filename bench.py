@@ -170,16 +170,14 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from bwtb3m_b200 import Engine, workloads
+    from bwtb3m_b200 import Engine, multigpu, workloads
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        from bwtb3m_b200 import multigpu
-        return multigpu.bench_main(args, METRIC, UNIT, config_dict, build_params, ClockSampler, measured_peak_gbs)
-
     torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     itype, data, nsym = workloads.make(args.workload, args.scale)
     params = build_params(args.workload)
     host_in = torch.from_numpy(data).pin_memory()
@@ -187,20 +185,34 @@ def run_ours(args):
     stream = torch.cuda.Stream()
     eng = Engine(local, stream.cuda_stream)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    state = {"drv": None}
+
+    def build():
+        if world == 1:
+            eng.build(numblocks=args.numblocks, **params)
+        else:
+            state["drv"], _ = multigpu.build_distributed(eng, local_blocks=args.numblocks, driver=state["drv"], **params)
 
     def step_device():
         eng.load_device(dev_in.data_ptr(), dev_in.numel(), itype)
-        eng.build(numblocks=args.numblocks, **params)
+        build()
 
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    warmup = max(args.warmup, 3)
     with torch.cuda.stream(stream):
-        for _ in range(max(args.warmup, 3)):
+        for _ in range(warmup):
             step_device()
         info = eng.info()
-        # ---- value: device-resident input, CUDA events on the engine's stream ----
+        # ---- value: device-resident input, CUDA events on the engine's stream, max over ranks ----
         sampler = ClockSampler(local)
         sampler.start()
         time.sleep(0.15)
-        torch.cuda.synchronize()
+        sync_all()
         l0 = eng.info()["launches"]
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         for k in range(args.steps):
@@ -208,49 +220,71 @@ def run_ours(args):
             ev[k][0].record(stream)
             step_device()
             ev[k][1].record(stream)
-        torch.cuda.synchronize()
+        sync_all()
         total_ms = sum(a.elapsed_time(b) for a, b in ev)
         l1 = eng.info()["launches"]
         time.sleep(0.1)
         sampler.stop()
         info = eng.info()
+        launches = int(l1 - l0)
+        if world > 1:
+            red = torch.tensor([total_ms, float(launches)], dtype=torch.float64, device="cuda")
+            mx = red.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(red, op=dist.ReduceOp.SUM)
+            total_ms, launches = float(mx[0].item()), int(red[1].item())
 
-        # ---- e2e: pinned host input -> results in pinned host buffers, wall clock ----
+        # ---- e2e: pinned host input -> results in pinned host buffers (rank 0), wall clock ----
         n = info["n"]
-        out = {
-            "bwt": torch.empty(n, dtype=torch.uint8).pin_memory(),
-            "preisa": torch.empty(2 * info["npreisa"], dtype=torch.int64).pin_memory(),
-            "sa": torch.empty(max(info["nsa"], 1), dtype=torch.int64).pin_memory(),
-            "isa": torch.empty(max(info["nisa"], 1), dtype=torch.int64).pin_memory(),
-        }
+        out = None
+        if rank == 0:
+            out = {
+                "bwt": torch.empty(n, dtype=torch.uint8).pin_memory(),
+                "preisa": torch.empty(2 * info["npreisa"], dtype=torch.int64).pin_memory(),
+                "sa": torch.empty(max(info["nsa"], 1), dtype=torch.int64).pin_memory(),
+                "isa": torch.empty(max(info["nisa"], 1), dtype=torch.int64).pin_memory(),
+            }
 
         def step_e2e():
             eng.load_host_ptr(host_in.data_ptr(), host_in.numel(), itype)
-            eng.build(numblocks=args.numblocks, **params)
-            eng.fetch_ptrs(out["bwt"].data_ptr(), out["preisa"].data_ptr(),
-                           out["sa"].data_ptr() if info["nsa"] else 0, out["isa"].data_ptr() if info["nisa"] else 0)
+            build()
+            if rank == 0:
+                eng.fetch_ptrs(out["bwt"].data_ptr(), out["preisa"].data_ptr(),
+                               out["sa"].data_ptr() if info["nsa"] else 0, out["isa"].data_ptr() if info["nisa"] else 0)
 
         step_e2e()
-        torch.cuda.synchronize()
-        e2e_s = 0.0
-        for k in range(args.steps):
-            flush.fill_(k & 0xFF)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
+        sync_all()
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
             step_e2e()
-            torch.cuda.synchronize()
-            e2e_s += time.perf_counter() - t0
-        h2d = int(host_in.numel())
+        sync_all()
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            mx = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            e2e_s = float(mx[0].item())
+        h2d = int(host_in.numel()) * world
         d2h = int(n + 16 * info["npreisa"] + 8 * info["nsa"] + 8 * info["nisa"])
 
-        # ---- roofline of the dominant kernel: per-kernel CUDA events, separate profiled steps ----
+        # ---- roofline of the dominant kernel: per-kernel CUDA events on separate profiled steps ----
         eng.set_profile(True)
-        for k in range(3):
+        nprof = 2
+        for k in range(nprof):
             flush.fill_(k)
             step_device()
+        sync_all()
         kt = eng.kernel_times()
         eng.set_profile(False)
-        lf_ms, _ = eng.lf_bench(1 << 20, 256)
+        lf_ms = None
+        if rank == 0:
+            lf_ms, _ = eng.lf_bench(1 << 20, 256)
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     peak, peak_src = measured_peak_gbs()
     dom = max(kt.items(), key=lambda kv: kv[1]["ms"]) if kt else (None, None)
@@ -263,8 +297,9 @@ def run_ours(args):
         if os.path.exists(tp):
             try:
                 tj = json.load(open(tp))
-                if tj.get("kernel") == name and tj.get("workload") == args.workload and args.scale == 1.0:
-                    traffic = tj.get("dram_bytes_per_launch")
+                ent = tj.get(args.workload, {}).get(name) if args.scale == 1.0 else None
+                if ent:
+                    traffic = ent.get("dram_bytes_per_launch")
             except Exception:
                 pass
         roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -272,10 +307,10 @@ def run_ours(args):
                 "avg_launch_ms": r["ms"] / r["launches"], "algorithmic_bytes_per_launch": r["bytes"] / r["launches"],
                 "share_of_step": r["ms"] / sum(x["ms"] for x in kt.values())}
 
-    # ---- CPU baseline: the oracle port on this box's host cores ----
+    # ---- CPU baseline: the oracle port on this box's host cores (N=1 only) ----
     threads = os.cpu_count() or 1
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:
         sample = min(nsym, args.cpu_sample)
         dt, nn, nblocks = cpu_oracle_run(itype, data, sample, params, threads)
         cpu = {"value": sample / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port", "seconds": dt,
@@ -283,23 +318,26 @@ def run_ours(args):
 
     total_s = total_ms * 1e-3
     line = {
-        "metric": METRIC, "value": nsym * args.steps / total_s / 1e6, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+        "metric": METRIC, "value": nsym * args.steps / total_s / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": config_dict(args, nsym, itype, {"numblocks": info["numblocks"], "preisarate": info["preisarate"]}),
+        "config": config_dict(args, nsym, itype, {"numblocks": info["numblocks"], "preisarate": info["preisarate"],
+                                                  "parallelism": "text replicated, %d block ranges, merge tree over NCCL" % world if world > 1 else "single GPU"}),
         "clocks": sampler.summary(),
-        "e2e": {"value": nsym * args.steps / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": 1e3 * e2e_s / args.steps},
-        "gpu_launches": int(l1 - l0),
+        "e2e": {"value": nsym * e2e_steps / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps},
+        "gpu_launches": launches,
         "roofline": roof,
         "cpu_baseline": cpu,
         "phases_ms": {k[3:]: round(info[k], 4) for k in info if k.startswith("ms_")},
         "counters": {k: info[k] for k in ("sort_rounds", "radix_passes", "radix_bytes", "sort_active_sum", "walk_lf_steps",
                                           "walk_chains", "gap_lf_steps", "max_lcpnext")},
-        "kernels_ms_per_step": {k: round(v["ms"] / 3, 4) for k, v in kt.items()},
+        "kernels_ms_per_step": {k: round(v["ms"] / nprof, 4) for k, v in kt.items()},
         "lf_steps_per_s": (1 << 20) * 256 / (lf_ms * 1e-3),
     }
     print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():
@@ -314,6 +352,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=48_000_000, help="symbols of the workload the cpu_baseline leg processes")
     ap.add_argument("--ref-sample", type=int, default=8_000_000, help="symbols per step of --impl reference")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=5, help="steps of the end-to-end (host buffers) leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

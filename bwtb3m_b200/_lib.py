@@ -56,6 +56,9 @@ EXPORTS = [
     "b3m_engine_device_results", "b3m_engine_lf_bench", "b3m_engine_sync", "b3m_engine_set_profile",
     "b3m_engine_kernel_times", "b3m_engine_write_bwt", "b3m_engine_fetch_runs", "b3m_engine_ssa_from_bwt",
     "b3m_bwt_length", "b3m_bwt_decode", "b3m_bwt_encode_host",
+    "b3m_engine_blk_begin", "b3m_engine_blk_build_range", "b3m_engine_blk_chains", "b3m_engine_blk_zranks", "b3m_engine_blk_gap",
+    "b3m_engine_blk_merge", "b3m_engine_blk_merge_samples", "b3m_engine_blk_finish",
+    "b3m_engine_default_preisarate",
 ]
 
 _lib = None
@@ -92,6 +95,16 @@ def lib():
     L.b3m_bwt_length.argtypes = [C.c_char_p, u64p, C.c_char_p, C.c_size_t]
     L.b3m_bwt_decode.argtypes = [C.c_char_p, vp, u64, u64, C.c_char_p, C.c_size_t]
     L.b3m_bwt_encode_host.argtypes = [C.c_char_p, vp, u64, C.c_char_p, C.c_size_t]
+    u32p = C.POINTER(C.c_uint32)
+    L.b3m_engine_default_preisarate.argtypes = [vp, C.c_int, u64p]
+    L.b3m_engine_blk_begin.argtypes = [vp, u64, u64, vp, vp, vp]
+    L.b3m_engine_blk_build_range.argtypes = [vp, u64, u64, u64, vp, u32p]
+    L.b3m_engine_blk_chains.argtypes = [vp, u64, u64p, u64p]
+    L.b3m_engine_blk_zranks.argtypes = [vp, u64, u64, u64, u64, u64, vp]
+    L.b3m_engine_blk_gap.argtypes = [vp, vp, u64, u64, C.c_uint32, u64, u64, u64, u64, u64, vp, vp, vp]
+    L.b3m_engine_blk_merge.argtypes = [vp, vp, u64, C.c_uint32, vp, u64, C.c_uint32, u64, vp, vp, u32p]
+    L.b3m_engine_blk_merge_samples.argtypes = [vp, u64, u64, u64, vp]
+    L.b3m_engine_blk_finish.argtypes = [vp, vp, C.c_uint32, u64, u64, u64, u64, C.c_int, u64]
     if True:
         L.b3m_options_init.argtypes = [C.POINTER(Options)]
         L.b3m_options_init.restype = None

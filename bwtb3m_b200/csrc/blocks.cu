@@ -9,6 +9,7 @@
 #include "scan.cuh"
 #include <string.h>
 #include <algorithm>
+#include <string>
 
 namespace b3m {
 
@@ -121,15 +122,14 @@ k_hist_range(const uint8_t * __restrict__ in, uint64_t n, unsigned long long * _
 // K5: gap array.  One backward-search chain per thread over R's text, right to left
 // (Appendix A.2):  r <- C_A[c] + rank_c(L_A, r) + [c == T[a1-1] and gt_R[j]],  G[r]++ .
 // ------------------------------------------------------------------------------------------
-struct CTab { uint32_t c[257]; };
 
 __global__ void __launch_bounds__(256)
-k_gap(DictView D, CTab C, TextRef t, uint64_t a1, uint64_t r1, uint64_t chl, uint64_t nch, const uint32_t * __restrict__ r0,
+k_gap(DictView D, CTab C, TextRef t, uint64_t a1, uint64_t r1, uint64_t chl, uint64_t c_lo, uint64_t c_hi, const uint32_t * __restrict__ r0,
       const uint8_t * __restrict__ gt_in /* indexed by text position */, uint8_t * __restrict__ gt_out /* indexed by position - a1 */,
       const uint32_t * __restrict__ special, uint32_t isa_a0, uint64_t ratemask, uint32_t rateshift,
       uint32_t * __restrict__ G, uint32_t * __restrict__ rsamp /* indexed by position / rate */) {
-	uint64_t const c = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (c >= nch) return;
+	uint64_t const c = c_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= c_hi) return;
 	uint64_t const zlo = a1 + c * chl;
 	uint64_t zhi = zlo + chl;
 	if (zhi > r1) zhi = r1;
@@ -246,7 +246,7 @@ void Engine::leaf_build(BlockLeaf & leaf, uint64_t s, uint64_t m, uint8_t * L, u
 		}
 		B3M_LAUNCH(st, k_leaf_emit, (unsigned)div_up(mt, 256), 256, 0, T.codes, s, (const uint32_t *)leaf.sa.get(), mt, shift, L, d_special.get());
 		B3M_LAUNCH(st, k_leaf_gt_samples, (unsigned)div_up(mt, 256), 256, 0, (const uint32_t *)wrank.get(), mt, shift, s, prerate - 1, ilog2u(prerate),
-		           gt.get(), prerank.get());
+		           gtp, prep);
 		extract_bytes += mt * (4 + 32 + 1 + 4 + 1);
 	}
 	if (has_termsuffix) {
@@ -257,103 +257,132 @@ void Engine::leaf_build(BlockLeaf & leaf, uint64_t s, uint64_t m, uint8_t * L, u
 			B3M_CUDA(cudaMemsetAsync(L, 0, 1, st.s));
 			B3M_CUDA(cudaMemsetAsync(d_special.get(), 0, 4, st.s));
 		}
-		B3M_CUDA(cudaMemsetAsync(gt.get() + T.ntext, 0, 1, st.s));
-		if ((T.ntext & (prerate - 1)) == 0) B3M_CUDA(cudaMemcpyAsync(prerank.get() + T.ntext / prerate, &zero, 4, cudaMemcpyHostToDevice, st.s));
+		B3M_CUDA(cudaMemsetAsync(gtp + T.ntext, 0, 1, st.s));
+		if ((T.ntext & (prerate - 1)) == 0) B3M_CUDA(cudaMemcpyAsync(prep + T.ntext / prerate, &zero, 4, cudaMemcpyHostToDevice, st.s));
 	}
 	*term_pos = fetch_special(0);
 	if (!has_termsuffix) leaf.keep = true; else leaf.sa.release(); // the last block is never a left part
 }
 
-// A7 + A8: merge node A = [a0,a1) (left) with R = [a1,r1) (right) into M.
-void Engine::node_merge(BlockNode & A, BlockNode & R, std::vector<BlockLeaf> & leaves, BlockNode & M, EventAccum & tgap, EventAccum & tmerge) {
-	TextRef const t = text_ref(T);
-	uint64_t const a0 = A.a0, a1 = A.a1, r1 = R.a1;
-	uint64_t const na = a1 - a0, nr = r1 - a1;
-	B3M_REQUIRE(R.a0 == a1, "internal: merge of non-adjacent nodes");
+// ---- primitives of one merge (shared by the single-GPU tree and the multi-GPU driver) -------
+// dictionary over L_A (the placeholder of A's block-start row excluded) and C_A over A's text
+void Engine::gap_prepare(GapCtx & ctx, const uint8_t * LA, uint64_t a0, uint64_t na, uint32_t termA) {
 	int const flavour = T.sigma <= 4 ? 2 : 8;
-
-	tgap.begin();
-	// rank dictionary over L_A; the placeholder of A's block-start row is excluded from counts
-	DevBuf<uint8_t> dlines(st, dict_bytes(flavour, na, T.sigma));
-	k4_build_dict(st, A.L.get(), na, flavour, T.sigma, dlines.get());
-	DictView D;
-	D.base = dlines.get(); D.flavour = (uint32_t)flavour; D.spad = d8_spad(T.sigma);
+	ctx.lines.alloc(st, dict_bytes(flavour, na, T.sigma));
+	k4_build_dict(st, LA, na, flavour, T.sigma, ctx.lines.get());
+	DictView & D = ctx.D;
+	D.base = ctx.lines.get(); D.flavour = (uint32_t)flavour; D.spad = d8_spad(T.sigma);
 	D.stride = flavour == 2 ? 64u : 4u * D.spad + D8_SYMS;
-	D.exc_pos = A.term; D.exc_code = 0;
-	// C_A counted over A's text (Appendix A.2)
-	CTab C;
-	{
-		DevBuf<unsigned long long> dh(st, 256);
-		B3M_CUDA(cudaMemsetAsync(dh.get(), 0, 256 * 8, st.s));
-		unsigned const grid = (unsigned)std::min<uint64_t>(div_up(na, 256 * 64), (uint64_t)st.sms * 8);
-		B3M_LAUNCH(st, k_hist_range, grid ? grid : 1, 256, 0, T.codes + a0, na, dh.get());
-		B3M_CUDA(cudaMemcpyAsync(pinned, dh.get(), 256 * 8, cudaMemcpyDeviceToHost, st.s));
-		B3M_CUDA(cudaStreamSynchronize(st.s));
-		uint64_t acc = 0;
-		for (int c = 0; c < 257; ++c) { C.c[c] = (uint32_t)acc; if (c < 256) acc += ((unsigned long long *)pinned)[c]; }
-	}
-	// chains: R's text is split into nch pieces; the start rank of each piece is the sum of the
-	// z-ranks of A's leaves
-	uint64_t nch = std::min<uint64_t>(std::max<uint64_t>(nr / 64, 1), (uint64_t)st.sms * 2048 * 2);
-	uint64_t const chl = div_up(nr, nch);
-	nch = div_up(nr, chl);
-	DevBuf<uint32_t> r0(st, nch);
-	B3M_CUDA(cudaMemsetAsync(r0.get(), 0, 4 * nch, st.s));
-	for (auto & lf : leaves)
-		if (lf.keep && lf.s >= a0 && lf.s < a1 && lf.mt)
-			B3M_LAUNCH(st, k_zrank, (unsigned)div_up(nch, 128), 128, 0, t, (const uint32_t *)lf.sa.get(), lf.mt, lf.s, a1, chl, r1, nch, r0.get());
-	if (!(T.has_term && r1 == T.n)) B3M_LAUNCH(st, k_gt_top, 1, 1, 0, t, r1, a1, d_special.get());
-	DevBuf<uint32_t> G(st, na + 1);
-	DevBuf<uint8_t> gtnew(st, nr);
-	B3M_CUDA(cudaMemsetAsync(G.get(), 0, 4 * (na + 1), st.s));
-	B3M_LAUNCH_T(st, "gap_chains", nr * 128ull, k_gap, (unsigned)div_up(nch, 256), 256, 0, D, C, t, a1, r1, chl, nch, (const uint32_t *)r0.get(),
-	             (const uint8_t *)gt.get(), gtnew.get(), (const uint32_t *)d_special.get(), A.term, prerate - 1, ilog2u(prerate), G.get(), rsamp.get());
-	B3M_CUDA(cudaMemcpyAsync(gt.get() + a1, gtnew.get(), nr, cudaMemcpyDeviceToDevice, st.s));
-	gap_lf_steps += nr; gap_chains += nch;
-	tgap.end();
+	D.exc_pos = termA; D.exc_code = 0;
+	DevBuf<unsigned long long> dh(st, 256);
+	B3M_CUDA(cudaMemsetAsync(dh.get(), 0, 256 * 8, st.s));
+	unsigned const grid = (unsigned)std::min<uint64_t>(div_up(na, 256 * 64), (uint64_t)st.sms * 8);
+	B3M_LAUNCH(st, k_hist_range, grid ? grid : 1, 256, 0, T.codes + a0, na, dh.get());
+	B3M_CUDA(cudaMemcpyAsync(pinned, dh.get(), 256 * 8, cudaMemcpyDeviceToHost, st.s));
+	B3M_CUDA(cudaStreamSynchronize(st.s));
+	uint64_t acc = 0;
+	for (int c = 0; c < 257; ++c) { ctx.C.c[c] = (uint32_t)acc; if (c < 256) acc += ((unsigned long long *)pinned)[c]; }
+}
 
-	tmerge.begin();
+// R's text is split into nch chains of chl positions (the same rule on every rank)
+void Engine::chain_geometry(uint64_t nr, uint64_t * chl, uint64_t * nch) const {
+	uint64_t c = std::min<uint64_t>(std::max<uint64_t>(nr / 64, 1), (uint64_t)st.sms * 2048 * 2);
+	*chl = div_up(nr, c);
+	*nch = div_up(nr, *chl);
+}
+
+// r0[c] += number of suffixes of this engine's kept leaves inside [a0,a1) smaller than the
+// start point of chain c
+void Engine::zranks_add(std::vector<BlockLeaf> & lv, uint64_t a0, uint64_t a1, uint64_t r1, uint64_t chl, uint64_t nch, uint32_t * r0) {
+	TextRef const t = text_ref(T);
+	for (auto & lf : lv)
+		if (lf.keep && lf.s >= a0 && lf.s < a1 && lf.mt)
+			B3M_LAUNCH(st, k_zrank, (unsigned)div_up(nch, 128), 128, 0, t, (const uint32_t *)lf.sa.get(), lf.mt, lf.s, a1, chl, r1, nch, r0);
+}
+
+// K5 for the chains [c_lo,c_hi): G += gaps, gtnew[p-a1], rsamp[p/rate]
+void Engine::gap_run(GapCtx & ctx, uint64_t a1, uint64_t r1, uint64_t chl, uint64_t nch, uint64_t c_lo, uint64_t c_hi, const uint32_t * r0,
+                     const uint8_t * gt_in, uint8_t * gtnew, uint32_t termA, uint32_t * G, uint32_t * rs) {
+	TextRef const t = text_ref(T);
+	if (c_hi > nch) c_hi = nch;
+	if (c_lo >= c_hi) return;
+	if (!(T.has_term && r1 == T.n)) B3M_LAUNCH(st, k_gt_top, 1, 1, 0, t, r1, a1, d_special.get());
+	uint64_t const steps = std::min(a1 + c_hi * chl, r1) - (a1 + c_lo * chl);
+	B3M_LAUNCH_T(st, "gap_chains", steps * 128ull, k_gap, (unsigned)div_up(c_hi - c_lo, 256), 256, 0, ctx.D, ctx.C, t, a1, r1, chl, c_lo, c_hi, r0,
+	             gt_in, gtnew, (const uint32_t *)d_special.get(), termA, prerate - 1, ilog2u(prerate), G, rs);
+	gap_lf_steps += steps; gap_chains += c_hi - c_lo;
+}
+
+// K6: LM = merge of LA and LR by G; G is left holding its inclusive prefix sums
+void Engine::merge_run(const uint8_t * LA, uint64_t na, uint32_t termA, uint8_t * LR, uint64_t nr, uint32_t termR, uint64_t a1, uint32_t * G,
+                       uint8_t * LM, uint32_t * termM) {
 	// the stale placeholder of R becomes the true seam symbol T[a1-1] (Appendix A.4)
-	B3M_CUDA(cudaMemcpyAsync(R.L.get() + R.term, T.codes + a1 - 1, 1, cudaMemcpyDeviceToDevice, st.s));
-	M.a0 = a0; M.a1 = r1;
-	M.L.alloc(st, na + nr + 16);
+	B3M_CUDA(cudaMemcpyAsync(LR + termR, T.codes + a1 - 1, 1, cudaMemcpyDeviceToDevice, st.s));
 	DevBuf<BigGap> big(st, nr / BIG_GAP + 2);
 	uint32_t * bigcount = d_special.get() + 3;
 	B3M_CUDA(cudaMemsetAsync(bigcount, 0, 4, st.s));
 	{
-		uint32_t * g = G.get();
-		const uint8_t * LA = A.L.get();
-		const uint8_t * LR = R.L.get();
-		uint8_t * LM = M.L.get();
+		uint32_t * g = G;
+		const uint8_t * LRc = LR;
 		BigGap * bl = big.get();
 		uint64_t const nal = na;
 		scan_apply<OpSum>(st, na + 1,
 			[=] __device__(uint64_t k) -> uint32_t { return g[k]; },
 			[=] __device__(uint64_t k, uint32_t excl, uint32_t v) {
 				uint64_t const o = k + excl;
-				if (v <= BIG_GAP) { for (uint32_t x = 0; x < v; ++x) LM[o + x] = LR[excl + x]; }
+				if (v <= BIG_GAP) { for (uint32_t x = 0; x < v; ++x) LM[o + x] = LRc[excl + x]; }
 				else { uint32_t const e = atomicAdd(bigcount, 1u); bl[e] = BigGap{excl, (uint32_t)o, v}; }
 				if (k < nal) LM[o + v] = LA[k];
 				g[k] = excl + v;
 			}, "merge_scatter", 8ull * (na + 1) + 2ull * (na + nr));
-		B3M_LAUNCH(st, k_copy_big, dim3((unsigned)st.sms, 64), 256, 0, (const BigGap *)bl, (const uint32_t *)bigcount, LR, LM);
+		B3M_LAUNCH(st, k_copy_big, dim3((unsigned)st.sms, 64), 256, 0, (const BigGap *)bl, (const uint32_t *)bigcount, LRc, LM);
 	}
-	// anchors and the row of the merged node's block-start suffix move by the same rank maps
-	uint64_t const qA0 = div_up(a0, prerate), qA1 = div_up(a1, prerate), qR1 = div_up(r1, prerate);
-	if (qR1 > qA0)
-		B3M_LAUNCH(st, k_merge_samples, (unsigned)div_up(qR1 - qA0, 256), 256, 0, prerank.get(), qA0, qA1, qR1, (const uint32_t *)G.get(), (const uint32_t *)rsamp.get());
-	B3M_CUDA(cudaMemcpyAsync(pinned, G.get() + A.term, 4, cudaMemcpyDeviceToHost, st.s));
+	B3M_CUDA(cudaMemcpyAsync(pinned, G + termA, 4, cudaMemcpyDeviceToHost, st.s));
 	B3M_CUDA(cudaStreamSynchronize(st.s));
-	M.term = A.term + *(uint32_t *)pinned;
+	*termM = termA + *(uint32_t *)pinned;
 	merge_bytes += 8ull * (na + 1) + 2ull * (na + nr);
+}
+
+// anchors move by the same rank maps (Appendix A.4)
+void Engine::merge_samples(uint64_t a0, uint64_t a1, uint64_t r1, uint32_t * pre, const uint32_t * Sincl, const uint32_t * rs) {
+	uint64_t const qA0 = div_up(a0, prerate), qA1 = div_up(a1, prerate), qR1 = div_up(r1, prerate);
+	if (qR1 > qA0) B3M_LAUNCH(st, k_merge_samples, (unsigned)div_up(qR1 - qA0, 256), 256, 0, pre, qA0, qA1, qR1, Sincl, rs);
+}
+
+// A7 + A8: merge node A = [a0,a1) (left) with R = [a1,r1) (right) into M.
+void Engine::node_merge(BlockNode & A, BlockNode & R, std::vector<BlockLeaf> & leaves, BlockNode & M, EventAccum & tgap, EventAccum & tmerge) {
+	uint64_t const a0 = A.a0, a1 = A.a1, r1 = R.a1;
+	uint64_t const na = a1 - a0, nr = r1 - a1;
+	B3M_REQUIRE(R.a0 == a1, "internal: merge of non-adjacent nodes");
+	tgap.begin();
+	DevBuf<uint32_t> G(st, na + 1);
+	{
+		GapCtx ctx;
+		gap_prepare(ctx, A.L.get(), a0, na, A.term);
+		uint64_t chl, nch;
+		chain_geometry(nr, &chl, &nch);
+		DevBuf<uint32_t> r0(st, nch);
+		B3M_CUDA(cudaMemsetAsync(r0.get(), 0, 4 * nch, st.s));
+		zranks_add(leaves, a0, a1, r1, chl, nch, r0.get());
+		DevBuf<uint8_t> gtnew(st, nr);
+		B3M_CUDA(cudaMemsetAsync(G.get(), 0, 4 * (na + 1), st.s));
+		gap_run(ctx, a1, r1, chl, nch, 0, nch, r0.get(), gtp, gtnew.get(), A.term, G.get(), rsp);
+		B3M_CUDA(cudaMemcpyAsync(gtp + a1, gtnew.get(), nr, cudaMemcpyDeviceToDevice, st.s));
+	}
+	tgap.end();
+	tmerge.begin();
+	M.a0 = a0; M.a1 = r1;
+	M.L.alloc(st, na + nr + 16);
+	merge_run(A.L.get(), na, A.term, R.L.get(), nr, R.term, a1, G.get(), M.L.get(), &M.term);
+	merge_samples(a0, a1, r1, prep, G.get(), rsp);
 	tmerge.end();
 	A.L.release(); R.L.release();
 }
 
-void Engine::build_tree(std::vector<BlockLeaf> & leaves, uint64_t lo, uint64_t hi, uint64_t bs, BlockNode & out,
+void Engine::build_tree(std::vector<BlockLeaf> & leaves, uint64_t lo, uint64_t hi, uint64_t base, uint64_t end, uint64_t bs, BlockNode & out,
                         EventAccum & tsort, EventAccum & tgap, EventAccum & tmerge) {
 	if (hi - lo == 1) {
-		uint64_t const s = lo * bs, e = std::min(s + bs, T.n);
+		uint64_t const s = base + lo * bs, e = std::min(s + bs, end);
 		out.a0 = s; out.a1 = e;
 		out.L.alloc(st, e - s + 16);
 		tsort.begin();
@@ -363,8 +392,8 @@ void Engine::build_tree(std::vector<BlockLeaf> & leaves, uint64_t lo, uint64_t h
 	}
 	uint64_t const mid = (lo + hi) / 2;
 	BlockNode A, R;
-	build_tree(leaves, lo, mid, bs, A, tsort, tgap, tmerge);
-	build_tree(leaves, mid, hi, bs, R, tsort, tgap, tmerge);
+	build_tree(leaves, lo, mid, base, end, bs, A, tsort, tgap, tmerge);
+	build_tree(leaves, mid, hi, base, end, bs, R, tsort, tgap, tmerge);
 	node_merge(A, R, leaves, out, tgap, tmerge);
 }
 
@@ -374,13 +403,15 @@ void Engine::build_blocks(PhaseTimer & pt, uint32_t * exc_pos) {
 	B3M_REQUIRE(numblocks >= 2, "internal: build_blocks needs at least two blocks");
 	gt.alloc(st, T.n);
 	rsamp.alloc(st, npre);
+	gtp = gt.get(); prep = prerank.get(); rsp = rsamp.get();
 	std::vector<BlockLeaf> leaves(numblocks);
 	EventAccum tsort(st), tgap(st), tmerge(st);
 	BlockNode root;
 	sortstats = SortStats();
-	build_tree(leaves, 0, numblocks, bs, root, tsort, tgap, tmerge);
+	build_tree(leaves, 0, numblocks, 0, T.n, bs, root, tsort, tgap, tmerge);
 	leaves.clear();
 	gt.release(); rsamp.release();
+	gtp = nullptr; rsp = nullptr;
 	// root: the remaining placeholder is the row of suffix 0 (Appendix A.4)
 	if (T.has_term) *exc_pos = root.term;
 	else {
@@ -393,4 +424,153 @@ void Engine::build_blocks(PhaseTimer & pt, uint32_t * exc_pos) {
 	(void)pt;
 }
 
+// ------------------------------------------------------------------------------------------
+// Multi-GPU driver entry points (C ABI b3m_engine_blk_*): the same primitives on caller-owned
+// device buffers, so that block BWTs, gap arrays, gt bits and anchors can travel between the
+// ranks with NCCL.
+// ------------------------------------------------------------------------------------------
+void Engine::blk_begin(uint64_t preisarate, uint64_t largelcpthres, void * d_gt, void * d_prerank, void * d_rsamp) {
+	B3M_CUDA(cudaSetDevice(device));
+	B3M_REQUIRE(loaded, "no input loaded");
+	B3M_REQUIRE(d_gt && d_prerank && d_rsamp, "null block buffers");
+	reset_results();
+	params = b3m_build_params();
+	params.largelcpthres = largelcpthres ? largelcpthres : 16384;
+	prerate = preisarate ? preisarate : choose_preisarate_pub(T.n);
+	B3M_REQUIRE(prerate && !(prerate & (prerate - 1)), "preisarate must be a power of two");
+	npre = div_up(T.n, prerate);
+	gtp = (uint8_t *)d_gt; prep = (uint32_t *)d_prerank; rsp = (uint32_t *)d_rsamp;
+	dist_leaves.clear();
+	sortstats = SortStats(); walkstats = WalkStats();
+	gap_lf_steps = gap_chains = merge_bytes = extract_bytes = 0; max_lcpnext = large_lcp_blocks = 0;
+	ms_sort = ms_extract = ms_dict = ms_gap = ms_merge = ms_walk = ms_total = 0;
+	d_special.alloc(st, 8);
+	B3M_CUDA(cudaMemsetAsync(d_special.get(), 0xff, 16, st.s));
+}
+
+void Engine::blk_build_range(uint64_t a0, uint64_t a1, uint64_t nb, void * d_L_out, uint32_t * term_out) {
+	B3M_CUDA(cudaSetDevice(device));
+	B3M_REQUIRE(gtp, "blk_begin was not called");
+	B3M_REQUIRE(a0 < a1 && a1 <= T.n, "bad text range");
+	uint64_t const m = a1 - a0;
+	if (nb < 1) nb = 1;
+	if (nb > m) nb = m;
+	uint64_t const bs = div_up(m, nb);
+	nb = div_up(m, bs);
+	EventAccum tsort(st), tgap(st), tmerge(st);
+	size_t const first = dist_leaves.size();
+	dist_leaves.resize(first + nb);
+	// build_tree indexes leaves from 0: work on a temporary vector, then move
+	std::vector<BlockLeaf> lv(nb);
+	BlockNode root;
+	build_tree(lv, 0, nb, a0, a1, bs, root, tsort, tgap, tmerge);
+	for (uint64_t b = 0; b < nb; ++b) dist_leaves[first + b] = std::move(lv[b]);
+	B3M_CUDA(cudaMemcpyAsync(d_L_out, root.L.get(), m, cudaMemcpyDeviceToDevice, st.s));
+	B3M_CUDA(cudaStreamSynchronize(st.s));
+	*term_out = root.term;
+	ms_sort += tsort.total(); ms_gap += tgap.total(); ms_merge += tmerge.total();
+}
+
+void Engine::blk_finish(const void * d_L_root, uint32_t term_root, uint64_t q_lo, uint64_t q_hi, uint64_t sarate, uint64_t isarate, int bwtonly, uint64_t nblocks) {
+	B3M_CUDA(cudaSetDevice(device));
+	B3M_REQUIRE(gtp, "blk_begin was not called");
+	auto pow2 = [](uint64_t v) { return v && !(v & (v - 1)); };
+	B3M_REQUIRE(pow2(sarate) && pow2(isarate), "sampling rates must be powers of two");
+	params.sasamplingrate = sarate; params.isasamplingrate = isarate; params.bwtonly = bwtonly; params.preisarate = prerate;
+	numblocks = nblocks;
+	bwt.alloc(st, T.n + 16);
+	B3M_CUDA(cudaMemcpyAsync(bwt.get(), d_L_root, T.n, cudaMemcpyDeviceToDevice, st.s));
+	prerank.alloc(st, npre);
+	B3M_CUDA(cudaMemcpyAsync(prerank.get(), prep, 4 * npre, cudaMemcpyDeviceToDevice, st.s));
+	uint32_t exc_pos = 0xffffffffu;
+	if (T.has_term) exc_pos = term_root;
+	else B3M_CUDA(cudaMemcpyAsync(bwt.get() + term_root, T.codes + T.n - 1, 1, cudaMemcpyDeviceToDevice, st.s));
+	root_exc_pos = exc_pos;
+	PhaseTimer pt(st);
+	pt.mark();
+	make_dict(exc_pos, 0, 0);
+	pt.mark();
+	nsa = nisa = 0;
+	if (!bwtonly) {
+		nsa = div_up(T.n, sarate); nisa = div_up(T.n, isarate);
+		sa.alloc(st, nsa); isa.alloc(st, nisa);
+		B3M_CUDA(cudaMemsetAsync(sa.get(), 0xff, 8 * nsa, st.s));
+		B3M_CUDA(cudaMemsetAsync(isa.get(), 0xff, 8 * nisa, st.s));
+		if (q_hi > npre) q_hi = npre;
+		if (q_lo < q_hi)
+			k7_walk(st, D, prerank.get(), npre, prerate, T.n, sarate, isarate, sa.get(), isa.get(), &walkstats, q_lo, q_hi);
+	}
+	pt.mark();
+	B3M_CUDA(cudaStreamSynchronize(st.s));
+	ms_dict = pt.ms(0, 1); ms_walk = pt.ms(1, 2);
+	gtp = nullptr; rsp = nullptr; prep = nullptr;
+	dist_leaves.clear();
+	have_results = true;
+}
+
 } // namespace b3m
+
+// ---- C ABI ----------------------------------------------------------------------------------
+struct b3m_engine { b3m::Engine * e; std::string err; };
+#define B3M_GUARD(h, ...)                                                    \
+	if (!(h)) return 1;                                                      \
+	try { __VA_ARGS__; (h)->err.clear(); return 0; }                                \
+	catch (std::exception const & ex) { (h)->err = ex.what(); return 2; }    \
+	catch (...) { (h)->err = "unknown error"; return 3; }
+
+extern "C" {
+
+int b3m_engine_default_preisarate(b3m_engine * h, int bwtonly, uint64_t * rate) {
+	B3M_GUARD(h, { if (!rate) throw b3m::Error("null argument"); B3M_REQUIRE(h->e->loaded, "no input loaded"); *rate = bwtonly ? 64 : h->e->choose_preisarate_pub(h->e->T.n); });
+}
+int b3m_engine_blk_begin(b3m_engine * h, uint64_t preisarate, uint64_t largelcpthres, void * d_gt, void * d_prerank, void * d_rsamp) {
+	B3M_GUARD(h, h->e->blk_begin(preisarate, largelcpthres, d_gt, d_prerank, d_rsamp));
+}
+int b3m_engine_blk_build_range(b3m_engine * h, uint64_t a0, uint64_t a1, uint64_t numblocks, void * d_L_out, uint32_t * term_out) {
+	B3M_GUARD(h, { if (!d_L_out || !term_out) throw b3m::Error("null argument"); h->e->blk_build_range(a0, a1, numblocks, d_L_out, term_out); });
+}
+int b3m_engine_blk_chains(b3m_engine * h, uint64_t nr, uint64_t * chl, uint64_t * nch) {
+	B3M_GUARD(h, { if (!chl || !nch) throw b3m::Error("null argument"); h->e->chain_geometry(nr, chl, nch); });
+}
+int b3m_engine_blk_zranks(b3m_engine * h, uint64_t a0, uint64_t a1, uint64_t r1, uint64_t chl, uint64_t nch, void * d_r0) {
+	B3M_GUARD(h, { B3M_CUDA(cudaSetDevice(h->e->device)); h->e->zranks_add(h->e->dist_leaves, a0, a1, r1, chl, nch, (uint32_t *)d_r0); });
+}
+int b3m_engine_blk_gap(b3m_engine * h, const void * d_LA, uint64_t a0, uint64_t na, uint32_t termA, uint64_t r1, uint64_t chl, uint64_t nch,
+                       uint64_t c_lo, uint64_t c_hi, const void * d_r0, void * d_gtnew, void * d_G) {
+	B3M_GUARD(h, {
+		b3m::Engine & e = *h->e;
+		B3M_CUDA(cudaSetDevice(e.device));
+		B3M_REQUIRE(e.gtp, "blk_begin was not called");
+		b3m::EventAccum tg(e.st);
+		tg.begin();
+		b3m::GapCtx ctx;
+		e.gap_prepare(ctx, (const uint8_t *)d_LA, a0, na, termA);
+		e.gap_run(ctx, a0 + na, r1, chl, nch, c_lo, c_hi, (const uint32_t *)d_r0, e.gtp, (uint8_t *)d_gtnew, termA, (uint32_t *)d_G, e.rsp);
+		tg.end();
+		B3M_CUDA(cudaStreamSynchronize(e.st.s));
+		e.ms_gap += tg.total();
+	});
+}
+int b3m_engine_blk_merge(b3m_engine * h, const void * d_LA, uint64_t na, uint32_t termA, void * d_LR, uint64_t nr, uint32_t termR, uint64_t a1,
+                         void * d_G, void * d_LM, uint32_t * termM) {
+	B3M_GUARD(h, {
+		b3m::Engine & e = *h->e;
+		B3M_CUDA(cudaSetDevice(e.device));
+		if (!termM) throw b3m::Error("null argument");
+		b3m::EventAccum tm(e.st);
+		tm.begin();
+		e.merge_run((const uint8_t *)d_LA, na, termA, (uint8_t *)d_LR, nr, termR, a1, (uint32_t *)d_G, (uint8_t *)d_LM, termM);
+		tm.end();
+		B3M_CUDA(cudaStreamSynchronize(e.st.s));
+		e.ms_merge += tm.total();
+	});
+}
+int b3m_engine_blk_merge_samples(b3m_engine * h, uint64_t a0, uint64_t a1, uint64_t r1, const void * d_Sincl) {
+	B3M_GUARD(h, { B3M_CUDA(cudaSetDevice(h->e->device)); B3M_REQUIRE(h->e->gtp, "blk_begin was not called"); h->e->merge_samples(a0, a1, r1, h->e->prep, (const uint32_t *)d_Sincl, h->e->rsp); });
+}
+int b3m_engine_blk_finish(b3m_engine * h, const void * d_L_root, uint32_t term_root, uint64_t q_lo, uint64_t q_hi, uint64_t sasamplingrate,
+                          uint64_t isasamplingrate, int bwtonly, uint64_t numblocks) {
+	B3M_GUARD(h, { if (!d_L_root) throw b3m::Error("null argument"); h->e->blk_finish(d_L_root, term_root, q_lo, q_hi, sasamplingrate, isasamplingrate, bwtonly, numblocks); });
+}
+
+} // extern "C"

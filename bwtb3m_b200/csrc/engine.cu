@@ -178,6 +178,8 @@ static uint64_t choose_preisarate(uint64_t n, int sms) {
 	return r;
 }
 
+uint64_t Engine::choose_preisarate_pub(uint64_t n) const { return choose_preisarate(n, st.sms); }
+
 void Engine::make_dict(uint32_t exc_pos, uint32_t exc_code, uint32_t exc_lf) {
 	int const flavour = T.sigma <= 4 ? 2 : 8;
 	size_t const bytes = dict_bytes(flavour, T.n, T.sigma);
@@ -248,7 +250,7 @@ void Engine::build(b3m_build_params const & p) {
 		sa.alloc(st, nsa); isa.alloc(st, nisa);
 		B3M_LAUNCH(st, k_fill_u64, (unsigned)div_up(nsa, 256), 256, 0, (unsigned long long *)sa.get(), nsa, ~0ull);
 		B3M_LAUNCH(st, k_fill_u64, (unsigned)div_up(nisa, 256), 256, 0, (unsigned long long *)isa.get(), nisa, ~0ull);
-		k7_walk(st, D, prerank.get(), npre, prerate, T.n, p.sasamplingrate, p.isasamplingrate, sa.get(), isa.get(), &walkstats);
+		k7_walk(st, D, prerank.get(), npre, prerate, T.n, p.sasamplingrate, p.isasamplingrate, sa.get(), isa.get(), &walkstats, 0, npre);
 	}
 	pt.mark(); // 4
 	B3M_CUDA(cudaStreamSynchronize(st.s));
@@ -439,10 +441,7 @@ void Engine::lf_bench(uint64_t nchains, uint64_t steps, float * ms, uint64_t * c
 // ------------------------------------------------------------------------------------------
 using b3m::Engine;
 
-struct b3m_engine {
-	Engine * e;
-	std::string err;
-};
+struct b3m_engine { b3m::Engine * e; std::string err; };
 
 static void set_err(char * err, size_t errlen, const char * msg) {
 	if (err && errlen) { strncpy(err, msg, errlen - 1); err[errlen - 1] = 0; }

@@ -2,6 +2,7 @@
 #pragma once
 #include "../../include/b3m.h"
 #include "kernels.h"
+#include "rankdict.cuh"
 
 namespace b3m {
 
@@ -15,6 +16,13 @@ struct PhaseTimer {
 	float ms(int a, int b) { float t = 0; cudaEventElapsedTime(&t, ev[a], ev[b]); return t; }
 };
 struct EventAccum;
+
+// what K5 needs from the left part of a merge: rank dictionary over L_A and C_A
+struct GapCtx {
+	DevBuf<uint8_t> lines;
+	DictView D;
+	CTab C;
+};
 
 // one leaf of the merge tree: the block's own suffixes in sorted order (kept for z-ranks)
 struct BlockLeaf {
@@ -76,11 +84,28 @@ struct Engine {
 	void load(const void * input, uint64_t nbytes, int itype, bool on_device);
 	void build(b3m_build_params const & p);
 	void build_blocks(PhaseTimer & pt, uint32_t * exc_pos);
-	void build_tree(std::vector<BlockLeaf> & leaves, uint64_t lo, uint64_t hi, uint64_t bs, BlockNode & out,
+	void build_tree(std::vector<BlockLeaf> & leaves, uint64_t lo, uint64_t hi, uint64_t base, uint64_t end, uint64_t bs, BlockNode & out,
 	                EventAccum & tsort, EventAccum & tgap, EventAccum & tmerge);
 	void leaf_build(BlockLeaf & leaf, uint64_t s, uint64_t m, uint8_t * L, uint32_t * term_pos, SortStats * ss);
 	void node_merge(BlockNode & A, BlockNode & R, std::vector<BlockLeaf> & leaves, BlockNode & M, EventAccum & tgap, EventAccum & tmerge);
 	uint32_t fetch_special(int slot);
+	// block-level buffers in use (the engine's own, or the caller's in the multi-GPU driver)
+	uint8_t * gtp = nullptr;
+	uint32_t * prep = nullptr;
+	uint32_t * rsp = nullptr;
+	std::vector<BlockLeaf> dist_leaves;
+	uint64_t choose_preisarate_pub(uint64_t n) const;
+	void blk_begin(uint64_t preisarate, uint64_t largelcpthres, void * d_gt, void * d_prerank, void * d_rsamp);
+	void blk_build_range(uint64_t a0, uint64_t a1, uint64_t nb, void * d_L_out, uint32_t * term_out);
+	void blk_finish(const void * d_L_root, uint32_t term_root, uint64_t q_lo, uint64_t q_hi, uint64_t sarate, uint64_t isarate, int bwtonly, uint64_t nblocks);
+	void gap_prepare(GapCtx & ctx, const uint8_t * LA, uint64_t a0, uint64_t na, uint32_t termA);
+	void chain_geometry(uint64_t nr, uint64_t * chl, uint64_t * nch) const;
+	void zranks_add(std::vector<BlockLeaf> & lv, uint64_t a0, uint64_t a1, uint64_t r1, uint64_t chl, uint64_t nch, uint32_t * r0);
+	void gap_run(GapCtx & ctx, uint64_t a1, uint64_t r1, uint64_t chl, uint64_t nch, uint64_t c_lo, uint64_t c_hi, const uint32_t * r0,
+	             const uint8_t * gt_in, uint8_t * gtnew, uint32_t termA, uint32_t * G, uint32_t * rs);
+	void merge_run(const uint8_t * LA, uint64_t na, uint32_t termA, uint8_t * LR, uint64_t nr, uint32_t termR, uint64_t a1, uint32_t * G,
+	               uint8_t * LM, uint32_t * termM);
+	void merge_samples(uint64_t a0, uint64_t a1, uint64_t r1, uint32_t * pre, const uint32_t * Sincl, const uint32_t * rs);
 	// K8 / output side
 	uint64_t rl_bytes = 0, rl_nruns = 0;
 	void symbols_device(DevBuf<uint8_t> & out);

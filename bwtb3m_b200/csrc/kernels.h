@@ -25,6 +25,8 @@ struct TextRef {
 	int has_term;
 };
 
+struct CTab { uint32_t c[257]; }; // C[code] passed to kernels by value
+
 // ---- K1 ---------------------------------------------------------------------------------
 void k1_hist_bytes(Stream & st, const uint8_t * d_in, uint64_t nbytes, uint64_t * d_hist256);
 void k1_map_bytes(Stream & st, const uint8_t * d_in, uint64_t n, const uint8_t * d_lut256, uint8_t * d_out);
@@ -76,7 +78,8 @@ struct WalkStats { uint64_t steps = 0; uint64_t chains = 0; };
 // sampling SA by rank and ISA by position.  pos_off: value added to a text position before it
 // is reported (0), n: BWT length.
 void k7_walk(Stream & st, DevDict const & D, const uint32_t * anchor_rank, uint64_t nanchors, uint64_t arate,
-             uint64_t n, uint64_t sarate, uint64_t isarate, uint64_t * sa_out, uint64_t * isa_out, WalkStats * ws);
+             uint64_t n, uint64_t sarate, uint64_t isarate, uint64_t * sa_out, uint64_t * isa_out, WalkStats * ws,
+             uint64_t q_lo, uint64_t q_hi /* anchors [q_lo,q_hi) only: the multi-GPU driver splits them over the ranks */);
 // the same from anchors at arbitrary positions: anchor_steps[q] = distance to the previous anchor
 void k7_walk_anchors(Stream & st, DevDict const & D, const uint32_t * anchor_rank, const uint64_t * anchor_pos, const uint64_t * anchor_steps,
                      uint64_t nanchors, uint64_t n, uint64_t sarate, uint64_t isarate, uint64_t * sa_out, uint64_t * isa_out, WalkStats * ws);

@@ -330,9 +330,9 @@ __device__ __forceinline__ uint32_t lf_step(DictView const & D, CTable const & C
 __global__ void __launch_bounds__(256)
 k_walk(DictView D, CTable C, uint32_t exc_lf, const uint32_t * __restrict__ anchor_rank, uint64_t nanchors, uint64_t arate, uint64_t n,
        uint32_t samask, uint32_t sashift, uint32_t isamask, uint32_t isashift,
-       unsigned long long * __restrict__ sa_out, unsigned long long * __restrict__ isa_out) {
-	uint64_t const q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (q >= nanchors) return;
+       unsigned long long * __restrict__ sa_out, unsigned long long * __restrict__ isa_out, uint64_t q_lo, uint64_t q_hi) {
+	uint64_t const q = q_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= q_hi) return;
 	uint32_t r = anchor_rank[q];
 	uint64_t p = q * arate;
 	uint64_t steps = q ? arate : n - (nanchors - 1) * arate;
@@ -391,14 +391,18 @@ static unsigned ilog2_exact(uint64_t v) {
 }
 
 void k7_walk(Stream & st, DevDict const & D, const uint32_t * anchor_rank, uint64_t nanchors, uint64_t arate,
-             uint64_t n, uint64_t sarate, uint64_t isarate, uint64_t * sa_out, uint64_t * isa_out, WalkStats * ws) {
-	if (!nanchors) return;
+             uint64_t n, uint64_t sarate, uint64_t isarate, uint64_t * sa_out, uint64_t * isa_out, WalkStats * ws, uint64_t q_lo, uint64_t q_hi) {
+	if (q_hi > nanchors) q_hi = nanchors;
+	if (q_lo >= q_hi) return;
 	CTable C;
 	for (int i = 0; i < 257; ++i) C.c[i] = D.C[i];
-	B3M_LAUNCH_T(st, "lf_walk", n * 64ull, k_walk, (unsigned)div_up(nanchors, 256), 256, 0, make_view(D), C, D.exc_lf, anchor_rank, nanchors, arate, n,
+	// anchor q walks arate steps back to anchor q-1; anchor 0 walks around the end of the text
+	uint64_t steps = (q_hi - q_lo) * arate;
+	if (q_lo == 0) steps = steps - arate + (n - (nanchors - 1) * arate);
+	B3M_LAUNCH_T(st, "lf_walk", steps * 64ull, k_walk, (unsigned)div_up(q_hi - q_lo, 256), 256, 0, make_view(D), C, D.exc_lf, anchor_rank, nanchors, arate, n,
 	           (uint32_t)(sarate - 1), ilog2_exact(sarate), (uint32_t)(isarate - 1), ilog2_exact(isarate),
-	           (unsigned long long *)sa_out, (unsigned long long *)isa_out);
-	if (ws) { ws->steps += n; ws->chains += nanchors; }
+	           (unsigned long long *)sa_out, (unsigned long long *)isa_out, q_lo, q_hi);
+	if (ws) { ws->steps += steps; ws->chains += q_hi - q_lo; }
 }
 
 void k7_walk_anchors(Stream & st, DevDict const & D, const uint32_t * anchor_rank, const uint64_t * anchor_pos, const uint64_t * anchor_steps,

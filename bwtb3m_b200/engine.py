@@ -26,6 +26,7 @@ class Engine:
         if rc != 0:
             raise B3MError(err.value.decode() or "b3m_engine_create failed (%d)" % rc)
         self._h = h
+        self.stream_ptr = stream or 0
 
     def close(self):
         if getattr(self, "_h", None):
@@ -113,6 +114,12 @@ class Engine:
         isa = np.empty(i["nisa"], dtype=np.uint64)
         self._check(self._lib.b3m_engine_fetch(self._h, None, None, _ptr(sa), _ptr(isa)))
         return sa, isa
+
+    def default_preisarate(self, bwtonly=False):
+        """Anchor spacing the engine would choose for the loaded text."""
+        r = C.c_uint64(0)
+        self._check(self._lib.b3m_engine_default_preisarate(self._h, 1 if bwtonly else 0, C.byref(r)))
+        return int(r.value)
 
     def lf_bench(self, nchains, steps):
         ms = C.c_float(0)

@@ -1,0 +1,260 @@
+"""Multi-GPU driver: one process per GPU, text replicated, rank i sorts text range i, the balanced
+merge tree runs over torch.distributed (NCCL on GPUs, gloo in the CPU tests of the schedule).
+
+Replaces the block scheduling + merge tree of BwtMergeSortTemplate::computeBwt (libmaus2, reached
+from /root/reference/src/bwtb3m.cpp:63) for the case "blocks sharded over the GPUs of one box"
+(SURVEY.md 8e).  Per merge of A=[a0,a1) (ranks lo..mid-1, leader lo) and R=[a1,r1) (ranks
+mid..hi-1, leader mid):
+
+  1. broadcast L_A from lo and gt[a1:r1] from mid to the whole group,
+  2. every rank of A's side adds the z-ranks of its own leaves, all-reduce(sum) -> start ranks,
+  3. the chains of R's text are split evenly over ALL ranks of the group (K5 on each),
+  4. reduce(sum) the partial gap arrays and anchor ranks to lo, send L_R and R's anchors to lo,
+  5. lo merges (K6); if the node is needed as a right part later, its new gt bits are
+     all-reduced over the group.
+
+The arithmetic is behind an `ops` object: EngineOps (CUDA engine through the C ABI) on GPUs; the
+CPU tests plug in a numpy model of the same primitives to exercise this schedule under gloo.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def block_range(n, world, i):
+    bs = (n + world - 1) // world
+    return min(i * bs, n), min((i + 1) * bs, n)
+
+
+def tree_groups(world):
+    """All rank intervals [lo,hi) of the balanced merge tree with more than one rank, in a fixed
+    order (every rank must create the process groups in the same order)."""
+    out = []
+
+    def rec(lo, hi):
+        if hi - lo <= 1:
+            return
+        out.append((lo, hi))
+        mid = (lo + hi) // 2
+        rec(lo, mid)
+        rec(mid, hi)
+
+    rec(0, world)
+    return out
+
+
+class DistBuild:
+    """Runs the distributed build on the calling rank.  ops: see EngineOps."""
+
+    def __init__(self, ops, rank=None, world=None):
+        self.ops = ops
+        self.rank = dist.get_rank() if rank is None else rank
+        self.world = dist.get_world_size() if world is None else world
+        self.groups, self.pairs = {}, {}
+        for lo, hi in tree_groups(self.world):
+            g = dist.new_group(ranks=list(range(lo, hi)))
+            self.groups[(lo, hi)] = g
+            # the two leaders of a merge exchange L_R and R's anchors inside their own 2-rank group
+            self.pairs[(lo, hi)] = g if hi - lo == 2 else dist.new_group(ranks=[lo, (lo + hi) // 2])
+        self.stats = {"bytes_sent": 0, "merges": 0}
+
+    # -- 32-bit unsigned counters travel as int32 tensors: NCCL has no uint32, and a two's
+    #    complement sum has the same bits --
+    @staticmethod
+    def _i32(t):
+        return t
+
+    def _bcast(self, t, src, group):
+        dist.broadcast(self._i32(t), src=src, group=group)
+
+    def _allreduce_sum(self, t, group):
+        dist.all_reduce(self._i32(t), op=dist.ReduceOp.SUM, group=group)
+
+    def _reduce_sum(self, t, dst, group):
+        dist.reduce(self._i32(t), dst=dst, op=dist.ReduceOp.SUM, group=group)
+
+    def build(self, local_blocks=1, sasamplingrate=32, isasamplingrate=262144, bwtonly=False):
+        ops, r, W = self.ops, self.rank, self.world
+        n = ops.n
+        if n < 2 * W:
+            raise ValueError("text too short for %d ranks" % W)
+        self.gt = ops.zeros(n, torch.uint8)
+        self.prerank = ops.zeros(ops.npre, torch.int32)
+        self.rsamp = ops.zeros(ops.npre, torch.int32)
+        ops.begin(self.gt, self.prerank, self.rsamp)
+        node = self._rec(0, W, False, local_blocks)
+        # root: every rank gets the final BWT and the anchors, walks its share of the chains
+        L = node["L"] if r == 0 else ops.zeros(n + 16, torch.uint8)
+        meta = ops.zeros(1, torch.int64)
+        if r == 0:
+            meta[0] = node["term"]
+        if W > 1:
+            dist.broadcast(L, src=0)
+            dist.broadcast(meta, src=0)
+            self._bcast(self.prerank, 0, None)
+        term = int(meta[0].item())
+        q_lo, q_hi = ops.npre * r // W, ops.npre * (r + 1) // W
+        sa, isa = ops.finish(L, term, q_lo, q_hi, sasamplingrate, isasamplingrate, bwtonly, W * local_blocks)
+        if not bwtonly and W > 1:
+            # unset entries are ~0 = -1 as int64; every entry is set by exactly one rank
+            dist.reduce(sa.view(torch.int64), dst=0, op=dist.ReduceOp.MAX)
+            dist.reduce(isa.view(torch.int64), dst=0, op=dist.ReduceOp.MAX)
+        return {"L": L, "term": term, "sa": sa, "isa": isa}
+
+    def _rec(self, lo, hi, need_gt, local_blocks):
+        ops, r, n, W = self.ops, self.rank, self.ops.n, self.world
+        if hi - lo == 1:
+            a0, a1 = block_range(n, W, lo)
+            L = ops.zeros(a1 - a0 + 16, torch.uint8)
+            term = ops.build_range(a0, a1, local_blocks, L)
+            return {"a0": a0, "a1": a1, "L": L, "term": term}
+        mid = (lo + hi) // 2
+        mine = self._rec(lo, mid, need_gt, local_blocks) if r < mid else self._rec(mid, hi, True, local_blocks)
+        group = self.groups[(lo, hi)]
+        a0, a1, r1 = block_range(n, W, lo)[0], block_range(n, W, mid)[0], block_range(n, W, hi - 1)[1]
+        na, nr = a1 - a0, r1 - a1
+        # 1. placeholders rows, L_A and R's gt bits to everybody in the group
+        meta = ops.zeros(2, torch.int64)
+        if r == lo:
+            meta[0] = mine["term"]
+        if r == mid:
+            meta[1] = mine["term"]
+        dist.all_reduce(meta, op=dist.ReduceOp.SUM, group=group)
+        termA, termR = int(meta[0].item()), int(meta[1].item())
+        LA = mine["L"] if r == lo else ops.zeros(na + 16, torch.uint8)
+        dist.broadcast(LA, src=lo, group=group)
+        dist.broadcast(self.gt[a1:r1], src=mid, group=group)
+        self.stats["bytes_sent"] += (na + 16 + nr) * (hi - lo - 1) if r in (lo, mid) else 0
+        # 2. start ranks of the chains
+        chl, nch = ops.chains(nr)
+        r0 = ops.zeros(nch, torch.int32)
+        if r < mid:
+            ops.zranks(a0, a1, r1, chl, nch, r0)
+        self._allreduce_sum(r0, group)
+        # 3. K5 on this rank's share of the chains
+        P, g = hi - lo, r - lo
+        c_lo, c_hi = nch * g // P, nch * (g + 1) // P
+        G = ops.zeros(na + 1, torch.int32)
+        gtnew = ops.zeros(nr, torch.uint8)
+        qA1, qR1 = -(-a1 // ops.prerate), -(-r1 // ops.prerate)
+        self.rsamp[qA1:qR1].zero_()
+        ops.gap(LA, a0, na, termA, r1, chl, nch, c_lo, c_hi, r0, gtnew, G)
+        # 4. partial gap arrays and anchor ranks to the leader; L_R and R's anchors to the leader
+        self._reduce_sum(G, lo, group)
+        if qR1 > qA1:
+            self._reduce_sum(self.rsamp[qA1:qR1], lo, group)
+        out = None
+        pair = self.pairs[(lo, hi)]
+        if r == mid:
+            dist.broadcast(mine["L"], src=mid, group=pair)
+            if qR1 > qA1:
+                dist.broadcast(self.prerank[qA1:qR1], src=mid, group=pair)
+            self.stats["bytes_sent"] += nr + 16
+        if r == lo:
+            LR = ops.zeros(nr + 16, torch.uint8)
+            dist.broadcast(LR, src=mid, group=pair)
+            if qR1 > qA1:
+                dist.broadcast(self.prerank[qA1:qR1], src=mid, group=pair)
+            LM = ops.zeros(na + nr + 16, torch.uint8)
+            termM = ops.merge(LA, na, termA, LR, nr, termR, a1, G, LM)
+            ops.merge_samples(a0, a1, r1, G)
+            out = {"a0": a0, "a1": r1, "L": LM, "term": termM}
+            self.stats["merges"] += 1
+        # 5. gt bits of the merged node, if it (or an ancestor reached through left links) is a right part later
+        if need_gt:
+            dist.all_reduce(gtnew, op=dist.ReduceOp.SUM, group=group)
+            self.gt[a1:r1].copy_(gtnew)
+        return out
+
+
+class _DevArray:
+    """Zero-copy view of engine-owned device memory for torch (CUDA array interface)."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+class EngineOps:
+    """The primitives of the build on one GPU, through the b3m_engine_blk_* C ABI."""
+
+    def __init__(self, engine, preisarate=0, largelcpthres=16384):
+        self.e = engine
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        i = engine.info()
+        self.n = i["n"]
+        self._preisarate = preisarate
+        self._largelcpthres = largelcpthres
+        # the anchor spacing must be known before the buffers are allocated: same rule as the engine
+        self.prerate = preisarate or engine.default_preisarate()
+        self.npre = (self.n + self.prerate - 1) // self.prerate
+
+    def zeros(self, n, dtype):
+        return torch.zeros(n, dtype=dtype, device=self.device)
+
+    def _chk(self, rc):
+        self.e._check(rc)
+
+    def begin(self, gt, prerank, rsamp):
+        self._keep = (gt, prerank, rsamp)
+        self._chk(self.e._lib.b3m_engine_blk_begin(self.e._h, self.prerate, self._largelcpthres, gt.data_ptr(), prerank.data_ptr(), rsamp.data_ptr()))
+
+    def build_range(self, a0, a1, nblocks, L):
+        t = C.c_uint32(0)
+        self._chk(self.e._lib.b3m_engine_blk_build_range(self.e._h, a0, a1, nblocks, L.data_ptr(), C.byref(t)))
+        return int(t.value)
+
+    def chains(self, nr):
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self._chk(self.e._lib.b3m_engine_blk_chains(self.e._h, nr, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def zranks(self, a0, a1, r1, chl, nch, r0):
+        self._chk(self.e._lib.b3m_engine_blk_zranks(self.e._h, a0, a1, r1, chl, nch, r0.data_ptr()))
+
+    def gap(self, LA, a0, na, termA, r1, chl, nch, c_lo, c_hi, r0, gtnew, G):
+        self._chk(self.e._lib.b3m_engine_blk_gap(self.e._h, LA.data_ptr(), a0, na, termA, r1, chl, nch, c_lo, c_hi, r0.data_ptr(),
+                                                 gtnew.data_ptr(), G.data_ptr()))
+
+    def merge(self, LA, na, termA, LR, nr, termR, a1, G, LM):
+        t = C.c_uint32(0)
+        self._chk(self.e._lib.b3m_engine_blk_merge(self.e._h, LA.data_ptr(), na, termA, LR.data_ptr(), nr, termR, a1, G.data_ptr(),
+                                                   LM.data_ptr(), C.byref(t)))
+        return int(t.value)
+
+    def merge_samples(self, a0, a1, r1, G):
+        self._chk(self.e._lib.b3m_engine_blk_merge_samples(self.e._h, a0, a1, r1, G.data_ptr()))
+
+    def finish(self, L, term, q_lo, q_hi, sarate, isarate, bwtonly, numblocks):
+        self._chk(self.e._lib.b3m_engine_blk_finish(self.e._h, L.data_ptr(), term, q_lo, q_hi, sarate, isarate, 1 if bwtonly else 0, numblocks))
+        if bwtonly:
+            return None, None
+        i = self.e.info()
+        p = [C.c_void_p() for _ in range(4)]
+        self._chk(self.e._lib.b3m_engine_device_results(self.e._h, *[C.byref(x) for x in p]))
+        sa = torch.as_tensor(_DevArray(p[2].value, i["nsa"], "<i8"), device=self.device)
+        isa = torch.as_tensor(_DevArray(p[3].value, i["nisa"], "<i8"), device=self.device)
+        return sa, isa
+
+
+def build_distributed(engine, local_blocks=1, preisarate=0, sasamplingrate=32, isasamplingrate=262144, bwtonly=False,
+                      largelcpthres=16384, driver=None):
+    """Every rank has loaded the same text into `engine`; after the call rank 0's engine holds the
+    complete results (fetch / write_bwt as after a single-GPU build)."""
+    ops = EngineOps(engine, preisarate, largelcpthres)
+    drv = driver or DistBuild(ops)
+    drv.ops = ops
+    with torch.cuda.stream(torch.cuda.ExternalStream(engine.stream_ptr)) if engine.stream_ptr else _null():
+        res = drv.build(local_blocks, sasamplingrate, isasamplingrate, bwtonly)
+        torch.cuda.current_stream().synchronize()
+    return drv, res
+
+
+class _null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False

@@ -174,6 +174,38 @@ int b3m_engine_fetch_runs(b3m_engine * e, uint8_t * syms, uint64_t * lens, uint6
 int b3m_engine_ssa_from_bwt(b3m_engine * e, const uint8_t * bwt, uint64_t n, const uint64_t * preisa_pairs, uint64_t npairs,
                             uint64_t sasamplingrate, uint64_t isasamplingrate);
 
+/* ---- multi-GPU driver: the steps of one merge on caller-owned DEVICE buffers -----------------
+ * One engine per GPU, text replicated (every rank calls b3m_engine_load_*), rank i sorts the text
+ * range [i*bs,(i+1)*bs); block BWTs, gap arrays, gt bits and anchors travel between the ranks
+ * with NCCL (bwtb3m_b200/multigpu.py is the driver).  Replaces the merge tree of
+ * BwtMergeSortTemplate::computeBwt (libmaus2; reached from /root/reference/src/bwtb3m.cpp:63).
+ *   d_gt      n bytes          gt[i] = [rot(i) > rot(start of i's node)]        (Appendix A.3)
+ *   d_prerank ceil(n/rate) u32 rank of position q*rate inside its current node
+ *   d_rsamp   ceil(n/rate) u32 r(j) at the anchors of the right part (written by blk_gap)     */
+/* anchor spacing b3m_engine_build would choose for the loaded text (64 when bwtonly, as the reference) */
+int b3m_engine_default_preisarate(b3m_engine * e, int bwtonly, uint64_t * rate);
+int b3m_engine_blk_begin(b3m_engine * e, uint64_t preisarate, uint64_t largelcpthres, void * d_gt, void * d_prerank, void * d_rsamp);
+/* sort the range [a0,a1) (numblocks leaves merged locally): d_L_out receives a1-a0 codes, the
+ * placeholder row (the reference's bwtterm) is returned in *term_out */
+int b3m_engine_blk_build_range(b3m_engine * e, uint64_t a0, uint64_t a1, uint64_t numblocks, void * d_L_out, uint32_t * term_out);
+/* chain geometry for a right part of nr symbols (identical on every rank) */
+int b3m_engine_blk_chains(b3m_engine * e, uint64_t nr, uint64_t * chl, uint64_t * nch);
+/* d_r0[c] (u32) += z-rank of chain c's start over this engine's leaves inside [a0,a1) */
+int b3m_engine_blk_zranks(b3m_engine * e, uint64_t a0, uint64_t a1, uint64_t r1, uint64_t chl, uint64_t nch, void * d_r0);
+/* K5 for the chains [c_lo,c_hi) of the merge A=[a0,a0+na) | R=[a0+na,r1): d_G (u32[na+1]) += gaps,
+ * d_gtnew[p-a1] = new gt bits, d_rsamp[p/rate] = r(p) */
+int b3m_engine_blk_gap(b3m_engine * e, const void * d_LA, uint64_t a0, uint64_t na, uint32_t termA, uint64_t r1, uint64_t chl, uint64_t nch,
+                       uint64_t c_lo, uint64_t c_hi, const void * d_r0, void * d_gtnew, void * d_G);
+/* K6: d_LM (na+nr codes) = merge by d_G, which is left holding its inclusive prefix sums */
+int b3m_engine_blk_merge(b3m_engine * e, const void * d_LA, uint64_t na, uint32_t termA, void * d_LR, uint64_t nr, uint32_t termR, uint64_t a1,
+                         void * d_G, void * d_LM, uint32_t * termM);
+/* anchors of [a0,r1) move by the rank maps of the merge (d_prerank, d_rsamp of blk_begin) */
+int b3m_engine_blk_merge_samples(b3m_engine * e, uint64_t a0, uint64_t a1, uint64_t r1, const void * d_Sincl);
+/* install the root BWT (n codes) and the anchors in d_prerank, build the dictionary and walk the
+ * anchors [q_lo,q_hi); unset SA/ISA samples hold ~0 so that the ranks' partial arrays combine */
+int b3m_engine_blk_finish(b3m_engine * e, const void * d_L_root, uint32_t term_root, uint64_t q_lo, uint64_t q_hi, uint64_t sasamplingrate,
+                          uint64_t isasamplingrate, int bwtonly, uint64_t numblocks);
+
 /* LF-steps/s instrument on the dictionary of the last build: nchains dependent LF chains of
  * `steps` steps each, started at evenly spaced sampled ranks; returns elapsed device ms.
  * Restates /root/reference/src/bwttestdecodespeed.cpp:82-96 for thousands of chains. */

@@ -1,0 +1,67 @@
+"""torchrun script: multi-GPU build (bwtb3m_b200.multigpu, NCCL) == single-GPU build, bit for bit.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tools/dist_check.py [--workload cfg2 --scale 0.1 | --n 200003 --itype pacterm] [--local-blocks 1]
+"""
+import argparse
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from bwtb3m_b200 import Engine, multigpu, workloads  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--workload", default="")
+ap.add_argument("--scale", type=float, default=1.0)
+ap.add_argument("--n", type=int, default=200_003)
+ap.add_argument("--itype", default="pacterm")
+ap.add_argument("--local-blocks", type=int, default=1)
+ap.add_argument("--seed", type=int, default=7)
+a = ap.parse_args()
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+if a.workload:
+    itype, data, nsym = workloads.make(a.workload, a.scale)
+elif a.itype in ("pac", "pacterm"):
+    itype, data = a.itype, workloads.random_pac(a.n, a.seed)
+else:
+    itype, data = "bytestream", np.random.default_rng(a.seed).integers(0, 256, size=a.n, dtype=np.uint8)
+
+stream = torch.cuda.Stream()
+eng = Engine(local, stream.cuda_stream)
+eng.load_host(data, itype)
+drv = None
+for it in range(2):
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    drv, res = multigpu.build_distributed(eng, local_blocks=a.local_blocks, sasamplingrate=32, isasamplingrate=1024, driver=drv)
+    torch.cuda.synchronize()
+    dist.barrier()
+    dt = time.perf_counter() - t0
+ok = True
+if rank == 0:
+    multi = eng.fetch()
+    info = eng.info()
+    ref = Engine(local)
+    ref.load_host(data, itype)
+    ref.build(numblocks=1, sasamplingrate=32, isasamplingrate=1024, preisarate=info["preisarate"])
+    one = ref.fetch()
+    for k in ("bwt", "preisa", "sa", "isa"):
+        same = np.array_equal(multi[k], one[k])
+        ok = ok and same
+        print("%s: %s" % (k, "equal" if same else "DIFFERENT"))
+    print("world=%d n=%d second build %.1f ms; phases ms sort=%.1f gap=%.1f merge=%.1f walk=%.1f  %s" %
+          (world, info["n"], dt * 1e3, info["ms_sort"], info["ms_gap"], info["ms_merge"], info["ms_walk"], "DIST_CHECK_OK" if ok else "DIST_CHECK_FAILED"))
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
