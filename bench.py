@@ -43,7 +43,7 @@ def config_dict(args, n, itype, extra=None):
         "isasamplingrate": 262144,
         "bwtonly": 1 if args.workload == "cfg1" else 0,
         "scale": args.scale,
-        "l2": "flushed between timed steps (256 MiB write)",
+        "l2": "flushed between timed steps (256 MiB write); cfg3/cfg5 inputs are also far larger than L2",
     }
     if extra:
         d.update(extra)
@@ -343,14 +343,14 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only; invalid as a bench value)")
     ap.add_argument("--numblocks", type=int, default=1)
-    ap.add_argument("--cpu-sample", type=int, default=48_000_000, help="symbols of the workload the cpu_baseline leg processes")
-    ap.add_argument("--ref-sample", type=int, default=8_000_000, help="symbols per step of --impl reference")
+    ap.add_argument("--cpu-sample", type=int, default=256_000_000, help="symbols of the workload the cpu_baseline leg processes")
+    ap.add_argument("--ref-sample", type=int, default=32_000_000, help="symbols per step of --impl reference")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5, help="steps of the end-to-end (host buffers) leg")
     args = ap.parse_args()
