@@ -17,6 +17,7 @@ class BuildParams(C.Structure):
         ("isasamplingrate", C.c_uint64),
         ("bwtonly", C.c_int),
         ("largelcpthres", C.c_uint64),
+        ("sampling", C.c_int),
     ]
 
 
@@ -30,6 +31,7 @@ class Info(C.Structure):
                                      "extract_bytes", "dict_bytes", "decode_bytes", "launches", "max_lcpnext")]
         + [(k, C.c_float) for k in ("ms_decode", "ms_sort", "ms_extract", "ms_dict", "ms_gap", "ms_merge", "ms_walk",
                                     "ms_total")]
+        + [(k, C.c_uint64) for k in ("sort_tied0", "sort_unresolved0")]
     )
 
 

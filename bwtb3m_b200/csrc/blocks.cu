@@ -228,8 +228,8 @@ void Engine::leaf_build(BlockLeaf & leaf, uint64_t s, uint64_t m, uint8_t * L, u
 	if (mt) {
 		DevBuf<uint32_t> wrank(st, W);
 		{
-			DevBuf<uint32_t> wsa(st, W);
-			k2_suffix_sort(st, T, s, W, 0, T.has_term ? 0 : 1, wsa.get(), wrank.get(), ss);
+			DevBuf<uint32_t> wsa;
+			k2_suffix_sort(st, T, s, W, 0, T.has_term ? 0 : 1, wsa, wrank.get(), ss, nullptr);
 			leaf.sa.alloc(st, mt);
 			// keep the block's own suffixes, in order; wrank becomes the block-local rank by position
 			const uint32_t * sa = wsa.get();

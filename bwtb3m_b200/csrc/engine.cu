@@ -25,7 +25,7 @@ Engine::Engine(int dev, void * stream) : device(dev) {
 Engine::~Engine() {
 	cudaSetDevice(device);
 	cudaStreamSynchronize(st.s);
-	raw.release(); codes.release(); bwt.release(); prerank.release(); sa.release(); isa.release(); dict.release();
+	raw.release(); codes.release(); packed.release(); bwt.release(); prerank.release(); sa.release(); isa.release(); dict.release();
 	d_hist.release(); d_special.release();
 	cudaStreamSynchronize(st.s);
 	arena.release_all();
@@ -44,7 +44,7 @@ void Engine::load(const void * input, uint64_t nbytes, int itype, bool on_device
 	B3M_CUDA(cudaSetDevice(device));
 	B3M_REQUIRE(itype >= 0 && itype <= 3, "unknown input type");
 	reset_results();
-	codes.release(); raw.release(); d_hist.release(); d_special.release();
+	codes.release(); packed.release(); raw.release(); d_hist.release(); d_special.release();
 	inputtype = itype;
 	// one slab for the whole build: text + BWT + suffix/rank arrays + sort buffers (HBM layout)
 	{
@@ -140,6 +140,12 @@ void Engine::load(const void * input, uint64_t nbytes, int itype, bool on_device
 	B3M_REQUIRE(T.n < 0xFFFFFFF0ull, "inputs of 2^32 symbols or more are not supported yet");
 	T.codes = codes.get();
 	raw.release();
+	if (T.keybits == 2) {
+		packed.alloc(st, T.ntext / 32 + 3);
+		k1_pack2(st, T.codes, T.ntext, packed.get());
+		T.packed = packed.get();
+		decode_bytes += T.ntext + T.ntext / 4;
+	}
 	pt.mark();
 	B3M_CUDA(cudaStreamSynchronize(st.s));
 	ms_decode = pt.ms(0, 1);
@@ -216,26 +222,50 @@ void Engine::build(b3m_build_params const & p) {
 	bwt.alloc(st, T.n + 16);
 	prerank.alloc(st, npre);
 	uint32_t exc_pos = 0xffffffffu;
+	// With the whole text in one block the sorted order itself yields the sampled SA/ISA; the LF
+	// walk (K7) is what the reference must do because it never holds a full suffix array.
+	bool const direct = numblocks == 1 && !p.bwtonly && p.sampling != B3M_SAMPLING_WALK;
+	nsa = nisa = 0;
+	if (!p.bwtonly) {
+		nsa = div_up(T.n, p.sasamplingrate);
+		nisa = div_up(T.n, p.isasamplingrate);
+		sa.alloc(st, nsa); isa.alloc(st, nisa);
+		if (!direct) {
+			B3M_LAUNCH(st, k_fill_u64, (unsigned)div_up(nsa, 256), 256, 0, (unsigned long long *)sa.get(), nsa, ~0ull);
+			B3M_LAUNCH(st, k_fill_u64, (unsigned)div_up(nisa, 256), 256, 0, (unsigned long long *)isa.get(), nisa, ~0ull);
+		}
+	}
 	if (numblocks == 1) {
 		uint64_t const W = T.ntext;
-		DevBuf<uint32_t> dsa(st, W), drank(st, W);
-		k2_suffix_sort(st, T, 0, W, T.has_term ? 0 : 1, 0, dsa.get(), drank.get(), &sortstats);
-		pt.mark(); // 1
 		uint64_t const shift = T.has_term ? 1 : 0;
-		k3_extract_bwt(st, T, 0, dsa.get(), W, bwt.get(), shift, d_special.get());
-		if (T.has_term) // rank 0 is the terminator suffix; its predecessor is the last base
-			B3M_CUDA(cudaMemcpyAsync(bwt.get(), T.codes + T.ntext - 1, 1, cudaMemcpyDeviceToDevice, st.s));
-		B3M_LAUNCH(st, k_sample_ranks, (unsigned)div_up(npre, 256), 256, 0, (const uint32_t *)drank.get(), T.ntext, prerate,
-		           (uint32_t)shift, npre, prerank.get());
-		extract_bytes = W * (4 + 32 + 1) + npre * 36;
+		FusedOut fo;
+		fo.bwt = bwt.get(); fo.shift = shift; fo.has_term = T.has_term; fo.special = d_special.get();
+		fo.prerank = prerank.get(); fo.prelog = ceil_log2_u64(prerate);
+		if (direct) {
+			fo.sa_s = (unsigned long long *)sa.get(); fo.salog = ceil_log2_u64(p.sasamplingrate);
+			fo.isa_s = (unsigned long long *)isa.get(); fo.isalog = ceil_log2_u64(p.isasamplingrate);
+		}
+		{
+			DevBuf<uint32_t> dsa;
+			k2_suffix_sort(st, T, 0, W, T.has_term ? 0 : 1, 0, dsa, nullptr, &sortstats, &fo);
+		}
 		if (T.has_term) {
+			// rank 0 is the terminator suffix (text position ntext); its predecessor is the last base
+			B3M_CUDA(cudaMemcpyAsync(bwt.get(), T.codes + T.ntext - 1, 1, cudaMemcpyDeviceToDevice, st.s));
+			uint64_t const zero = 0, pos = T.ntext;
+			if ((T.ntext & (prerate - 1)) == 0) B3M_CUDA(cudaMemsetAsync(prerank.get() + T.ntext / prerate, 0, 4, st.s));
+			if (direct) {
+				B3M_CUDA(cudaMemcpyAsync(sa.get(), &pos, 8, cudaMemcpyHostToDevice, st.s));
+				if ((T.ntext & (p.isasamplingrate - 1)) == 0) B3M_CUDA(cudaMemcpyAsync(isa.get() + T.ntext / p.isasamplingrate, &zero, 8, cudaMemcpyHostToDevice, st.s));
+			}
 			B3M_CUDA(cudaMemcpyAsync(pinned, d_special.get(), 16, cudaMemcpyDeviceToHost, st.s));
 			B3M_CUDA(cudaStreamSynchronize(st.s));
 			exc_pos = ((uint32_t *)pinned)[0];
 			B3M_REQUIRE(exc_pos != 0xffffffffu, "internal: terminator row not found");
 		}
+		extract_bytes = W * 37 + npre * 4 + (direct ? 8 * (nsa + nisa) : 0);
+		pt.mark(); // 1
 		pt.mark(); // 2
-		ms_sort = -1; // filled below
 	} else {
 		build_blocks(pt, &exc_pos);
 		pt.mark(); pt.mark(); // 1, 2: the phases are timed inside build_blocks
@@ -243,15 +273,8 @@ void Engine::build(b3m_build_params const & p) {
 	root_exc_pos = exc_pos;
 	make_dict(exc_pos, 0, 0);
 	pt.mark(); // 3
-	nsa = nisa = 0;
-	if (!p.bwtonly) {
-		nsa = div_up(T.n, p.sasamplingrate);
-		nisa = div_up(T.n, p.isasamplingrate);
-		sa.alloc(st, nsa); isa.alloc(st, nisa);
-		B3M_LAUNCH(st, k_fill_u64, (unsigned)div_up(nsa, 256), 256, 0, (unsigned long long *)sa.get(), nsa, ~0ull);
-		B3M_LAUNCH(st, k_fill_u64, (unsigned)div_up(nisa, 256), 256, 0, (unsigned long long *)isa.get(), nisa, ~0ull);
+	if (!p.bwtonly && !direct)
 		k7_walk(st, D, prerank.get(), npre, prerate, T.n, p.sasamplingrate, p.isasamplingrate, sa.get(), isa.get(), &walkstats, 0, npre);
-	}
 	pt.mark(); // 4
 	B3M_CUDA(cudaStreamSynchronize(st.s));
 	if (numblocks == 1) { ms_sort = pt.ms(0, 1); ms_extract = pt.ms(1, 2); }
@@ -295,6 +318,7 @@ void Engine::info(b3m_info * o) {
 	o->gap_lf_steps = gap_lf_steps; o->walk_lf_steps = walkstats.steps; o->walk_chains = walkstats.chains; o->gap_chains = gap_chains;
 	o->merge_bytes = merge_bytes; o->extract_bytes = extract_bytes; o->dict_bytes = dict_bytes_moved; o->decode_bytes = decode_bytes;
 	o->launches = st.launches; o->max_lcpnext = max_lcpnext;
+	o->sort_tied0 = sortstats.tied0; o->sort_unresolved0 = sortstats.unresolved0;
 	o->ms_decode = ms_decode; o->ms_sort = ms_sort; o->ms_extract = ms_extract; o->ms_dict = ms_dict;
 	o->ms_gap = ms_gap; o->ms_merge = ms_merge; o->ms_walk = ms_walk; o->ms_total = ms_total;
 }
@@ -318,7 +342,7 @@ void Engine::ssa_from_bwt(const uint8_t * h_bwt, uint64_t n, const uint64_t * h_
 	auto pow2 = [](uint64_t v) { return v && !(v & (v - 1)); };
 	B3M_REQUIRE(pow2(sarate) && pow2(isarate), "sampling rates must be powers of two");
 	reset_results();
-	codes.release(); raw.release(); d_hist.release(); d_special.release();
+	codes.release(); packed.release(); raw.release(); d_hist.release(); d_special.release();
 	loaded = false;
 	arena.reserve((size_t)(n * 4 + 16 * npairs + (64u << 20)));
 	PhaseTimer pt(st);

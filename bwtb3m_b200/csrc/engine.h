@@ -49,6 +49,7 @@ struct Engine {
 	bool loaded = false;
 	int inputtype = 0;
 	DevBuf<uint8_t> raw, codes;
+	DevBuf<uint64_t> packed;   // 2-bit packed text when sigma <= 4 (textview.cuh)
 	DevBuf<uint64_t> d_hist;
 	DevText T;
 	uint64_t hist[256];      // reference symbol -> count

@@ -11,6 +11,7 @@ namespace b3m {
 // implicit: it sits at position ntext (n = ntext+1) and is smaller than every code.
 struct DevText {
 	const uint8_t * codes = nullptr;
+	const uint64_t * packed = nullptr; // sigma <= 4: 2 bit/symbol, 32 per word, first symbol in the top bits (textview.cuh)
 	uint64_t ntext = 0;     // stored symbols
 	uint64_t n = 0;         // BWT length (ntext, or ntext+1 with implicit terminator)
 	uint32_t sigma = 0;     // number of distinct codes
@@ -32,6 +33,8 @@ void k1_hist_bytes(Stream & st, const uint8_t * d_in, uint64_t nbytes, uint64_t 
 void k1_map_bytes(Stream & st, const uint8_t * d_in, uint64_t n, const uint8_t * d_lut256, uint8_t * d_out);
 void k1_unpack_pac(Stream & st, const uint8_t * d_pac, uint64_t l, uint8_t * d_out, uint64_t * d_hist256);
 void k1_unpack_compact(Stream & st, const uint8_t * d_words, uint64_t n, unsigned b, uint8_t * d_out, uint64_t * d_hist256);
+// packed copy of n codes < 4; d_out holds n/32 + 3 words, the tail is zero
+void k1_pack2(Stream & st, const uint8_t * d_codes, uint64_t n, uint64_t * d_out);
 
 // ---- K2 ---------------------------------------------------------------------------------
 struct SortStats {
@@ -40,15 +43,35 @@ struct SortStats {
 	uint64_t radix_bytes = 0;     // algorithmic bytes of all radix passes
 	uint64_t active_sum = 0;      // sum over rounds of records entering the round
 	uint64_t other_bytes = 0;     // key extraction, flagging, rank scatter, compaction
+	uint64_t tied0 = 0;           // suffixes sharing their first k0 symbols with another one (after round 0)
+	uint64_t unresolved0 = 0;     // suffixes still tied after the in-CTA group sort (enter prefix doubling)
+};
+
+// What a whole-text sort (wstart == 0, W == ntext) can emit straight from the sorted order, fused
+// with the last sorting step (K3 + the sampling the reference does by LF walk): the BWT, the
+// (rank,pos) anchors and the sampled SA / ISA.  rank of window suffix k = k + shift.
+struct FusedOut {
+	uint8_t * bwt = nullptr;       // bwt[k + shift] = code preceding suffix sa[k]
+	uint64_t shift = 0;
+	int has_term = 0;              // the suffix at text position 0 is preceded by the terminator: code 0, row -> special[0]
+	uint32_t * special = nullptr;  // [0] row of the terminator symbol, [1] row of the suffix at position 0
+	uint32_t * prerank = nullptr;  // prerank[p >> prelog] = rank of position p, p multiple of 2^prelog
+	uint32_t prelog = 0;
+	unsigned long long * sa_s = nullptr;  // sa_s[r >> salog] = position, r multiple of 2^salog (nullptr: bwtonly)
+	uint32_t salog = 0;
+	unsigned long long * isa_s = nullptr; // isa_s[p >> isalog] = rank
+	uint32_t isalog = 0;
 };
 
 // Sorts the W suffixes that start at text positions wstart+i, 0 <= i < W.
 // circular != 0: W == ntext, wstart == 0, indices wrap (terminator-free whole text).
 // circular == 0: the end of the window is a sentinel smaller than every symbol; text positions
 //                wrap modulo ntext when text_wraps != 0.
-// sa[k] = window-relative start of the k-th smallest suffix; rank = inverse permutation.
+// sa (allocated here, W entries): sa[k] = window-relative start of the k-th smallest suffix;
+// rank (caller's, W entries, may be nullptr): the inverse permutation.
+// fo (may be nullptr; whole-text windows only): fused outputs, see FusedOut.
 void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W, int circular, int text_wraps,
-                    uint32_t * sa, uint32_t * rank, SortStats * stats);
+                    DevBuf<uint32_t> & sa, uint32_t * rank, SortStats * stats, const FusedOut * fo);
 
 // ---- K3 ---------------------------------------------------------------------------------
 // bwt[k + shift] = code preceding suffix sa[k] (text position wstart+sa[k]); the suffix at text

@@ -154,6 +154,36 @@ void k1_unpack_compact(Stream & st, const uint8_t * d_words, uint64_t n, unsigne
 	B3M_LAUNCH(st, k_unpack_compact, grid, 256, 0, d_words, n, b, d_out, (unsigned long long *)d_hist256);
 }
 
+// 2-bit packed copy of the codes (textview.cuh): 32 symbols per uint64, first symbol in the top bits
+__global__ void __launch_bounds__(256) k_pack2(const uint8_t * __restrict__ codes, uint64_t n, uint64_t * __restrict__ out, uint64_t nwords) {
+	uint64_t const w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (w >= nwords) return;
+	uint64_t const first = w * 32;
+	uint64_t acc = 0;
+	if (first + 32 <= n) {
+		const uint4 * src = reinterpret_cast<const uint4 *>(codes + first);
+		#pragma unroll
+		for (int q = 0; q < 2; ++q) {
+			uint4 const x4 = ld_stream_u4(src + q);
+			uint32_t const x[4] = {x4.x, x4.y, x4.z, x4.w};
+			#pragma unroll
+			for (int k = 0; k < 4; ++k) {
+				uint32_t const y = x[k] & 0x03030303u;
+				uint32_t const z = ((y & 3u) << 6) | ((y >> 4) & 0x30u) | ((y >> 14) & 0x0cu) | ((y >> 24) & 3u);
+				acc = (acc << 8) | z;
+			}
+		}
+	} else {
+		for (uint32_t j = 0; j < 32; ++j) acc = (acc << 2) | ((first + j < n) ? (uint64_t)(codes[first + j] & 3u) : 0ull);
+	}
+	out[w] = acc;
+}
+
+void k1_pack2(Stream & st, const uint8_t * d_codes, uint64_t n, uint64_t * d_out) {
+	uint64_t const nwords = n / 32 + 3;
+	B3M_LAUNCH(st, k_pack2, (unsigned)div_up(nwords, 256), 256, 0, d_codes, n, d_out, nwords);
+}
+
 // ------------------------------------------------------------------------------------------
 // K3: L[k] = T[(SA[k]-1) mod n]   (/root/reference/src/lcpbit.cpp:3668-3669)
 // ------------------------------------------------------------------------------------------

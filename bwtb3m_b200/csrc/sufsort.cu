@@ -1,38 +1,27 @@
-// K2: per-block suffix sorting by prefix doubling on top of the LSD radix sort (radix.cuh).
-// Replaces libmaus2's CPU block sorter reached through BwtMergeBlockSortRequest::dispatch
-// (/root/reference/src/checkbwt.cpp:24); comparisons are circular exactly as in
-// the reference's definition BWT[i] = s[(SA[i]+n-1)%n] (/root/reference/src/lcpbit.cpp:3668-3669).
+// K2: per-block suffix sorting.  Replaces libmaus2's CPU block sorter reached through
+// BwtMergeBlockSortRequest::dispatch (/root/reference/src/checkbwt.cpp:24);
+// comparisons are circular exactly as in the reference's definition
+// BWT[i] = s[(SA[i]+n-1)%n] (/root/reference/src/lcpbit.cpp:3668-3669).
 //
-// Round 0 sorts all W suffixes by a 32-bit key holding their first k0 = 32/keybits symbols.
-// Round r >= 1 touches only suffixes whose group is still tied: it gathers the rank of the
-// suffix h symbols ahead, radix sorts (group, rank-ahead) and splits the groups; h doubles.
+// Round 0   LSD radix sort (radix.cuh) of all W suffixes by a 32-bit key holding their first
+//           k0 = 32/keybits symbols.
+// Resolve   k_resolve: one pass over the sorted (key, index) pairs.  Runs of equal keys of up to
+//           RS_EXT suffixes are sorted inside the CTA by their next 64 key bits read from the
+//           text; with the whole text in one window the same pass emits the BWT, the anchors
+//           and the sampled SA/ISA (FusedOut).  On random DNA this finishes the sort: no
+//           rank-by-position array is ever written.
+// Doubling  only if some suffixes are still tied (repeats longer than k0 + 64/keybits symbols,
+//           or runs longer than RS_EXT): classic prefix doubling on the tied suffixes only --
+//           gather the rank of the suffix h symbols ahead, radix sort (group, rank ahead),
+//           split the groups; h doubles.
 #include "kernels.h"
 #include "radix.cuh"
 #include "scan.cuh"
+#include "textview.cuh"
 #include <time.h>
 #include <stdlib.h>
 
 namespace b3m {
-
-struct TextView {
-	const uint8_t * codes;
-	uint64_t ntext;
-	uint64_t wstart;
-	uint64_t W;
-	int circular;    // window == whole text, indices wrap modulo W
-	int text_wraps;  // text positions wrap modulo ntext (linear window over a circular text)
-};
-
-__device__ __forceinline__ uint32_t tv_symbol(TextView const & v, uint64_t i /* window index, may exceed W */) {
-	if (v.circular) {
-		if (i >= v.W) i -= v.W;
-		return v.codes[i];
-	}
-	if (i >= v.W) return 0u; // past the window: padding (order fixed by the short-suffix rule)
-	uint64_t p = v.wstart + i;
-	if (v.text_wraps) p %= v.ntext;
-	return v.codes[p];
-}
 
 // Input order of round 0: in linear mode the nshort suffixes that run past the window end come
 // first, shortest first, so that the stable sort leaves them in front of equal padded keys.
@@ -41,9 +30,7 @@ k_make_keys(TextView v, unsigned bits, unsigned k0, uint64_t nshort, uint32_t * 
 	uint64_t const t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= v.W) return;
 	uint64_t const i = (t < nshort) ? (v.W - 1 - t) : (t - nshort);
-	uint32_t k = 0;
-	for (unsigned s = 0; s < k0; ++s) k = (k << bits) | tv_symbol(v, i + s);
-	key[t] = k;
+	key[t] = (uint32_t)tv_symbols(v, i, k0, bits);
 	idx[t] = (uint32_t)i;
 }
 
@@ -57,6 +44,158 @@ k_gather_ahead(const uint32_t * __restrict__ aidx, uint64_t na, const uint32_t *
 	if (circular) { j %= W; k = rank[j]; }
 	else k = (j < W) ? rank[j] + 1u : 0u;
 	key2[a] = k;
+}
+
+__global__ void __launch_bounds__(256)
+k_rank_scatter(const uint32_t * __restrict__ sa, uint64_t W, uint32_t * __restrict__ rank) {
+	uint64_t const k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (k < W) rank[sa[k]] = (uint32_t)k;
+}
+
+// ------------------------------------------------------------------------------------------
+// fused outputs of one suffix in its final place (K3 + sampling)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t fo_pred(TextView const & v, FusedOut const & fo, uint32_t i) {
+	if (i == 0) return fo.has_term ? 0u : (uint32_t)v.codes[v.ntext - 1];
+	return tv_code_before(v, i);
+}
+
+__device__ __forceinline__ void fo_emit(FusedOut const & fo, uint32_t i, uint64_t k, uint32_t c) {
+	uint64_t const r = k + fo.shift;
+	fo.bwt[r] = (uint8_t)c;
+	if (i == 0) { if (fo.has_term) fo.special[0] = (uint32_t)r; fo.special[1] = (uint32_t)r; }
+	if ((i & ((1u << fo.prelog) - 1u)) == 0) fo.prerank[i >> fo.prelog] = (uint32_t)r;
+	if (fo.isa_s && ((uint64_t)i & ((1ull << fo.isalog) - 1ull)) == 0) fo.isa_s[i >> fo.isalog] = r;
+	if (fo.sa_s && (r & ((1ull << fo.salog) - 1ull)) == 0) fo.sa_s[r >> fo.salog] = i;
+}
+
+// K3 on a final suffix array of the whole text (the path taken after prefix doubling)
+__global__ void __launch_bounds__(256)
+k_extract_sample(TextView v, const uint32_t * __restrict__ sa, uint64_t m, FusedOut fo) {
+	uint64_t const k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= m) return;
+	uint32_t const i = sa[k];
+	fo_emit(fo, i, k, fo_pred(v, fo, i));
+}
+
+// ------------------------------------------------------------------------------------------
+// Resolve: sorts every run of equal round-0 keys that is at most RS_EXT long inside one CTA.
+// A CTA owns the runs that START in its tile; it loads RS_EXT records on either side so that
+// every suffix can find the start and the end of its run.  The second key of a suffix is its
+// next 64/bits symbols; suffixes that reach the sentinel of a linear window inside that range
+// compare by remaining length (shorter = smaller), which is also what keeps equal padded keys
+// apart.  Longer runs and runs with equal second keys stay in their current order and are
+// counted; hflag[k] = 1 where the record in final place k starts a new group.
+// ------------------------------------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 8;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
+constexpr int RS_EXT = 64;
+constexpr int RS_REG = RS_TILE + 2 * RS_EXT;
+enum { RS_SKIP = 0, RS_PASS = 1, RS_SINGLE = 2, RS_TIED = 3 };
+
+template <bool FUSED>
+__global__ void __launch_bounds__(RS_THREADS)
+k_resolve(TextView v, unsigned bits, unsigned k0, int lin, const uint32_t * __restrict__ key, const uint32_t * __restrict__ idx,
+          uint32_t * __restrict__ sa_out, uint8_t * __restrict__ hflag, FusedOut fo, unsigned long long * __restrict__ counters) {
+	__shared__ uint32_t s_key[RS_REG];
+	__shared__ uint32_t s_idx[RS_REG];
+	__shared__ unsigned long long s_k2[RS_REG];
+	__shared__ uint8_t s_rem[RS_REG];
+	__shared__ uint8_t s_head[RS_REG];
+	int64_t const W = (int64_t)v.W;
+	int64_t const t0 = (int64_t)blockIdx.x * RS_TILE;
+	int64_t const kbase = t0 - RS_EXT; // region index x <-> global place kbase + x
+	unsigned const k2syms = 64u / bits;
+	unsigned const full = k0 + k2syms;
+
+	for (int x = threadIdx.x; x < RS_REG; x += RS_THREADS) {
+		int64_t const k = kbase + x;
+		bool const valid = k >= 0 && k < W;
+		s_key[x] = valid ? key[k] : 0u;
+		s_idx[x] = valid ? idx[k] : 0u;
+	}
+	__syncthreads();
+	for (int x = threadIdx.x; x < RS_REG; x += RS_THREADS) {
+		int64_t const k = kbase + x;
+		bool head = true;
+		if (k > 0 && k < W && x > 0) {
+			head = s_key[x] != s_key[x - 1];
+			if (lin) head = head || ((uint64_t)s_idx[x] + k0 > (uint64_t)W) || ((uint64_t)s_idx[x - 1] + k0 > (uint64_t)W);
+		}
+		s_head[x] = head ? 1 : 0;
+	}
+	__syncthreads();
+
+	uint8_t cls[RS_ITEMS + 1];
+	uint16_t gs[RS_ITEMS + 1], ge[RS_ITEMS + 1];
+	uint8_t pc[RS_ITEMS + 1];
+	uint32_t ntied = 0, nunres = 0;
+	#pragma unroll
+	for (int j = 0; j <= RS_ITEMS; ++j) {
+		int const x = RS_EXT + j * RS_THREADS + (int)threadIdx.x;
+		cls[j] = RS_SKIP; gs[j] = ge[j] = 0; pc[j] = 0;
+		if (j == RS_ITEMS && threadIdx.x >= RS_EXT) continue;
+		int64_t const k = kbase + x;
+		if (k >= W) continue;
+		bool const tile_el = j < RS_ITEMS;
+		int y = x, steps = 0;
+		while (!s_head[y] && steps < RS_EXT - 1) { --y; ++steps; }
+		bool big = !s_head[y];
+		int z = x + 1;
+		if (!big) {
+			if (y >= RS_EXT + RS_TILE) continue; // run of the next tile
+			while (z - y <= RS_EXT && !s_head[z]) ++z;
+			big = z - y > RS_EXT;
+		}
+		if (big) { if (tile_el) cls[j] = RS_PASS; else continue; }
+		else if (y < RS_EXT) continue; // run of the previous tile
+		else { cls[j] = (z - y == 1) ? RS_SINGLE : RS_TIED; gs[j] = (uint16_t)y; ge[j] = (uint16_t)z; }
+		uint32_t const i = s_idx[x];
+		if (FUSED) pc[j] = (uint8_t)fo_pred(v, fo, i);
+		if (cls[j] == RS_TIED) {
+			s_k2[x] = tv_symbols(v, (uint64_t)i + k0, k2syms, bits);
+			uint64_t const left = (uint64_t)W - i;
+			s_rem[x] = (uint8_t)((lin && left < full) ? left : full);
+		}
+	}
+	__syncthreads();
+	#pragma unroll
+	for (int j = 0; j <= RS_ITEMS; ++j) {
+		if (cls[j] == RS_SKIP) continue;
+		int const x = RS_EXT + j * RS_THREADS + (int)threadIdx.x;
+		uint32_t const i = s_idx[x];
+		int f = x;
+		uint8_t hf = 1;
+		if (cls[j] == RS_PASS) { hf = s_head[x]; ++nunres; }
+		else if (cls[j] == RS_TIED) {
+			unsigned long long const mk = s_k2[x];
+			uint8_t const mr = s_rem[x];
+			int less = 0, eqb = 0, eqt = 0;
+			for (int y = gs[j]; y < ge[j]; ++y) {
+				unsigned long long const ok = s_k2[y];
+				uint8_t const orr = s_rem[y];
+				bool const eq = ok == mk && orr == mr;
+				less += (ok < mk || (ok == mk && orr < mr)) ? 1 : 0;
+				eqt += eq ? 1 : 0;
+				eqb += (eq && y < x) ? 1 : 0;
+			}
+			f = gs[j] + less + eqb;
+			hf = eqb == 0 ? 1 : 0;
+			++ntied;
+			if (eqt > 1) ++nunres;
+		}
+		int64_t const kf = kbase + f;
+		sa_out[kf] = i;
+		hflag[kf] = hf;
+		if (FUSED) fo_emit(fo, i, (uint64_t)kf, pc[j]);
+	}
+	ntied = __reduce_add_sync(0xffffffffu, ntied);
+	nunres = __reduce_add_sync(0xffffffffu, nunres);
+	if ((threadIdx.x & 31) == 0) {
+		if (nunres) atomicAdd(&counters[0], (unsigned long long)nunres);
+		if (ntied) atomicAdd(&counters[1], (unsigned long long)ntied);
+	}
 }
 
 static double wall_ms() {
@@ -74,25 +213,27 @@ static uint32_t fetch_u32(Stream & st, const uint32_t * d) {
 }
 
 void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W, int circular, int text_wraps,
-                    uint32_t * sa, uint32_t * rank, SortStats * stats) {
+                    DevBuf<uint32_t> & sa_buf, uint32_t * rank, SortStats * stats, const FusedOut * fo) {
 	if (W == 0) return;
 	B3M_REQUIRE(W < 0xFFFFFFF0ull, "window too large for 32-bit suffix indices");
+	B3M_REQUIRE(!fo || (wstart == 0 && W == T.ntext), "internal: fused outputs need the whole text in one window");
 	unsigned const bits = T.keybits;
 	unsigned const k0 = 32 / bits;
 	uint64_t const nshort = circular ? 0 : (W < (uint64_t)(k0 - 1) ? W : (uint64_t)(k0 - 1));
-	TextView v{T.codes, T.ntext, wstart, W, circular, text_wraps};
+	TextView v{T.codes, bits == 2 ? T.packed : nullptr, T.ntext, wstart, W, circular, text_wraps};
+	int const lin = !circular;
 	SortStats S;
 	double t_last = wall_ms();
 
 	DevBuf<uint32_t> scalar(st, 4);
 	uint32_t * d_total = scalar.get();
-	uint64_t na = 0;
-	DevBuf<uint32_t> pool[6];
+	DevBuf<unsigned long long> counters(st, 2);
+	DevBuf<uint8_t> hflag(st, W);
+	uint64_t unresolved = 0;
 	{
 		// ---------------- round 0 ----------------
-		DevBuf<uint32_t> key0(st, W), key1(st, W), idx1(st, W);
-		// sa doubles as the first index buffer
-		RadixRec<2> cur{{key0.get(), sa}}, alt{{key1.get(), idx1.get()}};
+		DevBuf<uint32_t> key0(st, W), key1(st, W), idx0(st, W), idx1(st, W);
+		RadixRec<2> cur{{key0.get(), idx0.get()}}, alt{{key1.get(), idx1.get()}};
 		unsigned const grid = (unsigned)div_up(W, 256);
 		TRACE("r0 alloc");
 		B3M_LAUNCH_T(st, "make_keys", W * 9ull, k_make_keys, grid, 256, 0, v, bits, k0, nshort, cur.a[0], cur.a[1]);
@@ -102,122 +243,145 @@ void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W,
 		radix_sort_bits<2>(st, cur, alt, 0, W, 0, 32, &rs);
 		TRACE("r0 radix");
 		S.radix_passes += rs.passes; S.radix_bytes += rs.bytes; S.active_sum += W; S.rounds = 1;
-		const uint32_t * skey = cur.a[0];
-		const uint32_t * sidx = cur.a[1];
-		uint32_t * grp = alt.a[0];
-		uint64_t const Wm = W, k0m = k0;
-		int const lin = !circular;
-		// head flags -> group head position (max-scan); rank scatter; final place of every index
-		scan_apply<OpMax>(st, W,
-			[=] __device__(uint64_t k) -> uint32_t {
-				if (k == 0) return 0u;
-				bool head = skey[k] != skey[k - 1];
-				if (lin) head = head || ((uint64_t)sidx[k] + k0m > Wm) || ((uint64_t)sidx[k - 1] + k0m > Wm);
-				return head ? (uint32_t)k : 0u;
-			},
-			[=] __device__(uint64_t k, uint32_t excl, uint32_t v0) {
-				uint32_t const head = excl > v0 ? excl : v0;
-				grp[k] = head;
-				uint32_t const i = sidx[k];
-				rank[i] = head;
-				if (sa != sidx) sa[k] = i;
-			}, "heads_rank_scatter", W * 48ull);
-		S.other_bytes += W * (8ull + 8ull + 4ull + 4ull + 4ull);
-		TRACE("r0 heads+rank scatter");
-		// compaction of suffixes whose group has more than one member
-		B3M_CUDA(cudaMemsetAsync(d_total, 0, 4, st.s));
-		// two passes: count, then allocate and fill
-		auto active = [=] __device__(uint64_t k) -> uint32_t {
-			bool const hk = grp[k] == (uint32_t)k;
-			bool const hn = (k + 1 == Wm) || (grp[k + 1] == (uint32_t)(k + 1));
-			return (hk && hn) ? 0u : 1u;
-		};
-		scan_apply<OpSum>(st, W, active,
-			[=] __device__(uint64_t k, uint32_t excl, uint32_t v0) { if (k + 1 == Wm) *d_total = excl + v0; });
-		na = fetch_u32(st, d_total);
-		S.other_bytes += W * 8ull;
-		TRACE("r0 count active");
-		if (na) {
-			for (int b = 0; b < 6; ++b) pool[b].alloc(st, na);
-			uint32_t * agrp = pool[0].get();
-			uint32_t * aidx = pool[1].get();
-			const uint32_t * saf = sa;
-			scan_apply<OpSum>(st, W, active,
-				[=] __device__(uint64_t k, uint32_t excl, uint32_t v0) {
-					if (v0) { agrp[excl] = grp[k]; aidx[excl] = saf[k]; }
-				});
-			S.other_bytes += W * 8ull + na * 8ull;
-		}
-		TRACE("r0 compact");
+		// ---------------- resolve (+ fused extraction) ----------------
+		B3M_CUDA(cudaMemsetAsync(counters.get(), 0, 16, st.s));
+		unsigned const rgrid = (unsigned)div_up(W, RS_TILE);
+		uint64_t const rbytes = W * (8ull + 4ull + 1ull + (fo ? 33ull : 0ull));
+		if (fo) B3M_LAUNCH_T(st, "resolve_extract", rbytes, (k_resolve<true>), rgrid, RS_THREADS, 0, v, bits, k0, lin, (const uint32_t *)cur.a[0],
+		                     (const uint32_t *)cur.a[1], alt.a[1], hflag.get(), *fo, counters.get());
+		else B3M_LAUNCH_T(st, "resolve", rbytes, (k_resolve<false>), rgrid, RS_THREADS, 0, v, bits, k0, lin, (const uint32_t *)cur.a[0],
+		                  (const uint32_t *)cur.a[1], alt.a[1], hflag.get(), FusedOut(), counters.get());
+		unsigned long long hc[2];
+		B3M_CUDA(cudaMemcpyAsync(hc, counters.get(), 16, cudaMemcpyDeviceToHost, st.s));
+		B3M_CUDA(cudaStreamSynchronize(st.s));
+		unresolved = hc[0];
+		S.tied0 = hc[1]; S.unresolved0 = hc[0];
+		S.other_bytes += rbytes + 32ull * hc[1];
+		sa_buf = (alt.a[1] == idx1.get()) ? std::move(idx1) : std::move(idx0);
+		TRACE("r0 resolve");
 	}
-	TRACE("r0 free");
+	uint32_t * const sa = sa_buf.get();
 
-	// ---------------- doubling rounds ----------------
-	uint32_t * bufs[6];
-	for (int b = 0; b < 6; ++b) bufs[b] = pool[b].get();
-	// roles: bufs[0]=grp, bufs[1]=idx, bufs[2]=key2, bufs[3..5]=ping-pong partners
-	uint64_t h = k0;
-	int const bw = (int)ceil_log2_u64(W + 2);
-	while (na) {
-		if (circular && h >= W) break; // non-primitive text: ties stay in current order (unpinned)
-		unsigned const grid = (unsigned)div_up(na, 256);
-		B3M_LAUNCH_T(st, "gather_ahead", na * 40ull, k_gather_ahead, grid, 256, 0, (const uint32_t *)bufs[1], na, (const uint32_t *)rank, h, W, circular, bufs[2]);
-		S.other_bytes += na * (4ull + 32ull + 4ull);
-		TRACE("rN gather");
-		RadixRec<3> cur{{bufs[0], bufs[2], bufs[1]}}, alt{{bufs[3], bufs[4], bufs[5]}};
-		RadixStats rs;
-		radix_sort_bits<3>(st, cur, alt, 1, na, 0, bw, &rs); // rank ahead (minor key)
-		radix_sort_bits<3>(st, cur, alt, 0, na, 0, bw, &rs); // group (major key)
-		S.radix_passes += rs.passes; S.radix_bytes += rs.bytes; S.active_sum += na; S.rounds++;
-		TRACE("rN radix");
-		const uint32_t * sg = cur.a[0];
-		const uint32_t * sk = cur.a[1];
-		const uint32_t * si = cur.a[2];
-		uint32_t * ngrp = alt.a[0];
-		uint64_t const nam = na;
-		scan_apply<OpMaxMax>(st, na,
-			[=] __device__(uint64_t a) -> uint2 {
-				if (a == 0) return make_uint2(0u, 0u);
-				bool const seg = sg[a] != sg[a - 1];
-				bool const head = seg || (sk[a] != sk[a - 1]);
-				return make_uint2(seg ? (uint32_t)a : 0u, head ? (uint32_t)a : 0u);
-			},
-			[=] __device__(uint64_t a, uint2 excl, uint2 v0) {
-				uint32_t const segstart = excl.x > v0.x ? excl.x : v0.x;
-				uint32_t const newhead = excl.y > v0.y ? excl.y : v0.y;
-				uint32_t const g = sg[a];
-				uint32_t const i = si[a];
-				uint32_t const ng = g + (newhead - segstart);
-				sa[g + ((uint32_t)a - segstart)] = i;
-				rank[i] = ng;
-				ngrp[a] = ng;
-			});
-		S.other_bytes += na * (2 * 12ull + 4ull + 32ull + 4ull);
-		auto active = [=] __device__(uint64_t a) -> uint32_t {
-			bool const hk = (a == 0) || (ngrp[a] != ngrp[a - 1]);
-			bool const hn = (a + 1 == nam) || (ngrp[a + 1] != ngrp[a]);
-			return (hk && hn) ? 0u : 1u;
-		};
-		uint32_t * ogrp = alt.a[1];
-		uint32_t * oidx = alt.a[2];
-		scan_apply<OpSum>(st, na, active,
-			[=] __device__(uint64_t a, uint32_t excl, uint32_t v0) {
-				if (v0) { ogrp[excl] = ngrp[a]; oidx[excl] = si[a]; }
-				if (a + 1 == nam) *d_total = excl + v0;
-			});
-		S.other_bytes += na * (2 * 8ull + 8ull);
-		uint64_t const nn = fetch_u32(st, d_total);
-		TRACE("rN split+compact");
-		// next round: grp = alt[1], idx = alt[2]; everything else is free
-		uint32_t * nb[6] = {alt.a[1], alt.a[2], cur.a[0], cur.a[1], cur.a[2], alt.a[0]};
-		for (int b = 0; b < 6; ++b) bufs[b] = nb[b];
-		na = nn;
-		h *= 2;
+	if (unresolved == 0) {
+		if (rank) {
+			B3M_LAUNCH_T(st, "rank_scatter", W * 36ull, k_rank_scatter, (unsigned)div_up(W, 256), 256, 0, (const uint32_t *)sa, W, rank);
+			S.other_bytes += W * 36ull;
+		}
+	} else {
+		// ---------------- prefix doubling on the suffixes that are still tied ----------------
+		DevBuf<uint32_t> own_rank;
+		if (!rank) { own_rank.alloc(st, W); rank = own_rank.get(); }
+		uint64_t na = 0;
+		DevBuf<uint32_t> pool[6];
+		{
+			DevBuf<uint32_t> grpb(st, W);
+			uint32_t * grp = grpb.get();
+			const uint8_t * hf = hflag.get();
+			uint64_t const Wm = W;
+			// head flags -> group head position (max-scan); rank of every suffix = head of its group
+			scan_apply<OpMax>(st, W,
+				[=] __device__(uint64_t k) -> uint32_t { return (k && hf[k]) ? (uint32_t)k : 0u; },
+				[=] __device__(uint64_t k, uint32_t excl, uint32_t v0) {
+					uint32_t const head = excl > v0 ? excl : v0;
+					grp[k] = head;
+					rank[sa[k]] = head;
+				}, "heads_rank_scatter", W * 42ull);
+			S.other_bytes += W * (2ull + 4ull + 4ull + 32ull);
+			TRACE("heads+rank scatter");
+			auto active = [=] __device__(uint64_t k) -> uint32_t {
+				bool const hk = grp[k] == (uint32_t)k;
+				bool const hn = (k + 1 == Wm) || (grp[k + 1] == (uint32_t)(k + 1));
+				return (hk && hn) ? 0u : 1u;
+			};
+			B3M_CUDA(cudaMemsetAsync(d_total, 0, 4, st.s));
+			scan_apply<OpSum>(st, W, active,
+				[=] __device__(uint64_t k, uint32_t excl, uint32_t v0) { if (k + 1 == Wm) *d_total = excl + v0; });
+			na = fetch_u32(st, d_total);
+			S.other_bytes += W * 8ull;
+			if (na) {
+				for (int b = 0; b < 6; ++b) pool[b].alloc(st, na);
+				uint32_t * agrp = pool[0].get();
+				uint32_t * aidx = pool[1].get();
+				scan_apply<OpSum>(st, W, active,
+					[=] __device__(uint64_t k, uint32_t excl, uint32_t v0) {
+						if (v0) { agrp[excl] = grp[k]; aidx[excl] = sa[k]; }
+					});
+				S.other_bytes += W * 8ull + na * 8ull;
+			}
+			TRACE("compact");
+		}
+		hflag.release();
+		uint32_t * bufs[6];
+		for (int b = 0; b < 6; ++b) bufs[b] = pool[b].get();
+		// roles: bufs[0]=grp, bufs[1]=idx, bufs[2]=key2, bufs[3..5]=ping-pong partners
+		uint64_t h = k0; // every group shares at least its first k0 symbols
+		int const bw = (int)ceil_log2_u64(W + 2);
+		while (na) {
+			if (circular && h >= W) break; // non-primitive text: ties stay in current order (unpinned)
+			unsigned const grid = (unsigned)div_up(na, 256);
+			B3M_LAUNCH_T(st, "gather_ahead", na * 40ull, k_gather_ahead, grid, 256, 0, (const uint32_t *)bufs[1], na, (const uint32_t *)rank, h, W, circular, bufs[2]);
+			S.other_bytes += na * (4ull + 32ull + 4ull);
+			TRACE("rN gather");
+			RadixRec<3> cur{{bufs[0], bufs[2], bufs[1]}}, alt{{bufs[3], bufs[4], bufs[5]}};
+			RadixStats rs;
+			radix_sort_bits<3>(st, cur, alt, 1, na, 0, bw, &rs); // rank ahead (minor key)
+			radix_sort_bits<3>(st, cur, alt, 0, na, 0, bw, &rs); // group (major key)
+			S.radix_passes += rs.passes; S.radix_bytes += rs.bytes; S.active_sum += na; S.rounds++;
+			TRACE("rN radix");
+			const uint32_t * sg = cur.a[0];
+			const uint32_t * sk = cur.a[1];
+			const uint32_t * si = cur.a[2];
+			uint32_t * ngrp = alt.a[0];
+			uint64_t const nam = na;
+			scan_apply<OpMaxMax>(st, na,
+				[=] __device__(uint64_t a) -> uint2 {
+					if (a == 0) return make_uint2(0u, 0u);
+					bool const seg = sg[a] != sg[a - 1];
+					bool const head = seg || (sk[a] != sk[a - 1]);
+					return make_uint2(seg ? (uint32_t)a : 0u, head ? (uint32_t)a : 0u);
+				},
+				[=] __device__(uint64_t a, uint2 excl, uint2 v0) {
+					uint32_t const segstart = excl.x > v0.x ? excl.x : v0.x;
+					uint32_t const newhead = excl.y > v0.y ? excl.y : v0.y;
+					uint32_t const g = sg[a];
+					uint32_t const i = si[a];
+					uint32_t const ng = g + (newhead - segstart);
+					sa[g + ((uint32_t)a - segstart)] = i;
+					rank[i] = ng;
+					ngrp[a] = ng;
+				}, "split_scatter", na * 92ull);
+			S.other_bytes += na * (2 * 12ull + 4ull + 32ull + 32ull);
+			auto active = [=] __device__(uint64_t a) -> uint32_t {
+				bool const hk = (a == 0) || (ngrp[a] != ngrp[a - 1]);
+				bool const hn = (a + 1 == nam) || (ngrp[a + 1] != ngrp[a]);
+				return (hk && hn) ? 0u : 1u;
+			};
+			uint32_t * ogrp = alt.a[1];
+			uint32_t * oidx = alt.a[2];
+			scan_apply<OpSum>(st, na, active,
+				[=] __device__(uint64_t a, uint32_t excl, uint32_t v0) {
+					if (v0) { ogrp[excl] = ngrp[a]; oidx[excl] = si[a]; }
+					if (a + 1 == nam) *d_total = excl + v0;
+				});
+			S.other_bytes += na * (2 * 8ull + 8ull);
+			uint64_t const nn = fetch_u32(st, d_total);
+			TRACE("rN split+compact");
+			// next round: grp = alt[1], idx = alt[2]; everything else is free
+			uint32_t * nb[6] = {alt.a[1], alt.a[2], cur.a[0], cur.a[1], cur.a[2], alt.a[0]};
+			for (int b = 0; b < 6; ++b) bufs[b] = nb[b];
+			na = nn;
+			h *= 2;
+		}
+		if (fo) {
+			B3M_LAUNCH_T(st, "extract_sample", W * 37ull, k_extract_sample, (unsigned)div_up(W, 256), 256, 0, v, (const uint32_t *)sa, W, *fo);
+			S.other_bytes += W * 37ull;
+		}
 	}
 	if (stats) { // accumulated over the leaves of a multi-block build
 		stats->rounds = stats->rounds > S.rounds ? stats->rounds : S.rounds;
 		stats->radix_passes += S.radix_passes; stats->radix_bytes += S.radix_bytes;
 		stats->active_sum += S.active_sum; stats->other_bytes += S.other_bytes;
+		stats->tied0 += S.tied0; stats->unresolved0 += S.unresolved0;
 	}
 }
 

@@ -56,8 +56,11 @@ class Engine:
         self._check(self._lib.b3m_engine_load_device(self._h, C.c_void_p(dptr), nbytes, INPUT_TYPES[inputtype]))
 
     def build(self, numblocks=1, preisarate=0, sasamplingrate=32, isasamplingrate=262144, bwtonly=False,
-              largelcpthres=16384):
-        p = BuildParams(numblocks, preisarate, sasamplingrate, isasamplingrate, 1 if bwtonly else 0, largelcpthres)
+              largelcpthres=16384, sampling="auto"):
+        """sampling: "auto" (sampled SA/ISA straight from the suffix array when one block holds the whole
+        text, LF walk otherwise) or "walk" (always the reference's LF walk from the anchors)."""
+        p = BuildParams(numblocks, preisarate, sasamplingrate, isasamplingrate, 1 if bwtonly else 0, largelcpthres,
+                        {"auto": 0, "walk": 1}[sampling])
         self._check(self._lib.b3m_engine_build(self._h, C.byref(p)))
 
     def info(self):

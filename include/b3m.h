@@ -127,7 +127,13 @@ typedef struct b3m_build_params {
 	uint64_t isasamplingrate;  /* power of two */
 	int bwtonly;
 	uint64_t largelcpthres;
+	int sampling;              /* B3M_SAMPLING_*: how the sampled SA/ISA are obtained */
 } b3m_build_params;
+/* AUTO: straight from the suffix array when the build holds all of it (one block), by the LF walk
+ * from the anchors (the reference's method, /root/reference/src/hwtPreIsaToIsa.cpp:114-161)
+ * otherwise.  WALK: always by the LF walk.  The results are identical. */
+#define B3M_SAMPLING_AUTO 0
+#define B3M_SAMPLING_WALK 1
 
 /* K2..K7: block sort -> gap arrays -> merge -> final BWT, anchors, sampled SA/ISA; results stay
  * in HBM until fetched.  Replaces BwtMergeSortTemplate<InputTypes>::computeBwt. */
@@ -149,6 +155,9 @@ typedef struct b3m_info {
 	uint64_t max_lcpnext;
 	/* device time per phase of the last build, milliseconds (CUDA events on the engine stream) */
 	float ms_decode, ms_sort, ms_extract, ms_dict, ms_gap, ms_merge, ms_walk, ms_total;
+	/* K2: suffixes that shared their whole first sort key with another suffix, and those still
+	 * tied after the in-CTA group sort (they enter the prefix-doubling rounds) */
+	uint64_t sort_tied0, sort_unresolved0;
 } b3m_info;
 int b3m_engine_info(b3m_engine * e, b3m_info * info);
 

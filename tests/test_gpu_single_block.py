@@ -114,3 +114,72 @@ def test_checkbwt_property_8mbp(eng, oracle):
     assert info["preisarate"] == 64 and info["nsa"] == 0
     rc, checked = oracle.checkbwt(t, res["bwt"], res["preisa"], numthreads=8)
     assert rc == 1 and checked == t.size
+
+
+def _check_all(oracle, res, t, prerate, sarate, isarate):
+    sa = oracle.sa_circular(t)
+    bwt, isa = oracle.bwt_from_sa(t, sa)
+    assert np.array_equal(res["bwt"], bwt)
+    assert np.array_equal(res["preisa"][:, 0], isa[::prerate].astype(np.uint64))
+    assert np.array_equal(res["sa"], sa[::sarate].astype(np.uint64))
+    assert np.array_equal(res["isa"], isa[::isarate].astype(np.uint64))
+
+
+@pytest.mark.parametrize("sampling", ["auto", "walk"])
+@pytest.mark.parametrize("itype", ["bytestream", "pacterm", "pac"])
+def test_sampling_modes_agree(eng, oracle, itype, sampling):
+    """Sampled SA/ISA straight from the suffix array (one block) == the reference's LF walk."""
+    rng = np.random.default_rng(31)
+    bases = rng.integers(0, 4, size=150_001, dtype=np.uint8)
+    if itype == "bytestream":
+        data, t = bases, bases
+    else:
+        data = oracle.encode_pac(bases)
+        t = oracle.decode_pac(data.tobytes(), term=(itype == "pacterm"))
+    res, info = run(eng, data, itype, preisarate=32, sasamplingrate=8, isasamplingrate=16, sampling=sampling)
+    assert (info["walk_lf_steps"] > 0) == (sampling == "walk")
+    _check_all(oracle, res, t, 32, 8, 16)
+
+
+@pytest.mark.parametrize("n,sigma", [(500_000, 2), (400_000, 3)])
+def test_many_small_groups_across_tiles(eng, oracle, n, sigma):
+    """Small alphabets: almost every suffix is tied after round 0, the runs of equal keys straddle
+    the tiles of the resolve kernel."""
+    rng = np.random.default_rng(n + sigma)
+    t = rng.integers(0, sigma, size=n, dtype=np.uint8)
+    res, info = run(eng, t, "bytestream", preisarate=64, sasamplingrate=32, isasamplingrate=128)
+    if sigma == 2:
+        assert info["sort_tied0"] > n // 2
+    _check_all(oracle, res, t, 64, 32, 128)
+
+
+@pytest.mark.parametrize("itype", ["bytestream", "pacterm"])
+def test_long_runs_big_groups(eng, oracle, itype):
+    """Runs of one symbol far longer than the first key: groups larger than the resolve kernel
+    sorts in place, so the prefix-doubling rounds must finish the job."""
+    rng = np.random.default_rng(77)
+    parts = []
+    for k in range(40):
+        parts.append(np.full(int(rng.integers(50, 3000)), k % 4, dtype=np.uint8))
+        parts.append(rng.integers(0, 4, size=int(rng.integers(1, 200)), dtype=np.uint8))
+    bases = np.concatenate(parts)
+    if itype == "bytestream":
+        data, t = bases, bases
+    else:
+        data = oracle.encode_pac(bases)
+        t = oracle.decode_pac(data.tobytes(), term=True)
+    res, info = run(eng, data, itype, preisarate=16, sasamplingrate=4, isasamplingrate=8)
+    assert info["sort_unresolved0"] > 0 and info["sort_rounds"] > 1
+    _check_all(oracle, res, t, 16, 4, 8)
+
+
+def test_tail_within_second_key(eng, oracle):
+    """pacterm: suffixes that reach the terminator inside the second key compare by length."""
+    for l in (17, 31, 33, 47, 48, 49, 63, 64, 65, 100):
+        for fill in (0, 3):
+            bases = np.full(l, fill, dtype=np.uint8)
+            bases[l // 2] = (fill + 1) % 4
+            data = oracle.encode_pac(bases)
+            t = oracle.decode_pac(data.tobytes(), term=True)
+            res, info = run(eng, data, "pacterm", preisarate=1, sasamplingrate=1, isasamplingrate=1)
+            _check_all(oracle, res, t, 1, 1, 1)
