@@ -6,8 +6,8 @@
 // Round 0   LSD radix sort (radix.cuh) of all W suffixes by a 32-bit key holding their first
 //           k0 = 32/keybits symbols.
 // Resolve   k_resolve: one pass over the sorted (key, index) pairs.  Runs of equal keys of up to
-//           RS_EXT suffixes are sorted inside the CTA by their next 64 key bits read from the
-//           text; with the whole text in one window the same pass emits the BWT, the anchors
+//           RS_EXT suffixes are sorted inside the CTA by the symbols carried in the aux byte and,
+//           where those tie, by their next 64 key bits read from the text; with the whole text in one window the same pass emits the BWT, the anchors
 //           and the sampled SA/ISA (FusedOut).  On random DNA this finishes the sort: no
 //           rank-by-position array is ever written.
 // Doubling  only if some suffixes are still tied (repeats longer than k0 + 64/keybits symbols,
@@ -25,13 +25,19 @@ namespace b3m {
 
 // Input order of round 0: in linear mode the nshort suffixes that run past the window end come
 // first, shortest first, so that the stable sort leaves them in front of equal padded keys.
+// aux byte of a record: the code preceding the suffix (what K3 needs) in the top `bits` bits and
+// the nx = 8/bits - 1 symbols that follow the key below it (they extend the key without a gather)
 __global__ void __launch_bounds__(256)
-k_make_keys(TextView v, unsigned bits, unsigned k0, uint64_t nshort, uint32_t * __restrict__ key, uint32_t * __restrict__ idx) {
+k_make_keys(TextView v, unsigned bits, unsigned k0, uint64_t nshort, uint32_t * __restrict__ key, uint32_t * __restrict__ idx,
+            uint8_t * __restrict__ aux) {
 	uint64_t const t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= v.W) return;
 	uint64_t const i = (t < nshort) ? (v.W - 1 - t) : (t - nshort);
-	key[t] = (uint32_t)tv_symbols(v, i, k0, bits);
+	unsigned const nx = 8u / bits - 1u;
+	uint64_t const ks = tv_symbols(v, i, k0 + nx, bits);
+	key[t] = (uint32_t)(ks >> (nx * bits));
 	idx[t] = (uint32_t)i;
+	aux[t] = (uint8_t)((tv_pred(v, i) << (nx * bits)) | (uint32_t)(ks & ((1u << (nx * bits)) - 1u)));
 }
 
 __global__ void __launch_bounds__(256)
@@ -80,122 +86,165 @@ k_extract_sample(TextView v, const uint32_t * __restrict__ sa, uint64_t m, Fused
 
 // ------------------------------------------------------------------------------------------
 // Resolve: sorts every run of equal round-0 keys that is at most RS_EXT long inside one CTA.
-// A CTA owns the runs that START in its tile; it loads RS_EXT records on either side so that
-// every suffix can find the start and the end of its run.  The second key of a suffix is its
-// next 64/bits symbols; suffixes that reach the sentinel of a linear window inside that range
-// compare by remaining length (shorter = smaller), which is also what keeps equal padded keys
-// apart.  Longer runs and runs with equal second keys stay in their current order and are
-// counted; hflag[k] = 1 where the record in final place k starts a new group.
+// A CTA owns the runs that START in its tile; it looks at RS_EXT records on either side so that
+// every suffix can find the start and the end of its run: the head flags of the region are kept
+// as ballot words, and a 64-bit window around a record gives both ends with one clz / ffs.
+// Order inside a run: (1) the symbols carried in the aux byte; only records that tie on those
+// (about 1 in 100 on random DNA) read (2) their next 64/bits symbols from the text; records
+// that reach the sentinel of a linear window inside that range compare by (3) remaining length
+// (shorter = smaller), which is also what keeps equal zero-padded keys apart.  Longer runs and
+// records equal on all three stay in their current order and are counted; hflag[k] = 1 where
+// the record in final place k starts a new group.
 // ------------------------------------------------------------------------------------------
 constexpr int RS_THREADS = 256;
-constexpr int RS_ITEMS = 8;
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
-constexpr int RS_EXT = 64;
-constexpr int RS_REG = RS_TILE + 2 * RS_EXT;
-enum { RS_SKIP = 0, RS_PASS = 1, RS_SINGLE = 2, RS_TIED = 3 };
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_EXT = 32;
+constexpr int RS_TROWS = 64;                      // tile rows of 32 records
+constexpr int RS_TILE = RS_TROWS * 32;
+constexpr int RS_ROWS = RS_TROWS + 2;             // + one row on either side
+constexpr int RS_REG = RS_ROWS * 32;
+constexpr int RS_RPW = (RS_ROWS + RS_WARPS - 1) / RS_WARPS; // rows per warp
+constexpr int RS_CSLOTS = 256;
+enum { RS_SKIP = 0, RS_PASS = 1, RS_SINGLE = 2, RS_TIED = 3, RS_TIED2 = 4 };
 
 template <bool FUSED>
 __global__ void __launch_bounds__(RS_THREADS)
 k_resolve(TextView v, unsigned bits, unsigned k0, int lin, const uint32_t * __restrict__ key, const uint32_t * __restrict__ idx,
-          uint32_t * __restrict__ sa_out, uint8_t * __restrict__ hflag, FusedOut fo, unsigned long long * __restrict__ counters) {
-	__shared__ uint32_t s_key[RS_REG];
-	__shared__ uint32_t s_idx[RS_REG];
+          const uint8_t * __restrict__ aux, uint32_t * __restrict__ sa_out, uint8_t * __restrict__ hflag, FusedOut fo, unsigned long long * __restrict__ counters) {
 	__shared__ unsigned long long s_k2[RS_REG];
+	__shared__ uint32_t s_hb[RS_ROWS + 2];        // head flags of row q in s_hb[q + 1]
+	__shared__ uint8_t s_aux[RS_REG];
 	__shared__ uint8_t s_rem[RS_REG];
-	__shared__ uint8_t s_head[RS_REG];
+	__shared__ uint32_t s_cnt[3];
 	int64_t const W = (int64_t)v.W;
-	int64_t const t0 = (int64_t)blockIdx.x * RS_TILE;
-	int64_t const kbase = t0 - RS_EXT; // region index x <-> global place kbase + x
+	int64_t const kbase = (int64_t)blockIdx.x * RS_TILE - RS_EXT; // region index x <-> global place kbase + x
+	unsigned const w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	unsigned const nx = 8u / bits - 1u;          // symbols carried in the aux byte behind the key
+	unsigned const xmask = (1u << (nx * bits)) - 1u;
 	unsigned const k2syms = 64u / bits;
-	unsigned const full = k0 + k2syms;
+	unsigned const full = k0 + nx + k2syms;
+	if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
+	if (threadIdx.x == 0) { s_hb[0] = 0xffffffffu; s_hb[RS_ROWS + 1] = 0xffffffffu; }
 
-	for (int x = threadIdx.x; x < RS_REG; x += RS_THREADS) {
+	uint32_t ridx[RS_RPW];
+	#pragma unroll
+	for (int j = 0; j < RS_RPW; ++j) {
+		int const q = j * RS_WARPS + (int)w;
+		ridx[j] = 0;
+		if (q >= RS_ROWS) continue;
+		int const x = q * 32 + (int)lane;
 		int64_t const k = kbase + x;
 		bool const valid = k >= 0 && k < W;
-		s_key[x] = valid ? key[k] : 0u;
-		s_idx[x] = valid ? idx[k] : 0u;
-	}
-	__syncthreads();
-	for (int x = threadIdx.x; x < RS_REG; x += RS_THREADS) {
-		int64_t const k = kbase + x;
+		uint32_t const mk = valid ? key[k] : 0u;
+		uint32_t const mi = valid ? idx[k] : 0u;
+		ridx[j] = mi;
+		s_aux[x] = valid ? aux[k] : (uint8_t)0;
+		// the record before this one: the lane below, or one extra load for lane 0
+		uint32_t pk = __shfl_up_sync(0xffffffffu, mk, 1), pi = __shfl_up_sync(0xffffffffu, mi, 1);
+		if (lane == 0 && k > 0 && k <= W) { pk = key[k - 1]; pi = idx[k - 1]; }
 		bool head = true;
-		if (k > 0 && k < W && x > 0) {
-			head = s_key[x] != s_key[x - 1];
-			if (lin) head = head || ((uint64_t)s_idx[x] + k0 > (uint64_t)W) || ((uint64_t)s_idx[x - 1] + k0 > (uint64_t)W);
+		if (k > 0 && k < W) {
+			head = mk != pk;
+			if (lin) head = head || ((uint64_t)mi + k0 > (uint64_t)W) || ((uint64_t)pi + k0 > (uint64_t)W);
 		}
-		s_head[x] = head ? 1 : 0;
+		uint32_t const hb = __ballot_sync(0xffffffffu, head);
+		if (lane == 0) s_hb[q + 1] = hb;
 	}
 	__syncthreads();
 
-	uint8_t cls[RS_ITEMS + 1];
-	uint16_t gs[RS_ITEMS + 1], ge[RS_ITEMS + 1];
-	uint8_t pc[RS_ITEMS + 1];
-	uint32_t ntied = 0, nunres = 0;
+	uint32_t info[RS_RPW]; // cls | gs << 4 | ge << 16
+	uint32_t part[RS_RPW]; // records of the run that are smaller by the carried symbols
+	uint32_t ntied = 0, nunres = 0, ngather = 0;
 	#pragma unroll
-	for (int j = 0; j <= RS_ITEMS; ++j) {
-		int const x = RS_EXT + j * RS_THREADS + (int)threadIdx.x;
-		cls[j] = RS_SKIP; gs[j] = ge[j] = 0; pc[j] = 0;
-		if (j == RS_ITEMS && threadIdx.x >= RS_EXT) continue;
-		int64_t const k = kbase + x;
-		if (k >= W) continue;
-		bool const tile_el = j < RS_ITEMS;
-		int y = x, steps = 0;
-		while (!s_head[y] && steps < RS_EXT - 1) { --y; ++steps; }
-		bool big = !s_head[y];
-		int z = x + 1;
-		if (!big) {
-			if (y >= RS_EXT + RS_TILE) continue; // run of the next tile
-			while (z - y <= RS_EXT && !s_head[z]) ++z;
-			big = z - y > RS_EXT;
+	for (int j = 0; j < RS_RPW; ++j) {
+		int const q = j * RS_WARPS + (int)w;
+		info[j] = RS_SKIP; part[j] = 0;
+		if (q < 1 || q >= RS_ROWS) continue;
+		int const x = q * 32 + (int)lane;
+		if (kbase + x >= W) continue;
+		bool const tile_el = q <= RS_TROWS;
+		// run start: highest head bit at or below x inside the 64 records that end with this row
+		unsigned long long const hb = ((unsigned long long)s_hb[q + 1] << 32) | s_hb[q];
+		unsigned long long const below = hb & ((2ull << (32 + lane)) - 1ull);
+		int const y = below ? (q - 1) * 32 + 63 - __clzll((long long)below) : -1;
+		// run end: lowest head bit above x inside the 64 records that start with this row
+		unsigned long long const hf = (((unsigned long long)s_hb[q + 2] << 32) | s_hb[q + 1]) >> (lane + 1);
+		int const z = hf ? x + __ffsll((long long)hf) : RS_REG + RS_EXT;
+		bool const big = y < 0 || x - y >= RS_EXT || z - y > RS_EXT;
+		uint32_t cls;
+		if (big) cls = tile_el ? RS_PASS : RS_SKIP;
+		else if (y < RS_EXT || y >= RS_EXT + RS_TILE) cls = RS_SKIP; // run of a neighbouring tile
+		else cls = (z - y == 1) ? RS_SINGLE : RS_TIED;
+		if (cls == RS_TIED) {
+			uint32_t const mx = s_aux[x] & xmask;
+			uint32_t less = 0, eq = 0;
+			for (int y2 = y; y2 < z; ++y2) {
+				uint32_t const ox = s_aux[y2] & xmask;
+				less += ox < mx ? 1u : 0u;
+				eq += ox == mx ? 1u : 0u;
+			}
+			part[j] = less;
+			++ntied;
+			if (eq > 1) {
+				// the carried symbols do not separate this record from the rest of its run: second key from the text
+				cls = RS_TIED2;
+				uint32_t const i = ridx[j];
+				s_k2[x] = tv_symbols(v, (uint64_t)i + k0 + nx, k2syms, bits);
+				uint64_t const left = (uint64_t)W - i;
+				s_rem[x] = (uint8_t)((lin && left < full) ? left : full);
+				++ngather;
+			}
 		}
-		if (big) { if (tile_el) cls[j] = RS_PASS; else continue; }
-		else if (y < RS_EXT) continue; // run of the previous tile
-		else { cls[j] = (z - y == 1) ? RS_SINGLE : RS_TIED; gs[j] = (uint16_t)y; ge[j] = (uint16_t)z; }
-		uint32_t const i = s_idx[x];
-		if (FUSED) pc[j] = (uint8_t)fo_pred(v, fo, i);
-		if (cls[j] == RS_TIED) {
-			s_k2[x] = tv_symbols(v, (uint64_t)i + k0, k2syms, bits);
-			uint64_t const left = (uint64_t)W - i;
-			s_rem[x] = (uint8_t)((lin && left < full) ? left : full);
-		}
+		info[j] = cls | ((uint32_t)(y < 0 ? 0 : y) << 4) | ((uint32_t)(z > RS_REG ? RS_REG : z) << 16);
 	}
 	__syncthreads();
 	#pragma unroll
-	for (int j = 0; j <= RS_ITEMS; ++j) {
-		if (cls[j] == RS_SKIP) continue;
-		int const x = RS_EXT + j * RS_THREADS + (int)threadIdx.x;
-		uint32_t const i = s_idx[x];
+	for (int j = 0; j < RS_RPW; ++j) {
+		uint32_t const cls = info[j] & 15u;
+		if (cls == RS_SKIP) continue;
+		int const q = j * RS_WARPS + (int)w;
+		int const x = q * 32 + (int)lane;
+		int const y = (int)((info[j] >> 4) & 0xfffu), z = (int)(info[j] >> 16);
+		uint32_t const i = ridx[j];
+		uint32_t const ax = s_aux[x];
 		int f = x;
 		uint8_t hf = 1;
-		if (cls[j] == RS_PASS) { hf = s_head[x]; ++nunres; }
-		else if (cls[j] == RS_TIED) {
+		if (cls == RS_PASS) { hf = (uint8_t)((s_hb[q + 1] >> lane) & 1u); ++nunres; }
+		else if (cls == RS_TIED) f = y + (int)part[j];
+		else if (cls == RS_TIED2) {
 			unsigned long long const mk = s_k2[x];
-			uint8_t const mr = s_rem[x];
+			uint32_t const mr = s_rem[x], mx = ax & xmask;
 			int less = 0, eqb = 0, eqt = 0;
-			for (int y = gs[j]; y < ge[j]; ++y) {
-				unsigned long long const ok = s_k2[y];
-				uint8_t const orr = s_rem[y];
+			for (int y2 = y; y2 < z; ++y2) {
+				if ((s_aux[y2] & xmask) != mx) continue;
+				unsigned long long const ok = s_k2[y2];
+				uint32_t const orr = s_rem[y2];
 				bool const eq = ok == mk && orr == mr;
 				less += (ok < mk || (ok == mk && orr < mr)) ? 1 : 0;
 				eqt += eq ? 1 : 0;
-				eqb += (eq && y < x) ? 1 : 0;
+				eqb += (eq && y2 < x) ? 1 : 0;
 			}
-			f = gs[j] + less + eqb;
+			f = y + (int)part[j] + less + eqb;
 			hf = eqb == 0 ? 1 : 0;
-			++ntied;
 			if (eqt > 1) ++nunres;
 		}
 		int64_t const kf = kbase + f;
 		sa_out[kf] = i;
 		hflag[kf] = hf;
-		if (FUSED) fo_emit(fo, i, (uint64_t)kf, pc[j]);
+		if (FUSED) fo_emit(fo, i, (uint64_t)kf, ax >> (nx * bits));
 	}
+	// per-CTA totals, spread over RS_CSLOTS counter sets (one hot address would serialise in L2)
 	ntied = __reduce_add_sync(0xffffffffu, ntied);
 	nunres = __reduce_add_sync(0xffffffffu, nunres);
-	if ((threadIdx.x & 31) == 0) {
-		if (nunres) atomicAdd(&counters[0], (unsigned long long)nunres);
-		if (ntied) atomicAdd(&counters[1], (unsigned long long)ntied);
+	ngather = __reduce_add_sync(0xffffffffu, ngather);
+	if (lane == 0) {
+		if (nunres) atomicAdd(&s_cnt[0], nunres);
+		if (ntied) atomicAdd(&s_cnt[1], ntied);
+		if (ngather) atomicAdd(&s_cnt[2], ngather);
 	}
+	__syncthreads();
+	if (threadIdx.x < 3 && s_cnt[threadIdx.x])
+		atomicAdd(&counters[(blockIdx.x % RS_CSLOTS) * 4 + threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
 }
 
 static double wall_ms() {
@@ -220,43 +269,52 @@ void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W,
 	unsigned const bits = T.keybits;
 	unsigned const k0 = 32 / bits;
 	uint64_t const nshort = circular ? 0 : (W < (uint64_t)(k0 - 1) ? W : (uint64_t)(k0 - 1));
-	TextView v{T.codes, bits == 2 ? T.packed : nullptr, T.ntext, wstart, W, circular, text_wraps};
+	TextView v{T.codes, bits == 2 ? T.packed : nullptr, T.ntext, wstart, W, circular, text_wraps, T.has_term};
 	int const lin = !circular;
 	SortStats S;
 	double t_last = wall_ms();
 
 	DevBuf<uint32_t> scalar(st, 4);
 	uint32_t * d_total = scalar.get();
-	DevBuf<unsigned long long> counters(st, 2);
+	DevBuf<unsigned long long> counters(st, 4 * RS_CSLOTS);
 	DevBuf<uint8_t> hflag(st, W);
 	uint64_t unresolved = 0;
 	{
 		// ---------------- round 0 ----------------
 		DevBuf<uint32_t> key0(st, W), key1(st, W), idx0(st, W), idx1(st, W);
-		RadixRec<2> cur{{key0.get(), idx0.get()}}, alt{{key1.get(), idx1.get()}};
+		DevBuf<uint8_t> aux0(st, W), aux1(st, W);
+		RadixRec<2> cur{{key0.get(), idx0.get()}, aux0.get()}, alt{{key1.get(), idx1.get()}, aux1.get()};
 		unsigned const grid = (unsigned)div_up(W, 256);
 		TRACE("r0 alloc");
-		B3M_LAUNCH_T(st, "make_keys", W * 9ull, k_make_keys, grid, 256, 0, v, bits, k0, nshort, cur.a[0], cur.a[1]);
-		S.other_bytes += W * (1ull + 8ull);
 		RadixStats rs;
-		TRACE("r0 make_keys");
-		radix_sort_bits<2>(st, cur, alt, 0, W, 0, 32, &rs);
+		if (bits == 2 && v.packed) {
+			// the first pass reads its records straight from the packed text
+			radix_sort_suffix_keys(st, v, nshort, k0, cur, alt, &rs);
+		} else {
+			B3M_LAUNCH_T(st, "make_keys", W * 10ull, k_make_keys, grid, 256, 0, v, bits, k0, nshort, cur.a[0], cur.a[1], cur.aux);
+			S.other_bytes += W * (1ull + 9ull);
+			TRACE("r0 make_keys");
+			radix_sort_bits<2>(st, cur, alt, 0, W, 0, 32, &rs);
+		}
 		TRACE("r0 radix");
 		S.radix_passes += rs.passes; S.radix_bytes += rs.bytes; S.active_sum += W; S.rounds = 1;
 		// ---------------- resolve (+ fused extraction) ----------------
-		B3M_CUDA(cudaMemsetAsync(counters.get(), 0, 16, st.s));
+		B3M_CUDA(cudaMemsetAsync(counters.get(), 0, 32 * RS_CSLOTS, st.s));
 		unsigned const rgrid = (unsigned)div_up(W, RS_TILE);
-		uint64_t const rbytes = W * (8ull + 4ull + 1ull + (fo ? 33ull : 0ull));
+		// key + index + aux in, suffix array + head flag (+ BWT code) out; second-key gathers are added below
+		uint64_t const rbytes = W * (9ull + 4ull + 1ull + (fo ? 1ull : 0ull));
 		if (fo) B3M_LAUNCH_T(st, "resolve_extract", rbytes, (k_resolve<true>), rgrid, RS_THREADS, 0, v, bits, k0, lin, (const uint32_t *)cur.a[0],
-		                     (const uint32_t *)cur.a[1], alt.a[1], hflag.get(), *fo, counters.get());
+		                     (const uint32_t *)cur.a[1], (const uint8_t *)cur.aux, alt.a[1], hflag.get(), *fo, counters.get());
 		else B3M_LAUNCH_T(st, "resolve", rbytes, (k_resolve<false>), rgrid, RS_THREADS, 0, v, bits, k0, lin, (const uint32_t *)cur.a[0],
-		                  (const uint32_t *)cur.a[1], alt.a[1], hflag.get(), FusedOut(), counters.get());
-		unsigned long long hc[2];
-		B3M_CUDA(cudaMemcpyAsync(hc, counters.get(), 16, cudaMemcpyDeviceToHost, st.s));
+		                  (const uint32_t *)cur.a[1], (const uint8_t *)cur.aux, alt.a[1], hflag.get(), FusedOut(), counters.get());
+		std::vector<unsigned long long> hcs(4 * RS_CSLOTS);
+		B3M_CUDA(cudaMemcpyAsync(hcs.data(), counters.get(), 32 * RS_CSLOTS, cudaMemcpyDeviceToHost, st.s));
 		B3M_CUDA(cudaStreamSynchronize(st.s));
+		unsigned long long hc[4] = {0, 0, 0, 0};
+		for (int q = 0; q < RS_CSLOTS; ++q) for (int c = 0; c < 3; ++c) hc[c] += hcs[4 * q + c];
 		unresolved = hc[0];
 		S.tied0 = hc[1]; S.unresolved0 = hc[0];
-		S.other_bytes += rbytes + 32ull * hc[1];
+		S.other_bytes += rbytes + 32ull * hc[2];
 		sa_buf = (alt.a[1] == idx1.get()) ? std::move(idx1) : std::move(idx0);
 		TRACE("r0 resolve");
 	}

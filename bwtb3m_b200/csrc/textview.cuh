@@ -25,6 +25,7 @@ struct TextView {
 	uint64_t W;
 	int circular;
 	int text_wraps;
+	int has_term;            // the text ends in an implicit unique terminator (pacterm)
 };
 
 // symbol at window index i (any i >= 0)
@@ -66,6 +67,15 @@ __device__ __forceinline__ uint64_t tv_symbols(TextView const & v, uint64_t i, u
 	uint64_t k = 0;
 	for (uint32_t s = 0; s < count; ++s) k = (k << bits) | tv_symbol(v, i + s);
 	return k;
+}
+
+// Code preceding the suffix at window index i, as it appears in the BWT: 0 when the suffix starts
+// at text position 0 of a terminated text (the row of the terminator, fixed up by the caller).
+__device__ __forceinline__ uint32_t tv_pred(TextView const & v, uint64_t i) {
+	uint64_t p = v.wstart + i;
+	if (p >= v.ntext) p %= v.ntext;
+	if (p == 0) return v.has_term ? 0u : (uint32_t)v.codes[v.ntext - 1];
+	return v.codes[p - 1];
 }
 
 // code preceding text position p (p >= 1)
