@@ -103,41 +103,42 @@ constexpr int RS_TROWS = 64;                      // tile rows of 32 records
 constexpr int RS_TILE = RS_TROWS * 32;
 constexpr int RS_ROWS = RS_TROWS + 2;             // + one row on either side
 constexpr int RS_REG = RS_ROWS * 32;
-constexpr int RS_RPW = (RS_ROWS + RS_WARPS - 1) / RS_WARPS; // rows per warp
 constexpr int RS_CSLOTS = 256;
-enum { RS_SKIP = 0, RS_PASS = 1, RS_SINGLE = 2, RS_TIED = 3, RS_TIED2 = 4 };
+
+// second key of the suffix at window index i: its symbols from k0+nx on, and its length if it
+// reaches the sentinel of a linear window inside that range
+__device__ __forceinline__ void rs_second_key(TextView const & v, unsigned bits, unsigned skip, int lin, uint32_t i, unsigned long long & k2, uint32_t & rem) {
+	unsigned const k2syms = 64u / bits;
+	k2 = tv_symbols(v, (uint64_t)i + skip, k2syms, bits);
+	uint64_t const left = v.W - i;
+	rem = (uint32_t)((lin && left < skip + k2syms) ? left : skip + k2syms);
+}
 
 template <bool FUSED>
 __global__ void __launch_bounds__(RS_THREADS)
 k_resolve(TextView v, unsigned bits, unsigned k0, int lin, const uint32_t * __restrict__ key, const uint32_t * __restrict__ idx,
           const uint8_t * __restrict__ aux, uint32_t * __restrict__ sa_out, uint8_t * __restrict__ hflag, FusedOut fo, unsigned long long * __restrict__ counters) {
-	__shared__ unsigned long long s_k2[RS_REG];
+	__shared__ uint32_t s_idx[RS_REG];
 	__shared__ uint32_t s_hb[RS_ROWS + 2];        // head flags of row q in s_hb[q + 1]
 	__shared__ uint8_t s_aux[RS_REG];
-	__shared__ uint8_t s_rem[RS_REG];
 	__shared__ uint32_t s_cnt[3];
 	int64_t const W = (int64_t)v.W;
 	int64_t const kbase = (int64_t)blockIdx.x * RS_TILE - RS_EXT; // region index x <-> global place kbase + x
 	unsigned const w = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	unsigned const nx = 8u / bits - 1u;          // symbols carried in the aux byte behind the key
-	unsigned const xmask = (1u << (nx * bits)) - 1u;
-	unsigned const k2syms = 64u / bits;
-	unsigned const full = k0 + nx + k2syms;
+	unsigned const xbits = nx * bits;
+	unsigned const xmask = (1u << xbits) - 1u;
 	if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
 	if (threadIdx.x == 0) { s_hb[0] = 0xffffffffu; s_hb[RS_ROWS + 1] = 0xffffffffu; }
 
-	uint32_t ridx[RS_RPW];
-	#pragma unroll
-	for (int j = 0; j < RS_RPW; ++j) {
-		int const q = j * RS_WARPS + (int)w;
-		ridx[j] = 0;
-		if (q >= RS_ROWS) continue;
+	#pragma unroll 1
+	for (int q = (int)w; q < RS_ROWS; q += RS_WARPS) {
 		int const x = q * 32 + (int)lane;
 		int64_t const k = kbase + x;
 		bool const valid = k >= 0 && k < W;
 		uint32_t const mk = valid ? key[k] : 0u;
 		uint32_t const mi = valid ? idx[k] : 0u;
-		ridx[j] = mi;
+		s_idx[x] = mi;
 		s_aux[x] = valid ? aux[k] : (uint8_t)0;
 		// the record before this one: the lane below, or one extra load for lane 0
 		uint32_t pk = __shfl_up_sync(0xffffffffu, mk, 1), pi = __shfl_up_sync(0xffffffffu, mi, 1);
@@ -152,86 +153,64 @@ k_resolve(TextView v, unsigned bits, unsigned k0, int lin, const uint32_t * __re
 	}
 	__syncthreads();
 
-	uint32_t info[RS_RPW]; // cls | gs << 4 | ge << 16
-	uint32_t part[RS_RPW]; // records of the run that are smaller by the carried symbols
 	uint32_t ntied = 0, nunres = 0, ngather = 0;
-	#pragma unroll
-	for (int j = 0; j < RS_RPW; ++j) {
-		int const q = j * RS_WARPS + (int)w;
-		info[j] = RS_SKIP; part[j] = 0;
-		if (q < 1 || q >= RS_ROWS) continue;
+	#pragma unroll 1
+	for (int q = 1 + (int)w; q < RS_ROWS; q += RS_WARPS) {
 		int const x = q * 32 + (int)lane;
 		if (kbase + x >= W) continue;
-		bool const tile_el = q <= RS_TROWS;
 		// run start: highest head bit at or below x inside the 64 records that end with this row
-		unsigned long long const hb = ((unsigned long long)s_hb[q + 1] << 32) | s_hb[q];
-		unsigned long long const below = hb & ((2ull << (32 + lane)) - 1ull);
+		unsigned long long const hbw = ((unsigned long long)s_hb[q + 1] << 32) | s_hb[q];
+		unsigned long long const below = hbw & ((2ull << (32 + lane)) - 1ull);
 		int const y = below ? (q - 1) * 32 + 63 - __clzll((long long)below) : -1;
 		// run end: lowest head bit above x inside the 64 records that start with this row
-		unsigned long long const hf = (((unsigned long long)s_hb[q + 2] << 32) | s_hb[q + 1]) >> (lane + 1);
-		int const z = hf ? x + __ffsll((long long)hf) : RS_REG + RS_EXT;
+		unsigned long long const hfw = (((unsigned long long)s_hb[q + 2] << 32) | s_hb[q + 1]) >> (lane + 1);
+		int const z = hfw ? x + __ffsll((long long)hfw) : RS_REG + RS_EXT;
 		bool const big = y < 0 || x - y >= RS_EXT || z - y > RS_EXT;
-		uint32_t cls;
-		if (big) cls = tile_el ? RS_PASS : RS_SKIP;
-		else if (y < RS_EXT || y >= RS_EXT + RS_TILE) cls = RS_SKIP; // run of a neighbouring tile
-		else cls = (z - y == 1) ? RS_SINGLE : RS_TIED;
-		if (cls == RS_TIED) {
-			uint32_t const mx = s_aux[x] & xmask;
-			uint32_t less = 0, eq = 0;
-			for (int y2 = y; y2 < z; ++y2) {
-				uint32_t const ox = s_aux[y2] & xmask;
-				less += ox < mx ? 1u : 0u;
-				eq += ox == mx ? 1u : 0u;
-			}
-			part[j] = less;
-			++ntied;
-			if (eq > 1) {
-				// the carried symbols do not separate this record from the rest of its run: second key from the text
-				cls = RS_TIED2;
-				uint32_t const i = ridx[j];
-				s_k2[x] = tv_symbols(v, (uint64_t)i + k0 + nx, k2syms, bits);
-				uint64_t const left = (uint64_t)W - i;
-				s_rem[x] = (uint8_t)((lin && left < full) ? left : full);
-				++ngather;
-			}
-		}
-		info[j] = cls | ((uint32_t)(y < 0 ? 0 : y) << 4) | ((uint32_t)(z > RS_REG ? RS_REG : z) << 16);
-	}
-	__syncthreads();
-	#pragma unroll
-	for (int j = 0; j < RS_RPW; ++j) {
-		uint32_t const cls = info[j] & 15u;
-		if (cls == RS_SKIP) continue;
-		int const q = j * RS_WARPS + (int)w;
-		int const x = q * 32 + (int)lane;
-		int const y = (int)((info[j] >> 4) & 0xfffu), z = (int)(info[j] >> 16);
-		uint32_t const i = ridx[j];
 		uint32_t const ax = s_aux[x];
 		int f = x;
-		uint8_t hf = 1;
-		if (cls == RS_PASS) { hf = (uint8_t)((s_hb[q + 1] >> lane) & 1u); ++nunres; }
-		else if (cls == RS_TIED) f = y + (int)part[j];
-		else if (cls == RS_TIED2) {
-			unsigned long long const mk = s_k2[x];
-			uint32_t const mr = s_rem[x], mx = ax & xmask;
-			int less = 0, eqb = 0, eqt = 0;
-			for (int y2 = y; y2 < z; ++y2) {
-				if ((s_aux[y2] & xmask) != mx) continue;
-				unsigned long long const ok = s_k2[y2];
-				uint32_t const orr = s_rem[y2];
-				bool const eq = ok == mk && orr == mr;
-				less += (ok < mk || (ok == mk && orr < mr)) ? 1 : 0;
-				eqt += eq ? 1 : 0;
-				eqb += (eq && y2 < x) ? 1 : 0;
+		uint32_t hf = 1;
+		if (big) {
+			if (q > RS_TROWS) continue;                        // the next tile passes it through
+			hf = (s_hb[q + 1] >> lane) & 1u;
+			++nunres;
+		} else {
+			if (y < RS_EXT || y >= RS_EXT + RS_TILE) continue; // run of a neighbouring tile
+			if (z - y > 1) {
+				uint32_t const mx = ax & xmask;
+				uint32_t less = 0, eq = 0;
+				for (int y2 = y; y2 < z; ++y2) {
+					uint32_t const ox = s_aux[y2] & xmask;
+					less += ox < mx ? 1u : 0u;
+					eq += ox == mx ? 1u : 0u;
+				}
+				++ntied;
+				f = y + (int)less;
+				if (eq > 1) {
+					// the carried symbols do not separate this record from the rest of its run: compare the
+					// second keys, read from the text (about 1 record in 100 on random DNA)
+					unsigned long long mk2; uint32_t mr;
+					rs_second_key(v, bits, k0 + nx, lin, s_idx[x], mk2, mr);
+					uint32_t eqb = 0, eqa = 0;
+					for (int y2 = y; y2 < z; ++y2) {
+						if (y2 == x || (s_aux[y2] & xmask) != mx) continue;
+						unsigned long long ok2; uint32_t orr;
+						rs_second_key(v, bits, k0 + nx, lin, s_idx[y2], ok2, orr);
+						bool const same = ok2 == mk2 && orr == mr;
+						f += (ok2 < mk2 || (ok2 == mk2 && orr < mr) || (same && y2 < x)) ? 1 : 0;
+						eqb += (same && y2 < x) ? 1u : 0u;
+						eqa += same ? 1u : 0u;
+					}
+					hf = eqb == 0 ? 1u : 0u;
+					if (eqa) ++nunres;
+					++ngather;
+				}
 			}
-			f = y + (int)part[j] + less + eqb;
-			hf = eqb == 0 ? 1 : 0;
-			if (eqt > 1) ++nunres;
 		}
-		int64_t const kf = kbase + f;
+		uint32_t const i = s_idx[x];
+		uint32_t const kf = (uint32_t)(kbase + f);
 		sa_out[kf] = i;
-		hflag[kf] = hf;
-		if (FUSED) fo_emit(fo, i, (uint64_t)kf, ax >> (nx * bits));
+		hflag[kf] = (uint8_t)hf;
+		if (FUSED) fo_emit(fo, i, (uint64_t)kf, ax >> xbits);
 	}
 	// per-CTA totals, spread over RS_CSLOTS counter sets (one hot address would serialise in L2)
 	ntied = __reduce_add_sync(0xffffffffu, ntied);
