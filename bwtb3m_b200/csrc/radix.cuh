@@ -18,10 +18,11 @@
 
 namespace b3m {
 
-constexpr int RADIX_THREADS = 256;
+constexpr int RADIX_THREADS = 512;
 constexpr int RADIX_WARPS = RADIX_THREADS / 32;
 constexpr int RADIX_ITEMS = 16;
-constexpr int RADIX_TILE = RADIX_THREADS * RADIX_ITEMS; // 4096 records
+constexpr int RADIX_CTAS_PER_SM = 2;
+constexpr int RADIX_TILE = RADIX_THREADS * RADIX_ITEMS; // 8192 records: long runs per digit keep the scattered writes DRAM-friendly
 constexpr int RADIX_BINS = 256;
 constexpr int RADIX_MAXDIG = 4;
 
@@ -33,14 +34,17 @@ struct RadixRec {
 
 // lanes holding the same 8-bit digit
 __device__ __forceinline__ unsigned warp_peers8(uint32_t d) {
-	unsigned peers = 0xffffffffu;
+	unsigned mism = 0u; // lanes whose digit differs from mine in some bit
 	#pragma unroll
 	for (int b = 0; b < 8; ++b) {
-		bool const bit = (d >> b) & 1u;
-		unsigned const m = __ballot_sync(0xffffffffu, bit);
-		peers &= bit ? m : ~m;
+		// m = ballot(bit b of d); mism |= bit ? ~m : m   (predicate straight from the AND, no shifts or selects)
+		asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 m, t;\n\t"
+		             "and.b32 t, %1, %2;\n\tsetp.ne.u32 p, t, 0;\n\t"
+		             "vote.sync.ballot.b32 m, p, 0xffffffff;\n\t"
+		             "@p not.b32 m, m;\n\tor.b32 %0, %0, m;\n\t}"
+		             : "+r"(mism) : "r"(d), "r"(1u << b));
 	}
-	return peers;
+	return ~mism;
 }
 
 // ---- digit histograms of one key array: up to 4 digits in one read -----------------------
@@ -114,31 +118,36 @@ __device__ __forceinline__ void radix_text_record(RadixTextSrc const & S, uint64
 	aux = ((tv_pred(S.v, i) << (nx * S.bits)) | (uint32_t)(ks & ((1u << (nx * S.bits)) - 1u))) & 255u;
 }
 
-template <int NA, bool AUX, bool TEXT>
-__global__ void __launch_bounds__(RADIX_THREADS, 3)
+template <int NA, bool AUX, bool TEXT, bool FULL>
+__global__ void __launch_bounds__(RADIX_THREADS, RADIX_CTAS_PER_SM)
 k_radix_onesweep(RadixPassArgs<NA> A, RadixTextSrc S, uint64_t n, int shift, uint32_t mask, const uint32_t * __restrict__ base /* [256] */,
-                 unsigned long long * __restrict__ status /* [ntiles][256] */, uint32_t * __restrict__ ticket) {
-	__shared__ uint32_t wcnt[RADIX_WARPS][RADIX_BINS];
+                 unsigned long long * __restrict__ status /* [ntiles][256] */, uint32_t * __restrict__ ticket, uint32_t flags) {
+	__shared__ uint16_t wcnt[RADIX_WARPS][RADIX_BINS]; // counts, then tile-local offsets: all below RADIX_TILE
 	__shared__ uint32_t gbase[RADIX_BINS];
-	__shared__ uint32_t skey[RADIX_TILE];
-	__shared__ uint32_t sval[RADIX_TILE];
-	__shared__ uint8_t saux[AUX ? RADIX_TILE : 4];
+	__shared__ uint32_t wsum[RADIX_BINS / 32];
+	// dynamic part (radix_smem_bytes): keys, one payload array, aux bytes of the tile in sorted order
+	extern __shared__ __align__(16) uint8_t radix_dyn[];
+	uint32_t * const skey = reinterpret_cast<uint32_t *>(radix_dyn);
+	uint32_t * const sval = skey + RADIX_TILE;
+	uint8_t * const saux = reinterpret_cast<uint8_t *>(sval + (NA > 1 ? RADIX_TILE : 0));
 	__shared__ uint32_t s_tile;
 	unsigned const w = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-	for (int i = threadIdx.x; i < RADIX_WARPS * RADIX_BINS; i += RADIX_THREADS) (&wcnt[0][0])[i] = 0;
+	for (int i = threadIdx.x; i < RADIX_WARPS * RADIX_BINS / 2; i += RADIX_THREADS) reinterpret_cast<uint32_t *>(&wcnt[0][0])[i] = 0;
 	__syncthreads();
 	uint32_t const tile = s_tile;
 	uint64_t const tbase = (uint64_t)tile * RADIX_TILE;
 	uint64_t const chunk = tbase + (uint64_t)w * (32 * RADIX_ITEMS);
-	uint32_t const nvalid = (n - tbase) < (uint64_t)RADIX_TILE ? (uint32_t)(n - tbase) : (uint32_t)RADIX_TILE;
+	// FULL: every record of the tile exists (the one partial tile at the end is a launch of its own)
+	uint32_t const nvalid = FULL ? (uint32_t)RADIX_TILE : ((n - tbase) < (uint64_t)RADIX_TILE ? (uint32_t)(n - tbase) : (uint32_t)RADIX_TILE);
+	#define RADIX_VALID(i) (FULL || (i) < n)
 
 	uint32_t k[RADIX_ITEMS];
-	uint32_t taux[TEXT ? RADIX_ITEMS / 4 : 1];
+	uint32_t taux[TEXT ? (RADIX_ITEMS + 3) / 4 : 1];
 	if (TEXT) {
 		static_assert(!TEXT || (NA == 2 && AUX), "text source: (key, index) records with an aux byte");
-		// Fast path (2-bit packed text, the warp's 512 records away from both ends of the window and
-		// of the text): lane l reads the words under positions p0+l, p0+l+32, ... -- its bit offset
+		// Fast path (2-bit packed text, the warp's records away from both ends of the window and of
+		// the text): lane l reads the words under positions p0+l, p0+l+32, ... -- its bit offset
 		// inside a word never changes, and every word is the second half of the previous record's window.
 		uint64_t const i0 = chunk - S.nshort;
 		uint64_t p0 = S.v.wstart + i0;
@@ -167,7 +176,7 @@ k_radix_onesweep(RadixPassArgs<NA> A, RadixTextSrc S, uint64_t n, int shift, uin
 			for (int j = 0; j < RADIX_ITEMS; ++j) {
 				uint64_t const i = chunk + j * 32 + lane;
 				uint32_t kk = 0xffffffffu, ii = 0, aa = 0;
-				if (i < n) radix_text_record(S, i, kk, ii, aa);
+				if (RADIX_VALID(i)) radix_text_record(S, i, kk, ii, aa);
 				k[j] = kk;
 				if ((j & 3) == 0) taux[TEXT ? j / 4 : 0] = aa; else taux[TEXT ? j / 4 : 0] |= aa << (8 * (j & 3));
 			}
@@ -176,44 +185,57 @@ k_radix_onesweep(RadixPassArgs<NA> A, RadixTextSrc S, uint64_t n, int shift, uin
 		#pragma unroll
 		for (int j = 0; j < RADIX_ITEMS; ++j) {
 			uint64_t const i = chunk + j * 32 + lane;
-			k[j] = (i < n) ? A.in[0][i] : 0xffffffffu;
+			k[j] = RADIX_VALID(i) ? A.in[0][i] : 0xffffffffu;
 		}
 	}
 	// stable rank inside the warp; records past n take the last bin and, being last in tile
 	// order, rank behind every real record
 	uint16_t slot[RADIX_ITEMS];
-	uint32_t * mycnt = wcnt[w];
+	uint16_t * mycnt = wcnt[w];
 	unsigned const lt = lanemask_lt();
 	#pragma unroll
 	for (int j = 0; j < RADIX_ITEMS; ++j) {
 		uint64_t const i = chunk + j * 32 + lane;
-		uint32_t const d = (i < n) ? ((k[j] >> shift) & mask) : (uint32_t)(RADIX_BINS - 1);
+		uint32_t const d = RADIX_VALID(i) ? ((k[j] >> shift) & mask) : (uint32_t)(RADIX_BINS - 1);
 		unsigned const peers = warp_peers8(d);
 		uint32_t const before = mycnt[d];
 		__syncwarp();
-		if ((peers & lt) == 0) mycnt[d] = before + __popc(peers);
+		if ((peers & lt) == 0) mycnt[d] = (uint16_t)(before + __popc(peers));
 		__syncwarp();
 		slot[j] = (uint16_t)(before + __popc(peers & lt));
 	}
 	__syncthreads();
 	// per digit (thread d <-> bin d): scan over warps, publish the tile aggregate, scan over digits
-	{
+	bool const binthread = threadIdx.x < RADIX_BINS;
+	uint32_t bs = 0, bcnt = 0, bincl = 0;
+	volatile unsigned long long * stw = status + (uint64_t)tile * RADIX_BINS + (threadIdx.x & (RADIX_BINS - 1));
+	if (binthread) {
 		uint32_t const d = threadIdx.x;
-		uint32_t s = 0;
 		#pragma unroll
-		for (int ww = 0; ww < RADIX_WARPS; ++ww) { uint32_t const t = wcnt[ww][d]; wcnt[ww][d] = s; s += t; }
+		for (int ww = 0; ww < RADIX_WARPS; ++ww) { uint32_t const t = wcnt[ww][d]; wcnt[ww][d] = (uint16_t)bs; bs += t; }
 		// invalid records were counted in the last bin: they are not part of the global count
-		uint32_t const cnt = (d == RADIX_BINS - 1) ? s - (RADIX_TILE - nvalid) : s;
-		volatile unsigned long long * st = status + (uint64_t)tile * RADIX_BINS + d;
-		*st = (tile == 0 ? RADIX_FLAG_INC : RADIX_FLAG_AGG) | cnt;
-		uint32_t total;
-		uint32_t const incl = block_scan_inclusive<OpSum>(s, &total);
-		uint32_t const dstart = incl - s;
+		bcnt = (!FULL && d == RADIX_BINS - 1) ? bs - (RADIX_TILE - nvalid) : bs;
+		*stw = (tile == 0 ? RADIX_FLAG_INC : RADIX_FLAG_AGG) | bcnt;
+		bincl = bs;
 		#pragma unroll
-		for (int ww = 0; ww < RADIX_WARPS; ++ww) wcnt[ww][d] += dstart;
+		for (int o = 1; o < 32; o <<= 1) {
+			uint32_t const t = __shfl_up_sync(0xffffffffu, bincl, o);
+			if (lane >= (unsigned)o) bincl += t;
+		}
+		if (lane == 31) wsum[w] = bincl;
+	}
+	__syncthreads();
+	if (binthread) {
+		uint32_t const d = threadIdx.x;
+		uint32_t add = 0;
+		#pragma unroll
+		for (int ww = 0; ww < RADIX_BINS / 32; ++ww) add += (ww < (int)w) ? wsum[ww] : 0u;
+		uint32_t const dstart = bincl - bs + add;
+		#pragma unroll
+		for (int ww = 0; ww < RADIX_WARPS; ++ww) wcnt[ww][d] = (uint16_t)(wcnt[ww][d] + dstart);
 		// decoupled look-back
 		uint32_t excl = 0;
-		if (tile > 0) {
+		if (tile > 0 && !(flags & 1u)) {
 			int64_t t = (int64_t)tile - 1;
 			while (true) {
 				unsigned long long const v = *(volatile unsigned long long *)(status + (uint64_t)t * RADIX_BINS + d);
@@ -222,7 +244,7 @@ k_radix_onesweep(RadixPassArgs<NA> A, RadixTextSrc S, uint64_t n, int shift, uin
 				if ((v >> 62) == 2) break;
 				--t;
 			}
-			*st = RADIX_FLAG_INC | (unsigned long long)(excl + cnt);
+			*stw = RADIX_FLAG_INC | (unsigned long long)(excl + bcnt);
 		}
 		gbase[d] = base[d] + excl - dstart;
 	}
@@ -230,7 +252,7 @@ k_radix_onesweep(RadixPassArgs<NA> A, RadixTextSrc S, uint64_t n, int shift, uin
 	#pragma unroll
 	for (int j = 0; j < RADIX_ITEMS; ++j) {
 		uint64_t const i = chunk + j * 32 + lane;
-		uint32_t const d = (i < n) ? ((k[j] >> shift) & mask) : (uint32_t)(RADIX_BINS - 1);
+		uint32_t const d = RADIX_VALID(i) ? ((k[j] >> shift) & mask) : (uint32_t)(RADIX_BINS - 1);
 		slot[j] = (uint16_t)(slot[j] + wcnt[w][d]);
 		skey[slot[j]] = k[j];
 	}
@@ -241,14 +263,14 @@ k_radix_onesweep(RadixPassArgs<NA> A, RadixTextSrc S, uint64_t n, int shift, uin
 		for (int j = 0; j < RADIX_ITEMS; ++j) {
 			uint64_t const i = chunk + j * 32 + lane;
 			if (TEXT) v[j] = (uint32_t)((i < S.nshort) ? (S.v.W - 1 - i) : (i - S.nshort)); // the record's window index
-			else v[j] = (i < n) ? A.in[1][i] : 0u;
+			else v[j] = RADIX_VALID(i) ? A.in[1][i] : 0u;
 		}
 	}
 	__syncthreads();
 	#pragma unroll
 	for (int j = 0; j < RADIX_ITEMS; ++j) {
 		uint32_t const s = j * RADIX_THREADS + threadIdx.x;
-		if (s < nvalid) {
+		if (FULL || s < nvalid) {
 			uint32_t const kk = skey[s];
 			A.out[0][gbase[(kk >> shift) & mask] + s] = kk;
 		}
@@ -260,7 +282,7 @@ k_radix_onesweep(RadixPassArgs<NA> A, RadixTextSrc S, uint64_t n, int shift, uin
 			#pragma unroll
 			for (int j = 0; j < RADIX_ITEMS; ++j) {
 				uint64_t const i = chunk + j * 32 + lane;
-				v[j] = (i < n) ? A.in[a][i] : 0u;
+				v[j] = RADIX_VALID(i) ? A.in[a][i] : 0u;
 			}
 		}
 		#pragma unroll
@@ -269,7 +291,7 @@ k_radix_onesweep(RadixPassArgs<NA> A, RadixTextSrc S, uint64_t n, int shift, uin
 		#pragma unroll
 		for (int j = 0; j < RADIX_ITEMS; ++j) {
 			uint32_t const s = j * RADIX_THREADS + threadIdx.x;
-			if (s < nvalid) A.out[a][gbase[(skey[s] >> shift) & mask] + s] = sval[s];
+			if (FULL || s < nvalid) A.out[a][gbase[(skey[s] >> shift) & mask] + s] = sval[s];
 		}
 	}
 	if (AUX) {
@@ -277,15 +299,48 @@ k_radix_onesweep(RadixPassArgs<NA> A, RadixTextSrc S, uint64_t n, int shift, uin
 		for (int j = 0; j < RADIX_ITEMS; ++j) {
 			uint64_t const i = chunk + j * 32 + lane;
 			if (TEXT) saux[slot[j]] = (uint8_t)(taux[TEXT ? j / 4 : 0] >> (8 * (j & 3)));
-			else saux[slot[j]] = (i < n) ? A.aux_in[i] : (uint8_t)0;
+			else saux[slot[j]] = RADIX_VALID(i) ? A.aux_in[i] : (uint8_t)0;
 		}
 		__syncthreads();
 		#pragma unroll
 		for (int j = 0; j < RADIX_ITEMS; ++j) {
 			uint32_t const s = j * RADIX_THREADS + threadIdx.x;
-			if (s < nvalid) A.aux_out[gbase[(skey[s] >> shift) & mask] + s] = saux[s];
+			if (FULL || s < nvalid) A.aux_out[gbase[(skey[s] >> shift) & mask] + s] = saux[s];
 		}
 	}
+	#undef RADIX_VALID
+}
+
+template <int NA, bool AUX>
+constexpr size_t radix_smem_bytes() { return (size_t)RADIX_TILE * (4 + (NA > 1 ? 4 : 0) + (AUX ? 1 : 0)); }
+
+// one pass: the full tiles, then the partial tile at the end (same ticket counter, so it is the last tile)
+template <int NA, bool AUX, bool TEXT>
+void radix_launch_pass(Stream & st, const char * label, uint64_t pbytes, RadixPassArgs<NA> const & A, RadixTextSrc const & S, uint64_t n,
+                       int shift, uint32_t mask, const uint32_t * base, unsigned long long * status, uint32_t * ticket) {
+	uint32_t const nfull = (uint32_t)(n / RADIX_TILE);
+	bool const partial = (n % RADIX_TILE) != 0;
+	uint32_t const flags = 0;
+	size_t const smem = radix_smem_bytes<NA, AUX>();
+	static bool configured = false; // per template instance
+	if (!configured) {
+		B3M_CUDA(cudaFuncSetAttribute(k_radix_onesweep<NA, AUX, TEXT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		B3M_CUDA(cudaFuncSetAttribute(k_radix_onesweep<NA, AUX, TEXT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		configured = true;
+	}
+	if (st.kt.on) {
+		KernelTimes::Rec r{label, pbytes, st.kt.get(), st.kt.get()};
+		cudaEventRecord(r.a, st.s);
+		if (nfull) k_radix_onesweep<NA, AUX, TEXT, true><<<nfull, RADIX_THREADS, smem, st.s>>>(A, S, n, shift, mask, base, status, ticket, flags);
+		if (partial) k_radix_onesweep<NA, AUX, TEXT, false><<<1, RADIX_THREADS, smem, st.s>>>(A, S, n, shift, mask, base, status, ticket, flags);
+		cudaEventRecord(r.b, st.s);
+		st.kt.recs.push_back(r);
+	} else {
+		if (nfull) k_radix_onesweep<NA, AUX, TEXT, true><<<nfull, RADIX_THREADS, smem, st.s>>>(A, S, n, shift, mask, base, status, ticket, flags);
+		if (partial) k_radix_onesweep<NA, AUX, TEXT, false><<<1, RADIX_THREADS, smem, st.s>>>(A, S, n, shift, mask, base, status, ticket, flags);
+	}
+	st.launches += (nfull ? 1 : 0) + (partial ? 1 : 0);
+	B3M_CUDA(cudaGetLastError());
 }
 
 struct RadixStats {
@@ -329,13 +384,11 @@ void radix_sort_bits(Stream & st, RadixRec<NA> & cur, RadixRec<NA> & alt, int ka
 			A.aux_in = cur.aux; A.aux_out = alt.aux;
 			uint64_t const pbytes = n * (8ull * NA + (cur.aux ? 2ull : 0ull));
 			if (cur.aux)
-				B3M_LAUNCH_T(st, NA == 2 ? "radix_onesweep<2+aux>" : "radix_onesweep<+aux>", pbytes,
-				           (k_radix_onesweep<NA, true, false>), ntiles, RADIX_THREADS, 0, A, RadixTextSrc(), n, lo + 8 * d,
-				           (d == ndig - 1 ? lastmask : 255u), (const uint32_t *)(base.get() + d * RADIX_BINS), status.get(), ticket + d);
+				radix_launch_pass<NA, true, false>(st, NA == 2 ? "radix_onesweep<2+aux>" : "radix_onesweep<+aux>", pbytes, A, RadixTextSrc(), n, lo + 8 * d,
+				                                   (d == ndig - 1 ? lastmask : 255u), (const uint32_t *)(base.get() + d * RADIX_BINS), status.get(), ticket + d);
 			else
-				B3M_LAUNCH_T(st, NA == 2 ? "radix_onesweep<2>" : (NA == 3 ? "radix_onesweep<3>" : "radix_onesweep"), pbytes,
-				           (k_radix_onesweep<NA, false, false>), ntiles, RADIX_THREADS, 0, A, RadixTextSrc(), n, lo + 8 * d,
-				           (d == ndig - 1 ? lastmask : 255u), (const uint32_t *)(base.get() + d * RADIX_BINS), status.get(), ticket + d);
+				radix_launch_pass<NA, false, false>(st, NA == 2 ? "radix_onesweep<2>" : (NA == 3 ? "radix_onesweep<3>" : "radix_onesweep"), pbytes, A, RadixTextSrc(), n, lo + 8 * d,
+				                                    (d == ndig - 1 ? lastmask : 255u), (const uint32_t *)(base.get() + d * RADIX_BINS), status.get(), ticket + d);
 			RadixRec<NA> t = cur; cur = alt; alt = t;
 			if (rs) { rs->passes++; rs->bytes += pbytes; }
 		}
@@ -421,11 +474,9 @@ inline void radix_sort_suffix_keys(Stream & st, TextView const & v, uint64_t nsh
 		A.aux_in = cur.aux; A.aux_out = alt.aux;
 		uint64_t const pbytes = d ? n * 18ull : n * 9ull + n / 4;
 		if (d == 0)
-			B3M_LAUNCH_T(st, "radix_onesweep<text>", pbytes, (k_radix_onesweep<2, true, true>), ntiles, RADIX_THREADS, 0, A, S, n, 0, 255u,
-			           (const uint32_t *)base.get(), status.get(), ticket);
+			radix_launch_pass<2, true, true>(st, "radix_onesweep<text>", pbytes, A, S, n, 0, 255u, (const uint32_t *)base.get(), status.get(), ticket);
 		else
-			B3M_LAUNCH_T(st, "radix_onesweep<2+aux>", pbytes, (k_radix_onesweep<2, true, false>), ntiles, RADIX_THREADS, 0, A, S, n, 8 * d, 255u,
-			           (const uint32_t *)(base.get() + d * RADIX_BINS), status.get(), ticket + d);
+			radix_launch_pass<2, true, false>(st, "radix_onesweep<2+aux>", pbytes, A, S, n, 8 * d, 255u, (const uint32_t *)(base.get() + d * RADIX_BINS), status.get(), ticket + d);
 		RadixRec<2> t = cur; cur = alt; alt = t;
 		if (rs) { rs->passes++; rs->bytes += pbytes; }
 	}
