@@ -185,13 +185,14 @@ def run_ours(args):
     stream = torch.cuda.Stream()
     eng = Engine(local, stream.cuda_stream)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    state = {"drv": None}
+    state = {"drv": None, "strategy": "single"}
 
     def build():
         if world == 1:
             eng.build(numblocks=args.numblocks, **params)
         else:
-            state["drv"], _ = multigpu.build_distributed(eng, local_blocks=args.numblocks, driver=state["drv"], **params)
+            state["drv"], res = multigpu.build_distributed(eng, local_blocks=args.numblocks, driver=state["drv"], strategy=args.strategy, **params)
+            state["strategy"] = res["strategy"]
 
     def step_device():
         eng.load_device(dev_in.data_ptr(), dev_in.numel(), itype)
@@ -237,9 +238,13 @@ def run_ours(args):
         # ---- e2e: pinned host input -> results in pinned host buffers (rank 0), wall clock ----
         n = info["n"]
         out = None
+        # pacterm builds deliver what the reference pipeline ends in (bwtb3m -> bwtb3mtobwa): BWA's packed
+        # BWT words + sampled SA (+ ISA, anchors); other inputs deliver the BWT as one byte per symbol
+        as_bwa = itype == "pacterm" and not params["bwtonly"]
+        nwords = (n - 1 + 15) >> 4
         if rank == 0:
             out = {
-                "bwt": torch.empty(n, dtype=torch.uint8).pin_memory(),
+                "bwt": (torch.empty(nwords, dtype=torch.int32) if as_bwa else torch.empty(n, dtype=torch.uint8)).pin_memory(),
                 "preisa": torch.empty(2 * info["npreisa"], dtype=torch.int64).pin_memory(),
                 "sa": torch.empty(max(info["nsa"], 1), dtype=torch.int64).pin_memory(),
                 "isa": torch.empty(max(info["nisa"], 1), dtype=torch.int64).pin_memory(),
@@ -249,7 +254,9 @@ def run_ours(args):
             eng.load_host_ptr(host_in.data_ptr(), host_in.numel(), itype)
             build()
             if rank == 0:
-                eng.fetch_ptrs(out["bwt"].data_ptr(), out["preisa"].data_ptr(),
+                if as_bwa:
+                    eng.fetch_bwa(out_ptr=out["bwt"].data_ptr())
+                eng.fetch_ptrs(0 if as_bwa else out["bwt"].data_ptr(), out["preisa"].data_ptr(),
                                out["sa"].data_ptr() if info["nsa"] else 0, out["isa"].data_ptr() if info["nisa"] else 0)
 
         step_e2e()
@@ -265,7 +272,7 @@ def run_ours(args):
             dist.all_reduce(mx, op=dist.ReduceOp.MAX)
             e2e_s = float(mx[0].item())
         h2d = int(host_in.numel()) * world
-        d2h = int(n + 16 * info["npreisa"] + 8 * info["nsa"] + 8 * info["nisa"])
+        d2h = int((4 * nwords if as_bwa else n) + 16 * info["npreisa"] + 8 * info["nsa"] + 8 * info["nisa"])
 
         # ---- roofline of the dominant kernel: per-kernel CUDA events on separate profiled steps ----
         eng.set_profile(True)
@@ -322,10 +329,13 @@ def run_ours(args):
         "warmup": warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": config_dict(args, nsym, itype, {"numblocks": info["numblocks"], "preisarate": info["preisarate"],
-                                                  "parallelism": "text replicated, %d block ranges, merge tree over NCCL" % world if world > 1 else "single GPU"}),
+                                                  "parallelism": ("single GPU" if world == 1 else
+                                                                  "text replicated, %d suffix key ranges, slices sum-reduced to rank 0 over NCCL" % world if state["strategy"] == "shard" else
+                                                                  "text replicated, %d block ranges, merge tree over NCCL" % world)}),
         "clocks": sampler.summary(),
         "e2e": {"value": nsym * e2e_steps / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps},
+                "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps,
+                "outputs": ("BWA packed BWT words (b3m_engine_fetch_bwa)" if as_bwa else "BWT bytes") + " + anchors + sampled SA + sampled ISA"},
         "gpu_launches": launches,
         "roofline": roof,
         "cpu_baseline": cpu,
@@ -349,6 +359,7 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only; invalid as a bench value)")
     ap.add_argument("--numblocks", type=int, default=1)
+    ap.add_argument("--strategy", default="auto", choices=["auto", "shard", "merge"], help="multi-GPU decomposition (bwtb3m_b200.multigpu)")
     ap.add_argument("--cpu-sample", type=int, default=256_000_000, help="symbols of the workload the cpu_baseline leg processes")
     ap.add_argument("--ref-sample", type=int, default=32_000_000, help="symbols per step of --impl reference")
     ap.add_argument("--no-cpu", action="store_true")

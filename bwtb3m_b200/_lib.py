@@ -60,7 +60,8 @@ EXPORTS = [
     "b3m_bwt_length", "b3m_bwt_decode", "b3m_bwt_encode_host",
     "b3m_engine_blk_begin", "b3m_engine_blk_build_range", "b3m_engine_blk_chains", "b3m_engine_blk_zranks", "b3m_engine_blk_gap",
     "b3m_engine_blk_merge", "b3m_engine_blk_merge_samples", "b3m_engine_blk_finish",
-    "b3m_engine_default_preisarate",
+    "b3m_engine_default_preisarate", "b3m_engine_fetch_bwa",
+    "b3m_engine_shard_build", "b3m_engine_shard_finish",
 ]
 
 _lib = None
@@ -94,6 +95,9 @@ def lib():
     L.b3m_engine_write_bwt.argtypes = [vp, C.c_char_p]
     L.b3m_engine_fetch_runs.argtypes = [vp, vp, vp, u64, u64p]
     L.b3m_engine_ssa_from_bwt.argtypes = [vp, vp, u64, vp, u64, u64, u64]
+    L.b3m_engine_fetch_bwa.argtypes = [vp, vp, u64, u64p, u64p, u64p]
+    L.b3m_engine_shard_build.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(BuildParams), vp, vp, vp, vp, vp, u64p]
+    L.b3m_engine_shard_finish.argtypes = [vp, vp, vp, vp, vp, vp, C.c_uint32]
     L.b3m_bwt_length.argtypes = [C.c_char_p, u64p, C.c_char_p, C.c_size_t]
     L.b3m_bwt_decode.argtypes = [C.c_char_p, vp, u64, u64, C.c_char_p, C.c_size_t]
     L.b3m_bwt_encode_host.argtypes = [C.c_char_p, vp, u64, C.c_char_p, C.c_size_t]

@@ -45,6 +45,7 @@ void Engine::load(const void * input, uint64_t nbytes, int itype, bool on_device
 	B3M_REQUIRE(itype >= 0 && itype <= 3, "unknown input type");
 	reset_results();
 	codes.release(); packed.release(); raw.release(); d_hist.release(); d_special.release();
+	kr_plan = KeyRangePlan();
 	inputtype = itype;
 	// one slab for the whole build: text + BWT + suffix/rank arrays + sort buffers (HBM layout)
 	{
@@ -281,6 +282,82 @@ void Engine::build(b3m_build_params const & p) {
 	ms_dict = pt.ms(2, 3);
 	ms_walk = pt.ms(3, 4);
 	ms_total = pt.ms(0, 4);
+	have_results = true;
+}
+
+// ------------------------------------------------------------------------------------------
+// Multi-GPU, suffix-range sharding: every rank holds the whole text and sorts ONE key range of
+// the suffixes; slices of BWT / anchors / samples land in caller-owned, zero-initialised buffers
+// at their global places, so that the ranks' buffers combine by a sum (bwtb3m_b200/multigpu.py).
+// ------------------------------------------------------------------------------------------
+void Engine::kr_build_part(uint32_t part, uint32_t nparts, b3m_build_params const & p, void * d_bwt, void * d_prerank, void * d_sa, void * d_isa,
+                           void * d_special, uint64_t * unresolved) {
+	B3M_CUDA(cudaSetDevice(device));
+	B3M_REQUIRE(loaded, "no input loaded");
+	B3M_REQUIRE(d_bwt && d_prerank && d_special && unresolved, "null argument");
+	B3M_REQUIRE(part < nparts, "bad part index");
+	auto pow2 = [](uint64_t v) { return v && !(v & (v - 1)); };
+	B3M_REQUIRE(pow2(p.sasamplingrate) && pow2(p.isasamplingrate), "sampling rates must be powers of two");
+	B3M_REQUIRE(p.bwtonly || (d_sa && d_isa), "null sample buffers");
+	reset_results();
+	params = p;
+	prerate = p.preisarate ? p.preisarate : (p.bwtonly ? 64 : choose_preisarate(T.n, st.sms));
+	B3M_REQUIRE(pow2(prerate), "preisarate must be a power of two");
+	npre = div_up(T.n, prerate);
+	nsa = p.bwtonly ? 0 : div_up(T.n, p.sasamplingrate);
+	nisa = p.bwtonly ? 0 : div_up(T.n, p.isasamplingrate);
+	numblocks = nparts;
+	sortstats = SortStats(); walkstats = WalkStats();
+	gap_lf_steps = gap_chains = merge_bytes = extract_bytes = 0; max_lcpnext = large_lcp_blocks = 0;
+	ms_sort = ms_extract = ms_dict = ms_gap = ms_merge = ms_walk = ms_total = 0;
+	PhaseTimer pt(st);
+	pt.mark();
+	int const circular = T.has_term ? 0 : 1;
+	if (kr_plan.nparts != nparts) k2_keyrange_plan(st, T, circular, nparts, kr_plan);
+	FusedOut fo;
+	fo.bwt = (uint8_t *)d_bwt; fo.shift = T.has_term ? 1 : 0; fo.has_term = T.has_term; fo.special = (uint32_t *)d_special;
+	fo.prerank = (uint32_t *)d_prerank; fo.prelog = ceil_log2_u64(prerate);
+	if (!p.bwtonly) {
+		fo.sa_s = (unsigned long long *)d_sa; fo.salog = ceil_log2_u64(p.sasamplingrate);
+		fo.isa_s = (unsigned long long *)d_isa; fo.isalog = ceil_log2_u64(p.isasamplingrate);
+	}
+	*unresolved = k2_sort_keyrange(st, T, circular, kr_plan, part, fo, &sortstats);
+	if (part == 0 && T.has_term) {
+		// rank 0 is the terminator suffix (text position ntext): its predecessor is the last base; its
+		// anchor / ISA entries are rank 0 = the buffers' initial value
+		B3M_CUDA(cudaMemcpyAsync(d_bwt, T.codes + T.ntext - 1, 1, cudaMemcpyDeviceToDevice, st.s));
+		uint64_t const pos = T.ntext;
+		if (!p.bwtonly) B3M_CUDA(cudaMemcpyAsync(d_sa, &pos, 8, cudaMemcpyHostToDevice, st.s));
+	}
+	pt.mark();
+	B3M_CUDA(cudaStreamSynchronize(st.s));
+	ms_sort = pt.ms(0, 1); ms_total = ms_sort;
+	extract_bytes = (kr_plan.base[part + 1] - kr_plan.base[part]) * 6;
+}
+
+void Engine::kr_finish(const void * d_bwt, const void * d_prerank, const void * d_sa, const void * d_isa, const void * d_special, uint32_t nparts) {
+	B3M_CUDA(cudaSetDevice(device));
+	B3M_REQUIRE(loaded && npre, "kr_build_part was not called");
+	PhaseTimer pt(st);
+	pt.mark();
+	bwt.alloc(st, T.n + 16);
+	B3M_CUDA(cudaMemcpyAsync(bwt.get(), d_bwt, T.n, cudaMemcpyDeviceToDevice, st.s));
+	prerank.alloc(st, npre);
+	B3M_CUDA(cudaMemcpyAsync(prerank.get(), d_prerank, 4 * npre, cudaMemcpyDeviceToDevice, st.s));
+	if (nsa) { sa.alloc(st, nsa); B3M_CUDA(cudaMemcpyAsync(sa.get(), d_sa, 8 * nsa, cudaMemcpyDeviceToDevice, st.s)); }
+	if (nisa) { isa.alloc(st, nisa); B3M_CUDA(cudaMemcpyAsync(isa.get(), d_isa, 8 * nisa, cudaMemcpyDeviceToDevice, st.s)); }
+	uint32_t exc_pos = 0xffffffffu;
+	if (T.has_term) {
+		B3M_CUDA(cudaMemcpyAsync(pinned, d_special, 16, cudaMemcpyDeviceToHost, st.s));
+		B3M_CUDA(cudaStreamSynchronize(st.s));
+		exc_pos = ((uint32_t *)pinned)[0];
+	}
+	root_exc_pos = exc_pos;
+	numblocks = nparts;
+	make_dict(exc_pos, 0, 0);
+	pt.mark();
+	B3M_CUDA(cudaStreamSynchronize(st.s));
+	ms_dict = pt.ms(0, 1);
 	have_results = true;
 }
 
@@ -545,6 +622,17 @@ int b3m_engine_write_bwt(b3m_engine * h, const char * bwtfn) {
 }
 int b3m_engine_fetch_runs(b3m_engine * h, uint8_t * syms, uint64_t * lens, uint64_t cap, uint64_t * nruns) {
 	B3M_GUARD(h, h->e->fetch_runs(syms, lens, cap, nruns));
+}
+int b3m_engine_shard_build(b3m_engine * h, uint32_t part, uint32_t nparts, const b3m_build_params * p, void * d_bwt, void * d_prerank,
+                           void * d_sa, void * d_isa, void * d_special, uint64_t * unresolved) {
+	B3M_GUARD(h, { if (!p) throw b3m::Error("null params"); h->e->kr_build_part(part, nparts, *p, d_bwt, d_prerank, d_sa, d_isa, d_special, unresolved); });
+}
+int b3m_engine_shard_finish(b3m_engine * h, const void * d_bwt, const void * d_prerank, const void * d_sa, const void * d_isa, const void * d_special,
+                            uint32_t nparts) {
+	B3M_GUARD(h, h->e->kr_finish(d_bwt, d_prerank, d_sa, d_isa, d_special, nparts));
+}
+int b3m_engine_fetch_bwa(b3m_engine * h, uint32_t * bwt_words, uint64_t cap_words, uint64_t * primary, uint64_t * L2, uint64_t * seq_len) {
+	B3M_GUARD(h, h->e->fetch_bwa(bwt_words, cap_words, primary, L2, seq_len));
 }
 int b3m_engine_ssa_from_bwt(b3m_engine * h, const uint8_t * bwt, uint64_t n, const uint64_t * pairs, uint64_t npairs, uint64_t sarate, uint64_t isarate) {
 	B3M_GUARD(h, { if (!bwt || !pairs) throw b3m::Error("null argument"); h->e->ssa_from_bwt(bwt, n, pairs, npairs, sarate, isarate); });

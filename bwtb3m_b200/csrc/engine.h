@@ -107,12 +107,18 @@ struct Engine {
 	void merge_run(const uint8_t * LA, uint64_t na, uint32_t termA, uint8_t * LR, uint64_t nr, uint32_t termR, uint64_t a1, uint32_t * G,
 	               uint8_t * LM, uint32_t * termM);
 	void merge_samples(uint64_t a0, uint64_t a1, uint64_t r1, uint32_t * pre, const uint32_t * Sincl, const uint32_t * rs);
+	// multi-GPU, suffix-range sharding (sufsort.cu): one key range per engine, caller-owned output buffers
+	KeyRangePlan kr_plan;
+	void kr_build_part(uint32_t part, uint32_t nparts, b3m_build_params const & p, void * d_bwt, void * d_prerank, void * d_sa, void * d_isa,
+	                   void * d_special, uint64_t * unresolved);
+	void kr_finish(const void * d_bwt, const void * d_prerank, const void * d_sa, const void * d_isa, const void * d_special, uint32_t nparts);
 	// K8 / output side
 	uint64_t rl_bytes = 0, rl_nruns = 0;
 	void symbols_device(DevBuf<uint8_t> & out);
 	uint64_t rl_runs(const uint8_t * s, DevBuf<uint32_t> & start);
 	void write_bwt(const char * fn);
 	void fetch_runs(uint8_t * h_sym, uint64_t * h_len, uint64_t cap, uint64_t * nruns_out);
+	void fetch_bwa(uint32_t * h_words, uint64_t cap, uint64_t * primary, uint64_t * L2, uint64_t * seq_len_out);
 	// sampled SA/ISA from an existing BWT and (rank,pos) anchors (bwtcomputessa path)
 	void ssa_from_bwt(const uint8_t * h_bwt, uint64_t n, const uint64_t * h_pairs, uint64_t npairs, uint64_t sarate, uint64_t isarate);
 	void make_dict(uint32_t exc_pos, uint32_t exc_code, uint32_t exc_lf);

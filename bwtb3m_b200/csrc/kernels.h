@@ -73,6 +73,18 @@ struct FusedOut {
 void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W, int circular, int text_wraps,
                     DevBuf<uint32_t> & sa, uint32_t * rank, SortStats * stats, const FusedOut * fo);
 
+// Suffix-range sharding (multi-GPU, sufsort.cu): part p holds the suffixes whose first-key bin lies
+// in [bin_lo[p], bin_lo[p+1]); base[p] = number of suffixes of the window in smaller bins.
+struct KeyRangePlan {
+	uint32_t nparts = 0;
+	std::vector<uint32_t> bin_lo;
+	std::vector<uint64_t> base;
+};
+void k2_keyrange_plan(Stream & st, DevText const & T, int circular, uint32_t nparts, KeyRangePlan & plan);
+// sorts the suffixes of one part of the whole text and emits their fused outputs at global ranks
+// fo.shift + base[part] + k; returns the number of suffixes left unresolved (0: the slice is final)
+uint64_t k2_sort_keyrange(Stream & st, DevText const & T, int circular, KeyRangePlan const & plan, uint32_t part, FusedOut const & fo, SortStats * stats);
+
 // ---- K3 ---------------------------------------------------------------------------------
 // bwt[k + shift] = code preceding suffix sa[k] (text position wstart+sa[k]); the suffix at text
 // position 0 of a terminated text gets code 0 and its output index is written to *d_termrank.

@@ -155,6 +155,50 @@ void Engine::symbols_device(DevBuf<uint8_t> & out) {
 	B3M_CUDA(cudaStreamSynchronize(st.s)); // pinned is reused by the caller
 }
 
+// ------------------------------------------------------------------------------------------
+// K9: BWA's packed BWT straight from the device BWT (engine half of MausFmToBwaConversion::rewrite,
+// /root/reference/src/bwtb3mtobwa.cpp:29; layout: bwa's bwt_dump_bwt): 16 symbols per
+// uint32, symbol k at bits (15-(k&15))*2, the terminator row (primary) removed, so rows behind it
+// move up by one.  pacterm codes 0..3 are BWA's A,C,G,T.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_pack_bwa(const uint8_t * __restrict__ bwt, uint64_t seq_len, uint64_t primary, uint32_t * __restrict__ words, uint64_t nwords) {
+	uint64_t const w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (w >= nwords) return;
+	uint64_t const k0 = w << 4;
+	uint32_t acc = 0;
+	if (k0 + 16 <= seq_len && (k0 + 16 <= primary || k0 >= primary)) {
+		// 16 rows on one side of the primary: 16 consecutive bytes (unaligned when shifted)
+		const uint8_t * src = bwt + k0 + (k0 >= primary ? 1 : 0);
+		#pragma unroll
+		for (int j = 0; j < 16; ++j) acc = (acc << 2) | (uint32_t)(src[j] & 3u);
+	} else {
+		for (uint64_t k = k0; k < k0 + 16; ++k) {
+			uint32_t c = 0;
+			if (k < seq_len) c = bwt[k < primary ? k : k + 1] & 3u;
+			acc = (acc << 2) | c;
+		}
+	}
+	words[w] = acc;
+}
+
+void Engine::fetch_bwa(uint32_t * h_words, uint64_t cap, uint64_t * primary, uint64_t * L2, uint64_t * seq_len_out) {
+	B3M_CUDA(cudaSetDevice(device));
+	B3M_REQUIRE(have_results && !ssa_only, "no BWT to export");
+	B3M_REQUIRE(T.has_term && T.sigma <= 4, "the BWA export needs a pacterm build (bases A,C,G,T and one terminator)");
+	uint64_t const seq_len = T.n - 1;
+	uint64_t const nwords = (seq_len + 15) >> 4;
+	if (seq_len_out) *seq_len_out = seq_len;
+	if (primary) *primary = root_exc_pos;
+	if (L2) { L2[0] = 0; for (int c = 0; c < 4; ++c) L2[c + 1] = L2[c] + codehist[c]; }
+	if (!h_words) return;
+	B3M_REQUIRE(cap >= nwords, "BWA word buffer too small");
+	DevBuf<uint32_t> words(st, nwords);
+	B3M_LAUNCH_T(st, "pack_bwa", T.n + 4 * nwords, k_pack_bwa, (unsigned)div_up(nwords, 256), 256, 0, (const uint8_t *)bwt.get(), seq_len, (uint64_t)root_exc_pos, words.get(), nwords);
+	B3M_CUDA(cudaMemcpyAsync(h_words, words.get(), 4 * nwords, cudaMemcpyDeviceToHost, st.s));
+	B3M_CUDA(cudaStreamSynchronize(st.s));
+}
+
 // runs of the BWT: start positions (device) and their number
 uint64_t Engine::rl_runs(const uint8_t * s, DevBuf<uint32_t> & start) {
 	uint64_t const n = T.n;

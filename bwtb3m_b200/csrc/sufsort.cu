@@ -117,12 +117,13 @@ __device__ __forceinline__ void rs_second_key(TextView const & v, unsigned bits,
 template <bool FUSED>
 __global__ void __launch_bounds__(RS_THREADS)
 k_resolve(TextView v, unsigned bits, unsigned k0, int lin, const uint32_t * __restrict__ key, const uint32_t * __restrict__ idx,
-          const uint8_t * __restrict__ aux, uint32_t * __restrict__ sa_out, uint8_t * __restrict__ hflag, FusedOut fo, unsigned long long * __restrict__ counters) {
+          const uint8_t * __restrict__ aux, uint64_t nrec, uint32_t * __restrict__ sa_out, uint8_t * __restrict__ hflag, FusedOut fo, unsigned long long * __restrict__ counters) {
 	__shared__ uint32_t s_idx[RS_REG];
 	__shared__ uint32_t s_hb[RS_ROWS + 2];        // head flags of row q in s_hb[q + 1]
 	__shared__ uint8_t s_aux[RS_REG];
 	__shared__ uint32_t s_cnt[3];
-	int64_t const W = (int64_t)v.W;
+	int64_t const W = (int64_t)v.W;      // window length: decides which suffixes reach the sentinel
+	int64_t const NR = (int64_t)nrec;    // records to resolve (all W suffixes, or the ones of one key range)
 	int64_t const kbase = (int64_t)blockIdx.x * RS_TILE - RS_EXT; // region index x <-> global place kbase + x
 	unsigned const w = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	unsigned const nx = 8u / bits - 1u;          // symbols carried in the aux byte behind the key
@@ -135,16 +136,16 @@ k_resolve(TextView v, unsigned bits, unsigned k0, int lin, const uint32_t * __re
 	for (int q = (int)w; q < RS_ROWS; q += RS_WARPS) {
 		int const x = q * 32 + (int)lane;
 		int64_t const k = kbase + x;
-		bool const valid = k >= 0 && k < W;
+		bool const valid = k >= 0 && k < NR;
 		uint32_t const mk = valid ? key[k] : 0u;
 		uint32_t const mi = valid ? idx[k] : 0u;
 		s_idx[x] = mi;
 		s_aux[x] = valid ? aux[k] : (uint8_t)0;
 		// the record before this one: the lane below, or one extra load for lane 0
 		uint32_t pk = __shfl_up_sync(0xffffffffu, mk, 1), pi = __shfl_up_sync(0xffffffffu, mi, 1);
-		if (lane == 0 && k > 0 && k <= W) { pk = key[k - 1]; pi = idx[k - 1]; }
+		if (lane == 0 && k > 0 && k <= NR) { pk = key[k - 1]; pi = idx[k - 1]; }
 		bool head = true;
-		if (k > 0 && k < W) {
+		if (k > 0 && k < NR) {
 			head = mk != pk;
 			if (lin) head = head || ((uint64_t)mi + k0 > (uint64_t)W) || ((uint64_t)pi + k0 > (uint64_t)W);
 		}
@@ -157,7 +158,7 @@ k_resolve(TextView v, unsigned bits, unsigned k0, int lin, const uint32_t * __re
 	#pragma unroll 1
 	for (int q = 1 + (int)w; q < RS_ROWS; q += RS_WARPS) {
 		int const x = q * 32 + (int)lane;
-		if (kbase + x >= W) continue;
+		if (kbase + x >= NR) continue;
 		// run start: highest head bit at or below x inside the 64 records that end with this row
 		unsigned long long const hbw = ((unsigned long long)s_hb[q + 1] << 32) | s_hb[q];
 		unsigned long long const below = hbw & ((2ull << (32 + lane)) - 1ull);
@@ -240,6 +241,150 @@ static uint32_t fetch_u32(Stream & st, const uint32_t * d) {
 	return h;
 }
 
+// ------------------------------------------------------------------------------------------
+// Suffix-range sharding (multi-GPU): the suffixes are split by the top 12 bits of their first key
+// into `nparts` contiguous key ranges of about equal size; one engine sorts one range and emits
+// its slice of the BWT / anchors / samples with the global rank offset of the range.  The text is
+// replicated, so every rank derives the same plan without communication, and no gap array or
+// merge is needed.  Only texts whose ties all resolve in k_resolve take this path (the caller
+// falls back to the block merge tree otherwise).
+// ------------------------------------------------------------------------------------------
+constexpr int KR_BINS = 4096;
+constexpr int KR_TILE = 2048; // text positions per CTA of the filter kernels
+
+__global__ void __launch_bounds__(256)
+k_keyrange_hist(RadixTextSrc S, unsigned long long * __restrict__ ghist /* [KR_BINS] */) {
+	__shared__ uint32_t sh[KR_BINS];
+	for (int i = threadIdx.x; i < KR_BINS; i += blockDim.x) sh[i] = 0;
+	__syncthreads();
+	for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < S.v.W; t += (uint64_t)gridDim.x * blockDim.x) {
+		uint32_t key, idx, aux;
+		radix_text_record(S, t, key, idx, aux);
+		atomicAdd(&sh[key >> 20], 1u);
+	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < KR_BINS; i += blockDim.x) if (sh[i]) atomicAdd(&ghist[i], (unsigned long long)sh[i]);
+}
+
+// records whose key bin lies in [blo, bhi), in input order: counts per tile (WRITE == false), then
+// the records themselves at the scanned tile offsets (WRITE == true)
+template <bool WRITE>
+__global__ void __launch_bounds__(256)
+k_keyrange_filter(RadixTextSrc S, uint32_t blo, uint32_t bhi, uint32_t * __restrict__ tilecount, const uint32_t * __restrict__ tileoff,
+                  uint32_t * __restrict__ okey, uint32_t * __restrict__ oidx, uint8_t * __restrict__ oaux) {
+	__shared__ uint32_t wtot[8];
+	unsigned const w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	uint64_t const t0 = (uint64_t)blockIdx.x * KR_TILE + (uint64_t)w * 256; // a warp owns 256 consecutive records
+	uint32_t key[8], idx[8], aux[8];
+	uint32_t rowbase[8];
+	uint32_t mine = 0, total = 0;
+	#pragma unroll
+	for (int j = 0; j < 8; ++j) {
+		uint64_t const t = t0 + j * 32 + lane;
+		bool in = false;
+		key[j] = idx[j] = aux[j] = 0;
+		if (t < S.v.W) {
+			radix_text_record(S, t, key[j], idx[j], aux[j]);
+			uint32_t const b = key[j] >> 20;
+			in = b >= blo && b < bhi;
+		}
+		unsigned const m = __ballot_sync(0xffffffffu, in);
+		rowbase[j] = total + __popc(m & lanemask_lt());
+		if (in) mine |= 1u << j;
+		total += __popc(m);
+	}
+	if (lane == 0) wtot[w] = total;
+	__syncthreads();
+	if (!WRITE) {
+		if (threadIdx.x == 0) { uint32_t s = 0; for (int i = 0; i < 8; ++i) s += wtot[i]; tilecount[blockIdx.x] = s; }
+		return;
+	}
+	uint32_t off = tileoff[blockIdx.x];
+	for (unsigned i = 0; i < w; ++i) off += wtot[i];
+	#pragma unroll
+	for (int j = 0; j < 8; ++j)
+		if ((mine >> j) & 1u) { uint32_t const o = off + rowbase[j]; okey[o] = key[j]; oidx[o] = idx[j]; oaux[o] = (uint8_t)aux[j]; }
+}
+
+void k2_keyrange_plan(Stream & st, DevText const & T, int circular, uint32_t nparts, KeyRangePlan & plan) {
+	B3M_REQUIRE(nparts >= 1 && nparts <= KR_BINS, "bad number of key ranges");
+	unsigned const bits = T.keybits, k0 = 32 / bits;
+	uint64_t const W = T.ntext;
+	uint64_t const nshort = circular ? 0 : (W < (uint64_t)(k0 - 1) ? W : (uint64_t)(k0 - 1));
+	TextView v{T.codes, bits == 2 ? T.packed : nullptr, T.ntext, 0, W, circular, 0, T.has_term};
+	RadixTextSrc S{v, nshort, bits, k0};
+	DevBuf<unsigned long long> gh(st, KR_BINS);
+	B3M_CUDA(cudaMemsetAsync(gh.get(), 0, KR_BINS * 8, st.s));
+	uint64_t const want = div_up(W, 256 * 32);
+	unsigned const grid = (unsigned)(want < (uint64_t)st.sms * 8 ? (want ? want : 1) : (uint64_t)st.sms * 8);
+	B3M_LAUNCH_T(st, "keyrange_hist", W / 4, k_keyrange_hist, grid, 256, 0, S, gh.get());
+	std::vector<unsigned long long> h(KR_BINS);
+	B3M_CUDA(cudaMemcpyAsync(h.data(), gh.get(), KR_BINS * 8, cudaMemcpyDeviceToHost, st.s));
+	B3M_CUDA(cudaStreamSynchronize(st.s));
+	plan.nparts = nparts;
+	plan.bin_lo.assign(nparts + 1, KR_BINS);
+	plan.base.assign(nparts + 1, W);
+	plan.bin_lo[0] = 0; plan.base[0] = 0;
+	uint64_t acc = 0;
+	uint32_t p = 1;
+	for (uint32_t b = 0; b < KR_BINS && p < nparts; ++b) {
+		// part p starts at the first bin boundary at or past p/nparts of the suffixes
+		while (p < nparts && acc >= (W * p) / nparts) { plan.bin_lo[p] = b; plan.base[p] = acc; ++p; }
+		acc += h[b];
+	}
+}
+
+uint64_t k2_sort_keyrange(Stream & st, DevText const & T, int circular, KeyRangePlan const & plan, uint32_t part, FusedOut const & fo0, SortStats * stats) {
+	B3M_REQUIRE(part < plan.nparts, "bad key range index");
+	unsigned const bits = T.keybits, k0 = 32 / bits;
+	uint64_t const W = T.ntext;
+	uint64_t const nshort = circular ? 0 : (W < (uint64_t)(k0 - 1) ? W : (uint64_t)(k0 - 1));
+	TextView v{T.codes, bits == 2 ? T.packed : nullptr, T.ntext, 0, W, circular, 0, T.has_term};
+	RadixTextSrc S{v, nshort, bits, k0};
+	uint32_t const blo = plan.bin_lo[part], bhi = plan.bin_lo[part + 1];
+	uint64_t const m = plan.base[part + 1] - plan.base[part];
+	SortStats St;
+	St.rounds = 1;
+	if (m == 0) return 0;
+	// stable compaction of the range's records out of the text
+	uint32_t const ntiles = (uint32_t)div_up(W, KR_TILE);
+	DevBuf<uint32_t> tcount(st, ntiles);
+	B3M_LAUNCH_T(st, "keyrange_count", W / 4, (k_keyrange_filter<false>), ntiles, 256, 0, S, blo, bhi, tcount.get(), (const uint32_t *)nullptr,
+	             (uint32_t *)nullptr, (uint32_t *)nullptr, (uint8_t *)nullptr);
+	scan_exclusive_inplace<OpSum>(st, tcount.get(), ntiles);
+	DevBuf<uint32_t> key0(st, m), key1(st, m), idx0(st, m), idx1(st, m);
+	DevBuf<uint8_t> aux0(st, m), aux1(st, m);
+	B3M_LAUNCH_T(st, "keyrange_write", W / 4 + 9 * m, (k_keyrange_filter<true>), ntiles, 256, 0, S, blo, bhi, (uint32_t *)nullptr, (const uint32_t *)tcount.get(),
+	             key0.get(), idx0.get(), aux0.get());
+	St.other_bytes += W / 2 + 9 * m;
+	RadixRec<2> cur{{key0.get(), idx0.get()}, aux0.get()}, alt{{key1.get(), idx1.get()}, aux1.get()};
+	RadixStats rs;
+	radix_sort_bits<2>(st, cur, alt, 0, m, 0, 32, &rs);
+	St.radix_passes += rs.passes; St.radix_bytes += rs.bytes; St.active_sum += m;
+	DevBuf<unsigned long long> counters(st, 4 * RS_CSLOTS);
+	DevBuf<uint8_t> hflag(st, m);
+	B3M_CUDA(cudaMemsetAsync(counters.get(), 0, 32 * RS_CSLOTS, st.s));
+	FusedOut fo = fo0;
+	fo.shift = fo0.shift + plan.base[part];
+	uint64_t const rbytes = m * 15ull;
+	B3M_LAUNCH_T(st, "resolve_extract", rbytes, (k_resolve<true>), (unsigned)div_up(m, RS_TILE), RS_THREADS, 0, v, bits, k0, !circular, (const uint32_t *)cur.a[0],
+	             (const uint32_t *)cur.a[1], (const uint8_t *)cur.aux, m, alt.a[1], hflag.get(), fo, counters.get());
+	std::vector<unsigned long long> hcs(4 * RS_CSLOTS);
+	B3M_CUDA(cudaMemcpyAsync(hcs.data(), counters.get(), 32 * RS_CSLOTS, cudaMemcpyDeviceToHost, st.s));
+	B3M_CUDA(cudaStreamSynchronize(st.s));
+	unsigned long long hc[4] = {0, 0, 0, 0};
+	for (int q = 0; q < RS_CSLOTS; ++q) for (int c = 0; c < 3; ++c) hc[c] += hcs[4 * q + c];
+	St.tied0 = hc[1]; St.unresolved0 = hc[0];
+	St.other_bytes += rbytes + 32ull * hc[2];
+	if (stats) {
+		stats->rounds = stats->rounds > St.rounds ? stats->rounds : St.rounds;
+		stats->radix_passes += St.radix_passes; stats->radix_bytes += St.radix_bytes;
+		stats->active_sum += St.active_sum; stats->other_bytes += St.other_bytes;
+		stats->tied0 += St.tied0; stats->unresolved0 += St.unresolved0;
+	}
+	return hc[0];
+}
+
 void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W, int circular, int text_wraps,
                     DevBuf<uint32_t> & sa_buf, uint32_t * rank, SortStats * stats, const FusedOut * fo) {
 	if (W == 0) return;
@@ -283,9 +428,9 @@ void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W,
 		// key + index + aux in, suffix array + head flag (+ BWT code) out; second-key gathers are added below
 		uint64_t const rbytes = W * (9ull + 4ull + 1ull + (fo ? 1ull : 0ull));
 		if (fo) B3M_LAUNCH_T(st, "resolve_extract", rbytes, (k_resolve<true>), rgrid, RS_THREADS, 0, v, bits, k0, lin, (const uint32_t *)cur.a[0],
-		                     (const uint32_t *)cur.a[1], (const uint8_t *)cur.aux, alt.a[1], hflag.get(), *fo, counters.get());
+		                     (const uint32_t *)cur.a[1], (const uint8_t *)cur.aux, W, alt.a[1], hflag.get(), *fo, counters.get());
 		else B3M_LAUNCH_T(st, "resolve", rbytes, (k_resolve<false>), rgrid, RS_THREADS, 0, v, bits, k0, lin, (const uint32_t *)cur.a[0],
-		                  (const uint32_t *)cur.a[1], (const uint8_t *)cur.aux, alt.a[1], hflag.get(), FusedOut(), counters.get());
+		                  (const uint32_t *)cur.a[1], (const uint8_t *)cur.aux, W, alt.a[1], hflag.get(), FusedOut(), counters.get());
 		std::vector<unsigned long long> hcs(4 * RS_CSLOTS);
 		B3M_CUDA(cudaMemcpyAsync(hcs.data(), counters.get(), 32 * RS_CSLOTS, cudaMemcpyDeviceToHost, st.s));
 		B3M_CUDA(cudaStreamSynchronize(st.s));

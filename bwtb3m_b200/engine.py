@@ -107,6 +107,36 @@ class Engine:
         self._check(self._lib.b3m_engine_fetch_runs(self._h, _ptr(syms), _ptr(lens), n.value, C.byref(n)))
         return syms, lens
 
+    def shard_build(self, part, nparts, bwt_ptr, prerank_ptr, sa_ptr, isa_ptr, special_ptr, preisarate=0, sasamplingrate=32,
+                    isasamplingrate=262144, bwtonly=False):
+        """Suffix-range sharding: sorts key range `part` of `nparts` into caller-owned, zeroed device
+        buffers (global places); returns the number of suffixes this path left unresolved."""
+        p = BuildParams(nparts, preisarate, sasamplingrate, isasamplingrate, 1 if bwtonly else 0, 16384, 0)
+        un = C.c_uint64(0)
+        vp = lambda a: C.c_void_p(a) if a else None
+        self._check(self._lib.b3m_engine_shard_build(self._h, part, nparts, C.byref(p), vp(bwt_ptr), vp(prerank_ptr), vp(sa_ptr), vp(isa_ptr),
+                                                     vp(special_ptr), C.byref(un)))
+        return int(un.value)
+
+    def shard_finish(self, nparts, bwt_ptr, prerank_ptr, sa_ptr, isa_ptr, special_ptr):
+        vp = lambda a: C.c_void_p(a) if a else None
+        self._check(self._lib.b3m_engine_shard_finish(self._h, vp(bwt_ptr), vp(prerank_ptr), vp(sa_ptr), vp(isa_ptr), vp(special_ptr), nparts))
+
+    def fetch_bwa(self, out=None, out_ptr=0):
+        """BWA's packed BWT of the last pacterm build: (words uint32, primary, L2[5], seq_len).
+        `out` (numpy uint32) or `out_ptr` (address of a buffer of enough words) may receive the words."""
+        primary, seq_len = C.c_uint64(0), C.c_uint64(0)
+        l2 = (C.c_uint64 * 5)()
+        self._check(self._lib.b3m_engine_fetch_bwa(self._h, None, 0, C.byref(primary), l2, C.byref(seq_len)))
+        nw = (seq_len.value + 15) >> 4
+        if out_ptr:
+            self._check(self._lib.b3m_engine_fetch_bwa(self._h, C.c_void_p(out_ptr), nw, None, None, None))
+            words = None
+        else:
+            words = out if out is not None else np.empty(nw, dtype=np.uint32)
+            self._check(self._lib.b3m_engine_fetch_bwa(self._h, _ptr(words), words.size, None, None, None))
+        return words, int(primary.value), [int(x) for x in l2], int(seq_len.value)
+
     def ssa_from_bwt(self, bwt, preisa_pairs, sasamplingrate=32, isasamplingrate=32):
         """K4 + K7 on an existing BWT (bwtcomputessa path); returns (sa, isa) samples."""
         b = np.ascontiguousarray(bwt, dtype=np.uint8)

@@ -239,17 +239,85 @@ class EngineOps:
         return sa, isa
 
 
+class ShardBuffers:
+    """Zeroed device buffers one rank's suffix-range build writes at GLOBAL places (b3m_engine_shard_build)."""
+
+    def __init__(self, engine, preisarate, sasamplingrate, isasamplingrate, bwtonly, device=None):
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        n = engine.info()["n"]
+        self.prerate = preisarate or engine.default_preisarate(bwtonly)
+        self.n = n
+        z = lambda k, dt: torch.zeros(k, dtype=dt, device=self.device)
+        self.bwt = z(n + 16, torch.uint8)
+        self.prerank = z((n + self.prerate - 1) // self.prerate, torch.int32)
+        self.sa = None if bwtonly else z((n + sasamplingrate - 1) // sasamplingrate, torch.int64)
+        self.isa = None if bwtonly else z((n + isasamplingrate - 1) // isasamplingrate, torch.int64)
+        self.special = z(4, torch.int32)
+
+    def zero_(self):
+        for t in (self.bwt, self.prerank, self.sa, self.isa, self.special):
+            if t is not None:
+                t.zero_()
+
+    def ptrs(self):
+        p = lambda t: t.data_ptr() if t is not None else 0
+        return p(self.bwt), p(self.prerank), p(self.sa), p(self.isa), p(self.special)
+
+    def tensors(self):
+        return [t for t in (self.bwt, self.prerank, self.sa, self.isa, self.special) if t is not None]
+
+
+def build_sharded(engine, preisarate=0, sasamplingrate=32, isasamplingrate=262144, bwtonly=False, buffers=None, rank=None, world=None):
+    """Suffix-range sharding: rank r sorts key range r of the replicated
+    text; the slices combine by one sum-reduce to rank 0, whose engine then holds the complete results.
+    Returns (ok, buffers): ok is False when some rank met repeats this path does not sort -- the
+    caller then runs the block merge tree (build_distributed(..., strategy="merge"))."""
+    rank = dist.get_rank() if rank is None else rank
+    world = dist.get_world_size() if world is None else world
+    buf = buffers or ShardBuffers(engine, preisarate, sasamplingrate, isasamplingrate, bwtonly)
+    if buffers is not None:
+        buf.zero_()
+    unres = engine.shard_build(rank, world, *buf.ptrs(), preisarate=buf.prerate, sasamplingrate=sasamplingrate,
+                               isasamplingrate=isasamplingrate, bwtonly=bwtonly)
+    flag = torch.tensor([unres], dtype=torch.int64, device=buf.device)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.SUM)
+    if int(flag.item()) != 0:
+        return False, buf
+    if world > 1:
+        for t in buf.tensors():  # every entry is written by exactly one rank, the others hold 0
+            dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        engine.shard_finish(world, *buf.ptrs())
+    return True, buf
+
+
 def build_distributed(engine, local_blocks=1, preisarate=0, sasamplingrate=32, isasamplingrate=262144, bwtonly=False,
-                      largelcpthres=16384, driver=None):
+                      largelcpthres=16384, driver=None, strategy="auto"):
     """Every rank has loaded the same text into `engine`; after the call rank 0's engine holds the
-    complete results (fetch / write_bwt as after a single-GPU build)."""
+    complete results (fetch / write_bwt as after a single-GPU build).
+    strategy: "shard" = suffix-range sharding only (raises if the text needs the general path),
+    "merge" = the reference's block merge tree over NCCL, "auto" = shard, then merge if needed.
+    `driver` caches the process groups / buffers between calls: pass back the first return value."""
+    state = driver if isinstance(driver, dict) else {"merge": driver, "shard": None}
+    if strategy in ("auto", "shard"):
+        with torch.cuda.stream(torch.cuda.ExternalStream(engine.stream_ptr)) if engine.stream_ptr else _null():
+            ok, state["shard"] = build_sharded(engine, preisarate, sasamplingrate, isasamplingrate, bwtonly, buffers=state["shard"])
+            torch.cuda.current_stream().synchronize()
+        if ok:
+            return state, {"strategy": "shard"}
+        if strategy == "shard":
+            raise RuntimeError("suffix-range sharding left suffixes unresolved; use strategy='merge'")
     ops = EngineOps(engine, preisarate, largelcpthres)
+    driver = state["merge"]
     drv = driver or DistBuild(ops)
     drv.ops = ops
     with torch.cuda.stream(torch.cuda.ExternalStream(engine.stream_ptr)) if engine.stream_ptr else _null():
         res = drv.build(local_blocks, sasamplingrate, isasamplingrate, bwtonly)
         torch.cuda.current_stream().synchronize()
-    return drv, res
+    state["merge"] = drv
+    res["strategy"] = "merge"
+    return state, res
 
 
 class _null:

@@ -178,6 +178,13 @@ int b3m_engine_write_bwt(b3m_engine * e, const char * bwtfn);
  * libmaus2's own RLEncoderStd::encodeRun (/root/reference/src/lcpbit.cpp:728-745).  With both
  * pointers NULL only *nruns is returned. */
 int b3m_engine_fetch_runs(b3m_engine * e, uint8_t * syms, uint64_t * lens, uint64_t cap, uint64_t * nruns);
+/* K9: the BWA index of the last build (pacterm input only), packed on the device; engine half of
+ * MausFmToBwaConversion::rewrite (/root/reference/src/bwtb3mtobwa.cpp:29) for callers that hold the
+ * engine.  bwt_words: ceil(seq_len/16) uint32 exactly as in BWA's .bwt file behind its 40-byte
+ * header (16 symbols per word, symbol k at bits (15-(k&15))*2, terminator row removed);
+ * primary = rank of the suffix at text position 0; L2[0..4] = cumulative base counts; seq_len = n-1.
+ * BWA's .sa payload is sa[1..] of b3m_engine_fetch.  With bwt_words NULL only the scalars are returned. */
+int b3m_engine_fetch_bwa(b3m_engine * e, uint32_t * bwt_words, uint64_t cap_words, uint64_t * primary, uint64_t * L2, uint64_t * seq_len);
 /* K4 + K7 on an existing BWT: sampled SA/ISA from n symbols and npairs (rank,pos) anchors
  * (engine half of b3m_compute_ssa); fetch with b3m_engine_fetch(e, NULL, NULL, sa, isa). */
 int b3m_engine_ssa_from_bwt(b3m_engine * e, const uint8_t * bwt, uint64_t n, const uint64_t * preisa_pairs, uint64_t npairs,
@@ -214,6 +221,23 @@ int b3m_engine_blk_merge_samples(b3m_engine * e, uint64_t a0, uint64_t a1, uint6
  * anchors [q_lo,q_hi); unset SA/ISA samples hold ~0 so that the ranks' partial arrays combine */
 int b3m_engine_blk_finish(b3m_engine * e, const void * d_L_root, uint32_t term_root, uint64_t q_lo, uint64_t q_hi, uint64_t sasamplingrate,
                           uint64_t isasamplingrate, int bwtonly, uint64_t numblocks);
+
+/* ---- multi-GPU driver, suffix-range sharding ---------------------------------------------------
+ * The text is replicated; the suffixes are split by the leading symbols of their first sort key into
+ * nparts key ranges of about equal size (every rank derives the same split from the text), and
+ * engine `part` sorts range `part` only.  Because the ranges are contiguous in suffix-array order,
+ * each rank produces a contiguous slice of the BWT and of the rank-sampled SA, and its share of
+ * the anchors / position-sampled ISA, at their GLOBAL places in caller-owned device buffers that
+ * must be zero on entry: d_bwt n+16 bytes (codes), d_prerank ceil(n/preisarate) u32, d_sa / d_isa
+ * u64 (NULL when bwtonly), d_special 4 u32.  The ranks' buffers combine by a sum (ncclSum); no gap
+ * array and no merge is needed.  *unresolved != 0 means the text has repeats this path does not
+ * sort (longer than the two sort keys); the caller then uses the block merge tree (blk_* above).
+ * b3m_engine_shard_finish installs the combined buffers as the engine's results.  This path is an
+ * addition of this implementation; it replaces the same computeBwt call as b3m_engine_build. */
+int b3m_engine_shard_build(b3m_engine * e, uint32_t part, uint32_t nparts, const b3m_build_params * p, void * d_bwt, void * d_prerank,
+                           void * d_sa, void * d_isa, void * d_special, uint64_t * unresolved);
+int b3m_engine_shard_finish(b3m_engine * e, const void * d_bwt, const void * d_prerank, const void * d_sa, const void * d_isa,
+                            const void * d_special, uint32_t nparts);
 
 /* LF-steps/s instrument on the dictionary of the last build: nchains dependent LF chains of
  * `steps` steps each, started at evenly spaced sampled ranks; returns elapsed device ms.

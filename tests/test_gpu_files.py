@@ -134,3 +134,27 @@ def test_fetch_runs(oracle):
     assert np.array_equal(np.repeat(syms, lens.astype(np.int64)), bwt)
     assert np.all(syms[1:] != syms[:-1])
     e.close()
+
+
+@pytest.mark.parametrize("l", [1, 15, 16, 17, 1000, 65537])
+def test_engine_fetch_bwa_matches_oracle(oracle, l):
+    """K9: the device-packed BWA words, primary and L2 equal the oracle's BWA export of the same BWT."""
+    from bwtb3m_b200 import Engine
+    rng = np.random.default_rng(900 + l)
+    bases = rng.integers(0, 4, size=l, dtype=np.uint8)
+    pac = oracle.encode_pac(bases)
+    eng = Engine(0)
+    try:
+        eng.load_host(pac, "pacterm")
+        eng.build(sasamplingrate=4, isasamplingrate=8)
+        res = eng.fetch()
+        words, primary, l2, seq_len = eng.fetch_bwa()
+    finally:
+        eng.close()
+    ob, osa = oracle.to_bwa(res["bwt"], res["sa"], 4)
+    assert seq_len == l
+    assert primary == int(np.frombuffer(ob[:8], dtype=np.uint64)[0])
+    assert l2[1:] == np.frombuffer(ob[8:40], dtype=np.uint64).tolist()
+    assert words.tobytes() == ob[40:40 + 4 * words.size]
+    # BWA's .sa payload is the rank-sampled SA without its first entry
+    assert res["sa"][1:].tobytes() == osa[56:56 + 8 * (res["sa"].size - 1)]

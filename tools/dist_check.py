@@ -24,6 +24,7 @@ ap.add_argument("--n", type=int, default=200_003)
 ap.add_argument("--itype", default="pacterm")
 ap.add_argument("--local-blocks", type=int, default=1)
 ap.add_argument("--seed", type=int, default=7)
+ap.add_argument("--strategy", default="auto", choices=["auto", "shard", "merge"])
 a = ap.parse_args()
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -44,7 +45,7 @@ for it in range(2):
     torch.cuda.synchronize()
     dist.barrier()
     t0 = time.perf_counter()
-    drv, res = multigpu.build_distributed(eng, local_blocks=a.local_blocks, sasamplingrate=32, isasamplingrate=1024, driver=drv)
+    drv, res = multigpu.build_distributed(eng, local_blocks=a.local_blocks, sasamplingrate=32, isasamplingrate=1024, driver=drv, strategy=a.strategy)
     torch.cuda.synchronize()
     dist.barrier()
     dt = time.perf_counter() - t0
@@ -60,6 +61,7 @@ if rank == 0:
         same = np.array_equal(multi[k], one[k])
         ok = ok and same
         print("%s: %s" % (k, "equal" if same else "DIFFERENT"))
+    print("strategy used: %s" % res["strategy"])
     print("world=%d n=%d second build %.1f ms; phases ms sort=%.1f gap=%.1f merge=%.1f walk=%.1f  %s" %
           (world, info["n"], dt * 1e3, info["ms_sort"], info["ms_gap"], info["ms_merge"], info["ms_walk"], "DIST_CHECK_OK" if ok else "DIST_CHECK_FAILED"))
 dist.barrier()
