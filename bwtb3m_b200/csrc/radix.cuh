@@ -118,6 +118,47 @@ __device__ __forceinline__ void radix_text_record(RadixTextSrc const & S, uint64
 	aux = ((tv_pred(S.v, i) << (nx * S.bits)) | (uint32_t)(ks & ((1u << (nx * S.bits)) - 1u))) & 255u;
 }
 
+// Keys and aux bytes of the records chunk + 32*j + lane, j < ITEMS (one warp, `chunk` warp-uniform).
+// Fast path (2-bit packed text, the warp's records away from both ends of the window and of the
+// text): lane l reads the words under positions p0+l, p0+l+32, ... -- its bit offset inside a word
+// never changes, and every word is the second half of the previous record's window.
+template <int ITEMS>
+__device__ __forceinline__ void radix_text_load(RadixTextSrc const & S, uint64_t chunk, unsigned lane, uint32_t (&k)[ITEMS], uint32_t (&aux)[ITEMS]) {
+	uint64_t const i0 = chunk - S.nshort;
+	uint64_t p0 = S.v.wstart + i0;
+	if (S.v.text_wraps && p0 >= S.v.ntext) p0 -= S.v.ntext;
+	bool const fast = S.bits == 2 && S.v.packed && chunk >= S.nshort && i0 + 32 * ITEMS + 35 <= S.v.W &&
+	                  p0 >= 1 && p0 + 32 * ITEMS + 35 <= S.v.ntext;
+	if (fast) {
+		uint64_t const pl = p0 + lane;
+		const uint64_t * wp = S.v.packed + (pl >> 5);
+		unsigned const sh = (unsigned)(pl & 31u) << 1;
+		uint64_t prevw = (sh == 0) ? __ldg(wp - 1) : 0ull; // pl >= 32 whenever sh == 0 (p0 >= 1)
+		uint64_t cw = __ldg(wp);
+		#pragma unroll
+		for (int j = 0; j < ITEMS; ++j) {
+			uint64_t const nw = __ldg(wp + j + 1);
+			uint64_t const win = sh ? ((cw << sh) | (nw >> (64u - sh))) : cw;
+			uint32_t const pred = sh ? (uint32_t)(cw >> (64u - sh)) & 3u : (uint32_t)prevw & 3u;
+			k[j] = (uint32_t)(win >> 32);
+			aux[j] = (pred << 6) | ((uint32_t)(win >> 26) & 63u);
+			prevw = cw; cw = nw;
+		}
+	} else {
+		#pragma unroll
+		for (int j = 0; j < ITEMS; ++j) {
+			uint64_t const t = chunk + j * 32 + lane;
+			uint32_t ii;
+			k[j] = 0xffffffffu; aux[j] = 0;
+			if (t < S.v.W) radix_text_record(S, t, k[j], ii, aux[j]);
+		}
+	}
+}
+// window index of record t of the text source
+__device__ __forceinline__ uint32_t radix_text_index(RadixTextSrc const & S, uint64_t t) {
+	return (uint32_t)((t < S.nshort) ? (S.v.W - 1 - t) : (t - S.nshort));
+}
+
 template <int NA, bool AUX, bool TEXT, bool FULL>
 __global__ void __launch_bounds__(RADIX_THREADS, RADIX_CTAS_PER_SM)
 k_radix_onesweep(RadixPassArgs<NA> A, RadixTextSrc S, uint64_t n, int shift, uint32_t mask, const uint32_t * __restrict__ base /* [256] */,

@@ -15,10 +15,10 @@ def ngpus():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("args", [["--n", "200003", "--itype", "pacterm"], ["--n", "150001", "--itype", "bytestream"],
-                                  ["--n", "300000", "--itype", "pac", "--local-blocks", "2"],
-                                  ["--n", "200003", "--itype", "pacterm", "--strategy", "merge"],
-                                  ["--n", "250001", "--itype", "pac", "--strategy", "shard"]])
+@pytest.mark.parametrize("args", [["--nsym", "200003", "--itype", "pacterm"], ["--nsym", "150001", "--itype", "bytestream"],
+                                  ["--nsym", "300000", "--itype", "pac", "--local-blocks", "2"],
+                                  ["--nsym", "200003", "--itype", "pacterm", "--strategy", "merge"],
+                                  ["--nsym", "250001", "--itype", "pac", "--strategy", "shard"]])
 def test_nccl_build_equals_single(args):
     if ngpus() < 2:
         pytest.skip("needs at least 2 GPUs")

@@ -1,7 +1,7 @@
 """torchrun script: multi-GPU build (bwtb3m_b200.multigpu, NCCL) == single-GPU build, bit for bit.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-        tools/dist_check.py [--workload cfg2 --scale 0.1 | --n 200003 --itype pacterm] [--local-blocks 1]
+        tools/dist_check.py [--workload cfg2 --scale 0.1 | --nsym 200003 --itype pacterm] [--local-blocks 1]
 """
 import argparse
 import os
@@ -20,7 +20,7 @@ from bwtb3m_b200 import Engine, multigpu, workloads  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="")
 ap.add_argument("--scale", type=float, default=1.0)
-ap.add_argument("--n", type=int, default=200_003)
+ap.add_argument("--nsym", type=int, default=200_003)
 ap.add_argument("--itype", default="pacterm")
 ap.add_argument("--local-blocks", type=int, default=1)
 ap.add_argument("--seed", type=int, default=7)
@@ -33,9 +33,9 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 if a.workload:
     itype, data, nsym = workloads.make(a.workload, a.scale)
 elif a.itype in ("pac", "pacterm"):
-    itype, data = a.itype, workloads.random_pac(a.n, a.seed)
+    itype, data = a.itype, workloads.random_pac(a.nsym, a.seed)
 else:
-    itype, data = "bytestream", np.random.default_rng(a.seed).integers(0, 256, size=a.n, dtype=np.uint8)
+    itype, data = "bytestream", np.random.default_rng(a.seed).integers(0, 256, size=a.nsym, dtype=np.uint8)
 
 stream = torch.cuda.Stream()
 eng = Engine(local, stream.cuda_stream)
