@@ -138,7 +138,7 @@ void Engine::load(const void * input, uint64_t nbytes, int itype, bool on_device
 		T.keybits = sigma <= 4 ? 2 : (sigma <= 16 ? 4 : 8);
 		decode_bytes = 3 * nsym;
 	}
-	B3M_REQUIRE(T.n < 0xFFFFFFF0ull, "inputs of 2^32 symbols or more are not supported yet");
+	B3M_REQUIRE(T.n < 0xFFFFFF00ull, "inputs of 2^32 - 256 symbols or more are not supported yet");
 	T.codes = codes.get();
 	raw.release();
 	if (T.keybits == 2) {

@@ -67,12 +67,13 @@ __device__ __forceinline__ uint32_t fo_pred(TextView const & v, FusedOut const &
 }
 
 __device__ __forceinline__ void fo_emit(FusedOut const & fo, uint32_t i, uint64_t k, uint32_t c) {
-	uint64_t const r = k + fo.shift;
+	// ranks and positions are below 2^32 (the engine rejects longer texts)
+	uint32_t const r = (uint32_t)(k + fo.shift);
 	fo.bwt[r] = (uint8_t)c;
-	if (i == 0) { if (fo.has_term) fo.special[0] = (uint32_t)r; fo.special[1] = (uint32_t)r; }
-	if ((i & ((1u << fo.prelog) - 1u)) == 0) fo.prerank[i >> fo.prelog] = (uint32_t)r;
-	if (fo.isa_s && ((uint64_t)i & ((1ull << fo.isalog) - 1ull)) == 0) fo.isa_s[i >> fo.isalog] = r;
-	if (fo.sa_s && (r & ((1ull << fo.salog) - 1ull)) == 0) fo.sa_s[r >> fo.salog] = i;
+	if (i == 0) { if (fo.has_term) fo.special[0] = r; fo.special[1] = r; }
+	if (fo.prelog >= 32 ? i == 0 : (i & ((1u << fo.prelog) - 1u)) == 0) fo.prerank[fo.prelog >= 32 ? 0 : (i >> fo.prelog)] = r;
+	if (fo.isa_s && (fo.isalog >= 32 ? i == 0 : (i & ((1u << fo.isalog) - 1u)) == 0)) fo.isa_s[fo.isalog >= 32 ? 0 : (i >> fo.isalog)] = r;
+	if (fo.sa_s && (fo.salog >= 32 ? r == 0 : (r & ((1u << fo.salog) - 1u)) == 0)) fo.sa_s[fo.salog >= 32 ? 0 : (r >> fo.salog)] = i;
 }
 
 // K3 on a final suffix array of the whole text (the path taken after prefix doubling)
@@ -122,9 +123,12 @@ k_resolve(TextView v, unsigned bits, unsigned k0, int lin, const uint32_t * __re
 	__shared__ uint32_t s_hb[RS_ROWS + 2];        // head flags of row q in s_hb[q + 1]
 	__shared__ uint8_t s_aux[RS_REG];
 	__shared__ uint32_t s_cnt[3];
-	int64_t const W = (int64_t)v.W;      // window length: decides which suffixes reach the sentinel
-	int64_t const NR = (int64_t)nrec;    // records to resolve (all W suffixes, or the ones of one key range)
-	int64_t const kbase = (int64_t)blockIdx.x * RS_TILE - RS_EXT; // region index x <-> global place kbase + x
+	// all indices fit 32 bits (windows of 2^32-16 suffixes at most); places before the first record
+	// wrap around to huge values and read as invalid
+	uint32_t const NR = (uint32_t)nrec;                       // records to resolve (all W suffixes, or the ones of one key range)
+	bool const allshort = v.W < (uint64_t)k0;
+	uint32_t const shortlim = allshort ? 0u : (uint32_t)(v.W - k0); // suffix i reaches the sentinel inside its first key iff i > shortlim
+	uint32_t const kbase = blockIdx.x * (uint32_t)RS_TILE - (uint32_t)RS_EXT; // region index x <-> global place kbase + x
 	unsigned const w = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	unsigned const nx = 8u / bits - 1u;          // symbols carried in the aux byte behind the key
 	unsigned const xbits = nx * bits;
@@ -133,22 +137,19 @@ k_resolve(TextView v, unsigned bits, unsigned k0, int lin, const uint32_t * __re
 	if (threadIdx.x == 0) { s_hb[0] = 0xffffffffu; s_hb[RS_ROWS + 1] = 0xffffffffu; }
 
 	#pragma unroll 1
-	for (int q = (int)w; q < RS_ROWS; q += RS_WARPS) {
-		int const x = q * 32 + (int)lane;
-		int64_t const k = kbase + x;
-		bool const valid = k >= 0 && k < NR;
-		uint32_t const mk = valid ? key[k] : 0u;
-		uint32_t const mi = valid ? idx[k] : 0u;
+	for (unsigned q = w; q < RS_ROWS; q += RS_WARPS) {
+		unsigned const x = q * 32 + lane;
+		uint32_t const k = kbase + x;
+		bool const valid = k < NR;
+		uint32_t mk = 0, mi = 0, ma = 0;
+		if (valid) { mk = key[k]; mi = idx[k]; ma = aux[k]; }
 		s_idx[x] = mi;
-		s_aux[x] = valid ? aux[k] : (uint8_t)0;
+		s_aux[x] = (uint8_t)ma;
 		// the record before this one: the lane below, or one extra load for lane 0
 		uint32_t pk = __shfl_up_sync(0xffffffffu, mk, 1), pi = __shfl_up_sync(0xffffffffu, mi, 1);
-		if (lane == 0 && k > 0 && k <= NR) { pk = key[k - 1]; pi = idx[k - 1]; }
-		bool head = true;
-		if (k > 0 && k < NR) {
-			head = mk != pk;
-			if (lin) head = head || ((uint64_t)mi + k0 > (uint64_t)W) || ((uint64_t)pi + k0 > (uint64_t)W);
-		}
+		if (lane == 0 && k - 1u < NR) { pk = key[k - 1]; pi = idx[k - 1]; }
+		bool head = !valid || k == 0 || mk != pk;
+		if (lin) head = head || allshort || mi > shortlim || pi > shortlim;
 		uint32_t const hb = __ballot_sync(0xffffffffu, head);
 		if (lane == 0) s_hb[q + 1] = hb;
 	}
@@ -156,29 +157,30 @@ k_resolve(TextView v, unsigned bits, unsigned k0, int lin, const uint32_t * __re
 
 	uint32_t ntied = 0, nunres = 0, ngather = 0;
 	#pragma unroll 1
-	for (int q = 1 + (int)w; q < RS_ROWS; q += RS_WARPS) {
-		int const x = q * 32 + (int)lane;
-		if (kbase + x >= NR) continue;
+	for (unsigned q = 1 + w; q < RS_ROWS; q += RS_WARPS) {
+		int const x = (int)(q * 32 + lane);
+		if (kbase + (uint32_t)x >= NR) continue;
 		// run start: highest head bit at or below x inside the 64 records that end with this row
-		unsigned long long const hbw = ((unsigned long long)s_hb[q + 1] << 32) | s_hb[q];
-		unsigned long long const below = hbw & ((2ull << (32 + lane)) - 1ull);
-		int const y = below ? (q - 1) * 32 + 63 - __clzll((long long)below) : -1;
+		uint32_t const h0 = s_hb[q], h1 = s_hb[q + 1], h2 = s_hb[q + 2];
+		uint32_t const b1 = h1 & (0xffffffffu >> (31 - lane));
+		int const y = b1 ? (int)(q * 32) + 31 - __clz((int)b1) : (h0 ? (int)(q * 32) - 1 - __clz((int)h0) : -1);
 		// run end: lowest head bit above x inside the 64 records that start with this row
-		unsigned long long const hfw = (((unsigned long long)s_hb[q + 2] << 32) | s_hb[q + 1]) >> (lane + 1);
-		int const z = hfw ? x + __ffsll((long long)hfw) : RS_REG + RS_EXT;
+		uint32_t const a1 = lane == 31 ? 0u : (h1 >> (lane + 1));
+		int const z = a1 ? x + __ffs((int)a1) : (h2 ? (int)(q * 32) + 31 + __ffs((int)h2) : RS_REG + RS_EXT);
 		bool const big = y < 0 || x - y >= RS_EXT || z - y > RS_EXT;
 		uint32_t const ax = s_aux[x];
 		int f = x;
 		uint32_t hf = 1;
 		if (big) {
 			if (q > RS_TROWS) continue;                        // the next tile passes it through
-			hf = (s_hb[q + 1] >> lane) & 1u;
+			hf = (h1 >> lane) & 1u;
 			++nunres;
 		} else {
 			if (y < RS_EXT || y >= RS_EXT + RS_TILE) continue; // run of a neighbouring tile
 			if (z - y > 1) {
 				uint32_t const mx = ax & xmask;
 				uint32_t less = 0, eq = 0;
+				#pragma unroll 1
 				for (int y2 = y; y2 < z; ++y2) {
 					uint32_t const ox = s_aux[y2] & xmask;
 					less += ox < mx ? 1u : 0u;
@@ -192,6 +194,7 @@ k_resolve(TextView v, unsigned bits, unsigned k0, int lin, const uint32_t * __re
 					unsigned long long mk2; uint32_t mr;
 					rs_second_key(v, bits, k0 + nx, lin, s_idx[x], mk2, mr);
 					uint32_t eqb = 0, eqa = 0;
+					#pragma unroll 1
 					for (int y2 = y; y2 < z; ++y2) {
 						if (y2 == x || (s_aux[y2] & xmask) != mx) continue;
 						unsigned long long ok2; uint32_t orr;
@@ -208,7 +211,7 @@ k_resolve(TextView v, unsigned bits, unsigned k0, int lin, const uint32_t * __re
 			}
 		}
 		uint32_t const i = s_idx[x];
-		uint32_t const kf = (uint32_t)(kbase + f);
+		uint32_t const kf = kbase + (uint32_t)f;
 		sa_out[kf] = i;
 		hflag[kf] = (uint8_t)hf;
 		if (FUSED) fo_emit(fo, i, (uint64_t)kf, ax >> xbits);
@@ -393,7 +396,7 @@ uint64_t k2_sort_keyrange(Stream & st, DevText const & T, int circular, KeyRange
 void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W, int circular, int text_wraps,
                     DevBuf<uint32_t> & sa_buf, uint32_t * rank, SortStats * stats, const FusedOut * fo) {
 	if (W == 0) return;
-	B3M_REQUIRE(W < 0xFFFFFFF0ull, "window too large for 32-bit suffix indices");
+	B3M_REQUIRE(W < 0xFFFFFF00ull, "window too large for 32-bit suffix indices");
 	B3M_REQUIRE(!fo || (wstart == 0 && W == T.ntext), "internal: fused outputs need the whole text in one window");
 	unsigned const bits = T.keybits;
 	unsigned const k0 = 32 / bits;
