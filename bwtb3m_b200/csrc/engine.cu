@@ -36,6 +36,7 @@ Engine::~Engine() {
 void Engine::reset_results() {
 	ssa_only = false;
 	bwt.release(); prerank.release(); sa.release(); isa.release(); dict.release();
+	D = DevDict();
 	have_results = false;
 }
 
@@ -272,7 +273,9 @@ void Engine::build(b3m_build_params const & p) {
 		pt.mark(); pt.mark(); // 1, 2: the phases are timed inside build_blocks
 	}
 	root_exc_pos = exc_pos;
-	make_dict(exc_pos, 0, 0);
+	// the rank dictionary (K4) serves the LF walk; with direct sampling it is built on first use (lf_bench)
+	dict.release(); D = DevDict();
+	if (!p.bwtonly && !direct) make_dict(exc_pos, 0, 0);
 	pt.mark(); // 3
 	if (!p.bwtonly && !direct)
 		k7_walk(st, D, prerank.get(), npre, prerate, T.n, p.sasamplingrate, p.isasamplingrate, sa.get(), isa.get(), &walkstats, 0, npre);
@@ -354,7 +357,7 @@ void Engine::kr_finish(const void * d_bwt, const void * d_prerank, const void * 
 	}
 	root_exc_pos = exc_pos;
 	numblocks = nparts;
-	make_dict(exc_pos, 0, 0);
+	dict.release(); D = DevDict();
 	pt.mark();
 	B3M_CUDA(cudaStreamSynchronize(st.s));
 	ms_dict = pt.ms(0, 1);
@@ -520,6 +523,8 @@ void Engine::lf_bench(uint64_t nchains, uint64_t steps, float * ms, uint64_t * c
 	B3M_CUDA(cudaSetDevice(device));
 	B3M_REQUIRE(have_results, "no results");
 	B3M_REQUIRE(nchains >= 1, "nchains must be >= 1");
+	B3M_REQUIRE(!ssa_only || D.lines, "no dictionary");
+	if (!D.lines) make_dict(root_exc_pos, 0, 0);
 	DevBuf<uint32_t> start(st, nchains), out(st, nchains);
 	B3M_LAUNCH(st, k_pick_starts, (unsigned)div_up(nchains, 256), 256, 0, (const uint32_t *)prerank.get(), npre, nchains, start.get());
 	PhaseTimer pt(st);
