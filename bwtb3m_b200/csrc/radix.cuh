@@ -308,12 +308,15 @@ k_radix_onesweep(RadixPassArgs<NA> A, RadixTextSrc S, uint64_t n, int shift, uin
 		}
 	}
 	__syncthreads();
+	// the global place of sorted slot s is computed once (k[] is free now) and reused by every array of the record
 	#pragma unroll
 	for (int j = 0; j < RADIX_ITEMS; ++j) {
 		uint32_t const s = j * RADIX_THREADS + threadIdx.x;
 		if (FULL || s < nvalid) {
 			uint32_t const kk = skey[s];
-			A.out[0][gbase[(kk >> shift) & mask] + s] = kk;
+			uint32_t const o = gbase[(kk >> shift) & mask] + s;
+			A.out[0][o] = kk;
+			k[j] = o;
 		}
 	}
 	#pragma unroll
@@ -332,7 +335,7 @@ k_radix_onesweep(RadixPassArgs<NA> A, RadixTextSrc S, uint64_t n, int shift, uin
 		#pragma unroll
 		for (int j = 0; j < RADIX_ITEMS; ++j) {
 			uint32_t const s = j * RADIX_THREADS + threadIdx.x;
-			if (FULL || s < nvalid) A.out[a][gbase[(skey[s] >> shift) & mask] + s] = sval[s];
+			if (FULL || s < nvalid) A.out[a][k[j]] = sval[s];
 		}
 	}
 	if (AUX) {
@@ -346,7 +349,7 @@ k_radix_onesweep(RadixPassArgs<NA> A, RadixTextSrc S, uint64_t n, int shift, uin
 		#pragma unroll
 		for (int j = 0; j < RADIX_ITEMS; ++j) {
 			uint32_t const s = j * RADIX_THREADS + threadIdx.x;
-			if (FULL || s < nvalid) A.aux_out[gbase[(skey[s] >> shift) & mask] + s] = saux[s];
+			if (FULL || s < nvalid) A.aux_out[k[j]] = saux[s];
 		}
 	}
 	#undef RADIX_VALID

@@ -64,6 +64,18 @@ __device__ __forceinline__ uint64_t tv_symbols(TextView const & v, uint64_t i, u
 		uint64_t const p = tv_interior(v, i, 32);
 		if (p != ~0ull) return pk_window(v.packed, p) >> (64u - 2u * count);
 	}
+	if (bits == 8 && count <= 8) {
+		// byte codes: one unaligned 8-byte window out of two aligned words, first symbol most significant
+		uint64_t const p = tv_interior(v, i, 16);
+		if (p != ~0ull) {
+			const uint64_t * wp = reinterpret_cast<const uint64_t *>(v.codes) + (p >> 3); // the code array is 16-byte aligned and padded
+			unsigned const sh = (unsigned)(p & 7u) << 3;
+			uint64_t const a = __ldg(wp), b = __ldg(wp + 1);
+			uint64_t const x = sh ? ((a >> sh) | (b << (64u - sh))) : a;
+			uint64_t const be = ((uint64_t)__byte_perm((uint32_t)x, 0u, 0x0123) << 32) | __byte_perm((uint32_t)(x >> 32), 0u, 0x0123);
+			return be >> (64u - 8u * count);
+		}
+	}
 	uint64_t k = 0;
 	for (uint32_t s = 0; s < count; ++s) k = (k << bits) | tv_symbol(v, i + s);
 	return k;
