@@ -123,6 +123,22 @@ k_hist_range(const uint8_t * __restrict__ in, uint64_t n, unsigned long long * _
 // (Appendix A.2):  r <- C_A[c] + rank_c(L_A, r) + [c == T[a1-1] and gt_R[j]],  G[r]++ .
 // ------------------------------------------------------------------------------------------
 
+// byte k (0..15) of a 16-byte block held in registers
+__device__ __forceinline__ uint32_t byte_of(uint4 const & v, uint32_t k) {
+	uint32_t const w = (k & 8u) ? ((k & 4u) ? v.w : v.z) : ((k & 4u) ? v.y : v.x);
+	return (w >> ((k & 3u) * 8u)) & 255u;
+}
+__device__ __forceinline__ void or_byte(uint4 & v, uint32_t k, uint32_t val) {
+	uint32_t const b = val << ((k & 3u) * 8u);
+	uint32_t const wi = k >> 2;
+	v.x |= wi == 0 ? b : 0u; v.y |= wi == 1 ? b : 0u; v.z |= wi == 2 ? b : 0u; v.w |= wi == 3 ? b : 0u;
+}
+
+// Every chain streams through its own stretch of the text, of gt_in and of gt_out, one byte per
+// step.  With half a million chains in flight those sectors do not survive in L1/L2 between two
+// steps (an ncu capture showed 370 B of DRAM reads per step, profiles/r01s), so each stream is
+// read / written in aligned 16-byte blocks held in registers: per step that leaves the dictionary
+// line (64 B) and the counter sector of G.
 __global__ void __launch_bounds__(256)
 k_gap(DictView D, CTab C, TextRef t, uint64_t a1, uint64_t r1, uint64_t chl, uint64_t c_lo, uint64_t c_hi, const uint32_t * __restrict__ r0,
       const uint8_t * __restrict__ gt_in /* indexed by text position */, uint8_t * __restrict__ gt_out /* indexed by position - a1 */,
@@ -135,18 +151,37 @@ k_gap(DictView D, CTab C, TextRef t, uint64_t a1, uint64_t r1, uint64_t chl, uin
 	if (zhi > r1) zhi = r1;
 	uint32_t const lastA = t.codes[a1 - 1];
 	uint32_t r = r0[c];
+	uint4 cb = make_uint4(0, 0, 0, 0), gb = make_uint4(0, 0, 0, 0), ob = make_uint4(0, 0, 0, 0);
+	uint64_t cblk = ~0ull, gblk = ~0ull, oblk = ~0ull;
+	uint32_t omask = 0;
+	uint64_t const gt_blocks = t.n >> 4; // whole 16-byte blocks of gt_in (the tail is read bytewise)
+	auto flush = [&]() {
+		if (omask == 0xffffu) *reinterpret_cast<uint4 *>(gt_out + (oblk << 4)) = ob;
+		else for (uint32_t k = 0; k < 16; ++k) if ((omask >> k) & 1u) gt_out[(oblk << 4) + k] = (uint8_t)byte_of(ob, k);
+	};
 	for (uint64_t j = zhi; j > zlo; --j) {
 		uint64_t const p = j - 1;
 		if (t.has_term && p == t.ntext) r = 0; // the terminator suffix is smaller than every suffix of A
 		else {
-			uint32_t const g = (j < r1) ? gt_in[j] : special[2];
-			uint32_t const c0 = t.codes[p];
+			uint32_t g;
+			if (j < r1) {
+				if ((j >> 4) < gt_blocks) {
+					if ((j >> 4) != gblk) { gblk = j >> 4; gb = __ldg(reinterpret_cast<const uint4 *>(gt_in) + gblk); }
+					g = byte_of(gb, (uint32_t)(j & 15u));
+				} else g = gt_in[j];
+			} else g = special[2];
+			if ((p >> 4) != cblk) { cblk = p >> 4; cb = __ldg(reinterpret_cast<const uint4 *>(t.codes) + cblk); } // codes are padded by 16 bytes
+			uint32_t const c0 = byte_of(cb, (uint32_t)(p & 15u));
 			r = C.c[c0] + dict_rank(D, c0, r) + ((c0 == lastA && g) ? 1u : 0u);
 		}
 		atomicAdd(&G[r], 1u);
-		gt_out[p - a1] = r > isa_a0; // Appendix A.3
+		uint64_t const q = p - a1;
+		if ((q >> 4) != oblk) { if (omask) flush(); oblk = q >> 4; ob = make_uint4(0, 0, 0, 0); omask = 0; }
+		or_byte(ob, (uint32_t)(q & 15u), r > isa_a0 ? 1u : 0u); // Appendix A.3
+		omask |= 1u << (uint32_t)(q & 15u);
 		if ((p & ratemask) == 0) rsamp[p >> rateshift] = r;
 	}
+	if (omask) flush();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -229,7 +264,9 @@ void Engine::leaf_build(BlockLeaf & leaf, uint64_t s, uint64_t m, uint8_t * L, u
 		DevBuf<uint32_t> wrank(st, W);
 		{
 			DevBuf<uint32_t> wsa;
-			k2_suffix_sort(st, T, s, W, 0, T.has_term ? 0 : 1, wsa, wrank.get(), ss, nullptr);
+			// the rank by position is only asked of the sort when the window is the block itself; otherwise the
+			// compaction below writes the block-local ranks anyway (one random scatter instead of two)
+			k2_suffix_sort(st, T, s, W, 0, T.has_term ? 0 : 1, wsa, W == mt ? wrank.get() : nullptr, ss, nullptr);
 			leaf.sa.alloc(st, mt);
 			// keep the block's own suffixes, in order; wrank becomes the block-local rank by position
 			const uint32_t * sa = wsa.get();
