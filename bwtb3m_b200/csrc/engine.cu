@@ -338,6 +338,17 @@ void Engine::kr_build_part(uint32_t part, uint32_t nparts, b3m_build_params cons
 	extract_bytes = (kr_plan.base[part + 1] - kr_plan.base[part]) * 6;
 }
 
+// first BWT row of every key range (rows of range p: [first[p], first[p+1])); range 0 also owns the terminator row
+void Engine::kr_rows(uint32_t nparts, uint64_t * first) {
+	B3M_CUDA(cudaSetDevice(device));
+	B3M_REQUIRE(loaded, "no input loaded");
+	B3M_REQUIRE(first, "null argument");
+	if (kr_plan.nparts != nparts) k2_keyrange_plan(st, T, T.has_term ? 0 : 1, nparts, kr_plan);
+	uint64_t const shift = T.has_term ? 1 : 0;
+	for (uint32_t p = 0; p <= nparts; ++p) first[p] = kr_plan.base[p] + shift;
+	first[0] = 0; first[nparts] = T.n;
+}
+
 void Engine::kr_finish(const void * d_bwt, const void * d_prerank, const void * d_sa, const void * d_isa, const void * d_special, uint32_t nparts) {
 	B3M_CUDA(cudaSetDevice(device));
 	B3M_REQUIRE(loaded && npre, "kr_build_part was not called");
@@ -631,6 +642,9 @@ int b3m_engine_fetch_runs(b3m_engine * h, uint8_t * syms, uint64_t * lens, uint6
 int b3m_engine_shard_build(b3m_engine * h, uint32_t part, uint32_t nparts, const b3m_build_params * p, void * d_bwt, void * d_prerank,
                            void * d_sa, void * d_isa, void * d_special, uint64_t * unresolved) {
 	B3M_GUARD(h, { if (!p) throw b3m::Error("null params"); h->e->kr_build_part(part, nparts, *p, d_bwt, d_prerank, d_sa, d_isa, d_special, unresolved); });
+}
+int b3m_engine_shard_rows(b3m_engine * h, uint32_t nparts, uint64_t * first_row) {
+	B3M_GUARD(h, h->e->kr_rows(nparts, first_row));
 }
 int b3m_engine_shard_finish(b3m_engine * h, const void * d_bwt, const void * d_prerank, const void * d_sa, const void * d_isa, const void * d_special,
                             uint32_t nparts) {

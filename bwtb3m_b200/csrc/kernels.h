@@ -77,6 +77,7 @@ void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W,
 // in [bin_lo[p], bin_lo[p+1]); base[p] = number of suffixes of the window in smaller bins.
 struct KeyRangePlan {
 	uint32_t nparts = 0;
+	uint32_t binshift = 20;       // bin of a suffix = its first key >> binshift
 	std::vector<uint32_t> bin_lo;
 	std::vector<uint64_t> base;
 };

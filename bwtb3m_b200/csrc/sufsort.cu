@@ -280,7 +280,7 @@ k_keyrange_hist(RadixTextSrc S, unsigned long long * __restrict__ ghist /* [KR_B
 // 1.5 M small tiles.
 template <bool WRITE>
 __global__ void __launch_bounds__(256)
-k_keyrange_filter(RadixTextSrc S, uint32_t blo, uint32_t bhi, uint32_t * __restrict__ tilecount, const uint32_t * __restrict__ tileoff,
+k_keyrange_filter(RadixTextSrc S, uint32_t binshift, uint32_t blo, uint32_t bhi, uint32_t * __restrict__ tilecount, const uint32_t * __restrict__ tileoff,
                   uint32_t * __restrict__ okey, uint32_t * __restrict__ oidx, uint8_t * __restrict__ oaux) {
 	__shared__ uint32_t wtot[8];
 	unsigned const w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -291,7 +291,7 @@ k_keyrange_filter(RadixTextSrc S, uint32_t blo, uint32_t bhi, uint32_t * __restr
 	uint32_t mine = 0, total = 0;
 	#pragma unroll
 	for (int j = 0; j < 8; ++j) {
-		uint32_t const b = key[j] >> 20;
+		uint32_t const b = key[j] >> binshift;
 		bool const in = (t0 + j * 32 + lane < S.v.W) && b >= blo && b < bhi;
 		unsigned const m = __ballot_sync(0xffffffffu, in);
 		rowbase[j] = total + __popc(m & lanemask_lt());
@@ -321,21 +321,38 @@ void k2_keyrange_plan(Stream & st, DevText const & T, int circular, uint32_t npa
 	uint64_t const nshort = circular ? 0 : (W < (uint64_t)(k0 - 1) ? W : (uint64_t)(k0 - 1));
 	TextView v{T.codes, bits == 2 ? T.packed : nullptr, T.ntext, 0, W, circular, 0, T.has_term};
 	RadixTextSrc S{v, nshort, bits, k0};
-	DevBuf<unsigned long long> gh(st, KR_BINS);
-	B3M_CUDA(cudaMemsetAsync(gh.get(), 0, KR_BINS * 8, st.s));
-	uint64_t const want = div_up(W, KR_TILE);
-	unsigned const grid = (unsigned)(want < (uint64_t)st.sms * 8 ? (want ? want : 1) : (uint64_t)st.sms * 8);
-	B3M_LAUNCH_T(st, "keyrange_hist", W / 4, k_keyrange_hist, grid, 256, 0, S, gh.get());
-	std::vector<unsigned long long> h(KR_BINS);
-	B3M_CUDA(cudaMemcpyAsync(h.data(), gh.get(), KR_BINS * 8, cudaMemcpyDeviceToHost, st.s));
-	B3M_CUDA(cudaStreamSynchronize(st.s));
+	std::vector<unsigned long long> h;
+	uint32_t nbins;
+	if (bits == 2 && v.packed) {
+		// the leading 4 symbols of every suffix: the top digit of the first key, whose histogram the sort needs anyway
+		nbins = RADIX_BINS; plan.binshift = 24;
+		DevBuf<unsigned long long> gh(st, RADIX_MAXDIG * RADIX_BINS);
+		B3M_CUDA(cudaMemsetAsync(gh.get(), 0, gh.bytes(), st.s));
+		uint64_t const want = div_up(div_up(W, 32), 256 * 4);
+		unsigned const grid = (unsigned)(want < (uint64_t)st.sms * 8 ? (want ? want : 1) : (uint64_t)st.sms * 8);
+		B3M_LAUNCH_T(st, "hist_4mers", W / 4, k_hist_4mers, grid, 256, 0, v, gh.get());
+		B3M_LAUNCH(st, k_hist_4mers_fix, 1, 256, 0, v, gh.get());
+		h.resize(nbins);
+		B3M_CUDA(cudaMemcpyAsync(h.data(), gh.get() + 3 * RADIX_BINS, nbins * 8, cudaMemcpyDeviceToHost, st.s));
+		B3M_CUDA(cudaStreamSynchronize(st.s));
+	} else {
+		nbins = KR_BINS; plan.binshift = 20;
+		DevBuf<unsigned long long> gh(st, KR_BINS);
+		B3M_CUDA(cudaMemsetAsync(gh.get(), 0, KR_BINS * 8, st.s));
+		uint64_t const want = div_up(W, KR_TILE);
+		unsigned const grid = (unsigned)(want < (uint64_t)st.sms * 8 ? (want ? want : 1) : (uint64_t)st.sms * 8);
+		B3M_LAUNCH_T(st, "keyrange_hist", W / 4, k_keyrange_hist, grid, 256, 0, S, gh.get());
+		h.resize(nbins);
+		B3M_CUDA(cudaMemcpyAsync(h.data(), gh.get(), KR_BINS * 8, cudaMemcpyDeviceToHost, st.s));
+		B3M_CUDA(cudaStreamSynchronize(st.s));
+	}
 	plan.nparts = nparts;
-	plan.bin_lo.assign(nparts + 1, KR_BINS);
+	plan.bin_lo.assign(nparts + 1, nbins);
 	plan.base.assign(nparts + 1, W);
 	plan.bin_lo[0] = 0; plan.base[0] = 0;
 	uint64_t acc = 0;
 	uint32_t p = 1;
-	for (uint32_t b = 0; b < KR_BINS && p < nparts; ++b) {
+	for (uint32_t b = 0; b < nbins && p < nparts; ++b) {
 		// part p starts at the first bin boundary at or past p/nparts of the suffixes
 		while (p < nparts && acc >= (W * p) / nparts) { plan.bin_lo[p] = b; plan.base[p] = acc; ++p; }
 		acc += h[b];
@@ -357,12 +374,12 @@ uint64_t k2_sort_keyrange(Stream & st, DevText const & T, int circular, KeyRange
 	// stable compaction of the range's records out of the text
 	uint32_t const ntiles = (uint32_t)div_up(W, KR_TILE);
 	DevBuf<uint32_t> tcount(st, ntiles);
-	B3M_LAUNCH_T(st, "keyrange_count", W / 4, (k_keyrange_filter<false>), ntiles, 256, 0, S, blo, bhi, tcount.get(), (const uint32_t *)nullptr,
+	B3M_LAUNCH_T(st, "keyrange_count", W / 4, (k_keyrange_filter<false>), ntiles, 256, 0, S, plan.binshift, blo, bhi, tcount.get(), (const uint32_t *)nullptr,
 	             (uint32_t *)nullptr, (uint32_t *)nullptr, (uint8_t *)nullptr);
 	scan_exclusive_inplace<OpSum>(st, tcount.get(), ntiles);
 	DevBuf<uint32_t> key0(st, m), key1(st, m), idx0(st, m), idx1(st, m);
 	DevBuf<uint8_t> aux0(st, m), aux1(st, m);
-	B3M_LAUNCH_T(st, "keyrange_write", W / 4 + 9 * m, (k_keyrange_filter<true>), ntiles, 256, 0, S, blo, bhi, (uint32_t *)nullptr, (const uint32_t *)tcount.get(),
+	B3M_LAUNCH_T(st, "keyrange_write", W / 4 + 9 * m, (k_keyrange_filter<true>), ntiles, 256, 0, S, plan.binshift, blo, bhi, (uint32_t *)nullptr, (const uint32_t *)tcount.get(),
 	             key0.get(), idx0.get(), aux0.get());
 	St.other_bytes += W / 2 + 9 * m;
 	RadixRec<2> cur{{key0.get(), idx0.get()}, aux0.get()}, alt{{key1.get(), idx1.get()}, aux1.get()};

@@ -118,6 +118,12 @@ class Engine:
                                                      vp(special_ptr), C.byref(un)))
         return int(un.value)
 
+    def shard_rows(self, nparts):
+        """first BWT row of every key range (nparts + 1 values)"""
+        a = (C.c_uint64 * (nparts + 1))()
+        self._check(self._lib.b3m_engine_shard_rows(self._h, nparts, a))
+        return [int(x) for x in a]
+
     def shard_finish(self, nparts, bwt_ptr, prerank_ptr, sa_ptr, isa_ptr, special_ptr):
         vp = lambda a: C.c_void_p(a) if a else None
         self._check(self._lib.b3m_engine_shard_finish(self._h, vp(bwt_ptr), vp(prerank_ptr), vp(sa_ptr), vp(isa_ptr), vp(special_ptr), nparts))

@@ -285,7 +285,32 @@ def build_sharded(engine, preisarate=0, sasamplingrate=32, isasamplingrate=26214
     if int(flag.item()) != 0:
         return False, buf
     if world > 1:
-        for t in buf.tensors():  # every entry is written by exactly one rank, the others hold 0
+        # dense results (BWT rows, rank-sampled SA) are contiguous per rank: they travel as slices straight
+        # into rank 0's buffers; the sparse ones (anchors, ISA samples, special rows) are summed -- every entry
+        # is written by exactly one rank, the others hold 0
+        rows = engine.shard_rows(world) if hasattr(engine, "shard_rows") else None
+        if rows is not None:
+            sr = sasamplingrate
+            ops = []
+            for p in range(1, world):
+                lo, hi = rows[p], rows[p + 1]
+                pieces = [buf.bwt[lo:hi]]
+                if buf.sa is not None:
+                    pieces.append(buf.sa[(lo + sr - 1) // sr:(hi + sr - 1) // sr])
+                for t in pieces:
+                    if t.numel() == 0:
+                        continue
+                    if rank == 0:
+                        ops.append(dist.P2POp(dist.irecv, t, p))
+                    elif rank == p:
+                        ops.append(dist.P2POp(dist.isend, t, 0))
+            if ops:
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+            sparse = [t for t in (buf.prerank, buf.isa, buf.special) if t is not None]
+        else:
+            sparse = buf.tensors()
+        for t in sparse:
             dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
     if rank == 0:
         engine.shard_finish(world, *buf.ptrs())

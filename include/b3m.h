@@ -236,6 +236,10 @@ int b3m_engine_blk_finish(b3m_engine * e, const void * d_L_root, uint32_t term_r
  * addition of this implementation; it replaces the same computeBwt call as b3m_engine_build. */
 int b3m_engine_shard_build(b3m_engine * e, uint32_t part, uint32_t nparts, const b3m_build_params * p, void * d_bwt, void * d_prerank,
                            void * d_sa, void * d_isa, void * d_special, uint64_t * unresolved);
+/* first_row[p] (p = 0..nparts) = first BWT row of key range p: range p produces the rows
+ * [first_row[p], first_row[p+1]) of the BWT and the SA samples of the ranks in that interval, so the
+ * dense results can travel as slices instead of a reduction over the whole arrays */
+int b3m_engine_shard_rows(b3m_engine * e, uint32_t nparts, uint64_t * first_row);
 int b3m_engine_shard_finish(b3m_engine * e, const void * d_bwt, const void * d_prerank, const void * d_sa, const void * d_isa,
                             const void * d_special, uint32_t nparts);
 

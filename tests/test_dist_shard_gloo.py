@@ -29,6 +29,10 @@ class ModelEngine:
     def default_preisarate(self, bwtonly=False):
         return 64
 
+    def shard_rows(self, nparts):
+        n = int(self.t.size)
+        return [p * n // nparts for p in range(nparts + 1)]
+
     @staticmethod
     def _view(ptr, n, dt):
         return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(dt)), shape=(n,))
