@@ -185,32 +185,40 @@ k_radix_onesweep(RadixPassArgs<NA> A, RadixTextSrc S, uint64_t n, int shift, uin
 
 	uint32_t k[RADIX_ITEMS];
 	uint32_t taux[TEXT ? (RADIX_ITEMS + 3) / 4 : 1];
+	bool tfast = false; // TEXT: this warp's records are taken lane-blocked (see below)
 	if (TEXT) {
 		static_assert(!TEXT || (NA == 2 && AUX), "text source: (key, index) records with an aux byte");
 		// Fast path (2-bit packed text, the warp's records away from both ends of the window and of
-		// the text): lane l reads the words under positions p0+l, p0+l+32, ... -- its bit offset
-		// inside a word never changes, and every word is the second half of the previous record's window.
+		// the text): lane l takes the RADIX_ITEMS CONSECUTIVE positions p0 + ITEMS*l + j.  Three words
+		// give it the 64 symbols from one before its first position; every key, carried symbol and
+		// preceding code is then a constant-distance bit field of that 128-bit value.  (The first pass
+		// may take the records of a warp in any fixed order: nothing has been sorted yet, and the short
+		// suffixes that must stay in front sit in a warp that takes the general path.)
 		uint64_t const i0 = chunk - S.nshort;
 		uint64_t p0 = S.v.wstart + i0;
 		if (S.v.text_wraps && p0 >= S.v.ntext) p0 -= S.v.ntext;
 		bool const fast = S.bits == 2 && S.v.packed && chunk >= S.nshort && i0 + 32 * RADIX_ITEMS + 35 <= S.v.W &&
 		                  p0 >= 1 && p0 + 32 * RADIX_ITEMS + 35 <= S.v.ntext;
+		tfast = fast;
 		if (fast) {
-			uint64_t const pl = p0 + lane;
-			const uint64_t * wp = S.v.packed + (pl >> 5);
-			unsigned const sh = (unsigned)(pl & 31u) << 1;
-			uint64_t prevw = (sh == 0) ? __ldg(wp - 1) : 0ull; // pl >= 32 whenever sh == 0 (p0 >= 1)
-			uint64_t cw = __ldg(wp);
+			static_assert(RADIX_ITEMS <= 16, "a lane's records must fit one 64-symbol window");
+			uint64_t const q = p0 + (uint64_t)RADIX_ITEMS * lane - 1; // symbol before the lane's first record
+			const uint64_t * wp = S.v.packed + (q >> 5);
+			unsigned const sh = (unsigned)(q & 31u) << 1;
+			uint64_t const w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+			uint64_t const hi = sh ? ((w0 << sh) | (w1 >> (64u - sh))) : w0; // symbols q .. q+31
+			uint64_t const lo = sh ? ((w1 << sh) | (w2 >> (64u - sh))) : w1; // symbols q+32 .. q+63
 			#pragma unroll
 			for (int j = 0; j < RADIX_ITEMS; ++j) {
-				uint64_t const nw = __ldg(wp + j + 1);
-				uint64_t const win = sh ? ((cw << sh) | (nw >> (64u - sh))) : cw;
-				uint32_t const k19 = (uint32_t)(win >> 26) & 63u;
-				uint32_t const pred = sh ? (uint32_t)(cw >> (64u - sh)) & 3u : (uint32_t)prevw & 3u;
-				k[j] = (uint32_t)(win >> 32);
+				// record j: preceding code = symbol j, key = symbols j+1 .. j+16, carried = symbols j+17 .. j+19
+				uint32_t const pred = (uint32_t)(hi >> (62 - 2 * j)) & 3u;
+				k[j] = (uint32_t)(((hi << (2 * j + 2)) | (lo >> (62 - 2 * j))) >> 32);
+				int const xo = 2 * j + 34; // bit offset of the carried symbols from the top of hi:lo
+				uint32_t const k19 = xo + 6 <= 64 ? (uint32_t)(hi >> (58 - xo)) & 63u
+				                   : (xo >= 64 ? (uint32_t)(lo >> (122 - xo)) & 63u
+				                               : (uint32_t)((hi << (xo - 58)) | (lo >> (122 - xo))) & 63u);
 				uint32_t const aa = (pred << 6) | k19;
 				if ((j & 3) == 0) taux[TEXT ? j / 4 : 0] = aa; else taux[TEXT ? j / 4 : 0] |= aa << (8 * (j & 3));
-				prevw = cw; cw = nw;
 			}
 		} else {
 			#pragma unroll
@@ -303,7 +311,10 @@ k_radix_onesweep(RadixPassArgs<NA> A, RadixTextSrc S, uint64_t n, int shift, uin
 		#pragma unroll
 		for (int j = 0; j < RADIX_ITEMS; ++j) {
 			uint64_t const i = chunk + j * 32 + lane;
-			if (TEXT) v[j] = (uint32_t)((i < S.nshort) ? (S.v.W - 1 - i) : (i - S.nshort)); // the record's window index
+			if (TEXT) { // the record's window index
+				uint64_t const t = tfast ? chunk + (uint64_t)RADIX_ITEMS * lane + j : i;
+				v[j] = (uint32_t)((t < S.nshort) ? (S.v.W - 1 - t) : (t - S.nshort));
+			}
 			else v[j] = RADIX_VALID(i) ? A.in[1][i] : 0u;
 		}
 	}

@@ -115,7 +115,9 @@ __device__ __forceinline__ void rs_second_key(TextView const & v, unsigned bits,
 	rem = (uint32_t)((lin && left < skip + k2syms) ? left : skip + k2syms);
 }
 
-template <bool FUSED>
+// ORDER: write the resolved order (suffix array + head flags); a fused whole-text sort leaves it out
+// and only comes back for it when something stayed unresolved.
+template <bool FUSED, bool ORDER>
 __global__ void __launch_bounds__(RS_THREADS)
 k_resolve(TextView v, unsigned bits, unsigned k0, int lin, const uint32_t * __restrict__ key, const uint32_t * __restrict__ idx,
           const uint8_t * __restrict__ aux, uint64_t nrec, uint32_t * __restrict__ sa_out, uint8_t * __restrict__ hflag, FusedOut fo, unsigned long long * __restrict__ counters) {
@@ -212,8 +214,7 @@ k_resolve(TextView v, unsigned bits, unsigned k0, int lin, const uint32_t * __re
 		}
 		uint32_t const i = s_idx[x];
 		uint32_t const kf = kbase + (uint32_t)f;
-		sa_out[kf] = i;
-		hflag[kf] = (uint8_t)hf;
+		if (ORDER) { sa_out[kf] = i; hflag[kf] = (uint8_t)hf; }
 		if (FUSED) fo_emit(fo, i, (uint64_t)kf, ax >> xbits);
 	}
 	// per-CTA totals, spread over RS_CSLOTS counter sets (one hot address would serialise in L2)
@@ -391,8 +392,8 @@ uint64_t k2_sort_keyrange(Stream & st, DevText const & T, int circular, KeyRange
 	B3M_CUDA(cudaMemsetAsync(counters.get(), 0, 32 * RS_CSLOTS, st.s));
 	FusedOut fo = fo0;
 	fo.shift = fo0.shift + plan.base[part];
-	uint64_t const rbytes = m * 15ull;
-	B3M_LAUNCH_T(st, "resolve_extract", rbytes, (k_resolve<true>), (unsigned)div_up(m, RS_TILE), RS_THREADS, 0, v, bits, k0, !circular, (const uint32_t *)cur.a[0],
+	uint64_t const rbytes = m * 10ull;
+	B3M_LAUNCH_T(st, "resolve_extract", rbytes, (k_resolve<true, false>), (unsigned)div_up(m, RS_TILE), RS_THREADS, 0, v, bits, k0, !circular, (const uint32_t *)cur.a[0],
 	             (const uint32_t *)cur.a[1], (const uint8_t *)cur.aux, m, alt.a[1], hflag.get(), fo, counters.get());
 	std::vector<unsigned long long> hcs(4 * RS_CSLOTS);
 	B3M_CUDA(cudaMemcpyAsync(hcs.data(), counters.get(), 32 * RS_CSLOTS, cudaMemcpyDeviceToHost, st.s));
@@ -451,19 +452,36 @@ void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W,
 		B3M_CUDA(cudaMemsetAsync(counters.get(), 0, 32 * RS_CSLOTS, st.s));
 		unsigned const rgrid = (unsigned)div_up(W, RS_TILE);
 		// key + index + aux in, suffix array + head flag (+ BWT code) out; second-key gathers are added below
-		uint64_t const rbytes = W * (9ull + 4ull + 1ull + (fo ? 1ull : 0ull));
-		if (fo) B3M_LAUNCH_T(st, "resolve_extract", rbytes, (k_resolve<true>), rgrid, RS_THREADS, 0, v, bits, k0, lin, (const uint32_t *)cur.a[0],
-		                     (const uint32_t *)cur.a[1], (const uint8_t *)cur.aux, W, alt.a[1], hflag.get(), *fo, counters.get());
-		else B3M_LAUNCH_T(st, "resolve", rbytes, (k_resolve<false>), rgrid, RS_THREADS, 0, v, bits, k0, lin, (const uint32_t *)cur.a[0],
-		                  (const uint32_t *)cur.a[1], (const uint8_t *)cur.aux, W, alt.a[1], hflag.get(), FusedOut(), counters.get());
-		std::vector<unsigned long long> hcs(4 * RS_CSLOTS);
-		B3M_CUDA(cudaMemcpyAsync(hcs.data(), counters.get(), 32 * RS_CSLOTS, cudaMemcpyDeviceToHost, st.s));
-		B3M_CUDA(cudaStreamSynchronize(st.s));
-		unsigned long long hc[4] = {0, 0, 0, 0};
-		for (int q = 0; q < RS_CSLOTS; ++q) for (int c = 0; c < 3; ++c) hc[c] += hcs[4 * q + c];
+		uint64_t const rbytes = W * (9ull + 4ull + 1ull);
+		auto read_counters = [&](unsigned long long * hc) {
+			std::vector<unsigned long long> hcs(4 * RS_CSLOTS);
+			B3M_CUDA(cudaMemcpyAsync(hcs.data(), counters.get(), 32 * RS_CSLOTS, cudaMemcpyDeviceToHost, st.s));
+			B3M_CUDA(cudaStreamSynchronize(st.s));
+			for (int c = 0; c < 4; ++c) hc[c] = 0;
+			for (int q = 0; q < RS_CSLOTS; ++q) for (int c = 0; c < 3; ++c) hc[c] += hcs[4 * q + c];
+		};
+		unsigned long long hc[4];
+		if (fo) {
+			// fused: emit BWT / anchors / samples and skip the order; it is only needed if something stays unresolved
+			B3M_LAUNCH_T(st, "resolve_extract", W * 10ull, (k_resolve<true, false>), rgrid, RS_THREADS, 0, v, bits, k0, lin, (const uint32_t *)cur.a[0],
+			             (const uint32_t *)cur.a[1], (const uint8_t *)cur.aux, W, alt.a[1], hflag.get(), *fo, counters.get());
+			read_counters(hc);
+			S.other_bytes += W * 10ull + 32ull * hc[2];
+			if (hc[0]) {
+				B3M_CUDA(cudaMemsetAsync(counters.get(), 0, 32 * RS_CSLOTS, st.s));
+				B3M_LAUNCH_T(st, "resolve", rbytes, (k_resolve<false, true>), rgrid, RS_THREADS, 0, v, bits, k0, lin, (const uint32_t *)cur.a[0],
+				             (const uint32_t *)cur.a[1], (const uint8_t *)cur.aux, W, alt.a[1], hflag.get(), FusedOut(), counters.get());
+				read_counters(hc);
+				S.other_bytes += rbytes + 32ull * hc[2];
+			}
+		} else {
+			B3M_LAUNCH_T(st, "resolve", rbytes, (k_resolve<false, true>), rgrid, RS_THREADS, 0, v, bits, k0, lin, (const uint32_t *)cur.a[0],
+			             (const uint32_t *)cur.a[1], (const uint8_t *)cur.aux, W, alt.a[1], hflag.get(), FusedOut(), counters.get());
+			read_counters(hc);
+			S.other_bytes += rbytes + 32ull * hc[2];
+		}
 		unresolved = hc[0];
 		S.tied0 = hc[1]; S.unresolved0 = hc[0];
-		S.other_bytes += rbytes + 32ull * hc[2];
 		sa_buf = (alt.a[1] == idx1.get()) ? std::move(idx1) : std::move(idx0);
 		TRACE("r0 resolve");
 	}
