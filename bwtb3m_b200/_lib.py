@@ -18,6 +18,7 @@ class BuildParams(C.Structure):
         ("bwtonly", C.c_int),
         ("largelcpthres", C.c_uint64),
         ("sampling", C.c_int),
+        ("host_sa", C.c_void_p),
     ]
 
 

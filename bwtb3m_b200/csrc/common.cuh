@@ -117,6 +117,7 @@ struct KernelTimes {
 // Per-engine launch context: the stream every kernel goes to, the arena, and counters the bench reports.
 struct Stream {
 	cudaStream_t s = nullptr;
+	cudaStream_t copy = nullptr;  // second stream: results that are final early travel to the host while the build runs
 	uint64_t launches = 0;      // kernels launched by this library (bench: "gpu_launches")
 	int sms = 148;              // multiprocessor count of the device
 	Arena * arena = nullptr;

@@ -19,6 +19,7 @@ Engine::Engine(int dev, void * stream) : device(dev) {
 	if (stream) { st.s = (cudaStream_t)stream; own_stream = false; }
 	else { B3M_CUDA(cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking)); own_stream = true; }
 	st.arena = &arena;
+	B3M_CUDA(cudaStreamCreateWithFlags(&st.copy, cudaStreamNonBlocking));
 	B3M_CUDA(cudaMallocHost((void **)&pinned, 4096));
 }
 
@@ -30,6 +31,7 @@ Engine::~Engine() {
 	cudaStreamSynchronize(st.s);
 	arena.release_all();
 	if (pinned) cudaFreeHost(pinned);
+	if (st.copy) cudaStreamDestroy(st.copy);
 	if (own_stream) cudaStreamDestroy(st.s);
 }
 
@@ -37,6 +39,7 @@ void Engine::reset_results() {
 	ssa_only = false;
 	bwt.release(); prerank.release(); sa.release(); isa.release(); dict.release();
 	D = DevDict();
+	sa_on_host = nullptr;
 	have_results = false;
 }
 
@@ -247,9 +250,18 @@ void Engine::build(b3m_build_params const & p) {
 			fo.sa_s = (unsigned long long *)sa.get(); fo.salog = ceil_log2_u64(p.sasamplingrate);
 			fo.isa_s = (unsigned long long *)isa.get(); fo.isalog = ceil_log2_u64(p.isasamplingrate);
 		}
+		StreamOut so;
+		if (direct && p.host_sa) { so.host_sa = (unsigned long long *)p.host_sa; so.nsa = nsa; }
 		{
 			DevBuf<uint32_t> dsa;
-			k2_suffix_sort(st, T, 0, W, T.has_term ? 0 : 1, 0, dsa, nullptr, &sortstats, &fo);
+			k2_suffix_sort(st, T, 0, W, T.has_term ? 0 : 1, 0, dsa, nullptr, &sortstats, &fo, &so);
+		}
+		if (so.host_sa) {
+			B3M_CUDA(cudaStreamSynchronize(st.copy));
+			if (!so.delivered) B3M_CUDA(cudaMemcpyAsync(so.host_sa, sa.get(), 8 * nsa, cudaMemcpyDeviceToHost, st.s)); // rewritten after doubling
+			B3M_CUDA(cudaStreamSynchronize(st.s));
+			if (T.has_term) so.host_sa[0] = T.ntext; // the terminator suffix, set on the device below
+			sa_on_host = (uint64_t *)so.host_sa;
 		}
 		if (T.has_term) {
 			// rank 0 is the terminator suffix (text position ntext); its predecessor is the last base
@@ -392,7 +404,7 @@ void Engine::fetch(uint8_t * h_bwt, uint64_t * h_pairs, uint64_t * h_sa, uint64_
 		B3M_CUDA(cudaMemcpyAsync(h_pairs, pairs.get(), 16 * npre, cudaMemcpyDeviceToHost, st.s));
 		B3M_CUDA(cudaStreamSynchronize(st.s));
 	}
-	if (h_sa && nsa) B3M_CUDA(cudaMemcpyAsync(h_sa, sa.get(), 8 * nsa, cudaMemcpyDeviceToHost, st.s));
+	if (h_sa && nsa && h_sa != sa_on_host) B3M_CUDA(cudaMemcpyAsync(h_sa, sa.get(), 8 * nsa, cudaMemcpyDeviceToHost, st.s));
 	if (h_isa && nisa) B3M_CUDA(cudaMemcpyAsync(h_isa, isa.get(), 8 * nisa, cudaMemcpyDeviceToHost, st.s));
 	B3M_CUDA(cudaStreamSynchronize(st.s));
 }

@@ -65,6 +65,7 @@ struct Engine {
 	DevBuf<uint8_t> bwt;        // n dense codes (terminator row holds code 0, see root_exc_pos)
 	DevBuf<uint32_t> prerank;   // rank of positions 0, prerate, 2*prerate, ...
 	DevBuf<uint64_t> sa, isa;
+	uint64_t * sa_on_host = nullptr; // host buffer that already holds the sampled SA of the last build (b3m_build_params.host_sa)
 	DevBuf<uint8_t> dict;
 	DevBuf<uint32_t> d_special;
 	DevBuf<uint8_t> gt;         // multi-block: gt[i] = [rot(i) > rot(start of i's current node)]

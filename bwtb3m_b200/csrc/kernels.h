@@ -63,6 +63,14 @@ struct FusedOut {
 	uint32_t isalog = 0;
 };
 
+// Optional early delivery: a pinned host buffer that receives the rank-sampled SA in chunks while
+// the last sorting step is still running (PCIe D2H overlaps the kernel).
+struct StreamOut {
+	unsigned long long * host_sa = nullptr; // nsa values
+	uint64_t nsa = 0;
+	bool delivered = false;                 // set when host_sa holds every value but [0] of a terminated text
+};
+
 // Sorts the W suffixes that start at text positions wstart+i, 0 <= i < W.
 // circular != 0: W == ntext, wstart == 0, indices wrap (terminator-free whole text).
 // circular == 0: the end of the window is a sentinel smaller than every symbol; text positions
@@ -71,7 +79,7 @@ struct FusedOut {
 // rank (caller's, W entries, may be nullptr): the inverse permutation.
 // fo (may be nullptr; whole-text windows only): fused outputs, see FusedOut.
 void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W, int circular, int text_wraps,
-                    DevBuf<uint32_t> & sa, uint32_t * rank, SortStats * stats, const FusedOut * fo);
+                    DevBuf<uint32_t> & sa, uint32_t * rank, SortStats * stats, const FusedOut * fo, StreamOut * so = nullptr);
 
 // Suffix-range sharding (multi-GPU, sufsort.cu): part p holds the suffixes whose first-key bin lies
 // in [bin_lo[p], bin_lo[p+1]); base[p] = number of suffixes of the window in smaller bins.

@@ -19,6 +19,8 @@
 #include "scan.cuh"
 #include "textview.cuh"
 #include <time.h>
+#include <algorithm>
+#include <vector>
 #include <stdlib.h>
 
 namespace b3m {
@@ -120,7 +122,7 @@ __device__ __forceinline__ void rs_second_key(TextView const & v, unsigned bits,
 template <bool FUSED, bool ORDER>
 __global__ void __launch_bounds__(RS_THREADS)
 k_resolve(TextView v, unsigned bits, unsigned k0, int lin, const uint32_t * __restrict__ key, const uint32_t * __restrict__ idx,
-          const uint8_t * __restrict__ aux, uint64_t nrec, uint32_t * __restrict__ sa_out, uint8_t * __restrict__ hflag, FusedOut fo, unsigned long long * __restrict__ counters) {
+          const uint8_t * __restrict__ aux, uint64_t nrec, uint32_t tile0, uint32_t * __restrict__ sa_out, uint8_t * __restrict__ hflag, FusedOut fo, unsigned long long * __restrict__ counters) {
 	__shared__ uint32_t s_idx[RS_REG];
 	__shared__ uint32_t s_hb[RS_ROWS + 2];        // head flags of row q in s_hb[q + 1]
 	__shared__ uint8_t s_aux[RS_REG];
@@ -130,7 +132,8 @@ k_resolve(TextView v, unsigned bits, unsigned k0, int lin, const uint32_t * __re
 	uint32_t const NR = (uint32_t)nrec;                       // records to resolve (all W suffixes, or the ones of one key range)
 	bool const allshort = v.W < (uint64_t)k0;
 	uint32_t const shortlim = allshort ? 0u : (uint32_t)(v.W - k0); // suffix i reaches the sentinel inside its first key iff i > shortlim
-	uint32_t const kbase = blockIdx.x * (uint32_t)RS_TILE - (uint32_t)RS_EXT; // region index x <-> global place kbase + x
+	uint32_t const tile = blockIdx.x + tile0;
+	uint32_t const kbase = tile * (uint32_t)RS_TILE - (uint32_t)RS_EXT; // region index x <-> global place kbase + x
 	unsigned const w = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	unsigned const nx = 8u / bits - 1u;          // symbols carried in the aux byte behind the key
 	unsigned const xbits = nx * bits;
@@ -228,7 +231,7 @@ k_resolve(TextView v, unsigned bits, unsigned k0, int lin, const uint32_t * __re
 	}
 	__syncthreads();
 	if (threadIdx.x < 3 && s_cnt[threadIdx.x])
-		atomicAdd(&counters[(blockIdx.x % RS_CSLOTS) * 4 + threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+		atomicAdd(&counters[(tile % RS_CSLOTS) * 4 + threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
 }
 
 static double wall_ms() {
@@ -394,7 +397,7 @@ uint64_t k2_sort_keyrange(Stream & st, DevText const & T, int circular, KeyRange
 	fo.shift = fo0.shift + plan.base[part];
 	uint64_t const rbytes = m * 10ull;
 	B3M_LAUNCH_T(st, "resolve_extract", rbytes, (k_resolve<true, false>), (unsigned)div_up(m, RS_TILE), RS_THREADS, 0, v, bits, k0, !circular, (const uint32_t *)cur.a[0],
-	             (const uint32_t *)cur.a[1], (const uint8_t *)cur.aux, m, alt.a[1], hflag.get(), fo, counters.get());
+	             (const uint32_t *)cur.a[1], (const uint8_t *)cur.aux, m, 0u, alt.a[1], hflag.get(), fo, counters.get());
 	std::vector<unsigned long long> hcs(4 * RS_CSLOTS);
 	B3M_CUDA(cudaMemcpyAsync(hcs.data(), counters.get(), 32 * RS_CSLOTS, cudaMemcpyDeviceToHost, st.s));
 	B3M_CUDA(cudaStreamSynchronize(st.s));
@@ -412,7 +415,7 @@ uint64_t k2_sort_keyrange(Stream & st, DevText const & T, int circular, KeyRange
 }
 
 void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W, int circular, int text_wraps,
-                    DevBuf<uint32_t> & sa_buf, uint32_t * rank, SortStats * stats, const FusedOut * fo) {
+                    DevBuf<uint32_t> & sa_buf, uint32_t * rank, SortStats * stats, const FusedOut * fo, StreamOut * so) {
 	if (W == 0) return;
 	B3M_REQUIRE(W < 0xFFFFFF00ull, "window too large for 32-bit suffix indices");
 	B3M_REQUIRE(!fo || (wstart == 0 && W == T.ntext), "internal: fused outputs need the whole text in one window");
@@ -463,20 +466,37 @@ void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W,
 		unsigned long long hc[4];
 		if (fo) {
 			// fused: emit BWT / anchors / samples and skip the order; it is only needed if something stays unresolved
-			B3M_LAUNCH_T(st, "resolve_extract", W * 10ull, (k_resolve<true, false>), rgrid, RS_THREADS, 0, v, bits, k0, lin, (const uint32_t *)cur.a[0],
-			             (const uint32_t *)cur.a[1], (const uint8_t *)cur.aux, W, alt.a[1], hflag.get(), *fo, counters.get());
+			bool const stream_sa = so && so->host_sa && fo->sa_s && st.copy && rgrid >= 64;
+			unsigned const nchunks = stream_sa ? 8u : 1u;
+			for (unsigned c = 0; c < nchunks; ++c) {
+				unsigned const t_lo = (unsigned)((uint64_t)rgrid * c / nchunks), t_hi = (unsigned)((uint64_t)rgrid * (c + 1) / nchunks);
+				B3M_LAUNCH_T(st, "resolve_extract", (uint64_t)(t_hi - t_lo) * RS_TILE * 10ull, (k_resolve<true, false>), t_hi - t_lo, RS_THREADS, 0, v, bits, k0, lin,
+				             (const uint32_t *)cur.a[0], (const uint32_t *)cur.a[1], (const uint8_t *)cur.aux, W, t_lo, alt.a[1], hflag.get(), *fo, counters.get());
+				if (stream_sa) {
+					// rows below t_hi * RS_TILE + shift are final once these tiles are done: their SA samples go to the host now
+					uint64_t const rows_lo = c ? (uint64_t)t_lo * RS_TILE + fo->shift : 0, rows_hi = (c + 1 == nchunks) ? W + fo->shift : (uint64_t)t_hi * RS_TILE + fo->shift;
+					uint64_t const k_lo = div_up(rows_lo, 1ull << fo->salog), k_hi = std::min<uint64_t>(div_up(rows_hi, 1ull << fo->salog), so->nsa);
+					cudaEvent_t ev;
+					B3M_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+					B3M_CUDA(cudaEventRecord(ev, st.s));
+					B3M_CUDA(cudaStreamWaitEvent(st.copy, ev, 0));
+					B3M_CUDA(cudaEventDestroy(ev));
+					if (k_hi > k_lo) B3M_CUDA(cudaMemcpyAsync(so->host_sa + k_lo, fo->sa_s + k_lo, (k_hi - k_lo) * 8, cudaMemcpyDeviceToHost, st.copy));
+				}
+			}
 			read_counters(hc);
 			S.other_bytes += W * 10ull + 32ull * hc[2];
+			if (stream_sa) so->delivered = hc[0] == 0; // otherwise the samples are rewritten after the doubling rounds
 			if (hc[0]) {
 				B3M_CUDA(cudaMemsetAsync(counters.get(), 0, 32 * RS_CSLOTS, st.s));
 				B3M_LAUNCH_T(st, "resolve", rbytes, (k_resolve<false, true>), rgrid, RS_THREADS, 0, v, bits, k0, lin, (const uint32_t *)cur.a[0],
-				             (const uint32_t *)cur.a[1], (const uint8_t *)cur.aux, W, alt.a[1], hflag.get(), FusedOut(), counters.get());
+				             (const uint32_t *)cur.a[1], (const uint8_t *)cur.aux, W, 0u, alt.a[1], hflag.get(), FusedOut(), counters.get());
 				read_counters(hc);
 				S.other_bytes += rbytes + 32ull * hc[2];
 			}
 		} else {
 			B3M_LAUNCH_T(st, "resolve", rbytes, (k_resolve<false, true>), rgrid, RS_THREADS, 0, v, bits, k0, lin, (const uint32_t *)cur.a[0],
-			             (const uint32_t *)cur.a[1], (const uint8_t *)cur.aux, W, alt.a[1], hflag.get(), FusedOut(), counters.get());
+			             (const uint32_t *)cur.a[1], (const uint8_t *)cur.aux, W, 0u, alt.a[1], hflag.get(), FusedOut(), counters.get());
 			read_counters(hc);
 			S.other_bytes += rbytes + 32ull * hc[2];
 		}

@@ -128,6 +128,9 @@ typedef struct b3m_build_params {
 	int bwtonly;
 	uint64_t largelcpthres;
 	int sampling;              /* B3M_SAMPLING_*: how the sampled SA/ISA are obtained */
+	uint64_t * host_sa;        /* optional PINNED host buffer of ceil(n/sasamplingrate) values: the sampled SA is copied
+	                            * there while the build is still running (one block, direct sampling); a later
+	                            * b3m_engine_fetch with the same pointer does not copy again.  NULL: off */
 } b3m_build_params;
 /* AUTO: straight from the suffix array when the build holds all of it (one block), by the LF walk
  * from the anchors (the reference's method, /root/reference/src/hwtPreIsaToIsa.cpp:114-161)

@@ -183,3 +183,33 @@ def test_tail_within_second_key(eng, oracle):
             t = oracle.decode_pac(data.tobytes(), term=True)
             res, info = run(eng, data, "pacterm", preisarate=1, sasamplingrate=1, isasamplingrate=1)
             _check_all(oracle, res, t, 1, 1, 1)
+
+
+def test_sa_streamed_to_pinned_host(oracle):
+    """b3m_build_params.host_sa: the sampled SA is delivered to a pinned host buffer during the build
+    (chunks of the last sorting step) and equals the fetched one; also on the prefix-doubling path."""
+    import torch
+    from bwtb3m_b200 import Engine
+    rng = np.random.default_rng(41)
+    e = Engine(0)
+    try:
+        for kind in ("random", "repeats"):
+            if kind == "random":
+                bases = rng.integers(0, 4, size=1_500_003, dtype=np.uint8)
+            else:
+                u = rng.integers(0, 4, size=40_000, dtype=np.uint8)
+                bases = np.concatenate([u, u[:30_000], rng.integers(0, 4, size=300_000, dtype=np.uint8), u])
+            pac = oracle.encode_pac(bases)
+            e.load_host(pac, "pacterm")
+            n = bases.size + 1
+            host = torch.full(((n + 31) // 32,), -1, dtype=torch.int64).pin_memory()
+            e.build(sasamplingrate=32, isasamplingrate=64, host_sa_ptr=host.data_ptr())
+            info = e.info()
+            assert (info["sort_unresolved0"] > 0) == (kind == "repeats")
+            res = e.fetch()
+            assert np.array_equal(host.numpy().astype(np.uint64), res["sa"])
+            t = oracle.decode_pac(pac.tobytes(), term=True)
+            sa = oracle.sa_circular(t)
+            assert np.array_equal(res["sa"], sa[::32].astype(np.uint64))
+    finally:
+        e.close()
