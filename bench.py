@@ -187,10 +187,10 @@ def run_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     state = {"drv": None, "strategy": "single"}
 
-    def build(host_sa_ptr=0):
+    def build(host_sa_ptr=0, host_bwa_ptr=0):
         if world == 1:
-            # e2e leg: the sampled SA lands in the caller's pinned buffer while the last sorting step still runs
-            eng.build(numblocks=args.numblocks, host_sa_ptr=host_sa_ptr, **params)
+            # e2e leg: the sampled SA and BWA's packed BWT land in the caller's pinned buffers while the last sorting step still runs
+            eng.build(numblocks=args.numblocks, host_sa_ptr=host_sa_ptr, host_bwa_ptr=host_bwa_ptr, **params)
         else:
             state["drv"], res = multigpu.build_distributed(eng, local_blocks=args.numblocks, driver=state["drv"], strategy=args.strategy, **params)
             state["strategy"] = res["strategy"]
@@ -253,7 +253,7 @@ def run_ours(args):
 
         def step_e2e():
             eng.load_host_ptr(host_in.data_ptr(), host_in.numel(), itype)
-            build(out["sa"].data_ptr() if (rank == 0 and info["nsa"]) else 0)
+            build(out["sa"].data_ptr() if (rank == 0 and info["nsa"]) else 0, out["bwt"].data_ptr() if (rank == 0 and as_bwa) else 0)
             if rank == 0:
                 if as_bwa:
                     eng.fetch_bwa(out_ptr=out["bwt"].data_ptr())

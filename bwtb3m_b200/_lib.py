@@ -19,6 +19,7 @@ class BuildParams(C.Structure):
         ("largelcpthres", C.c_uint64),
         ("sampling", C.c_int),
         ("host_sa", C.c_void_p),
+        ("host_bwa", C.c_void_p),
     ]
 
 

@@ -39,7 +39,7 @@ void Engine::reset_results() {
 	ssa_only = false;
 	bwt.release(); prerank.release(); sa.release(); isa.release(); dict.release();
 	D = DevDict();
-	sa_on_host = nullptr;
+	sa_on_host = nullptr; bwa_on_host = nullptr; bwa_words.release();
 	have_results = false;
 }
 
@@ -252,6 +252,12 @@ void Engine::build(b3m_build_params const & p) {
 		}
 		StreamOut so;
 		if (direct && p.host_sa) { so.host_sa = (unsigned long long *)p.host_sa; so.nsa = nsa; }
+		if (T.has_term) // rank 0 is the terminator suffix (text position ntext); its predecessor is the last base
+			B3M_CUDA(cudaMemcpyAsync(bwt.get(), T.codes + T.ntext - 1, 1, cudaMemcpyDeviceToDevice, st.s));
+		if (p.host_bwa && T.has_term && T.sigma <= 4) {
+			bwa_words.alloc(st, (T.ntext + 15) / 16 + 1);
+			so.host_bwa = p.host_bwa; so.d_bwa = bwa_words.get();
+		}
 		{
 			DevBuf<uint32_t> dsa;
 			k2_suffix_sort(st, T, 0, W, T.has_term ? 0 : 1, 0, dsa, nullptr, &sortstats, &fo, &so);
@@ -263,9 +269,12 @@ void Engine::build(b3m_build_params const & p) {
 			if (T.has_term) so.host_sa[0] = T.ntext; // the terminator suffix, set on the device below
 			sa_on_host = (uint64_t *)so.host_sa;
 		}
+		if (so.host_bwa) {
+			B3M_CUDA(cudaStreamSynchronize(st.copy));
+			if (so.bwa_delivered) bwa_on_host = so.host_bwa; // otherwise b3m_engine_fetch_bwa packs and copies as usual
+			bwa_words.release();
+		}
 		if (T.has_term) {
-			// rank 0 is the terminator suffix (text position ntext); its predecessor is the last base
-			B3M_CUDA(cudaMemcpyAsync(bwt.get(), T.codes + T.ntext - 1, 1, cudaMemcpyDeviceToDevice, st.s));
 			uint64_t const zero = 0, pos = T.ntext;
 			if ((T.ntext & (prerate - 1)) == 0) B3M_CUDA(cudaMemsetAsync(prerank.get() + T.ntext / prerate, 0, 4, st.s));
 			if (direct) {

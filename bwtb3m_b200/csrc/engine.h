@@ -65,6 +65,8 @@ struct Engine {
 	DevBuf<uint8_t> bwt;        // n dense codes (terminator row holds code 0, see root_exc_pos)
 	DevBuf<uint32_t> prerank;   // rank of positions 0, prerate, 2*prerate, ...
 	DevBuf<uint64_t> sa, isa;
+	uint32_t * bwa_on_host = nullptr; // likewise BWA's packed BWT words (b3m_build_params.host_bwa)
+	DevBuf<uint32_t> bwa_words;
 	uint64_t * sa_on_host = nullptr; // host buffer that already holds the sampled SA of the last build (b3m_build_params.host_sa)
 	DevBuf<uint8_t> dict;
 	DevBuf<uint32_t> d_special;

@@ -69,7 +69,13 @@ struct StreamOut {
 	unsigned long long * host_sa = nullptr; // nsa values
 	uint64_t nsa = 0;
 	bool delivered = false;                 // set when host_sa holds every value but [0] of a terminated text
+	// BWA's packed BWT (terminated texts): needs the row of the suffix at position 0 (primary) before the
+	// rows behind it can be packed, so the sort resolves that suffix's tile first
+	uint32_t * host_bwa = nullptr;          // ceil((n-1)/16) words
+	uint32_t * d_bwa = nullptr;             // device staging buffer of the same size
+	bool bwa_delivered = false;
 };
+void k9_pack_bwa_range(cudaStream_t s, const uint8_t * bwt, uint64_t seq_len, uint64_t primary, uint32_t * words, uint64_t w_lo, uint64_t w_hi);
 
 // Sorts the W suffixes that start at text positions wstart+i, 0 <= i < W.
 // circular != 0: W == ntext, wstart == 0, indices wrap (terminator-free whole text).

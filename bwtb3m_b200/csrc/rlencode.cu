@@ -162,8 +162,8 @@ void Engine::symbols_device(DevBuf<uint8_t> & out) {
 // move up by one.  pacterm codes 0..3 are BWA's A,C,G,T.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_pack_bwa(const uint8_t * __restrict__ bwt, uint64_t seq_len, uint64_t primary, uint32_t * __restrict__ words, uint64_t nwords) {
-	uint64_t const w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+k_pack_bwa(const uint8_t * __restrict__ bwt, uint64_t seq_len, uint64_t primary, uint32_t * __restrict__ words, uint64_t w_lo, uint64_t nwords) {
+	uint64_t const w = w_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (w >= nwords) return;
 	uint64_t const k0 = w << 4;
 	uint32_t acc = 0;
@@ -182,6 +182,13 @@ k_pack_bwa(const uint8_t * __restrict__ bwt, uint64_t seq_len, uint64_t primary,
 	words[w] = acc;
 }
 
+// words [w_lo, w_hi) on any stream (used while the sort is still emitting later rows)
+void k9_pack_bwa_range(cudaStream_t s, const uint8_t * bwt, uint64_t seq_len, uint64_t primary, uint32_t * words, uint64_t w_lo, uint64_t w_hi) {
+	if (w_hi <= w_lo) return;
+	k_pack_bwa<<<(unsigned)div_up(w_hi - w_lo, 256), 256, 0, s>>>(bwt, seq_len, primary, words, w_lo, w_hi);
+	B3M_CUDA(cudaGetLastError());
+}
+
 void Engine::fetch_bwa(uint32_t * h_words, uint64_t cap, uint64_t * primary, uint64_t * L2, uint64_t * seq_len_out) {
 	B3M_CUDA(cudaSetDevice(device));
 	B3M_REQUIRE(have_results && !ssa_only, "no BWT to export");
@@ -191,10 +198,10 @@ void Engine::fetch_bwa(uint32_t * h_words, uint64_t cap, uint64_t * primary, uin
 	if (seq_len_out) *seq_len_out = seq_len;
 	if (primary) *primary = root_exc_pos;
 	if (L2) { L2[0] = 0; for (int c = 0; c < 4; ++c) L2[c + 1] = L2[c] + codehist[c]; }
-	if (!h_words) return;
+	if (!h_words || h_words == bwa_on_host) return; // already delivered during the build (b3m_build_params.host_bwa)
 	B3M_REQUIRE(cap >= nwords, "BWA word buffer too small");
 	DevBuf<uint32_t> words(st, nwords);
-	B3M_LAUNCH_T(st, "pack_bwa", T.n + 4 * nwords, k_pack_bwa, (unsigned)div_up(nwords, 256), 256, 0, (const uint8_t *)bwt.get(), seq_len, (uint64_t)root_exc_pos, words.get(), nwords);
+	B3M_LAUNCH_T(st, "pack_bwa", T.n + 4 * nwords, k_pack_bwa, (unsigned)div_up(nwords, 256), 256, 0, (const uint8_t *)bwt.get(), seq_len, (uint64_t)root_exc_pos, words.get(), (uint64_t)0, nwords);
 	B3M_CUDA(cudaMemcpyAsync(h_words, words.get(), 4 * nwords, cudaMemcpyDeviceToHost, st.s));
 	B3M_CUDA(cudaStreamSynchronize(st.s));
 }

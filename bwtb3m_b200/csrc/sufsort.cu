@@ -234,6 +234,13 @@ k_resolve(TextView v, unsigned bits, unsigned k0, int lin, const uint32_t * __re
 		atomicAdd(&counters[(tile % RS_CSLOTS) * 4 + threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
 }
 
+// first place whose key is not below `key0` (the records are sorted by key)
+__global__ void k_lower_bound(const uint32_t * __restrict__ key, uint32_t n, uint32_t key0, uint32_t * __restrict__ out) {
+	uint32_t lo = 0, hi = n;
+	while (lo < hi) { uint32_t const mid = lo + ((hi - lo) >> 1); if (key[mid] < key0) lo = mid + 1; else hi = mid; }
+	*out = lo;
+}
+
 static double wall_ms() {
 	struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
 	return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
@@ -467,26 +474,64 @@ void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W,
 		if (fo) {
 			// fused: emit BWT / anchors / samples and skip the order; it is only needed if something stays unresolved
 			bool const stream_sa = so && so->host_sa && fo->sa_s && st.copy && rgrid >= 64;
-			unsigned const nchunks = stream_sa ? 8u : 1u;
+			// BWA words: find the row of the suffix at position 0 first (its tile is resolved ahead of the rest:
+			// resolving a tile twice writes the same values), then every chunk of rows can be packed and sent
+			bool stream_bwa = so && so->host_bwa && so->d_bwa && fo->has_term && st.copy && rgrid >= 64 && bits == 2 && W >= 64;
+			uint64_t primary = 0;
+			if (stream_bwa) {
+				uint32_t key0 = 0;
+				{ // the first key of the suffix at position 0, from the packed text (W >= 64: no padding)
+					uint64_t w0 = 0;
+					B3M_CUDA(cudaMemcpyAsync(&w0, v.packed, 8, cudaMemcpyDeviceToHost, st.s));
+					B3M_CUDA(cudaStreamSynchronize(st.s));
+					key0 = (uint32_t)(w0 >> 32);
+				}
+				B3M_LAUNCH(st, k_lower_bound, 1, 1, 0, (const uint32_t *)cur.a[0], (uint32_t)W, key0, d_total);
+				uint32_t const lb = fetch_u32(st, d_total);
+				unsigned const t0 = lb / RS_TILE, tn = std::min<unsigned>(2u, rgrid - t0);
+				B3M_CUDA(cudaMemsetAsync(fo->special, 0xff, 8, st.s));
+				B3M_LAUNCH_T(st, "resolve_extract", (uint64_t)tn * RS_TILE * 10ull, (k_resolve<true, false>), tn, RS_THREADS, 0, v, bits, k0, lin,
+				             (const uint32_t *)cur.a[0], (const uint32_t *)cur.a[1], (const uint8_t *)cur.aux, W, t0, alt.a[1], hflag.get(), *fo, counters.get());
+				uint32_t const row0 = fetch_u32(st, fo->special);
+				if (row0 == 0xffffffffu) stream_bwa = false; // in a run too long for the CTA: no early primary
+				else primary = row0;
+				B3M_CUDA(cudaMemsetAsync(counters.get(), 0, 32 * RS_CSLOTS, st.s)); // those tiles are counted again below
+			}
+			uint64_t const seq_len = W, nwords_bwa = (W + 15) >> 4; // terminated text: n - 1 = W bases
+			uint64_t words_done = 0;
+			unsigned const nchunks = (stream_sa || stream_bwa) ? 8u : 1u;
 			for (unsigned c = 0; c < nchunks; ++c) {
 				unsigned const t_lo = (unsigned)((uint64_t)rgrid * c / nchunks), t_hi = (unsigned)((uint64_t)rgrid * (c + 1) / nchunks);
 				B3M_LAUNCH_T(st, "resolve_extract", (uint64_t)(t_hi - t_lo) * RS_TILE * 10ull, (k_resolve<true, false>), t_hi - t_lo, RS_THREADS, 0, v, bits, k0, lin,
 				             (const uint32_t *)cur.a[0], (const uint32_t *)cur.a[1], (const uint8_t *)cur.aux, W, t_lo, alt.a[1], hflag.get(), *fo, counters.get());
-				if (stream_sa) {
-					// rows below t_hi * RS_TILE + shift are final once these tiles are done: their SA samples go to the host now
+				if (stream_sa || stream_bwa) {
+					// rows below t_hi * RS_TILE + shift are final once these tiles are done: their SA samples and BWA words go to the host now
 					uint64_t const rows_lo = c ? (uint64_t)t_lo * RS_TILE + fo->shift : 0, rows_hi = (c + 1 == nchunks) ? W + fo->shift : (uint64_t)t_hi * RS_TILE + fo->shift;
-					uint64_t const k_lo = div_up(rows_lo, 1ull << fo->salog), k_hi = std::min<uint64_t>(div_up(rows_hi, 1ull << fo->salog), so->nsa);
 					cudaEvent_t ev;
 					B3M_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
 					B3M_CUDA(cudaEventRecord(ev, st.s));
 					B3M_CUDA(cudaStreamWaitEvent(st.copy, ev, 0));
 					B3M_CUDA(cudaEventDestroy(ev));
-					if (k_hi > k_lo) B3M_CUDA(cudaMemcpyAsync(so->host_sa + k_lo, fo->sa_s + k_lo, (k_hi - k_lo) * 8, cudaMemcpyDeviceToHost, st.copy));
+					if (stream_sa) {
+						uint64_t const k_lo = div_up(rows_lo, 1ull << fo->salog), k_hi = std::min<uint64_t>(div_up(rows_hi, 1ull << fo->salog), so->nsa);
+						if (k_hi > k_lo) B3M_CUDA(cudaMemcpyAsync(so->host_sa + k_lo, fo->sa_s + k_lo, (k_hi - k_lo) * 8, cudaMemcpyDeviceToHost, st.copy));
+					}
+					if (stream_bwa) {
+						// word w reads the rows 16w .. 16w+16 (one further behind the primary)
+						uint64_t const w_hi = (c + 1 == nchunks) ? nwords_bwa : (rows_hi >= 17 ? std::min<uint64_t>((rows_hi - 17) / 16 + 1, nwords_bwa) : 0);
+						if (w_hi > words_done) {
+							k9_pack_bwa_range(st.copy, fo->bwt, seq_len, primary, so->d_bwa, words_done, w_hi);
+							++st.launches;
+							B3M_CUDA(cudaMemcpyAsync(so->host_bwa + words_done, so->d_bwa + words_done, (w_hi - words_done) * 4, cudaMemcpyDeviceToHost, st.copy));
+							words_done = w_hi;
+						}
+					}
 				}
 			}
 			read_counters(hc);
 			S.other_bytes += W * 10ull + 32ull * hc[2];
 			if (stream_sa) so->delivered = hc[0] == 0; // otherwise the samples are rewritten after the doubling rounds
+			if (stream_bwa) so->bwa_delivered = hc[0] == 0;
 			if (hc[0]) {
 				B3M_CUDA(cudaMemsetAsync(counters.get(), 0, 32 * RS_CSLOTS, st.s));
 				B3M_LAUNCH_T(st, "resolve", rbytes, (k_resolve<false, true>), rgrid, RS_THREADS, 0, v, bits, k0, lin, (const uint32_t *)cur.a[0],

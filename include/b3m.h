@@ -131,6 +131,8 @@ typedef struct b3m_build_params {
 	uint64_t * host_sa;        /* optional PINNED host buffer of ceil(n/sasamplingrate) values: the sampled SA is copied
 	                            * there while the build is still running (one block, direct sampling); a later
 	                            * b3m_engine_fetch with the same pointer does not copy again.  NULL: off */
+	uint32_t * host_bwa;       /* likewise (pacterm, one block): PINNED host buffer of ceil((n-1)/16) words that receives
+	                            * BWA's packed BWT (see b3m_engine_fetch_bwa) while the build runs.  NULL: off */
 } b3m_build_params;
 /* AUTO: straight from the suffix array when the build holds all of it (one block), by the LF walk
  * from the anchors (the reference's method, /root/reference/src/hwtPreIsaToIsa.cpp:114-161)

@@ -185,8 +185,8 @@ def test_tail_within_second_key(eng, oracle):
             _check_all(oracle, res, t, 1, 1, 1)
 
 
-def test_sa_streamed_to_pinned_host(oracle):
-    """b3m_build_params.host_sa: the sampled SA is delivered to a pinned host buffer during the build
+def test_results_streamed_to_pinned_host(oracle):
+    """b3m_build_params.host_sa / host_bwa: the sampled SA and BWA's packed BWT are delivered to a pinned host buffer during the build
     (chunks of the last sorting step) and equals the fetched one; also on the prefix-doubling path."""
     import torch
     from bwtb3m_b200 import Engine
@@ -203,11 +203,17 @@ def test_sa_streamed_to_pinned_host(oracle):
             e.load_host(pac, "pacterm")
             n = bases.size + 1
             host = torch.full(((n + 31) // 32,), -1, dtype=torch.int64).pin_memory()
-            e.build(sasamplingrate=32, isasamplingrate=64, host_sa_ptr=host.data_ptr())
+            hbwa = torch.full(((n - 1 + 15) // 16,), -1, dtype=torch.int32).pin_memory()
+            e.build(sasamplingrate=32, isasamplingrate=64, host_sa_ptr=host.data_ptr(), host_bwa_ptr=hbwa.data_ptr())
             info = e.info()
             assert (info["sort_unresolved0"] > 0) == (kind == "repeats")
             res = e.fetch()
             assert np.array_equal(host.numpy().astype(np.uint64), res["sa"])
+            words, primary, l2, seq_len = e.fetch_bwa()  # packed again into a fresh buffer
+            if kind == "random":
+                assert np.array_equal(hbwa.numpy().view(np.uint32), words)  # delivered during the build
+            e.fetch_bwa(out_ptr=hbwa.data_ptr())  # no-op when delivered, a normal fetch otherwise
+            assert np.array_equal(hbwa.numpy().view(np.uint32), words)
             t = oracle.decode_pac(pac.tobytes(), term=True)
             sa = oracle.sa_circular(t)
             assert np.array_equal(res["sa"], sa[::32].astype(np.uint64))
