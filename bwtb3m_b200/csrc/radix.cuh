@@ -1,17 +1,24 @@
-// LSD radix sort on records held as NA parallel uint32 arrays (structure of arrays), 8-bit
-// digits, one kernel per digit ("onesweep"): each CTA takes the next tile from a ticket counter,
-// ranks its records stably in shared memory (8 ballots per record find equal digits inside a
-// warp), obtains its global offsets by decoupled look-back over the tile status words of its
-// predecessors, reorders through shared memory and writes coalesced runs.
+// LSD radix sort on records held as NA parallel uint32 arrays (structure of arrays) plus an
+// optional aux byte, 8-bit digits, one kernel per digit ("onesweep"): each CTA (512 threads,
+// 16 records per thread) takes the next 8192-record tile from a ticket counter, ranks its records
+// stably (eight ballots per record, their predicates from one R2P, find the lanes with an equal
+// digit; 16-bit per-warp counters in shared memory), obtains its global offsets by decoupled
+// look-back over the tile status words of its predecessors, reorders through shared memory and
+// writes runs of records that share a digit.  The only partial tile is a launch of its own, so the
+// main kernel carries no bounds checks.  For suffix sorting the first pass builds its records
+// straight from the 2-bit packed text (radix_sort_suffix_keys).
 //
-// Why not __match_any_sync: MATCH runs on the ADU pipe; a first version measured 98% ADU
-// utilisation and 7% of HBM peak, and in this kernel it takes a pass from 20.2 to 27.5 ms
-// (3.1 G records, B200).
+// Measured at 3.1 G records on a B200: 20.2 ms per pass = 42 % of HBM peak,
+// 16.4 ms on already sorted input, 25 ms with 4096-record tiles, 21.8 ms with 16384-record tiles
+// at one CTA per SM, 27.5 ms with __match_any_sync instead of the ballots (MATCH runs on the ADU
+// pipe).  What bounds it is instruction issue and shared-memory wavefronts (45 % of them bank
+// conflicts of the scatter into sorted order), not DRAM.
 // Forward progress: tickets are handed out in launch order, so every predecessor of a tile is
 // already resident or finished when the tile starts to look back.
 //
-// Algorithmic HBM bytes per pass and record: 4*NA read + 4*NA write, plus one
-// 4-byte key read per radix_sort_bits() call for the digit histograms.
+// Algorithmic HBM bytes per pass and record: 4*NA (+1 aux) read and the same
+// written, plus one 4-byte key read per radix_sort_bits() call for the digit histograms (the
+// suffix-key sort gets all four histograms from one pass over the packed text, k_hist_4mers).
 #pragma once
 #include "common.cuh"
 #include "scan.cuh"

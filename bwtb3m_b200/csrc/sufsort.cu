@@ -4,16 +4,22 @@
 // BWT[i] = s[(SA[i]+n-1)%n] (/root/reference/src/lcpbit.cpp:3668-3669).
 //
 // Round 0   LSD radix sort (radix.cuh) of all W suffixes by a 32-bit key holding their first
-//           k0 = 32/keybits symbols.
-// Resolve   k_resolve: one pass over the sorted (key, index) pairs.  Runs of equal keys of up to
-//           RS_EXT suffixes are sorted inside the CTA by the symbols carried in the aux byte and,
-//           where those tie, by their next 64 key bits read from the text; with the whole text in one window the same pass emits the BWT, the anchors
-//           and the sampled SA/ISA (FusedOut).  On random DNA this finishes the sort: no
-//           rank-by-position array is ever written.
-// Doubling  only if some suffixes are still tied (repeats longer than k0 + 64/keybits symbols,
-//           or runs longer than RS_EXT): classic prefix doubling on the tied suffixes only --
-//           gather the rank of the suffix h symbols ahead, radix sort (group, rank ahead),
-//           split the groups; h doubles.
+//           k0 = 32/keybits symbols; every record also carries its index and an aux byte (the
+//           symbol before the suffix + the symbols right behind the key).  For 2-bit alphabets
+//           the first pass makes the records from the packed text.
+// Resolve   k_resolve: one pass over the sorted records.  Runs of equal keys of up to RS_EXT
+//           suffixes are sorted inside the CTA by the symbols carried in the aux byte and, where
+//           those tie, by their next 64 key bits read from the text.  With the whole text in one
+//           window the same pass emits the BWT, the anchors and the sampled SA/ISA (FusedOut),
+//           in chunks, so that finished rows can leave for the host while later chunks run
+//           (StreamOut).  On random DNA this finishes the sort: no rank-by-position array is
+//           ever written.
+// Doubling  only if some suffixes are still tied (repeats longer than k0 + nx + 64/keybits
+//           symbols, or runs longer than RS_EXT): classic prefix doubling on the tied suffixes
+//           only -- gather the rank of the suffix h symbols ahead, radix sort (group, rank
+//           ahead), split the groups; h doubles.
+// Sharding  k2_keyrange_plan / k2_sort_keyrange: the same on one key range of the suffixes
+//           (multi-GPU, one range per rank).
 #include "kernels.h"
 #include "radix.cuh"
 #include "scan.cuh"

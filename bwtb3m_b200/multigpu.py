@@ -276,7 +276,13 @@ def build_sharded(engine, preisarate=0, sasamplingrate=32, isasamplingrate=26214
     world = dist.get_world_size() if world is None else world
     buf = buffers or ShardBuffers(engine, preisarate, sasamplingrate, isasamplingrate, bwtonly)
     if buffers is not None:
-        buf.zero_()
+        if world > 1 and hasattr(engine, "shard_rows"):
+            # reused buffers: only the summed (sparse) ones must start from zero, the dense slices are overwritten
+            for t in (buf.prerank, buf.isa, buf.special):
+                if t is not None:
+                    t.zero_()
+        else:
+            buf.zero_()
     unres = engine.shard_build(rank, world, *buf.ptrs(), preisarate=buf.prerate, sasamplingrate=sasamplingrate,
                                isasamplingrate=isasamplingrate, bwtonly=bwtonly)
     flag = torch.tensor([unres], dtype=torch.int64, device=buf.device)
