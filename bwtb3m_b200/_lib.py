@@ -63,7 +63,7 @@ EXPORTS = [
     "b3m_engine_blk_begin", "b3m_engine_blk_build_range", "b3m_engine_blk_chains", "b3m_engine_blk_zranks", "b3m_engine_blk_gap",
     "b3m_engine_blk_merge", "b3m_engine_blk_merge_samples", "b3m_engine_blk_finish",
     "b3m_engine_default_preisarate", "b3m_engine_fetch_bwa",
-    "b3m_engine_shard_build", "b3m_engine_shard_finish", "b3m_engine_shard_rows",
+    "b3m_engine_shard_build", "b3m_engine_shard_finish", "b3m_engine_shard_rows", "b3m_engine_pack_rows", "b3m_engine_unpack_rows",
 ]
 
 _lib = None
@@ -101,6 +101,8 @@ def lib():
     L.b3m_engine_shard_build.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(BuildParams), vp, vp, vp, vp, vp, u64p]
     L.b3m_engine_shard_finish.argtypes = [vp, vp, vp, vp, vp, vp, C.c_uint32]
     L.b3m_engine_shard_rows.argtypes = [vp, C.c_uint32, u64p]
+    L.b3m_engine_pack_rows.argtypes = [vp, vp, u64, vp]
+    L.b3m_engine_unpack_rows.argtypes = [vp, vp, u64, vp]
     L.b3m_bwt_length.argtypes = [C.c_char_p, u64p, C.c_char_p, C.c_size_t]
     L.b3m_bwt_decode.argtypes = [C.c_char_p, vp, u64, u64, C.c_char_p, C.c_size_t]
     L.b3m_bwt_encode_host.argtypes = [C.c_char_p, vp, u64, C.c_char_p, C.c_size_t]

@@ -664,6 +664,12 @@ int b3m_engine_shard_build(b3m_engine * h, uint32_t part, uint32_t nparts, const
                            void * d_sa, void * d_isa, void * d_special, uint64_t * unresolved) {
 	B3M_GUARD(h, { if (!p) throw b3m::Error("null params"); h->e->kr_build_part(part, nparts, *p, d_bwt, d_prerank, d_sa, d_isa, d_special, unresolved); });
 }
+int b3m_engine_pack_rows(b3m_engine * h, const void * d_rows, uint64_t nrows, void * d_packed) {
+	B3M_GUARD(h, h->e->pack_rows(d_rows, nrows, d_packed, false));
+}
+int b3m_engine_unpack_rows(b3m_engine * h, const void * d_packed, uint64_t nrows, void * d_rows) {
+	B3M_GUARD(h, h->e->pack_rows(d_rows, nrows, const_cast<void *>(d_packed), true));
+}
 int b3m_engine_shard_rows(b3m_engine * h, uint32_t nparts, uint64_t * first_row) {
 	B3M_GUARD(h, h->e->kr_rows(nparts, first_row));
 }

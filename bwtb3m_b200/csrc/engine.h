@@ -115,6 +115,7 @@ struct Engine {
 	void kr_build_part(uint32_t part, uint32_t nparts, b3m_build_params const & p, void * d_bwt, void * d_prerank, void * d_sa, void * d_isa,
 	                   void * d_special, uint64_t * unresolved);
 	void kr_rows(uint32_t nparts, uint64_t * first);
+	void pack_rows(const void * d_rows, uint64_t nrows, void * d_packed, bool unpack);
 	void kr_finish(const void * d_bwt, const void * d_prerank, const void * d_sa, const void * d_isa, const void * d_special, uint32_t nparts);
 	// K8 / output side
 	uint64_t rl_bytes = 0, rl_nruns = 0;

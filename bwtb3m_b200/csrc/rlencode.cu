@@ -182,6 +182,37 @@ k_pack_bwa(const uint8_t * __restrict__ bwt, uint64_t seq_len, uint64_t primary,
 	words[w] = acc;
 }
 
+// ------------------------------------------------------------------------------------------
+// 2-bit transport packing of BWT rows (codes < 4) for the multi-GPU slice exchange: row lo+4q+j of
+// the slice sits in bits [2j, 2j+1] of byte q.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_pack_rows(const uint8_t * __restrict__ rows, uint64_t nrows, uint8_t * __restrict__ packed) {
+	uint64_t const q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= div_up(nrows, 4)) return;
+	uint32_t b = 0;
+	#pragma unroll
+	for (int j = 0; j < 4; ++j) if (4 * q + j < nrows) b |= (uint32_t)(rows[4 * q + j] & 3u) << (2 * j);
+	packed[q] = (uint8_t)b;
+}
+__global__ void __launch_bounds__(256)
+k_unpack_rows(const uint8_t * __restrict__ packed, uint64_t nrows, uint8_t * __restrict__ rows) {
+	uint64_t const q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= div_up(nrows, 4)) return;
+	uint32_t const b = packed[q];
+	#pragma unroll
+	for (int j = 0; j < 4; ++j) if (4 * q + j < nrows) rows[4 * q + j] = (uint8_t)((b >> (2 * j)) & 3u);
+}
+
+void Engine::pack_rows(const void * d_rows, uint64_t nrows, void * d_packed, bool unpack) {
+	B3M_CUDA(cudaSetDevice(device));
+	B3M_REQUIRE(loaded && T.sigma <= 4, "2-bit row packing needs an alphabet of at most four codes");
+	if (!nrows) return;
+	unsigned const grid = (unsigned)div_up(div_up(nrows, 4), 256);
+	if (unpack) B3M_LAUNCH(st, k_unpack_rows, grid, 256, 0, (const uint8_t *)d_packed, nrows, (uint8_t *)const_cast<void *>(d_rows));
+	else B3M_LAUNCH(st, k_pack_rows, grid, 256, 0, (const uint8_t *)d_rows, nrows, (uint8_t *)d_packed);
+}
+
 // words [w_lo, w_hi) on any stream (used while the sort is still emitting later rows)
 void k9_pack_bwa_range(cudaStream_t s, const uint8_t * bwt, uint64_t seq_len, uint64_t primary, uint32_t * words, uint64_t w_lo, uint64_t w_hi) {
 	if (w_hi <= w_lo) return;

@@ -124,6 +124,13 @@ class Engine:
         self._check(self._lib.b3m_engine_shard_rows(self._h, nparts, a))
         return [int(x) for x in a]
 
+    def pack_rows(self, rows_ptr, nrows, packed_ptr):
+        """2-bit transport packing of BWT rows; returns False when the alphabet has more than four codes."""
+        return self._lib.b3m_engine_pack_rows(self._h, C.c_void_p(rows_ptr), nrows, C.c_void_p(packed_ptr)) == 0
+
+    def unpack_rows(self, packed_ptr, nrows, rows_ptr):
+        self._check(self._lib.b3m_engine_unpack_rows(self._h, C.c_void_p(packed_ptr), nrows, C.c_void_p(rows_ptr)))
+
     def shard_finish(self, nparts, bwt_ptr, prerank_ptr, sa_ptr, isa_ptr, special_ptr):
         vp = lambda a: C.c_void_p(a) if a else None
         self._check(self._lib.b3m_engine_shard_finish(self._h, vp(bwt_ptr), vp(prerank_ptr), vp(sa_ptr), vp(isa_ptr), vp(special_ptr), nparts))

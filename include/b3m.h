@@ -245,6 +245,10 @@ int b3m_engine_shard_build(b3m_engine * e, uint32_t part, uint32_t nparts, const
  * [first_row[p], first_row[p+1]) of the BWT and the SA samples of the ranks in that interval, so the
  * dense results can travel as slices instead of a reduction over the whole arrays */
 int b3m_engine_shard_rows(b3m_engine * e, uint32_t nparts, uint64_t * first_row);
+/* transport packing of BWT rows for the slice exchange (alphabets of at most four codes): nrows
+ * codes <-> ceil(nrows/4) bytes, row 4q+j in bits [2j,2j+1] of byte q; fails for larger alphabets */
+int b3m_engine_pack_rows(b3m_engine * e, const void * d_rows, uint64_t nrows, void * d_packed);
+int b3m_engine_unpack_rows(b3m_engine * e, const void * d_packed, uint64_t nrows, void * d_rows);
 int b3m_engine_shard_finish(b3m_engine * e, const void * d_bwt, const void * d_prerank, const void * d_sa, const void * d_isa,
                             const void * d_special, uint32_t nparts);
 
