@@ -374,6 +374,25 @@ k_radix_onesweep(RadixPassArgs<NA> A, RadixTextSrc S, uint64_t n, int shift, uin
 	#undef RADIX_VALID
 }
 
+// radix_text_record with a short cut for the common case (2-bit packed text, the record away from
+// both ends): one 64-bit window starting one symbol before the suffix holds the preceding code
+// (2 bits), the key (32 bits) and the carried symbols (6 bits).
+__device__ __forceinline__ void radix_text_record_any(RadixTextSrc const & S, uint64_t t, uint32_t & key, uint32_t & idx, uint32_t & aux) {
+	if (S.bits == 2 && S.v.packed && t >= S.nshort) {
+		uint64_t const i = t - S.nshort;
+		uint64_t p = S.v.wstart + i;
+		if (S.v.text_wraps && p >= S.v.ntext) p -= S.v.ntext;
+		if (p >= 1 && i + 35 <= S.v.W && p + 35 <= S.v.ntext) {
+			uint64_t const w = pk_window(S.v.packed, p - 1);
+			key = (uint32_t)(w >> 30);
+			idx = (uint32_t)i;
+			aux = ((uint32_t)(w >> 62) << 6) | ((uint32_t)(w >> 24) & 63u);
+			return;
+		}
+	}
+	radix_text_record(S, t, key, idx, aux);
+}
+
 template <int NA, bool AUX>
 constexpr size_t radix_smem_bytes() { return (size_t)RADIX_TILE * (4 + (NA > 1 ? 4 : 0) + (AUX ? 1 : 0)); }
 

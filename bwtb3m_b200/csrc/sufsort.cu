@@ -291,44 +291,84 @@ k_keyrange_hist(RadixTextSrc S, unsigned long long * __restrict__ ghist /* [KR_B
 	for (int i = threadIdx.x; i < KR_BINS; i += blockDim.x) if (sh[i]) atomicAdd(&ghist[i], (unsigned long long)sh[i]);
 }
 
-// The records whose key bin lies in [blo, bhi), in input order: counts per tile (WRITE == false),
-// then, after an exclusive scan of the counts, the records themselves (WRITE == true).  Both
-// passes re-read the packed text (0.25 B/symbol), which is cheaper than a look-back chain over
-// 1.5 M small tiles.
-template <bool WRITE>
+// The records whose key bin lies in [blo, bhi), in input order, in two passes whose cost follows
+// the work: (1) one bit per record "in range" + counts per tile, read off the packed text as 4-mers
+// (a few instructions per position); (2) after an exclusive scan of the counts, every warp spreads
+// the set bits of its 1024 records evenly over its lanes (prefix sums + find-nth-set) and only
+// then builds and writes the records, so the expensive part is proportional to the range's size.
+// (The lanes first list the places of their own set bits in shared memory, at the offsets given
+// by a prefix sum of their popcounts.)
+constexpr int KR_FTILE = 8192; // records per CTA of both passes: 256 flag words
+
 __global__ void __launch_bounds__(256)
-k_keyrange_filter(RadixTextSrc S, uint32_t binshift, uint32_t blo, uint32_t bhi, uint32_t * __restrict__ tilecount, const uint32_t * __restrict__ tileoff,
+k_keyrange_flags(RadixTextSrc S, uint32_t binshift, uint32_t blo, uint32_t bhi, uint32_t * __restrict__ flags, uint32_t * __restrict__ tilecount) {
+	__shared__ uint32_t wsum[8];
+	uint64_t const t0 = ((uint64_t)blockIdx.x * 256 + threadIdx.x) * 32;
+	uint32_t m = 0;
+	if (t0 < S.v.W) {
+		uint64_t const i0 = t0 - S.nshort;
+		uint64_t p0 = S.v.wstart + i0;
+		if (S.v.text_wraps && p0 >= S.v.ntext) p0 -= S.v.ntext;
+		bool const fast = binshift == 24 && S.bits == 2 && S.v.packed && t0 >= S.nshort && i0 + 67 <= S.v.W && p0 + 67 <= S.v.ntext;
+		if (fast) {
+			uint64_t const a = pk_window(S.v.packed, p0), b = pk_window(S.v.packed, p0 + 32);
+			uint32_t const span = bhi - blo;
+			#pragma unroll
+			for (int s = 0; s < 32; ++s) {
+				uint32_t const kmer = (s <= 28 ? (uint32_t)(a >> (56 - 2 * s)) : (uint32_t)((a << (2 * s - 56)) | (b >> (120 - 2 * s)))) & 255u;
+				m |= (kmer - blo < span ? 1u : 0u) << s;
+			}
+		} else {
+			for (int s = 0; s < 32; ++s) {
+				uint64_t const t = t0 + s;
+				if (t >= S.v.W) break;
+				uint32_t key, idx, aux;
+				radix_text_record(S, t, key, idx, aux);
+				uint32_t const bin = key >> binshift;
+				m |= ((bin >= blo && bin < bhi) ? 1u : 0u) << s;
+			}
+		}
+		flags[t0 >> 5] = m;
+	}
+	uint32_t c = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(m));
+	if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+	__syncthreads();
+	if (threadIdx.x == 0) { uint32_t tot = 0; for (int i = 0; i < 8; ++i) tot += wsum[i]; tilecount[blockIdx.x] = tot; }
+}
+
+__global__ void __launch_bounds__(256)
+k_keyrange_gather(RadixTextSrc S, const uint32_t * __restrict__ flags, const uint32_t * __restrict__ tileoff,
                   uint32_t * __restrict__ okey, uint32_t * __restrict__ oidx, uint8_t * __restrict__ oaux) {
 	__shared__ uint32_t wtot[8];
+	__shared__ uint16_t s_list[8][1024];
 	unsigned const w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	uint64_t const t0 = (uint64_t)blockIdx.x * KR_TILE + (uint64_t)w * 256; // a warp owns 256 consecutive records
-	uint32_t key[8], aux[8];
-	radix_text_load<8>(S, t0, lane, key, aux);
-	uint32_t rowbase[8];
-	uint32_t mine = 0, total = 0;
+	uint64_t const tbase = (uint64_t)blockIdx.x * KR_FTILE + (uint64_t)w * 1024; // a warp owns 32 flag words
+	uint64_t const nwords = div_up(S.v.W, 32);
+	uint64_t const wi = (tbase >> 5) + lane;
+	uint32_t const m = wi < nwords ? flags[wi] : 0u;
+	uint32_t incl = (uint32_t)__popc(m);
 	#pragma unroll
-	for (int j = 0; j < 8; ++j) {
-		uint32_t const b = key[j] >> binshift;
-		bool const in = (t0 + j * 32 + lane < S.v.W) && b >= blo && b < bhi;
-		unsigned const m = __ballot_sync(0xffffffffu, in);
-		rowbase[j] = total + __popc(m & lanemask_lt());
-		if (in) mine |= 1u << j;
-		total += __popc(m);
-	}
+	for (int o = 1; o < 32; o <<= 1) { uint32_t const x = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += x; }
+	uint32_t const excl = incl - (uint32_t)__popc(m);
+	uint32_t const total = __shfl_sync(0xffffffffu, incl, 31);
 	if (lane == 0) wtot[w] = total;
 	__syncthreads();
-	if (!WRITE) {
-		if (threadIdx.x == 0) { uint32_t c = 0; for (int i = 0; i < 8; ++i) c += wtot[i]; tilecount[blockIdx.x] = c; }
-		return;
-	}
 	uint32_t off = tileoff[blockIdx.x];
 	for (unsigned i = 0; i < w; ++i) off += wtot[i];
-	#pragma unroll
-	for (int j = 0; j < 8; ++j)
-		if ((mine >> j) & 1u) {
-			uint32_t const o = off + rowbase[j];
-			okey[o] = key[j]; oidx[o] = radix_text_index(S, t0 + j * 32 + lane); oaux[o] = (uint8_t)aux[j];
-		}
+	// every lane lists the places of its own set bits behind those of the lanes below it ...
+	uint16_t * const list = s_list[w];
+	{
+		uint32_t mm = m, j = excl;
+		while (mm) { list[j++] = (uint16_t)(32u * lane + (uint32_t)__ffs((int)mm) - 1u); mm &= mm - 1u; }
+	}
+	__syncwarp();
+	// ... and the warp takes the listed records 32 at a time
+	for (uint32_t k = lane; k < total; k += 32) {
+		uint64_t const t = tbase + list[k];
+		uint32_t key, idx, aux;
+		radix_text_record_any(S, t, key, idx, aux);
+		okey[off + k] = key; oidx[off + k] = idx; oaux[off + k] = (uint8_t)aux;
+	}
 }
 
 void k2_keyrange_plan(Stream & st, DevText const & T, int circular, uint32_t nparts, KeyRangePlan & plan) {
@@ -389,16 +429,15 @@ uint64_t k2_sort_keyrange(Stream & st, DevText const & T, int circular, KeyRange
 	St.rounds = 1;
 	if (m == 0) return 0;
 	// stable compaction of the range's records out of the text
-	uint32_t const ntiles = (uint32_t)div_up(W, KR_TILE);
-	DevBuf<uint32_t> tcount(st, ntiles);
-	B3M_LAUNCH_T(st, "keyrange_count", W / 4, (k_keyrange_filter<false>), ntiles, 256, 0, S, plan.binshift, blo, bhi, tcount.get(), (const uint32_t *)nullptr,
-	             (uint32_t *)nullptr, (uint32_t *)nullptr, (uint8_t *)nullptr);
+	uint32_t const ntiles = (uint32_t)div_up(W, KR_FTILE);
+	DevBuf<uint32_t> tcount(st, ntiles), fl(st, (size_t)ntiles * (KR_FTILE / 32));
+	B3M_LAUNCH_T(st, "keyrange_flags", W / 4 + W / 8, k_keyrange_flags, ntiles, 256, 0, S, plan.binshift, blo, bhi, fl.get(), tcount.get());
 	scan_exclusive_inplace<OpSum>(st, tcount.get(), ntiles);
 	DevBuf<uint32_t> key0(st, m), key1(st, m), idx0(st, m), idx1(st, m);
 	DevBuf<uint8_t> aux0(st, m), aux1(st, m);
-	B3M_LAUNCH_T(st, "keyrange_write", W / 4 + 9 * m, (k_keyrange_filter<true>), ntiles, 256, 0, S, plan.binshift, blo, bhi, (uint32_t *)nullptr, (const uint32_t *)tcount.get(),
+	B3M_LAUNCH_T(st, "keyrange_gather", W / 8 + 9 * m, k_keyrange_gather, ntiles, 256, 0, S, (const uint32_t *)fl.get(), (const uint32_t *)tcount.get(),
 	             key0.get(), idx0.get(), aux0.get());
-	St.other_bytes += W / 2 + 9 * m;
+	St.other_bytes += W / 4 + W / 4 + 9 * m;
 	RadixRec<2> cur{{key0.get(), idx0.get()}, aux0.get()}, alt{{key1.get(), idx1.get()}, aux1.get()};
 	RadixStats rs;
 	radix_sort_bits<2>(st, cur, alt, 0, m, 0, 32, &rs);
