@@ -544,6 +544,73 @@ void Engine::ssa_from_bwt(const uint8_t * h_bwt, uint64_t n, const uint64_t * h_
 	have_results = true;
 }
 
+// ------------------------------------------------------------------------------------------
+// checkbwt (/root/reference/src/checkbwt.cpp:26-246) on the device: the text has been loaded
+// (K1); the BWT comes in the reference's symbol space, the anchors as (rank,pos) pairs.  Every
+// text position is compared exactly once; the symbol counts must agree as well.
+// ------------------------------------------------------------------------------------------
+uint64_t Engine::check_bwt(const uint8_t * h_bwt, uint64_t n, const uint64_t * h_pairs, uint64_t npairs, uint64_t * badrank) {
+	B3M_CUDA(cudaSetDevice(device));
+	B3M_REQUIRE(loaded, "no text loaded");
+	B3M_REQUIRE(npairs > 0, "no (rank,pos) anchors: the .preisa file is empty");
+	if (badrank) *badrank = ~0ull;
+	if (n != T.n) return n > T.n ? n : T.n; // lengths differ: nothing matches
+	reset_results();
+	// symbols -> the text's codes; the terminator of a terminated text is the exception row
+	int lut[256];
+	for (int c = 0; c < 256; ++c) lut[c] = -1;
+	for (uint32_t c = 0; c < T.sigma; ++c) lut[code2sym[c]] = (int)c;
+	std::vector<uint8_t> hc(n);
+	uint64_t cnt[256];
+	memset(cnt, 0, sizeof(cnt));
+	uint64_t exc = ~0ull, nterm = 0, unknown = 0;
+	for (uint64_t i = 0; i < n; ++i) {
+		uint8_t const sym = h_bwt[i];
+		if (T.has_term && sym == 0) { exc = i; ++nterm; hc[i] = 0; }
+		else if (lut[sym] < 0) { ++unknown; hc[i] = 0; }
+		else { hc[i] = (uint8_t)lut[sym]; cnt[lut[sym]]++; }
+	}
+	uint64_t histdiff = unknown + (T.has_term ? (nterm > 1 ? nterm - 1 : 1 - nterm) : 0);
+	for (uint32_t c = 0; c < T.sigma; ++c) histdiff += cnt[c] > codehist[c] ? cnt[c] - codehist[c] : codehist[c] - cnt[c];
+	if (histdiff) return histdiff; // a walk over a BWT with other symbol counts proves nothing more
+	bwt.alloc(st, n + 16);
+	B3M_CUDA(cudaMemcpyAsync(bwt.get(), hc.data(), n, cudaMemcpyHostToDevice, st.s));
+	B3M_CUDA(cudaStreamSynchronize(st.s));
+	make_dict(T.has_term ? (uint32_t)exc : 0xffffffffu, 0, 0);
+	std::vector<std::pair<uint64_t, uint64_t>> A(npairs);
+	for (uint64_t k = 0; k < npairs; ++k) {
+		A[k] = std::make_pair(h_pairs[2 * k + 1], h_pairs[2 * k]);
+		B3M_REQUIRE(A[k].first < n && A[k].second < n, "anchor out of range in .preisa");
+	}
+	std::sort(A.begin(), A.end());
+	std::vector<uint32_t> ar(npairs);
+	std::vector<uint64_t> ap(npairs), as(npairs);
+	for (uint64_t k = 0; k < npairs; ++k) {
+		uint64_t const prev = A[(k + npairs - 1) % npairs].first;
+		uint64_t todo = (A[k].first + n - prev) % n;
+		if (todo == 0) todo = npairs == 1 ? n : 0;
+		ar[k] = (uint32_t)A[k].second; ap[k] = A[k].first; as[k] = todo;
+	}
+	DevBuf<uint32_t> dar(st, npairs);
+	DevBuf<uint64_t> dap(st, npairs), das(st, npairs), dres(st, 2);
+	B3M_CUDA(cudaMemcpyAsync(dar.get(), ar.data(), 4 * npairs, cudaMemcpyHostToDevice, st.s));
+	B3M_CUDA(cudaMemcpyAsync(dap.get(), ap.data(), 8 * npairs, cudaMemcpyHostToDevice, st.s));
+	B3M_CUDA(cudaMemcpyAsync(das.get(), as.data(), 8 * npairs, cudaMemcpyHostToDevice, st.s));
+	B3M_CUDA(cudaMemsetAsync(dres.get(), 0, 16, st.s));
+	PhaseTimer pt(st);
+	pt.mark();
+	k7_check_walk(st, D, T.codes, T.ntext, T.has_term, dar.get(), dap.get(), das.get(), npairs, n, dres.get());
+	pt.mark();
+	uint64_t res[2];
+	B3M_CUDA(cudaMemcpyAsync(res, dres.get(), 16, cudaMemcpyDeviceToHost, st.s));
+	B3M_CUDA(cudaStreamSynchronize(st.s));
+	ms_walk = pt.ms(0, 1);
+	walkstats = WalkStats(); walkstats.steps = n; walkstats.chains = npairs;
+	if (badrank && res[0]) *badrank = res[1];
+	bwt.release(); dict.release(); D = DevDict();
+	return res[0];
+}
+
 __global__ void __launch_bounds__(256)
 k_pick_starts(const uint32_t * __restrict__ prerank, uint64_t npre, uint64_t nchains, uint32_t * __restrict__ start) {
 	uint64_t const q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -126,6 +126,8 @@ struct Engine {
 	void fetch_bwa(uint32_t * h_words, uint64_t cap, uint64_t * primary, uint64_t * L2, uint64_t * seq_len_out);
 	// sampled SA/ISA from an existing BWT and (rank,pos) anchors (bwtcomputessa path)
 	void ssa_from_bwt(const uint8_t * h_bwt, uint64_t n, const uint64_t * h_pairs, uint64_t npairs, uint64_t sarate, uint64_t isarate);
+	// checkbwt: verifies BWT symbols (reference symbol space) + anchors against the loaded text; returns mismatches
+	uint64_t check_bwt(const uint8_t * h_bwt, uint64_t n, const uint64_t * h_pairs, uint64_t npairs, uint64_t * badrank);
 	void make_dict(uint32_t exc_pos, uint32_t exc_code, uint32_t exc_lf);
 	void fetch(uint8_t * h_bwt, uint64_t * h_pairs, uint64_t * h_sa, uint64_t * h_isa);
 	void info(b3m_info * o);

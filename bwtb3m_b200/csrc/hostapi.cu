@@ -205,6 +205,43 @@ int b3m_compute_ssa(const char * bwtfn, uint64_t sasamplingrate, uint64_t isasam
 	catch (...) { set_err(err, errlen, "unknown error"); return 3; }
 }
 
+// checkbwt <in.bwt> <text>  (/root/reference/src/checkbwt.cpp:26-246): *ok = 1 iff the LF walk from the
+// anchors of <prefix>.preisa reproduces the text, every position compared once
+int b3m_check_bwt(const char * bwtfn, const char * textfn, const char * inputtype, uint64_t numthreads, int device, int verbose,
+                  int * ok, uint64_t * mismatches, char * err, size_t errlen) {
+	try {
+		if (!bwtfn || !*bwtfn || !textfn || !*textfn) throw Error("checkbwt needs a .bwt file and the text");
+		check_device_available();
+		int const itype = b3m_parse_inputtype(inputtype && *inputtype ? inputtype : "bytestream");
+		if (itype < 0) throw Error("unknown/unsupported input type");
+		double const t0 = now_sec();
+		std::string const prefix = clip_off(bwtfn, ".bwt");
+		std::string const preisafn = prefix + ".preisa";
+		if (!file_exists(bwtfn)) throw IoError(std::string(bwtfn) + " does not exist");
+		if (!file_exists(textfn)) throw IoError(std::string(textfn) + " does not exist");
+		if (!file_exists(preisafn)) throw IoError(preisafn + " does not exist (checkbwt needs the anchors: run bwtb3m with bwtonly=1)");
+		if (!numthreads) numthreads = 1;
+		std::vector<uint8_t> const L = RlDecoder::decodeAll(std::vector<std::string>(1, bwtfn), numthreads);
+		std::vector<uint64_t> const pairs = read_preisa(preisafn);
+		Engine e(device, nullptr);
+		{
+			PinnedFile text(textfn);
+			e.load(text.p, text.n, itype, false);
+		}
+		uint64_t badrank = ~0ull;
+		uint64_t const bad = e.check_bwt(L.data(), L.size(), pairs.data(), pairs.size() / 2, &badrank);
+		if (verbose) {
+			if (bad && badrank != ~0ull) fprintf(stderr, "[E] failure at rank %llu\n", (unsigned long long)badrank);
+			fprintf(stderr, "[V] %llu/%llu symbols compared from %llu anchors, %llu mismatches, walk %.3f ms, total %.3f s\n", (unsigned long long)L.size(),
+			        (unsigned long long)e.T.n, (unsigned long long)(pairs.size() / 2), (unsigned long long)bad, e.ms_walk, now_sec() - t0);
+		}
+		if (ok) *ok = bad == 0;
+		if (mismatches) *mismatches = bad;
+		return 0;
+	} catch (std::exception const & ex) { set_err(err, errlen, ex.what()); return 2; }
+	catch (...) { set_err(err, errlen, "unknown error"); return 3; }
+}
+
 // BWA's on-disk formats (public bwt_dump_bwt / bwt_dump_sa):
 //   .bwt: primary, L2[1..4], then ceil(seq_len/16) uint32 words, 16 symbols per word, symbol i
 //         at bits (15-(i&15))*2, the terminator row removed

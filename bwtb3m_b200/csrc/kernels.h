@@ -133,6 +133,9 @@ void k7_walk(Stream & st, DevDict const & D, const uint32_t * anchor_rank, uint6
 // the same from anchors at arbitrary positions: anchor_steps[q] = distance to the previous anchor
 void k7_walk_anchors(Stream & st, DevDict const & D, const uint32_t * anchor_rank, const uint64_t * anchor_pos, const uint64_t * anchor_steps,
                      uint64_t nanchors, uint64_t n, uint64_t sarate, uint64_t isarate, uint64_t * sa_out, uint64_t * isa_out, WalkStats * ws);
+// checkbwt: the same walk, comparing the BWT symbol at every rank with the text (d_result: [0] mismatches, [1] a bad rank)
+void k7_check_walk(Stream & st, DevDict const & D, const uint8_t * codes, uint64_t ntext, int has_term, const uint32_t * anchor_rank,
+                   const uint64_t * anchor_pos, const uint64_t * anchor_steps, uint64_t nanchors, uint64_t n, uint64_t * d_result);
 // LF-steps/s instrument (restates bwttestdecodespeed.cpp:82-96 for many chains)
 void k7_lfbench(Stream & st, DevDict const & D, const uint32_t * start_rank, uint64_t nchains, uint64_t steps, uint32_t * out_rank);
 

@@ -402,6 +402,31 @@ k_lfbench(DictView D, CTable C, uint32_t exc_lf, const uint32_t * __restrict__ s
 	out[q] = r;
 }
 
+// checkbwt (/root/reference/src/checkbwt.cpp:176-243): from every anchor walk LF back to the
+// previous anchor and compare the symbol the BWT holds at the current rank with the text symbol
+// in front of the current position ("text circularly reversed at the anchor").  Codes are the
+// text's dense codes; exc_pos is the row of the terminator symbol of a terminated text.
+__global__ void __launch_bounds__(256)
+k_check_walk(DictView D, CTable C, uint32_t exc_lf, const uint8_t * __restrict__ codes, uint64_t ntext, int has_term,
+             const uint32_t * __restrict__ anchor_rank, const unsigned long long * __restrict__ anchor_pos,
+             const unsigned long long * __restrict__ anchor_steps, uint64_t nanchors, uint64_t n,
+             unsigned long long * __restrict__ result /* [0] mismatches, [1] rank of one of them */) {
+	uint64_t const q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= nanchors) return;
+	uint32_t r = anchor_rank[q];
+	uint64_t p = anchor_pos[q];
+	uint64_t steps = anchor_steps[q];
+	uint32_t bad = 0, badrank = 0;
+	while (steps--) {
+		p = p ? p - 1 : n - 1;
+		int const want = (has_term && p == ntext) ? -1 : (int)codes[p];
+		int const have = (r == D.exc_pos) ? -1 : (int)dict_symbol(D, r);
+		if (want != have) { if (!bad) badrank = r; ++bad; }
+		r = lf_step(D, C, exc_lf, r);
+	}
+	if (bad) { atomicAdd(&result[0], (unsigned long long)bad); result[1] = badrank; }
+}
+
 static DictView make_view(DevDict const & D) {
 	DictView v;
 	v.base = reinterpret_cast<const uint8_t *>(D.lines);
@@ -445,6 +470,15 @@ void k7_walk_anchors(Stream & st, DevDict const & D, const uint32_t * anchor_ran
 	           (uint32_t)(sarate - 1), ilog2_exact(sarate), (uint32_t)(isarate - 1), ilog2_exact(isarate),
 	           (unsigned long long *)sa_out, (unsigned long long *)isa_out);
 	if (ws) { ws->steps += n; ws->chains += nanchors; }
+}
+
+void k7_check_walk(Stream & st, DevDict const & D, const uint8_t * codes, uint64_t ntext, int has_term, const uint32_t * anchor_rank,
+                   const uint64_t * anchor_pos, const uint64_t * anchor_steps, uint64_t nanchors, uint64_t n, uint64_t * d_result) {
+	if (!nanchors) return;
+	CTable C;
+	for (int i = 0; i < 257; ++i) C.c[i] = D.C[i];
+	B3M_LAUNCH_T(st, "check_walk", n * 65ull, k_check_walk, (unsigned)div_up(nanchors, 256), 256, 0, make_view(D), C, D.exc_lf, codes, ntext, has_term, anchor_rank,
+	             (const unsigned long long *)anchor_pos, (const unsigned long long *)anchor_steps, nanchors, n, (unsigned long long *)d_result);
 }
 
 void k7_lfbench(Stream & st, DevDict const & D, const uint32_t * start_rank, uint64_t nchains, uint64_t steps, uint32_t * out_rank) {

@@ -100,3 +100,14 @@ def read_hist(fn):
     if a.size < 1 or a.size != 1 + 2 * int(a[0]):
         raise B3MError("malformed .hist " + fn)
     return {int(a[1 + 2 * i]): int(a[2 + 2 * i]) for i in range(int(a[0]))}
+
+
+def check_bwt(bwtfn, textfn, inputtype="bytestream", numthreads=0, device=0, verbose=0):
+    """checkbwt (reference: src/checkbwt.cpp:26-246) on the GPU; returns (ok, mismatches)."""
+    ok, bad = C.c_int(0), C.c_uint64(0)
+    err = C.create_string_buffer(2048)
+    rc = lib().b3m_check_bwt(os.fsencode(bwtfn), os.fsencode(textfn), inputtype.encode(), numthreads or (os.cpu_count() or 1), device, verbose,
+                             C.byref(ok), C.byref(bad), err, len(err))
+    if rc != 0:
+        raise RuntimeError(err.value.decode())
+    return bool(ok.value), int(bad.value)

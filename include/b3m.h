@@ -94,6 +94,13 @@ int b3m_compute_ssa(const char * bwtfn, uint64_t sasamplingrate, uint64_t isasam
  * (/root/reference/src/bwtb3mtobwa.cpp:29) */
 int b3m_to_bwa(const char * inbwt, const char * outbwt, const char * outsa, char * err, size_t errlen);
 
+/* replaces the reference's verifier checkBwt<io_type>(arg) (/root/reference/src/checkbwt.cpp:26-246): LF-walks
+ * the BWT from the (rank,pos) anchors of <prefix>.preisa and compares every symbol with the text in front of the
+ * walk's position; every text position is compared exactly once, the symbol counts must agree too.
+ * *ok = 1 iff nothing differs (the reference prints this as "[V] gok=1"); *mismatches = how many symbols differ */
+int b3m_check_bwt(const char * bwtfn, const char * textfn, const char * inputtype, uint64_t numthreads, int device, int verbose,
+                  int * ok, uint64_t * mismatches, char * err, size_t errlen);
+
 /* Reader of the .bwt container for bindings that cannot link C++: replaces
  * libmaus2::huffman::RLDecoder::getLength (/root/reference/src/hwtPreIsaToIsa.cpp:53) and a full
  * RLDecoder::decode() loop (/root/reference/src/bwtb3mdecoderl.cpp:27-46). */

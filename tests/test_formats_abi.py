@@ -144,3 +144,18 @@ def test_sampled_and_preisa_layouts(tmp_path):
     np.array([[5, 0], [9, 64]], dtype=np.uint64).tofile(fn)
     assert files.read_preisa(fn).tolist() == [[5, 0], [9, 64]]
     assert os.path.getsize(fn) % 16 == 0
+
+
+def test_sasubsample_tool(tmp_path):
+    """cli/sasubsample: [rate][count][values] -> every s-th value, rate*s (reference: src/sasubsample.cpp:34-58)."""
+    import subprocess
+    import numpy as np
+    exe = os.path.join(ROOT, "bin", "sasubsample")
+    if not os.path.exists(exe):
+        pytest.skip("bin/sasubsample not built")
+    vals = np.arange(100, 100 + 37, dtype=np.uint64)
+    src = np.concatenate([np.array([32, vals.size], dtype=np.uint64), vals]).tobytes()
+    out = subprocess.run([exe, "-s", "4"], input=src, capture_output=True, check=True).stdout
+    a = np.frombuffer(out, dtype=np.uint64)
+    assert a[0] == 128 and a[1] == (37 + 3) // 4 and np.array_equal(a[2:], vals[::4])
+    assert subprocess.run([exe, "-s", "3"], input=src, capture_output=True).returncode != 0

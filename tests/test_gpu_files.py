@@ -158,3 +158,40 @@ def test_engine_fetch_bwa_matches_oracle(oracle, l):
     assert words.tobytes() == ob[40:40 + 4 * words.size]
     # BWA's .sa payload is the rank-sampled SA without its first entry
     assert res["sa"][1:].tobytes() == osa[56:56 + 8 * (res["sa"].size - 1)]
+
+
+@pytest.mark.parametrize("itype", ["pacterm", "bytestream"])
+def test_checkbwt_tool_and_abi(tmp_path, oracle, itype):
+    """checkbwt on the GPU (b3m_check_bwt + cli/checkbwt): accepts the files bwtb3m wrote, rejects a
+    BWT with two rows swapped (same symbol counts) and one with a changed symbol."""
+    from bwtb3m_b200 import files
+    if itype == "pacterm":
+        data, t = make_pac(oracle, 120_003, 9)
+        fn = tmp_path / "g.pac"
+    else:
+        t = np.random.default_rng(10).integers(0, 200, size=90_001, dtype=np.uint8)
+        data = t
+        fn = tmp_path / "t.bin"
+    data.tofile(fn)
+    res = files.compute_bwt(str(fn), inputtype=itype, outputfilename=str(tmp_path / "x.bwt"), bwtonly=True)
+    ok, bad = files.check_bwt(res["bwtfn"], str(fn), inputtype=itype)
+    assert ok and bad == 0
+    r = subprocess.run([os.path.join(BIN, "checkbwt"), "-i", itype, res["bwtfn"], str(fn)], capture_output=True, text=True)
+    assert r.returncode == 0 and "[V] gok=1" in r.stderr
+    bwt = files.read_bwt(res["bwtfn"])
+    # swap two neighbouring rows that hold different symbols: histogram unchanged, LF walk derails
+    k = int(np.nonzero(bwt[1000:-1] != bwt[1001:])[0][0]) + 1000
+    broken = bwt.copy()
+    broken[k], broken[k + 1] = bwt[k + 1], bwt[k]
+    files.write_bwt_host(res["bwtfn"], broken)
+    ok, bad = files.check_bwt(res["bwtfn"], str(fn), inputtype=itype)
+    assert not ok and bad > 0
+    r = subprocess.run([os.path.join(BIN, "checkbwt"), "-i", itype, res["bwtfn"], str(fn)], capture_output=True, text=True)
+    assert r.returncode == 0 and "[V] gok=0" in r.stderr
+    # a changed symbol changes the counts
+    broken = bwt.copy()
+    j = 5000 if bwt[5000] != 0 else 5001  # not the terminator row
+    broken[j] = (bwt[j] % 4) + 1 if itype == "pacterm" else (int(bwt[j]) + 1) % 200
+    files.write_bwt_host(res["bwtfn"], broken)
+    ok, bad = files.check_bwt(res["bwtfn"], str(fn), inputtype=itype)
+    assert not ok
