@@ -54,7 +54,7 @@ class Result(C.Structure):
 
 # every symbol include/b3m.h declares
 EXPORTS = [
-    "b3m_version", "b3m_parse_inputtype", "b3m_options_init", "b3m_compute_bwt", "b3m_compute_ssa", "b3m_to_bwa", "b3m_check_bwt",
+    "b3m_version", "b3m_parse_inputtype", "b3m_options_init", "b3m_compute_bwt", "b3m_compute_ssa", "b3m_to_bwa", "b3m_check_bwt", "b3m_lf_speed",
     "b3m_engine_create", "b3m_engine_destroy", "b3m_engine_last_error", "b3m_engine_load_host",
     "b3m_engine_load_device", "b3m_engine_build", "b3m_engine_info", "b3m_engine_fetch",
     "b3m_engine_device_results", "b3m_engine_lf_bench", "b3m_engine_sync", "b3m_engine_set_profile",
@@ -123,6 +123,7 @@ def lib():
         L.b3m_compute_ssa.argtypes = [C.c_char_p, u64, u64, C.c_char_p, C.c_int, u64, u64, u64, C.c_int, C.c_char_p,
                                       C.c_char_p, C.c_int, C.c_char_p, C.c_size_t]
         L.b3m_to_bwa.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_size_t]
+        L.b3m_lf_speed.argtypes = [C.c_char_p, u64, u64, u64, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_char_p, C.c_size_t]
         L.b3m_check_bwt.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, u64, C.c_int, C.c_int, C.POINTER(C.c_int), u64p, C.c_char_p, C.c_size_t]
     _lib = L
     return L

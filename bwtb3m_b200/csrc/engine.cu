@@ -447,18 +447,14 @@ k_find_byte(const uint8_t * __restrict__ s, uint64_t n, uint32_t v, uint32_t * _
 	if (i < n && s[i] == v) *out = (uint32_t)i;
 }
 
-void Engine::ssa_from_bwt(const uint8_t * h_bwt, uint64_t n, const uint64_t * h_pairs, uint64_t npairs, uint64_t sarate, uint64_t isarate) {
+// K4 on a BWT that arrives in the reference's symbol space (a .bwt file): dense codes + rank dictionary
+void Engine::install_bwt_symbols(const uint8_t * h_bwt, uint64_t n, uint64_t extra_bytes) {
 	B3M_CUDA(cudaSetDevice(device));
 	B3M_REQUIRE(n > 0 && n < 0xFFFFFFF0ull, "BWT length out of range");
-	B3M_REQUIRE(npairs > 0, "no (rank,pos) anchors: the .preisa file is empty");
-	auto pow2 = [](uint64_t v) { return v && !(v & (v - 1)); };
-	B3M_REQUIRE(pow2(sarate) && pow2(isarate), "sampling rates must be powers of two");
 	reset_results();
 	codes.release(); packed.release(); raw.release(); d_hist.release(); d_special.release();
 	loaded = false;
-	arena.reserve((size_t)(n * 4 + 16 * npairs + (64u << 20)));
-	PhaseTimer pt(st);
-	pt.mark();
+	arena.reserve((size_t)(n * 4 + extra_bytes + (64u << 20)));
 	raw.alloc(st, n + 16);
 	B3M_CUDA(cudaMemcpyAsync(raw.get(), h_bwt, n, cudaMemcpyHostToDevice, st.s));
 	d_hist.alloc(st, 256);
@@ -505,6 +501,19 @@ void Engine::ssa_from_bwt(const uint8_t * h_bwt, uint64_t n, const uint64_t * h_
 	D.flavour = flavour; D.n = n; D.lines = dict.get(); D.sigma = sigma;
 	D.exc_pos = exc_pos; D.exc_code = 0; D.exc_lf = use_exc ? (uint32_t)csym[unique_sym] : 0;
 	dict_bytes_moved = n + bytes;
+	root_exc_pos = 0xffffffffu;
+	npre = 0; prerate = 0; numblocks = 0;
+	ssa_only = true;
+}
+
+void Engine::ssa_from_bwt(const uint8_t * h_bwt, uint64_t n, const uint64_t * h_pairs, uint64_t npairs, uint64_t sarate, uint64_t isarate) {
+	B3M_CUDA(cudaSetDevice(device));
+	B3M_REQUIRE(npairs > 0, "no (rank,pos) anchors: the .preisa file is empty");
+	auto pow2 = [](uint64_t v) { return v && !(v & (v - 1)); };
+	B3M_REQUIRE(pow2(sarate) && pow2(isarate), "sampling rates must be powers of two");
+	PhaseTimer pt(st);
+	pt.mark();
+	install_bwt_symbols(h_bwt, n, 16 * npairs);
 	pt.mark();
 	// anchors sorted by position; each walks back to its predecessor
 	std::vector<std::pair<uint64_t, uint64_t>> A(npairs);
@@ -616,6 +625,24 @@ k_pick_starts(const uint32_t * __restrict__ prerank, uint64_t npre, uint64_t nch
 	uint64_t const q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (q >= nchains) return;
 	start[q] = prerank[(q * npre) / nchains];
+}
+
+// LF-steps/s of the dictionary in place, chains started at the given ranks (bwttestdecodespeed: evenly spaced .isa samples)
+void Engine::lf_speed(const uint64_t * h_start, uint64_t nstart, uint64_t nchains, uint64_t steps, float * ms) {
+	B3M_CUDA(cudaSetDevice(device));
+	B3M_REQUIRE(D.lines, "no dictionary");
+	B3M_REQUIRE(nstart >= 1 && nchains >= 1, "need start ranks and at least one chain");
+	std::vector<uint32_t> h(nchains);
+	for (uint64_t c = 0; c < nchains; ++c) h[c] = (uint32_t)h_start[(c * nstart) / nchains];
+	DevBuf<uint32_t> start(st, nchains), out(st, nchains);
+	B3M_CUDA(cudaMemcpyAsync(start.get(), h.data(), 4 * nchains, cudaMemcpyHostToDevice, st.s));
+	B3M_CUDA(cudaStreamSynchronize(st.s));
+	PhaseTimer pt(st);
+	pt.mark();
+	k7_lfbench(st, D, start.get(), nchains, steps, out.get());
+	pt.mark();
+	B3M_CUDA(cudaStreamSynchronize(st.s));
+	*ms = pt.ms(0, 1);
 }
 
 void Engine::lf_bench(uint64_t nchains, uint64_t steps, float * ms, uint64_t * checksum) {

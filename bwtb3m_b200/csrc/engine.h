@@ -125,6 +125,8 @@ struct Engine {
 	void fetch_runs(uint8_t * h_sym, uint64_t * h_len, uint64_t cap, uint64_t * nruns_out);
 	void fetch_bwa(uint32_t * h_words, uint64_t cap, uint64_t * primary, uint64_t * L2, uint64_t * seq_len_out);
 	// sampled SA/ISA from an existing BWT and (rank,pos) anchors (bwtcomputessa path)
+	void install_bwt_symbols(const uint8_t * h_bwt, uint64_t n, uint64_t extra_bytes);
+	void lf_speed(const uint64_t * h_start, uint64_t nstart, uint64_t nchains, uint64_t steps, float * ms);
 	void ssa_from_bwt(const uint8_t * h_bwt, uint64_t n, const uint64_t * h_pairs, uint64_t npairs, uint64_t sarate, uint64_t isarate);
 	// checkbwt: verifies BWT symbols (reference symbol space) + anchors against the loaded text; returns mismatches
 	uint64_t check_bwt(const uint8_t * h_bwt, uint64_t n, const uint64_t * h_pairs, uint64_t npairs, uint64_t * badrank);

@@ -242,6 +242,35 @@ int b3m_check_bwt(const char * bwtfn, const char * textfn, const char * inputtyp
 	catch (...) { set_err(err, errlen, "unknown error"); return 3; }
 }
 
+// bwttestdecodespeed <in.bwt>  (/root/reference/src/bwttestdecodespeed.cpp:27-97): dependent LF chains started at
+// evenly spaced samples of <prefix>.isa over a rank dictionary of the BWT; steps_per_s = nchains * steps / seconds
+int b3m_lf_speed(const char * bwtfn, uint64_t nchains, uint64_t steps, uint64_t numthreads, int device, double * steps_per_s, double * seconds,
+                 char * err, size_t errlen) {
+	try {
+		if (!bwtfn || !*bwtfn) throw Error("no .bwt file name");
+		check_device_available();
+		std::string const prefix = clip_off(bwtfn, ".bwt");
+		std::string const isafn = prefix + ".isa";
+		if (!file_exists(bwtfn)) throw IoError(std::string(bwtfn) + " does not exist");
+		if (!file_exists(isafn)) throw IoError(isafn + " does not exist (bwttestdecodespeed starts its chains at the sampled ISA)");
+		if (!numthreads) numthreads = 1;
+		std::vector<uint8_t> const L = RlDecoder::decodeAll(std::vector<std::string>(1, bwtfn), numthreads);
+		uint64_t rate = 0; std::vector<uint64_t> isa;
+		read_sampled(isafn, &rate, &isa);
+		if (isa.empty()) throw Error("empty sampled ISA");
+		Engine e(device, nullptr);
+		e.install_bwt_symbols(L.data(), L.size(), 16 * nchains);
+		if (!steps) steps = std::min<uint64_t>(div_up(L.size(), nchains), 128ull << 20); // bwttestdecodespeed.cpp:84
+		float ms = 0;
+		e.lf_speed(isa.data(), isa.size(), nchains, 16, &ms); // warm up
+		e.lf_speed(isa.data(), isa.size(), nchains, steps, &ms);
+		if (seconds) *seconds = ms * 1e-3;
+		if (steps_per_s) *steps_per_s = (double)nchains * (double)steps / (ms * 1e-3);
+		return 0;
+	} catch (std::exception const & ex) { set_err(err, errlen, ex.what()); return 2; }
+	catch (...) { set_err(err, errlen, "unknown error"); return 3; }
+}
+
 // BWA's on-disk formats (public bwt_dump_bwt / bwt_dump_sa):
 //   .bwt: primary, L2[1..4], then ceil(seq_len/16) uint32 words, 16 symbols per word, symbol i
 //         at bits (15-(i&15))*2, the terminator row removed

@@ -111,3 +111,13 @@ def check_bwt(bwtfn, textfn, inputtype="bytestream", numthreads=0, device=0, ver
     if rc != 0:
         raise RuntimeError(err.value.decode())
     return bool(ok.value), int(bad.value)
+
+
+def lf_speed(bwtfn, nchains, steps=0, numthreads=0, device=0):
+    """bwttestdecodespeed (reference: src/bwttestdecodespeed.cpp:27-97) on the GPU; returns (LF steps per second, seconds)."""
+    sps, sec = C.c_double(0), C.c_double(0)
+    err = C.create_string_buffer(2048)
+    rc = lib().b3m_lf_speed(os.fsencode(bwtfn), nchains, steps, numthreads or (os.cpu_count() or 1), device, C.byref(sps), C.byref(sec), err, len(err))
+    if rc != 0:
+        raise RuntimeError(err.value.decode())
+    return float(sps.value), float(sec.value)

@@ -101,6 +101,12 @@ int b3m_to_bwa(const char * inbwt, const char * outbwt, const char * outsa, char
 int b3m_check_bwt(const char * bwtfn, const char * textfn, const char * inputtype, uint64_t numthreads, int device, int verbose,
                   int * ok, uint64_t * mismatches, char * err, size_t errlen);
 
+/* replaces the LF-steps/s instrument bwttestdecodespeed (/root/reference/src/bwttestdecodespeed.cpp:27-97):
+ * `nchains` dependent LF chains of `steps` steps (0: min(ceil(n/nchains), 2^27) as in the reference) over a rank
+ * dictionary of the BWT, started at evenly spaced samples of <prefix>.isa */
+int b3m_lf_speed(const char * bwtfn, uint64_t nchains, uint64_t steps, uint64_t numthreads, int device, double * steps_per_s, double * seconds,
+                 char * err, size_t errlen);
+
 /* Reader of the .bwt container for bindings that cannot link C++: replaces
  * libmaus2::huffman::RLDecoder::getLength (/root/reference/src/hwtPreIsaToIsa.cpp:53) and a full
  * RLDecoder::decode() loop (/root/reference/src/bwtb3mdecoderl.cpp:27-46). */

@@ -195,3 +195,16 @@ def test_checkbwt_tool_and_abi(tmp_path, oracle, itype):
     files.write_bwt_host(res["bwtfn"], broken)
     ok, bad = files.check_bwt(res["bwtfn"], str(fn), inputtype=itype)
     assert not ok
+
+
+def test_lf_speed_instrument(tmp_path, oracle):
+    """bwttestdecodespeed on the GPU: runs from the files bwtb3m wrote and reports a positive rate."""
+    from bwtb3m_b200 import files
+    data, t = make_pac(oracle, 300_001, 12)
+    fn = tmp_path / "g.pac"
+    data.tofile(fn)
+    res = files.compute_bwt(str(fn), inputtype="pacterm", outputfilename=str(tmp_path / "g.bwt"), isasamplingrate=64)
+    sps, sec = files.lf_speed(res["bwtfn"], 4096, 200)
+    assert sps > 1e6 and sec > 0
+    r = subprocess.run([os.path.join(BIN, "bwttestdecodespeed"), res["bwtfn"], "chains=2048", "steps=100"], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.split()[0] == "2048"
