@@ -544,7 +544,7 @@ void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W,
 			}
 			uint64_t const seq_len = W, nwords_bwa = (W + 15) >> 4; // terminated text: n - 1 = W bases
 			uint64_t words_done = 0;
-			unsigned const nchunks = (stream_sa || stream_bwa) ? 8u : 1u;
+			unsigned const nchunks = (stream_sa || stream_bwa) ? 16u : 1u; // the last chunk's copies are the exposed tail
 			for (unsigned c = 0; c < nchunks; ++c) {
 				unsigned const t_lo = (unsigned)((uint64_t)rgrid * c / nchunks), t_hi = (unsigned)((uint64_t)rgrid * (c + 1) / nchunks);
 				B3M_LAUNCH_T(st, "resolve_extract", (uint64_t)(t_hi - t_lo) * RS_TILE * 10ull, (k_resolve<true, false>), t_hi - t_lo, RS_THREADS, 0, v, bits, k0, lin,
