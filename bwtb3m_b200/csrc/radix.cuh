@@ -515,7 +515,7 @@ struct RadixStats {
 // buffers; on return `cur` names the arrays that hold the result.
 template <int NA>
 void radix_sort_bits(Stream & st, RadixRec<NA> & cur, RadixRec<NA> & alt, int ka, uint64_t n,
-                     int bit_lo, int bit_hi, RadixStats * rs) {
+                     int bit_lo, int bit_hi, RadixStats * rs, const unsigned long long * pre_hist = nullptr /* [4][256] digit histograms of bits 0..31, if the caller has them */) {
 	if (n == 0 || bit_hi <= bit_lo) return;
 	uint32_t const ntiles = (uint32_t)div_up(n, RADIX_TILE);
 	DevBuf<unsigned long long> status(st, (size_t)ntiles * RADIX_BINS);
@@ -532,9 +532,12 @@ void radix_sort_bits(Stream & st, RadixRec<NA> & cur, RadixRec<NA> & alt, int ka
 		B3M_CUDA(cudaMemsetAsync(skip, 0, (8 + RADIX_MAXDIG) * sizeof(uint32_t), st.s));
 		uint64_t const want = div_up(n, 256 * 16);
 		unsigned const hgrid = (unsigned)(want < (uint64_t)st.sms * 8 ? want : (uint64_t)st.sms * 8);
-		B3M_LAUNCH_T(st, "radix_hist", 4ull * n, k_radix_hist, hgrid, 256, 0, (const uint32_t *)cur.a[ka], n, lo, ndig, lastmask, ghist.get());
-		B3M_LAUNCH(st, k_radix_hist_scan, 1, 256, 0, (const unsigned long long *)ghist.get(), ndig, n, base.get(), skip);
-		if (rs) rs->bytes += 4ull * n;
+		bool const have_hist = pre_hist && lo == 0 && hi == 32;
+		if (!have_hist) {
+			B3M_LAUNCH_T(st, "radix_hist", 4ull * n, k_radix_hist, hgrid, 256, 0, (const uint32_t *)cur.a[ka], n, lo, ndig, lastmask, ghist.get());
+			if (rs) rs->bytes += 4ull * n;
+		}
+		B3M_LAUNCH(st, k_radix_hist_scan, 1, 256, 0, have_hist ? pre_hist : (const unsigned long long *)ghist.get(), ndig, n, base.get(), skip);
 		uint32_t hskip[4];
 		B3M_CUDA(cudaMemcpyAsync(hskip, skip, sizeof(hskip), cudaMemcpyDeviceToHost, st.s));
 		B3M_CUDA(cudaStreamSynchronize(st.s));

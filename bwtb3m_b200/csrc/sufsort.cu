@@ -337,38 +337,50 @@ k_keyrange_flags(RadixTextSrc S, uint32_t binshift, uint32_t blo, uint32_t bhi, 
 }
 
 __global__ void __launch_bounds__(256)
-k_keyrange_gather(RadixTextSrc S, const uint32_t * __restrict__ flags, const uint32_t * __restrict__ tileoff,
-                  uint32_t * __restrict__ okey, uint32_t * __restrict__ oidx, uint8_t * __restrict__ oaux) {
+k_keyrange_gather(RadixTextSrc S, const uint32_t * __restrict__ flags, const uint32_t * __restrict__ tileoff, uint32_t ntiles,
+                  uint32_t * __restrict__ okey, uint32_t * __restrict__ oidx, uint8_t * __restrict__ oaux,
+                  unsigned long long * __restrict__ ghist /* [4][256]: digit histograms of the keys written, for the radix passes */) {
 	__shared__ uint32_t wtot[8];
 	__shared__ uint16_t s_list[8][1024];
+	__shared__ uint32_t s_hist[RADIX_MAXDIG][RADIX_BINS];
 	unsigned const w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	uint64_t const tbase = (uint64_t)blockIdx.x * KR_FTILE + (uint64_t)w * 1024; // a warp owns 32 flag words
+	for (int i = threadIdx.x; i < RADIX_MAXDIG * RADIX_BINS; i += blockDim.x) (&s_hist[0][0])[i] = 0;
 	uint64_t const nwords = div_up(S.v.W, 32);
-	uint64_t const wi = (tbase >> 5) + lane;
-	uint32_t const m = wi < nwords ? flags[wi] : 0u;
-	uint32_t incl = (uint32_t)__popc(m);
-	#pragma unroll
-	for (int o = 1; o < 32; o <<= 1) { uint32_t const x = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += x; }
-	uint32_t const excl = incl - (uint32_t)__popc(m);
-	uint32_t const total = __shfl_sync(0xffffffffu, incl, 31);
-	if (lane == 0) wtot[w] = total;
+	for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+		__syncthreads(); // s_hist cleared / wtot of the previous tile consumed
+		uint64_t const tbase = (uint64_t)tile * KR_FTILE + (uint64_t)w * 1024; // a warp owns 32 flag words
+		uint64_t const wi = (tbase >> 5) + lane;
+		uint32_t const m = wi < nwords ? flags[wi] : 0u;
+		uint32_t incl = (uint32_t)__popc(m);
+		#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { uint32_t const x = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += x; }
+		uint32_t const excl = incl - (uint32_t)__popc(m);
+		uint32_t const total = __shfl_sync(0xffffffffu, incl, 31);
+		if (lane == 0) wtot[w] = total;
+		__syncthreads();
+		uint32_t off = tileoff[tile];
+		for (unsigned i = 0; i < w; ++i) off += wtot[i];
+		// every lane lists the places of its own set bits behind those of the lanes below it ...
+		uint16_t * const list = s_list[w];
+		{
+			uint32_t mm = m, j = excl;
+			while (mm) { list[j++] = (uint16_t)(32u * lane + (uint32_t)__ffs((int)mm) - 1u); mm &= mm - 1u; }
+		}
+		__syncwarp();
+		// ... and the warp takes the listed records 32 at a time
+		for (uint32_t k = lane; k < total; k += 32) {
+			uint64_t const t = tbase + list[k];
+			uint32_t key, idx, aux;
+			radix_text_record_any(S, t, key, idx, aux);
+			okey[off + k] = key; oidx[off + k] = idx; oaux[off + k] = (uint8_t)aux;
+			atomicAdd(&s_hist[0][key & 255u], 1u); atomicAdd(&s_hist[1][(key >> 8) & 255u], 1u);
+			atomicAdd(&s_hist[2][(key >> 16) & 255u], 1u); atomicAdd(&s_hist[3][key >> 24], 1u);
+		}
+		__syncwarp();
+	}
 	__syncthreads();
-	uint32_t off = tileoff[blockIdx.x];
-	for (unsigned i = 0; i < w; ++i) off += wtot[i];
-	// every lane lists the places of its own set bits behind those of the lanes below it ...
-	uint16_t * const list = s_list[w];
-	{
-		uint32_t mm = m, j = excl;
-		while (mm) { list[j++] = (uint16_t)(32u * lane + (uint32_t)__ffs((int)mm) - 1u); mm &= mm - 1u; }
-	}
-	__syncwarp();
-	// ... and the warp takes the listed records 32 at a time
-	for (uint32_t k = lane; k < total; k += 32) {
-		uint64_t const t = tbase + list[k];
-		uint32_t key, idx, aux;
-		radix_text_record_any(S, t, key, idx, aux);
-		okey[off + k] = key; oidx[off + k] = idx; oaux[off + k] = (uint8_t)aux;
-	}
+	for (int i = threadIdx.x; i < RADIX_MAXDIG * RADIX_BINS; i += blockDim.x)
+		if ((&s_hist[0][0])[i]) atomicAdd(&ghist[i], (unsigned long long)(&s_hist[0][0])[i]);
 }
 
 void k2_keyrange_plan(Stream & st, DevText const & T, int circular, uint32_t nparts, KeyRangePlan & plan) {
@@ -435,12 +447,15 @@ uint64_t k2_sort_keyrange(Stream & st, DevText const & T, int circular, KeyRange
 	scan_exclusive_inplace<OpSum>(st, tcount.get(), ntiles);
 	DevBuf<uint32_t> key0(st, m), key1(st, m), idx0(st, m), idx1(st, m);
 	DevBuf<uint8_t> aux0(st, m), aux1(st, m);
-	B3M_LAUNCH_T(st, "keyrange_gather", W / 8 + 9 * m, k_keyrange_gather, ntiles, 256, 0, S, (const uint32_t *)fl.get(), (const uint32_t *)tcount.get(),
-	             key0.get(), idx0.get(), aux0.get());
+	DevBuf<unsigned long long> khist(st, RADIX_MAXDIG * RADIX_BINS);
+	B3M_CUDA(cudaMemsetAsync(khist.get(), 0, khist.bytes(), st.s));
+	unsigned const ggrid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)st.sms * 8);
+	B3M_LAUNCH_T(st, "keyrange_gather", W / 8 + 9 * m, k_keyrange_gather, ggrid, 256, 0, S, (const uint32_t *)fl.get(), (const uint32_t *)tcount.get(), ntiles,
+	             key0.get(), idx0.get(), aux0.get(), khist.get());
 	St.other_bytes += W / 4 + W / 4 + 9 * m;
 	RadixRec<2> cur{{key0.get(), idx0.get()}, aux0.get()}, alt{{key1.get(), idx1.get()}, aux1.get()};
 	RadixStats rs;
-	radix_sort_bits<2>(st, cur, alt, 0, m, 0, 32, &rs);
+	radix_sort_bits<2>(st, cur, alt, 0, m, 0, 32, &rs, khist.get());
 	St.radix_passes += rs.passes; St.radix_bytes += rs.bytes; St.active_sum += m;
 	DevBuf<unsigned long long> counters(st, 4 * RS_CSLOTS);
 	DevBuf<uint8_t> hflag(st, m);
