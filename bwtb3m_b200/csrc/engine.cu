@@ -159,14 +159,6 @@ void Engine::load(const void * input, uint64_t nbytes, int itype, bool on_device
 
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_sample_ranks(const uint32_t * __restrict__ rank, uint64_t ntext, uint64_t rate, uint32_t shift, uint64_t ns, uint32_t * __restrict__ out) {
-	uint64_t const q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (q >= ns) return;
-	uint64_t const p = q * rate;
-	out[q] = p < ntext ? rank[p] + shift : 0u; // p == ntext: the terminator suffix has rank 0
-}
-
-__global__ void __launch_bounds__(256)
 k_pairs(const uint32_t * __restrict__ prerank, uint64_t ns, uint64_t rate, unsigned long long * __restrict__ pairs) {
 	uint64_t const q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (q >= ns) return;

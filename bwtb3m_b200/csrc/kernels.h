@@ -100,12 +100,6 @@ void k2_keyrange_plan(Stream & st, DevText const & T, int circular, uint32_t npa
 // fo.shift + base[part] + k; returns the number of suffixes left unresolved (0: the slice is final)
 uint64_t k2_sort_keyrange(Stream & st, DevText const & T, int circular, KeyRangePlan const & plan, uint32_t part, FusedOut const & fo, SortStats * stats);
 
-// ---- K3 ---------------------------------------------------------------------------------
-// bwt[k + shift] = code preceding suffix sa[k] (text position wstart+sa[k]); the suffix at text
-// position 0 of a terminated text gets code 0 and its output index is written to *d_termrank.
-void k3_extract_bwt(Stream & st, DevText const & T, uint64_t wstart, const uint32_t * sa, uint64_t m,
-                    uint8_t * bwt, uint64_t shift, uint32_t * d_special);
-
 // ---- K4 / K7 ----------------------------------------------------------------------------
 // Rank dictionary, 2-bit flavour: 64-byte lines = 4 x uint32 cumulative counts + 48 bytes
 // (192 symbols x 2 bit).  Byte flavour: 128 symbols per block, 256 x uint32 counts + 128 bytes.

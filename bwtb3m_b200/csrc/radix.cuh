@@ -170,7 +170,7 @@ __device__ __forceinline__ uint32_t radix_text_index(RadixTextSrc const & S, uin
 template <int NA, bool AUX, bool TEXT, bool FULL>
 __global__ void __launch_bounds__(RADIX_THREADS, RADIX_CTAS_PER_SM)
 k_radix_onesweep(RadixPassArgs<NA> A, RadixTextSrc S, uint64_t n, int shift, uint32_t mask, const uint32_t * __restrict__ base /* [256] */,
-                 unsigned long long * __restrict__ status /* [ntiles][256] */, uint32_t * __restrict__ ticket, uint32_t flags) {
+                 unsigned long long * __restrict__ status /* [ntiles][256] */, uint32_t * __restrict__ ticket) {
 	__shared__ uint16_t wcnt[RADIX_WARPS][RADIX_BINS]; // counts, then tile-local offsets: all below RADIX_TILE
 	__shared__ uint32_t gbase[RADIX_BINS];
 	__shared__ uint32_t wsum[RADIX_BINS / 32];
@@ -292,7 +292,7 @@ k_radix_onesweep(RadixPassArgs<NA> A, RadixTextSrc S, uint64_t n, int shift, uin
 		for (int ww = 0; ww < RADIX_WARPS; ++ww) wcnt[ww][d] = (uint16_t)(wcnt[ww][d] + dstart);
 		// decoupled look-back
 		uint32_t excl = 0;
-		if (tile > 0 && !(flags & 1u)) {
+		if (tile > 0) {
 			int64_t t = (int64_t)tile - 1;
 			while (true) {
 				unsigned long long const v = *(volatile unsigned long long *)(status + (uint64_t)t * RADIX_BINS + d);
@@ -483,7 +483,6 @@ void radix_launch_pass(Stream & st, const char * label, uint64_t pbytes, RadixPa
                        int shift, uint32_t mask, const uint32_t * base, unsigned long long * status, uint32_t * ticket) {
 	uint32_t const nfull = (uint32_t)(n / RADIX_TILE);
 	bool const partial = (n % RADIX_TILE) != 0;
-	uint32_t const flags = 0;
 	size_t const smem = radix_smem_bytes<NA, AUX>() + (TEXT ? (size_t)RADIX_TILE : 0);
 	static bool configured = false; // per template instance
 	if (!configured) {
@@ -494,13 +493,13 @@ void radix_launch_pass(Stream & st, const char * label, uint64_t pbytes, RadixPa
 	if (st.kt.on) {
 		KernelTimes::Rec r{label, pbytes, st.kt.get(), st.kt.get()};
 		cudaEventRecord(r.a, st.s);
-		if (nfull) k_radix_onesweep<NA, AUX, TEXT, true><<<nfull, RADIX_THREADS, smem, st.s>>>(A, S, n, shift, mask, base, status, ticket, flags);
-		if (partial) k_radix_onesweep<NA, AUX, TEXT, false><<<1, RADIX_THREADS, smem, st.s>>>(A, S, n, shift, mask, base, status, ticket, flags);
+		if (nfull) k_radix_onesweep<NA, AUX, TEXT, true><<<nfull, RADIX_THREADS, smem, st.s>>>(A, S, n, shift, mask, base, status, ticket);
+		if (partial) k_radix_onesweep<NA, AUX, TEXT, false><<<1, RADIX_THREADS, smem, st.s>>>(A, S, n, shift, mask, base, status, ticket);
 		cudaEventRecord(r.b, st.s);
 		st.kt.recs.push_back(r);
 	} else {
-		if (nfull) k_radix_onesweep<NA, AUX, TEXT, true><<<nfull, RADIX_THREADS, smem, st.s>>>(A, S, n, shift, mask, base, status, ticket, flags);
-		if (partial) k_radix_onesweep<NA, AUX, TEXT, false><<<1, RADIX_THREADS, smem, st.s>>>(A, S, n, shift, mask, base, status, ticket, flags);
+		if (nfull) k_radix_onesweep<NA, AUX, TEXT, true><<<nfull, RADIX_THREADS, smem, st.s>>>(A, S, n, shift, mask, base, status, ticket);
+		if (partial) k_radix_onesweep<NA, AUX, TEXT, false><<<1, RADIX_THREADS, smem, st.s>>>(A, S, n, shift, mask, base, status, ticket);
 	}
 	st.launches += (nfull ? 1 : 0) + (partial ? 1 : 0);
 	B3M_CUDA(cudaGetLastError());

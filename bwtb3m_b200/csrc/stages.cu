@@ -184,32 +184,7 @@ void k1_pack2(Stream & st, const uint8_t * d_codes, uint64_t n, uint64_t * d_out
 	B3M_LAUNCH(st, k_pack2, (unsigned)div_up(nwords, 256), 256, 0, d_codes, n, d_out, nwords);
 }
 
-// ------------------------------------------------------------------------------------------
-// K3: L[k] = T[(SA[k]-1) mod n]   (/root/reference/src/lcpbit.cpp:3668-3669)
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_extract_bwt(const uint8_t * __restrict__ codes, uint64_t ntext, int has_term, uint64_t wstart, int text_wraps,
-              const uint32_t * __restrict__ sa, uint64_t m, uint8_t * __restrict__ bwt, uint64_t shift, uint32_t * __restrict__ special) {
-	uint64_t const k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (k >= m) return;
-	uint32_t const i = sa[k];
-	uint64_t p = wstart + i;
-	if (text_wraps && p >= ntext) p -= ntext;
-	uint8_t c;
-	if (p == 0) {
-		if (has_term) { c = 0; special[0] = (uint32_t)(k + shift); } // predecessor is the terminator
-		else c = codes[ntext - 1];
-	} else c = codes[p - 1];
-	if (i == 0) special[1] = (uint32_t)(k + shift);                   // rank of the block-start suffix
-	bwt[k + shift] = c;
-}
-
-void k3_extract_bwt(Stream & st, DevText const & T, uint64_t wstart, const uint32_t * sa, uint64_t m,
-                    uint8_t * bwt, uint64_t shift, uint32_t * d_special) {
-	if (!m) return;
-	B3M_LAUNCH_T(st, "extract_bwt", m * 37ull, k_extract_bwt, (unsigned)div_up(m, 256), 256, 0, T.codes, T.ntext, T.has_term, wstart,
-	           T.has_term ? 0 : 1, sa, m, bwt, shift, d_special);
-}
+// K3 (BWT extraction) lives with the sort: k_resolve / k_extract_sample in sufsort.cu, k_leaf_emit in blocks.cu.
 
 // ------------------------------------------------------------------------------------------
 // K4: dictionary build
