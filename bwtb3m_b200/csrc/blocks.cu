@@ -7,6 +7,7 @@
 #include "engine.h"
 #include "rankdict.cuh"
 #include "scan.cuh"
+#include "textview.cuh"
 #include <string.h>
 #include <algorithm>
 #include <string>
@@ -33,20 +34,46 @@ __device__ int cmp_rot(TextRef const & t, uint64_t a, uint64_t b) {
 	return 0;
 }
 
+// LCP of the rotations starting at a and b, bounded by cap, and the sign of the comparison at the first
+// difference (0: none within cap).  2-bit packed texts are compared 32 symbols per step while both
+// cursors are away from the end of the text.
+__device__ __forceinline__ void cmp_lcp(TextRef const & t, uint64_t a, uint64_t b, uint64_t cap, uint64_t & lcp, int & sign) {
+	uint64_t l = 0;
+	sign = 0;
+	while (l < cap) {
+		if (t.packed && a + 32 <= t.ntext && b + 32 <= t.ntext) {
+			uint64_t const x = pk_window(t.packed, a), y = pk_window(t.packed, b);
+			if (x == y) {
+				uint64_t const step = cap - l < 32 ? cap - l : 32;
+				l += step; a += step; b += step;
+				if (a == t.n) a = 0;
+				if (b == t.n) b = 0;
+				continue;
+			}
+			uint64_t const d = (uint64_t)__clzll((long long)(x ^ y)) >> 1; // first differing symbol
+			if (d >= cap - l) { l = cap; break; }
+			l += d;
+			sign = x > y ? 1 : -1;
+			break;
+		}
+		int const sx = text_sym(t, a), sy = text_sym(t, b);
+		if (sx != sy) { sign = sx < sy ? -1 : 1; break; }
+		if (sx < 0) break; // both cursors on the terminator: the same position
+		++l;
+		a = (a + 1 == t.n) ? 0 : a + 1;
+		b = (b + 1 == t.n) ? 0 : b + 1;
+	}
+	lcp = l;
+}
+
 // A4: lcpnext = max over i in [s,e), i != ep, of LCP(rot(i), rot(ep)), each LCP bounded by cap
 __global__ void __launch_bounds__(256)
 k_lcpnext(TextRef t, uint64_t s, uint64_t e, uint64_t ep, uint64_t cap, uint64_t skip_below, unsigned long long * __restrict__ out) {
 	uint64_t const i = s + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	uint64_t l = 0;
 	if (i < e && i != ep) {
-		uint64_t a = i, b = ep;
-		while (l < cap) {
-			int const x = text_sym(t, a), y = text_sym(t, b);
-			if (x != y || x < 0) break;
-			++l;
-			a = (a + 1 == t.n) ? 0 : a + 1;
-			b = (b + 1 == t.n) ? 0 : b + 1;
-		}
+		int sign;
+		cmp_lcp(t, i, ep, cap, l, sign);
 		if (l < skip_below) l = 0;
 	}
 	// warp maximum, one atomic per warp
@@ -61,28 +88,30 @@ k_lcpnext(TextRef t, uint64_t s, uint64_t e, uint64_t ep, uint64_t cap, uint64_t
 }
 
 // leaf: block BWT from the block's own suffixes in sorted order; the block-start suffix gets
-// the placeholder code 0 (bwtterm of the reference) and its row is recorded
+// the placeholder code 0 (bwtterm of the reference) and its row is recorded; the (rank,pos) anchors
+// of the block are picked up on the way
 __global__ void __launch_bounds__(256)
 k_leaf_emit(const uint8_t * __restrict__ codes, uint64_t s, const uint32_t * __restrict__ bsa, uint64_t mt, uint32_t shift,
-            uint8_t * __restrict__ L, uint32_t * __restrict__ special) {
+            uint64_t ratemask, uint32_t rateshift, uint8_t * __restrict__ L, uint32_t * __restrict__ special, uint32_t * __restrict__ prerank) {
 	uint64_t const k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (k >= mt) return;
 	uint32_t const i = bsa[k];
 	uint8_t c = 0;
 	if (i == 0) special[0] = (uint32_t)k + shift; else c = codes[s + i - 1];
 	L[k + shift] = c;
+	uint64_t const p = s + i;
+	if ((p & ratemask) == 0) prerank[p >> rateshift] = (uint32_t)k + shift;
 }
 
-// leaf: gt bits relative to the block start (Appendix A.3) and the (rank,pos) anchors
+// leaf: gt bits relative to the block start (Appendix A.3): gt[i] = [rot(i) > rot(s)], decided on the text
+// itself -- a streaming pass with coalesced writes instead of a rank-by-position scatter
 __global__ void __launch_bounds__(256)
-k_leaf_gt_samples(const uint32_t * __restrict__ brank, uint64_t mt, uint32_t shift, uint64_t s, uint64_t ratemask, uint32_t rateshift,
-                  uint8_t * __restrict__ gt, uint32_t * __restrict__ prerank) {
+k_leaf_gt(TextRef t, uint64_t s, uint64_t mt, uint8_t * __restrict__ gt) {
 	uint64_t const i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= mt) return;
-	uint32_t const r = brank[i], r0 = brank[0];
-	gt[s + i] = r > r0;
-	uint64_t const p = s + i;
-	if ((p & ratemask) == 0) prerank[p >> rateshift] = r + shift;
+	int sign = 0;
+	if (i) { uint64_t l; cmp_lcp(t, s + i, s, t.n, l, sign); }
+	gt[s + i] = sign > 0;
 }
 
 // number of suffixes of one leaf that are smaller than rot(z), for the start point z of every chain
@@ -221,7 +250,7 @@ struct EventAccum {
 	float total() { float t = 0; for (auto & p : ev) { float x = 0; cudaEventElapsedTime(&x, p.first, p.second); t += x; } return t; }
 };
 
-static TextRef text_ref(DevText const & T) { return TextRef{T.codes, T.ntext, T.n, T.has_term}; }
+static TextRef text_ref(DevText const & T) { return TextRef{T.codes, T.ntext, T.n, T.has_term, T.keybits == 2 ? T.packed : nullptr}; }
 
 static unsigned ilog2u(uint64_t v) { unsigned s = 0; while ((1ull << s) < v) ++s; return s; }
 
@@ -261,29 +290,26 @@ void Engine::leaf_build(BlockLeaf & leaf, uint64_t s, uint64_t m, uint8_t * L, u
 	}
 	leaf.s = s; leaf.mt = mt;
 	if (mt) {
-		DevBuf<uint32_t> wrank(st, W);
 		{
 			DevBuf<uint32_t> wsa;
-			// the rank by position is only asked of the sort when the window is the block itself; otherwise the
-			// compaction below writes the block-local ranks anyway (one random scatter instead of two)
-			k2_suffix_sort(st, T, s, W, 0, T.has_term ? 0 : 1, wsa, W == mt ? wrank.get() : nullptr, ss, nullptr);
+			// no rank by position is needed: gt bits come from the text, anchors from the sorted order
+			k2_suffix_sort(st, T, s, W, 0, T.has_term ? 0 : 1, wsa, nullptr, ss, nullptr);
 			leaf.sa.alloc(st, mt);
-			// keep the block's own suffixes, in order; wrank becomes the block-local rank by position
+			// keep the block's own suffixes, in order
 			const uint32_t * sa = wsa.get();
 			uint32_t * bsa = leaf.sa.get();
-			uint32_t * br = wrank.get();
 			uint64_t const mtl = mt;
 			if (W == mt) {
 				B3M_CUDA(cudaMemcpyAsync(bsa, sa, 4 * mt, cudaMemcpyDeviceToDevice, st.s));
 			} else {
 				scan_apply<OpSum>(st, W,
 					[=] __device__(uint64_t k) -> uint32_t { return sa[k] < mtl ? 1u : 0u; },
-					[=] __device__(uint64_t k, uint32_t excl, uint32_t v) { if (v) { uint32_t const i = sa[k]; bsa[excl] = i; br[i] = excl; } });
+					[=] __device__(uint64_t k, uint32_t excl, uint32_t v) { if (v) bsa[excl] = sa[k]; });
 			}
 		}
-		B3M_LAUNCH(st, k_leaf_emit, (unsigned)div_up(mt, 256), 256, 0, T.codes, s, (const uint32_t *)leaf.sa.get(), mt, shift, L, d_special.get());
-		B3M_LAUNCH(st, k_leaf_gt_samples, (unsigned)div_up(mt, 256), 256, 0, (const uint32_t *)wrank.get(), mt, shift, s, prerate - 1, ilog2u(prerate),
-		           gtp, prep);
+		B3M_LAUNCH(st, k_leaf_emit, (unsigned)div_up(mt, 256), 256, 0, T.codes, s, (const uint32_t *)leaf.sa.get(), mt, shift, prerate - 1, ilog2u(prerate),
+		           L, d_special.get(), prep);
+		B3M_LAUNCH(st, k_leaf_gt, (unsigned)div_up(mt, 256), 256, 0, t, s, mt, gtp);
 		extract_bytes += mt * (4 + 32 + 1 + 4 + 1);
 	}
 	if (has_termsuffix) {

@@ -24,6 +24,7 @@ struct TextRef {
 	const uint8_t * codes;
 	uint64_t ntext, n;
 	int has_term;
+	const uint64_t * packed; // 2-bit packed copy (textview.cuh) or nullptr
 };
 
 struct CTab { uint32_t c[257]; }; // C[code] passed to kernels by value
