@@ -19,9 +19,9 @@ $(CSRC)/%.o: $(CSRC)/%.cpp $(wildcard $(CSRC)/*.h) include/b3m.h
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -ccbin $(CXX) -shared -o $@ $(OBJS)
 
-bin/%: cli/%.cpp $(LIB) include/b3m.h
+bin/%: cli/%.cpp $(LIB) include/b3m.h $(wildcard cli/*.h)
 	@mkdir -p bin
-	$(CXX) -std=c++17 -O2 -Wall -Iinclude -o $@ $< -Lbwtb3m_b200 -lb3m -Wl,-rpath,'$$ORIGIN/../bwtb3m_b200'
+	$(CXX) -std=c++17 -O2 -Wall -Iinclude -o $@ $< -Lbwtb3m_b200 -lb3m -lz -Wl,-rpath,'$$ORIGIN/../bwtb3m_b200'
 
 oracle:
 	$(MAKE) -s -C oracle

@@ -460,6 +460,112 @@ std::vector<uint8_t> RlDecoder::decodeAll(std::vector<std::string> const & fns, 
 	return out;
 }
 
+// ---- compactstream container [layout unpinned] ---------------------------------------------
+struct CompactWriter::Impl {
+	File f;
+	unsigned b;
+	uint64_t n = 0, acc = 0;
+	unsigned fill = 0; // bits held in acc
+	std::vector<uint8_t> out;
+	bool open = true;
+	Impl(std::string const & fn, unsigned bits) : f(fn, "wb"), b(bits) {}
+	void word() {
+		for (int i = 7; i >= 0; --i) out.push_back((uint8_t)(acc >> (8 * i)));
+		acc = 0; fill = 0;
+		if (out.size() >= (1u << 20)) { f.write(out.data(), out.size()); out.clear(); }
+	}
+};
+CompactWriter::CompactWriter(std::string const & fn, unsigned bits) : impl(new Impl(fn, bits)) {
+	if (bits < 1 || bits > 8) throw IoError("compact container: bits per symbol must be 1..8");
+	std::vector<uint8_t> h;
+	put_be64(h, bits); put_be64(h, 0); put_be64(h, 0); put_be64(h, 0);
+	impl->f.write(h.data(), h.size());
+}
+CompactWriter::~CompactWriter() {
+	try { flush(); } catch (...) {}
+}
+uint64_t CompactWriter::size() const { return impl->n; }
+void CompactWriter::write(const uint8_t * syms, size_t n) {
+	Impl & w = *impl;
+	if (!w.open) throw IoError("compact container: write after flush on " + w.f.fn);
+	unsigned const b = w.b;
+	for (size_t i = 0; i < n; ++i) {
+		uint64_t const v = syms[i];
+		if (v >> b) throw IoError("compact container: symbol does not fit the bits per symbol");
+		unsigned const room = 64 - w.fill;
+		if (b <= room) {
+			w.acc |= v << (room - b);
+			w.fill += b;
+			if (w.fill == 64) w.word();
+		} else { // the symbol straddles two words
+			unsigned const lo = b - room;
+			w.acc |= v >> lo;
+			w.word();
+			w.acc = (v & ((1ull << lo) - 1)) << (64 - lo);
+			w.fill = lo;
+		}
+	}
+	w.n += n;
+}
+void CompactWriter::flush() {
+	Impl & w = *impl;
+	if (!w.open) return;
+	w.open = false;
+	if (w.fill) w.word();
+	w.f.write(w.out.data(), w.out.size());
+	w.out.clear();
+	uint64_t const words = (w.n * w.b + 63) / 64;
+	std::vector<uint8_t> h;
+	put_be64(h, w.b); put_be64(h, w.n); put_be64(h, words); put_be64(h, words);
+	w.f.seek(0);
+	w.f.write(h.data(), h.size());
+	w.f.close();
+}
+
+struct CompactReader::Impl {
+	File f;
+	uint64_t n = 0, pos = 0;
+	unsigned b = 0;
+	std::vector<uint8_t> buf;
+	uint64_t bufbit = 0; // bit offset of buf[0] within the payload
+	explicit Impl(std::string const & fn) : f(fn, "rb") {}
+};
+CompactReader::CompactReader(std::string const & fn) : impl(new Impl(fn)) {
+	uint64_t const fsz = file_size(fn);
+	if (fsz < 32) throw IoError("compact file too short: " + fn);
+	uint8_t h[32];
+	impl->f.read(h, 32);
+	uint64_t const b = get_be64(h);
+	impl->n = get_be64(h + 8);
+	if (b < 1 || b > 8) throw IoError("compact file: unsupported bits per symbol in " + fn);
+	if (impl->n > (fsz - 32) * 8 / b) throw IoError("compact file: truncated: " + fn);
+	impl->b = (unsigned)b;
+}
+CompactReader::~CompactReader() {}
+uint64_t CompactReader::size() const { return impl->n; }
+unsigned CompactReader::bits() const { return impl->b; }
+size_t CompactReader::read(uint8_t * out, size_t want) {
+	Impl & r = *impl;
+	size_t const n = (size_t)std::min<uint64_t>(want, r.n - r.pos);
+	if (!n) return 0;
+	uint64_t const bit0 = r.pos * r.b, bit1 = (r.pos + n) * r.b;
+	uint64_t const byte0 = bit0 >> 3, byte1 = (bit1 + 7) >> 3;
+	r.buf.resize((size_t)(byte1 - byte0) + 1);
+	r.f.seek(32 + byte0);
+	r.f.read(r.buf.data(), (size_t)(byte1 - byte0));
+	r.buf[(size_t)(byte1 - byte0)] = 0;
+	unsigned const b = r.b;
+	uint32_t const mask = (1u << b) - 1u;
+	for (size_t i = 0; i < n; ++i) {
+		uint64_t const bit = bit0 + (uint64_t)i * b - (byte0 << 3);
+		size_t const by = (size_t)(bit >> 3);
+		uint32_t const two = ((uint32_t)r.buf[by] << 8) | r.buf[by + 1];
+		out[i] = (uint8_t)((two >> (16 - (unsigned)(bit & 7) - b)) & mask);
+	}
+	r.pos += n;
+	return n;
+}
+
 // ---- key=value arguments -------------------------------------------------------------------
 ArgInfo::ArgInfo(int argc, char ** argv) {
 	progname = argc ? argv[0] : "";

@@ -6,6 +6,7 @@
 //   .preisa    native uint64 (rank,pos) pairs          (/root/reference/src/hwtPreIsaToIsa.cpp:55-77)
 //   .preisa.meta  one big-endian number = rate         (/root/reference/src/hwtPreIsaToIsa.cpp:41,45-51)
 // Parity unpinned (libmaus2 internals, no golden bytes in the reference):
+//   .compact   CompactArrayWriterFile container: four big-endian numbers + MSB-first bit stream
 //   .hist      NumberMapSerialisation: big-endian uint64 count, then (symbol,count) pairs
 //   .bwt       run-length Huffman container: only the decoded run/symbol sequence is pinned
 //              (/root/reference/src/bwtb3mdecoderl.cpp:27-34); the byte layout here is this
@@ -105,6 +106,40 @@ public:
 	static uint64_t getLength(std::string const & file, uint64_t numthreads = 1) { return getLength(std::vector<std::string>(1, file), numthreads); }
 	// whole sequence into memory, blocks decoded by numthreads threads
 	static std::vector<uint8_t> decodeAll(std::vector<std::string> const & files, uint64_t numthreads);
+private:
+	struct Impl;
+	std::unique_ptr<Impl> impl;
+};
+
+// ---- compactstream container ----------------------------------------------------------------
+// What libmaus2::bitio::CompactArrayWriterFile writes and CompactDecoderWrapper reads
+// (/root/reference/src/fagzToCompact4.cpp:105,232,265; /root/reference/src/decodecompact.cpp:30-36).
+// Layout [parity unpinned, SURVEY 8c]: four big-endian uint64 (bits per symbol, number of symbols,
+// number of 64-bit words, the word count again as the array header), then the symbols MSB first in
+// a big-endian bit stream padded with zero bits to a whole number of 64-bit words.  The same layout
+// is what K1 (`k_unpack_compact`) and the oracle (`orc_decode_compact`) read.
+class CompactWriter {
+public:
+	CompactWriter(std::string const & fn, unsigned bits);
+	~CompactWriter();
+	// values must be < 2^bits
+	void write(const uint8_t * syms, size_t n);
+	// pads the last word, patches the counts into the header and closes the file
+	void flush();
+	uint64_t size() const;
+private:
+	struct Impl;
+	std::unique_ptr<Impl> impl;
+};
+
+class CompactReader {
+public:
+	explicit CompactReader(std::string const & fn);
+	~CompactReader();
+	uint64_t size() const;
+	unsigned bits() const;
+	// next (at most n) symbols, one per byte; returns how many were delivered (0 at the end)
+	size_t read(uint8_t * out, size_t n);
 private:
 	struct Impl;
 	std::unique_ptr<Impl> impl;

@@ -365,4 +365,41 @@ int b3m_bwt_encode_host(const char * bwtfn, const uint8_t * syms, uint64_t n, ch
 	catch (...) { set_err(err, errlen, "unknown error"); return 3; }
 }
 
+// the compactstream container on the host (converters, tests, bindings)
+int b3m_compact_write(const char * fn, unsigned bits, const uint8_t * syms, uint64_t n, char * err, size_t errlen) {
+	try {
+		if (!fn || (!syms && n)) throw Error("null argument");
+		CompactWriter w(fn, bits);
+		w.write(syms, n);
+		w.flush();
+		return 0;
+	} catch (std::exception const & ex) { set_err(err, errlen, ex.what()); return 2; }
+	catch (...) { set_err(err, errlen, "unknown error"); return 3; }
+}
+
+int b3m_compact_info(const char * fn, unsigned * bits, uint64_t * n, char * err, size_t errlen) {
+	try {
+		if (!fn || !bits || !n) throw Error("null argument");
+		CompactReader r(fn);
+		*bits = r.bits();
+		*n = r.size();
+		return 0;
+	} catch (std::exception const & ex) { set_err(err, errlen, ex.what()); return 2; }
+	catch (...) { set_err(err, errlen, "unknown error"); return 3; }
+}
+
+int b3m_compact_read(const char * fn, uint8_t * out, uint64_t cap, char * err, size_t errlen) {
+	try {
+		if (!fn || !out) throw Error("null argument");
+		CompactReader r(fn);
+		if (r.size() > cap) throw Error("output buffer too small");
+		uint64_t done = 0;
+		size_t got;
+		while ((got = r.read(out + done, (size_t)std::min<uint64_t>(r.size() - done, 1u << 20))) != 0) done += got;
+		if (done != r.size()) throw Error("compact file shorter than its header says");
+		return 0;
+	} catch (std::exception const & ex) { set_err(err, errlen, ex.what()); return 2; }
+	catch (...) { set_err(err, errlen, "unknown error"); return 3; }
+}
+
 } // extern "C"

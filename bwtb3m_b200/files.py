@@ -79,6 +79,26 @@ def write_bwt_host(bwtfn, syms):
         raise B3MError(err.value.decode(errors="replace"))
 
 
+def write_compact(fn, syms, bits):
+    """Compact container for inputtype=compactstream (CompactArrayWriterFile, fagzToCompact4.cpp:105,232,265)."""
+    a = np.ascontiguousarray(syms, dtype=np.uint8)
+    err = C.create_string_buffer(2048)
+    if lib().b3m_compact_write(_b(fn), bits, C.c_void_p(a.ctypes.data), a.size, err, len(err)) != 0:
+        raise B3MError(err.value.decode(errors="replace"))
+
+
+def read_compact(fn):
+    """(symbols one per byte, bits per symbol) of a compact container (CompactDecoderWrapper, decodecompact.cpp:30-36)."""
+    err = C.create_string_buffer(2048)
+    bits, n = C.c_uint(0), C.c_uint64(0)
+    if lib().b3m_compact_info(_b(fn), C.byref(bits), C.byref(n), err, len(err)) != 0:
+        raise B3MError(err.value.decode(errors="replace"))
+    out = np.empty(n.value, dtype=np.uint8)
+    if lib().b3m_compact_read(_b(fn), C.c_void_p(out.ctypes.data), n.value, err, len(err)) != 0:
+        raise B3MError(err.value.decode(errors="replace"))
+    return out, bits.value
+
+
 def read_sampled(fn):
     """.sa / .isa: native uint64 [rate][count][values] (/root/reference/src/sasubsample.cpp:34-58)."""
     a = np.fromfile(fn, dtype=np.uint64)

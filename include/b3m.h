@@ -117,6 +117,14 @@ int b3m_bwt_decode(const char * bwtfn, uint8_t * out, uint64_t cap, uint64_t num
  * b3m_compute_bwt encodes on the device and never calls it. */
 int b3m_bwt_encode_host(const char * bwtfn, const uint8_t * syms, uint64_t n, char * err, size_t errlen);
 
+/* The compactstream container (`inputtype=compactstream`) for bindings that cannot link C++: replaces
+ * libmaus2::bitio::CompactArrayWriterFile(fn,b) + write + flush (/root/reference/src/fagzToCompact4.cpp:105,232,265;
+ * /root/reference/src/digitsToCompact.cpp:35,79,89) and libmaus2::bitio::CompactDecoderWrapper
+ * (/root/reference/src/decodecompact.cpp:30-36).  bits = 1..8, symbols one per byte. */
+int b3m_compact_write(const char * fn, unsigned bits, const uint8_t * syms, uint64_t n, char * err, size_t errlen);
+int b3m_compact_info(const char * fn, unsigned * bits, uint64_t * n, char * err, size_t errlen);
+int b3m_compact_read(const char * fn, uint8_t * out, uint64_t cap, char * err, size_t errlen);
+
 /* ------------------------------------------------------------------------------------------
  * Engine level: the same path on caller-owned host or device buffers.  One engine per GPU and
  * per host thread; the engine owns its device memory and enqueues everything on one stream.

@@ -197,6 +197,45 @@ def test_checkbwt_tool_and_abi(tmp_path, oracle, itype):
     assert not ok
 
 
+def test_fasta_to_compactstream_pipeline(tmp_path, oracle):
+    """README's DNA route: fagzToCompact4 (forward + reverse complement, N runs replaced) -> bwtb3m inputtype=compactstream
+    -> checkbwt -i compactstream; the .bwt equals the naive BWT of the symbols the oracle reads from the container."""
+    import gzip
+    from bwtb3m_b200 import files
+    rng = np.random.default_rng(23)
+    lines = []
+    for k, l in enumerate((30_001, 12_345, 77)):
+        seq = "".join(rng.choice(list("ACGT"), size=l))
+        if k == 0:
+            seq = seq[:1000] + "N" * 500 + seq[1500:]
+        lines.append(">seq%d" % k)
+        lines.extend(seq[i:i + 70] for i in range(0, l, 70))
+    fa = tmp_path / "g.fa.gz"
+    fa.write_bytes(gzip.compress(("\n".join(lines) + "\n").encode()))
+    r = subprocess.run([os.path.join(BIN, "fagzToCompact4"), "verbose=0", str(fa)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    cfn = tmp_path / "g.compact"
+    t, bits = oracle.decode_compact(cfn.read_bytes())
+    assert bits == 2 and t.size == 2 * (30_001 + 12_345 + 77)
+    sa = oracle.sa_circular(t)
+    bwt, isa = oracle.bwt_from_sa(t, sa)
+    out = tmp_path / "g.bwt"
+    r = subprocess.run([os.path.join(BIN, "bwtb3m"), "inputtype=compactstream", "outputfilename=" + str(out), "sasamplingrate=16",
+                        "isasamplingrate=64", str(cfn)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert np.array_equal(files.read_bwt(str(out)), bwt)
+    rate, v = files.read_sampled(str(tmp_path / "g.sa"))
+    assert rate == 16 and np.array_equal(v, sa[::16].astype(np.uint64))
+    rate, v = files.read_sampled(str(tmp_path / "g.isa"))
+    assert rate == 64 and np.array_equal(v, isa[::64].astype(np.uint64))
+    # the verifier reads the same container (needs the anchors: rebuild with bwtonly=1, which keeps .preisa)
+    res = files.compute_bwt(str(cfn), inputtype="compactstream", outputfilename=str(tmp_path / "v.bwt"), bwtonly=True)
+    ok, bad = files.check_bwt(res["bwtfn"], str(cfn), inputtype="compactstream")
+    assert ok and bad == 0
+    r = subprocess.run([os.path.join(BIN, "checkbwt"), "-i", "compactstream", res["bwtfn"], str(cfn)], capture_output=True, text=True)
+    assert r.returncode == 0 and "[V] gok=1" in r.stderr
+
+
 def test_lf_speed_instrument(tmp_path, oracle):
     """bwttestdecodespeed on the GPU: runs from the files bwtb3m wrote and reports a positive rate."""
     from bwtb3m_b200 import files

@@ -65,6 +65,30 @@ def test_random_bytestream_vs_oracle(eng, oracle, seed, n, sigma):
     assert np.array_equal(res["isa"], isa[::128].astype(np.uint64))
 
 
+@pytest.mark.parametrize("bits,n,sigma", [(2, 70_001, 4), (3, 10_000, 5), (4, 33_333, 11), (8, 20_000, 256), (1, 4_097, 2), (2, 1, 4),
+                                          (5, 64, 32), (7, 250_003, 100)])
+def test_random_compactstream_vs_oracle(eng, oracle, bits, n, sigma):
+    """inputtype=compactstream (K1 k_unpack_compact): container written by the oracle's numpy writer, symbols of every
+    width incl. ones that straddle bytes and 64-bit words; same result as the naive sort of the decoded symbols."""
+    rng = np.random.default_rng(100 * bits + sigma)
+    t = rng.integers(0, sigma, size=n, dtype=np.uint8)
+    data = oracle.encode_compact(t, bits)
+    dec, b = oracle.decode_compact(data.tobytes())
+    assert b == bits and np.array_equal(dec, t)
+    sa = oracle.sa_circular(t)
+    bwt, isa = oracle.bwt_from_sa(t, sa)
+    res, info = run(eng, data, "compactstream", preisarate=64, sasamplingrate=32, isasamplingrate=128)
+    assert info["n"] == n
+    assert np.array_equal(res["bwt"], bwt)
+    assert np.array_equal(res["preisa"][:, 0], isa[::64].astype(np.uint64))
+    assert np.array_equal(res["sa"], sa[::32].astype(np.uint64))
+    assert np.array_equal(res["isa"], isa[::128].astype(np.uint64))
+    # several blocks: same BWT
+    if n > 1000:
+        res3, _ = run(eng, data, "compactstream", numblocks=3, preisarate=64, sasamplingrate=32, isasamplingrate=128)
+        assert np.array_equal(res3["bwt"], bwt) and np.array_equal(res3["sa"], res["sa"]) and np.array_equal(res3["isa"], res["isa"])
+
+
 @pytest.mark.parametrize("seed,l", [(11, 8), (12, 1001), (13, 65536), (14, 250003), (15, 3), (16, 16), (17, 15)])
 @pytest.mark.parametrize("itype", ["pac", "pacterm"])
 def test_random_pac_vs_oracle(eng, oracle, seed, l, itype):
