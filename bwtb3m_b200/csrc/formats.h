@@ -117,7 +117,7 @@ private:
 // Layout [parity unpinned, SURVEY 8c]: four big-endian uint64 (bits per symbol, number of symbols,
 // number of 64-bit words, the word count again as the array header), then the symbols MSB first in
 // a big-endian bit stream padded with zero bits to a whole number of 64-bit words.  The same layout
-// is what K1 (`k_unpack_compact`) and the oracle (`orc_decode_compact`) read.
+// is what K1 (`k_unpack_compact`) reads on the device.
 class CompactWriter {
 public:
 	CompactWriter(std::string const & fn, unsigned bits);
