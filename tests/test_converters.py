@@ -13,6 +13,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "bin")
 
 
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    subprocess.check_call(["make", "-s", "-C", ROOT, "all"])
+
+
 @pytest.mark.parametrize("bits", [1, 2, 3, 4, 5, 7, 8])
 @pytest.mark.parametrize("n", [0, 1, 21, 64, 1000, 70_001])
 def test_compact_container_roundtrip_vs_oracle(tmp_path, oracle, bits, n):
