@@ -1,4 +1,4 @@
-"""CPU, gloo, world size 2 and 3: the suffix-range sharding driver (bwtb3m_b200.multigpu.build_sharded)
+"""CPU, gloo, world size 2, 3 and 4: the suffix-range sharding driver (bwtb3m_b200.multigpu.build_sharded)
 with a model engine that writes its slice from the oracle's suffix array -- exercises the zeroed
 global-place buffers, the unresolved vote and the sum-reduce to rank 0."""
 import ctypes as C
@@ -88,7 +88,7 @@ def _worker(rank, world, port, force, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,force", [(2, None), (3, None), (2, 1)])
+@pytest.mark.parametrize("world,force", [(2, None), (3, None), (4, None), (2, 1)])
 def test_sharded_driver_gloo(world, force):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
