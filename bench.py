@@ -7,7 +7,10 @@ A step = one pass of the hot path (K1 decode -> K2 sort -> K3 extract -> [K5 gap
 K4 dictionary -> K7 SA/ISA walk) over one synthetic input.  `value`: inputs already resident in
 HBM; `e2e`: the same through the C ABI with pinned HOST buffers (H2D of the input file bytes,
 D2H of BWT + anchors + SA + ISA inside the timed region).  The CPU oracle is executed only for
-the `cpu_baseline` leg and by `--impl reference`.
+the `cpu_baseline` leg and by `--impl reference`.  The metric's second half, LF-steps/s, is
+`lf_steps_per_s` (K7's dictionary, 2^20 chains x 256 dependent steps on the GPU) next to
+`cpu_baseline.lf_steps_per_s` (the reference's bwttestdecodespeed instrument restated: 8 interleaved
+chains on one host thread over the BWT of the CPU sample; measured outside the timed build).
 """
 import argparse
 import json
@@ -112,7 +115,7 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_oracle_run(itype, filebytes, nsyms_limit, params, threads):
+def cpu_oracle_run(itype, filebytes, nsyms_limit, params, threads, want_lf=False):
     """Times the CPU oracle (restated reference algorithm) on a prefix of the workload."""
     from oracle import oracle as orc
     orc.build()
@@ -131,6 +134,11 @@ def cpu_oracle_run(itype, filebytes, nsyms_limit, params, threads):
     if not params["bwtonly"]:
         orc.ssa(bwt, pp, params["sasamplingrate"], params["isasamplingrate"], nthreads=threads)
     dt = time.perf_counter() - t0
+    if want_lf:
+        # LF-steps/s on the host, outside the timed build: the reference's instrument (bwttestdecodespeed.cpp:67-97),
+        # 8 interleaved dependent chains on one thread over the BWT of the sample, started at anchor ranks
+        lf = orc.lf_speed(bwt, pp[:, 0], tpar=8, maxsteps=1 << 21)
+        return dt, n, nblocks, lf
     return dt, n, nblocks
 
 
@@ -329,9 +337,10 @@ def run_ours(args):
     cpu = None
     if not args.no_cpu and world == 1:
         sample = min(nsym, args.cpu_sample)
-        dt, nn, nblocks = cpu_oracle_run(itype, data, sample, params, threads)
+        dt, nn, nblocks, cpu_lf = cpu_oracle_run(itype, data, sample, params, threads, want_lf=True)
         cpu = {"value": sample / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port", "seconds": dt,
-               "sample": "first %d symbols of the workload, %d blocks, full pipeline; restated reference (libmaus2 unavailable)" % (sample, nblocks)}
+               "sample": "first %d symbols of the workload, %d blocks, full pipeline; restated reference (libmaus2 unavailable)" % (sample, nblocks),
+               "lf_steps_per_s": cpu_lf, "lf_instrument": "bwttestdecodespeed restated: 8 interleaved chains, 1 thread, BWT of the sample"}
 
     total_s = total_ms * 1e-3
     line = {
