@@ -104,18 +104,27 @@ void Engine::load(const void * input, uint64_t nbytes, int itype, bool on_device
 	} else {
 		uint64_t nsym;
 		if (itype == B3M_INPUT_COMPACTSTREAM) {
-			// [layout unpinned, SURVEY 8c] 4 big-endian uint64: bits, n, words, words; then the bit stream
+			// [layout unpinned, SURVEY 8c] the serialised CompactArray the reference's writers leave behind
+			// (/root/reference/src/digitsToCompact.cpp:35,122): 4 uint64 (bits, n, words, words), then the words.
+			// Both byte orders are accepted: native little-endian numbers and words (what libmaus2's
+			// Serialize<uint64_t> writes) or big-endian numbers with a big-endian bit stream; bits per
+			// symbol is 1..8 in exactly one of the two readings.
 			B3M_REQUIRE(nbytes >= 32, "compact file too short");
 			uint8_t hdr[16];
 			peek(0, 16, hdr);
-			uint64_t b = 0, n = 0;
-			for (int i = 0; i < 8; ++i) { b = (b << 8) | hdr[i]; n = (n << 8) | hdr[8 + i]; }
+			uint64_t bb = 0, nb = 0, bl = 0, nl = 0;
+			for (int i = 0; i < 8; ++i) {
+				bb = (bb << 8) | hdr[i]; nb = (nb << 8) | hdr[8 + i];
+				bl = (bl << 8) | hdr[7 - i]; nl = (nl << 8) | hdr[15 - i];
+			}
+			bool const le_words = !(bb >= 1 && bb <= 8);
+			uint64_t const b = le_words ? bl : bb, n = le_words ? nl : nb;
 			B3M_REQUIRE(b >= 1 && b <= 8, "compact file: unsupported bits per symbol");
-			B3M_REQUIRE((n * b + 7) / 8 <= nbytes - 32, "compact file: truncated");
+			B3M_REQUIRE(n <= (nbytes - 32) * 8 / b && (!le_words || (n * b + 63) / 64 * 8 <= nbytes - 32), "compact file: truncated");
 			B3M_REQUIRE(n > 0, "empty input");
 			stage(32, nbytes - 32, 8);
 			codes.alloc(st, n + 16);
-			k1_unpack_compact(st, d_in, n, (unsigned)b, codes.get(), d_hist.get());
+			k1_unpack_compact(st, d_in, n, (unsigned)b, le_words, codes.get(), d_hist.get());
 			nsym = n;
 		} else {
 			B3M_REQUIRE(nbytes > 0, "empty input");

@@ -461,6 +461,8 @@ std::vector<uint8_t> RlDecoder::decodeAll(std::vector<std::string> const & fns, 
 }
 
 // ---- compactstream container [layout unpinned] ---------------------------------------------
+static void put_le64(std::vector<uint8_t> & o, uint64_t v) { for (int i = 0; i < 8; ++i) o.push_back((uint8_t)(v >> (8 * i))); }
+static uint64_t get_le64(const uint8_t * p) { uint64_t v = 0; for (int i = 7; i >= 0; --i) v = (v << 8) | p[i]; return v; }
 struct CompactWriter::Impl {
 	File f;
 	unsigned b;
@@ -469,8 +471,8 @@ struct CompactWriter::Impl {
 	std::vector<uint8_t> out;
 	bool open = true;
 	Impl(std::string const & fn, unsigned bits) : f(fn, "wb"), b(bits) {}
-	void word() {
-		for (int i = 7; i >= 0; --i) out.push_back((uint8_t)(acc >> (8 * i)));
+	void word() { // native little-endian uint64, the first symbol in its top bits
+		for (int i = 0; i < 8; ++i) out.push_back((uint8_t)(acc >> (8 * i)));
 		acc = 0; fill = 0;
 		if (out.size() >= (1u << 20)) { f.write(out.data(), out.size()); out.clear(); }
 	}
@@ -478,7 +480,7 @@ struct CompactWriter::Impl {
 CompactWriter::CompactWriter(std::string const & fn, unsigned bits) : impl(new Impl(fn, bits)) {
 	if (bits < 1 || bits > 8) throw IoError("compact container: bits per symbol must be 1..8");
 	std::vector<uint8_t> h;
-	put_be64(h, bits); put_be64(h, 0); put_be64(h, 0); put_be64(h, 0);
+	put_le64(h, bits); put_le64(h, 0); put_le64(h, 0); put_le64(h, 0);
 	impl->f.write(h.data(), h.size());
 }
 CompactWriter::~CompactWriter() {
@@ -516,7 +518,7 @@ void CompactWriter::flush() {
 	w.out.clear();
 	uint64_t const words = (w.n * w.b + 63) / 64;
 	std::vector<uint8_t> h;
-	put_be64(h, w.b); put_be64(h, w.n); put_be64(h, words); put_be64(h, words);
+	put_le64(h, w.b); put_le64(h, w.n); put_le64(h, words); put_le64(h, words);
 	w.f.seek(0);
 	w.f.write(h.data(), h.size());
 	w.f.close();
@@ -526,8 +528,8 @@ struct CompactReader::Impl {
 	File f;
 	uint64_t n = 0, pos = 0;
 	unsigned b = 0;
+	bool le_words = false; // words stored as native little-endian uint64 (else: big-endian byte stream)
 	std::vector<uint8_t> buf;
-	uint64_t bufbit = 0; // bit offset of buf[0] within the payload
 	explicit Impl(std::string const & fn) : f(fn, "rb") {}
 };
 CompactReader::CompactReader(std::string const & fn) : impl(new Impl(fn)) {
@@ -535,10 +537,12 @@ CompactReader::CompactReader(std::string const & fn) : impl(new Impl(fn)) {
 	if (fsz < 32) throw IoError("compact file too short: " + fn);
 	uint8_t h[32];
 	impl->f.read(h, 32);
-	uint64_t const b = get_be64(h);
+	// bits per symbol is 1..8 in exactly one of the two byte orders (formats.h)
+	uint64_t b = get_be64(h);
 	impl->n = get_be64(h + 8);
+	if (b < 1 || b > 8) { b = get_le64(h); impl->n = get_le64(h + 8); impl->le_words = true; }
 	if (b < 1 || b > 8) throw IoError("compact file: unsupported bits per symbol in " + fn);
-	if (impl->n > (fsz - 32) * 8 / b) throw IoError("compact file: truncated: " + fn);
+	if (impl->n > (fsz - 32) * 8 / b || (impl->le_words && (impl->n * b + 63) / 64 * 8 > fsz - 32)) throw IoError("compact file: truncated: " + fn);
 	impl->b = (unsigned)b;
 }
 CompactReader::~CompactReader() {}
@@ -549,17 +553,19 @@ size_t CompactReader::read(uint8_t * out, size_t want) {
 	size_t const n = (size_t)std::min<uint64_t>(want, r.n - r.pos);
 	if (!n) return 0;
 	uint64_t const bit0 = r.pos * r.b, bit1 = (r.pos + n) * r.b;
-	uint64_t const byte0 = bit0 >> 3, byte1 = (bit1 + 7) >> 3;
-	r.buf.resize((size_t)(byte1 - byte0) + 1);
+	// whole 64-bit words around the wanted bits, so that the little-endian flip stays inside the buffer
+	uint64_t const byte0 = (bit0 >> 6) << 3, byte1 = ((bit1 + 63) >> 6) << 3;
+	uint64_t const have = std::min<uint64_t>(byte1, file_size(r.f.fn) - 32) - byte0;
+	r.buf.assign((size_t)(byte1 - byte0) + 8, 0);
 	r.f.seek(32 + byte0);
-	r.f.read(r.buf.data(), (size_t)(byte1 - byte0));
-	r.buf[(size_t)(byte1 - byte0)] = 0;
+	r.f.read(r.buf.data(), (size_t)have);
 	unsigned const b = r.b;
 	uint32_t const mask = (1u << b) - 1u;
+	size_t const flip = r.le_words ? 7 : 0;
 	for (size_t i = 0; i < n; ++i) {
 		uint64_t const bit = bit0 + (uint64_t)i * b - (byte0 << 3);
 		size_t const by = (size_t)(bit >> 3);
-		uint32_t const two = ((uint32_t)r.buf[by] << 8) | r.buf[by + 1];
+		uint32_t const two = ((uint32_t)r.buf[by ^ flip] << 8) | r.buf[(by + 1) ^ flip];
 		out[i] = (uint8_t)((two >> (16 - (unsigned)(bit & 7) - b)) & mask);
 	}
 	r.pos += n;

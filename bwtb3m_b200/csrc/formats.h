@@ -6,7 +6,7 @@
 //   .preisa    native uint64 (rank,pos) pairs          (/root/reference/src/hwtPreIsaToIsa.cpp:55-77)
 //   .preisa.meta  one big-endian number = rate         (/root/reference/src/hwtPreIsaToIsa.cpp:41,45-51)
 // Parity unpinned (libmaus2 internals, no golden bytes in the reference):
-//   .compact   CompactArrayWriterFile container: four big-endian numbers + MSB-first bit stream
+//   .compact   CompactArrayWriterFile container: four numbers + 64-bit words, symbols MSB first (either byte order is read)
 //   .hist      NumberMapSerialisation: big-endian uint64 count, then (symbol,count) pairs
 //   .bwt       run-length Huffman container: only the decoded run/symbol sequence is pinned
 //              (/root/reference/src/bwtb3mdecoderl.cpp:27-34); the byte layout here is this
@@ -114,10 +114,12 @@ private:
 // ---- compactstream container ----------------------------------------------------------------
 // What libmaus2::bitio::CompactArrayWriterFile writes and CompactDecoderWrapper reads
 // (/root/reference/src/fagzToCompact4.cpp:105,232,265; /root/reference/src/decodecompact.cpp:30-36).
-// Layout [parity unpinned, SURVEY 8c]: four big-endian uint64 (bits per symbol, number of symbols,
-// number of 64-bit words, the word count again as the array header), then the symbols MSB first in
-// a big-endian bit stream padded with zero bits to a whole number of 64-bit words.  The same layout
-// is what K1 (`k_unpack_compact`) reads on the device.
+// Layout [parity unpinned, SURVEY 8c]: the serialised CompactArray (/root/reference/src/digitsToCompact.cpp:122 reads
+// the writer's file back as one): four uint64 (bits per symbol, number of symbols, number of 64-bit words, the word
+// count again as the array header), then the words; symbols MSB first inside a word, the last word zero padded.
+// Byte order: the writer emits native little-endian numbers and words (libmaus2's Serialize<uint64_t>, the facility
+// behind .sa/.isa, /root/reference/src/sasubsample.cpp:34-58); the reader and K1 (`k_unpack_compact`) also accept
+// big-endian numbers with a big-endian bit stream -- bits per symbol is 1..8 in exactly one of the two readings.
 class CompactWriter {
 public:
 	CompactWriter(std::string const & fn, unsigned bits);

@@ -127,9 +127,10 @@ void k1_unpack_pac(Stream & st, const uint8_t * d_pac, uint64_t l, uint8_t * d_o
 	B3M_LAUNCH(st, k_unpack_pac, grid, 256, 0, d_pac, l, d_out, (unsigned long long *)d_hist256);
 }
 
-// compactstream payload: b-bit symbols, MSB first, in a big-endian bit stream [layout unpinned,
-// SURVEY 8c]; one thread per symbol (b <= 8).
-__global__ void __launch_bounds__(256) k_unpack_compact(const uint8_t * __restrict__ d, uint64_t n, unsigned b, uint8_t * __restrict__ out,
+// compactstream payload: b-bit symbols, MSB first, in 64-bit words [layout unpinned, SURVEY 8c].  The words lie
+// either as a big-endian byte stream (flip = 0) or as native little-endian uint64 (flip = 7: byte k of the bit
+// stream is byte k ^ 7 of the file, what libmaus2's native Serialize<uint64_t> writes); one thread per symbol (b <= 8).
+__global__ void __launch_bounds__(256) k_unpack_compact(const uint8_t * __restrict__ d, uint64_t n, unsigned b, unsigned flip, uint8_t * __restrict__ out,
                                                         unsigned long long * __restrict__ hist) {
 	__shared__ uint32_t sh[256];
 	sh[threadIdx.x] = 0;
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(256) k_unpack_compact(const uint8_t * __restri
 	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
 		uint64_t const bit = i * b;
 		uint64_t const byte = bit >> 3;
-		uint32_t const two = ((uint32_t)d[byte] << 8) | (uint32_t)d[byte + 1]; // one pad byte is guaranteed by the loader
+		uint32_t const two = ((uint32_t)d[byte ^ flip] << 8) | (uint32_t)d[(byte + 1) ^ flip]; // eight pad bytes are guaranteed by the loader
 		uint32_t const v = (two >> (16 - (bit & 7) - b)) & ((1u << b) - 1u);
 		out[i] = (uint8_t)v;
 		atomicAdd(&sh[v], 1u);
@@ -146,12 +147,12 @@ __global__ void __launch_bounds__(256) k_unpack_compact(const uint8_t * __restri
 	if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
 }
 
-void k1_unpack_compact(Stream & st, const uint8_t * d_words, uint64_t n, unsigned b, uint8_t * d_out, uint64_t * d_hist256) {
+void k1_unpack_compact(Stream & st, const uint8_t * d_words, uint64_t n, unsigned b, bool le_words, uint8_t * d_out, uint64_t * d_hist256) {
 	B3M_CUDA(cudaMemsetAsync(d_hist256, 0, 256 * sizeof(uint64_t), st.s));
 	if (!n) return;
 	uint64_t want = div_up(n, 256 * 16);
 	unsigned grid = (unsigned)(want < (uint64_t)st.sms * 16 ? (want ? want : 1) : (uint64_t)st.sms * 16);
-	B3M_LAUNCH(st, k_unpack_compact, grid, 256, 0, d_words, n, b, d_out, (unsigned long long *)d_hist256);
+	B3M_LAUNCH(st, k_unpack_compact, grid, 256, 0, d_words, n, b, le_words ? 7u : 0u, d_out, (unsigned long long *)d_hist256);
 }
 
 // 2-bit packed copy of the codes (textview.cuh): 32 symbols per uint64, first symbol in the top bits

@@ -120,7 +120,10 @@ int b3m_bwt_encode_host(const char * bwtfn, const uint8_t * syms, uint64_t n, ch
 /* The compactstream container (`inputtype=compactstream`) for bindings that cannot link C++: replaces
  * libmaus2::bitio::CompactArrayWriterFile(fn,b) + write + flush (/root/reference/src/fagzToCompact4.cpp:105,232,265;
  * /root/reference/src/digitsToCompact.cpp:35,79,89) and libmaus2::bitio::CompactDecoderWrapper
- * (/root/reference/src/decodecompact.cpp:30-36).  bits = 1..8, symbols one per byte. */
+ * (/root/reference/src/decodecompact.cpp:30-36).  bits = 1..8, symbols one per byte.  The file is a serialised
+ * CompactArray (/root/reference/src/digitsToCompact.cpp:122): four uint64 (bits, n, words, words) and the 64-bit words,
+ * symbols MSB first in a word; written with native little-endian numbers and words, read in either byte order
+ * (the byte order is not pinned by anything in the reference). */
 int b3m_compact_write(const char * fn, unsigned bits, const uint8_t * syms, uint64_t n, char * err, size_t errlen);
 int b3m_compact_info(const char * fn, unsigned * bits, uint64_t * n, char * err, size_t errlen);
 int b3m_compact_read(const char * fn, uint8_t * out, uint64_t cap, char * err, size_t errlen);

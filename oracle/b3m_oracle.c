@@ -80,32 +80,46 @@ uint64_t orc_encode_pac(const uint8_t *syms, uint64_t l, uint8_t *file)
 	return p;
 }
 
-/* compactstream [parity unpinned, SURVEY 8c]: 8-byte BE b, 8-byte BE n, 8-byte BE word count,
- * 8-byte BE word count (array header), then 64-bit BE words holding b-bit symbols MSB first. */
+/* compactstream [parity unpinned, SURVEY 8c]: the serialised CompactArray the reference's writers leave
+ * behind [REF digitsToCompact.cpp:35,122; arraytocompact.cpp:78,100]: four uint64 (b, n, word count, word
+ * count again as the array header), then 64-bit words holding b-bit symbols MSB first.  The byte order of
+ * the numbers and words is not pinned by anything in the reference: libmaus2's Serialize<uint64_t> (the
+ * facility the .sa/.isa files use, [REF sasubsample.cpp:34-58]) is native little-endian; a big-endian
+ * reading is accepted too.  b is 1..64 in exactly one of the two readings. */
 static uint64_t be64(const uint8_t *p)
 {
 	uint64_t v = 0;
 	for (int i = 0; i < 8; ++i) v = (v << 8) | p[i];
 	return v;
 }
+static uint64_t le64(const uint8_t *p)
+{
+	uint64_t v = 0;
+	for (int i = 7; i >= 0; --i) v = (v << 8) | p[i];
+	return v;
+}
+/* returns 0 = big-endian layout, 1 = little-endian words, -1 = not a compact file */
 int orc_compact_header(const uint8_t *file, uint64_t fsize, uint64_t *b, uint64_t *n)
 {
 	if (fsize < 32) return -1;
-	*b = be64(file);
-	*n = be64(file + 8);
-	return 0;
+	uint64_t const bb = be64(file), bl = le64(file);
+	if (bb >= 1 && bb <= 64) { *b = bb; *n = be64(file + 8); return 0; }
+	if (bl >= 1 && bl <= 64) { *b = bl; *n = le64(file + 8); return 1; }
+	return -1;
 }
 uint64_t orc_decode_compact(const uint8_t *file, uint64_t fsize, uint8_t *out)
 {
 	uint64_t b, n;
-	if (orc_compact_header(file, fsize, &b, &n)) return 0;
+	int const le = orc_compact_header(file, fsize, &b, &n);
+	if (le < 0 || b > 8) return 0;
 	const uint8_t *d = file + 32;
 	for (uint64_t i = 0; i < n; ++i) {
 		uint64_t v = 0;
 		for (uint64_t k = 0; k < b; ++k) {
-			uint64_t const bit = i * b + k;
-			uint64_t const byte = bit >> 3;
-			v = (v << 1) | ((d[byte] >> (7 - (bit & 7))) & 1);
+			uint64_t const bit = i * b + k; /* bit 0 = MSB of word 0 */
+			uint64_t const word = bit >> 6, inword = bit & 63;
+			uint64_t const w = le ? le64(d + 8 * word) : be64(d + 8 * word);
+			v = (v << 1) | ((w >> (63 - inword)) & 1);
 		}
 		out[i] = (uint8_t)v;
 	}

@@ -78,29 +78,35 @@ def decode_pac(filebytes, term):
 
 
 def decode_compact(filebytes):
-    """Symbols (one per byte) and bits per symbol of a compactstream container
+    """Symbols (one per byte) and bits per symbol of a compactstream container, either byte order
     [layout unpinned; the reader the reference uses is CompactDecoderWrapper, decodecompact.cpp:30-36]."""
     f = _u8(np.frombuffer(bytes(filebytes), dtype=np.uint8))
     assert f.size >= 32
     b = int.from_bytes(f[0:8].tobytes(), "big")
     n = int.from_bytes(f[8:16].tobytes(), "big")
+    if not 1 <= b <= 64:
+        b = int.from_bytes(f[0:8].tobytes(), "little")
+        n = int.from_bytes(f[8:16].tobytes(), "little")
     out = np.empty(n, dtype=np.uint8)
     got = lib().orc_decode_compact(_p(f, C.c_uint8), f.size, _p(out, C.c_uint8))
     assert got == n
     return out, b
 
 
-def encode_compact(syms, bits):
+def encode_compact(syms, bits, layout="le"):
     """The container CompactArrayWriterFile(fn, bits) leaves behind (fagzToCompact4.cpp:105,232,265), as numpy
-    bit arithmetic independent of the product's writer: 4 big-endian uint64 (bits, n, words, words), then the
-    symbols MSB first, zero padded to whole 64-bit words."""
+    bit arithmetic independent of the product's writer: 4 uint64 (bits, n, words, words), then 64-bit words with the
+    symbols MSB first, zero padded.  layout "le": native little-endian numbers and words; "be": big-endian."""
     s = _u8(syms)
-    assert 1 <= bits <= 8 and (s.size == 0 or int(s.max()) < (1 << bits))
+    assert 1 <= bits <= 8 and (s.size == 0 or int(s.max()) < (1 << bits)) and layout in ("le", "be")
     allbits = np.unpackbits(s.reshape(-1, 1), axis=1)[:, 8 - bits:].reshape(-1)
     words = (s.size * bits + 63) // 64
     pad = words * 64 - allbits.size
-    payload = np.packbits(np.concatenate([allbits, np.zeros(pad, dtype=np.uint8)]))
-    hdr = b"".join(int(v).to_bytes(8, "big") for v in (bits, s.size, words, words))
+    payload = np.packbits(np.concatenate([allbits, np.zeros(pad, dtype=np.uint8)]))  # big-endian bit stream
+    order = "big" if layout == "be" else "little"
+    if layout == "le":
+        payload = payload.reshape(-1, 8)[:, ::-1].reshape(-1)
+    hdr = b"".join(int(v).to_bytes(8, order) for v in (bits, s.size, words, words))
     return np.frombuffer(hdr + payload.tobytes(), dtype=np.uint8).copy()
 
 

@@ -26,12 +26,21 @@ def test_compact_container_roundtrip_vs_oracle(tmp_path, oracle, bits, n):
     fn = str(tmp_path / "t.compact")
     files.write_compact(fn, t, bits)
     raw = np.fromfile(fn, dtype=np.uint8)
-    # same bytes as the independent numpy writer, same symbols through the oracle's reader and ours
-    assert raw.tobytes() == oracle.encode_compact(t, bits).tobytes()
+    # same bytes as the independent numpy writer (native little-endian words), same symbols through the oracle's reader and ours
+    assert raw.tobytes() == oracle.encode_compact(t, bits, "le").tobytes()
     got, b = oracle.decode_compact(raw.tobytes())
     assert b == bits and np.array_equal(got, t)
     got2, b2 = files.read_compact(fn)
     assert b2 == bits and np.array_equal(got2, t)
+    # the big-endian reading of the container is accepted by both readers too
+    be = oracle.encode_compact(t, bits, "be")
+    got, b = oracle.decode_compact(be.tobytes())
+    assert b == bits and np.array_equal(got, t)
+    be.tofile(fn)
+    got2, b2 = files.read_compact(fn)
+    assert b2 == bits and np.array_equal(got2, t)
+    r = subprocess.run([os.path.join(BIN, "decodecompact"), fn], capture_output=True)
+    assert r.returncode == 0 and r.stdout == t.tobytes()
 
 
 def test_compact_container_errors(tmp_path):

@@ -67,12 +67,14 @@ def test_random_bytestream_vs_oracle(eng, oracle, seed, n, sigma):
 
 @pytest.mark.parametrize("bits,n,sigma", [(2, 70_001, 4), (3, 10_000, 5), (4, 33_333, 11), (8, 20_000, 256), (1, 4_097, 2), (2, 1, 4),
                                           (5, 64, 32), (7, 250_003, 100)])
-def test_random_compactstream_vs_oracle(eng, oracle, bits, n, sigma):
+@pytest.mark.parametrize("layout", ["le", "be"])
+def test_random_compactstream_vs_oracle(eng, oracle, bits, n, sigma, layout):
     """inputtype=compactstream (K1 k_unpack_compact): container written by the oracle's numpy writer, symbols of every
-    width incl. ones that straddle bytes and 64-bit words; same result as the naive sort of the decoded symbols."""
+    width incl. ones that straddle bytes and 64-bit words, words in either byte order; same result as the naive sort of
+    the decoded symbols."""
     rng = np.random.default_rng(100 * bits + sigma)
     t = rng.integers(0, sigma, size=n, dtype=np.uint8)
-    data = oracle.encode_compact(t, bits)
+    data = oracle.encode_compact(t, bits, layout)
     dec, b = oracle.decode_compact(data.tobytes())
     assert b == bits and np.array_equal(dec, t)
     sa = oracle.sa_circular(t)
