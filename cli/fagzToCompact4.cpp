@@ -12,38 +12,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
-#include <fstream>
 #include <iostream>
 #include <sstream>
-
-// 1025 -> "1k 1" (/root/reference/src/fagzToCompact4.cpp:31-58)
-static std::string formatBytes(uint64_t n) {
-	static const char * units[] = {"", "k", "m", "g", "t", "p", "e", "z", "y"};
-	std::vector<std::string> parts;
-	for (unsigned u = 0; n; ++u, n /= 1024) parts.push_back(std::to_string(n % 1024) + units[u]);
-	std::string s;
-	for (size_t i = parts.size(); i-- > 0;) { s += parts[i]; if (i) s += " "; }
-	return s;
-}
-static std::string basename_of(std::string const & s) {
-	size_t const p = s.rfind('/');
-	return p == std::string::npos ? s : s.substr(p + 1);
-}
-static std::string strip_after_dot(std::string const & s) { return s.substr(0, s.find('.')); }
-static std::string clip_off(std::string const & s, std::string const & suffix) {
-	if (s.size() >= suffix.size() && !s.compare(s.size() - suffix.size(), suffix.size(), suffix)) return s.substr(0, s.size() - suffix.size());
-	return s;
-}
-static std::string common_prefix(std::vector<std::string> const & v) {
-	if (v.empty()) return std::string();
-	std::string p = v[0];
-	for (size_t i = 1; i < v.size(); ++i) {
-		size_t k = 0;
-		while (k < p.size() && k < v[i].size() && p[k] == v[i][k]) ++k;
-		p.resize(k);
-	}
-	return p;
-}
 
 struct SplitMix64 {
 	uint64_t s;
@@ -61,21 +31,15 @@ int main(int argc, char ** argv) {
 		bool const rc = arg.getu("rc", 1) != 0;
 		bool const gz = arg.getu("gz", 1) != 0;
 		int const verbose = (int)arg.getu("verbose", 1);
-		std::vector<std::string> inputfilenames = arg.rest;
-		if (arg.has("inputfilenames")) {
-			std::ifstream lst(arg.get("inputfilenames", ""));
-			if (!lst) throw std::runtime_error("cannot open " + arg.get("inputfilenames", ""));
-			std::string line;
-			while (std::getline(lst, line)) if (!line.empty()) inputfilenames.push_back(line);
-		}
+		std::vector<std::string> const inputfilenames = b3mcli::input_names(arg.rest, arg.get("inputfilenames", ""));
 		if (arg.help || inputfilenames.empty()) {
 			std::cerr << "usage: " << arg.progname << " [rc=1] [gz=1] [outputfilename=<prefix.compact>] [inputfilenames=<file of names>] [verbose=1] <in.fa[.gz]> ..." << std::endl;
 			return EXIT_FAILURE;
 		}
-		std::string defout = common_prefix(inputfilenames);
-		defout = clip_off(defout, ".gz");
-		defout = clip_off(defout, ".fasta");
-		defout = clip_off(defout, ".fa");
+		std::string defout = b3mcli::common_prefix(inputfilenames);
+		defout = b3mcli::clip_off(defout, ".gz");
+		defout = b3mcli::clip_off(defout, ".fasta");
+		defout = b3mcli::clip_off(defout, ".fa");
 		std::string const outputfilename = arg.get("outputfilename", defout + ".compact");
 		std::string const metaoutputfilename = outputfilename + ".meta";
 		b3m::CompactWriter compactout(outputfilename, 2);
@@ -98,7 +62,7 @@ int main(int argc, char ** argv) {
 			b3mcli::ByteSource src(fn, gz);
 			b3mcli::FastaReader fain(src);
 			while (fain.next(pat)) {
-				if (verbose) std::cerr << (i + 1) << " " << strip_after_dot(basename_of(fn)) << " " << pat.sid << "...";
+				if (verbose) std::cerr << (i + 1) << " " << b3mcli::strip_after_dot(b3mcli::basename_of(fn)) << " " << pat.sid << "...";
 				std::string & s = pat.spattern;
 				b3m::put_be64(meta, s.size());
 				size_t const nrpos = meta.size();
@@ -127,7 +91,7 @@ int main(int argc, char ** argv) {
 				}
 				insize += s.size() + 1;
 				++nseq;
-				if (verbose) std::cerr << "done, input size " << formatBytes(s.size() + 1) << " acc " << formatBytes(insize) << std::endl;
+				if (verbose) std::cerr << "done, input size " << b3mcli::format_bytes(s.size() + 1) << " acc " << b3mcli::format_bytes(insize) << std::endl;
 			}
 		}
 		for (int k = 0; k < 8; ++k) meta[k] = (uint8_t)(nseq >> (8 * (7 - k)));

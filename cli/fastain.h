@@ -95,4 +95,51 @@ private:
 	ByteSource & src;
 };
 
+// ---- small helpers shared by the fagzToCompact* converters ---------------------------------
+// 1025 -> "1k 1" (/root/reference/src/fagzToCompact4.cpp:31-58)
+inline std::string format_bytes(uint64_t n) {
+	static const char * units[] = {"", "k", "m", "g", "t", "p", "e", "z", "y"};
+	std::vector<std::string> parts;
+	for (unsigned u = 0; n; ++u, n /= 1024) parts.push_back(std::to_string(n % 1024) + units[u]);
+	std::string s;
+	for (size_t i = parts.size(); i-- > 0;) { s += parts[i]; if (i) s += " "; }
+	return s;
+}
+inline std::string basename_of(std::string const & s) {
+	size_t const p = s.rfind('/');
+	return p == std::string::npos ? s : s.substr(p + 1);
+}
+inline std::string strip_after_dot(std::string const & s) { return s.substr(0, s.find('.')); }
+inline std::string clip_off(std::string const & s, std::string const & suffix) {
+	if (s.size() >= suffix.size() && !s.compare(s.size() - suffix.size(), suffix.size(), suffix)) return s.substr(0, s.size() - suffix.size());
+	return s;
+}
+inline std::string common_prefix(std::vector<std::string> const & v) {
+	if (v.empty()) return std::string();
+	std::string p = v[0];
+	for (size_t i = 1; i < v.size(); ++i) {
+		size_t k = 0;
+		while (k < p.size() && k < v[i].size() && p[k] == v[i][k]) ++k;
+		p.resize(k);
+	}
+	return p;
+}
+// positional file names plus the non-empty lines of the file named by inputfilenames=
+inline std::vector<std::string> input_names(std::vector<std::string> const & rest, std::string const & listfn) {
+	std::vector<std::string> names = rest;
+	if (!listfn.empty()) {
+		FILE * f = fopen(listfn.c_str(), "r");
+		if (!f) throw std::runtime_error("cannot open " + listfn);
+		std::string line;
+		int c;
+		while ((c = fgetc(f)) != EOF) {
+			if (c == '\n') { if (!line.empty()) names.push_back(line); line.clear(); }
+			else if (c != '\r') line.push_back((char)c);
+		}
+		if (!line.empty()) names.push_back(line);
+		fclose(f);
+	}
+	return names;
+}
+
 } // namespace b3mcli

@@ -164,3 +164,64 @@ def test_digitsToCompact(tmp_path, oracle, term, gz):
     assert np.array_equal(syms, want)
     r = subprocess.run([os.path.join(BIN, "digitsToCompact"), "outputfilename=" + str(out)], input=b"123\n", capture_output=True, text=False)
     assert r.returncode == 1 and b"non decimal digit" in r.stderr
+
+
+def _revcomp_codes(codes, a, t, other):
+    """reverse complement on mapped symbols: A..T = a..t swap ends, `other` stays"""
+    c = codes[::-1].copy()
+    m = (c >= a) & (c <= t)
+    c[m] = (a + t) - c[m]
+    return c
+
+
+@pytest.mark.parametrize("rc", [1, 0])
+def test_fagzToCompact_3bit(tmp_path, oracle, rc):
+    """3 bit per symbol: A,C,G,T = 1..4, other letters 5, a 0 behind every sequence (fagzToCompact.cpp:108-160)."""
+    recs = [("s1 x", "ACGTNacgtRY"), ("s2", "T"), ("s3", "GGGCCCAAATTT" * 9)]
+    fa = tmp_path / "in.fa.gz"
+    fa.write_bytes(gzip.compress(_fasta(recs, width=13)))
+    out = tmp_path / "o.compact"
+    r = subprocess.run([os.path.join(BIN, "fagzToCompact"), "rc=%d" % rc, "outputfilename=" + str(out), str(fa)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Done, total input size %d" % sum(len(s) + 1 for _, s in recs) in r.stderr
+    syms, bits = oracle.decode_compact(out.read_bytes())
+    assert bits == 3
+    code = {"A": 1, "C": 2, "G": 3, "T": 4}
+    want = []
+    for _, s in recs:
+        f = np.array([code.get(c.upper(), 5) for c in s], dtype=np.uint8)
+        want += f.tolist() + [0]
+        if rc:
+            want += _revcomp_codes(f, 1, 4, 5).tolist() + [0]
+    assert syms.tolist() == want
+    # limit=: files are only opened while the accumulated size is below it
+    r = subprocess.run([os.path.join(BIN, "fagzToCompact"), "rc=0", "verbose=0", "limit=5", "outputfilename=" + str(out), str(fa), str(fa)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    syms2, _ = oracle.decode_compact(out.read_bytes())
+    assert syms2.size == sum(len(s) + 1 for _, s in recs)  # the second file is skipped
+
+
+@pytest.mark.parametrize("rc", [1, 0])
+def test_fagzToCompactUTerm(tmp_path, oracle, rc):
+    """A,C,G,T = 2..5, other letters 6, and behind sequence k its id in `seqbits` symbols 0/1, MSB first
+    (fagzToCompactUTerm.cpp:78-85,140-210)."""
+    recs = [("a", "ACGTN"), ("b", "tt"), ("c", "GATTACA")]
+    fa = tmp_path / "in.fa"
+    fa.write_bytes(_fasta(recs))
+    out = tmp_path / "u.compact"
+    r = subprocess.run([os.path.join(BIN, "fagzToCompactUTerm"), "gz=0", "rc=%d" % rc, "outputfilename=" + str(out), str(fa)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    numseq = len(recs) * (2 if rc else 1)
+    assert "[V] numseq=%d" % numseq in r.stderr
+    seqbits = (numseq - 1).bit_length()
+    syms, bits = oracle.decode_compact(out.read_bytes())
+    assert bits == 3
+    code = {"A": 2, "C": 3, "G": 4, "T": 5}
+    want, sid = [], 0
+    for _, s in recs:
+        f = np.array([code.get(c.upper(), 6) for c in s], dtype=np.uint8)
+        for part in ([f, _revcomp_codes(f, 2, 5, 6)] if rc else [f]):
+            want += part.tolist() + [(sid >> (seqbits - 1 - i)) & 1 for i in range(seqbits)]
+            sid += 1
+    assert syms.tolist() == want
