@@ -4,12 +4,14 @@ record: the CPU-side check of instruction counts before GPU time is spent on a k
     python tools/sass_mix.py bwtb3m_b200/csrc/sufsort.o 'k_radix_onesweepILi2ELb1ELb0ELb1E' 16
 """
 import re
+import signal
 import subprocess
 import sys
 from collections import Counter
 
 
 def main():
+    signal.signal(signal.SIGPIPE, signal.SIG_DFL)  # `| head` is fine
     obj, pat, per = sys.argv[1], sys.argv[2], float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
     txt = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True, check=True).stdout
     cur, mix, name = None, Counter(), None
