@@ -123,9 +123,18 @@ __device__ __forceinline__ void rs_second_key(TextView const & v, unsigned bits,
 	rem = (uint32_t)((lin && left < skip + k2syms) ? left : skip + k2syms);
 }
 
+// EXPERIMENT (B3M_EXPERIMENT_RESOLVE_DEFER=1; default off, not yet measured on a GPU): the records that need a second
+// key (about 1 in 100) are queued in shared memory and finished after the main loop by consecutive threads, so that
+// the two random text reads and the run loop behind them are not paid by a whole warp for one active lane.
+constexpr unsigned RS_QCAP = 512;                 // queue entries per tile (about 30 are expected); overflow is handled inline
+__device__ __forceinline__ uint32_t * rs_defer_queue() {
+	__shared__ uint32_t q[RS_QCAP + 1];           // [RS_QCAP] = fill count
+	return q;
+}
+
 // ORDER: write the resolved order (suffix array + head flags); a fused whole-text sort leaves it out
 // and only comes back for it when something stayed unresolved.
-template <bool FUSED, bool ORDER>
+template <bool FUSED, bool ORDER, bool DEFER = false>
 __global__ void __launch_bounds__(RS_THREADS)
 k_resolve(TextView v, unsigned bits, unsigned k0, int lin, const uint32_t * __restrict__ key, const uint32_t * __restrict__ idx,
           const uint8_t * __restrict__ aux, uint64_t nrec, uint32_t tile0, uint32_t * __restrict__ sa_out, uint8_t * __restrict__ hflag, FusedOut fo, unsigned long long * __restrict__ counters) {
@@ -146,6 +155,8 @@ k_resolve(TextView v, unsigned bits, unsigned k0, int lin, const uint32_t * __re
 	unsigned const xmask = (1u << xbits) - 1u;
 	if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
 	if (threadIdx.x == 0) { s_hb[0] = 0xffffffffu; s_hb[RS_ROWS + 1] = 0xffffffffu; }
+	uint32_t * s_q = nullptr;
+	if constexpr (DEFER) { s_q = rs_defer_queue(); if (threadIdx.x == 0) s_q[RS_QCAP] = 0; }
 
 	#pragma unroll 1
 	for (unsigned q = w; q < RS_ROWS; q += RS_WARPS) {
@@ -199,6 +210,12 @@ k_resolve(TextView v, unsigned bits, unsigned k0, int lin, const uint32_t * __re
 				}
 				++ntied;
 				f = y + (int)less;
+				if constexpr (DEFER) {
+					if (eq > 1) {
+						unsigned const qi = atomicAdd(&s_q[RS_QCAP], 1u);
+						if (qi < RS_QCAP) { s_q[qi] = (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)(z - y) << 24); continue; } // finished below
+					}
+				}
 				if (eq > 1) {
 					// the carried symbols do not separate this record from the rest of its run: compare the
 					// second keys, read from the text (about 1 record in 100 on random DNA)
@@ -226,6 +243,38 @@ k_resolve(TextView v, unsigned bits, unsigned k0, int lin, const uint32_t * __re
 		if (ORDER) { sa_out[kf] = i; hflag[kf] = (uint8_t)hf; }
 		if (FUSED) fo_emit(fo, i, (uint64_t)kf, ax >> xbits);
 	}
+	if constexpr (DEFER) {
+		// the queued records, one per thread: same ranking as above, every lane busy
+		__syncthreads();
+		unsigned const qn = s_q[RS_QCAP] < RS_QCAP ? s_q[RS_QCAP] : RS_QCAP;
+		for (unsigned t = threadIdx.x; t < qn; t += RS_THREADS) {
+			uint32_t const e = s_q[t];
+			int const x = (int)(e & 4095u), y = (int)((e >> 12) & 4095u), z = y + (int)(e >> 24);
+			uint32_t const ax = s_aux[x], mx = ax & xmask;
+			int f = y;
+			#pragma unroll 1
+			for (int y2 = y; y2 < z; ++y2) f += (s_aux[y2] & xmask) < mx ? 1 : 0;
+			unsigned long long mk2; uint32_t mr;
+			rs_second_key(v, bits, k0 + nx, lin, s_idx[x], mk2, mr);
+			uint32_t eqb = 0, eqa = 0;
+			#pragma unroll 1
+			for (int y2 = y; y2 < z; ++y2) {
+				if (y2 == x || (s_aux[y2] & xmask) != mx) continue;
+				unsigned long long ok2; uint32_t orr;
+				rs_second_key(v, bits, k0 + nx, lin, s_idx[y2], ok2, orr);
+				bool const same = ok2 == mk2 && orr == mr;
+				f += (ok2 < mk2 || (ok2 == mk2 && orr < mr) || (same && y2 < x)) ? 1 : 0;
+				eqb += (same && y2 < x) ? 1u : 0u;
+				eqa += same ? 1u : 0u;
+			}
+			if (eqa) ++nunres;
+			++ngather;
+			uint32_t const i = s_idx[x];
+			uint32_t const kf = kbase + (uint32_t)f;
+			if (ORDER) { sa_out[kf] = i; hflag[kf] = (uint8_t)(eqb == 0 ? 1u : 0u); }
+			if (FUSED) fo_emit(fo, i, (uint64_t)kf, ax >> xbits);
+		}
+	}
 	// per-CTA totals, spread over RS_CSLOTS counter sets (one hot address would serialise in L2)
 	ntied = __reduce_add_sync(0xffffffffu, ntied);
 	nunres = __reduce_add_sync(0xffffffffu, nunres);
@@ -251,6 +300,13 @@ static double wall_ms() {
 	struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
 	return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
+static bool resolve_defer() { static int t = -1; if (t < 0) t = getenv("B3M_EXPERIMENT_RESOLVE_DEFER") ? 1 : 0; return t == 1; }
+// k_resolve<F, O> on `grid` tiles; the experiment switch picks the variant with the deferred second keys
+#define RS_LAUNCH(label, bytes_, F, O, grid, ...)                                                                         \
+	do {                                                                                                              \
+		if (resolve_defer()) B3M_LAUNCH_T(st, label, bytes_, (k_resolve<F, O, true>), grid, RS_THREADS, 0, __VA_ARGS__);  \
+		else B3M_LAUNCH_T(st, label, bytes_, (k_resolve<F, O, false>), grid, RS_THREADS, 0, __VA_ARGS__);                 \
+	} while (0)
 static bool trace_on() { static int t = -1; if (t < 0) t = getenv("B3M_TRACE") ? 1 : 0; return t == 1; }
 #define TRACE(msg) do { if (trace_on()) { cudaStreamSynchronize(st.s); double t_ = wall_ms(); fprintf(stderr, "[T] %-28s %9.3f ms\n", msg, t_ - t_last); t_last = wall_ms(); } } while (0)
 
@@ -463,7 +519,7 @@ uint64_t k2_sort_keyrange(Stream & st, DevText const & T, int circular, KeyRange
 	FusedOut fo = fo0;
 	fo.shift = fo0.shift + plan.base[part];
 	uint64_t const rbytes = m * 10ull;
-	B3M_LAUNCH_T(st, "resolve_extract", rbytes, (k_resolve<true, false>), (unsigned)div_up(m, RS_TILE), RS_THREADS, 0, v, bits, k0, !circular, (const uint32_t *)cur.a[0],
+	RS_LAUNCH("resolve_extract", rbytes, true, false, (unsigned)div_up(m, RS_TILE), v, bits, k0, !circular, (const uint32_t *)cur.a[0],
 	             (const uint32_t *)cur.a[1], (const uint8_t *)cur.aux, m, 0u, alt.a[1], hflag.get(), fo, counters.get());
 	std::vector<unsigned long long> hcs(4 * RS_CSLOTS);
 	B3M_CUDA(cudaMemcpyAsync(hcs.data(), counters.get(), 32 * RS_CSLOTS, cudaMemcpyDeviceToHost, st.s));
@@ -550,7 +606,7 @@ void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W,
 				uint32_t const lb = fetch_u32(st, d_total);
 				unsigned const t0 = lb / RS_TILE, tn = std::min<unsigned>(2u, rgrid - t0);
 				B3M_CUDA(cudaMemsetAsync(fo->special, 0xff, 8, st.s));
-				B3M_LAUNCH_T(st, "resolve_extract", (uint64_t)tn * RS_TILE * 10ull, (k_resolve<true, false>), tn, RS_THREADS, 0, v, bits, k0, lin,
+				RS_LAUNCH("resolve_extract", (uint64_t)tn * RS_TILE * 10ull, true, false, tn, v, bits, k0, lin,
 				             (const uint32_t *)cur.a[0], (const uint32_t *)cur.a[1], (const uint8_t *)cur.aux, W, t0, alt.a[1], hflag.get(), *fo, counters.get());
 				uint32_t const row0 = fetch_u32(st, fo->special);
 				if (row0 == 0xffffffffu) stream_bwa = false; // in a run too long for the CTA: no early primary
@@ -562,7 +618,7 @@ void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W,
 			unsigned const nchunks = (stream_sa || stream_bwa) ? 16u : 1u; // the last chunk's copies are the exposed tail
 			for (unsigned c = 0; c < nchunks; ++c) {
 				unsigned const t_lo = (unsigned)((uint64_t)rgrid * c / nchunks), t_hi = (unsigned)((uint64_t)rgrid * (c + 1) / nchunks);
-				B3M_LAUNCH_T(st, "resolve_extract", (uint64_t)(t_hi - t_lo) * RS_TILE * 10ull, (k_resolve<true, false>), t_hi - t_lo, RS_THREADS, 0, v, bits, k0, lin,
+				RS_LAUNCH("resolve_extract", (uint64_t)(t_hi - t_lo) * RS_TILE * 10ull, true, false, t_hi - t_lo, v, bits, k0, lin,
 				             (const uint32_t *)cur.a[0], (const uint32_t *)cur.a[1], (const uint8_t *)cur.aux, W, t_lo, alt.a[1], hflag.get(), *fo, counters.get());
 				if (stream_sa || stream_bwa) {
 					// rows below t_hi * RS_TILE + shift are final once these tiles are done: their SA samples and BWA words go to the host now
@@ -594,13 +650,13 @@ void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W,
 			if (stream_bwa) so->bwa_delivered = hc[0] == 0;
 			if (hc[0]) {
 				B3M_CUDA(cudaMemsetAsync(counters.get(), 0, 32 * RS_CSLOTS, st.s));
-				B3M_LAUNCH_T(st, "resolve", rbytes, (k_resolve<false, true>), rgrid, RS_THREADS, 0, v, bits, k0, lin, (const uint32_t *)cur.a[0],
+				RS_LAUNCH("resolve", rbytes, false, true, rgrid, v, bits, k0, lin, (const uint32_t *)cur.a[0],
 				             (const uint32_t *)cur.a[1], (const uint8_t *)cur.aux, W, 0u, alt.a[1], hflag.get(), FusedOut(), counters.get());
 				read_counters(hc);
 				S.other_bytes += rbytes + 32ull * hc[2];
 			}
 		} else {
-			B3M_LAUNCH_T(st, "resolve", rbytes, (k_resolve<false, true>), rgrid, RS_THREADS, 0, v, bits, k0, lin, (const uint32_t *)cur.a[0],
+			RS_LAUNCH("resolve", rbytes, false, true, rgrid, v, bits, k0, lin, (const uint32_t *)cur.a[0],
 			             (const uint32_t *)cur.a[1], (const uint8_t *)cur.aux, W, 0u, alt.a[1], hflag.get(), FusedOut(), counters.get());
 			read_counters(hc);
 			S.other_bytes += rbytes + 32ull * hc[2];
