@@ -26,13 +26,7 @@ bin/%: cli/%.cpp $(LIB) include/b3m.h $(wildcard cli/*.h)
 oracle:
 	$(MAKE) -s -C oracle
 
-# standalone measurements for the next GPU session (experiments/README.md); not part of `all`
-experiments: bin/exp_rec64_pass
-bin/exp_%: experiments/%.cu $(wildcard $(CSRC)/*.cuh)
-	@mkdir -p bin
-	$(NVCC) $(NVFLAGS) -Xptxas -v -o $@ $<
-
 clean:
 	rm -f $(CSRC)/*.o $(LIB) $(BINS)
 	$(MAKE) -s -C oracle clean
-.PHONY: all oracle clean experiments
+.PHONY: all oracle clean

@@ -20,6 +20,7 @@ class BuildParams(C.Structure):
         ("sampling", C.c_int),
         ("host_sa", C.c_void_p),
         ("host_bwa", C.c_void_p),
+        ("sortpath", C.c_int),
     ]
 
 

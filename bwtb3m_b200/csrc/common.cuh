@@ -1,6 +1,7 @@
 // Shared helpers for the b3m CUDA engine (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include "../../include/b3m.h"
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -122,6 +123,7 @@ struct Stream {
 	int sms = 148;              // multiprocessor count of the device
 	Arena * arena = nullptr;
 	KernelTimes kt;
+	int sortpath = 0;           // B3M_SORT_*: which round-0 sort a whole-text build of a 2-bit alphabet takes
 };
 
 // launch + (when profiling is switched on) bracket with events; `bytes` = algorithmic HBM bytes

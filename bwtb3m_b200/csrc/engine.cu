@@ -211,8 +211,10 @@ void Engine::build(b3m_build_params const & p) {
 	B3M_REQUIRE(p.numblocks >= 1, "numblocks must be >= 1");
 	auto pow2 = [](uint64_t v) { return v && !(v & (v - 1)); };
 	B3M_REQUIRE(pow2(p.sasamplingrate) && pow2(p.isasamplingrate), "sampling rates must be powers of two");
+	B3M_REQUIRE(p.sortpath >= B3M_SORT_AUTO && p.sortpath <= B3M_SORT_MSD, "unknown sortpath");
 	reset_results();
 	params = p;
+	st.sortpath = p.sortpath;
 	prerate = p.preisarate ? p.preisarate : (p.bwtonly ? 64 : choose_preisarate(T.n, st.sms));
 	B3M_REQUIRE(pow2(prerate), "preisarate must be a power of two");
 	npre = div_up(T.n, prerate);
@@ -324,8 +326,11 @@ void Engine::kr_build_part(uint32_t part, uint32_t nparts, b3m_build_params cons
 	auto pow2 = [](uint64_t v) { return v && !(v & (v - 1)); };
 	B3M_REQUIRE(pow2(p.sasamplingrate) && pow2(p.isasamplingrate), "sampling rates must be powers of two");
 	B3M_REQUIRE(p.bwtonly || (d_sa && d_isa), "null sample buffers");
+	B3M_REQUIRE(p.sortpath >= B3M_SORT_AUTO && p.sortpath <= B3M_SORT_MSD, "unknown sortpath");
 	reset_results();
 	params = p;
+	if (st.sortpath != p.sortpath) kr_plan = KeyRangePlan(); // the plan depends on the sorter
+	st.sortpath = p.sortpath;
 	prerate = p.preisarate ? p.preisarate : (p.bwtonly ? 64 : choose_preisarate(T.n, st.sms));
 	B3M_REQUIRE(pow2(prerate), "preisarate must be a power of two");
 	npre = div_up(T.n, prerate);

@@ -95,6 +95,9 @@ struct KeyRangePlan {
 	uint32_t binshift = 20;       // bin of a suffix = its first key >> binshift
 	std::vector<uint32_t> bin_lo;
 	std::vector<uint64_t> base;
+	// 2-bit alphabets: the bins are the level-1 buckets of the MSD path (msd.cuh) and hist their sizes
+	unsigned msd_b1 = 0, msd_b2 = 0;
+	std::vector<unsigned long long> hist;
 };
 void k2_keyrange_plan(Stream & st, DevText const & T, int circular, uint32_t nparts, KeyRangePlan & plan);
 // sorts the suffixes of one part of the whole text and emits their fused outputs at global ranks

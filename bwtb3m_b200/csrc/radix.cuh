@@ -645,16 +645,6 @@ inline void radix_sort_suffix_keys(Stream & st, TextView const & v, uint64_t nsh
 		RadixRec<2> t = cur; cur = alt; alt = t;
 		if (rs) { rs->passes++; rs->bytes += pbytes; }
 	}
-	if (getenv("B3M_EXPERIMENT_SORTED_PASS")) {
-		// timing experiment: the top digit once more on sorted records (identity permutation, sequential writes)
-		B3M_CUDA(cudaMemsetAsync(status.get(), 0, status.bytes(), st.s));
-		B3M_CUDA(cudaMemsetAsync(ticket + 3, 0, 4, st.s));
-		RadixPassArgs<2> A;
-		A.in[0] = cur.a[0]; A.out[0] = alt.a[0]; A.in[1] = cur.a[1]; A.out[1] = alt.a[1];
-		A.aux_in = cur.aux; A.aux_out = alt.aux;
-		radix_launch_pass<2, true, false>(st, "radix_onesweep<sorted input>", n * 18ull, A, S, n, 24, 255u, (const uint32_t *)(base.get() + 3 * RADIX_BINS), status.get(), ticket + 3);
-		RadixRec<2> t = cur; cur = alt; alt = t;
-	}
 }
 
 } // namespace b3m

@@ -24,6 +24,7 @@
 #include "radix.cuh"
 #include "scan.cuh"
 #include "textview.cuh"
+#include "msd.cuh"
 #include <time.h>
 #include <algorithm>
 #include <vector>
@@ -123,18 +124,9 @@ __device__ __forceinline__ void rs_second_key(TextView const & v, unsigned bits,
 	rem = (uint32_t)((lin && left < skip + k2syms) ? left : skip + k2syms);
 }
 
-// EXPERIMENT (B3M_EXPERIMENT_RESOLVE_DEFER=1; default off, not yet measured on a GPU): the records that need a second
-// key (about 1 in 100) are queued in shared memory and finished after the main loop by consecutive threads, so that
-// the two random text reads and the run loop behind them are not paid by a whole warp for one active lane.
-constexpr unsigned RS_QCAP = 512;                 // queue entries per tile (about 30 are expected); overflow is handled inline
-__device__ __forceinline__ uint32_t * rs_defer_queue() {
-	__shared__ uint32_t q[RS_QCAP + 1];           // [RS_QCAP] = fill count
-	return q;
-}
-
 // ORDER: write the resolved order (suffix array + head flags); a fused whole-text sort leaves it out
 // and only comes back for it when something stayed unresolved.
-template <bool FUSED, bool ORDER, bool DEFER = false>
+template <bool FUSED, bool ORDER>
 __global__ void __launch_bounds__(RS_THREADS)
 k_resolve(TextView v, unsigned bits, unsigned k0, int lin, const uint32_t * __restrict__ key, const uint32_t * __restrict__ idx,
           const uint8_t * __restrict__ aux, uint64_t nrec, uint32_t tile0, uint32_t * __restrict__ sa_out, uint8_t * __restrict__ hflag, FusedOut fo, unsigned long long * __restrict__ counters) {
@@ -155,8 +147,6 @@ k_resolve(TextView v, unsigned bits, unsigned k0, int lin, const uint32_t * __re
 	unsigned const xmask = (1u << xbits) - 1u;
 	if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
 	if (threadIdx.x == 0) { s_hb[0] = 0xffffffffu; s_hb[RS_ROWS + 1] = 0xffffffffu; }
-	uint32_t * s_q = nullptr;
-	if constexpr (DEFER) { s_q = rs_defer_queue(); if (threadIdx.x == 0) s_q[RS_QCAP] = 0; }
 
 	#pragma unroll 1
 	for (unsigned q = w; q < RS_ROWS; q += RS_WARPS) {
@@ -210,12 +200,6 @@ k_resolve(TextView v, unsigned bits, unsigned k0, int lin, const uint32_t * __re
 				}
 				++ntied;
 				f = y + (int)less;
-				if constexpr (DEFER) {
-					if (eq > 1) {
-						unsigned const qi = atomicAdd(&s_q[RS_QCAP], 1u);
-						if (qi < RS_QCAP) { s_q[qi] = (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)(z - y) << 24); continue; } // finished below
-					}
-				}
 				if (eq > 1) {
 					// the carried symbols do not separate this record from the rest of its run: compare the
 					// second keys, read from the text (about 1 record in 100 on random DNA)
@@ -243,38 +227,6 @@ k_resolve(TextView v, unsigned bits, unsigned k0, int lin, const uint32_t * __re
 		if (ORDER) { sa_out[kf] = i; hflag[kf] = (uint8_t)hf; }
 		if (FUSED) fo_emit(fo, i, (uint64_t)kf, ax >> xbits);
 	}
-	if constexpr (DEFER) {
-		// the queued records, one per thread: same ranking as above, every lane busy
-		__syncthreads();
-		unsigned const qn = s_q[RS_QCAP] < RS_QCAP ? s_q[RS_QCAP] : RS_QCAP;
-		for (unsigned t = threadIdx.x; t < qn; t += RS_THREADS) {
-			uint32_t const e = s_q[t];
-			int const x = (int)(e & 4095u), y = (int)((e >> 12) & 4095u), z = y + (int)(e >> 24);
-			uint32_t const ax = s_aux[x], mx = ax & xmask;
-			int f = y;
-			#pragma unroll 1
-			for (int y2 = y; y2 < z; ++y2) f += (s_aux[y2] & xmask) < mx ? 1 : 0;
-			unsigned long long mk2; uint32_t mr;
-			rs_second_key(v, bits, k0 + nx, lin, s_idx[x], mk2, mr);
-			uint32_t eqb = 0, eqa = 0;
-			#pragma unroll 1
-			for (int y2 = y; y2 < z; ++y2) {
-				if (y2 == x || (s_aux[y2] & xmask) != mx) continue;
-				unsigned long long ok2; uint32_t orr;
-				rs_second_key(v, bits, k0 + nx, lin, s_idx[y2], ok2, orr);
-				bool const same = ok2 == mk2 && orr == mr;
-				f += (ok2 < mk2 || (ok2 == mk2 && orr < mr) || (same && y2 < x)) ? 1 : 0;
-				eqb += (same && y2 < x) ? 1u : 0u;
-				eqa += same ? 1u : 0u;
-			}
-			if (eqa) ++nunres;
-			++ngather;
-			uint32_t const i = s_idx[x];
-			uint32_t const kf = kbase + (uint32_t)f;
-			if (ORDER) { sa_out[kf] = i; hflag[kf] = (uint8_t)(eqb == 0 ? 1u : 0u); }
-			if (FUSED) fo_emit(fo, i, (uint64_t)kf, ax >> xbits);
-		}
-	}
 	// per-CTA totals, spread over RS_CSLOTS counter sets (one hot address would serialise in L2)
 	ntied = __reduce_add_sync(0xffffffffu, ntied);
 	nunres = __reduce_add_sync(0xffffffffu, nunres);
@@ -300,13 +252,7 @@ static double wall_ms() {
 	struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
 	return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
-static bool resolve_defer() { static int t = -1; if (t < 0) t = getenv("B3M_EXPERIMENT_RESOLVE_DEFER") ? 1 : 0; return t == 1; }
-// k_resolve<F, O> on `grid` tiles; the experiment switch picks the variant with the deferred second keys
-#define RS_LAUNCH(label, bytes_, F, O, grid, ...)                                                                         \
-	do {                                                                                                              \
-		if (resolve_defer()) B3M_LAUNCH_T(st, label, bytes_, (k_resolve<F, O, true>), grid, RS_THREADS, 0, __VA_ARGS__);  \
-		else B3M_LAUNCH_T(st, label, bytes_, (k_resolve<F, O, false>), grid, RS_THREADS, 0, __VA_ARGS__);                 \
-	} while (0)
+#define RS_LAUNCH(label, bytes_, F, O, grid, ...) B3M_LAUNCH_T(st, label, bytes_, (k_resolve<F, O>), grid, RS_THREADS, 0, __VA_ARGS__)
 static bool trace_on() { static int t = -1; if (t < 0) t = getenv("B3M_TRACE") ? 1 : 0; return t == 1; }
 #define TRACE(msg) do { if (trace_on()) { cudaStreamSynchronize(st.s); double t_ = wall_ms(); fprintf(stderr, "[T] %-28s %9.3f ms\n", msg, t_ - t_last); t_last = wall_ms(); } } while (0)
 
@@ -315,6 +261,194 @@ static uint32_t fetch_u32(Stream & st, const uint32_t * d) {
 	B3M_CUDA(cudaMemcpyAsync(&h, d, sizeof(uint32_t), cudaMemcpyDeviceToHost, st.s));
 	B3M_CUDA(cudaStreamSynchronize(st.s));
 	return h;
+}
+
+// ------------------------------------------------------------------------------------------
+// MSD path (msd.cuh): round 0 of a whole-text sort of a 2-bit alphabet, on all suffixes or on the
+// key range [d_lo, d_hi) of level-1 bins (suffix-range sharding).
+// ------------------------------------------------------------------------------------------
+struct MsdGeom { unsigned b1 = 0, b2 = 0; };
+
+// bits of the two global levels: sub-buckets of 2048..4095 suffixes on average
+static bool msd_geometry(Stream const & st, DevText const & T, uint64_t W, MsdGeom & g) {
+	if (st.sortpath == B3M_SORT_LSD) return false;
+	if (T.keybits != 2 || !T.packed || W < 64 || W >= 0xFFFFFF00ull) return false;
+	if (st.sortpath != B3M_SORT_MSD && W < (1u << 16)) return false;
+	unsigned tb = 0;
+	while (tb < 21 && (W >> (tb + 12))) ++tb; // floor(log2(W / 2048))
+	if (tb < 4) tb = 4;
+	g.b1 = 2 * ((tb + 3) / 4);
+	if (g.b1 > 10) g.b1 = 10;
+	g.b2 = tb - g.b1;
+	if (g.b2 < 1) g.b2 = 1;
+	if (g.b2 > 11) g.b2 = 11;
+	return true;
+}
+
+static void msd_hist(Stream & st, TextView const & v, unsigned b1, std::vector<unsigned long long> & h) {
+	unsigned const nb = 1u << b1;
+	DevBuf<unsigned long long> gh(st, nb);
+	B3M_CUDA(cudaMemsetAsync(gh.get(), 0, gh.bytes(), st.s));
+	uint64_t const want = div_up(div_up(v.W, 32), 256);
+	unsigned const grid = (unsigned)(want < (uint64_t)st.sms * 8 ? (want ? want : 1) : (uint64_t)st.sms * 8);
+	B3M_LAUNCH_T(st, "msd_hist", v.W / 4, k_msd_hist, grid, 256, 0, v, b1, gh.get());
+	h.resize(nb);
+	B3M_CUDA(cudaMemcpyAsync(h.data(), gh.get(), nb * 8, cudaMemcpyDeviceToHost, st.s));
+	B3M_CUDA(cudaStreamSynchronize(st.s));
+}
+
+static void msd_configure() {
+	static bool done = false;
+	if (done) return;
+	B3M_CUDA(cudaFuncSetAttribute(k_msd_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, MSD_TILE * 8));
+	B3M_CUDA(cudaFuncSetAttribute(k_msd_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (MSD_TILE + 2) * 8));
+	B3M_CUDA(cudaFuncSetAttribute(k_msd_finish<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MSD_CAP * 9));
+	B3M_CUDA(cudaFuncSetAttribute(k_msd_finish<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MSD_CAP * 9));
+	done = true;
+}
+
+// Returns false when the path does not apply (a level-1 bin of 2^30 suffixes or more).  On return
+// `unresolved` counts the suffixes still tied; if that is not zero and sa_buf is given, sa_buf / hflag
+// hold the order reached and the head flags of its groups, which share at least `hstart` symbols.
+static bool msd_round0(Stream & st, TextView const & v, int lin, MsdGeom const & g, uint32_t d_lo, uint32_t d_hi,
+                       std::vector<unsigned long long> const & hist, FusedOut const & fo, StreamOut * so,
+                       DevBuf<uint32_t> * sa_buf, DevBuf<uint8_t> * hflag, SortStats & S, uint64_t & unresolved, uint64_t & hstart) {
+	unsigned const nb2 = 1u << g.b2, nkeep = d_hi - d_lo;
+	uint64_t const W = v.W;
+	std::vector<uint32_t> hb(2 * (nkeep + 1)); // first record | first level-2 tile of every kept bin
+	uint64_t m = 0, nt2 = 0;
+	for (unsigned b = 0; b < nkeep; ++b) {
+		unsigned long long const c = hist[d_lo + b];
+		if (c >= (1ull << 30)) return false;
+		hb[b] = (uint32_t)m; hb[nkeep + 1 + b] = (uint32_t)nt2;
+		m += c; nt2 += div_up(c, MSD_TILE);
+	}
+	hb[nkeep] = (uint32_t)m; hb[2 * nkeep + 1] = (uint32_t)nt2;
+	unresolved = 0;
+	S.rounds = 1; S.active_sum += m;
+	if (m == 0) return true;
+	msd_configure();
+	double t_last = wall_ms();
+	DevBuf<uint32_t> dplan(st, hb.size());
+	B3M_CUDA(cudaMemcpyAsync(dplan.get(), hb.data(), hb.size() * 4, cudaMemcpyHostToDevice, st.s));
+	const uint32_t * d_base = dplan.get(), * d_tpre = dplan.get() + nkeep + 1;
+	DevBuf<unsigned long long> recs(st, m + 2);
+	{
+		// level 1
+		uint64_t const nt1 = div_up(W, MSD_TILE);
+		DevBuf<uint32_t> status(st, nt1 * nkeep + 1);
+		B3M_CUDA(cudaMemsetAsync(status.get(), 0, status.bytes(), st.s));
+		MsdP1 A{v, g.b1, d_lo, nkeep, d_base, status.get(), status.get() + nt1 * nkeep, recs.get()};
+		B3M_LAUNCH_T(st, "msd_scatter", W / 4 + 8 * m, k_msd_scatter, (unsigned)nt1, MSD_THREADS, MSD_TILE * 8, A);
+		S.radix_passes++; S.radix_bytes += W / 4 + 8 * m; S.other_bytes += W / 4;
+	}
+	TRACE("msd level 1");
+	DevBuf<uint16_t> table(st, nt2 * (nb2 + 1));
+	{
+		MsdP2 A{g.b2, nkeep, d_base, d_tpre, recs.get(), table.get()};
+		B3M_LAUNCH_T(st, "msd_local", 16 * m, k_msd_local, (unsigned)nt2, MSD_THREADS, (MSD_TILE + 2) * 8, A);
+		S.radix_passes++; S.radix_bytes += 16 * m;
+	}
+	TRACE("msd level 2");
+	uint64_t const nsb = (uint64_t)nkeep * nb2;
+	DevBuf<uint32_t> sub(st, nsb + 1), scal(st, 4);
+	B3M_CUDA(cudaMemsetAsync(scal.get(), 0, 16, st.s));
+	B3M_CUDA(cudaMemsetAsync(sub.get() + nsb, 0, 4, st.s));
+	B3M_LAUNCH_T(st, "msd_subtotals", nt2 * (nb2 + 1) * 2ull, k_msd_subtotals, nkeep, 256, 0, g.b2, d_tpre, (const uint16_t *)table.get(), sub.get(), scal.get());
+	scan_exclusive_inplace<OpSum>(st, sub.get(), nsb + 1);
+	S.other_bytes += nt2 * (nb2 + 1) * 4ull + nsb * 12;
+	unsigned const lb = MSD_LBITS;
+	unsigned glog = 2;
+	while (glog < 5 && (1u << glog) < ((unsigned)MSD_TILE >> g.b2)) ++glog;
+	DevBuf<unsigned long long> counters(st, 4 * MSD_CSLOTS);
+	B3M_CUDA(cudaMemsetAsync(counters.get(), 0, 32 * MSD_CSLOTS, st.s));
+	MsdFin F{v, lin, g.b1, g.b2, lb, glog, nkeep, recs.get(), d_base, d_tpre, table.get(), sub.get(), 0u, nullptr, nullptr, fo, counters.get()};
+	auto read_counters = [&](unsigned long long * hc) {
+		std::vector<unsigned long long> hcs(4 * MSD_CSLOTS);
+		B3M_CUDA(cudaMemcpyAsync(hcs.data(), counters.get(), 32 * MSD_CSLOTS, cudaMemcpyDeviceToHost, st.s));
+		B3M_CUDA(cudaStreamSynchronize(st.s));
+		for (int c = 0; c < 4; ++c) hc[c] = 0;
+		for (int q = 0; q < MSD_CSLOTS; ++q) { for (int c = 0; c < 3; ++c) hc[c] += hcs[4 * q + c]; hc[3] |= hcs[4 * q + 3]; }
+	};
+	// early delivery (StreamOut): rows below a finished range of sub-buckets are final
+	bool const stream_sa = so && so->host_sa && fo.sa_s && st.copy && nsb >= 64 && d_lo == 0 && nkeep == (1u << g.b1);
+	bool stream_bwa = so && so->host_bwa && so->d_bwa && fo.has_term && st.copy && nsb >= 64 && d_lo == 0 && nkeep == (1u << g.b1);
+	uint64_t primary = 0;
+	if (stream_bwa) {
+		// the row of the suffix at position 0 first: its sub-bucket is known from the first text word
+		uint64_t w0 = 0;
+		B3M_CUDA(cudaMemcpyAsync(&w0, v.packed, 8, cudaMemcpyDeviceToHost, st.s));
+		B3M_CUDA(cudaStreamSynchronize(st.s));
+		F.sb0 = (uint32_t)(w0 >> (64u - g.b1 - g.b2));
+		B3M_CUDA(cudaMemsetAsync(fo.special, 0xff, 8, st.s));
+		B3M_LAUNCH_T(st, "msd_finish", 0, (k_msd_finish<true, false>), 1, MSD_THREADS, MSD_CAP * 9, F);
+		uint32_t const row0 = fetch_u32(st, fo.special + 1);
+		unsigned long long hc0[4];
+		read_counters(hc0);
+		if (row0 == 0xffffffffu || hc0[0]) stream_bwa = false; // tied beyond what the finish compares: no early primary
+		else primary = row0;
+		B3M_CUDA(cudaMemsetAsync(counters.get(), 0, 32 * MSD_CSLOTS, st.s)); // that sub-bucket is counted again below
+	}
+	unsigned const nchunks = (stream_sa || stream_bwa) ? 16u : 1u;
+	std::vector<uint32_t> rows(nchunks + 1, 0);
+	if (nchunks > 1) {
+		for (unsigned c = 1; c < nchunks; ++c)
+			B3M_CUDA(cudaMemcpyAsync(&rows[c], sub.get() + nsb * c / nchunks, 4, cudaMemcpyDeviceToHost, st.s));
+		B3M_CUDA(cudaStreamSynchronize(st.s));
+	}
+	uint64_t const seq_len = W, nwords_bwa = (W + 15) >> 4;
+	uint64_t words_done = 0;
+	for (unsigned c = 0; c < nchunks; ++c) {
+		uint32_t const s_lo = (uint32_t)(nsb * c / nchunks), s_hi = (uint32_t)(nsb * (c + 1) / nchunks);
+		F.sb0 = s_lo;
+		uint64_t const cm = nchunks > 1 ? (c + 1 == nchunks ? m : rows[c + 1]) - rows[c] : m;
+		B3M_LAUNCH_T(st, "msd_finish", cm * 37ull / 4, (k_msd_finish<true, false>), s_hi - s_lo, MSD_THREADS, MSD_CAP * 9, F);
+		if (stream_sa || stream_bwa) {
+			uint64_t const rows_lo = c ? rows[c] + fo.shift : 0, rows_hi = (c + 1 == nchunks) ? W + fo.shift : rows[c + 1] + fo.shift;
+			cudaEvent_t ev;
+			B3M_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+			B3M_CUDA(cudaEventRecord(ev, st.s));
+			B3M_CUDA(cudaStreamWaitEvent(st.copy, ev, 0));
+			B3M_CUDA(cudaEventDestroy(ev));
+			if (stream_sa) {
+				uint64_t const k_lo = div_up(rows_lo, 1ull << fo.salog), k_hi = std::min<uint64_t>(div_up(rows_hi, 1ull << fo.salog), so->nsa);
+				if (k_hi > k_lo) B3M_CUDA(cudaMemcpyAsync(so->host_sa + k_lo, fo.sa_s + k_lo, (k_hi - k_lo) * 8, cudaMemcpyDeviceToHost, st.copy));
+			}
+			if (stream_bwa) {
+				// word w reads the rows 16w .. 16w+16 (one further behind the primary)
+				uint64_t const w_hi = (c + 1 == nchunks) ? nwords_bwa : (rows_hi >= 17 ? std::min<uint64_t>((rows_hi - 17) / 16 + 1, nwords_bwa) : 0);
+				if (w_hi > words_done) {
+					k9_pack_bwa_range(st.copy, fo.bwt, seq_len, primary, so->d_bwa, words_done, w_hi);
+					++st.launches;
+					B3M_CUDA(cudaMemcpyAsync(so->host_bwa + words_done, so->d_bwa + words_done, (w_hi - words_done) * 4, cudaMemcpyDeviceToHost, st.copy));
+					words_done = w_hi;
+				}
+			}
+		}
+	}
+	unsigned long long hc[4];
+	read_counters(hc);
+	TRACE("msd finish");
+	S.other_bytes += m * 37ull / 4 + 32ull * hc[2];
+	S.tied0 = hc[1]; S.unresolved0 = hc[0];
+	unresolved = hc[0];
+	if (stream_sa) so->delivered = hc[0] == 0;
+	if (stream_bwa) so->bwa_delivered = hc[0] == 0;
+	if (hc[0] && sa_buf) {
+		// something stays tied: write the order reached and its head flags for the doubling rounds
+		sa_buf->alloc(st, m);
+		hflag->alloc(st, m);
+		B3M_CUDA(cudaMemsetAsync(counters.get(), 0, 32 * MSD_CSLOTS, st.s));
+		F.sb0 = 0; F.sa_out = sa_buf->get(); F.hflag = hflag->get(); F.fo = FusedOut();
+		B3M_LAUNCH_T(st, "msd_finish<order>", m * 13ull, (k_msd_finish<false, true>), (unsigned)nsb, MSD_THREADS, MSD_CAP * 9, F);
+		read_counters(hc);
+		S.other_bytes += m * 13ull + 32ull * hc[2];
+		unsigned const skip = (g.b1 + 30u) / 2;
+		hstart = (hc[3] & 2) ? (g.b1 + g.b2) / 2 : ((hc[3] & 1) ? (g.b1 + g.b2 + lb) / 2 : skip + 32u);
+		if (hstart < 1) hstart = 1;
+		TRACE("msd finish<order>");
+	}
+	return true;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -448,7 +582,14 @@ void k2_keyrange_plan(Stream & st, DevText const & T, int circular, uint32_t npa
 	RadixTextSrc S{v, nshort, bits, k0};
 	std::vector<unsigned long long> h;
 	uint32_t nbins;
-	if (bits == 2 && v.packed) {
+	MsdGeom mg;
+	plan.msd_b1 = plan.msd_b2 = 0; plan.hist.clear();
+	if (msd_geometry(st, T, W, mg)) {
+		// the level-1 buckets of the MSD path: the histogram the sort needs anyway
+		msd_hist(st, v, mg.b1, h);
+		nbins = 1u << mg.b1; plan.binshift = 32 - mg.b1;
+		plan.msd_b1 = mg.b1; plan.msd_b2 = mg.b2; plan.hist = h;
+	} else if (bits == 2 && v.packed) {
 		// the leading 4 symbols of every suffix: the top digit of the first key, whose histogram the sort needs anyway
 		nbins = RADIX_BINS; plan.binshift = 24;
 		DevBuf<unsigned long long> gh(st, RADIX_MAXDIG * RADIX_BINS);
@@ -496,6 +637,23 @@ uint64_t k2_sort_keyrange(Stream & st, DevText const & T, int circular, KeyRange
 	SortStats St;
 	St.rounds = 1;
 	if (m == 0) return 0;
+	if (plan.msd_b1) {
+		MsdGeom mg; mg.b1 = plan.msd_b1; mg.b2 = plan.msd_b2;
+		FusedOut fo = fo0;
+		fo.shift = fo0.shift + plan.base[part];
+		uint64_t unresolved = 0, hstart = 0;
+		St.other_bytes += W / 4;
+		if (msd_round0(st, v, !circular, mg, blo, bhi, plan.hist, fo, nullptr, nullptr, nullptr, St, unresolved, hstart)) {
+			if (stats) {
+				stats->rounds = stats->rounds > St.rounds ? stats->rounds : St.rounds;
+				stats->radix_passes += St.radix_passes; stats->radix_bytes += St.radix_bytes;
+				stats->active_sum += St.active_sum; stats->other_bytes += St.other_bytes;
+				stats->tied0 += St.tied0; stats->unresolved0 += St.unresolved0;
+			}
+			return unresolved;
+		}
+		return m; // a level-1 bucket too large for the path: the caller takes the merge tree
+	}
 	// stable compaction of the range's records out of the text
 	uint32_t const ntiles = (uint32_t)div_up(W, KR_FTILE);
 	DevBuf<uint32_t> tcount(st, ntiles), fl(st, (size_t)ntiles * (KR_FTILE / 32));
@@ -553,10 +711,21 @@ void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W,
 	DevBuf<uint32_t> scalar(st, 4);
 	uint32_t * d_total = scalar.get();
 	DevBuf<unsigned long long> counters(st, 4 * RS_CSLOTS);
-	DevBuf<uint8_t> hflag(st, W);
+	DevBuf<uint8_t> hflag;
 	uint64_t unresolved = 0;
-	{
-		// ---------------- round 0 ----------------
+	uint64_t hstart = k0; // every group left by round 0 shares at least this many symbols
+	bool round0_done = false;
+	MsdGeom mg;
+	if (fo && msd_geometry(st, T, W, mg)) {
+		// ---------------- round 0, MSD path (msd.cuh) ----------------
+		std::vector<unsigned long long> h;
+		msd_hist(st, v, mg.b1, h);
+		S.other_bytes += W / 4;
+		round0_done = msd_round0(st, v, lin, mg, 0u, 1u << mg.b1, h, *fo, so, &sa_buf, &hflag, S, unresolved, hstart);
+	}
+	if (!round0_done) {
+		// ---------------- round 0, LSD path ----------------
+		hflag.alloc(st, W);
 		DevBuf<uint32_t> key0(st, W), key1(st, W), idx0(st, W), idx1(st, W);
 		DevBuf<uint8_t> aux0(st, W), aux1(st, W);
 		RadixRec<2> cur{{key0.get(), idx0.get()}, aux0.get()}, alt{{key1.get(), idx1.get()}, aux1.get()};
@@ -720,7 +889,7 @@ void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W,
 		uint32_t * bufs[6];
 		for (int b = 0; b < 6; ++b) bufs[b] = pool[b].get();
 		// roles: bufs[0]=grp, bufs[1]=idx, bufs[2]=key2, bufs[3..5]=ping-pong partners
-		uint64_t h = k0; // every group shares at least its first k0 symbols
+		uint64_t h = hstart;
 		int const bw = (int)ceil_log2_u64(W + 2);
 		while (na) {
 			if (circular && h >= W) break; // non-primitive text: ties stay in current order (unpinned)

@@ -6,6 +6,9 @@ import numpy as np
 from ._lib import INPUT_TYPES, BuildParams, Info, lib
 
 
+SORTPATHS = {"auto": 0, "lsd": 1, "msd": 2}  # B3M_SORT_* of include/b3m.h
+
+
 class B3MError(RuntimeError):
     pass
 
@@ -56,11 +59,11 @@ class Engine:
         self._check(self._lib.b3m_engine_load_device(self._h, C.c_void_p(dptr), nbytes, INPUT_TYPES[inputtype]))
 
     def build(self, numblocks=1, preisarate=0, sasamplingrate=32, isasamplingrate=262144, bwtonly=False,
-              largelcpthres=16384, sampling="auto", host_sa_ptr=0, host_bwa_ptr=0):
+              largelcpthres=16384, sampling="auto", host_sa_ptr=0, host_bwa_ptr=0, sortpath="auto"):
         """sampling: "auto" (sampled SA/ISA straight from the suffix array when one block holds the whole
         text, LF walk otherwise) or "walk" (always the reference's LF walk from the anchors)."""
         p = BuildParams(numblocks, preisarate, sasamplingrate, isasamplingrate, 1 if bwtonly else 0, largelcpthres,
-                        {"auto": 0, "walk": 1}[sampling], host_sa_ptr or None, host_bwa_ptr or None)
+                        {"auto": 0, "walk": 1}[sampling], host_sa_ptr or None, host_bwa_ptr or None, SORTPATHS[sortpath])
         self._check(self._lib.b3m_engine_build(self._h, C.byref(p)))
 
     def info(self):
@@ -108,10 +111,10 @@ class Engine:
         return syms, lens
 
     def shard_build(self, part, nparts, bwt_ptr, prerank_ptr, sa_ptr, isa_ptr, special_ptr, preisarate=0, sasamplingrate=32,
-                    isasamplingrate=262144, bwtonly=False):
+                    isasamplingrate=262144, bwtonly=False, sortpath="auto"):
         """Suffix-range sharding: sorts key range `part` of `nparts` into caller-owned, zeroed device
         buffers (global places); returns the number of suffixes this path left unresolved."""
-        p = BuildParams(nparts, preisarate, sasamplingrate, isasamplingrate, 1 if bwtonly else 0, 16384, 0, None, None)
+        p = BuildParams(nparts, preisarate, sasamplingrate, isasamplingrate, 1 if bwtonly else 0, 16384, 0, None, None, SORTPATHS[sortpath])
         un = C.c_uint64(0)
         vp = lambda a: C.c_void_p(a) if a else None
         self._check(self._lib.b3m_engine_shard_build(self._h, part, nparts, C.byref(p), vp(bwt_ptr), vp(prerank_ptr), vp(sa_ptr), vp(isa_ptr),

@@ -157,7 +157,13 @@ typedef struct b3m_build_params {
 	                            * b3m_engine_fetch with the same pointer does not copy again.  NULL: off */
 	uint32_t * host_bwa;       /* likewise (pacterm, one block): PINNED host buffer of ceil((n-1)/16) words that receives
 	                            * BWA's packed BWT (see b3m_engine_fetch_bwa) while the build runs.  NULL: off */
+	int sortpath;              /* B3M_SORT_*: suffix sorter of a one-block build over an alphabet of at most four codes */
 } b3m_build_params;
+/* AUTO: the MSD bucket sort (two global levels + a finish in shared memory) for texts of 2^16 symbols or more,
+ * the LSD radix sort otherwise.  LSD / MSD force one of them (tests, measurements).  Same results. */
+#define B3M_SORT_AUTO 0
+#define B3M_SORT_LSD 1
+#define B3M_SORT_MSD 2
 /* AUTO: straight from the suffix array when the build holds all of it (one block), by the LF walk
  * from the anchors (the reference's method, /root/reference/src/hwtPreIsaToIsa.cpp:114-161)
  * otherwise.  WALK: always by the LF walk.  The results are identical. */
