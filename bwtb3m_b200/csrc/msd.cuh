@@ -359,10 +359,13 @@ k_msd_finish(MsdFin A) {
 	__shared__ uint32_t r_src[MSD_THREADS];
 	__shared__ uint16_t r_off[MSD_THREADS], r_len[MSD_THREADS];
 	__shared__ uint32_t s_cnt[4];
+	// linear windows: the suffixes shorter than the prefix an unresolved group shares (at most 16 in the whole text)
+	__shared__ uint32_t s_sh_e[16], s_sh_L[16], s_nshort;
 	unsigned const nb2 = 1u << A.b2;
 	uint32_t const sb = blockIdx.x + A.sb0;
 	uint32_t const o0 = A.subbase[sb], m = A.subbase[sb + 1] - o0;
 	if (m == 0) return;
+	uint32_t const W32 = (uint32_t)A.v.W;
 	unsigned const d = sb >> A.b2, d2 = sb & (nb2 - 1u);
 	uint32_t const tp = __ldg(A.tpre + d), ntp = __ldg(A.tpre + d + 1) - tp;
 	uint32_t const pstart = __ldg(A.base + d);
@@ -370,17 +373,45 @@ k_msd_finish(MsdFin A) {
 	const uint16_t * const row1 = row0 + ntp;
 	unsigned const lane = threadIdx.x & 31;
 	if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+	if (threadIdx.x == 0) s_nshort = 0;
+	__syncthreads();
 
 	if (m > (uint32_t)MSD_CAP) {
-		// too large for one CTA: the whole sub-bucket stays one unresolved group (it shares b1+b2 bits)
+		// too large for one CTA: the whole sub-bucket stays one unresolved group sharing h2 symbols.  The
+		// suffixes of a linear window that end inside those symbols are no members of it: they are smaller
+		// than the rest, shorter first, and are placed in front (a group must share REAL symbols, the
+		// doubling rounds compare what follows them).
 		if (ORDER) {
-			uint32_t done = 0; // runs are copied one after the other, a warp-wide loop per tile
+			uint32_t const h2 = (A.b1 + A.b2) >> 1;
+			if (A.lin) {
+				uint32_t done = 0;
+				for (uint32_t k = 0; k < ntp; ++k) {
+					uint32_t const s = row0[k], len = row1[k] - s;
+					const unsigned long long * src = A.recs + pstart + (uint64_t)k * MSD_TILE + s;
+					for (uint32_t x = threadIdx.x; x < len; x += MSD_THREADS) {
+						uint32_t const L = W32 - (uint32_t)src[x];
+						if (L < h2) { uint32_t const q = atomicAdd(&s_nshort, 1u); s_sh_e[q] = done + x; s_sh_L[q] = L; }
+					}
+					done += len;
+				}
+				__syncthreads();
+			}
+			uint32_t const ns = s_nshort;
+			uint32_t done = 0; // runs are copied one after the other
 			for (uint32_t k = 0; k < ntp; ++k) {
 				uint32_t const s = row0[k], len = row1[k] - s;
 				const unsigned long long * src = A.recs + pstart + (uint64_t)k * MSD_TILE + s;
 				for (uint32_t x = threadIdx.x; x < len; x += MSD_THREADS) {
-					A.sa_out[o0 + done + x] = (uint32_t)src[x];
-					A.hflag[o0 + done + x] = (uint8_t)((done + x) == 0 ? 1 : 0);
+					uint32_t const i = (uint32_t)src[x], e = done + x, L = W32 - i;
+					uint32_t pos = e, hf = e == 0 ? 1u : 0u;
+					if (ns) {
+						uint32_t before = 0, smaller = 0;
+						for (uint32_t q = 0; q < ns; ++q) { before += s_sh_e[q] < e ? 1u : 0u; smaller += s_sh_L[q] < L ? 1u : 0u; }
+						if (L < h2) { pos = smaller; hf = 1; }
+						else { pos = ns + e - before; hf = pos == ns ? 1u : 0u; }
+					}
+					A.sa_out[o0 + pos] = i;
+					A.hflag[o0 + pos] = (uint8_t)hf;
 				}
 				done += len;
 			}
@@ -466,6 +497,15 @@ k_msd_finish(MsdFin A) {
 		__syncthreads();
 	}
 
+	// crowded local digits stay unresolved groups sharing hbig symbols: list the suffixes too short for that
+	uint32_t const hbig = (A.b1 + A.b2 + A.lb) >> 1;
+	if (A.lin) {
+		for (uint32_t s = threadIdx.x; s < m; s += MSD_THREADS) {
+			uint32_t const L = W32 - (uint32_t)rec[s];
+			if (L < hbig) { uint32_t const q = atomicAdd(&s_nshort, 1u); s_sh_e[q] = s; s_sh_L[q] = L; }
+		}
+		__syncthreads();
+	}
 	// ---- order inside a local digit by comparison; emit ----
 	unsigned const skip = (A.b1 + 30u) >> 1; // symbols covered by b1 + key30
 	uint32_t ntied = 0, nunres = 0, ngather = 0, flags = 0;
@@ -477,7 +517,15 @@ k_msd_finish(MsdFin A) {
 		uint32_t const a = cnt[dg], b = cnt[dg + 1];
 		uint32_t f = a, hf = 1;
 		if (b - a > (uint32_t)MSD_MAXRUN) {
-			f = s; hf = s == a ? 1u : 0u; ++nunres; flags |= 1u;
+			// one unresolved group; the listed short suffixes of this digit go in front of it, shorter first
+			uint32_t const ns = s_nshort, myL = W32 - (uint32_t)me;
+			uint32_t nsb = 0, before = 0, smaller = 0;
+			for (uint32_t q = 0; q < ns; ++q) {
+				uint32_t const e = s_sh_e[q];
+				if (e >= a && e < b) { ++nsb; before += e < s ? 1u : 0u; smaller += s_sh_L[q] < myL ? 1u : 0u; }
+			}
+			if (A.lin && myL < hbig) { f = a + smaller; hf = 1; }
+			else { f = s + nsb - before; hf = (s - a == before) ? 1u : 0u; ++nunres; flags |= 1u; }
 		} else if (b - a > 1) {
 			uint32_t less = 0, eq = 0;
 			#pragma unroll 1
