@@ -6,25 +6,28 @@
 //
 // A record is ONE 64-bit word: [63:62] code preceding the suffix, [61:32] key30 = bits
 // [b1, b1+30) of the suffix (2 bits per symbol), [31:0] suffix index.
-//   hist     k_msd_hist      histogram of the first b1 bits of every suffix, read off the packed text
-//   level 1  k_msd_scatter   builds the records from the packed text (a thread takes 16 consecutive
+//   count    k_msd_count     per tile of 8192 text positions: how many suffixes start with each value of
+//                            their first b1 bits (read off the packed text; 16-bit counts)
+//            k_msd_col*      exclusive scan of those counts down every column: where the records of tile t
+//                            and bin b go inside bin b, and the size of every bin (no look-back chain, no
+//                            spinning between CTAs)
+//   level 1  k_msd_scatter   builds the records of a tile from the packed text (a thread takes 16 consecutive
 //                            positions out of three 64-bit words), ranks them by their first b1 bits
-//                            with shared-memory atomics (an MSD pass need not be stable), obtains the
-//                            global offsets by decoupled look-back and writes runs per bin
+//                            with shared-memory atomics (an MSD pass need not be stable) and writes runs per bin
 //   level 2  k_msd_local     sorts every tile of a level-1 bucket by its next b2 bits IN PLACE (loads
 //                            to registers, ranks with shared-memory atomics, one bulk async store
 //                            shared -> global per tile) and records where each of the 2^b2 runs starts
 //   totals   k_msd_subtotals size of every (b1+b2)-bit sub-bucket from the run tables; scan -> ranks
 //   finish   k_msd_finish    one CTA per sub-bucket: gathers its runs from the tiles of the parent
-//                            bucket, sorts them in shared memory (local digit by atomics, the few
-//                            records per digit by comparison: rest of key30, then 32 more symbols
-//                            read from the text, then remaining length), and emits BWT, anchors and
-//                            sampled SA/ISA at the final ranks (or the order + head flags)
-// Algorithmic HBM bytes per suffix: 0.25 (hist) + 0.25 + 8 (level 1) + 8 + 8 (level 2) +
-// 8 + 1.25 (finish) = 33.75, against 73.75 of the LSD path (radix.cuh) -- and about a quarter of
-// its instructions, which is what bounded that path.  Sub-buckets larger than MSD_CAP records and
-// local digits shared by more than MSD_MAXRUN records are left as unresolved groups for the
-// prefix-doubling rounds of sufsort.cu.
+//                            bucket (16-byte cp.async, no register staging), sorts them in shared memory
+//                            (local digit by atomics, the few records per digit by comparison: rest of
+//                            key30, then 32 more symbols read from the text, then remaining length), and
+//                            emits BWT, anchors and sampled SA/ISA at the final ranks (or the order + head flags)
+// Algorithmic HBM bytes per suffix: 0.25 + 0.25 (count) + 3 * 0.5 (column scan: 16-bit counts read
+// twice, 32-bit offsets written) + 0.25 + 0.5 + 8 (level 1) + 8 + 8 (level 2) + 8 + 1.25 (finish)
+// = 36.5, against 73.75 of the LSD path (radix.cuh) -- and a fraction of its instructions, which is
+// what bounded that path.  Sub-buckets larger than MSD_CAP records and local digits shared by more
+// than MSD_MAXRUN records are left as unresolved groups for the prefix-doubling rounds of sufsort.cu.
 #pragma once
 #include "common.cuh"
 #include "scan.cuh"
@@ -36,25 +39,26 @@ namespace b3m {
 constexpr int MSD_THREADS = 512;
 constexpr int MSD_ITEMS = 16;
 constexpr int MSD_TILE = MSD_THREADS * MSD_ITEMS;   // 8192 records per tile of both levels
-constexpr int MSD_MAXBINS = 2048;
-constexpr int MSD_CAP = 8192;                       // records one finish CTA sorts
-constexpr int MSD_LBITS = 11;                       // local digit of the finish
+constexpr int MSD_MAXBINS = 2048;                   // bins of a global level
+constexpr int MSD_CAP = 8192;                       // records (incl. alignment padding) one finish CTA holds
+constexpr int MSD_LBITS_MIN = 8;                    // local digit of the finish: 256 ..
+constexpr int MSD_LBITS_MAX = 13;                   // .. 8192 bins, about two per record
 constexpr int MSD_MAXRUN = 32;                      // records per local digit sorted by comparison
 constexpr int MSD_CSLOTS = 256;
+constexpr int MSD_COLCHUNK = 256;                   // tiles per CTA of the column scan
 constexpr uint32_t MSD_KEYMASK = 0x3fffffffu;
-constexpr uint32_t MSD_FLAG_AGG = 1u << 30;
-constexpr uint32_t MSD_FLAG_INC = 2u << 30;
+constexpr unsigned long long MSD_PAD = ~0ull;       // not a record: indices stay below 2^32 - 256
 
-// exclusive scan of cnt[0..nb) in place (nb <= 4 * THREADS); mine[] = the counts of this thread's
+// exclusive scan of cnt[0..nb) in place (nb <= PERMAX * THREADS); mine[] = the counts of this thread's
 // bins b0 .. b0+per-1 (b0 = threadIdx.x * per); returns the total.  Ends with a barrier.
-template <int THREADS>
-__device__ __forceinline__ uint32_t msd_scan_bins(uint32_t * cnt, unsigned nb, uint32_t * wsum, uint32_t (&mine)[4], unsigned & b0, unsigned & per) {
+template <int THREADS, int PERMAX>
+__device__ __forceinline__ uint32_t msd_scan_bins(uint32_t * cnt, unsigned nb, uint32_t * wsum, uint32_t (&mine)[PERMAX], unsigned & b0, unsigned & per) {
 	unsigned const lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 	per = (nb + THREADS - 1) / THREADS;
 	b0 = threadIdx.x * per;
 	uint32_t s = 0;
 	#pragma unroll
-	for (unsigned q = 0; q < 4; ++q) { mine[q] = (q < per && b0 + q < nb) ? cnt[b0 + q] : 0u; s += mine[q]; }
+	for (unsigned q = 0; q < (unsigned)PERMAX; ++q) { mine[q] = (q < per && b0 + q < nb) ? cnt[b0 + q] : 0u; s += mine[q]; }
 	uint32_t incl = s;
 	#pragma unroll
 	for (int o = 1; o < 32; o <<= 1) { uint32_t const t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += t; }
@@ -70,9 +74,34 @@ __device__ __forceinline__ uint32_t msd_scan_bins(uint32_t * cnt, unsigned nb, u
 	uint32_t run = (w ? wsum[w - 1] : 0u) + incl - s;
 	uint32_t const total = wsum[THREADS / 32 - 1];
 	#pragma unroll
-	for (unsigned q = 0; q < 4; ++q) if (q < per && b0 + q < nb) { cnt[b0 + q] = run; run += mine[q]; }
+	for (unsigned q = 0; q < (unsigned)PERMAX; ++q) if (q < per && b0 + q < nb) { cnt[b0 + q] = run; run += mine[q]; }
 	__syncthreads();
 	return total;
+}
+
+// the same for any number of bins, keeping nothing in registers: every thread scans nb / THREADS consecutive bins
+template <int THREADS>
+__device__ __forceinline__ void msd_scan_bins_wide(uint32_t * cnt, unsigned nb, uint32_t * wsum) {
+	unsigned const lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	unsigned const per = (nb + THREADS - 1) / THREADS, b0 = threadIdx.x * per;
+	unsigned const b1 = b0 + per < nb ? b0 + per : nb;
+	uint32_t s = 0;
+	for (unsigned b = b0; b < b1; ++b) s += cnt[b];
+	uint32_t incl = s;
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { uint32_t const t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += t; }
+	if (lane == 31) wsum[w] = incl;
+	__syncthreads();
+	if (w == 0) {
+		uint32_t x = lane < THREADS / 32 ? wsum[lane] : 0u;
+		#pragma unroll
+		for (int o = 1; o < THREADS / 32; o <<= 1) { uint32_t const t = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (unsigned)o) x += t; }
+		if (lane < THREADS / 32) wsum[lane] = x;
+	}
+	__syncthreads();
+	uint32_t run = (w ? wsum[w - 1] : 0u) + incl - s;
+	for (unsigned b = b0; b < b1; ++b) { uint32_t const c = cnt[b]; cnt[b] = run; run += c; }
+	__syncthreads();
 }
 
 // first 64 bits of the suffix at window index i (zero behind the end of a linear window, wrapping
@@ -83,60 +112,11 @@ __device__ __forceinline__ void msd_record(TextView const & v, uint64_t i, unsig
 	hi32 = (tv_pred(v, i) << 30) | ((uint32_t)(sb >> (34u - b1)) & MSD_KEYMASK);
 }
 
-// ---- histogram of the first b1 bits --------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_msd_hist(TextView v, unsigned b1, unsigned long long * __restrict__ ghist) {
-	__shared__ uint32_t sh[MSD_MAXBINS];
-	unsigned const nb = 1u << b1;
-	for (unsigned i = threadIdx.x; i < nb; i += blockDim.x) sh[i] = 0;
-	__syncthreads();
-	uint64_t const nchunks = div_up(v.W, 32);
-	unsigned const sr = 64u - b1;
-	for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nchunks; q += (uint64_t)gridDim.x * blockDim.x) {
-		uint64_t const j0 = q * 32;
-		uint64_t const p = tv_interior(v, j0, 64);
-		if (p != ~0ull) {
-			uint64_t const a = pk_window(v.packed, p), b = pk_window(v.packed, p + 32);
-			atomicAdd(&sh[(uint32_t)(a >> sr)], 1u);
-			#pragma unroll
-			for (int s = 1; s < 32; ++s) atomicAdd(&sh[(uint32_t)(((a << (2 * s)) | (b >> (64 - 2 * s))) >> sr)], 1u);
-		} else {
-			for (uint64_t j = j0; j < j0 + 32 && j < v.W; ++j) atomicAdd(&sh[(uint32_t)(tv_symbols(v, j, 32, 2) >> sr)], 1u);
-		}
-	}
-	__syncthreads();
-	for (unsigned i = threadIdx.x; i < nb; i += blockDim.x) if (sh[i]) atomicAdd(&ghist[i], (unsigned long long)sh[i]);
-}
-
-// ---- level 1 ---------------------------------------------------------------------------------
-struct MsdP1 {
-	TextView v;
-	unsigned b1;
-	uint32_t d_lo, nkeep;           // bins [d_lo, d_lo + nkeep) are kept (one key range of a sharded build, or all)
-	const uint32_t * base;          // [nkeep + 1] first record of kept bin b
-	uint32_t * status;              // [ntiles][nkeep]
-	uint32_t * ticket;
-	unsigned long long * out;
-};
-
-__global__ void __launch_bounds__(MSD_THREADS, 2)
-k_msd_scatter(MsdP1 A) {
-	extern __shared__ __align__(16) uint8_t msd_dyn[];
-	unsigned long long * const stage = reinterpret_cast<unsigned long long *>(msd_dyn);
-	__shared__ uint32_t cnt[MSD_MAXBINS];
-	__shared__ uint32_t gdel[MSD_MAXBINS];
-	__shared__ uint32_t wsum[MSD_THREADS / 32];
-	__shared__ uint32_t s_tile;
-	TextView const & v = A.v;
-	unsigned const b1 = A.b1, nkeep = A.nkeep;
-	if (threadIdx.x == 0) s_tile = atomicAdd(A.ticket, 1u);
-	for (unsigned i = threadIdx.x; i < nkeep; i += MSD_THREADS) cnt[i] = 0;
-	__syncthreads();
-	uint32_t const tile = s_tile;
-	uint64_t const t0 = (uint64_t)tile * MSD_TILE;
-	uint64_t const pos0 = t0 + (uint64_t)MSD_ITEMS * threadIdx.x;
-
-	uint32_t hi32[MSD_ITEMS], dr[MSD_ITEMS]; // dr = (kept bin << 16) | rank inside the tile's bin; ~0: not kept
+// The MSD_ITEMS records of the positions pos0 .. pos0+15 (one thread): d[j] = first b1 bits (~0: no such
+// position), hi32[j] = upper half of the record.  Fast path: three packed words hold the symbols from one
+// before pos0 on; every field is a constant-distance bit field of that 128-bit window.
+template <bool WANT_HI>
+__device__ __forceinline__ void msd_records16(TextView const & v, unsigned b1, uint64_t pos0, uint32_t (&d)[MSD_ITEMS], uint32_t (&hi32)[MSD_ITEMS]) {
 	bool const fast = pos0 >= 1 && (v.circular ? pos0 + MSD_ITEMS + 32 <= v.W : pos0 + MSD_ITEMS <= v.W);
 	if (fast) {
 		uint64_t const q = pos0 - 1; // wstart == 0: window index == text position
@@ -148,54 +128,135 @@ k_msd_scatter(MsdP1 A) {
 		#pragma unroll
 		for (int j = 0; j < MSD_ITEMS; ++j) {
 			uint64_t const sb = (hi << (2 * j + 2)) | (lo >> (62 - 2 * j)); // suffix bits from symbol j+1 on
-			uint32_t const d = (uint32_t)(sb >> (64u - b1)) - A.d_lo;
-			hi32[j] = ((uint32_t)(hi >> (62 - 2 * j)) << 30) | ((uint32_t)(sb >> (34u - b1)) & MSD_KEYMASK);
-			dr[j] = d < nkeep ? ((d << 16) | atomicAdd(&cnt[d], 1u)) : 0xffffffffu;
+			d[j] = (uint32_t)(sb >> (64u - b1));
+			if (WANT_HI) hi32[j] = ((uint32_t)(hi >> (62 - 2 * j)) << 30) | ((uint32_t)(sb >> (34u - b1)) & MSD_KEYMASK);
 		}
 	} else {
 		#pragma unroll
 		for (int j = 0; j < MSD_ITEMS; ++j) {
 			uint64_t const i = pos0 + j;
-			uint32_t d = 0xffffffffu, h = 0;
-			if (i < v.W) { msd_record(v, i, b1, d, h); d -= A.d_lo; }
-			hi32[j] = h;
-			dr[j] = d < nkeep ? ((d << 16) | atomicAdd(&cnt[d], 1u)) : 0xffffffffu;
+			uint32_t dd = 0xffffffffu, h = 0;
+			if (i < v.W) msd_record(v, i, b1, dd, h);
+			d[j] = dd;
+			if (WANT_HI) hi32[j] = h;
 		}
+	}
+}
+
+// ---- histogram of the first b1 bits over the whole text (the plan of a sharded build) --------
+__global__ void __launch_bounds__(256)
+k_msd_hist(TextView v, unsigned b1, unsigned long long * __restrict__ ghist) {
+	__shared__ uint32_t sh[MSD_MAXBINS];
+	unsigned const nb = 1u << b1;
+	for (unsigned i = threadIdx.x; i < nb; i += blockDim.x) sh[i] = 0;
+	__syncthreads();
+	uint64_t const nchunks = div_up(v.W, MSD_ITEMS);
+	for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nchunks; q += (uint64_t)gridDim.x * blockDim.x) {
+		uint32_t d[MSD_ITEMS], h[MSD_ITEMS];
+		msd_records16<false>(v, b1, q * MSD_ITEMS, d, h);
+		#pragma unroll
+		for (int j = 0; j < MSD_ITEMS; ++j) if (d[j] != 0xffffffffu) atomicAdd(&sh[d[j]], 1u);
+	}
+	__syncthreads();
+	for (unsigned i = threadIdx.x; i < nb; i += blockDim.x) if (sh[i]) atomicAdd(&ghist[i], (unsigned long long)sh[i]);
+}
+
+// ---- per-tile counts of the kept bins -------------------------------------------------------
+__global__ void __launch_bounds__(MSD_THREADS)
+k_msd_count(TextView v, unsigned b1, uint32_t d_lo, uint32_t nkeep, uint16_t * __restrict__ tcount /* [ntiles][nkeep] */) {
+	__shared__ uint32_t cnt[MSD_MAXBINS];
+	for (unsigned i = threadIdx.x; i < nkeep; i += MSD_THREADS) cnt[i] = 0;
+	__syncthreads();
+	uint32_t d[MSD_ITEMS], h[MSD_ITEMS];
+	msd_records16<false>(v, b1, (uint64_t)blockIdx.x * MSD_TILE + (uint64_t)MSD_ITEMS * threadIdx.x, d, h);
+	#pragma unroll
+	for (int j = 0; j < MSD_ITEMS; ++j) { uint32_t const b = d[j] - d_lo; if (b < nkeep) atomicAdd(&cnt[b], 1u); }
+	__syncthreads();
+	uint16_t * const row = tcount + (uint64_t)blockIdx.x * nkeep;
+	for (unsigned i = threadIdx.x; i < nkeep; i += MSD_THREADS) row[i] = (uint16_t)cnt[i]; // at most 8192 per tile and bin
+}
+
+// ---- column scan of the tile counts ------------------------------------------------------------
+// partial[c][b] = sum of tcount[t][b] over the tiles t of chunk c
+__global__ void __launch_bounds__(256)
+k_msd_colsum(const uint16_t * __restrict__ tcount, uint32_t ntiles, uint32_t nkeep, uint32_t * __restrict__ partial) {
+	uint32_t const t_lo = blockIdx.x * MSD_COLCHUNK, t_hi = t_lo + MSD_COLCHUNK < ntiles ? t_lo + MSD_COLCHUNK : ntiles;
+	for (uint32_t b = threadIdx.x; b < nkeep; b += 256) {
+		uint32_t s = 0;
+		for (uint32_t t = t_lo; t < t_hi; ++t) s += tcount[(uint64_t)t * nkeep + b];
+		partial[(uint64_t)blockIdx.x * nkeep + b] = s;
+	}
+}
+// exclusive scan of partial down every column, in place; total[b] = size of bin b
+__global__ void __launch_bounds__(256)
+k_msd_colscan(uint32_t * __restrict__ partial, uint32_t nchunks, uint32_t nkeep, unsigned long long * __restrict__ total) {
+	uint32_t const b = blockIdx.x * 256 + threadIdx.x;
+	if (b >= nkeep) return;
+	unsigned long long run = 0;
+	for (uint32_t c = 0; c < nchunks; ++c) {
+		uint32_t const x = partial[(uint64_t)c * nkeep + b];
+		partial[(uint64_t)c * nkeep + b] = (uint32_t)run;
+		run += x;
+	}
+	total[b] = run;
+}
+// toff[t][b] = number of records of bin b in the tiles before t
+__global__ void __launch_bounds__(256)
+k_msd_colapply(const uint16_t * __restrict__ tcount, uint32_t ntiles, uint32_t nkeep, const uint32_t * __restrict__ partial, uint32_t * __restrict__ toff) {
+	uint32_t const t_lo = blockIdx.x * MSD_COLCHUNK, t_hi = t_lo + MSD_COLCHUNK < ntiles ? t_lo + MSD_COLCHUNK : ntiles;
+	for (uint32_t b = threadIdx.x; b < nkeep; b += 256) {
+		uint32_t run = partial[(uint64_t)blockIdx.x * nkeep + b];
+		for (uint32_t t = t_lo; t < t_hi; ++t) {
+			toff[(uint64_t)t * nkeep + b] = run;
+			run += tcount[(uint64_t)t * nkeep + b];
+		}
+	}
+}
+
+// ---- level 1 ---------------------------------------------------------------------------------
+struct MsdP1 {
+	TextView v;
+	unsigned b1;
+	uint32_t d_lo, nkeep;           // bins [d_lo, d_lo + nkeep) are kept (one key range of a sharded build, or all)
+	const uint32_t * base;          // [nkeep + 1] first record of kept bin b
+	const uint32_t * toff;          // [ntiles][nkeep] records of bin b in earlier tiles
+	unsigned long long * out;
+};
+
+__global__ void __launch_bounds__(MSD_THREADS, 2)
+k_msd_scatter(MsdP1 A) {
+	extern __shared__ __align__(16) uint8_t msd_dyn[];
+	unsigned long long * const stage = reinterpret_cast<unsigned long long *>(msd_dyn);
+	__shared__ uint32_t cnt[MSD_MAXBINS];
+	__shared__ uint32_t gdel[MSD_MAXBINS];
+	__shared__ uint32_t wsum[MSD_THREADS / 32];
+	unsigned const nkeep = A.nkeep;
+	for (unsigned i = threadIdx.x; i < nkeep; i += MSD_THREADS) cnt[i] = 0;
+	__syncthreads();
+	uint32_t const tile = blockIdx.x;
+	uint64_t const t0 = (uint64_t)tile * MSD_TILE;
+
+	uint32_t hi32[MSD_ITEMS], dr[MSD_ITEMS]; // dr = (kept bin << 16) | rank inside the tile's bin; ~0: not kept
+	msd_records16<true>(A.v, A.b1, t0 + (uint64_t)MSD_ITEMS * threadIdx.x, dr, hi32);
+	#pragma unroll
+	for (int j = 0; j < MSD_ITEMS; ++j) {
+		uint32_t const d = dr[j] - A.d_lo;
+		dr[j] = d < nkeep ? ((d << 16) | atomicAdd(&cnt[d], 1u)) : 0xffffffffu;
 	}
 	__syncthreads();
 	uint32_t mine[4];
 	unsigned b0, per;
-	uint32_t const nvalid = msd_scan_bins<MSD_THREADS>(cnt, nkeep, wsum, mine, b0, per);
-	// publish the tile's counts, stage the records, then look back
-	uint32_t * const strow = A.status + (uint64_t)tile * nkeep;
+	uint32_t const nvalid = msd_scan_bins<MSD_THREADS, 4>(cnt, nkeep, wsum, mine, b0, per);
+	const uint32_t * const orow = A.toff + (uint64_t)tile * nkeep;
 	#pragma unroll
 	for (unsigned q = 0; q < 4; ++q)
-		if (q < per && b0 + q < nkeep) __stcg(&strow[b0 + q], (tile == 0 ? MSD_FLAG_INC : MSD_FLAG_AGG) | mine[q]);
+		if (q < per && b0 + q < nkeep) gdel[b0 + q] = __ldg(A.base + b0 + q) + __ldg(orow + b0 + q) - cnt[b0 + q];
 	#pragma unroll
 	for (int j = 0; j < MSD_ITEMS; ++j) {
 		if (dr[j] != 0xffffffffu) {
 			uint32_t const d = dr[j] >> 16;
 			uint32_t const slot = cnt[d] + (dr[j] & 0xffffu);
 			stage[slot] = ((unsigned long long)hi32[j] << 32) | (d << 14) | (uint32_t)(MSD_ITEMS * threadIdx.x + j);
-		}
-	}
-	#pragma unroll
-	for (unsigned q = 0; q < 4; ++q) {
-		if (q < per && b0 + q < nkeep) {
-			unsigned const b = b0 + q;
-			uint32_t excl = 0;
-			if (tile > 0) {
-				int64_t t = (int64_t)tile - 1;
-				while (true) {
-					uint32_t const sv = *(volatile uint32_t *)(A.status + (uint64_t)t * nkeep + b);
-					if ((sv >> 30) == 0) continue;
-					excl += sv & MSD_KEYMASK;
-					if ((sv >> 30) == 2) break;
-					--t;
-				}
-				__stcg(&strow[b], MSD_FLAG_INC | (excl + mine[q]));
-			}
-			gdel[b] = A.base[b] + excl - cnt[b];
 		}
 	}
 	__syncthreads();
@@ -211,13 +272,6 @@ k_msd_scatter(MsdP1 A) {
 }
 
 // ---- level 2 ---------------------------------------------------------------------------------
-// tile g of the grid -> (kept bin d, tile k of that bin): tpre[d] <= g < tpre[d+1]
-__device__ __forceinline__ unsigned msd_find_bin(const uint32_t * __restrict__ tpre, unsigned nkeep, uint32_t g) {
-	unsigned lo = 0, hi = nkeep; // tpre[lo] <= g < tpre[hi]
-	while (hi - lo > 1) { unsigned const mid = (lo + hi) >> 1; if (__ldg(tpre + mid) <= g) lo = mid; else hi = mid; }
-	return lo;
-}
-
 struct MsdP2 {
 	unsigned b2, nkeep;
 	const uint32_t * base;          // [nkeep + 1]
@@ -234,7 +288,9 @@ k_msd_local(MsdP2 A) {
 	__shared__ uint32_t wsum[MSD_THREADS / 32];
 	__shared__ uint32_t s_bin;
 	unsigned const nb2 = 1u << A.b2;
-	if (threadIdx.x == 0) s_bin = msd_find_bin(A.tpre, A.nkeep, blockIdx.x);
+	// tile g of the grid -> (kept bin d, tile k of that bin): tpre[d] <= g < tpre[d+1]; every thread tests a few bins
+	for (unsigned b = threadIdx.x; b < A.nkeep; b += MSD_THREADS)
+		if (__ldg(A.tpre + b) <= blockIdx.x && blockIdx.x < __ldg(A.tpre + b + 1)) s_bin = b;
 	for (unsigned i = threadIdx.x; i < nb2; i += MSD_THREADS) cnt[i] = 0;
 	__syncthreads();
 	unsigned const d = s_bin;
@@ -260,7 +316,7 @@ k_msd_local(MsdP2 A) {
 	__syncthreads();
 	uint32_t mine[4];
 	unsigned b0, per;
-	msd_scan_bins<MSD_THREADS>(cnt, nb2, wsum, mine, b0, per);
+	msd_scan_bins<MSD_THREADS, 4>(cnt, nb2, wsum, mine, b0, per);
 	uint16_t * const tab = A.table + (uint64_t)tp * (nb2 + 1) + k;
 	for (unsigned b = threadIdx.x; b <= nb2; b += MSD_THREADS) tab[(uint64_t)b * ntp] = (uint16_t)(b < nb2 ? cnt[b] : m);
 	// sorted tile in shared memory, shifted by the parity of `start` so that 16-byte aligned global
@@ -321,7 +377,7 @@ k_msd_subtotals(unsigned b2, const uint32_t * __restrict__ tpre, const uint16_t 
 struct MsdFin {
 	TextView v;
 	int lin;
-	unsigned b1, b2, lb, glog;      // lb: bits of the local digit; 2^glog lanes copy one run
+	unsigned b1, b2, glog;          // 2^glog lanes copy one run
 	unsigned nkeep;
 	const unsigned long long * recs;
 	const uint32_t * base, * tpre;
@@ -331,6 +387,7 @@ struct MsdFin {
 	uint32_t * sa_out;              // ORDER
 	uint8_t * hflag;
 	FusedOut fo;                    // FUSED (shift includes the rank of the first kept record)
+	uint32_t imask, rmask;          // a suffix at position i / of rank r is sampled only if (i & imask) == 0 or (r & rmask) == 0
 	unsigned long long * counters;  // [MSD_CSLOTS][4]: unresolved, tied, second keys read, flags (1: run too long, 2: sub-bucket too large)
 };
 
@@ -348,16 +405,40 @@ __device__ __forceinline__ void msd_emit_samples(FusedOut const & fo, uint32_t i
 	if (fo.sa_s && (fo.salog >= 32 ? r == 0 : (r & ((1u << fo.salog) - 1u)) == 0)) fo.sa_s[fo.salog >= 32 ? 0 : (r >> fo.salog)] = i;
 }
 
+// one chunk of MSD_THREADS tiles of the parent bucket: thread <-> tile k0 + threadIdx.x; returns this
+// thread's run widened to 16-byte boundaries as (first record a0, padded length plen, place off in rec[])
+// and adds the chunk's padded total to `done`.  g0/g1 = the run itself.
+__device__ __forceinline__ void msd_run_place(const uint16_t * __restrict__ row0, const uint16_t * __restrict__ row1, uint32_t pstart, uint32_t ntp,
+                                              uint32_t k0, uint32_t * wsum, uint32_t & done, uint32_t & g0, uint32_t & g1, uint32_t & a0, uint32_t & plen, uint32_t & off) {
+	unsigned const lane = threadIdx.x & 31;
+	uint32_t const k = k0 + threadIdx.x;
+	g0 = g1 = 0;
+	if (k < ntp) { uint32_t const s = row0[k]; g0 = pstart + k * (uint32_t)MSD_TILE + s; g1 = g0 + (row1[k] - s); }
+	a0 = g0 & ~1u;
+	plen = g1 > g0 ? ((g1 + 1u) & ~1u) - a0 : 0u;
+	uint32_t incl = plen;
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { uint32_t const t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += t; }
+	__syncthreads(); // wsum (and the caller's descriptors) of the previous chunk have been consumed
+	if (lane == 31) wsum[threadIdx.x >> 5] = incl;
+	__syncthreads();
+	uint32_t before = 0, ctot = 0;
+	#pragma unroll
+	for (int ww = 0; ww < MSD_THREADS / 32; ++ww) { uint32_t const x = wsum[ww]; before += ww < (int)(threadIdx.x >> 5) ? x : 0u; ctot += x; }
+	off = done + before + incl - plen;
+	done += ctot;
+}
+
 template <bool FUSED, bool ORDER>
 __global__ void __launch_bounds__(MSD_THREADS, 2)
 k_msd_finish(MsdFin A) {
 	extern __shared__ __align__(16) uint8_t msd_dyn[];
 	unsigned long long * const rec = reinterpret_cast<unsigned long long *>(msd_dyn);   // MSD_CAP
 	uint8_t * const s_bwt = msd_dyn + (size_t)MSD_CAP * 8;                                 // MSD_CAP
-	__shared__ uint32_t cnt[MSD_MAXBINS + 1];
+	uint32_t * const cnt = reinterpret_cast<uint32_t *>(msd_dyn + (size_t)MSD_CAP * 9);    // 2^MSD_LBITS_MAX + 1
 	__shared__ uint32_t wsum[MSD_THREADS / 32];
-	__shared__ uint32_t r_src[MSD_THREADS];
-	__shared__ uint16_t r_off[MSD_THREADS], r_len[MSD_THREADS];
+	__shared__ uint32_t r_src[MSD_THREADS];                       // per run of a chunk of tiles: first 16-byte aligned record,
+	__shared__ uint16_t r_off[MSD_THREADS], r_n[MSD_THREADS];     // its place in rec[], its length in 16-byte pieces
 	__shared__ uint32_t s_cnt[4];
 	// linear windows: the suffixes shorter than the prefix an unresolved group shares (at most 16 in the whole text)
 	__shared__ uint32_t s_sh_e[16], s_sh_L[16], s_nshort;
@@ -376,7 +457,7 @@ k_msd_finish(MsdFin A) {
 	if (threadIdx.x == 0) s_nshort = 0;
 	__syncthreads();
 
-	if (m > (uint32_t)MSD_CAP) {
+	if ((uint64_t)m + 2ull * ntp > (uint64_t)MSD_CAP) {
 		// too large for one CTA: the whole sub-bucket stays one unresolved group sharing h2 symbols.  The
 		// suffixes of a linear window that end inside those symbols are no members of it: they are smaller
 		// than the rest, shorter first, and are placed in front (a group must share REAL symbols, the
@@ -423,82 +504,78 @@ k_msd_finish(MsdFin A) {
 		return;
 	}
 
-	// ---- gather the runs of this sub-bucket: 2^glog lanes per run ----
+	// ---- gather the runs of this sub-bucket with 16-byte cp.async: a run is widened to 16-byte boundaries,
+	//      the (at most two) records of neighbouring runs this drags in are overwritten with MSD_PAD afterwards ----
 	unsigned const gsz = 1u << A.glog, gl = threadIdx.x & (gsz - 1u), grp = threadIdx.x >> A.glog, ngrp = MSD_THREADS >> A.glog;
-	uint32_t done = 0;
+	uint32_t const rec_s = (uint32_t)__cvta_generic_to_shared(rec);
+	uint32_t mpad = 0; // records in rec[], padding included
 	for (uint32_t k0 = 0; k0 < ntp; k0 += MSD_THREADS) {
-		uint32_t const k = k0 + threadIdx.x;
-		uint32_t s = 0, len = 0;
-		if (k < ntp) { s = row0[k]; len = row1[k] - s; }
-		uint32_t incl = len;
-		#pragma unroll
-		for (int o = 1; o < 32; o <<= 1) { uint32_t const t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += t; }
-		__syncthreads(); // the descriptors of the previous chunk have been consumed
-		if (lane == 31) wsum[threadIdx.x >> 5] = incl;
-		__syncthreads();
-		uint32_t before = 0;
-		#pragma unroll
-		for (int ww = 0; ww < MSD_THREADS / 32; ++ww) before += ww < (int)(threadIdx.x >> 5) ? wsum[ww] : 0u;
-		uint32_t ctot = 0;
-		#pragma unroll
-		for (int ww = 0; ww < MSD_THREADS / 32; ++ww) ctot += wsum[ww];
-		r_src[threadIdx.x] = pstart + k * (uint32_t)MSD_TILE + s;
-		r_off[threadIdx.x] = (uint16_t)(done + before + incl - len);
-		r_len[threadIdx.x] = (uint16_t)len;
+		uint32_t g0, g1, a0, plen, off;
+		msd_run_place(row0, row1, pstart, ntp, k0, wsum, mpad, g0, g1, a0, plen, off);
+		r_src[threadIdx.x] = a0;
+		r_off[threadIdx.x] = (uint16_t)off;
+		r_n[threadIdx.x] = (uint16_t)(plen >> 1);
 		__syncthreads();
 		uint32_t const nr = ntp - k0 < (uint32_t)MSD_THREADS ? ntp - k0 : (uint32_t)MSD_THREADS;
-		for (uint32_t i0 = 0; i0 < nr; i0 += 4 * ngrp) {
-			unsigned long long val[4];
-			#pragma unroll
-			for (int u = 0; u < 4; ++u) {
-				uint32_t const q = i0 + u * ngrp + grp;
-				val[u] = (q < nr && gl < r_len[q]) ? __ldcs(A.recs + r_src[q] + gl) : 0ull;
-			}
-			#pragma unroll
-			for (int u = 0; u < 4; ++u) {
-				uint32_t const q = i0 + u * ngrp + grp;
-				if (q < nr && gl < r_len[q]) rec[r_off[q] + gl] = val[u];
-			}
-			#pragma unroll 1
-			for (int u = 0; u < 4; ++u) {
-				uint32_t const q = i0 + u * ngrp + grp;
-				if (q < nr) for (uint32_t x = gl + gsz; x < r_len[q]; x += gsz) rec[r_off[q] + x] = __ldcs(A.recs + r_src[q] + x);
+		for (uint32_t q = grp; q < nr; q += ngrp) {
+			uint32_t const n16 = r_n[q];
+			const unsigned long long * const src = A.recs + r_src[q];
+			uint32_t const dst = rec_s + 8u * r_off[q];
+			for (uint32_t x = gl; x < n16; x += gsz)
+				asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + 16u * x), "l"(src + 2 * x) : "memory");
+		}
+	}
+	asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+	__syncthreads();
+	{
+		// the records dragged in from neighbouring runs: one more walk over the descriptors
+		uint32_t done = 0;
+		for (uint32_t k0 = 0; k0 < ntp; k0 += MSD_THREADS) {
+			uint32_t g0, g1, a0, plen, off;
+			msd_run_place(row0, row1, pstart, ntp, k0, wsum, done, g0, g1, a0, plen, off);
+			if (plen) {
+				if (g0 & 1u) rec[off] = MSD_PAD;
+				if (g1 & 1u) rec[off + plen - 1] = MSD_PAD;
 			}
 		}
-		done += ctot;
 	}
-	unsigned const nlb = 1u << A.lb;
+	// local digit: about two bins per record
+	unsigned lb = MSD_LBITS_MIN;
+	while (lb < (unsigned)MSD_LBITS_MAX && (1u << lb) < 2u * m) ++lb;
+	unsigned const nlb = 1u << lb;
 	for (unsigned i = threadIdx.x; i <= nlb; i += MSD_THREADS) cnt[i] = 0;
 	__syncthreads();
 
 	// ---- local digit: rank by atomics, scan, permute in place through registers ----
-	unsigned const lsh = 62u - A.b2 - A.lb; // the local digit follows the b2 bits of level 2 inside key30
+	unsigned const lsh = 62u - A.b2 - lb; // the local digit follows the b2 bits of level 2 inside key30
 	{
 		unsigned long long r[MSD_ITEMS];
 		uint32_t dr[MSD_ITEMS];
 		#pragma unroll
 		for (int j = 0; j < MSD_ITEMS; ++j) {
-			uint32_t const s = j * MSD_THREADS + threadIdx.x;
 			dr[j] = 0xffffffffu;
-			if (s < m) {
-				r[j] = rec[s];
-				uint32_t const dg = (uint32_t)(r[j] >> lsh) & (nlb - 1u);
-				dr[j] = (dg << 16) | atomicAdd(&cnt[dg], 1u);
+			if ((uint32_t)(j * MSD_THREADS) < mpad) { // uniform: whole iterations are skipped
+				uint32_t const s = j * MSD_THREADS + threadIdx.x;
+				if (s < mpad) {
+					r[j] = rec[s];
+					if (r[j] != MSD_PAD) {
+						uint32_t const dg = (uint32_t)(r[j] >> lsh) & (nlb - 1u);
+						dr[j] = (dg << 16) | atomicAdd(&cnt[dg], 1u);
+					}
+				}
 			}
 		}
 		__syncthreads();
-		uint32_t mine[4];
-		unsigned b0, per;
-		msd_scan_bins<MSD_THREADS>(cnt, nlb, wsum, mine, b0, per);
+		msd_scan_bins_wide<MSD_THREADS>(cnt, nlb, wsum);
 		if (threadIdx.x == 0) cnt[nlb] = m;
 		#pragma unroll
 		for (int j = 0; j < MSD_ITEMS; ++j)
-			if (dr[j] != 0xffffffffu) rec[cnt[dr[j] >> 16] + (dr[j] & 0xffffu)] = r[j];
+			if ((uint32_t)(j * MSD_THREADS) < mpad && dr[j] != 0xffffffffu) rec[cnt[dr[j] >> 16] + (dr[j] & 0xffffu)] = r[j];
 		__syncthreads();
 	}
 
 	// crowded local digits stay unresolved groups sharing hbig symbols: list the suffixes too short for that
-	uint32_t const hbig = (A.b1 + A.b2 + A.lb) >> 1;
+	uint32_t const hbig = (A.b1 + A.b2 + lb) >> 1;
 	if (A.lin) {
 		for (uint32_t s = threadIdx.x; s < m; s += MSD_THREADS) {
 			uint32_t const L = W32 - (uint32_t)rec[s];
@@ -561,7 +638,8 @@ k_msd_finish(MsdFin A) {
 		if (ORDER) { A.sa_out[o0 + f] = i; A.hflag[o0 + f] = (uint8_t)hf; }
 		if (FUSED) {
 			s_bwt[f] = (uint8_t)(me >> 62);
-			msd_emit_samples(A.fo, i, (uint32_t)(o0 + f + A.fo.shift));
+			uint32_t const r = (uint32_t)(o0 + f + A.fo.shift);
+			if ((i & A.imask) == 0 || (r & A.rmask) == 0) msd_emit_samples(A.fo, i, r);
 		}
 	}
 	if (FUSED) {

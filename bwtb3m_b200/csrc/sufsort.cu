@@ -269,14 +269,14 @@ static uint32_t fetch_u32(Stream & st, const uint32_t * d) {
 // ------------------------------------------------------------------------------------------
 struct MsdGeom { unsigned b1 = 0, b2 = 0; };
 
-// bits of the two global levels: sub-buckets of 2048..4095 suffixes on average
+// bits of the two global levels: sub-buckets of 3200..6400 suffixes on average (a finish CTA holds MSD_CAP = 8192
+// records including the padding of its runs)
 static bool msd_geometry(Stream const & st, DevText const & T, uint64_t W, MsdGeom & g) {
 	if (st.sortpath == B3M_SORT_LSD) return false;
 	if (T.keybits != 2 || !T.packed || W < 64 || W >= 0xFFFFFF00ull) return false;
 	if (st.sortpath != B3M_SORT_MSD && W < (1u << 16)) return false;
-	unsigned tb = 0;
-	while (tb < 21 && (W >> (tb + 12))) ++tb; // floor(log2(W / 2048))
-	if (tb < 4) tb = 4;
+	unsigned tb = 4;
+	while (tb < 21 && (W >> tb) > 6400) ++tb;
 	g.b1 = 2 * ((tb + 3) / 4);
 	if (g.b1 > 10) g.b1 = 10;
 	g.b2 = tb - g.b1;
@@ -285,11 +285,12 @@ static bool msd_geometry(Stream const & st, DevText const & T, uint64_t W, MsdGe
 	return true;
 }
 
+// sizes of the level-1 buckets of the whole text (the plan of a sharded build)
 static void msd_hist(Stream & st, TextView const & v, unsigned b1, std::vector<unsigned long long> & h) {
 	unsigned const nb = 1u << b1;
 	DevBuf<unsigned long long> gh(st, nb);
 	B3M_CUDA(cudaMemsetAsync(gh.get(), 0, gh.bytes(), st.s));
-	uint64_t const want = div_up(div_up(v.W, 32), 256);
+	uint64_t const want = div_up(div_up(v.W, MSD_ITEMS), 256);
 	unsigned const grid = (unsigned)(want < (uint64_t)st.sms * 8 ? (want ? want : 1) : (uint64_t)st.sms * 8);
 	B3M_LAUNCH_T(st, "msd_hist", v.W / 4, k_msd_hist, grid, 256, 0, v, b1, gh.get());
 	h.resize(nb);
@@ -297,57 +298,78 @@ static void msd_hist(Stream & st, TextView const & v, unsigned b1, std::vector<u
 	B3M_CUDA(cudaStreamSynchronize(st.s));
 }
 
+constexpr int MSD_FIN_SMEM = MSD_CAP * 9 + ((1 << MSD_LBITS_MAX) + 1) * 4;
+
 static void msd_configure() {
 	static bool done = false;
 	if (done) return;
 	B3M_CUDA(cudaFuncSetAttribute(k_msd_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, MSD_TILE * 8));
 	B3M_CUDA(cudaFuncSetAttribute(k_msd_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (MSD_TILE + 2) * 8));
-	B3M_CUDA(cudaFuncSetAttribute(k_msd_finish<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MSD_CAP * 9));
-	B3M_CUDA(cudaFuncSetAttribute(k_msd_finish<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MSD_CAP * 9));
+	B3M_CUDA(cudaFuncSetAttribute(k_msd_finish<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MSD_FIN_SMEM));
+	B3M_CUDA(cudaFuncSetAttribute(k_msd_finish<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MSD_FIN_SMEM));
 	done = true;
 }
 
-// Returns false when the path does not apply (a level-1 bin of 2^30 suffixes or more).  On return
-// `unresolved` counts the suffixes still tied; if that is not zero and sa_buf is given, sa_buf / hflag
-// hold the order reached and the head flags of its groups, which share at least `hstart` symbols.
+static uint32_t low_mask(unsigned log) { return log >= 32 ? 0xffffffffu : (1u << log) - 1u; }
+
+// Round 0 on the suffixes whose first b1 bits lie in [d_lo, d_hi).  Returns false when the path does not
+// apply (a level-1 bin of 2^30 suffixes or more).  On return `unresolved` counts the suffixes still tied;
+// if that is not zero and sa_buf is given, sa_buf / hflag hold the order reached and the head flags of its
+// groups, which share at least `hstart` symbols.
 static bool msd_round0(Stream & st, TextView const & v, int lin, MsdGeom const & g, uint32_t d_lo, uint32_t d_hi,
-                       std::vector<unsigned long long> const & hist, FusedOut const & fo, StreamOut * so,
-                       DevBuf<uint32_t> * sa_buf, DevBuf<uint8_t> * hflag, SortStats & S, uint64_t & unresolved, uint64_t & hstart) {
+                       FusedOut const & fo, StreamOut * so, DevBuf<uint32_t> * sa_buf, DevBuf<uint8_t> * hflag, SortStats & S,
+                       uint64_t & unresolved, uint64_t & hstart) {
 	unsigned const nb2 = 1u << g.b2, nkeep = d_hi - d_lo;
 	uint64_t const W = v.W;
+	unresolved = 0;
+	S.rounds = 1;
+	msd_configure();
+	double t_last = wall_ms();
+	// ---- counts per tile and bin, scanned down the columns ----
+	uint32_t const nt1 = (uint32_t)div_up(W, MSD_TILE), nch = (uint32_t)div_up(nt1, MSD_COLCHUNK);
+	DevBuf<uint32_t> toff(st, (uint64_t)nt1 * nkeep);
+	std::vector<unsigned long long> tot(nkeep);
+	{
+		DevBuf<uint16_t> tcount(st, (uint64_t)nt1 * nkeep);
+		DevBuf<uint32_t> partial(st, (uint64_t)nch * nkeep);
+		DevBuf<unsigned long long> dtot(st, nkeep);
+		B3M_LAUNCH_T(st, "msd_count", W / 4 + 2ull * nt1 * nkeep, k_msd_count, nt1, MSD_THREADS, 0, v, g.b1, d_lo, nkeep, tcount.get());
+		B3M_LAUNCH_T(st, "msd_colscan", 2ull * nt1 * nkeep, k_msd_colsum, nch, 256, 0, (const uint16_t *)tcount.get(), nt1, nkeep, partial.get());
+		B3M_LAUNCH(st, k_msd_colscan, (unsigned)div_up(nkeep, 256), 256, 0, partial.get(), nch, nkeep, dtot.get());
+		B3M_LAUNCH_T(st, "msd_colscan", 6ull * nt1 * nkeep, k_msd_colapply, nch, 256, 0, (const uint16_t *)tcount.get(), nt1, nkeep, (const uint32_t *)partial.get(), toff.get());
+		B3M_CUDA(cudaMemcpyAsync(tot.data(), dtot.get(), nkeep * 8, cudaMemcpyDeviceToHost, st.s));
+		B3M_CUDA(cudaStreamSynchronize(st.s));
+		S.other_bytes += W / 4 + 10ull * nt1 * nkeep;
+	}
+	TRACE("msd count");
 	std::vector<uint32_t> hb(2 * (nkeep + 1)); // first record | first level-2 tile of every kept bin
 	uint64_t m = 0, nt2 = 0;
 	for (unsigned b = 0; b < nkeep; ++b) {
-		unsigned long long const c = hist[d_lo + b];
+		unsigned long long const c = tot[b];
 		if (c >= (1ull << 30)) return false;
 		hb[b] = (uint32_t)m; hb[nkeep + 1 + b] = (uint32_t)nt2;
 		m += c; nt2 += div_up(c, MSD_TILE);
 	}
 	hb[nkeep] = (uint32_t)m; hb[2 * nkeep + 1] = (uint32_t)nt2;
-	unresolved = 0;
-	S.rounds = 1; S.active_sum += m;
+	S.active_sum += m;
 	if (m == 0) return true;
-	msd_configure();
-	double t_last = wall_ms();
 	DevBuf<uint32_t> dplan(st, hb.size());
 	B3M_CUDA(cudaMemcpyAsync(dplan.get(), hb.data(), hb.size() * 4, cudaMemcpyHostToDevice, st.s));
 	const uint32_t * d_base = dplan.get(), * d_tpre = dplan.get() + nkeep + 1;
 	DevBuf<unsigned long long> recs(st, m + 2);
 	{
 		// level 1
-		uint64_t const nt1 = div_up(W, MSD_TILE);
-		DevBuf<uint32_t> status(st, nt1 * nkeep + 1);
-		B3M_CUDA(cudaMemsetAsync(status.get(), 0, status.bytes(), st.s));
-		MsdP1 A{v, g.b1, d_lo, nkeep, d_base, status.get(), status.get() + nt1 * nkeep, recs.get()};
-		B3M_LAUNCH_T(st, "msd_scatter", W / 4 + 8 * m, k_msd_scatter, (unsigned)nt1, MSD_THREADS, MSD_TILE * 8, A);
-		S.radix_passes++; S.radix_bytes += W / 4 + 8 * m; S.other_bytes += W / 4;
+		MsdP1 A{v, g.b1, d_lo, nkeep, d_base, toff.get(), recs.get()};
+		B3M_LAUNCH_T(st, "msd_scatter", W / 4 + 4ull * nt1 * nkeep + 8 * m, k_msd_scatter, nt1, MSD_THREADS, MSD_TILE * 8, A);
+		S.radix_passes++; S.radix_bytes += W / 4 + 4ull * nt1 * nkeep + 8 * m;
 	}
+	toff.release();
 	TRACE("msd level 1");
 	DevBuf<uint16_t> table(st, nt2 * (nb2 + 1));
 	{
 		MsdP2 A{g.b2, nkeep, d_base, d_tpre, recs.get(), table.get()};
-		B3M_LAUNCH_T(st, "msd_local", 16 * m, k_msd_local, (unsigned)nt2, MSD_THREADS, (MSD_TILE + 2) * 8, A);
-		S.radix_passes++; S.radix_bytes += 16 * m;
+		B3M_LAUNCH_T(st, "msd_local", 16 * m + nt2 * (nb2 + 1) * 2ull, k_msd_local, (unsigned)nt2, MSD_THREADS, (MSD_TILE + 2) * 8, A);
+		S.radix_passes++; S.radix_bytes += 16 * m + nt2 * (nb2 + 1) * 2ull;
 	}
 	TRACE("msd level 2");
 	uint64_t const nsb = (uint64_t)nkeep * nb2;
@@ -356,13 +378,17 @@ static bool msd_round0(Stream & st, TextView const & v, int lin, MsdGeom const &
 	B3M_CUDA(cudaMemsetAsync(sub.get() + nsb, 0, 4, st.s));
 	B3M_LAUNCH_T(st, "msd_subtotals", nt2 * (nb2 + 1) * 2ull, k_msd_subtotals, nkeep, 256, 0, g.b2, d_tpre, (const uint16_t *)table.get(), sub.get(), scal.get());
 	scan_exclusive_inplace<OpSum>(st, sub.get(), nsb + 1);
-	S.other_bytes += nt2 * (nb2 + 1) * 4ull + nsb * 12;
-	unsigned const lb = MSD_LBITS;
-	unsigned glog = 2;
-	while (glog < 5 && (1u << glog) < ((unsigned)MSD_TILE >> g.b2)) ++glog;
+	S.other_bytes += nt2 * (nb2 + 1) * 2ull + nsb * 12;
+	// lanes per run of the gather: the 16-byte pieces of an average run
+	unsigned const pieces = (((unsigned)MSD_TILE >> g.b2) >> 1) + 1;
+	unsigned glog = 1;
+	while (glog < 5 && (1u << glog) < pieces) ++glog;
 	DevBuf<unsigned long long> counters(st, 4 * MSD_CSLOTS);
 	B3M_CUDA(cudaMemsetAsync(counters.get(), 0, 32 * MSD_CSLOTS, st.s));
-	MsdFin F{v, lin, g.b1, g.b2, lb, glog, nkeep, recs.get(), d_base, d_tpre, table.get(), sub.get(), 0u, nullptr, nullptr, fo, counters.get()};
+	uint32_t const imask = low_mask(std::min<unsigned>(fo.prelog, fo.isa_s ? fo.isalog : 32u));
+	uint32_t const rmask = fo.sa_s ? low_mask(fo.salog) : 0xffffffffu;
+	MsdFin F{v, lin, g.b1, g.b2, glog, nkeep, recs.get(), d_base, d_tpre, table.get(), sub.get(), 0u, nullptr, nullptr, fo, imask, rmask, counters.get()};
+	uint64_t const fbytes_per = 8 + 1; // record in, BWT code out (+ samples)
 	auto read_counters = [&](unsigned long long * hc) {
 		std::vector<unsigned long long> hcs(4 * MSD_CSLOTS);
 		B3M_CUDA(cudaMemcpyAsync(hcs.data(), counters.get(), 32 * MSD_CSLOTS, cudaMemcpyDeviceToHost, st.s));
@@ -371,8 +397,9 @@ static bool msd_round0(Stream & st, TextView const & v, int lin, MsdGeom const &
 		for (int q = 0; q < MSD_CSLOTS; ++q) { for (int c = 0; c < 3; ++c) hc[c] += hcs[4 * q + c]; hc[3] |= hcs[4 * q + 3]; }
 	};
 	// early delivery (StreamOut): rows below a finished range of sub-buckets are final
-	bool const stream_sa = so && so->host_sa && fo.sa_s && st.copy && nsb >= 64 && d_lo == 0 && nkeep == (1u << g.b1);
-	bool stream_bwa = so && so->host_bwa && so->d_bwa && fo.has_term && st.copy && nsb >= 64 && d_lo == 0 && nkeep == (1u << g.b1);
+	bool const whole = d_lo == 0 && nkeep == (1u << g.b1);
+	bool const stream_sa = so && so->host_sa && fo.sa_s && st.copy && nsb >= 64 && whole;
+	bool stream_bwa = so && so->host_bwa && so->d_bwa && fo.has_term && st.copy && nsb >= 64 && whole;
 	uint64_t primary = 0;
 	if (stream_bwa) {
 		// the row of the suffix at position 0 first: its sub-bucket is known from the first text word
@@ -381,7 +408,7 @@ static bool msd_round0(Stream & st, TextView const & v, int lin, MsdGeom const &
 		B3M_CUDA(cudaStreamSynchronize(st.s));
 		F.sb0 = (uint32_t)(w0 >> (64u - g.b1 - g.b2));
 		B3M_CUDA(cudaMemsetAsync(fo.special, 0xff, 8, st.s));
-		B3M_LAUNCH_T(st, "msd_finish", 0, (k_msd_finish<true, false>), 1, MSD_THREADS, MSD_CAP * 9, F);
+		B3M_LAUNCH_T(st, "msd_finish", 0, (k_msd_finish<true, false>), 1, MSD_THREADS, MSD_FIN_SMEM, F);
 		uint32_t const row0 = fetch_u32(st, fo.special + 1);
 		unsigned long long hc0[4];
 		read_counters(hc0);
@@ -402,7 +429,7 @@ static bool msd_round0(Stream & st, TextView const & v, int lin, MsdGeom const &
 		uint32_t const s_lo = (uint32_t)(nsb * c / nchunks), s_hi = (uint32_t)(nsb * (c + 1) / nchunks);
 		F.sb0 = s_lo;
 		uint64_t const cm = nchunks > 1 ? (c + 1 == nchunks ? m : rows[c + 1]) - rows[c] : m;
-		B3M_LAUNCH_T(st, "msd_finish", cm * 37ull / 4, (k_msd_finish<true, false>), s_hi - s_lo, MSD_THREADS, MSD_CAP * 9, F);
+		B3M_LAUNCH_T(st, "msd_finish", cm * fbytes_per + cm / 4, (k_msd_finish<true, false>), s_hi - s_lo, MSD_THREADS, MSD_FIN_SMEM, F);
 		if (stream_sa || stream_bwa) {
 			uint64_t const rows_lo = c ? rows[c] + fo.shift : 0, rows_hi = (c + 1 == nchunks) ? W + fo.shift : rows[c + 1] + fo.shift;
 			cudaEvent_t ev;
@@ -429,7 +456,7 @@ static bool msd_round0(Stream & st, TextView const & v, int lin, MsdGeom const &
 	unsigned long long hc[4];
 	read_counters(hc);
 	TRACE("msd finish");
-	S.other_bytes += m * 37ull / 4 + 32ull * hc[2];
+	S.other_bytes += m * fbytes_per + m / 4 + 32ull * hc[2];
 	S.tied0 = hc[1]; S.unresolved0 = hc[0];
 	unresolved = hc[0];
 	if (stream_sa) so->delivered = hc[0] == 0;
@@ -440,11 +467,13 @@ static bool msd_round0(Stream & st, TextView const & v, int lin, MsdGeom const &
 		hflag->alloc(st, m);
 		B3M_CUDA(cudaMemsetAsync(counters.get(), 0, 32 * MSD_CSLOTS, st.s));
 		F.sb0 = 0; F.sa_out = sa_buf->get(); F.hflag = hflag->get(); F.fo = FusedOut();
-		B3M_LAUNCH_T(st, "msd_finish<order>", m * 13ull, (k_msd_finish<false, true>), (unsigned)nsb, MSD_THREADS, MSD_CAP * 9, F);
+		B3M_LAUNCH_T(st, "msd_finish<order>", m * 13ull, (k_msd_finish<false, true>), (unsigned)nsb, MSD_THREADS, MSD_FIN_SMEM, F);
 		read_counters(hc);
 		S.other_bytes += m * 13ull + 32ull * hc[2];
+		// what every group left shares: a sub-bucket too large for a CTA b1+b2 bits, a crowded local digit at least
+		// MSD_LBITS_MIN more, records equal in all they carry and in the 32 symbols behind that
 		unsigned const skip = (g.b1 + 30u) / 2;
-		hstart = (hc[3] & 2) ? (g.b1 + g.b2) / 2 : ((hc[3] & 1) ? (g.b1 + g.b2 + lb) / 2 : skip + 32u);
+		hstart = (hc[3] & 2) ? (g.b1 + g.b2) / 2 : ((hc[3] & 1) ? (g.b1 + g.b2 + MSD_LBITS_MIN) / 2 : skip + 32u);
 		if (hstart < 1) hstart = 1;
 		TRACE("msd finish<order>");
 	}
@@ -642,8 +671,7 @@ uint64_t k2_sort_keyrange(Stream & st, DevText const & T, int circular, KeyRange
 		FusedOut fo = fo0;
 		fo.shift = fo0.shift + plan.base[part];
 		uint64_t unresolved = 0, hstart = 0;
-		St.other_bytes += W / 4;
-		if (msd_round0(st, v, !circular, mg, blo, bhi, plan.hist, fo, nullptr, nullptr, nullptr, St, unresolved, hstart)) {
+		if (msd_round0(st, v, !circular, mg, blo, bhi, fo, nullptr, nullptr, nullptr, St, unresolved, hstart)) {
 			if (stats) {
 				stats->rounds = stats->rounds > St.rounds ? stats->rounds : St.rounds;
 				stats->radix_passes += St.radix_passes; stats->radix_bytes += St.radix_bytes;
@@ -718,10 +746,7 @@ void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W,
 	MsdGeom mg;
 	if (fo && msd_geometry(st, T, W, mg)) {
 		// ---------------- round 0, MSD path (msd.cuh) ----------------
-		std::vector<unsigned long long> h;
-		msd_hist(st, v, mg.b1, h);
-		S.other_bytes += W / 4;
-		round0_done = msd_round0(st, v, lin, mg, 0u, 1u << mg.b1, h, *fo, so, &sa_buf, &hflag, S, unresolved, hstart);
+		round0_done = msd_round0(st, v, lin, mg, 0u, 1u << mg.b1, *fo, so, &sa_buf, &hflag, S, unresolved, hstart);
 	}
 	if (!round0_done) {
 		// ---------------- round 0, LSD path ----------------
