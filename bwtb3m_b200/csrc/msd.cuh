@@ -79,14 +79,20 @@ __device__ __forceinline__ uint32_t msd_scan_bins(uint32_t * cnt, unsigned nb, u
 	return total;
 }
 
-// the same for any number of bins, keeping nothing in registers: every thread scans nb / THREADS consecutive bins
+// the same for 2^k bins, keeping nothing in registers: every thread scans nb / THREADS consecutive bins (four at a
+// time with 128-bit accesses when it has that many; cnt is 16-byte aligned)
 template <int THREADS>
 __device__ __forceinline__ void msd_scan_bins_wide(uint32_t * cnt, unsigned nb, uint32_t * wsum) {
 	unsigned const lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 	unsigned const per = (nb + THREADS - 1) / THREADS, b0 = threadIdx.x * per;
 	unsigned const b1 = b0 + per < nb ? b0 + per : nb;
 	uint32_t s = 0;
-	for (unsigned b = b0; b < b1; ++b) s += cnt[b];
+	if ((per & 3u) == 0) {
+		const uint4 * c4 = reinterpret_cast<const uint4 *>(cnt + b0);
+		#pragma unroll 4
+		for (unsigned q = 0; q < per / 4; ++q) { uint4 const x = c4[q]; s += x.x + x.y + x.z + x.w; }
+	} else
+		for (unsigned b = b0; b < b1; ++b) s += cnt[b];
 	uint32_t incl = s;
 	#pragma unroll
 	for (int o = 1; o < 32; o <<= 1) { uint32_t const t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += t; }
@@ -100,7 +106,17 @@ __device__ __forceinline__ void msd_scan_bins_wide(uint32_t * cnt, unsigned nb, 
 	}
 	__syncthreads();
 	uint32_t run = (w ? wsum[w - 1] : 0u) + incl - s;
-	for (unsigned b = b0; b < b1; ++b) { uint32_t const c = cnt[b]; cnt[b] = run; run += c; }
+	if ((per & 3u) == 0) {
+		uint4 * c4 = reinterpret_cast<uint4 *>(cnt + b0);
+		#pragma unroll 4
+		for (unsigned q = 0; q < per / 4; ++q) {
+			uint4 const x = c4[q];
+			uint4 y;
+			y.x = run; y.y = y.x + x.x; y.z = y.y + x.y; y.w = y.z + x.z; run = y.w + x.w;
+			c4[q] = y;
+		}
+	} else
+		for (unsigned b = b0; b < b1; ++b) { uint32_t const c = cnt[b]; cnt[b] = run; run += c; }
 	__syncthreads();
 }
 
@@ -397,12 +413,13 @@ __device__ __forceinline__ void msd_second_key(TextView const & v, unsigned skip
 	rem = (uint32_t)((lin && left < skip + 32u) ? left : skip + 32u);
 }
 
-// everything fo_emit (sufsort.cu) writes except the BWT code
+// everything fo_emit (sufsort.cu) writes except the BWT code (SA: the sampled SA as well)
+template <bool SA>
 __device__ __forceinline__ void msd_emit_samples(FusedOut const & fo, uint32_t i, uint32_t r) {
 	if (i == 0) { if (fo.has_term) fo.special[0] = r; fo.special[1] = r; }
 	if (fo.prelog >= 32 ? i == 0 : (i & ((1u << fo.prelog) - 1u)) == 0) fo.prerank[fo.prelog >= 32 ? 0 : (i >> fo.prelog)] = r;
 	if (fo.isa_s && (fo.isalog >= 32 ? i == 0 : (i & ((1u << fo.isalog) - 1u)) == 0)) fo.isa_s[fo.isalog >= 32 ? 0 : (i >> fo.isalog)] = r;
-	if (fo.sa_s && (fo.salog >= 32 ? r == 0 : (r & ((1u << fo.salog) - 1u)) == 0)) fo.sa_s[fo.salog >= 32 ? 0 : (r >> fo.salog)] = i;
+	if (SA && fo.sa_s && (fo.salog >= 32 ? r == 0 : (r & ((1u << fo.salog) - 1u)) == 0)) fo.sa_s[fo.salog >= 32 ? 0 : (r >> fo.salog)] = i;
 }
 
 // one chunk of MSD_THREADS tiles of the parent bucket: thread <-> tile k0 + threadIdx.x; returns this
@@ -509,8 +526,8 @@ k_msd_finish(MsdFin A) {
 	unsigned const gsz = 1u << A.glog, gl = threadIdx.x & (gsz - 1u), grp = threadIdx.x >> A.glog, ngrp = MSD_THREADS >> A.glog;
 	uint32_t const rec_s = (uint32_t)__cvta_generic_to_shared(rec);
 	uint32_t mpad = 0; // records in rec[], padding included
+	uint32_t g0 = 0, g1 = 0, a0, plen = 0, off = 0;
 	for (uint32_t k0 = 0; k0 < ntp; k0 += MSD_THREADS) {
-		uint32_t g0, g1, a0, plen, off;
 		msd_run_place(row0, row1, pstart, ntp, k0, wsum, mpad, g0, g1, a0, plen, off);
 		r_src[threadIdx.x] = a0;
 		r_off[threadIdx.x] = (uint16_t)off;
@@ -527,11 +544,15 @@ k_msd_finish(MsdFin A) {
 	}
 	asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 	__syncthreads();
-	{
-		// the records dragged in from neighbouring runs: one more walk over the descriptors
+	// the records dragged in from neighbouring runs become padding (several chunks of tiles: one more walk over the descriptors)
+	if (ntp <= (uint32_t)MSD_THREADS) {
+		if (plen) {
+			if (g0 & 1u) rec[off] = MSD_PAD;
+			if (g1 & 1u) rec[off + plen - 1] = MSD_PAD;
+		}
+	} else {
 		uint32_t done = 0;
 		for (uint32_t k0 = 0; k0 < ntp; k0 += MSD_THREADS) {
-			uint32_t g0, g1, a0, plen, off;
 			msd_run_place(row0, row1, pstart, ntp, k0, wsum, done, g0, g1, a0, plen, off);
 			if (plen) {
 				if (g0 & 1u) rec[off] = MSD_PAD;
@@ -540,8 +561,8 @@ k_msd_finish(MsdFin A) {
 		}
 	}
 	// local digit: about two bins per record
-	unsigned lb = MSD_LBITS_MIN;
-	while (lb < (unsigned)MSD_LBITS_MAX && (1u << lb) < 2u * m) ++lb;
+	unsigned lb = 32u - (unsigned)__clz((int)(2u * m - 1u)); // ceil(log2(2m))
+	lb = lb < (unsigned)MSD_LBITS_MIN ? (unsigned)MSD_LBITS_MIN : (lb > (unsigned)MSD_LBITS_MAX ? (unsigned)MSD_LBITS_MAX : lb);
 	unsigned const nlb = 1u << lb;
 	for (unsigned i = threadIdx.x; i <= nlb; i += MSD_THREADS) cnt[i] = 0;
 	__syncthreads();
@@ -551,6 +572,8 @@ k_msd_finish(MsdFin A) {
 	{
 		unsigned long long r[MSD_ITEMS];
 		uint32_t dr[MSD_ITEMS];
+		uint32_t const shortlim = A.lin ? W32 - 18u : 0xffffffffu; // suffixes behind this position may be too short for a group
+		bool anyshort = false;
 		#pragma unroll
 		for (int j = 0; j < MSD_ITEMS; ++j) {
 			dr[j] = 0xffffffffu;
@@ -561,10 +584,12 @@ k_msd_finish(MsdFin A) {
 					if (r[j] != MSD_PAD) {
 						uint32_t const dg = (uint32_t)(r[j] >> lsh) & (nlb - 1u);
 						dr[j] = (dg << 16) | atomicAdd(&cnt[dg], 1u);
+						anyshort |= (uint32_t)r[j] > shortlim;
 					}
 				}
 			}
 		}
+		if (anyshort) s_nshort = 0x80000000u; // the list is made below
 		__syncthreads();
 		msd_scan_bins_wide<MSD_THREADS>(cnt, nlb, wsum);
 		if (threadIdx.x == 0) cnt[nlb] = m;
@@ -575,8 +600,11 @@ k_msd_finish(MsdFin A) {
 	}
 
 	// crowded local digits stay unresolved groups sharing hbig symbols: list the suffixes too short for that
-	uint32_t const hbig = (A.b1 + A.b2 + lb) >> 1;
-	if (A.lin) {
+	uint32_t const hbig = (A.b1 + A.b2 + lb) >> 1; // at most 16
+	if (s_nshort) { // uniform; only the CTAs whose sub-bucket holds one of the last 16 suffixes of a linear window
+		__syncthreads();
+		if (threadIdx.x == 0) s_nshort = 0;
+		__syncthreads();
 		for (uint32_t s = threadIdx.x; s < m; s += MSD_THREADS) {
 			uint32_t const L = W32 - (uint32_t)rec[s];
 			if (L < hbig) { uint32_t const q = atomicAdd(&s_nshort, 1u); s_sh_e[q] = s; s_sh_L[q] = L; }
@@ -584,6 +612,10 @@ k_msd_finish(MsdFin A) {
 		__syncthreads();
 	}
 	// ---- order inside a local digit by comparison; emit ----
+	// sampled SA through shared memory when a CTA holds at most 512 samples (the gather's descriptors are dead by now)
+	bool const stage_sa = FUSED && A.fo.sa_s && A.fo.salog >= 5 && A.fo.salog < 32;
+	uint32_t * const s_sa = r_src;
+	uint32_t const r_first = stage_sa ? ((o0 + (uint32_t)A.fo.shift + A.rmask) & ~A.rmask) : 0u; // first sampled rank of this CTA
 	unsigned const skip = (A.b1 + 30u) >> 1; // symbols covered by b1 + key30
 	uint32_t ntied = 0, nunres = 0, ngather = 0, flags = 0;
 	#pragma unroll 1
@@ -604,12 +636,18 @@ k_msd_finish(MsdFin A) {
 			if (A.lin && myL < hbig) { f = a + smaller; hf = 1; }
 			else { f = s + nsb - before; hf = (s - a == before) ? 1u : 0u; ++nunres; flags |= 1u; }
 		} else if (b - a > 1) {
+			// the key halves of the records of this digit, four loads in flight (most digits hold at most four records)
 			uint32_t less = 0, eq = 0;
+			const uint32_t * const kh = reinterpret_cast<const uint32_t *>(rec) + 2 * a + 1;
+			uint32_t const nb = b - a;
 			#pragma unroll 1
-			for (uint32_t y = a; y < b; ++y) {
-				uint32_t const ok = (uint32_t)(rec[y] >> 32) & MSD_KEYMASK;
-				less += ok < mk ? 1u : 0u;
-				eq += ok == mk ? 1u : 0u;
+			for (uint32_t y = 0; y < nb; y += 4) {
+				uint32_t const k0 = kh[2 * y] & MSD_KEYMASK;
+				uint32_t const k1 = y + 1 < nb ? kh[2 * y + 2] & MSD_KEYMASK : 0xffffffffu;
+				uint32_t const k2 = y + 2 < nb ? kh[2 * y + 4] & MSD_KEYMASK : 0xffffffffu;
+				uint32_t const k3 = y + 3 < nb ? kh[2 * y + 6] & MSD_KEYMASK : 0xffffffffu;
+				less += (k0 < mk ? 1u : 0u) + (k1 < mk ? 1u : 0u) + (k2 < mk ? 1u : 0u) + (k3 < mk ? 1u : 0u);
+				eq += (k0 == mk ? 1u : 0u) + (k1 == mk ? 1u : 0u) + (k2 == mk ? 1u : 0u) + (k3 == mk ? 1u : 0u);
 			}
 			f = a + less;
 			if (eq > 1) {
@@ -639,11 +677,20 @@ k_msd_finish(MsdFin A) {
 		if (FUSED) {
 			s_bwt[f] = (uint8_t)(me >> 62);
 			uint32_t const r = (uint32_t)(o0 + f + A.fo.shift);
-			if ((i & A.imask) == 0 || (r & A.rmask) == 0) msd_emit_samples(A.fo, i, r);
+			if (stage_sa) {
+				// sampled SA: the position goes to shared memory and leaves with a coalesced store below
+				if ((r & A.rmask) == 0) s_sa[(r - r_first) >> A.fo.salog] = i;
+				if ((i & A.imask) == 0) msd_emit_samples<false>(A.fo, i, r);
+			} else if ((i & A.imask) == 0 || (r & A.rmask) == 0) msd_emit_samples<true>(A.fo, i, r);
 		}
 	}
 	if (FUSED) {
 		__syncthreads();
+		if (stage_sa) {
+			uint32_t const r_end = o0 + m + (uint32_t)A.fo.shift;
+			uint32_t const ns = r_first < r_end ? ((r_end - 1u - r_first) >> A.fo.salog) + 1u : 0u;
+			for (uint32_t x = threadIdx.x; x < ns; x += MSD_THREADS) A.fo.sa_s[(r_first >> A.fo.salog) + x] = s_sa[x];
+		}
 		uint8_t * const out = A.fo.bwt + A.fo.shift + o0;
 		// head bytes up to a 4-byte boundary, words, tail bytes
 		uint32_t const mis = (uint32_t)((4u - ((uintptr_t)out & 3u)) & 3u);
