@@ -162,11 +162,18 @@ def run_reference(args):
         tot += dt
         syms += sample
     v = syms / tot / 1e6
+    cfg = config_dict(args, sample, itype)
+    if sample < nsym:
+        # the CPU arm cannot run the full workload inside the bench's time budget: its line names what it processed
+        cfg["workload"] = "first %d symbols of %s" % (sample, cfg["workload"])
+        cfg["full_workload_n_symbols"] = int(nsym)
+        cfg["note"] = ("bounded sample: the restated reference's throughput FALLS with n (see cpu_baseline.curve of the GPU arm), "
+                       "so a ratio against the full-size GPU line understates the CPU time of the full workload")
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": config_dict(args, nsym, itype),
+        "config": cfg,
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": "first %d symbols of the workload per step, %d blocks; restated reference (libmaus2 unavailable)" % (sample, nblocks)},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -304,6 +311,24 @@ def run_ours(args):
         lf_ms = None
         if rank == 0:
             lf_ms, _ = eng.lf_bench(1 << 20, 256)
+    # ---- N > 1: what was timed equals a single-GPU build of the same input, bit for bit ----
+    parity = None
+    if world > 1:
+        with torch.cuda.stream(stream):
+            step_device()
+            sync_all()
+            if rank == 0:
+                multi = eng.fetch()
+                ref = Engine(local)
+                ref.load_device(dev_in.data_ptr(), dev_in.numel(), itype)
+                ref.build(numblocks=1, preisarate=info["preisarate"], **params)
+                one = ref.fetch()
+                ref.close()
+                parity = {"against": "single-GPU build on rank 0, same input", "strategy": state["strategy"]}
+                for k in sorted(one):
+                    parity[k] = bool(np.array_equal(multi[k], one[k]))
+                parity["ok"] = all(v for k, v in parity.items() if k not in ("against", "strategy"))
+                del multi, one
     if world > 1:
         dist.barrier()
     if rank != 0:
@@ -341,6 +366,15 @@ def run_ours(args):
         cpu = {"value": sample / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port", "seconds": dt,
                "sample": "first %d symbols of the workload, %d blocks, full pipeline; restated reference (libmaus2 unavailable)" % (sample, nblocks),
                "lf_steps_per_s": cpu_lf, "lf_instrument": "bwttestdecodespeed restated: 8 interleaved chains, 1 thread, BWT of the sample"}
+        # throughput against n: the direction of the bias of every bounded CPU sample is on record
+        curve = [{"n_symbols": int(sample), "value": sample / dt / 1e6, "seconds": dt}]
+        for tok in [x for x in args.cpu_curve.split(",") if x.strip()]:
+            k = min(nsym, int(tok))
+            if any(c["n_symbols"] == k for c in curve):
+                continue
+            dtk, _, _ = cpu_oracle_run(itype, data, k, params, threads)
+            curve.append({"n_symbols": int(k), "value": k / dtk / 1e6, "seconds": dtk})
+        cpu["curve"] = sorted(curve, key=lambda c: c["n_symbols"])
 
     total_s = total_ms * 1e-3
     line = {
@@ -349,7 +383,7 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": config_dict(args, nsym, itype, {"numblocks": info["numblocks"], "preisarate": info["preisarate"],
                                                   "parallelism": ("single GPU" if world == 1 else
-                                                                  "text replicated, %d suffix key ranges, slices sum-reduced to rank 0 over NCCL" % world if state["strategy"] == "shard" else
+                                                                  "text replicated, %d suffix key ranges, every rank stores its BWT rows / samples into rank 0's HBM over NVLink (CUDA IPC peer stores from the sorting kernels), one all-reduce (NCCL) as vote and fence" % world if state["strategy"] == "shard" else
                                                                   "text replicated, %d block ranges, merge tree over NCCL" % world)}),
         "clocks": sampler.summary(),
         "e2e": {"value": nsym * e2e_steps / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -364,6 +398,8 @@ def run_ours(args):
         "kernels_ms_per_step": {k: round(v["ms"] / nprof, 4) for k, v in kt.items()},
         "lf_steps_per_s": (1 << 20) * 256 / (lf_ms * 1e-3),
     }
+    if parity is not None:
+        line["parity_check"] = parity
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -380,8 +416,9 @@ def main():
     ap.add_argument("--numblocks", type=int, default=1)
     ap.add_argument("--strategy", default="auto", choices=["auto", "shard", "merge"], help="multi-GPU decomposition (bwtb3m_b200.multigpu)")
     ap.add_argument("--cpu-sample", type=int, default=256_000_000, help="symbols of the workload the cpu_baseline leg processes")
-    ap.add_argument("--ref-sample", type=int, default=32_000_000, help="symbols per step of --impl reference")
+    ap.add_argument("--ref-sample", type=int, default=128_000_000, help="symbols per step of --impl reference (about 7 s of CPU work per step)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-curve", default="32000000,1000000000", help="further prefix sizes the cpu_baseline leg times (throughput against n); empty: none")
     ap.add_argument("--e2e-steps", type=int, default=5, help="steps of the end-to-end (host buffers) leg")
     args = ap.parse_args()
     if args.impl == "reference":

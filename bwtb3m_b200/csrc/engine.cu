@@ -354,10 +354,14 @@ void Engine::kr_build_part(uint32_t part, uint32_t nparts, b3m_build_params cons
 	*unresolved = k2_sort_keyrange(st, T, circular, kr_plan, part, fo, &sortstats);
 	if (part == 0 && T.has_term) {
 		// rank 0 is the terminator suffix (text position ntext): its predecessor is the last base; its
-		// anchor / ISA entries are rank 0 = the buffers' initial value
+		// anchor / ISA entries are rank 0 (written explicitly: the buffers may be another GPU's, not zeroed)
 		B3M_CUDA(cudaMemcpyAsync(d_bwt, T.codes + T.ntext - 1, 1, cudaMemcpyDeviceToDevice, st.s));
 		uint64_t const pos = T.ntext;
-		if (!p.bwtonly) B3M_CUDA(cudaMemcpyAsync(d_sa, &pos, 8, cudaMemcpyHostToDevice, st.s));
+		if ((T.ntext & (prerate - 1)) == 0) B3M_CUDA(cudaMemsetAsync((uint32_t *)d_prerank + T.ntext / prerate, 0, 4, st.s));
+		if (!p.bwtonly) {
+			B3M_CUDA(cudaMemcpyAsync(d_sa, &pos, 8, cudaMemcpyHostToDevice, st.s));
+			if ((T.ntext & (p.isasamplingrate - 1)) == 0) B3M_CUDA(cudaMemsetAsync((uint64_t *)d_isa + T.ntext / p.isasamplingrate, 0, 8, st.s));
+		}
 	}
 	pt.mark();
 	B3M_CUDA(cudaStreamSynchronize(st.s));
@@ -376,17 +380,27 @@ void Engine::kr_rows(uint32_t nparts, uint64_t * first) {
 	first[0] = 0; first[nparts] = T.n;
 }
 
-void Engine::kr_finish(const void * d_bwt, const void * d_prerank, const void * d_sa, const void * d_isa, const void * d_special, uint32_t nparts) {
+// adopt: the engine refers to the caller's buffers instead of copying them (they must stay valid until the
+// next load / build; the arena ignores pointers it does not own when the results are released)
+void Engine::kr_finish(const void * d_bwt, const void * d_prerank, const void * d_sa, const void * d_isa, const void * d_special, uint32_t nparts, bool adopt) {
 	B3M_CUDA(cudaSetDevice(device));
 	B3M_REQUIRE(loaded && npre, "kr_build_part was not called");
 	PhaseTimer pt(st);
 	pt.mark();
+	if (adopt) {
+		bwt.release(); prerank.release(); sa.release(); isa.release();
+		bwt.p = (uint8_t *)const_cast<void *>(d_bwt); bwt.n = T.n + 16; bwt.a = &arena;
+		prerank.p = (uint32_t *)const_cast<void *>(d_prerank); prerank.n = npre; prerank.a = &arena;
+		if (nsa) { sa.p = (uint64_t *)const_cast<void *>(d_sa); sa.n = nsa; sa.a = &arena; }
+		if (nisa) { isa.p = (uint64_t *)const_cast<void *>(d_isa); isa.n = nisa; isa.a = &arena; }
+	} else {
 	bwt.alloc(st, T.n + 16);
 	B3M_CUDA(cudaMemcpyAsync(bwt.get(), d_bwt, T.n, cudaMemcpyDeviceToDevice, st.s));
 	prerank.alloc(st, npre);
 	B3M_CUDA(cudaMemcpyAsync(prerank.get(), d_prerank, 4 * npre, cudaMemcpyDeviceToDevice, st.s));
 	if (nsa) { sa.alloc(st, nsa); B3M_CUDA(cudaMemcpyAsync(sa.get(), d_sa, 8 * nsa, cudaMemcpyDeviceToDevice, st.s)); }
 	if (nisa) { isa.alloc(st, nisa); B3M_CUDA(cudaMemcpyAsync(isa.get(), d_isa, 8 * nisa, cudaMemcpyDeviceToDevice, st.s)); }
+	}
 	uint32_t exc_pos = 0xffffffffu;
 	if (T.has_term) {
 		B3M_CUDA(cudaMemcpyAsync(pinned, d_special, 16, cudaMemcpyDeviceToHost, st.s));
@@ -775,7 +789,11 @@ int b3m_engine_shard_rows(b3m_engine * h, uint32_t nparts, uint64_t * first_row)
 }
 int b3m_engine_shard_finish(b3m_engine * h, const void * d_bwt, const void * d_prerank, const void * d_sa, const void * d_isa, const void * d_special,
                             uint32_t nparts) {
-	B3M_GUARD(h, h->e->kr_finish(d_bwt, d_prerank, d_sa, d_isa, d_special, nparts));
+	B3M_GUARD(h, h->e->kr_finish(d_bwt, d_prerank, d_sa, d_isa, d_special, nparts, false));
+}
+int b3m_engine_shard_adopt(b3m_engine * h, const void * d_bwt, const void * d_prerank, const void * d_sa, const void * d_isa, const void * d_special,
+                           uint32_t nparts) {
+	B3M_GUARD(h, h->e->kr_finish(d_bwt, d_prerank, d_sa, d_isa, d_special, nparts, true));
 }
 int b3m_engine_fetch_bwa(b3m_engine * h, uint32_t * bwt_words, uint64_t cap_words, uint64_t * primary, uint64_t * L2, uint64_t * seq_len) {
 	B3M_GUARD(h, h->e->fetch_bwa(bwt_words, cap_words, primary, L2, seq_len));
@@ -810,6 +828,45 @@ int b3m_engine_kernel_times(b3m_engine * h, char * buf, size_t buflen) {
 		if (buf && buflen) { strncpy(buf, out.c_str(), buflen - 1); buf[buflen - 1] = 0; }
 	});
 }
+// ---- device buffers shared between the processes of a multi-GPU build (CUDA IPC) ----
+#define B3M_PLAIN(...)                                                                  \
+	try { __VA_ARGS__; return 0; }                                                      \
+	catch (std::exception const & ex) { set_err(err, errlen, ex.what()); return 2; }    \
+	catch (...) { set_err(err, errlen, "unknown error"); return 3; }
+
+int b3m_dev_alloc(int device, uint64_t bytes, void ** dptr, char * err, size_t errlen) {
+	B3M_PLAIN({
+		if (!dptr) throw b3m::Error("null argument");
+		B3M_CUDA(cudaSetDevice(device));
+		B3M_CUDA(cudaMalloc(dptr, bytes ? bytes : 1));
+	});
+}
+int b3m_dev_free(int device, void * dptr, char * err, size_t errlen) {
+	B3M_PLAIN({ B3M_CUDA(cudaSetDevice(device)); B3M_CUDA(cudaFree(dptr)); });
+}
+int b3m_ipc_export(int device, const void * dptr, void * handle64, char * err, size_t errlen) {
+	B3M_PLAIN({
+		static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+		if (!dptr || !handle64) throw b3m::Error("null argument");
+		B3M_CUDA(cudaSetDevice(device));
+		cudaIpcMemHandle_t hd;
+		B3M_CUDA(cudaIpcGetMemHandle(&hd, const_cast<void *>(dptr)));
+		memcpy(handle64, &hd, 64);
+	});
+}
+int b3m_ipc_open(int device, const void * handle64, void ** dptr, char * err, size_t errlen) {
+	B3M_PLAIN({
+		if (!dptr || !handle64) throw b3m::Error("null argument");
+		B3M_CUDA(cudaSetDevice(device));
+		cudaIpcMemHandle_t hd;
+		memcpy(&hd, handle64, 64);
+		B3M_CUDA(cudaIpcOpenMemHandle(dptr, hd, cudaIpcMemLazyEnablePeerAccess));
+	});
+}
+int b3m_ipc_close(int device, void * dptr, char * err, size_t errlen) {
+	B3M_PLAIN({ B3M_CUDA(cudaSetDevice(device)); B3M_CUDA(cudaIpcCloseMemHandle(dptr)); });
+}
+
 int b3m_engine_sync(b3m_engine * h) {
 	B3M_GUARD(h, { B3M_CUDA(cudaSetDevice(h->e->device)); B3M_CUDA(cudaStreamSynchronize(h->e->st.s)); });
 }

@@ -116,7 +116,7 @@ struct Engine {
 	                   void * d_special, uint64_t * unresolved);
 	void kr_rows(uint32_t nparts, uint64_t * first);
 	void pack_rows(const void * d_rows, uint64_t nrows, void * d_packed, bool unpack);
-	void kr_finish(const void * d_bwt, const void * d_prerank, const void * d_sa, const void * d_isa, const void * d_special, uint32_t nparts);
+	void kr_finish(const void * d_bwt, const void * d_prerank, const void * d_sa, const void * d_isa, const void * d_special, uint32_t nparts, bool adopt);
 	// K8 / output side
 	uint64_t rl_bytes = 0, rl_nruns = 0;
 	void symbols_device(DevBuf<uint8_t> & out);

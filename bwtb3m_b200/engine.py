@@ -29,6 +29,7 @@ class Engine:
         if rc != 0:
             raise B3MError(err.value.decode() or "b3m_engine_create failed (%d)" % rc)
         self._h = h
+        self.device = device
         self.stream_ptr = stream or 0
 
     def close(self):
@@ -138,6 +139,11 @@ class Engine:
         vp = lambda a: C.c_void_p(a) if a else None
         self._check(self._lib.b3m_engine_shard_finish(self._h, vp(bwt_ptr), vp(prerank_ptr), vp(sa_ptr), vp(isa_ptr), vp(special_ptr), nparts))
 
+    def shard_adopt(self, nparts, bwt_ptr, prerank_ptr, sa_ptr, isa_ptr, special_ptr):
+        """shard_finish without the copies: the engine refers to the caller's buffers."""
+        vp = lambda a: C.c_void_p(a) if a else None
+        self._check(self._lib.b3m_engine_shard_adopt(self._h, vp(bwt_ptr), vp(prerank_ptr), vp(sa_ptr), vp(isa_ptr), vp(special_ptr), nparts))
+
     def fetch_bwa(self, out=None, out_ptr=0):
         """BWA's packed BWT of the last pacterm build: (words uint32, primary, L2[5], seq_len).
         `out` (numpy uint32) or `out_ptr` (address of a buffer of enough words) may receive the words."""
@@ -191,3 +197,38 @@ class Engine:
 
     def sync(self):
         self._check(self._lib.b3m_engine_sync(self._h))
+
+
+class DeviceMemory:
+    """cudaMalloc'ed device memory and its CUDA IPC handle (b3m_dev_alloc / b3m_ipc_*): result buffers that the
+    other processes of a multi-GPU build write directly."""
+
+    def __init__(self, device):
+        self._lib = lib()
+        self.device = device
+
+    def _call(self, fn, *args):
+        err = C.create_string_buffer(512)
+        if fn(*args, err, 512) != 0:
+            raise B3MError(err.value.decode())
+
+    def alloc(self, nbytes):
+        p = C.c_void_p()
+        self._call(self._lib.b3m_dev_alloc, self.device, nbytes, C.byref(p))
+        return p.value
+
+    def free(self, ptr):
+        self._call(self._lib.b3m_dev_free, self.device, C.c_void_p(ptr))
+
+    def export(self, ptr):
+        h = C.create_string_buffer(64)
+        self._call(self._lib.b3m_ipc_export, self.device, C.c_void_p(ptr), h)
+        return h.raw
+
+    def open(self, handle):
+        p = C.c_void_p()
+        self._call(self._lib.b3m_ipc_open, self.device, C.c_char_p(handle), C.byref(p))
+        return p.value
+
+    def close(self, ptr):
+        self._call(self._lib.b3m_ipc_close, self.device, C.c_void_p(ptr))

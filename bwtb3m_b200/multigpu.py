@@ -341,6 +341,66 @@ def build_sharded(engine, preisarate=0, sasamplingrate=32, isasamplingrate=26214
     return True, buf
 
 
+class DirectResults:
+    """Result buffers of a sharded build that every rank writes directly: rank 0 owns them (b3m_dev_alloc),
+    the other ranks map them through CUDA IPC, and the kernels of b3m_engine_shard_build store their BWT rows,
+    anchors and samples into rank 0's HBM over NVLink.  No gather, no reduction: every entry is written by
+    exactly one rank.  `mem` is a DeviceMemory-like object (alloc / export / open); the CPU tests plug in a
+    shared-memory model of it."""
+
+    def __init__(self, engine, preisarate, sasamplingrate, isasamplingrate, bwtonly, rank, world, mem=None):
+        from .engine import DeviceMemory
+        n = engine.info()["n"]
+        self.n, self.rank, self.world = n, rank, world
+        self.key = (n, sasamplingrate, isasamplingrate, bool(bwtonly))
+        self.prerate = preisarate or engine.default_preisarate(bwtonly)
+        self.mem = mem or DeviceMemory(engine.device)
+        sizes = [("bwt", n + 16), ("prerank", 4 * ((n + self.prerate - 1) // self.prerate))]
+        if not bwtonly:
+            sizes += [("sa", 8 * ((n + sasamplingrate - 1) // sasamplingrate)), ("isa", 8 * ((n + isasamplingrate - 1) // isasamplingrate))]
+        sizes.append(("special", 16))
+        self.sizes = dict(sizes)
+        self.p = {}
+        handles = None
+        if rank == 0:
+            self.p = {k: self.mem.alloc(sz) for k, sz in sizes}
+            handles = {k: self.mem.export(v) for k, v in self.p.items()}
+        if world > 1:
+            box = [handles]
+            dist.broadcast_object_list(box, src=0)
+            if rank != 0:
+                self.p = {k: self.mem.open(h) for k, h in box[0].items()}
+
+    def ptrs(self):
+        g = lambda k: self.p.get(k, 0)
+        return g("bwt"), g("prerank"), g("sa"), g("isa"), g("special")
+
+    def close(self):
+        for v in self.p.values():
+            (self.mem.free if self.rank == 0 else self.mem.close)(v)
+        self.p = {}
+
+
+def build_sharded_direct(engine, results, sasamplingrate=32, isasamplingrate=262144, bwtonly=False, device=None):
+    """Suffix-range sharding with direct stores (DirectResults): rank r sorts key range r and writes its outputs
+    into rank 0's buffers.  One all-reduce of the "suffixes left unresolved" counts on the build's stream is the
+    only collective: it is the vote on the fast path and, being ordered behind every rank's kernels, the point
+    after which rank 0 may read.  Returns False when the text needs the general path (block merge tree).
+    The next build must not start before rank 0 has consumed the results (a barrier, or the next collective)."""
+    rank, world = results.rank, results.world
+    unres = engine.shard_build(rank, world, *results.ptrs(), preisarate=results.prerate, sasamplingrate=sasamplingrate,
+                               isasamplingrate=isasamplingrate, bwtonly=bwtonly)
+    if world > 1:
+        flag = torch.tensor([unres], dtype=torch.int64, device=device or torch.device("cuda", torch.cuda.current_device()))
+        dist.all_reduce(flag, op=dist.ReduceOp.SUM)
+        unres = int(flag.item())
+    if unres != 0:
+        return False
+    if rank == 0:
+        engine.shard_adopt(world, *results.ptrs())
+    return True
+
+
 def build_distributed(engine, local_blocks=1, preisarate=0, sasamplingrate=32, isasamplingrate=262144, bwtonly=False,
                       largelcpthres=16384, driver=None, strategy="auto"):
     """Every rank has loaded the same text into `engine`; after the call rank 0's engine holds the
@@ -348,10 +408,25 @@ def build_distributed(engine, local_blocks=1, preisarate=0, sasamplingrate=32, i
     strategy: "shard" = suffix-range sharding only (raises if the text needs the general path),
     "merge" = the reference's block merge tree over NCCL, "auto" = shard, then merge if needed.
     `driver` caches the process groups / buffers between calls: pass back the first return value."""
-    state = driver if isinstance(driver, dict) else {"merge": driver, "shard": None}
+    state = driver if isinstance(driver, dict) else {"merge": driver, "shard": None, "direct": None}
+    if dist.get_backend() == "nccl" and not engine.stream_ptr:
+        # the engine's kernels and torch's collectives must share one stream: nothing else orders them
+        raise ValueError("build_distributed needs an Engine created on a torch stream: Engine(device, torch.cuda.Stream().cuda_stream)")
     if strategy in ("auto", "shard"):
         with torch.cuda.stream(torch.cuda.ExternalStream(engine.stream_ptr)) if engine.stream_ptr else _null():
-            ok, state["shard"] = build_sharded(engine, preisarate, sasamplingrate, isasamplingrate, bwtonly, buffers=state["shard"])
+            if hasattr(engine, "shard_adopt") and os.environ.get("B3M_SHARD_EXCHANGE", "0") != "1":
+                # every rank stores straight into rank 0's buffers (CUDA IPC)
+                res = state.get("direct")
+                key = (engine.info()["n"], sasamplingrate, isasamplingrate, bool(bwtonly))
+                if res is not None and (res.key != key or (preisarate and res.prerate != preisarate)):
+                    res.close()
+                    res = None
+                if res is None:
+                    res = DirectResults(engine, preisarate, sasamplingrate, isasamplingrate, bwtonly, dist.get_rank(), dist.get_world_size())
+                state["direct"] = res
+                ok = build_sharded_direct(engine, res, sasamplingrate, isasamplingrate, bwtonly)
+            else:
+                ok, state["shard"] = build_sharded(engine, preisarate, sasamplingrate, isasamplingrate, bwtonly, buffers=state["shard"])
             torch.cuda.current_stream().synchronize()
         if ok:
             return state, {"strategy": "shard"}

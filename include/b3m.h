@@ -282,6 +282,22 @@ int b3m_engine_unpack_rows(b3m_engine * e, const void * d_packed, uint64_t nrows
 int b3m_engine_shard_finish(b3m_engine * e, const void * d_bwt, const void * d_prerank, const void * d_sa, const void * d_isa,
                             const void * d_special, uint32_t nparts);
 
+/* the same without the copies: the engine refers to the caller's buffers, which must stay valid (and unchanged)
+ * until the engine's next load or build */
+int b3m_engine_shard_adopt(b3m_engine * e, const void * d_bwt, const void * d_prerank, const void * d_sa, const void * d_isa,
+                           const void * d_special, uint32_t nparts);
+
+/* Result buffers of a multi-GPU build that every rank writes DIRECTLY (one process per GPU): the owner allocates
+ * them with b3m_dev_alloc and exports a 64-byte CUDA IPC handle, the other processes open it and pass the mapped
+ * pointer to b3m_engine_shard_build, whose kernels then store their BWT rows, anchors and samples into the
+ * owner's HBM over NVLink (peer stores inside the sorting kernels: no gather, no reduction, no collective on the
+ * data path).  Every entry is written by exactly one rank, so the buffers need no initialisation. */
+int b3m_dev_alloc(int device, uint64_t bytes, void ** dptr, char * err, size_t errlen);
+int b3m_dev_free(int device, void * dptr, char * err, size_t errlen);
+int b3m_ipc_export(int device, const void * dptr, void * handle64, char * err, size_t errlen);
+int b3m_ipc_open(int device, const void * handle64, void ** dptr, char * err, size_t errlen);
+int b3m_ipc_close(int device, void * dptr, char * err, size_t errlen);
+
 /* LF-steps/s instrument on the dictionary of the last build: nchains dependent LF chains of
  * `steps` steps each, started at evenly spaced sampled ranks; returns elapsed device ms.
  * Restates /root/reference/src/bwttestdecodespeed.cpp:82-96 for thousands of chains. */
