@@ -34,7 +34,7 @@ class Info(C.Structure):
                                      "extract_bytes", "dict_bytes", "decode_bytes", "launches", "max_lcpnext")]
         + [(k, C.c_float) for k in ("ms_decode", "ms_sort", "ms_extract", "ms_dict", "ms_gap", "ms_merge", "ms_walk",
                                     "ms_total")]
-        + [(k, C.c_uint64) for k in ("sort_tied0", "sort_unresolved0")]
+        + [(k, C.c_uint64) for k in ("sort_tied0", "sort_unresolved0", "arena_capacity", "arena_peak")]
     )
 
 

@@ -520,6 +520,7 @@ void Engine::blk_build_range(uint64_t a0, uint64_t a1, uint64_t nb, void * d_L_o
 	if (nb > m) nb = m;
 	uint64_t const bs = div_up(m, nb);
 	nb = div_up(m, bs);
+	arena.ensure_slab(1, (size_t)work_bytes(2, bs, false));
 	EventAccum tsort(st), tgap(st), tmerge(st);
 	size_t const first = dist_leaves.size();
 	dist_leaves.resize(first + nb);

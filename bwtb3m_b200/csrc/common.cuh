@@ -60,6 +60,31 @@ struct Arena {
 		if (live.empty()) release_all();
 		add_slab(bytes);
 	}
+	// Slab `idx` (0: the text, 1: the working set of a build) holds at least `bytes`: it is created, or -- when
+	// nothing in it is live -- replaced by a larger one.  Keeps the two apart, so that neither `mem=` / `numblocks=`
+	// nor the choice of sorter is decided before the text has been seen (the working set is sized in build()).
+	void ensure_slab(size_t idx, size_t bytes) {
+		bytes = round_up(bytes);
+		while (slabs.size() <= idx) {
+			// placeholder slabs of the minimum size keep the index meaning stable
+			add_slab(slabs.size() == idx ? bytes : 512);
+		}
+		Slab & s = slabs[idx];
+		if (s.size >= bytes) return;
+		for (auto & l : live) if (l.second.first == (int)idx) return; // in use: alloc() grows the arena if it must
+		cudaFree(s.base);
+		capacity -= s.size;
+		s.size = bytes;
+		s.free_.clear();
+		cudaError_t const e = cudaMalloc((void **)&s.base, s.size);
+		if (e != cudaSuccess) {
+			cudaGetLastError();
+			s.base = nullptr; s.size = 0;
+			throw Error(std::string("out of device memory allocating ") + std::to_string(bytes >> 20) + " MiB: " + cudaGetErrorString(e));
+		}
+		s.free_[0] = s.size;
+		capacity += s.size;
+	}
 	void * alloc(size_t bytes) {
 		if (!bytes) return nullptr;
 		bytes = round_up(bytes);

@@ -51,10 +51,11 @@ void Engine::load(const void * input, uint64_t nbytes, int itype, bool on_device
 	codes.release(); packed.release(); raw.release(); d_hist.release(); d_special.release();
 	kr_plan = KeyRangePlan();
 	inputtype = itype;
-	// one slab for the whole build: text + BWT + suffix/rank arrays + sort buffers (HBM layout)
+	// slab 0 of the arena: the staged file, the byte codes, the packed text.  The working set of a build is
+	// sized in build(), once the block plan and the sorter are known (HBM layout)
 	{
 		uint64_t const nsym_est = (itype == B3M_INPUT_PAC || itype == B3M_INPUT_PACTERM) ? nbytes * 4 : nbytes;
-		arena.reserve((size_t)(nsym_est * 30 + nbytes + (64u << 20)));
+		arena.ensure_slab(0, (size_t)(nbytes + nsym_est + nsym_est / 4 + (8u << 20)));
 	}
 	PhaseTimer pt(st);
 	pt.mark();
@@ -192,6 +193,18 @@ static uint64_t choose_preisarate(uint64_t n, int sms) {
 
 uint64_t Engine::choose_preisarate_pub(uint64_t n) const { return choose_preisarate(n, st.sms); }
 
+// Device bytes the working set of a build needs in the common case (rarer needs -- the prefix-doubling rounds
+// of a repetitive text -- grow the arena on demand): `window` suffixes are sorted at a time.  MSD sorter
+// (msd.cuh): 8 B records + 0.75 B tables; LSD sorter and leaves: two (key, index, aux) record sets, order, flags.
+uint64_t Engine::work_bytes(uint64_t nblocks, uint64_t window, bool with_results) const {
+	bool const msd = nblocks == 1 && T.keybits == 2 && T.packed && st.sortpath != B3M_SORT_LSD && T.ntext >= 64 &&
+	                 (st.sortpath == B3M_SORT_MSD || T.ntext >= (1u << 16));
+	uint64_t need = (msd ? 10 : 30) * window + (64ull << 20);
+	if (nblocks > 1) need += 8 * T.n;          // node BWTs, gap array, gt bits, dictionary of the top merges
+	if (with_results) need += 2 * T.n + T.n / 2; // BWT, sampled SA / ISA, anchors, BWA words
+	return need;
+}
+
 void Engine::make_dict(uint32_t exc_pos, uint32_t exc_code, uint32_t exc_lf) {
 	int const flavour = T.sigma <= 4 ? 2 : 8;
 	size_t const bytes = dict_bytes(flavour, T.n, T.sigma);
@@ -222,6 +235,7 @@ void Engine::build(b3m_build_params const & p) {
 	gap_lf_steps = gap_chains = merge_bytes = extract_bytes = 0; max_lcpnext = large_lcp_blocks = 0;
 	ms_sort = ms_extract = ms_dict = ms_gap = ms_merge = ms_walk = 0;
 	numblocks = std::min<uint64_t>(p.numblocks, T.n);
+	arena.ensure_slab(1, (size_t)work_bytes(numblocks, div_up(T.n, numblocks), true));
 
 	PhaseTimer pt(st);
 	pt.mark(); // 0
@@ -340,6 +354,7 @@ void Engine::kr_build_part(uint32_t part, uint32_t nparts, b3m_build_params cons
 	sortstats = SortStats(); walkstats = WalkStats();
 	gap_lf_steps = gap_chains = merge_bytes = extract_bytes = 0; max_lcpnext = large_lcp_blocks = 0;
 	ms_sort = ms_extract = ms_dict = ms_gap = ms_merge = ms_walk = ms_total = 0;
+	arena.ensure_slab(1, (size_t)work_bytes(1, div_up(T.n, nparts) + T.n / 16, false));
 	PhaseTimer pt(st);
 	pt.mark();
 	int const circular = T.has_term ? 0 : 1;
@@ -451,6 +466,7 @@ void Engine::info(b3m_info * o) {
 	o->merge_bytes = merge_bytes; o->extract_bytes = extract_bytes; o->dict_bytes = dict_bytes_moved; o->decode_bytes = decode_bytes;
 	o->launches = st.launches; o->max_lcpnext = max_lcpnext;
 	o->sort_tied0 = sortstats.tied0; o->sort_unresolved0 = sortstats.unresolved0;
+	o->arena_capacity = arena.capacity; o->arena_peak = arena.peak;
 	o->ms_decode = ms_decode; o->ms_sort = ms_sort; o->ms_extract = ms_extract; o->ms_dict = ms_dict;
 	o->ms_gap = ms_gap; o->ms_merge = ms_merge; o->ms_walk = ms_walk; o->ms_total = ms_total;
 }

@@ -85,6 +85,7 @@ struct Engine {
 	Engine(int dev, void * stream);
 	~Engine();
 	void reset_results();
+	uint64_t work_bytes(uint64_t nblocks, uint64_t window, bool with_results) const;
 	void load(const void * input, uint64_t nbytes, int itype, bool on_device);
 	void build(b3m_build_params const & p);
 	void build_blocks(PhaseTimer & pt, uint32_t * exc_pos);

@@ -193,6 +193,8 @@ typedef struct b3m_info {
 	/* K2: suffixes that shared their whole first sort key with another suffix, and those still
 	 * tied after the in-CTA group sort (they enter the prefix-doubling rounds) */
 	uint64_t sort_tied0, sort_unresolved0;
+	/* device memory the engine holds (text slab + working-set slab of the last build) and the most it had in use */
+	uint64_t arena_capacity, arena_peak;
 } b3m_info;
 int b3m_engine_info(b3m_engine * e, b3m_info * info);
 
