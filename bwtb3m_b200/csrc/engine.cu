@@ -27,7 +27,8 @@ Engine::~Engine() {
 	cudaSetDevice(device);
 	cudaStreamSynchronize(st.s);
 	raw.release(); codes.release(); packed.release(); bwt.release(); prerank.release(); sa.release(); isa.release(); dict.release();
-	d_hist.release(); d_special.release();
+	d_hist.release(); d_special.release(); xs.toff.release();
+	delete xs_pt; xs_pt = nullptr;
 	cudaStreamSynchronize(st.s);
 	arena.release_all();
 	if (pinned) cudaFreeHost(pinned);
@@ -50,6 +51,7 @@ void Engine::load(const void * input, uint64_t nbytes, int itype, bool on_device
 	reset_results();
 	codes.release(); packed.release(); raw.release(); d_hist.release(); d_special.release();
 	kr_plan = KeyRangePlan();
+	xs = XShard();
 	inputtype = itype;
 	// slab 0 of the arena: the staged file, the byte codes, the packed text.  The working set of a build is
 	// sized in build(), once the block plan and the sorter are known (HBM layout)
@@ -382,6 +384,90 @@ void Engine::kr_build_part(uint32_t part, uint32_t nparts, b3m_build_params cons
 	B3M_CUDA(cudaStreamSynchronize(st.s));
 	ms_sort = pt.ms(0, 1); ms_total = ms_sort;
 	extract_bytes = (kr_plan.base[part + 1] - kr_plan.base[part]) * 6;
+}
+
+// ------------------------------------------------------------------------------------------
+// Multi-GPU, position sharding of level 1 (XShard): count -> [caller exchanges the counts] -> scatter (peer
+// stores) -> [caller: barrier] -> finish.  Outputs as in kr_build_part.
+// ------------------------------------------------------------------------------------------
+void Engine::prepare_shard_params(b3m_build_params const & p, uint32_t nparts) {
+	auto pow2 = [](uint64_t v) { return v && !(v & (v - 1)); };
+	B3M_REQUIRE(pow2(p.sasamplingrate) && pow2(p.isasamplingrate), "sampling rates must be powers of two");
+	B3M_REQUIRE(p.sortpath >= B3M_SORT_AUTO && p.sortpath <= B3M_SORT_MSD, "unknown sortpath");
+	reset_results();
+	params = p;
+	if (st.sortpath != p.sortpath) kr_plan = KeyRangePlan();
+	st.sortpath = p.sortpath;
+	prerate = p.preisarate ? p.preisarate : (p.bwtonly ? 64 : choose_preisarate(T.n, st.sms));
+	B3M_REQUIRE(pow2(prerate), "preisarate must be a power of two");
+	npre = div_up(T.n, prerate);
+	nsa = p.bwtonly ? 0 : div_up(T.n, p.sasamplingrate);
+	nisa = p.bwtonly ? 0 : div_up(T.n, p.isasamplingrate);
+	numblocks = nparts;
+	sortstats = SortStats(); walkstats = WalkStats();
+	gap_lf_steps = gap_chains = merge_bytes = extract_bytes = 0; max_lcpnext = large_lcp_blocks = 0;
+	ms_sort = ms_extract = ms_dict = ms_gap = ms_merge = ms_walk = ms_total = 0;
+}
+
+void Engine::xs_count(uint32_t part, uint32_t nparts, b3m_build_params const & p, void * d_totals, uint32_t * nbins) {
+	B3M_CUDA(cudaSetDevice(device));
+	B3M_REQUIRE(loaded, "no input loaded");
+	B3M_REQUIRE(d_totals && nbins, "null argument");
+	prepare_shard_params(p, nparts);
+	arena.ensure_slab(1, (size_t)work_bytes(1, div_up(T.n, nparts) + T.n / 16, false));
+	delete xs_pt;
+	xs_pt = new PhaseTimer(st);
+	xs_pt->mark();
+	k2_xshard_count(st, T, T.has_term ? 0 : 1, part, nparts, xs, (unsigned long long *)d_totals, nbins);
+}
+
+void Engine::xs_scatter(const uint64_t * h_alltot, void * const * d_recs, const uint64_t * caps) {
+	B3M_CUDA(cudaSetDevice(device));
+	B3M_REQUIRE(loaded && xs.nparts && xs_pt, "xshard_count was not called");
+	B3M_REQUIRE(h_alltot && d_recs && caps, "null argument");
+	k2_xshard_scatter(st, T, T.has_term ? 0 : 1, xs, (const unsigned long long *)h_alltot, (unsigned long long * const *)d_recs, caps, &sortstats);
+}
+
+void Engine::xs_finish(void * d_recs_own, void * d_bwt, void * d_prerank, void * d_sa, void * d_isa, void * d_special, uint64_t * unresolved) {
+	B3M_CUDA(cudaSetDevice(device));
+	B3M_REQUIRE(loaded && xs.nparts && xs_pt, "xshard_count was not called");
+	B3M_REQUIRE(d_recs_own && d_bwt && d_prerank && d_special && unresolved, "null argument");
+	b3m_build_params const & p = params;
+	B3M_REQUIRE(p.bwtonly || (d_sa && d_isa), "null sample buffers");
+	FusedOut fo;
+	fo.bwt = (uint8_t *)d_bwt; fo.shift = T.has_term ? 1 : 0; fo.has_term = T.has_term; fo.special = (uint32_t *)d_special;
+	fo.prerank = (uint32_t *)d_prerank; fo.prelog = ceil_log2_u64(prerate);
+	if (!p.bwtonly) {
+		fo.sa_s = (unsigned long long *)d_sa; fo.salog = ceil_log2_u64(p.sasamplingrate);
+		fo.isa_s = (unsigned long long *)d_isa; fo.isalog = ceil_log2_u64(p.isasamplingrate);
+	}
+	*unresolved = k2_xshard_finish(st, T, T.has_term ? 0 : 1, xs, (unsigned long long *)d_recs_own, fo, &sortstats);
+	if (xs.part == 0 && T.has_term) {
+		// rank 0 is the terminator suffix (text position ntext): written explicitly, the buffers are not zeroed
+		B3M_CUDA(cudaMemcpyAsync(d_bwt, T.codes + T.ntext - 1, 1, cudaMemcpyDeviceToDevice, st.s));
+		uint64_t const pos = T.ntext;
+		if ((T.ntext & (prerate - 1)) == 0) B3M_CUDA(cudaMemsetAsync((uint32_t *)d_prerank + T.ntext / prerate, 0, 4, st.s));
+		if (!p.bwtonly) {
+			B3M_CUDA(cudaMemcpyAsync(d_sa, &pos, 8, cudaMemcpyHostToDevice, st.s));
+			if ((T.ntext & (p.isasamplingrate - 1)) == 0) B3M_CUDA(cudaMemsetAsync((uint64_t *)d_isa + T.ntext / p.isasamplingrate, 0, 8, st.s));
+		}
+	}
+	// kr_rows / shard_adopt describe the result by the same plan structure
+	kr_plan = KeyRangePlan();
+	kr_plan.nparts = xs.nparts;
+	kr_plan.bin_lo.assign(xs.bnd.begin(), xs.bnd.end());
+	kr_plan.base.assign(xs.nparts + 1, T.ntext);
+	{
+		uint64_t acc = 0;
+		for (uint32_t q = 0, b = 0; q <= xs.nparts; ++q) {
+			for (; b < (q < xs.nparts ? xs.bnd[q] : (uint32_t)xs.total.size()); ++b) acc += xs.total[b];
+			kr_plan.base[q] = acc;
+		}
+	}
+	xs_pt->mark();
+	B3M_CUDA(cudaStreamSynchronize(st.s));
+	ms_sort = xs_pt->ms(0, 1); ms_total = ms_sort;
+	extract_bytes = xs.records * 6;
 }
 
 // first BWT row of every key range (rows of range p: [first[p], first[p+1])); range 0 also owns the terminator row
@@ -806,6 +892,15 @@ int b3m_engine_shard_rows(b3m_engine * h, uint32_t nparts, uint64_t * first_row)
 int b3m_engine_shard_finish(b3m_engine * h, const void * d_bwt, const void * d_prerank, const void * d_sa, const void * d_isa, const void * d_special,
                             uint32_t nparts) {
 	B3M_GUARD(h, h->e->kr_finish(d_bwt, d_prerank, d_sa, d_isa, d_special, nparts, false));
+}
+int b3m_engine_xshard_count(b3m_engine * h, uint32_t part, uint32_t nparts, const b3m_build_params * p, void * d_totals, uint32_t * nbins) {
+	B3M_GUARD(h, { if (!p) throw b3m::Error("null params"); h->e->xs_count(part, nparts, *p, d_totals, nbins); });
+}
+int b3m_engine_xshard_scatter(b3m_engine * h, const uint64_t * all_totals, void * const * d_recs, const uint64_t * caps) {
+	B3M_GUARD(h, h->e->xs_scatter(all_totals, d_recs, caps));
+}
+int b3m_engine_xshard_finish(b3m_engine * h, void * d_recs_own, void * d_bwt, void * d_prerank, void * d_sa, void * d_isa, void * d_special, uint64_t * unresolved) {
+	B3M_GUARD(h, h->e->xs_finish(d_recs_own, d_bwt, d_prerank, d_sa, d_isa, d_special, unresolved));
 }
 int b3m_engine_shard_adopt(b3m_engine * h, const void * d_bwt, const void * d_prerank, const void * d_sa, const void * d_isa, const void * d_special,
                            uint32_t nparts) {

@@ -116,6 +116,13 @@ struct Engine {
 	void kr_build_part(uint32_t part, uint32_t nparts, b3m_build_params const & p, void * d_bwt, void * d_prerank, void * d_sa, void * d_isa,
 	                   void * d_special, uint64_t * unresolved);
 	void kr_rows(uint32_t nparts, uint64_t * first);
+	// multi-GPU, position sharding of the MSD sorter's first level (XShard, kernels.h)
+	XShard xs;
+	void prepare_shard_params(b3m_build_params const & p, uint32_t nparts);
+	void xs_count(uint32_t part, uint32_t nparts, b3m_build_params const & p, void * d_totals, uint32_t * nbins);
+	void xs_scatter(const uint64_t * h_alltot, void * const * d_recs, const uint64_t * caps);
+	void xs_finish(void * d_recs_own, void * d_bwt, void * d_prerank, void * d_sa, void * d_isa, void * d_special, uint64_t * unresolved);
+	PhaseTimer * xs_pt = nullptr;
 	void pack_rows(const void * d_rows, uint64_t nrows, void * d_packed, bool unpack);
 	void kr_finish(const void * d_bwt, const void * d_prerank, const void * d_sa, const void * d_isa, const void * d_special, uint32_t nparts, bool adopt);
 	// K8 / output side

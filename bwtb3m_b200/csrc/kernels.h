@@ -104,6 +104,29 @@ void k2_keyrange_plan(Stream & st, DevText const & T, int circular, uint32_t npa
 // fo.shift + base[part] + k; returns the number of suffixes left unresolved (0: the slice is final)
 uint64_t k2_sort_keyrange(Stream & st, DevText const & T, int circular, KeyRangePlan const & plan, uint32_t part, FusedOut const & fo, SortStats * stats);
 
+// Position sharding of the MSD sorter's first level (multi-GPU, msd.cuh): part p counts and scatters the text
+// positions of ITS range of tiles for all bins, writing every record straight into the array of the part that
+// owns the record's bin (the other GPUs' arrays through CUDA IPC peer mappings: the exchange is the stores of the
+// scatter kernel); level 2 and the finish then run on the part's own bins.
+struct XShard {
+	unsigned b1 = 0, b2 = 0;
+	uint32_t part = 0, nparts = 0;
+	uint32_t t_lo = 0, t_hi = 0;                 // tiles of the text this part scatters
+	DevBuf<uint32_t> toff;                       // column-scanned counts of those tiles
+	std::vector<unsigned long long> total;       // global size of every level-1 bin (after the exchange of the counts)
+	std::vector<uint32_t> bnd;                   // part p owns the bins [bnd[p], bnd[p+1])
+	uint64_t rank_base = 0, records = 0;         // suffixes in the bins before this part's, and in them
+};
+// false: the sorter does not apply to this text (more than four codes, too short) -- use k2_sort_keyrange.
+// d_totals (device, 2^b1 values): sizes of the bins over this part's tiles; *nbins = 2^b1
+bool k2_xshard_count(Stream & st, DevText const & T, int circular, uint32_t part, uint32_t nparts, XShard & X, unsigned long long * d_totals, uint32_t * nbins);
+// h_alltot: [nparts][2^b1] the d_totals of every part (host); recs[p] / cap[p]: part p's record array (device pointer valid here) and its
+// capacity in records.  Throws when a bin or a part is too large for the path.
+void k2_xshard_scatter(Stream & st, DevText const & T, int circular, XShard & X, const unsigned long long * h_alltot, unsigned long long * const * recs,
+                       const uint64_t * cap, SortStats * stats);
+// after every part has scattered: level 2 + finish on this part's bins; returns the number of suffixes left unresolved
+uint64_t k2_xshard_finish(Stream & st, DevText const & T, int circular, XShard & X, unsigned long long * recs_own, FusedOut const & fo0, SortStats * stats);
+
 // ---- K4 / K7 ----------------------------------------------------------------------------
 // Rank dictionary, 2-bit flavour: 64-byte lines = 4 x uint32 cumulative counts + 48 bytes
 // (192 symbols x 2 bit).  Byte flavour: 128 symbols per block, 256 x uint32 counts + 128 bytes.

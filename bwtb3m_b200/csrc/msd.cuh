@@ -179,12 +179,12 @@ k_msd_hist(TextView v, unsigned b1, unsigned long long * __restrict__ ghist) {
 
 // ---- per-tile counts of the kept bins -------------------------------------------------------
 __global__ void __launch_bounds__(MSD_THREADS)
-k_msd_count(TextView v, unsigned b1, uint32_t d_lo, uint32_t nkeep, uint16_t * __restrict__ tcount /* [ntiles][nkeep] */) {
+k_msd_count(TextView v, unsigned b1, uint32_t d_lo, uint32_t nkeep, uint32_t t_lo, uint16_t * __restrict__ tcount /* [tiles from t_lo][nkeep] */) {
 	__shared__ uint32_t cnt[MSD_MAXBINS];
 	for (unsigned i = threadIdx.x; i < nkeep; i += MSD_THREADS) cnt[i] = 0;
 	__syncthreads();
 	uint32_t d[MSD_ITEMS], h[MSD_ITEMS];
-	msd_records16<false>(v, b1, (uint64_t)blockIdx.x * MSD_TILE + (uint64_t)MSD_ITEMS * threadIdx.x, d, h);
+	msd_records16<false>(v, b1, (uint64_t)(blockIdx.x + t_lo) * MSD_TILE + (uint64_t)MSD_ITEMS * threadIdx.x, d, h);
 	#pragma unroll
 	for (int j = 0; j < MSD_ITEMS; ++j) { uint32_t const b = d[j] - d_lo; if (b < nkeep) atomicAdd(&cnt[b], 1u); }
 	__syncthreads();
@@ -230,13 +230,19 @@ k_msd_colapply(const uint16_t * __restrict__ tcount, uint32_t ntiles, uint32_t n
 }
 
 // ---- level 1 ---------------------------------------------------------------------------------
+constexpr int MSD_MAXPARTS = 16;
 struct MsdP1 {
 	TextView v;
 	unsigned b1;
-	uint32_t d_lo, nkeep;           // bins [d_lo, d_lo + nkeep) are kept (one key range of a sharded build, or all)
-	const uint32_t * base;          // [nkeep + 1] first record of kept bin b
-	const uint32_t * toff;          // [ntiles][nkeep] records of bin b in earlier tiles
-	unsigned long long * out;
+	uint32_t d_lo, nkeep;           // bins [d_lo, d_lo + nkeep) are kept (one key range of a bin-sharded build, or all)
+	uint32_t t_lo;                  // first tile of the text this launch covers (position-sharded builds: one range of tiles per GPU)
+	const uint32_t * base;          // [nkeep] where this launch's first record of kept bin b goes in its destination array
+	const uint32_t * toff;          // [tiles of the launch][nkeep] records of bin b in the earlier tiles of the launch
+	// destination arrays: bin b belongs to part p with bnd[p] <= b < bnd[p+1]; out[p] may be another GPU's memory
+	// (CUDA IPC peer mapping): the records then cross NVLink as the stores of this kernel
+	unsigned nparts;
+	uint32_t bnd[MSD_MAXPARTS + 1];
+	unsigned long long * out[MSD_MAXPARTS];
 };
 
 __global__ void __launch_bounds__(MSD_THREADS, 2)
@@ -245,12 +251,15 @@ k_msd_scatter(MsdP1 A) {
 	unsigned long long * const stage = reinterpret_cast<unsigned long long *>(msd_dyn);
 	__shared__ uint32_t cnt[MSD_MAXBINS];
 	__shared__ uint32_t gdel[MSD_MAXBINS];
+	__shared__ uint8_t gown[MSD_MAXBINS];
+	__shared__ unsigned long long * s_out[MSD_MAXPARTS];
 	__shared__ uint32_t wsum[MSD_THREADS / 32];
 	unsigned const nkeep = A.nkeep;
 	for (unsigned i = threadIdx.x; i < nkeep; i += MSD_THREADS) cnt[i] = 0;
+	if (threadIdx.x < A.nparts) s_out[threadIdx.x] = A.out[threadIdx.x];
 	__syncthreads();
 	uint32_t const tile = blockIdx.x;
-	uint64_t const t0 = (uint64_t)tile * MSD_TILE;
+	uint64_t const t0 = (uint64_t)(tile + A.t_lo) * MSD_TILE;
 
 	uint32_t hi32[MSD_ITEMS], dr[MSD_ITEMS]; // dr = (kept bin << 16) | rank inside the tile's bin; ~0: not kept
 	msd_records16<true>(A.v, A.b1, t0 + (uint64_t)MSD_ITEMS * threadIdx.x, dr, hi32);
@@ -266,7 +275,13 @@ k_msd_scatter(MsdP1 A) {
 	const uint32_t * const orow = A.toff + (uint64_t)tile * nkeep;
 	#pragma unroll
 	for (unsigned q = 0; q < 4; ++q)
-		if (q < per && b0 + q < nkeep) gdel[b0 + q] = __ldg(A.base + b0 + q) + __ldg(orow + b0 + q) - cnt[b0 + q];
+		if (q < per && b0 + q < nkeep) {
+			unsigned const b = b0 + q;
+			gdel[b] = __ldg(A.base + b) + __ldg(orow + b) - cnt[b];
+			unsigned own = 0;
+			for (unsigned p = 1; p < A.nparts; ++p) own += A.bnd[p] <= b ? 1u : 0u;
+			gown[b] = (uint8_t)own;
+		}
 	#pragma unroll
 	for (int j = 0; j < MSD_ITEMS; ++j) {
 		if (dr[j] != 0xffffffffu) {
@@ -281,8 +296,8 @@ k_msd_scatter(MsdP1 A) {
 		uint32_t const s = j * MSD_THREADS + threadIdx.x;
 		if (s < nvalid) {
 			unsigned long long const w = stage[s];
-			uint32_t const lo = (uint32_t)w;
-			A.out[gdel[lo >> 14] + s] = (w & 0xffffffff00000000ull) | (uint32_t)(t0 + (lo & 0x3fffu));
+			uint32_t const lo = (uint32_t)w, d = lo >> 14;
+			s_out[gown[d]][gdel[d] + s] = (w & 0xffffffff00000000ull) | (uint32_t)(t0 + (lo & 0x3fffu));
 		}
 	}
 }

@@ -312,36 +312,100 @@ static void msd_configure() {
 
 static uint32_t low_mask(unsigned log) { return log >= 32 ? 0xffffffffu : (1u << log) - 1u; }
 
-// Round 0 on the suffixes whose first b1 bits lie in [d_lo, d_hi).  Returns false when the path does not
-// apply (a level-1 bin of 2^30 suffixes or more).  On return `unresolved` counts the suffixes still tied;
-// if that is not zero and sa_buf is given, sa_buf / hflag hold the order reached and the head flags of its
+// ---- the three phases of round 0 -------------------------------------------------------------
+// (1) counts of the tiles [t_lo, t_hi) of the text for the bins [d_lo, d_lo + nkeep), scanned down the columns;
+//     the bin totals of these tiles are left in d_tot (device)
+struct MsdCounts {
+	uint32_t t_lo = 0, t_hi = 0;
+	DevBuf<uint32_t> toff; // [t_hi - t_lo][nkeep] records of bin b in the earlier tiles of the range
+};
+static void msd_count_phase(Stream & st, TextView const & v, MsdGeom const & g, uint32_t d_lo, uint32_t nkeep, uint32_t t_lo, uint32_t t_hi,
+                            MsdCounts & C, unsigned long long * d_tot, SortStats & S) {
+	msd_configure();
+	uint32_t const nt = t_hi - t_lo, nch = (uint32_t)div_up(nt, MSD_COLCHUNK);
+	C.t_lo = t_lo; C.t_hi = t_hi;
+	if (nt == 0) { B3M_CUDA(cudaMemsetAsync(d_tot, 0, nkeep * 8, st.s)); return; }
+	C.toff.alloc(st, (uint64_t)nt * nkeep);
+	DevBuf<uint16_t> tcount(st, (uint64_t)nt * nkeep);
+	DevBuf<uint32_t> partial(st, (uint64_t)nch * nkeep);
+	uint64_t const npos = std::min<uint64_t>((uint64_t)nt * MSD_TILE, v.W - (uint64_t)t_lo * MSD_TILE);
+	B3M_LAUNCH_T(st, "msd_count", npos / 4 + 2ull * nt * nkeep, k_msd_count, nt, MSD_THREADS, 0, v, g.b1, d_lo, nkeep, t_lo, tcount.get());
+	B3M_LAUNCH_T(st, "msd_colscan", 2ull * nt * nkeep, k_msd_colsum, nch, 256, 0, (const uint16_t *)tcount.get(), nt, nkeep, partial.get());
+	B3M_LAUNCH(st, k_msd_colscan, (unsigned)div_up(nkeep, 256), 256, 0, partial.get(), nch, nkeep, d_tot);
+	B3M_LAUNCH_T(st, "msd_colscan", 6ull * nt * nkeep, k_msd_colapply, nch, 256, 0, (const uint16_t *)tcount.get(), nt, nkeep, (const uint32_t *)partial.get(), C.toff.get());
+	S.other_bytes += npos / 4 + 10ull * nt * nkeep;
+}
+
+// (2) level 1 on the counted tiles: the records of kept bin b go to out[p][destbase[b] ...], p the part that owns b
+static void msd_scatter_phase(Stream & st, TextView const & v, MsdGeom const & g, uint32_t d_lo, uint32_t nkeep, MsdCounts & C,
+                              std::vector<uint32_t> const & destbase, unsigned nparts, const uint32_t * bnd, unsigned long long * const * out,
+                              uint64_t nrec, SortStats & S) {
+	uint32_t const nt = C.t_hi - C.t_lo;
+	if (nt == 0) return;
+	B3M_REQUIRE(nparts >= 1 && nparts <= (unsigned)MSD_MAXPARTS, "too many destinations");
+	DevBuf<uint32_t> dbase(st, nkeep);
+	B3M_CUDA(cudaMemcpyAsync(dbase.get(), destbase.data(), nkeep * 4, cudaMemcpyHostToDevice, st.s));
+	MsdP1 A;
+	A.v = v; A.b1 = g.b1; A.d_lo = d_lo; A.nkeep = nkeep; A.t_lo = C.t_lo; A.base = dbase.get(); A.toff = C.toff.get(); A.nparts = nparts;
+	for (unsigned p = 0; p <= nparts; ++p) A.bnd[p] = bnd[p];
+	for (unsigned p = 0; p < nparts; ++p) A.out[p] = out[p];
+	uint64_t const npos = std::min<uint64_t>((uint64_t)nt * MSD_TILE, v.W - (uint64_t)C.t_lo * MSD_TILE);
+	B3M_LAUNCH_T(st, "msd_scatter", npos / 4 + 4ull * nt * nkeep + 8 * nrec, k_msd_scatter, nt, MSD_THREADS, MSD_TILE * 8, A);
+	S.radix_passes++; S.radix_bytes += npos / 4 + 4ull * nt * nkeep + 8 * nrec;
+	C.toff.release();
+}
+
+static bool msd_finish_phase(Stream & st, TextView const & v, int lin, MsdGeom const & g, uint32_t nkeep, const unsigned long long * tot,
+                             unsigned long long * recs_ptr, bool whole, FusedOut const & fo, StreamOut * so, DevBuf<uint32_t> * sa_buf,
+                             DevBuf<uint8_t> * hflag, SortStats & S, uint64_t & unresolved, uint64_t & hstart);
+
+// Round 0 on the suffixes whose first b1 bits lie in [d_lo, d_hi), all on this device.  Returns false when the
+// path does not apply (a level-1 bin of 2^30 suffixes or more).  On return `unresolved` counts the suffixes still
+// tied; if that is not zero and sa_buf is given, sa_buf / hflag hold the order reached and the head flags of its
 // groups, which share at least `hstart` symbols.
 static bool msd_round0(Stream & st, TextView const & v, int lin, MsdGeom const & g, uint32_t d_lo, uint32_t d_hi,
                        FusedOut const & fo, StreamOut * so, DevBuf<uint32_t> * sa_buf, DevBuf<uint8_t> * hflag, SortStats & S,
                        uint64_t & unresolved, uint64_t & hstart) {
-	unsigned const nb2 = 1u << g.b2, nkeep = d_hi - d_lo;
-	uint64_t const W = v.W;
+	unsigned const nkeep = d_hi - d_lo;
 	unresolved = 0;
 	S.rounds = 1;
-	msd_configure();
 	double t_last = wall_ms();
-	// ---- counts per tile and bin, scanned down the columns ----
-	uint32_t const nt1 = (uint32_t)div_up(W, MSD_TILE), nch = (uint32_t)div_up(nt1, MSD_COLCHUNK);
-	DevBuf<uint32_t> toff(st, (uint64_t)nt1 * nkeep);
+	MsdCounts C;
 	std::vector<unsigned long long> tot(nkeep);
 	{
-		DevBuf<uint16_t> tcount(st, (uint64_t)nt1 * nkeep);
-		DevBuf<uint32_t> partial(st, (uint64_t)nch * nkeep);
 		DevBuf<unsigned long long> dtot(st, nkeep);
-		B3M_LAUNCH_T(st, "msd_count", W / 4 + 2ull * nt1 * nkeep, k_msd_count, nt1, MSD_THREADS, 0, v, g.b1, d_lo, nkeep, tcount.get());
-		B3M_LAUNCH_T(st, "msd_colscan", 2ull * nt1 * nkeep, k_msd_colsum, nch, 256, 0, (const uint16_t *)tcount.get(), nt1, nkeep, partial.get());
-		B3M_LAUNCH(st, k_msd_colscan, (unsigned)div_up(nkeep, 256), 256, 0, partial.get(), nch, nkeep, dtot.get());
-		B3M_LAUNCH_T(st, "msd_colscan", 6ull * nt1 * nkeep, k_msd_colapply, nch, 256, 0, (const uint16_t *)tcount.get(), nt1, nkeep, (const uint32_t *)partial.get(), toff.get());
+		msd_count_phase(st, v, g, d_lo, nkeep, 0u, (uint32_t)div_up(v.W, MSD_TILE), C, dtot.get(), S);
 		B3M_CUDA(cudaMemcpyAsync(tot.data(), dtot.get(), nkeep * 8, cudaMemcpyDeviceToHost, st.s));
 		B3M_CUDA(cudaStreamSynchronize(st.s));
-		S.other_bytes += W / 4 + 10ull * nt1 * nkeep;
 	}
 	TRACE("msd count");
+	std::vector<uint32_t> destbase(nkeep);
+	uint64_t m = 0;
+	for (unsigned b = 0; b < nkeep; ++b) {
+		if (tot[b] >= (1ull << 30)) return false;
+		destbase[b] = (uint32_t)m;
+		m += tot[b];
+	}
+	S.active_sum += m;
+	if (m == 0) return true;
+	DevBuf<unsigned long long> recs(st, m + 2);
+	uint32_t const bnd[2] = {0u, nkeep};
+	unsigned long long * const out[1] = {recs.get()};
+	msd_scatter_phase(st, v, g, d_lo, nkeep, C, destbase, 1, bnd, out, m, S);
+	TRACE("msd level 1");
+	return msd_finish_phase(st, v, lin, g, nkeep, tot.data(), recs.get(), d_lo == 0 && nkeep == (1u << g.b1), fo, so, sa_buf, hflag, S, unresolved, hstart);
+}
+
+// (3) level 2, sub-bucket sizes and the finish on the `nkeep` bins whose records lie bin after bin in recs_ptr
+// (tot[b] of them in bin b); `whole`: these are all suffixes of the text (results may be streamed to the host)
+static bool msd_finish_phase(Stream & st, TextView const & v, int lin, MsdGeom const & g, uint32_t nkeep, const unsigned long long * tot,
+                             unsigned long long * recs_ptr, bool whole, FusedOut const & fo, StreamOut * so, DevBuf<uint32_t> * sa_buf,
+                             DevBuf<uint8_t> * hflag, SortStats & S, uint64_t & unresolved, uint64_t & hstart) {
+	unsigned const nb2 = 1u << g.b2;
+	uint64_t const W = v.W;
+	msd_configure();
+	double t_last = wall_ms();
+	unresolved = 0;
 	std::vector<uint32_t> hb(2 * (nkeep + 1)); // first record | first level-2 tile of every kept bin
 	uint64_t m = 0, nt2 = 0;
 	for (unsigned b = 0; b < nkeep; ++b) {
@@ -351,20 +415,12 @@ static bool msd_round0(Stream & st, TextView const & v, int lin, MsdGeom const &
 		m += c; nt2 += div_up(c, MSD_TILE);
 	}
 	hb[nkeep] = (uint32_t)m; hb[2 * nkeep + 1] = (uint32_t)nt2;
-	S.active_sum += m;
 	if (m == 0) return true;
+	B3M_REQUIRE(m < 0xFFFFFF00ull, "too many records for one device");
 	DevBuf<uint32_t> dplan(st, hb.size());
 	B3M_CUDA(cudaMemcpyAsync(dplan.get(), hb.data(), hb.size() * 4, cudaMemcpyHostToDevice, st.s));
 	const uint32_t * d_base = dplan.get(), * d_tpre = dplan.get() + nkeep + 1;
-	DevBuf<unsigned long long> recs(st, m + 2);
-	{
-		// level 1
-		MsdP1 A{v, g.b1, d_lo, nkeep, d_base, toff.get(), recs.get()};
-		B3M_LAUNCH_T(st, "msd_scatter", W / 4 + 4ull * nt1 * nkeep + 8 * m, k_msd_scatter, nt1, MSD_THREADS, MSD_TILE * 8, A);
-		S.radix_passes++; S.radix_bytes += W / 4 + 4ull * nt1 * nkeep + 8 * m;
-	}
-	toff.release();
-	TRACE("msd level 1");
+	struct { unsigned long long * p; unsigned long long * get() const { return p; } } recs{recs_ptr};
 	DevBuf<uint16_t> table(st, nt2 * (nb2 + 1));
 	{
 		MsdP2 A{g.b2, nkeep, d_base, d_tpre, recs.get(), table.get()};
@@ -397,7 +453,6 @@ static bool msd_round0(Stream & st, TextView const & v, int lin, MsdGeom const &
 		for (int q = 0; q < MSD_CSLOTS; ++q) { for (int c = 0; c < 3; ++c) hc[c] += hcs[4 * q + c]; hc[3] |= hcs[4 * q + 3]; }
 	};
 	// early delivery (StreamOut): rows below a finished range of sub-buckets are final
-	bool const whole = d_lo == 0 && nkeep == (1u << g.b1);
 	bool const stream_sa = so && so->host_sa && fo.sa_s && st.copy && nsb >= 64 && whole;
 	bool stream_bwa = so && so->host_bwa && so->d_bwa && fo.has_term && st.copy && nsb >= 64 && whole;
 	uint64_t primary = 0;
@@ -721,6 +776,96 @@ uint64_t k2_sort_keyrange(Stream & st, DevText const & T, int circular, KeyRange
 		stats->tied0 += St.tied0; stats->unresolved0 += St.unresolved0;
 	}
 	return hc[0];
+}
+
+// ------------------------------------------------------------------------------------------
+// Position sharding of level 1 (XShard, kernels.h)
+// ------------------------------------------------------------------------------------------
+bool k2_xshard_count(Stream & st, DevText const & T, int circular, uint32_t part, uint32_t nparts, XShard & X, unsigned long long * d_totals, uint32_t * nbins) {
+	B3M_REQUIRE(nparts >= 1 && nparts <= (uint32_t)MSD_MAXPARTS && part < nparts, "bad part index");
+	MsdGeom g;
+	*nbins = 0;
+	if (!msd_geometry(st, T, T.ntext, g)) return false;
+	TextView v{T.codes, T.packed, T.ntext, 0, T.ntext, circular, 0, T.has_term};
+	uint32_t const nt1 = (uint32_t)div_up(T.ntext, MSD_TILE);
+	X = XShard();
+	X.b1 = g.b1; X.b2 = g.b2; X.part = part; X.nparts = nparts;
+	X.t_lo = (uint32_t)((uint64_t)nt1 * part / nparts); X.t_hi = (uint32_t)((uint64_t)nt1 * (part + 1) / nparts);
+	MsdCounts C;
+	SortStats S;
+	msd_count_phase(st, v, g, 0u, 1u << g.b1, X.t_lo, X.t_hi, C, d_totals, S);
+	X.toff = std::move(C.toff);
+	*nbins = 1u << g.b1;
+	return true;
+}
+
+void k2_xshard_scatter(Stream & st, DevText const & T, int circular, XShard & X, const unsigned long long * h_alltot, unsigned long long * const * recs,
+                       const uint64_t * cap, SortStats * stats) {
+	B3M_REQUIRE(X.nparts, "xshard_count was not called");
+	unsigned const nb1 = 1u << X.b1;
+	uint32_t const P = X.nparts;
+	MsdGeom g; g.b1 = X.b1; g.b2 = X.b2;
+	TextView v{T.codes, T.packed, T.ntext, 0, T.ntext, circular, 0, T.has_term};
+	// global bin sizes; the bins are cut into P ranges of about W / P suffixes (the same on every part)
+	X.total.assign(nb1, 0);
+	for (uint32_t p = 0; p < P; ++p) for (unsigned b = 0; b < nb1; ++b) X.total[b] += h_alltot[(uint64_t)p * nb1 + b];
+	uint64_t const W = T.ntext;
+	X.bnd.assign(P + 1, nb1);
+	X.bnd[0] = 0;
+	std::vector<uint64_t> first(P + 1, W);
+	first[0] = 0;
+	{
+		uint64_t acc = 0;
+		uint32_t p = 1;
+		for (unsigned b = 0; b < nb1 && p < P; ++b) {
+			while (p < P && acc >= (W * p) / P) { X.bnd[p] = b; first[p] = acc; ++p; }
+			acc += X.total[b];
+		}
+	}
+	for (unsigned b = 0; b < nb1; ++b) B3M_REQUIRE(X.total[b] < (1ull << 30), "a level-1 bucket of 2^30 suffixes or more: use another strategy");
+	for (uint32_t p = 0; p < P; ++p) B3M_REQUIRE(first[p + 1] - first[p] + 2 <= cap[p] && first[p + 1] - first[p] < 0xFFFFFF00ull, "a key range exceeds its record array: use another strategy");
+	X.rank_base = first[X.part]; X.records = first[X.part + 1] - first[X.part];
+	// where this part's records of bin b go: start of the bin in its owner's array + the records of the lower parts
+	std::vector<uint32_t> destbase(nb1);
+	uint64_t nrec = 0;
+	for (uint32_t p = 0; p < P; ++p) {
+		uint64_t acc = 0;
+		for (unsigned b = X.bnd[p]; b < X.bnd[p + 1]; ++b) {
+			uint64_t below = 0;
+			for (uint32_t q = 0; q < X.part; ++q) below += h_alltot[(uint64_t)q * nb1 + b];
+			destbase[b] = (uint32_t)(acc + below);
+			acc += X.total[b];
+			nrec += h_alltot[(uint64_t)X.part * nb1 + b];
+		}
+	}
+	MsdCounts C;
+	C.t_lo = X.t_lo; C.t_hi = X.t_hi; C.toff = std::move(X.toff);
+	SortStats S;
+	msd_scatter_phase(st, v, g, 0u, nb1, C, destbase, P, X.bnd.data(), recs, nrec, S);
+	if (stats) { stats->radix_passes += S.radix_passes; stats->radix_bytes += S.radix_bytes; stats->other_bytes += S.other_bytes; }
+}
+
+uint64_t k2_xshard_finish(Stream & st, DevText const & T, int circular, XShard & X, unsigned long long * recs_own, FusedOut const & fo0, SortStats * stats) {
+	B3M_REQUIRE(X.nparts && !X.bnd.empty(), "xshard_scatter was not called");
+	MsdGeom g; g.b1 = X.b1; g.b2 = X.b2;
+	TextView v{T.codes, T.packed, T.ntext, 0, T.ntext, circular, 0, T.has_term};
+	uint32_t const d_lo = X.bnd[X.part], nkeep = X.bnd[X.part + 1] - d_lo;
+	FusedOut fo = fo0;
+	fo.shift = fo0.shift + X.rank_base;
+	SortStats S;
+	S.rounds = 1; S.active_sum = X.records;
+	uint64_t unresolved = 0, hstart = 0;
+	if (nkeep && X.records) {
+		bool const ok = msd_finish_phase(st, v, !circular, g, nkeep, X.total.data() + d_lo, recs_own, false, fo, nullptr, nullptr, nullptr, S, unresolved, hstart);
+		B3M_REQUIRE(ok, "internal: xshard finish does not apply");
+	}
+	if (stats) {
+		stats->rounds = stats->rounds > S.rounds ? stats->rounds : S.rounds;
+		stats->radix_passes += S.radix_passes; stats->radix_bytes += S.radix_bytes;
+		stats->active_sum += S.active_sum; stats->other_bytes += S.other_bytes;
+		stats->tied0 += S.tied0; stats->unresolved0 += S.unresolved0;
+	}
+	return unresolved;
 }
 
 void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W, int circular, int text_wraps,

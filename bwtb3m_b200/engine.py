@@ -139,6 +139,32 @@ class Engine:
         vp = lambda a: C.c_void_p(a) if a else None
         self._check(self._lib.b3m_engine_shard_finish(self._h, vp(bwt_ptr), vp(prerank_ptr), vp(sa_ptr), vp(isa_ptr), vp(special_ptr), nparts))
 
+    def xshard_count(self, part, nparts, totals_ptr, preisarate=0, sasamplingrate=32, isasamplingrate=262144, bwtonly=False, sortpath="auto"):
+        """Position-sharded build, step 1: counts of this part's text positions per leading-bits bin into the device buffer
+        totals_ptr (2048 uint64 at most); returns the number of bins, 0 when the sorter does not apply to the text."""
+        p = BuildParams(nparts, preisarate, sasamplingrate, isasamplingrate, 1 if bwtonly else 0, 16384, 0, None, None, SORTPATHS[sortpath])
+        nb = C.c_uint32(0)
+        self._check(self._lib.b3m_engine_xshard_count(self._h, part, nparts, C.byref(p), C.c_void_p(totals_ptr), C.byref(nb)))
+        return int(nb.value)
+
+    def xshard_scatter(self, all_totals, recs_ptrs, caps):
+        """Step 2: all_totals = host uint64 array [nparts][nbins]; recs_ptrs[q] = part q's record array as mapped in this
+        process; caps[q] = its capacity in records."""
+        t = np.ascontiguousarray(all_totals, dtype=np.uint64)
+        n = len(recs_ptrs)
+        pa = (C.c_void_p * n)(*[C.c_void_p(x) for x in recs_ptrs])
+        ca = (C.c_uint64 * n)(*caps)
+        self._check(self._lib.b3m_engine_xshard_scatter(self._h, C.c_void_p(t.ctypes.data), pa, ca))
+
+    def xshard_finish(self, recs_own_ptr, bwt_ptr, prerank_ptr, sa_ptr, isa_ptr, special_ptr):
+        """Step 3 (after every part has scattered): sorts this part's key range, outputs at their global places; returns the
+        number of suffixes left unresolved."""
+        un = C.c_uint64(0)
+        vp = lambda a: C.c_void_p(a) if a else None
+        self._check(self._lib.b3m_engine_xshard_finish(self._h, vp(recs_own_ptr), vp(bwt_ptr), vp(prerank_ptr), vp(sa_ptr), vp(isa_ptr), vp(special_ptr),
+                                                       C.byref(un)))
+        return int(un.value)
+
     def shard_adopt(self, nparts, bwt_ptr, prerank_ptr, sa_ptr, isa_ptr, special_ptr):
         """shard_finish without the copies: the engine refers to the caller's buffers."""
         vp = lambda a: C.c_void_p(a) if a else None

@@ -401,6 +401,69 @@ def build_sharded_direct(engine, results, sasamplingrate=32, isasamplingrate=262
     return True
 
 
+class XRecs:
+    """The record arrays of a position-sharded build (b3m_engine_xshard_*): every rank owns one, sized for its key
+    range, and maps all the others through CUDA IPC, so that the scatter kernel of rank p stores a record of rank
+    q's key range straight into q's HBM."""
+
+    def __init__(self, engine, rank, world, mem=None):
+        from .engine import DeviceMemory
+        n = engine.info()["n"]
+        self.n, self.rank, self.world = n, rank, world
+        self.cap = n // world + n // (4 * world) + (1 << 22)
+        self.mem = mem or DeviceMemory(engine.device)
+        self.own = self.mem.alloc(8 * self.cap)
+        handles = [None] * world
+        if world > 1:
+            dist.all_gather_object(handles, self.mem.export(self.own))
+        self.ptrs = [self.own if q == rank else self.mem.open(handles[q]) for q in range(world)]
+
+    def close(self):
+        for q, p in enumerate(self.ptrs):
+            (self.mem.free if q == self.rank else self.mem.close)(p)
+        self.ptrs = []
+
+
+def build_xsharded(engine, results, xrecs, sasamplingrate=32, isasamplingrate=262144, bwtonly=False, device=None):
+    """Position-sharded build: every rank counts and scatters 1/world of the text positions,
+    the records cross NVLink as the stores of the scatter kernel, every rank then sorts its own key range and stores
+    its outputs into rank 0's buffers (DirectResults).  Collectives: one all-gather of the bin counts (16 KiB per
+    rank), one all-reduce as the fence between scatter and sort, one all-reduce as vote + fence at the end.
+    Returns None when the path does not apply to the text (the caller uses build_sharded_direct), False when the
+    text needs the general path (block merge tree), True when rank 0's engine holds the results."""
+    from .engine import B3MError
+    rank, world = results.rank, results.world
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    tot = torch.zeros(2048, dtype=torch.int64, device=device)
+    nb = engine.xshard_count(rank, world, tot.data_ptr(), preisarate=results.prerate, sasamplingrate=sasamplingrate,
+                             isasamplingrate=isasamplingrate, bwtonly=bwtonly)
+    if nb == 0:
+        return None
+    allt = torch.empty(world * 2048, dtype=torch.int64, device=device)
+    if world > 1:
+        dist.all_gather_into_tensor(allt, tot)
+    else:
+        allt.copy_(tot)
+    h = allt.cpu().numpy().view(np.uint64).reshape(world, 2048)[:, :nb]
+    try:
+        engine.xshard_scatter(h, xrecs.ptrs, [xrecs.cap] * world)
+    except B3MError:
+        return None  # a key range too large for its array: decided from the same counts on every rank
+    fence = torch.zeros(1, dtype=torch.int64, device=device)
+    if world > 1:
+        dist.all_reduce(fence, op=dist.ReduceOp.SUM)  # every rank's records have landed before anyone sorts
+    unres = engine.xshard_finish(xrecs.own, *results.ptrs())
+    if world > 1:
+        flag = torch.tensor([unres], dtype=torch.int64, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.SUM)
+        unres = int(flag.item())
+    if unres != 0:
+        return False
+    if rank == 0:
+        engine.shard_adopt(world, *results.ptrs())
+    return True
+
+
 def build_distributed(engine, local_blocks=1, preisarate=0, sasamplingrate=32, isasamplingrate=262144, bwtonly=False,
                       largelcpthres=16384, driver=None, strategy="auto"):
     """Every rank has loaded the same text into `engine`; after the call rank 0's engine holds the
@@ -424,7 +487,18 @@ def build_distributed(engine, local_blocks=1, preisarate=0, sasamplingrate=32, i
                 if res is None:
                     res = DirectResults(engine, preisarate, sasamplingrate, isasamplingrate, bwtonly, dist.get_rank(), dist.get_world_size())
                 state["direct"] = res
-                ok = build_sharded_direct(engine, res, sasamplingrate, isasamplingrate, bwtonly)
+                ok = None
+                if hasattr(engine, "xshard_count") and dist.get_world_size() <= 16 and os.environ.get("B3M_SHARD_BINS", "0") != "1":
+                    xr = state.get("xrecs")
+                    if xr is not None and xr.n != key[0]:
+                        xr.close()
+                        xr = None
+                    if xr is None:
+                        xr = XRecs(engine, dist.get_rank(), dist.get_world_size())
+                    state["xrecs"] = xr
+                    ok = build_xsharded(engine, res, xr, sasamplingrate, isasamplingrate, bwtonly)
+                if ok is None:
+                    ok = build_sharded_direct(engine, res, sasamplingrate, isasamplingrate, bwtonly)
             else:
                 ok, state["shard"] = build_sharded(engine, preisarate, sasamplingrate, isasamplingrate, bwtonly, buffers=state["shard"])
             torch.cuda.current_stream().synchronize()

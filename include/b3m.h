@@ -284,6 +284,24 @@ int b3m_engine_unpack_rows(b3m_engine * e, const void * d_packed, uint64_t nrows
 int b3m_engine_shard_finish(b3m_engine * e, const void * d_bwt, const void * d_prerank, const void * d_sa, const void * d_isa,
                             const void * d_special, uint32_t nparts);
 
+/* ---- multi-GPU driver, position sharding of the first sorting level (alphabets of at most four codes) -------
+ * The scalable form of the sharded build: nothing is computed on the whole text by every GPU.  Part p
+ *   1. b3m_engine_xshard_count: counts, for ITS range of text positions, how many suffixes start with each value of
+ *      their leading bits (*nbins values in d_totals, device; *nbins = 0: the sorter does not apply to this text, use
+ *      b3m_engine_shard_build).  The caller exchanges the counts (all-gather, nparts * nbins values);
+ *   2. b3m_engine_xshard_scatter: builds the sort records of its positions and stores every record straight into the
+ *      record array of the part that owns the record's key range -- d_recs[q] is part q's array as mapped HERE (for
+ *      q != p a CUDA IPC peer mapping: the records cross NVLink as the stores of the scatter kernel), caps[q] its
+ *      capacity in 8-byte records (about n / nparts * 1.25).  all_totals: host, [nparts][nbins].  Fails (on every
+ *      part alike) when a key range does not fit.  The caller then synchronises the parts (any collective);
+ *   3. b3m_engine_xshard_finish: sorts its own key range (d_recs_own = d_recs[p]) and emits BWT rows, anchors and
+ *      samples at their global places as b3m_engine_shard_build does.
+ * b3m_engine_shard_rows / _shard_finish / _shard_adopt apply afterwards.  Build parameters are those of step 1. */
+int b3m_engine_xshard_count(b3m_engine * e, uint32_t part, uint32_t nparts, const b3m_build_params * p, void * d_totals, uint32_t * nbins);
+int b3m_engine_xshard_scatter(b3m_engine * e, const uint64_t * all_totals, void * const * d_recs, const uint64_t * caps);
+int b3m_engine_xshard_finish(b3m_engine * e, void * d_recs_own, void * d_bwt, void * d_prerank, void * d_sa, void * d_isa, void * d_special,
+                             uint64_t * unresolved);
+
 /* the same without the copies: the engine refers to the caller's buffers, which must stay valid (and unchanged)
  * until the engine's next load or build */
 int b3m_engine_shard_adopt(b3m_engine * e, const void * d_bwt, const void * d_prerank, const void * d_sa, const void * d_isa,
