@@ -90,3 +90,47 @@ def test_cfg4_repetitive_tenth_size():
     prefix-doubling rounds and the large-LCP block path must agree with the direct sampling."""
     info = _run("cfg4", 0.1, picks=400, depth=40000)
     assert info["sort_unresolved0"] > 0 and info["sort_rounds"] > 4
+
+
+def _oracle_checkbwt_full(workload, oracle):
+    """The reference's own verifier (checkbwt, /root/reference/src/checkbwt.cpp:126-243, restated in
+    oracle/b3m_oracle.c:orc_checkbwt) on the GPU's BWT + (rank,pos) anchors at the FULL size of the config:
+    an LF walk over the whole BWT on the host cores that compares every symbol with the circularly reversed
+    text and must arrive at every anchor's rank -- a complete proof of the symbol stream."""
+    import os
+    import torch
+    from bwtb3m_b200 import Engine, workloads
+    free, _ = torch.cuda.mem_get_info()
+    itype, data, nsym = workloads.make(workload, 1.0)
+    if free < 36 * nsym + (2 << 30):
+        pytest.skip("not enough free device memory for %s" % workload)
+    eng = Engine(0)
+    try:
+        eng.load_host(data, itype)
+        eng.build()
+        info = eng.info()
+        res = eng.fetch()
+    finally:
+        eng.close()
+    text = oracle.decode_pac(data.tobytes(), term=True) if itype == "pacterm" else np.ascontiguousarray(data)
+    n = info["n"]
+    assert text.size == n and res["bwt"].size == n
+    rc, checked = oracle.checkbwt(text, res["bwt"], res["preisa"], numthreads=os.cpu_count() or 8)
+    assert rc == 1, "the reference's verifier rejects the GPU BWT of %s" % workload
+    assert checked == n
+    return info
+
+
+def test_cfg3_full_size_oracle_checkbwt(oracle):
+    info = _oracle_checkbwt_full("cfg3", oracle)
+    assert info["n"] == 3_100_000_001
+
+
+def test_cfg5_full_size_oracle_checkbwt(oracle):
+    info = _oracle_checkbwt_full("cfg5", oracle)
+    assert info["n"] == 1_000_000_000 and info["sigma"] == 256
+
+
+def test_cfg4_full_size_oracle_checkbwt(oracle):
+    info = _oracle_checkbwt_full("cfg4", oracle)
+    assert info["n"] == 3_200_000_001 and info["sort_unresolved0"] > 0
