@@ -4,7 +4,7 @@ CXX  := /usr/bin/g++
 ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := -std=c++17 -O3 -lineinfo --extended-lambda $(ARCH) -ccbin $(CXX) -Xcompiler -fPIC,-Wall,-Wno-unused-function,-Wno-free-nonheap-object -Iinclude
 CSRC := bwtb3m_b200/csrc
-OBJS := $(CSRC)/engine.o $(CSRC)/sufsort.o $(CSRC)/stages.o $(CSRC)/blocks.o $(CSRC)/rlencode.o $(CSRC)/formats.o $(CSRC)/hostapi.o
+OBJS := $(CSRC)/engine.o $(CSRC)/sufsort.o $(CSRC)/stages.o $(CSRC)/blocks.o $(CSRC)/rlencode.o $(CSRC)/formats.o $(CSRC)/hostapi.o $(CSRC)/multi.o
 LIB  := bwtb3m_b200/libb3m.so
 BINS := $(patsubst cli/%.cpp,bin/%,$(wildcard cli/*.cpp))
 

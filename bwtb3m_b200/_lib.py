@@ -44,7 +44,7 @@ class Options(C.Structure):
         ("sasamplingrate", C.c_uint64), ("isasamplingrate", C.c_uint64), ("mem", C.c_uint64),
         ("numthreads", C.c_uint64), ("bwtonly", C.c_int), ("tmpprefix", C.c_char_p),
         ("sparsetmpprefix", C.c_char_p), ("copyinputtomemory", C.c_int), ("largelcpthres", C.c_uint64),
-        ("verbose", C.c_int), ("device", C.c_int), ("numblocks", C.c_uint64),
+        ("verbose", C.c_int), ("device", C.c_int), ("numblocks", C.c_uint64), ("ngpus", C.c_int),
     ]
 
 
@@ -67,6 +67,7 @@ EXPORTS = [
     "b3m_engine_default_preisarate", "b3m_engine_fetch_bwa",
     "b3m_engine_shard_build", "b3m_engine_shard_finish", "b3m_engine_shard_rows", "b3m_engine_pack_rows", "b3m_engine_unpack_rows",
     "b3m_engine_shard_adopt", "b3m_engine_xshard_count", "b3m_engine_xshard_scatter", "b3m_engine_xshard_finish", "b3m_dev_alloc", "b3m_dev_free", "b3m_ipc_export", "b3m_ipc_open", "b3m_ipc_close",
+    "b3m_multi_create", "b3m_multi_destroy", "b3m_multi_last_error", "b3m_multi_load_host", "b3m_multi_build", "b3m_multi_engine", "b3m_multi_stats",
 ]
 
 _lib = None
@@ -112,6 +113,16 @@ def lib():
     L.b3m_ipc_export.argtypes = [C.c_int, vp, C.c_char_p, C.c_char_p, C.c_size_t]
     L.b3m_ipc_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(vp), C.c_char_p, C.c_size_t]
     L.b3m_ipc_close.argtypes = [C.c_int, vp, C.c_char_p, C.c_size_t]
+    L.b3m_multi_create.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(vp), C.c_char_p, C.c_size_t]
+    L.b3m_multi_destroy.argtypes = [vp]
+    L.b3m_multi_destroy.restype = None
+    L.b3m_multi_last_error.argtypes = [vp]
+    L.b3m_multi_last_error.restype = C.c_char_p
+    L.b3m_multi_load_host.argtypes = [vp, vp, u64, C.c_int]
+    L.b3m_multi_build.argtypes = [vp, C.POINTER(BuildParams)]
+    L.b3m_multi_engine.argtypes = [vp, C.c_int]
+    L.b3m_multi_engine.restype = vp
+    L.b3m_multi_stats.argtypes = [vp, C.c_char_p, C.c_size_t, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.b3m_engine_shard_rows.argtypes = [vp, C.c_uint32, u64p]
     L.b3m_engine_pack_rows.argtypes = [vp, vp, u64, vp]
     L.b3m_engine_unpack_rows.argtypes = [vp, vp, u64, vp]

@@ -575,7 +575,6 @@ void Engine::blk_finish(const void * d_L_root, uint32_t term_root, uint64_t q_lo
 } // namespace b3m
 
 // ---- C ABI ----------------------------------------------------------------------------------
-struct b3m_engine { b3m::Engine * e; std::string err; };
 #define B3M_GUARD(h, ...)                                                    \
 	if (!(h)) return 1;                                                      \
 	try { __VA_ARGS__; (h)->err.clear(); return 0; }                                \

@@ -795,7 +795,6 @@ void Engine::lf_bench(uint64_t nchains, uint64_t steps, float * ms, uint64_t * c
 // ------------------------------------------------------------------------------------------
 using b3m::Engine;
 
-struct b3m_engine { b3m::Engine * e; std::string err; };
 
 static void set_err(char * err, size_t errlen, const char * msg) {
 	if (err && errlen) { strncpy(err, msg, errlen - 1); err[errlen - 1] = 0; }

@@ -145,3 +145,6 @@ struct Engine {
 };
 
 } // namespace b3m
+
+// the C ABI's engine handle (include/b3m.h)
+struct b3m_engine { b3m::Engine * e; std::string err; };

@@ -10,6 +10,7 @@
 #include <unistd.h>
 #include <algorithm>
 #include <thread>
+#include <memory>
 
 using namespace b3m;
 
@@ -81,6 +82,7 @@ void b3m_options_init(b3m_options * o) {
 	o->verbose = 0;
 	o->device = 0;
 	o->numblocks = 0;
+	o->ngpus = 1;
 }
 
 int b3m_compute_bwt(const b3m_options * o, b3m_result * res, char * err, size_t errlen) {
@@ -100,8 +102,24 @@ int b3m_compute_bwt(const b3m_options * o, b3m_result * res, char * err, size_t 
 
 		PinnedFile in(o->fn);
 		if (verbose) fprintf(stderr, "[V] read %llu bytes from %s in %.3f s\n", (unsigned long long)in.n, o->fn, now_sec() - t0);
-		Engine e(o->device, nullptr);
-		e.load(in.p, in.n, itype, false);
+		// ngpus > 1: the GPUs device .. device+ngpus-1 of this box share the build (multi.cu); engine 0 ends up with the results
+		int const ngpus = o->ngpus > 1 ? o->ngpus : 1;
+		struct MultiHolder { b3m_multi * m = nullptr; ~MultiHolder() { b3m_multi_destroy(m); } } mh;
+		std::unique_ptr<Engine> single;
+		Engine * ep = nullptr;
+		if (ngpus > 1) {
+			std::vector<int> devs(ngpus);
+			for (int i = 0; i < ngpus; ++i) devs[i] = o->device + i;
+			char merr[512] = {0};
+			if (b3m_multi_create(ngpus, devs.data(), &mh.m, merr, sizeof(merr))) throw Error(merr);
+			if (b3m_multi_load_host(mh.m, in.p, in.n, itype)) throw Error(b3m_multi_last_error(mh.m));
+			ep = b3m_multi_engine(mh.m, 0)->e;
+		} else {
+			single.reset(new Engine(o->device, nullptr));
+			single->load(in.p, in.n, itype, false);
+			ep = single.get();
+		}
+		Engine & e = *ep;
 		uint64_t const n = e.T.n;
 
 		// block size: the whole text is one block when its working set fits the memory target;
@@ -125,7 +143,14 @@ int b3m_compute_bwt(const b3m_options * o, b3m_result * res, char * err, size_t 
 		p.largelcpthres = o->largelcpthres ? o->largelcpthres : 16384;
 		if (verbose) fprintf(stderr, "[V] n=%llu sigma=%u numblocks=%llu (memory target %llu MiB)\n", (unsigned long long)n, e.T.sigma + (e.T.has_term ? 1 : 0),
 		                     (unsigned long long)numblocks, (unsigned long long)(target >> 20));
-		e.build(p);
+		if (ngpus > 1) {
+			if (b3m_multi_build(mh.m, &p)) throw Error(b3m_multi_last_error(mh.m));
+			if (verbose) {
+				char strat[64]; double msl = 0, msb = 0;
+				b3m_multi_stats(mh.m, strat, sizeof(strat), &msl, &msb);
+				fprintf(stderr, "[V] %d GPUs: load %.3f ms, build %.3f ms, strategy %s\n", ngpus, msl, msb, strat);
+			}
+		} else e.build(p);
 		b3m_info info;
 		e.info(&info);
 		if (verbose)

@@ -258,3 +258,65 @@ class DeviceMemory:
 
     def close(self, ptr):
         self._call(self._lib.b3m_ipc_close, self.device, C.c_void_p(ptr))
+
+
+class MultiEngine:
+    """The multi-GPU build inside one process (C ABI b3m_multi_*, what `ngpus=` of bwtb3m selects): `ngpus`
+    engines, one host thread per GPU inside libb3m.so.  After build() the results are read through
+    `self.engine` (GPU 0's engine): fetch / fetch_bwa / write_bwt / info as after a single-GPU build."""
+
+    def __init__(self, ngpus, devices=None):
+        self._lib = lib()
+        h = C.c_void_p()
+        err = C.create_string_buffer(1024)
+        devs = (C.c_int * ngpus)(*devices) if devices is not None else None
+        rc = self._lib.b3m_multi_create(ngpus, devs, C.byref(h), err, 1024)
+        if rc != 0:
+            raise B3MError(err.value.decode() or "b3m_multi_create failed (%d)" % rc)
+        self._h = h
+        self.ngpus = ngpus
+        # a non-owning view of engine 0
+        self.engine = Engine.__new__(Engine)
+        self.engine._lib = self._lib
+        self.engine._h = None
+        self.engine._view = C.c_void_p(self._lib.b3m_multi_engine(self._h, 0))
+        self.engine.device = devices[0] if devices is not None else 0
+        self.engine.stream_ptr = 0
+        self.engine._h = self.engine._view
+        self.engine.close = lambda: None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.engine._h = None
+            self._lib.b3m_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise B3MError(self._lib.b3m_multi_last_error(self._h).decode())
+
+    def load_host(self, data, inputtype="bytestream"):
+        a = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, dtype=np.uint8)
+        self._keep = a
+        self._check(self._lib.b3m_multi_load_host(self._h, C.c_void_p(a.ctypes.data), a.size, INPUT_TYPES[inputtype]))
+
+    def load_host_ptr(self, ptr, nbytes, inputtype="bytestream"):
+        self._check(self._lib.b3m_multi_load_host(self._h, C.c_void_p(ptr), nbytes, INPUT_TYPES[inputtype]))
+
+    def build(self, numblocks=1, preisarate=0, sasamplingrate=32, isasamplingrate=262144, bwtonly=False,
+              largelcpthres=16384, sampling="auto", sortpath="auto"):
+        p = BuildParams(numblocks, preisarate, sasamplingrate, isasamplingrate, 1 if bwtonly else 0, largelcpthres,
+                        {"auto": 0, "walk": 1}[sampling], None, None, SORTPATHS[sortpath])
+        self._check(self._lib.b3m_multi_build(self._h, C.byref(p)))
+
+    def stats(self):
+        s = C.create_string_buffer(128)
+        a, b = C.c_double(0), C.c_double(0)
+        self._check(self._lib.b3m_multi_stats(self._h, s, 128, C.byref(a), C.byref(b)))
+        return {"strategy": s.value.decode(), "ms_load": a.value, "ms_build": b.value}

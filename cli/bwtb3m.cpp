@@ -50,6 +50,7 @@ int main(int argc, char ** argv) {
 			str << "verbose=[" << o.verbose << "] (verbosity level)\n";
 			str << "device=[0] (CUDA device)\n";
 			str << "numblocks=[0] (0: derive from mem; >0: force the number of blocks)\n";
+			str << "ngpus=[1] (GPUs of this box sharing the build: devices device .. device+ngpus-1)\n";
 			throw std::runtime_error(str.str());
 		}
 		std::string const fn = arg.rest[0];
@@ -72,6 +73,7 @@ int main(int argc, char ** argv) {
 		o.verbose = (int)arg.getu("verbose", 0);
 		o.device = (int)arg.getu("device", 0);
 		o.numblocks = arg.getu("numblocks", 0);
+		o.ngpus = (int)arg.getu("ngpus", 1);
 		b3m_result res;
 		char err[2048] = "";
 		if (b3m_compute_bwt(&o, &res, err, sizeof(err)) != 0) throw std::runtime_error(err);

@@ -58,6 +58,9 @@ typedef struct b3m_options {
 	/* additions of this implementation */
 	int device;                   /* CUDA device ordinal, default 0 */
 	uint64_t numblocks;           /* 0: derive from mem (one block if it fits); >0: force */
+	int ngpus;                    /* GPUs of this box the build spreads over (devices device .. device+ngpus-1, which must be
+	                               * NVLink / PCIe peers); 0 or 1: one GPU.  The reference scales the same call with numthreads
+	                               * (/root/reference/src/bwtb3m.cpp:48-50); see b3m_multi_* below */
 } b3m_options;
 
 /* Mirrors libmaus2::suffixsort::bwtb3m::BwtMergeSortResult
@@ -317,6 +320,29 @@ int b3m_dev_free(int device, void * dptr, char * err, size_t errlen);
 int b3m_ipc_export(int device, const void * dptr, void * handle64, char * err, size_t errlen);
 int b3m_ipc_open(int device, const void * handle64, void ** dptr, char * err, size_t errlen);
 int b3m_ipc_close(int device, void * dptr, char * err, size_t errlen);
+
+/* ---- multi-GPU build inside ONE process (what `ngpus` of b3m_options / of the bwtb3m command line selects) ----
+ * ngpus engines, one host thread per GPU, peer access between all of them; no NCCL and no second process.
+ * Replaces the same BwtMergeSort::computeBwt call (/root/reference/src/bwtb3m.cpp:62-63), whose own scaling knob is
+ * numthreads (/root/reference/src/bwtb3m.cpp:48-50).
+ *   b3m_multi_load_host  every GPU uploads 1/ngpus of the input over its own PCIe link, the pieces are exchanged by
+ *                        peer copies (NVLink), every GPU decodes the text (K1);
+ *   b3m_multi_build      position-sharded sort (b3m_engine_xshard_*; alphabets of more than four codes: key ranges,
+ *                        b3m_engine_shard_build) with every GPU storing its BWT rows, anchors and samples into GPU 0's
+ *                        buffers; numblocks > 1, sampling = WALK and texts with repeats beyond the sort keys are built
+ *                        by GPU 0 alone (the general path).  Same results as b3m_engine_build, bit for bit.
+ * Afterwards b3m_multi_engine(m, 0) holds the results: fetch / fetch_bwa / write_bwt / info as after b3m_engine_build.
+ * devices: ngpus ordinals, or NULL for 0 .. ngpus-1. */
+typedef struct b3m_multi b3m_multi;
+int b3m_multi_create(int ngpus, const int * devices, b3m_multi ** out, char * err, size_t errlen);
+void b3m_multi_destroy(b3m_multi * m);
+const char * b3m_multi_last_error(const b3m_multi * m);
+int b3m_multi_load_host(b3m_multi * m, const void * input, uint64_t nbytes, int inputtype);
+int b3m_multi_build(b3m_multi * m, const b3m_build_params * p);
+b3m_engine * b3m_multi_engine(b3m_multi * m, int i);
+/* what the last load / build did: strategy = "xshard" | "shard" | "single" | "single (text with long repeats)";
+ * host wall-clock milliseconds of the two calls */
+int b3m_multi_stats(b3m_multi * m, char * strategy, size_t len, double * ms_load, double * ms_build);
 
 /* LF-steps/s instrument on the dictionary of the last build: nchains dependent LF chains of
  * `steps` steps each, started at evenly spaced sampled ranks; returns elapsed device ms.
