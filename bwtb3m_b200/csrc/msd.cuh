@@ -461,17 +461,50 @@ __device__ __forceinline__ void msd_run_place(const uint16_t * __restrict__ row0
 	done += ctot;
 }
 
+// ---- mbarrier + bulk async copy (TMA, 1-D) --------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(mbar), "r"(count) : "memory");
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t mbar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+	uint32_t ok;
+	do {
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+		             : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+	} while (!ok);
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completion is counted on the mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void * src, uint32_t bytes, uint32_t mbar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             :: "r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+
+constexpr int MSD_WIN = 3;                          // sentinel slots on either side of the sorted records
+constexpr int MSD_FIN_SMEM = 32 + (MSD_CAP + 4) * 8 + MSD_CAP + 16 + (1 << MSD_LBITS_MAX) * 4;
+
+// Shared memory: 32 B (front sentinels) | rec[MSD_CAP + 4] | s_bwt[MSD_CAP] | 16 B (cnt[-1] = 0) | cnt[2^lb]
+// Steps: (1) every run of the sub-bucket arrives by ONE bulk async copy issued by the thread that owns its
+// descriptor, all counted on one mbarrier; (2) local digit: count with shared-memory atomics, scan, then a
+// second atomic on the scanned table hands every record its slot (no rank kept in registers); afterwards bin d
+// is rec[cnt[d-1] .. cnt[d]); (3) order inside a bin: the bins hold 0.7 records on average, so a record
+// compares itself with its neighbours at distance 1 and 2 (the array is sorted by digit: a later record with a
+// smaller key, or an earlier one with a larger key, is in the same bin) and checks that the bin ends within
+// distance 2 on both sides; records with an equal neighbour or a longer bin take the general path (bin bounds
+// from the table, second keys from the text, unresolved groups); (4) emit as before.
 template <bool FUSED, bool ORDER>
 __global__ void __launch_bounds__(MSD_THREADS, 2)
-k_msd_finish(MsdFin A) {
+k_msd_finish(const __grid_constant__ MsdFin A) {
 	extern __shared__ __align__(16) uint8_t msd_dyn[];
-	unsigned long long * const rec = reinterpret_cast<unsigned long long *>(msd_dyn);   // MSD_CAP
-	uint8_t * const s_bwt = msd_dyn + (size_t)MSD_CAP * 8;                                 // MSD_CAP
-	uint32_t * const cnt = reinterpret_cast<uint32_t *>(msd_dyn + (size_t)MSD_CAP * 9);    // 2^MSD_LBITS_MAX + 1
+	unsigned long long * const rec = reinterpret_cast<unsigned long long *>(msd_dyn + 32);             // MSD_CAP + 4
+	uint8_t * const s_bwt = msd_dyn + 32 + (size_t)(MSD_CAP + 4) * 8;                                  // MSD_CAP
+	uint32_t * const cnt = reinterpret_cast<uint32_t *>(s_bwt + MSD_CAP + 16);                         // cnt[-1 .. 2^lb)
 	__shared__ uint32_t wsum[MSD_THREADS / 32];
-	__shared__ uint32_t r_src[MSD_THREADS];                       // per run of a chunk of tiles: first 16-byte aligned record,
-	__shared__ uint16_t r_off[MSD_THREADS], r_n[MSD_THREADS];     // its place in rec[], its length in 16-byte pieces
+	__shared__ uint32_t s_sa[MSD_THREADS];                        // sampled SA of this CTA's rows (at most MSD_CAP / 32)
 	__shared__ uint32_t s_cnt[4];
+	__shared__ __align__(8) unsigned long long s_mbar;
 	// linear windows: the suffixes shorter than the prefix an unresolved group shares (at most 16 in the whole text)
 	__shared__ uint32_t s_sh_e[16], s_sh_L[16], s_nshort;
 	unsigned const nb2 = 1u << A.b2;
@@ -487,9 +520,9 @@ k_msd_finish(MsdFin A) {
 	unsigned const lane = threadIdx.x & 31;
 	if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
 	if (threadIdx.x == 0) s_nshort = 0;
-	__syncthreads();
 
 	if ((uint64_t)m + 2ull * ntp > (uint64_t)MSD_CAP) {
+		__syncthreads();
 		// too large for one CTA: the whole sub-bucket stays one unresolved group sharing h2 symbols.  The
 		// suffixes of a linear window that end inside those symbols are no members of it: they are smaller
 		// than the rest, shorter first, and are placed in front (a group must share REAL symbols, the
@@ -536,29 +569,29 @@ k_msd_finish(MsdFin A) {
 		return;
 	}
 
-	// ---- gather the runs of this sub-bucket with 16-byte cp.async: a run is widened to 16-byte boundaries,
-	//      the (at most two) records of neighbouring runs this drags in are overwritten with MSD_PAD afterwards ----
-	unsigned const gsz = 1u << A.glog, gl = threadIdx.x & (gsz - 1u), grp = threadIdx.x >> A.glog, ngrp = MSD_THREADS >> A.glog;
-	uint32_t const rec_s = (uint32_t)__cvta_generic_to_shared(rec);
+	// local digit: about two bins per record
+	unsigned lb = 32u - (unsigned)__clz((int)(2u * m - 1u)); // ceil(log2(2m))
+	lb = lb < (unsigned)MSD_LBITS_MIN ? (unsigned)MSD_LBITS_MIN : (lb > (unsigned)MSD_LBITS_MAX ? (unsigned)MSD_LBITS_MAX : lb);
+	unsigned const nlb = 1u << lb;
+	unsigned const dsh = 30u - A.b2 - lb;  // the local digit follows the b2 bits of level 2 inside key30: bits [dsh, dsh + lb) of a record's upper word
+
+	// ---- (1) gather: one bulk copy per run (a run is widened to 16-byte boundaries, the at most two records of
+	//      neighbouring runs this drags in are overwritten with MSD_PAD afterwards); the table is cleared meanwhile ----
+	uint32_t const rec_s = (uint32_t)__cvta_generic_to_shared(rec), mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+	if (threadIdx.x == 0) mbar_init(mbar, (ntp + MSD_THREADS - 1) / MSD_THREADS);
+	__syncthreads();
 	uint32_t mpad = 0; // records in rec[], padding included
 	uint32_t g0 = 0, g1 = 0, a0, plen = 0, off = 0;
 	for (uint32_t k0 = 0; k0 < ntp; k0 += MSD_THREADS) {
+		uint32_t const before = mpad;
 		msd_run_place(row0, row1, pstart, ntp, k0, wsum, mpad, g0, g1, a0, plen, off);
-		r_src[threadIdx.x] = a0;
-		r_off[threadIdx.x] = (uint16_t)off;
-		r_n[threadIdx.x] = (uint16_t)(plen >> 1);
-		__syncthreads();
-		uint32_t const nr = ntp - k0 < (uint32_t)MSD_THREADS ? ntp - k0 : (uint32_t)MSD_THREADS;
-		for (uint32_t q = grp; q < nr; q += ngrp) {
-			uint32_t const n16 = r_n[q];
-			const unsigned long long * const src = A.recs + r_src[q];
-			uint32_t const dst = rec_s + 8u * r_off[q];
-			for (uint32_t x = gl; x < n16; x += gsz)
-				asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + 16u * x), "l"(src + 2 * x) : "memory");
-		}
+		if (plen) bulk_g2s(rec_s + 8u * off, A.recs + a0, plen * 8u, mbar);
+		if (threadIdx.x == 0) mbar_arrive_expect_tx(mbar, (mpad - before) * 8u);
 	}
-	asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-	__syncthreads();
+	for (unsigned i = threadIdx.x; i < nlb; i += MSD_THREADS) cnt[i] = 0;
+	if (threadIdx.x < 4) cnt[(int)threadIdx.x - 4] = 0;
+	if (threadIdx.x < (unsigned)MSD_WIN) rec[-1 - (int)threadIdx.x] = 0ull; // front sentinels: smaller than every key
+	mbar_wait(mbar, 0);
 	// the records dragged in from neighbouring runs become padding (several chunks of tiles: one more walk over the descriptors)
 	if (ntp <= (uint32_t)MSD_THREADS) {
 		if (plen) {
@@ -575,44 +608,36 @@ k_msd_finish(MsdFin A) {
 			}
 		}
 	}
-	// local digit: about two bins per record
-	unsigned lb = 32u - (unsigned)__clz((int)(2u * m - 1u)); // ceil(log2(2m))
-	lb = lb < (unsigned)MSD_LBITS_MIN ? (unsigned)MSD_LBITS_MIN : (lb > (unsigned)MSD_LBITS_MAX ? (unsigned)MSD_LBITS_MAX : lb);
-	unsigned const nlb = 1u << lb;
-	for (unsigned i = threadIdx.x; i <= nlb; i += MSD_THREADS) cnt[i] = 0;
 	__syncthreads();
 
-	// ---- local digit: rank by atomics, scan, permute in place through registers ----
-	unsigned const lsh = 62u - A.b2 - lb; // the local digit follows the b2 bits of level 2 inside key30
+	// ---- (2) local digit: count, scan, hand out the slots; the records pass through registers ----
 	{
 		unsigned long long r[MSD_ITEMS];
-		uint32_t dr[MSD_ITEMS];
 		uint32_t const shortlim = A.lin ? W32 - 18u : 0xffffffffu; // suffixes behind this position may be too short for a group
 		bool anyshort = false;
 		#pragma unroll
 		for (int j = 0; j < MSD_ITEMS; ++j) {
-			dr[j] = 0xffffffffu;
+			r[j] = MSD_PAD;
 			if ((uint32_t)(j * MSD_THREADS) < mpad) { // uniform: whole iterations are skipped
 				uint32_t const s = j * MSD_THREADS + threadIdx.x;
-				if (s < mpad) {
-					r[j] = rec[s];
-					if (r[j] != MSD_PAD) {
-						uint32_t const dg = (uint32_t)(r[j] >> lsh) & (nlb - 1u);
-						dr[j] = (dg << 16) | atomicAdd(&cnt[dg], 1u);
-						anyshort |= (uint32_t)r[j] > shortlim;
-					}
+				if (s < mpad) r[j] = rec[s];
+				if ((uint32_t)r[j] != 0xffffffffu) { // a record's index is below 2^32 - 256
+					atomicAdd(&cnt[((uint32_t)(r[j] >> 32) >> dsh) & (nlb - 1u)], 1u);
+					anyshort |= (uint32_t)r[j] > shortlim;
 				}
 			}
 		}
 		if (anyshort) s_nshort = 0x80000000u; // the list is made below
 		__syncthreads();
 		msd_scan_bins_wide<MSD_THREADS>(cnt, nlb, wsum);
-		if (threadIdx.x == 0) cnt[nlb] = m;
 		#pragma unroll
 		for (int j = 0; j < MSD_ITEMS; ++j)
-			if ((uint32_t)(j * MSD_THREADS) < mpad && dr[j] != 0xffffffffu) rec[cnt[dr[j] >> 16] + (dr[j] & 0xffffu)] = r[j];
+			if ((uint32_t)(j * MSD_THREADS) < mpad && (uint32_t)r[j] != 0xffffffffu)
+				rec[atomicAdd(&cnt[((uint32_t)(r[j] >> 32) >> dsh) & (nlb - 1u)], 1u)] = r[j];
+		if (threadIdx.x < (unsigned)MSD_WIN) rec[m + threadIdx.x] = (unsigned long long)MSD_KEYMASK << 32; // back sentinels: no key is larger
 		__syncthreads();
 	}
+	// now bin dg = rec[cnt[dg - 1] .. cnt[dg]), cnt[-1] = 0
 
 	// crowded local digits stay unresolved groups sharing hbig symbols: list the suffixes too short for that
 	uint32_t const hbig = (A.b1 + A.b2 + lb) >> 1; // at most 16
@@ -626,72 +651,76 @@ k_msd_finish(MsdFin A) {
 		}
 		__syncthreads();
 	}
-	// ---- order inside a local digit by comparison; emit ----
-	// sampled SA through shared memory when a CTA holds at most 512 samples (the gather's descriptors are dead by now)
+	// ---- (3) order inside a bin, (4) emit ----
+	// sampled SA through shared memory when a CTA holds at most 512 samples
 	bool const stage_sa = FUSED && A.fo.sa_s && A.fo.salog >= 5 && A.fo.salog < 32;
-	uint32_t * const s_sa = r_src;
-	uint32_t const r_first = stage_sa ? ((o0 + (uint32_t)A.fo.shift + A.rmask) & ~A.rmask) : 0u; // first sampled rank of this CTA
+	uint32_t const rshift = (uint32_t)A.fo.shift + o0;
+	uint32_t const r_first = stage_sa ? ((rshift + A.rmask) & ~A.rmask) : 0u; // first sampled rank of this CTA
 	unsigned const skip = (A.b1 + 30u) >> 1; // symbols covered by b1 + key30
 	uint32_t ntied = 0, nunres = 0, ngather = 0, flags = 0;
+	const uint32_t * const rh = reinterpret_cast<const uint32_t *>(rec) + 1; // upper word of slot y: rh[2 * y]
 	#pragma unroll 1
 	for (uint32_t s = threadIdx.x; s < m; s += MSD_THREADS) {
 		unsigned long long const me = rec[s];
-		uint32_t const mk = (uint32_t)(me >> 32) & MSD_KEYMASK;
-		uint32_t const dg = (uint32_t)(me >> lsh) & (nlb - 1u);
-		uint32_t const a = cnt[dg], b = cnt[dg + 1];
-		uint32_t f = a, hf = 1;
-		if (b - a > (uint32_t)MSD_MAXRUN) {
-			// one unresolved group; the listed short suffixes of this digit go in front of it, shorter first
-			uint32_t const ns = s_nshort, myL = W32 - (uint32_t)me;
-			uint32_t nsb = 0, before = 0, smaller = 0;
-			for (uint32_t q = 0; q < ns; ++q) {
-				uint32_t const e = s_sh_e[q];
-				if (e >= a && e < b) { ++nsb; before += e < s ? 1u : 0u; smaller += s_sh_L[q] < myL ? 1u : 0u; }
-			}
-			if (A.lin && myL < hbig) { f = a + smaller; hf = 1; }
-			else { f = s + nsb - before; hf = (s - a == before) ? 1u : 0u; ++nunres; flags |= 1u; }
-		} else if (b - a > 1) {
-			// the key halves of the records of this digit, four loads in flight (most digits hold at most four records)
-			uint32_t less = 0, eq = 0;
-			const uint32_t * const kh = reinterpret_cast<const uint32_t *>(rec) + 2 * a + 1;
-			uint32_t const nb = b - a;
-			#pragma unroll 1
-			for (uint32_t y = 0; y < nb; y += 4) {
-				uint32_t const k0 = kh[2 * y] & MSD_KEYMASK;
-				uint32_t const k1 = y + 1 < nb ? kh[2 * y + 2] & MSD_KEYMASK : 0xffffffffu;
-				uint32_t const k2 = y + 2 < nb ? kh[2 * y + 4] & MSD_KEYMASK : 0xffffffffu;
-				uint32_t const k3 = y + 3 < nb ? kh[2 * y + 6] & MSD_KEYMASK : 0xffffffffu;
-				less += (k0 < mk ? 1u : 0u) + (k1 < mk ? 1u : 0u) + (k2 < mk ? 1u : 0u) + (k3 < mk ? 1u : 0u);
-				eq += (k0 == mk ? 1u : 0u) + (k1 == mk ? 1u : 0u) + (k2 == mk ? 1u : 0u) + (k3 == mk ? 1u : 0u);
-			}
-			f = a + less;
-			if (eq > 1) {
-				// equal on all the bits a record carries: compare the next 32 symbols, read from the text
-				++ntied;
-				unsigned long long mk2; uint32_t mr;
-				msd_second_key(A.v, skip, A.lin, (uint32_t)me, mk2, mr);
-				uint32_t eqb = 0, eqa = 0;
+		uint32_t const mh = (uint32_t)(me >> 32), mk = mh & MSD_KEYMASK;
+		const uint32_t * const w = rh + 2 * s;
+		uint32_t const p1 = w[-2] & MSD_KEYMASK, p2 = w[-4] & MSD_KEYMASK, p3 = w[-6] & MSD_KEYMASK;
+		uint32_t const n1 = w[2] & MSD_KEYMASK, n2 = w[4] & MSD_KEYMASK, n3 = w[6] & MSD_KEYMASK;
+		uint32_t f = s + (n1 < mk ? 1u : 0u) + (n2 < mk ? 1u : 0u) - (p1 > mk ? 1u : 0u) - (p2 > mk ? 1u : 0u);
+		uint32_t hf = 1;
+		// an equal neighbour, or a bin that reaches distance 3 (the digit and everything above it are equal)
+		bool const general = p1 == mk || n1 == mk || p2 == mk || n2 == mk || ((p3 ^ mk) >> dsh) == 0 || ((n3 ^ mk) >> dsh) == 0;
+		if (general) {
+			uint32_t const dg = (mh >> dsh) & (nlb - 1u);
+			uint32_t const a = cnt[(int)dg - 1], b = cnt[dg];
+			f = a;
+			if (b - a > (uint32_t)MSD_MAXRUN) {
+				// one unresolved group; the listed short suffixes of this digit go in front of it, shorter first
+				uint32_t const ns = s_nshort, myL = W32 - (uint32_t)me;
+				uint32_t nsb = 0, before = 0, smaller = 0;
+				for (uint32_t q = 0; q < ns; ++q) {
+					uint32_t const e = s_sh_e[q];
+					if (e >= a && e < b) { ++nsb; before += e < s ? 1u : 0u; smaller += s_sh_L[q] < myL ? 1u : 0u; }
+				}
+				if (A.lin && myL < hbig) { f = a + smaller; hf = 1; }
+				else { f = s + nsb - before; hf = (s - a == before) ? 1u : 0u; ++nunres; flags |= 1u; }
+			} else if (b - a > 1) {
+				uint32_t less = 0, eq = 0;
 				#pragma unroll 1
 				for (uint32_t y = a; y < b; ++y) {
-					unsigned long long const o = rec[y];
-					if (y == s || ((uint32_t)(o >> 32) & MSD_KEYMASK) != mk) continue;
-					unsigned long long ok2; uint32_t orr;
-					msd_second_key(A.v, skip, A.lin, (uint32_t)o, ok2, orr);
-					bool const same = ok2 == mk2 && orr == mr;
-					f += (ok2 < mk2 || (ok2 == mk2 && orr < mr) || (same && y < s)) ? 1u : 0u;
-					eqb += (same && y < s) ? 1u : 0u;
-					eqa += same ? 1u : 0u;
+					uint32_t const k = rh[2 * y] & MSD_KEYMASK;
+					less += k < mk ? 1u : 0u;
+					eq += k == mk ? 1u : 0u;
 				}
-				hf = eqb == 0 ? 1u : 0u;
-				if (eqa) ++nunres;
-				++ngather;
+				f = a + less;
+				if (eq > 1) {
+					// equal on all the bits a record carries: compare the next 32 symbols, read from the text
+					++ntied;
+					unsigned long long mk2; uint32_t mr;
+					msd_second_key(A.v, skip, A.lin, (uint32_t)me, mk2, mr);
+					uint32_t eqb = 0, eqa = 0;
+					#pragma unroll 1
+					for (uint32_t y = a; y < b; ++y) {
+						unsigned long long const o = rec[y];
+						if (y == s || ((uint32_t)(o >> 32) & MSD_KEYMASK) != mk) continue;
+						unsigned long long ok2; uint32_t orr;
+						msd_second_key(A.v, skip, A.lin, (uint32_t)o, ok2, orr);
+						bool const same = ok2 == mk2 && orr == mr;
+						f += (ok2 < mk2 || (ok2 == mk2 && orr < mr) || (same && y < s)) ? 1u : 0u;
+						eqb += (same && y < s) ? 1u : 0u;
+						eqa += same ? 1u : 0u;
+					}
+					hf = eqb == 0 ? 1u : 0u;
+					if (eqa) ++nunres;
+					++ngather;
+				}
 			}
 		}
 		uint32_t const i = (uint32_t)me;
 		if (ORDER) { A.sa_out[o0 + f] = i; A.hflag[o0 + f] = (uint8_t)hf; }
 		if (FUSED) {
-			s_bwt[f] = (uint8_t)(me >> 62);
-			uint32_t const r = (uint32_t)(o0 + f + A.fo.shift);
+			s_bwt[f] = (uint8_t)(mh >> 30);
+			uint32_t const r = rshift + f;
 			if (stage_sa) {
 				// sampled SA: the position goes to shared memory and leaves with a coalesced store below
 				if ((r & A.rmask) == 0) s_sa[(r - r_first) >> A.fo.salog] = i;
@@ -702,7 +731,7 @@ k_msd_finish(MsdFin A) {
 	if (FUSED) {
 		__syncthreads();
 		if (stage_sa) {
-			uint32_t const r_end = o0 + m + (uint32_t)A.fo.shift;
+			uint32_t const r_end = rshift + m;
 			uint32_t const ns = r_first < r_end ? ((r_end - 1u - r_first) >> A.fo.salog) + 1u : 0u;
 			for (uint32_t x = threadIdx.x; x < ns; x += MSD_THREADS) A.fo.sa_s[(r_first >> A.fo.salog) + x] = s_sa[x];
 		}

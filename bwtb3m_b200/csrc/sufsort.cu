@@ -298,7 +298,6 @@ static void msd_hist(Stream & st, TextView const & v, unsigned b1, std::vector<u
 	B3M_CUDA(cudaStreamSynchronize(st.s));
 }
 
-constexpr int MSD_FIN_SMEM = MSD_CAP * 9 + ((1 << MSD_LBITS_MAX) + 1) * 4;
 
 static void msd_configure() {
 	static bool done = false;
