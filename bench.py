@@ -142,6 +142,45 @@ def cpu_oracle_run(itype, filebytes, nsyms_limit, params, threads, want_lf=False
     return dt, n, nblocks
 
 
+def file_level_leg(args, itype, data, nsym, params):
+    """The reference's own contract (/root/reference/src/bwtb3m.cpp:62-65): input FILE in, output FILES out, through
+    b3m_compute_bwt (K8 run-length Huffman encoding on the device, then the writes) -- and, for pacterm, the BWA
+    export b3m_to_bwa on top (/root/reference/src/bwtb3mtobwa.cpp:29).  Files live on tmpfs (/dev/shm) when it has
+    room, so the figure is host memory + PCIe + device, not a disk."""
+    import shutil
+    import tempfile
+    from bwtb3m_b200 import files
+    need = 6 * data.size + 16 * nsym // 32 + (1 << 30)
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > need else tempfile.gettempdir()
+    if shutil.disk_usage(base).free < need:
+        return {"skipped": "no room for the files (%d bytes needed under %s)" % (need, base)}
+    d = tempfile.mkdtemp(prefix="b3m_bench_", dir=base)
+    try:
+        fn = os.path.join(d, "in.dat")
+        data.tofile(fn)
+        out = os.path.join(d, "out.bwt")
+        runs = []
+        for _ in range(2):  # the first run also pays the CUDA context and the first pinned allocation
+            t0 = time.perf_counter()
+            r = files.compute_bwt(fn, inputtype=itype, outputfilename=out, sasamplingrate=params["sasamplingrate"],
+                                  isasamplingrate=params["isasamplingrate"], bwtonly=params["bwtonly"], tmpprefix=os.path.join(d, "tmp"))
+            runs.append((time.perf_counter() - t0, r["seconds_total"], r["seconds_device"]))
+        wall, tot, dev = min(runs)
+        sizes = {suf: os.path.getsize(out[:-4] + suf) for suf in (".bwt", ".hist", ".sa", ".isa", ".preisa") if os.path.exists(out[:-4] + suf)}
+        res = {"value": nsym / wall / 1e6, "unit": UNIT, "seconds": wall, "seconds_device": dev, "dir": base,
+               "call": "b3m_compute_bwt: %s file -> %s" % (itype, " + ".join(sorted(sizes))),
+               "bytes_in": int(data.size), "bytes_out": int(sum(sizes.values())), "first_run_seconds": runs[0][0]}
+        if itype == "pacterm" and not params["bwtonly"]:
+            t0 = time.perf_counter()
+            files.to_bwa(out, os.path.join(d, "bwa.bwt"), os.path.join(d, "bwa.sa"))
+            tb = time.perf_counter() - t0
+            res["to_bwa_seconds"] = tb
+            res["value_with_bwa_export"] = nsym / (wall + tb) / 1e6
+        return res
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path.  gt1/bwtb3m cannot be
     built here (libmaus2 is absent), so this arm times the oracle port, all host threads."""
@@ -309,8 +348,28 @@ def run_ours(args):
         kt = eng.kernel_times()
         eng.set_profile(False)
         lf_ms = None
+        k8 = None
         if rank == 0:
             lf_ms, _ = eng.lf_bench(1 << 20, 256)
+            if world == 1 and not args.no_file_level:
+                # K8 alone: run-length Huffman encoding of the BWT on the device, payload written to tmpfs
+                import tempfile
+                tdir = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+                tfn = os.path.join(tdir, "b3m_bench_k8_%d.bwt" % os.getpid())
+                try:
+                    eng.set_profile(True)
+                    t0 = time.perf_counter()
+                    eng.write_bwt(tfn)
+                    tw = time.perf_counter() - t0
+                    k8t = eng.kernel_times()
+                    eng.set_profile(False)
+                    kms = sum(v["ms"] for k, v in k8t.items() if k.startswith("rl_"))
+                    kb = sum(v["bytes"] for k, v in k8t.items() if k.startswith("rl_"))
+                    k8 = {"kernels_ms": {k: round(v["ms"], 4) for k, v in k8t.items()}, "rl_kernels_ms": kms, "algorithmic_bytes": kb,
+                          "achieved_gbs": kb / (kms * 1e-3) / 1e9 if kms else None, "write_bwt_seconds": tw, "file_bytes": os.path.getsize(tfn)}
+                finally:
+                    if os.path.exists(tfn):
+                        os.remove(tfn)
     # ---- N > 1: what was timed equals a single-GPU build of the same input, bit for bit ----
     parity = None
     if world > 1:
@@ -376,6 +435,17 @@ def run_ours(args):
             curve.append({"n_symbols": int(k), "value": k / dtk / 1e6, "seconds": dtk})
         cpu["curve"] = sorted(curve, key=lambda c: c["n_symbols"])
 
+    file_level = None
+    if world == 1 and not args.no_file_level:
+        try:
+            file_level = file_level_leg(args, itype, data, nsym, params)
+        except Exception as ex:  # the leg must never take the bench line down
+            file_level = {"failed": str(ex)[:300]}
+    if k8 is not None:
+        peak_k8, _ = measured_peak_gbs()
+        if k8.get("achieved_gbs"):
+            k8["frac_of_hbm_peak"] = k8["achieved_gbs"] / peak_k8
+
     total_s = total_ms * 1e-3
     line = {
         "metric": METRIC, "value": nsym * args.steps / total_s / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -398,6 +468,10 @@ def run_ours(args):
         "kernels_ms_per_step": {k: round(v["ms"] / nprof, 4) for k, v in kt.items()},
         "lf_steps_per_s": (1 << 20) * 256 / (lf_ms * 1e-3),
     }
+    if file_level is not None:
+        line["file_level"] = file_level
+    if k8 is not None:
+        line["k8_rl_encode"] = k8
     if parity is not None:
         line["parity_check"] = parity
     print(json.dumps(line), flush=True)
@@ -418,6 +492,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=256_000_000, help="symbols of the workload the cpu_baseline leg processes")
     ap.add_argument("--ref-sample", type=int, default=128_000_000, help="symbols per step of --impl reference (about 7 s of CPU work per step)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-file-level", action="store_true", help="skip the file-in / files-out leg (b3m_compute_bwt on tmpfs) and the K8 timing")
     ap.add_argument("--cpu-curve", default="32000000,1000000000", help="further prefix sizes the cpu_baseline leg times (throughput against n); empty: none")
     ap.add_argument("--e2e-steps", type=int, default=5, help="steps of the end-to-end (host buffers) leg")
     args = ap.parse_args()

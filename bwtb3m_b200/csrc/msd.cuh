@@ -420,7 +420,20 @@ struct MsdFin {
 	FusedOut fo;                    // FUSED (shift includes the rank of the first kept record)
 	uint32_t imask, rmask;          // a suffix at position i / of rank r is sampled only if (i & imask) == 0 or (r & rmask) == 0
 	unsigned long long * counters;  // [MSD_CSLOTS][4]: unresolved, tied, second keys read, flags (1: run too long, 2: sub-bucket too large)
+	const uint8_t * shortflag;      // linear windows: [sub-bucket] != 0 where one of the last 18 suffixes of the window lies (nullptr: none)
 };
+
+// marks the sub-buckets that hold one of the last 18 suffixes of a linear window: only there can a suffix be shorter
+// than the prefix an unresolved group shares
+__global__ void k_msd_shortflags(TextView v, unsigned b1, unsigned b2, uint32_t d_lo, uint32_t nkeep, uint8_t * __restrict__ flags) {
+	uint64_t const first = v.W > 18 ? v.W - 18 : 0;
+	uint64_t const i = first + threadIdx.x;
+	if (i >= v.W) return;
+	uint32_t d, hi32;
+	msd_record(v, i, b1, d, hi32);
+	uint32_t const b = d - d_lo;
+	if (b < nkeep) flags[((uint64_t)b << b2) | ((hi32 & MSD_KEYMASK) >> (30u - b2))] = 1;
+}
 
 __device__ __forceinline__ void msd_second_key(TextView const & v, unsigned skip, int lin, uint32_t i, unsigned long long & k2, uint32_t & rem) {
 	k2 = tv_symbols(v, (uint64_t)i + skip, 32, 2);
@@ -437,9 +450,10 @@ __device__ __forceinline__ void msd_emit_samples(FusedOut const & fo, uint32_t i
 	if (SA && fo.sa_s && (fo.salog >= 32 ? r == 0 : (r & ((1u << fo.salog) - 1u)) == 0)) fo.sa_s[fo.salog >= 32 ? 0 : (r >> fo.salog)] = i;
 }
 
-// one chunk of MSD_THREADS tiles of the parent bucket: thread <-> tile k0 + threadIdx.x; returns this
+// one chunk of THREADS tiles of the parent bucket: thread <-> tile k0 + threadIdx.x; returns this
 // thread's run widened to 16-byte boundaries as (first record a0, padded length plen, place off in rec[])
 // and adds the chunk's padded total to `done`.  g0/g1 = the run itself.
+template <int THREADS>
 __device__ __forceinline__ void msd_run_place(const uint16_t * __restrict__ row0, const uint16_t * __restrict__ row1, uint32_t pstart, uint32_t ntp,
                                               uint32_t k0, uint32_t * wsum, uint32_t & done, uint32_t & g0, uint32_t & g1, uint32_t & a0, uint32_t & plen, uint32_t & off) {
 	unsigned const lane = threadIdx.x & 31;
@@ -456,7 +470,7 @@ __device__ __forceinline__ void msd_run_place(const uint16_t * __restrict__ row0
 	__syncthreads();
 	uint32_t before = 0, ctot = 0;
 	#pragma unroll
-	for (int ww = 0; ww < MSD_THREADS / 32; ++ww) { uint32_t const x = wsum[ww]; before += ww < (int)(threadIdx.x >> 5) ? x : 0u; ctot += x; }
+	for (int ww = 0; ww < THREADS / 32; ++ww) { uint32_t const x = wsum[ww]; before += ww < (int)(threadIdx.x >> 5) ? x : 0u; ctot += x; }
 	off = done + before + incl - plen;
 	done += ctot;
 }
@@ -483,6 +497,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void * src, uint32_
 }
 
 constexpr int MSD_WIN = 3;                          // sentinel slots on either side of the sorted records
+constexpr int MSD_QCAP = 1024;                      // records of a CTA whose general path is deferred behind the main loop
 constexpr int MSD_FIN_SMEM = 32 + (MSD_CAP + 4) * 8 + MSD_CAP + 16 + (1 << MSD_LBITS_MAX) * 4;
 
 // Shared memory: 32 B (front sentinels) | rec[MSD_CAP + 4] | s_bwt[MSD_CAP] | 16 B (cnt[-1] = 0) | cnt[2^lb]
@@ -493,17 +508,20 @@ constexpr int MSD_FIN_SMEM = 32 + (MSD_CAP + 4) * 8 + MSD_CAP + 16 + (1 << MSD_L
 // compares itself with its neighbours at distance 1 and 2 (the array is sorted by digit: a later record with a
 // smaller key, or an earlier one with a larger key, is in the same bin) and checks that the bin ends within
 // distance 2 on both sides; records with an equal neighbour or a longer bin take the general path (bin bounds
-// from the table, second keys from the text, unresolved groups); (4) emit as before.
-template <bool FUSED, bool ORDER>
-__global__ void __launch_bounds__(MSD_THREADS, 2)
+// from the table, second keys from the text, unresolved groups) -- queued and worked off densely behind the main
+// loop, so that one such record does not hold up its warp; (4) emit.
+template <bool FUSED, bool ORDER, int THREADS>
+__global__ void __launch_bounds__(THREADS, 2)
 k_msd_finish(const __grid_constant__ MsdFin A) {
+	constexpr int ITEMS = MSD_CAP / THREADS;
 	extern __shared__ __align__(16) uint8_t msd_dyn[];
 	unsigned long long * const rec = reinterpret_cast<unsigned long long *>(msd_dyn + 32);             // MSD_CAP + 4
 	uint8_t * const s_bwt = msd_dyn + 32 + (size_t)(MSD_CAP + 4) * 8;                                  // MSD_CAP
 	uint32_t * const cnt = reinterpret_cast<uint32_t *>(s_bwt + MSD_CAP + 16);                         // cnt[-1 .. 2^lb)
-	__shared__ uint32_t wsum[MSD_THREADS / 32];
-	__shared__ uint32_t s_sa[MSD_THREADS];                        // sampled SA of this CTA's rows (at most MSD_CAP / 32)
-	__shared__ uint32_t s_cnt[4];
+	__shared__ uint32_t wsum[THREADS / 32];
+	__shared__ uint32_t s_sa[512];                                // sampled SA of this CTA's rows (at most MSD_CAP / 32)
+	__shared__ uint16_t s_q[MSD_QCAP];                            // deferred records
+	__shared__ uint32_t s_cnt[4], s_nq;
 	__shared__ __align__(8) unsigned long long s_mbar;
 	// linear windows: the suffixes shorter than the prefix an unresolved group shares (at most 16 in the whole text)
 	__shared__ uint32_t s_sh_e[16], s_sh_L[16], s_nshort;
@@ -519,7 +537,7 @@ k_msd_finish(const __grid_constant__ MsdFin A) {
 	const uint16_t * const row1 = row0 + ntp;
 	unsigned const lane = threadIdx.x & 31;
 	if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
-	if (threadIdx.x == 0) s_nshort = 0;
+	if (threadIdx.x == 0) { s_nshort = 0; s_nq = 0; }
 
 	if ((uint64_t)m + 2ull * ntp > (uint64_t)MSD_CAP) {
 		__syncthreads();
@@ -534,7 +552,7 @@ k_msd_finish(const __grid_constant__ MsdFin A) {
 				for (uint32_t k = 0; k < ntp; ++k) {
 					uint32_t const s = row0[k], len = row1[k] - s;
 					const unsigned long long * src = A.recs + pstart + (uint64_t)k * MSD_TILE + s;
-					for (uint32_t x = threadIdx.x; x < len; x += MSD_THREADS) {
+					for (uint32_t x = threadIdx.x; x < len; x += THREADS) {
 						uint32_t const L = W32 - (uint32_t)src[x];
 						if (L < h2) { uint32_t const q = atomicAdd(&s_nshort, 1u); s_sh_e[q] = done + x; s_sh_L[q] = L; }
 					}
@@ -547,7 +565,7 @@ k_msd_finish(const __grid_constant__ MsdFin A) {
 			for (uint32_t k = 0; k < ntp; ++k) {
 				uint32_t const s = row0[k], len = row1[k] - s;
 				const unsigned long long * src = A.recs + pstart + (uint64_t)k * MSD_TILE + s;
-				for (uint32_t x = threadIdx.x; x < len; x += MSD_THREADS) {
+				for (uint32_t x = threadIdx.x; x < len; x += THREADS) {
 					uint32_t const i = (uint32_t)src[x], e = done + x, L = W32 - i;
 					uint32_t pos = e, hf = e == 0 ? 1u : 0u;
 					if (ns) {
@@ -574,34 +592,36 @@ k_msd_finish(const __grid_constant__ MsdFin A) {
 	lb = lb < (unsigned)MSD_LBITS_MIN ? (unsigned)MSD_LBITS_MIN : (lb > (unsigned)MSD_LBITS_MAX ? (unsigned)MSD_LBITS_MAX : lb);
 	unsigned const nlb = 1u << lb;
 	unsigned const dsh = 30u - A.b2 - lb;  // the local digit follows the b2 bits of level 2 inside key30: bits [dsh, dsh + lb) of a record's upper word
+	uint32_t const dmask = nlb - 1u;
 
 	// ---- (1) gather: one bulk copy per run (a run is widened to 16-byte boundaries, the at most two records of
 	//      neighbouring runs this drags in are overwritten with MSD_PAD afterwards); the table is cleared meanwhile ----
 	uint32_t const rec_s = (uint32_t)__cvta_generic_to_shared(rec), mbar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
-	if (threadIdx.x == 0) mbar_init(mbar, (ntp + MSD_THREADS - 1) / MSD_THREADS);
+	if (threadIdx.x == 0) mbar_init(mbar, (ntp + THREADS - 1) / THREADS);
 	__syncthreads();
 	uint32_t mpad = 0; // records in rec[], padding included
 	uint32_t g0 = 0, g1 = 0, a0, plen = 0, off = 0;
-	for (uint32_t k0 = 0; k0 < ntp; k0 += MSD_THREADS) {
+	for (uint32_t k0 = 0; k0 < ntp; k0 += THREADS) {
 		uint32_t const before = mpad;
-		msd_run_place(row0, row1, pstart, ntp, k0, wsum, mpad, g0, g1, a0, plen, off);
+		msd_run_place<THREADS>(row0, row1, pstart, ntp, k0, wsum, mpad, g0, g1, a0, plen, off);
 		if (plen) bulk_g2s(rec_s + 8u * off, A.recs + a0, plen * 8u, mbar);
 		if (threadIdx.x == 0) mbar_arrive_expect_tx(mbar, (mpad - before) * 8u);
 	}
-	for (unsigned i = threadIdx.x; i < nlb; i += MSD_THREADS) cnt[i] = 0;
+	for (unsigned i = threadIdx.x; i < nlb; i += THREADS) cnt[i] = 0;
 	if (threadIdx.x < 4) cnt[(int)threadIdx.x - 4] = 0;
 	if (threadIdx.x < (unsigned)MSD_WIN) rec[-1 - (int)threadIdx.x] = 0ull; // front sentinels: smaller than every key
+	bool const shortsb = A.shortflag && A.shortflag[sb]; // uniform
 	mbar_wait(mbar, 0);
 	// the records dragged in from neighbouring runs become padding (several chunks of tiles: one more walk over the descriptors)
-	if (ntp <= (uint32_t)MSD_THREADS) {
+	if (ntp <= (uint32_t)THREADS) {
 		if (plen) {
 			if (g0 & 1u) rec[off] = MSD_PAD;
 			if (g1 & 1u) rec[off + plen - 1] = MSD_PAD;
 		}
 	} else {
 		uint32_t done = 0;
-		for (uint32_t k0 = 0; k0 < ntp; k0 += MSD_THREADS) {
-			msd_run_place(row0, row1, pstart, ntp, k0, wsum, done, g0, g1, a0, plen, off);
+		for (uint32_t k0 = 0; k0 < ntp; k0 += THREADS) {
+			msd_run_place<THREADS>(row0, row1, pstart, ntp, k0, wsum, done, g0, g1, a0, plen, off);
 			if (plen) {
 				if (g0 & 1u) rec[off] = MSD_PAD;
 				if (g1 & 1u) rec[off + plen - 1] = MSD_PAD;
@@ -612,28 +632,22 @@ k_msd_finish(const __grid_constant__ MsdFin A) {
 
 	// ---- (2) local digit: count, scan, hand out the slots; the records pass through registers ----
 	{
-		unsigned long long r[MSD_ITEMS];
-		uint32_t const shortlim = A.lin ? W32 - 18u : 0xffffffffu; // suffixes behind this position may be too short for a group
-		bool anyshort = false;
+		uint32_t rlo[ITEMS], rhi[ITEMS]; // lower word ~0: padding (a record's index is below 2^32 - 256) or no record
 		#pragma unroll
-		for (int j = 0; j < MSD_ITEMS; ++j) {
-			r[j] = MSD_PAD;
-			if ((uint32_t)(j * MSD_THREADS) < mpad) { // uniform: whole iterations are skipped
-				uint32_t const s = j * MSD_THREADS + threadIdx.x;
-				if (s < mpad) r[j] = rec[s];
-				if ((uint32_t)r[j] != 0xffffffffu) { // a record's index is below 2^32 - 256
-					atomicAdd(&cnt[((uint32_t)(r[j] >> 32) >> dsh) & (nlb - 1u)], 1u);
-					anyshort |= (uint32_t)r[j] > shortlim;
-				}
-			}
+		for (int j = 0; j < ITEMS; ++j) {
+			uint32_t const s = j * THREADS + threadIdx.x;
+			rlo[j] = 0xffffffffu; rhi[j] = 0;
+			if (s < mpad) { uint2 const x = *reinterpret_cast<const uint2 *>(rec + s); rlo[j] = x.x; rhi[j] = x.y; }
+			if (rlo[j] != 0xffffffffu) atomicAdd(&cnt[(rhi[j] >> dsh) & dmask], 1u);
 		}
-		if (anyshort) s_nshort = 0x80000000u; // the list is made below
 		__syncthreads();
-		msd_scan_bins_wide<MSD_THREADS>(cnt, nlb, wsum);
+		msd_scan_bins_wide<THREADS>(cnt, nlb, wsum);
 		#pragma unroll
-		for (int j = 0; j < MSD_ITEMS; ++j)
-			if ((uint32_t)(j * MSD_THREADS) < mpad && (uint32_t)r[j] != 0xffffffffu)
-				rec[atomicAdd(&cnt[((uint32_t)(r[j] >> 32) >> dsh) & (nlb - 1u)], 1u)] = r[j];
+		for (int j = 0; j < ITEMS; ++j)
+			if (rlo[j] != 0xffffffffu) {
+				uint32_t const pos = atomicAdd(&cnt[(rhi[j] >> dsh) & dmask], 1u);
+				*reinterpret_cast<uint2 *>(rec + pos) = make_uint2(rlo[j], rhi[j]);
+			}
 		if (threadIdx.x < (unsigned)MSD_WIN) rec[m + threadIdx.x] = (unsigned long long)MSD_KEYMASK << 32; // back sentinels: no key is larger
 		__syncthreads();
 	}
@@ -641,11 +655,8 @@ k_msd_finish(const __grid_constant__ MsdFin A) {
 
 	// crowded local digits stay unresolved groups sharing hbig symbols: list the suffixes too short for that
 	uint32_t const hbig = (A.b1 + A.b2 + lb) >> 1; // at most 16
-	if (s_nshort) { // uniform; only the CTAs whose sub-bucket holds one of the last 16 suffixes of a linear window
-		__syncthreads();
-		if (threadIdx.x == 0) s_nshort = 0;
-		__syncthreads();
-		for (uint32_t s = threadIdx.x; s < m; s += MSD_THREADS) {
+	if (shortsb) { // only the CTAs whose sub-bucket holds one of the last suffixes of a linear window
+		for (uint32_t s = threadIdx.x; s < m; s += THREADS) {
 			uint32_t const L = W32 - (uint32_t)rec[s];
 			if (L < hbig) { uint32_t const q = atomicAdd(&s_nshort, 1u); s_sh_e[q] = s; s_sh_L[q] = L; }
 		}
@@ -659,67 +670,60 @@ k_msd_finish(const __grid_constant__ MsdFin A) {
 	unsigned const skip = (A.b1 + 30u) >> 1; // symbols covered by b1 + key30
 	uint32_t ntied = 0, nunres = 0, ngather = 0, flags = 0;
 	const uint32_t * const rh = reinterpret_cast<const uint32_t *>(rec) + 1; // upper word of slot y: rh[2 * y]
-	#pragma unroll 1
-	for (uint32_t s = threadIdx.x; s < m; s += MSD_THREADS) {
-		unsigned long long const me = rec[s];
+
+	// final place f (relative to the sub-bucket) and head flag of the record in slot s, bin bounds from the table
+	auto general_path = [&](uint32_t s, unsigned long long me, uint32_t & f, uint32_t & hf) {
 		uint32_t const mh = (uint32_t)(me >> 32), mk = mh & MSD_KEYMASK;
-		const uint32_t * const w = rh + 2 * s;
-		uint32_t const p1 = w[-2] & MSD_KEYMASK, p2 = w[-4] & MSD_KEYMASK, p3 = w[-6] & MSD_KEYMASK;
-		uint32_t const n1 = w[2] & MSD_KEYMASK, n2 = w[4] & MSD_KEYMASK, n3 = w[6] & MSD_KEYMASK;
-		uint32_t f = s + (n1 < mk ? 1u : 0u) + (n2 < mk ? 1u : 0u) - (p1 > mk ? 1u : 0u) - (p2 > mk ? 1u : 0u);
-		uint32_t hf = 1;
-		// an equal neighbour, or a bin that reaches distance 3 (the digit and everything above it are equal)
-		bool const general = p1 == mk || n1 == mk || p2 == mk || n2 == mk || ((p3 ^ mk) >> dsh) == 0 || ((n3 ^ mk) >> dsh) == 0;
-		if (general) {
-			uint32_t const dg = (mh >> dsh) & (nlb - 1u);
-			uint32_t const a = cnt[(int)dg - 1], b = cnt[dg];
-			f = a;
-			if (b - a > (uint32_t)MSD_MAXRUN) {
-				// one unresolved group; the listed short suffixes of this digit go in front of it, shorter first
-				uint32_t const ns = s_nshort, myL = W32 - (uint32_t)me;
-				uint32_t nsb = 0, before = 0, smaller = 0;
-				for (uint32_t q = 0; q < ns; ++q) {
-					uint32_t const e = s_sh_e[q];
-					if (e >= a && e < b) { ++nsb; before += e < s ? 1u : 0u; smaller += s_sh_L[q] < myL ? 1u : 0u; }
-				}
-				if (A.lin && myL < hbig) { f = a + smaller; hf = 1; }
-				else { f = s + nsb - before; hf = (s - a == before) ? 1u : 0u; ++nunres; flags |= 1u; }
-			} else if (b - a > 1) {
-				uint32_t less = 0, eq = 0;
+		uint32_t const dg = (mh >> dsh) & dmask;
+		uint32_t const a = cnt[(int)dg - 1], b = cnt[dg];
+		f = a; hf = 1;
+		if (b - a > (uint32_t)MSD_MAXRUN) {
+			// one unresolved group; the listed short suffixes of this digit go in front of it, shorter first
+			uint32_t const ns = s_nshort, myL = W32 - (uint32_t)me;
+			uint32_t nsb = 0, before = 0, smaller = 0;
+			for (uint32_t q = 0; q < ns; ++q) {
+				uint32_t const e = s_sh_e[q];
+				if (e >= a && e < b) { ++nsb; before += e < s ? 1u : 0u; smaller += s_sh_L[q] < myL ? 1u : 0u; }
+			}
+			if (A.lin && myL < hbig) { f = a + smaller; hf = 1; }
+			else { f = s + nsb - before; hf = (s - a == before) ? 1u : 0u; ++nunres; flags |= 1u; }
+		} else if (b - a > 1) {
+			uint32_t less = 0, eq = 0;
+			#pragma unroll 1
+			for (uint32_t y = a; y < b; ++y) {
+				uint32_t const k = rh[2 * y] & MSD_KEYMASK;
+				less += k < mk ? 1u : 0u;
+				eq += k == mk ? 1u : 0u;
+			}
+			f = a + less;
+			if (eq > 1) {
+				// equal on all the bits a record carries: compare the next 32 symbols, read from the text
+				++ntied;
+				unsigned long long mk2; uint32_t mr;
+				msd_second_key(A.v, skip, A.lin, (uint32_t)me, mk2, mr);
+				uint32_t eqb = 0, eqa = 0;
 				#pragma unroll 1
 				for (uint32_t y = a; y < b; ++y) {
-					uint32_t const k = rh[2 * y] & MSD_KEYMASK;
-					less += k < mk ? 1u : 0u;
-					eq += k == mk ? 1u : 0u;
+					unsigned long long const o = rec[y];
+					if (y == s || ((uint32_t)(o >> 32) & MSD_KEYMASK) != mk) continue;
+					unsigned long long ok2; uint32_t orr;
+					msd_second_key(A.v, skip, A.lin, (uint32_t)o, ok2, orr);
+					bool const same = ok2 == mk2 && orr == mr;
+					f += (ok2 < mk2 || (ok2 == mk2 && orr < mr) || (same && y < s)) ? 1u : 0u;
+					eqb += (same && y < s) ? 1u : 0u;
+					eqa += same ? 1u : 0u;
 				}
-				f = a + less;
-				if (eq > 1) {
-					// equal on all the bits a record carries: compare the next 32 symbols, read from the text
-					++ntied;
-					unsigned long long mk2; uint32_t mr;
-					msd_second_key(A.v, skip, A.lin, (uint32_t)me, mk2, mr);
-					uint32_t eqb = 0, eqa = 0;
-					#pragma unroll 1
-					for (uint32_t y = a; y < b; ++y) {
-						unsigned long long const o = rec[y];
-						if (y == s || ((uint32_t)(o >> 32) & MSD_KEYMASK) != mk) continue;
-						unsigned long long ok2; uint32_t orr;
-						msd_second_key(A.v, skip, A.lin, (uint32_t)o, ok2, orr);
-						bool const same = ok2 == mk2 && orr == mr;
-						f += (ok2 < mk2 || (ok2 == mk2 && orr < mr) || (same && y < s)) ? 1u : 0u;
-						eqb += (same && y < s) ? 1u : 0u;
-						eqa += same ? 1u : 0u;
-					}
-					hf = eqb == 0 ? 1u : 0u;
-					if (eqa) ++nunres;
-					++ngather;
-				}
+				hf = eqb == 0 ? 1u : 0u;
+				if (eqa) ++nunres;
+				++ngather;
 			}
 		}
+	};
+	auto emit = [&](unsigned long long me, uint32_t f, uint32_t hf) {
 		uint32_t const i = (uint32_t)me;
 		if (ORDER) { A.sa_out[o0 + f] = i; A.hflag[o0 + f] = (uint8_t)hf; }
 		if (FUSED) {
-			s_bwt[f] = (uint8_t)(mh >> 30);
+			s_bwt[f] = (uint8_t)(me >> 62);
 			uint32_t const r = rshift + f;
 			if (stage_sa) {
 				// sampled SA: the position goes to shared memory and leaves with a coalesced store below
@@ -727,13 +731,45 @@ k_msd_finish(const __grid_constant__ MsdFin A) {
 				if ((i & A.imask) == 0) msd_emit_samples<false>(A.fo, i, r);
 			} else if ((i & A.imask) == 0 || (r & A.rmask) == 0) msd_emit_samples<true>(A.fo, i, r);
 		}
+	};
+
+	#pragma unroll 1
+	for (uint32_t s = threadIdx.x; s < m; s += THREADS) {
+		unsigned long long const me = rec[s];
+		uint32_t const mh = (uint32_t)(me >> 32), mk = mh & MSD_KEYMASK;
+		const uint32_t * const w = rh + 2 * s;
+		uint32_t const p1 = w[-2] & MSD_KEYMASK, p2 = w[-4] & MSD_KEYMASK, n1 = w[2] & MSD_KEYMASK, n2 = w[4] & MSD_KEYMASK;
+		uint32_t const p3 = w[-6], n3 = w[6];
+		// keys are below 2^30: the sign bit of a difference is the comparison
+		uint32_t f = s + ((n1 - mk) >> 31) + ((n2 - mk) >> 31) - ((mk - p1) >> 31) - ((mk - p2) >> 31);
+		uint32_t hf = 1;
+		// an equal neighbour, or a bin that reaches distance 3 (the digit and everything above it are equal)
+		bool const general = p1 == mk || n1 == mk || p2 == mk || n2 == mk || (((p3 ^ mh) & MSD_KEYMASK) >> dsh) == 0 || (((n3 ^ mh) & MSD_KEYMASK) >> dsh) == 0;
+		if (general) {
+			uint32_t const q = atomicAdd(&s_nq, 1u);
+			if (q < (uint32_t)MSD_QCAP) { s_q[q] = (uint16_t)s; continue; }
+			general_path(s, me, f, hf);
+		}
+		emit(me, f, hf);
+	}
+	__syncthreads();
+	{
+		uint32_t const nq = s_nq < (uint32_t)MSD_QCAP ? s_nq : (uint32_t)MSD_QCAP;
+		#pragma unroll 1
+		for (uint32_t q = threadIdx.x; q < nq; q += THREADS) {
+			uint32_t const s = s_q[q];
+			unsigned long long const me = rec[s];
+			uint32_t f, hf;
+			general_path(s, me, f, hf);
+			emit(me, f, hf);
+		}
 	}
 	if (FUSED) {
 		__syncthreads();
 		if (stage_sa) {
 			uint32_t const r_end = rshift + m;
 			uint32_t const ns = r_first < r_end ? ((r_end - 1u - r_first) >> A.fo.salog) + 1u : 0u;
-			for (uint32_t x = threadIdx.x; x < ns; x += MSD_THREADS) A.fo.sa_s[(r_first >> A.fo.salog) + x] = s_sa[x];
+			for (uint32_t x = threadIdx.x; x < ns; x += THREADS) A.fo.sa_s[(r_first >> A.fo.salog) + x] = s_sa[x];
 		}
 		uint8_t * const out = A.fo.bwt + A.fo.shift + o0;
 		// head bytes up to a 4-byte boundary, words, tail bytes
@@ -741,7 +777,7 @@ k_msd_finish(const __grid_constant__ MsdFin A) {
 		uint32_t const head = mis < m ? mis : m;
 		if (threadIdx.x < head) out[threadIdx.x] = s_bwt[threadIdx.x];
 		uint32_t const nw = (m - head) >> 2;
-		for (uint32_t x = threadIdx.x; x < nw; x += MSD_THREADS) {
+		for (uint32_t x = threadIdx.x; x < nw; x += THREADS) {
 			uint32_t const p = head + 4 * x;
 			reinterpret_cast<uint32_t *>(out + head)[x] = (uint32_t)s_bwt[p] | ((uint32_t)s_bwt[p + 1] << 8) | ((uint32_t)s_bwt[p + 2] << 16) | ((uint32_t)s_bwt[p + 3] << 24);
 		}

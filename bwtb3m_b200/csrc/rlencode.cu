@@ -262,7 +262,7 @@ void Engine::write_bwt(const char * fn) {
 	DevBuf<unsigned long long> dh(st, 512);
 	B3M_CUDA(cudaMemsetAsync(dh.get(), 0, 512 * 8, st.s));
 	unsigned const hgrid = (unsigned)std::min<uint64_t>(std::max<uint64_t>(div_up(nruns, 256 * 16), 1), (uint64_t)st.sms * 8);
-	B3M_LAUNCH(st, k_rl_hist, hgrid, 256, 0, (const uint8_t *)syms.get(), (const uint32_t *)start.get(), nruns, n, dh.get(), dh.get() + 256);
+	B3M_LAUNCH_T(st, "rl_hist", 5 * nruns, k_rl_hist, hgrid, 256, 0, (const uint8_t *)syms.get(), (const uint32_t *)start.get(), nruns, n, dh.get(), dh.get() + 256);
 	std::vector<uint64_t> hh(512);
 	B3M_CUDA(cudaMemcpyAsync(hh.data(), dh.get(), 512 * 8, cudaMemcpyDeviceToHost, st.s));
 	B3M_CUDA(cudaStreamSynchronize(st.s));
@@ -275,7 +275,7 @@ void Engine::write_bwt(const char * fn) {
 	// block sizes -> offsets (host scan: nblocks is nruns/4096)
 	DevBuf<uint32_t> bw(st, h.nblocks);
 	DevBuf<unsigned long long> bsym(st, h.nblocks), boff(st, h.nblocks);
-	B3M_LAUNCH(st, k_rl_blockbits, (unsigned)h.nblocks, RLE_THREADS, 0, (const uint8_t *)syms.get(), (const uint32_t *)start.get(), nruns, n,
+	B3M_LAUNCH_T(st, "rl_blockbits", 5 * nruns, k_rl_blockbits, (unsigned)h.nblocks, RLE_THREADS, 0, (const uint8_t *)syms.get(), (const uint32_t *)start.get(), nruns, n,
 	           (const RlTabs *)dtabs.get(), bw.get(), bsym.get());
 	std::vector<uint32_t> hbw(h.nblocks);
 	std::vector<uint64_t> woff(h.nblocks), soff(h.nblocks);

@@ -304,8 +304,10 @@ static void msd_configure() {
 	if (done) return;
 	B3M_CUDA(cudaFuncSetAttribute(k_msd_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, MSD_TILE * 8));
 	B3M_CUDA(cudaFuncSetAttribute(k_msd_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (MSD_TILE + 2) * 8));
-	B3M_CUDA(cudaFuncSetAttribute(k_msd_finish<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MSD_FIN_SMEM));
-	B3M_CUDA(cudaFuncSetAttribute(k_msd_finish<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MSD_FIN_SMEM));
+	B3M_CUDA(cudaFuncSetAttribute(k_msd_finish<true, false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, MSD_FIN_SMEM));
+	B3M_CUDA(cudaFuncSetAttribute(k_msd_finish<false, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, MSD_FIN_SMEM));
+	B3M_CUDA(cudaFuncSetAttribute(k_msd_finish<true, false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, MSD_FIN_SMEM));
+	B3M_CUDA(cudaFuncSetAttribute(k_msd_finish<false, true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, MSD_FIN_SMEM));
 	done = true;
 }
 
@@ -354,7 +356,7 @@ static void msd_scatter_phase(Stream & st, TextView const & v, MsdGeom const & g
 	C.toff.release();
 }
 
-static bool msd_finish_phase(Stream & st, TextView const & v, int lin, MsdGeom const & g, uint32_t nkeep, const unsigned long long * tot,
+static bool msd_finish_phase(Stream & st, TextView const & v, int lin, MsdGeom const & g, uint32_t d_lo, uint32_t nkeep, const unsigned long long * tot,
                              unsigned long long * recs_ptr, bool whole, FusedOut const & fo, StreamOut * so, DevBuf<uint32_t> * sa_buf,
                              DevBuf<uint8_t> * hflag, SortStats & S, uint64_t & unresolved, uint64_t & hstart);
 
@@ -392,12 +394,12 @@ static bool msd_round0(Stream & st, TextView const & v, int lin, MsdGeom const &
 	unsigned long long * const out[1] = {recs.get()};
 	msd_scatter_phase(st, v, g, d_lo, nkeep, C, destbase, 1, bnd, out, m, S);
 	TRACE("msd level 1");
-	return msd_finish_phase(st, v, lin, g, nkeep, tot.data(), recs.get(), d_lo == 0 && nkeep == (1u << g.b1), fo, so, sa_buf, hflag, S, unresolved, hstart);
+	return msd_finish_phase(st, v, lin, g, d_lo, nkeep, tot.data(), recs.get(), d_lo == 0 && nkeep == (1u << g.b1), fo, so, sa_buf, hflag, S, unresolved, hstart);
 }
 
 // (3) level 2, sub-bucket sizes and the finish on the `nkeep` bins whose records lie bin after bin in recs_ptr
 // (tot[b] of them in bin b); `whole`: these are all suffixes of the text (results may be streamed to the host)
-static bool msd_finish_phase(Stream & st, TextView const & v, int lin, MsdGeom const & g, uint32_t nkeep, const unsigned long long * tot,
+static bool msd_finish_phase(Stream & st, TextView const & v, int lin, MsdGeom const & g, uint32_t d_lo, uint32_t nkeep, const unsigned long long * tot,
                              unsigned long long * recs_ptr, bool whole, FusedOut const & fo, StreamOut * so, DevBuf<uint32_t> * sa_buf,
                              DevBuf<uint8_t> * hflag, SortStats & S, uint64_t & unresolved, uint64_t & hstart) {
 	unsigned const nb2 = 1u << g.b2;
@@ -442,7 +444,26 @@ static bool msd_finish_phase(Stream & st, TextView const & v, int lin, MsdGeom c
 	B3M_CUDA(cudaMemsetAsync(counters.get(), 0, 32 * MSD_CSLOTS, st.s));
 	uint32_t const imask = low_mask(std::min<unsigned>(fo.prelog, fo.isa_s ? fo.isalog : 32u));
 	uint32_t const rmask = fo.sa_s ? low_mask(fo.salog) : 0xffffffffu;
-	MsdFin F{v, lin, g.b1, g.b2, glog, nkeep, recs.get(), d_base, d_tpre, table.get(), sub.get(), 0u, nullptr, nullptr, fo, imask, rmask, counters.get()};
+	// linear windows: the sub-buckets that hold one of the last suffixes of the window
+	DevBuf<uint8_t> shortflag;
+	if (lin) {
+		shortflag.alloc(st, nsb);
+		B3M_CUDA(cudaMemsetAsync(shortflag.get(), 0, nsb, st.s));
+		B3M_LAUNCH(st, k_msd_shortflags, 1, 32, 0, v, g.b1, g.b2, d_lo, nkeep, shortflag.get());
+	}
+	MsdFin F{v, lin, g.b1, g.b2, glog, nkeep, recs.get(), d_base, d_tpre, table.get(), sub.get(), 0u, nullptr, nullptr, fo, imask, rmask, counters.get(), shortflag.get()};
+	// threads per finish CTA (MSD_CAP / threads records pass through each thread's registers)
+	static int fin_threads = 0;
+	if (!fin_threads) { const char * e = getenv("B3M_FIN_THREADS"); fin_threads = (e && atoi(e) == 1024) ? 1024 : 512; }
+	auto launch_fin = [&](bool order, const char * label, uint64_t bytes, unsigned grid) {
+		if (fin_threads == 1024) {
+			if (order) B3M_LAUNCH_T(st, label, bytes, (k_msd_finish<false, true, 1024>), grid, 1024, MSD_FIN_SMEM, F);
+			else B3M_LAUNCH_T(st, label, bytes, (k_msd_finish<true, false, 1024>), grid, 1024, MSD_FIN_SMEM, F);
+		} else {
+			if (order) B3M_LAUNCH_T(st, label, bytes, (k_msd_finish<false, true, 512>), grid, 512, MSD_FIN_SMEM, F);
+			else B3M_LAUNCH_T(st, label, bytes, (k_msd_finish<true, false, 512>), grid, 512, MSD_FIN_SMEM, F);
+		}
+	};
 	uint64_t const fbytes_per = 8 + 1; // record in, BWT code out (+ samples)
 	auto read_counters = [&](unsigned long long * hc) {
 		std::vector<unsigned long long> hcs(4 * MSD_CSLOTS);
@@ -462,7 +483,7 @@ static bool msd_finish_phase(Stream & st, TextView const & v, int lin, MsdGeom c
 		B3M_CUDA(cudaStreamSynchronize(st.s));
 		F.sb0 = (uint32_t)(w0 >> (64u - g.b1 - g.b2));
 		B3M_CUDA(cudaMemsetAsync(fo.special, 0xff, 8, st.s));
-		B3M_LAUNCH_T(st, "msd_finish", 0, (k_msd_finish<true, false>), 1, MSD_THREADS, MSD_FIN_SMEM, F);
+		launch_fin(false, "msd_finish", 0, 1);
 		uint32_t const row0 = fetch_u32(st, fo.special + 1);
 		unsigned long long hc0[4];
 		read_counters(hc0);
@@ -483,7 +504,7 @@ static bool msd_finish_phase(Stream & st, TextView const & v, int lin, MsdGeom c
 		uint32_t const s_lo = (uint32_t)(nsb * c / nchunks), s_hi = (uint32_t)(nsb * (c + 1) / nchunks);
 		F.sb0 = s_lo;
 		uint64_t const cm = nchunks > 1 ? (c + 1 == nchunks ? m : rows[c + 1]) - rows[c] : m;
-		B3M_LAUNCH_T(st, "msd_finish", cm * fbytes_per + cm / 4, (k_msd_finish<true, false>), s_hi - s_lo, MSD_THREADS, MSD_FIN_SMEM, F);
+		launch_fin(false, "msd_finish", cm * fbytes_per + cm / 4, s_hi - s_lo);
 		if (stream_sa || stream_bwa) {
 			uint64_t const rows_lo = c ? rows[c] + fo.shift : 0, rows_hi = (c + 1 == nchunks) ? W + fo.shift : rows[c + 1] + fo.shift;
 			cudaEvent_t ev;
@@ -521,7 +542,7 @@ static bool msd_finish_phase(Stream & st, TextView const & v, int lin, MsdGeom c
 		hflag->alloc(st, m);
 		B3M_CUDA(cudaMemsetAsync(counters.get(), 0, 32 * MSD_CSLOTS, st.s));
 		F.sb0 = 0; F.sa_out = sa_buf->get(); F.hflag = hflag->get(); F.fo = FusedOut();
-		B3M_LAUNCH_T(st, "msd_finish<order>", m * 13ull, (k_msd_finish<false, true>), (unsigned)nsb, MSD_THREADS, MSD_FIN_SMEM, F);
+		launch_fin(true, "msd_finish<order>", m * 13ull, (unsigned)nsb);
 		read_counters(hc);
 		S.other_bytes += m * 13ull + 32ull * hc[2];
 		// what every group left shares: a sub-bucket too large for a CTA b1+b2 bits, a crowded local digit at least
@@ -855,7 +876,7 @@ uint64_t k2_xshard_finish(Stream & st, DevText const & T, int circular, XShard &
 	S.rounds = 1; S.active_sum = X.records;
 	uint64_t unresolved = 0, hstart = 0;
 	if (nkeep && X.records) {
-		bool const ok = msd_finish_phase(st, v, !circular, g, nkeep, X.total.data() + d_lo, recs_own, false, fo, nullptr, nullptr, nullptr, S, unresolved, hstart);
+		bool const ok = msd_finish_phase(st, v, !circular, g, d_lo, nkeep, X.total.data() + d_lo, recs_own, false, fo, nullptr, nullptr, nullptr, S, unresolved, hstart);
 		B3M_REQUIRE(ok, "internal: xshard finish does not apply");
 	}
 	if (stats) {

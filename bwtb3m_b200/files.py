@@ -16,7 +16,7 @@ def _b(s):
 
 def compute_bwt(fn, inputtype="bytestream", outputfilename=None, sasamplingrate=32, isasamplingrate=262144, mem=0,
                 numthreads=0, bwtonly=False, tmpprefix=None, sparsetmpprefix=None, copyinputtomemory=False,
-                largelcpthres=16384, verbose=0, device=0, numblocks=0):
+                largelcpthres=16384, verbose=0, device=0, numblocks=0, ngpus=1):
     """BwtMergeSort::computeBwt(options) -> dict of result file names (BwtMergeSortResult)."""
     L = lib()
     o = Options()
@@ -29,6 +29,7 @@ def compute_bwt(fn, inputtype="bytestream", outputfilename=None, sasamplingrate=
     o.bwtonly = 1 if bwtonly else 0
     o.copyinputtomemory = 1 if copyinputtomemory else 0
     o.largelcpthres, o.verbose, o.device, o.numblocks = largelcpthres, verbose, device, numblocks
+    o.ngpus = ngpus
     r = Result()
     err = C.create_string_buffer(2048)
     if L.b3m_compute_bwt(C.byref(o), C.byref(r), err, len(err)) != 0:
