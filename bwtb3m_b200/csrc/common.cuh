@@ -10,6 +10,7 @@
 #include <vector>
 #include <map>
 #include <iterator>
+#include <atomic>
 
 namespace b3m {
 
@@ -201,6 +202,15 @@ struct DevBuf {
 	T * get() const { return p; }
 	size_t bytes() const { return n * sizeof(T); }
 };
+
+// true the first time it is called with this flag word on the current device (kernel attributes are per device,
+// and the multi-GPU host runs one thread per device inside one process)
+static inline bool first_on_device(std::atomic<uint64_t> & seen) {
+	int dev = 0;
+	B3M_CUDA(cudaGetDevice(&dev));
+	uint64_t const bit = 1ull << (dev & 63);
+	return !(seen.fetch_or(bit) & bit);
+}
 
 static inline unsigned ceil_log2_u64(uint64_t v) {
 	unsigned b = 0;

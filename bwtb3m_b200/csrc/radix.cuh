@@ -484,11 +484,10 @@ void radix_launch_pass(Stream & st, const char * label, uint64_t pbytes, RadixPa
 	uint32_t const nfull = (uint32_t)(n / RADIX_TILE);
 	bool const partial = (n % RADIX_TILE) != 0;
 	size_t const smem = radix_smem_bytes<NA, AUX>() + (TEXT ? (size_t)RADIX_TILE : 0);
-	static bool configured = false; // per template instance
-	if (!configured) {
+	static std::atomic<uint64_t> configured{0}; // per template instance and device
+	if (first_on_device(configured)) {
 		B3M_CUDA(cudaFuncSetAttribute(k_radix_onesweep<NA, AUX, TEXT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		B3M_CUDA(cudaFuncSetAttribute(k_radix_onesweep<NA, AUX, TEXT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		configured = true;
 	}
 	if (st.kt.on) {
 		KernelTimes::Rec r{label, pbytes, st.kt.get(), st.kt.get()};

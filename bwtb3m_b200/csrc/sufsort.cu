@@ -300,15 +300,12 @@ static void msd_hist(Stream & st, TextView const & v, unsigned b1, std::vector<u
 
 
 static void msd_configure() {
-	static bool done = false;
-	if (done) return;
+	static std::atomic<uint64_t> seen{0};
+	if (!first_on_device(seen)) return;
 	B3M_CUDA(cudaFuncSetAttribute(k_msd_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, MSD_TILE * 8));
 	B3M_CUDA(cudaFuncSetAttribute(k_msd_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (MSD_TILE + 2) * 8));
 	B3M_CUDA(cudaFuncSetAttribute(k_msd_finish<true, false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, MSD_FIN_SMEM));
 	B3M_CUDA(cudaFuncSetAttribute(k_msd_finish<false, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, MSD_FIN_SMEM));
-	B3M_CUDA(cudaFuncSetAttribute(k_msd_finish<true, false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, MSD_FIN_SMEM));
-	B3M_CUDA(cudaFuncSetAttribute(k_msd_finish<false, true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, MSD_FIN_SMEM));
-	done = true;
 }
 
 static uint32_t low_mask(unsigned log) { return log >= 32 ? 0xffffffffu : (1u << log) - 1u; }
@@ -452,17 +449,10 @@ static bool msd_finish_phase(Stream & st, TextView const & v, int lin, MsdGeom c
 		B3M_LAUNCH(st, k_msd_shortflags, 1, 32, 0, v, g.b1, g.b2, d_lo, nkeep, shortflag.get());
 	}
 	MsdFin F{v, lin, g.b1, g.b2, glog, nkeep, recs.get(), d_base, d_tpre, table.get(), sub.get(), 0u, nullptr, nullptr, fo, imask, rmask, counters.get(), shortflag.get()};
-	// threads per finish CTA (MSD_CAP / threads records pass through each thread's registers)
-	static int fin_threads = 0;
-	if (!fin_threads) { const char * e = getenv("B3M_FIN_THREADS"); fin_threads = (e && atoi(e) == 1024) ? 1024 : 512; }
+	// 512 threads per finish CTA, 16 records through each thread's registers (1024 x 8 measured 1.5 ms slower at cfg3, profiles/r2c_*)
 	auto launch_fin = [&](bool order, const char * label, uint64_t bytes, unsigned grid) {
-		if (fin_threads == 1024) {
-			if (order) B3M_LAUNCH_T(st, label, bytes, (k_msd_finish<false, true, 1024>), grid, 1024, MSD_FIN_SMEM, F);
-			else B3M_LAUNCH_T(st, label, bytes, (k_msd_finish<true, false, 1024>), grid, 1024, MSD_FIN_SMEM, F);
-		} else {
-			if (order) B3M_LAUNCH_T(st, label, bytes, (k_msd_finish<false, true, 512>), grid, 512, MSD_FIN_SMEM, F);
-			else B3M_LAUNCH_T(st, label, bytes, (k_msd_finish<true, false, 512>), grid, 512, MSD_FIN_SMEM, F);
-		}
+		if (order) B3M_LAUNCH_T(st, label, bytes, (k_msd_finish<false, true, 512>), grid, 512, MSD_FIN_SMEM, F);
+		else B3M_LAUNCH_T(st, label, bytes, (k_msd_finish<true, false, 512>), grid, 512, MSD_FIN_SMEM, F);
 	};
 	uint64_t const fbytes_per = 8 + 1; // record in, BWT code out (+ samples)
 	auto read_counters = [&](unsigned long long * hc) {
@@ -888,6 +878,128 @@ uint64_t k2_xshard_finish(Stream & st, DevText const & T, int circular, XShard &
 	return unresolved;
 }
 
+// ------------------------------------------------------------------------------------------
+// Prefix doubling, one round on the groups that fit a CTA (k_dbl_tile).  The active list holds the
+// suffixes of all groups of two or more, group after group: (g, i) = (place of the group's first member
+// in the suffix array, suffix).  A CTA owns the groups that START in its tile of the list and have at
+// most DT_GMAX members (it sees DT_GMAX elements on either side of the tile, so it knows).  It reads the
+// rank of the suffix h symbols ahead of every member (the only scattered access), and every member counts
+// the members of its group with a smaller key: that is its new place, and the new group id of all members
+// with an equal key.  Outputs, at the member's new place in the list: new group id, suffix, flags
+// (1: its new group still has two or more members, 2: member of a larger group -- passed through for the
+// radix round, 4: the group id changed).  The suffix array is updated in place (a group owns its range);
+// the rank array is NOT written here: other CTAs read it in the same round, and a mixture of old and new
+// ranks inside one comparison would order two suffixes of one old group wrongly.  The compaction pass that
+// follows writes the changed ranks.
+// ------------------------------------------------------------------------------------------
+constexpr int DT_THREADS = 512;
+constexpr int DT_TILE = 2048;
+constexpr int DT_GMAX = 256;
+constexpr int DT_REG = DT_TILE + 2 * DT_GMAX;
+constexpr int DT_PER = (DT_REG - DT_GMAX + DT_THREADS - 1) / DT_THREADS;
+
+// highest head at or below x, not below lo (-1: none)
+__device__ __forceinline__ int dbl_prev_head(const uint32_t * hb, int x, int lo) {
+	int q = x >> 5;
+	uint32_t w = hb[q] & (0xffffffffu >> (31 - (x & 31)));
+	for (;;) {
+		if (w) { int const p = q * 32 + 31 - __clz((int)w); return p >= lo ? p : -1; }
+		if (q * 32 <= lo) return -1;
+		w = hb[--q];
+	}
+}
+// lowest head above x, not above hi (-1: none)
+__device__ __forceinline__ int dbl_next_head(const uint32_t * hb, int x, int hi) {
+	int const x1 = x + 1;
+	int q = x1 >> 5;
+	uint32_t w = hb[q] & (0xffffffffu << (x1 & 31));
+	for (;;) {
+		if (w) { int const p = q * 32 + __ffs((int)w) - 1; return p <= hi ? p : -1; }
+		if ((q + 1) * 32 > hi) return -1;
+		w = hb[++q];
+	}
+}
+
+__global__ void __launch_bounds__(DT_THREADS)
+k_dbl_tile(const uint32_t * __restrict__ cg, const uint32_t * __restrict__ ci, uint32_t na, const uint32_t * __restrict__ rank,
+           uint32_t * __restrict__ sa, uint64_t h, uint64_t W, int circular, uint32_t * __restrict__ og, uint32_t * __restrict__ oi,
+           uint8_t * __restrict__ of, uint32_t * __restrict__ nbig) {
+	__shared__ uint32_t s_g[DT_REG], s_i[DT_REG], s_k[DT_REG];
+	__shared__ uint32_t s_hb[DT_REG / 32 + 1];
+	__shared__ uint32_t s_big;
+	uint32_t const t0 = blockIdx.x * (uint32_t)DT_TILE;
+	uint32_t const abase = t0 - (uint32_t)DT_GMAX; // region index x <-> list index abase + x; places before the list wrap to huge values
+	unsigned const lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	if (threadIdx.x == 0) s_big = 0;
+	for (int x = threadIdx.x; x < DT_REG; x += DT_THREADS) {
+		uint32_t const a = abase + (uint32_t)x;
+		bool const valid = a < na;
+		s_g[x] = valid ? cg[a] : 0xffffffffu;
+		s_i[x] = (valid && x >= DT_GMAX) ? ci[a] : 0u;
+	}
+	__syncthreads();
+	for (int q = w; q < DT_REG / 32; q += DT_THREADS / 32) {
+		int const x = q * 32 + (int)lane;
+		uint32_t const a = abase + (uint32_t)x;
+		bool const valid = a < na;
+		bool const head = !valid || a == 0 || x == 0 || s_g[x] != s_g[x - 1];
+		uint32_t const hb = __ballot_sync(0xffffffffu, head);
+		if (lane == 0) s_hb[q] = hb;
+	}
+	if (threadIdx.x == 0) s_hb[DT_REG / 32] = 0xffffffffu;
+	__syncthreads();
+	// group of every element of the tile and of the DT_GMAX elements behind it; the key of the members of my groups
+	uint32_t span[DT_PER]; // (first member) | (members << 16); 0: not mine
+	uint32_t nb = 0;
+	#pragma unroll
+	for (int j = 0; j < DT_PER; ++j) {
+		span[j] = 0;
+		int const x = DT_GMAX + j * DT_THREADS + (int)threadIdx.x;
+		if (x >= DT_REG) continue;
+		uint32_t const a = abase + (uint32_t)x;
+		if (a >= na) continue;
+		int const sx = dbl_prev_head(s_hb, x, x - DT_GMAX + 1);
+		int const ex = sx < 0 ? -1 : dbl_next_head(s_hb, x, sx + DT_GMAX);
+		bool const owned = x < DT_GMAX + DT_TILE;
+		if (sx < 0 || ex < 0) {
+			// a group of more than DT_GMAX members: left to the radix round
+			if (owned) { og[a] = s_g[x]; oi[a] = s_i[x]; of[a] = 2; ++nb; }
+			continue;
+		}
+		if (sx < DT_GMAX || sx >= DT_GMAX + DT_TILE) continue; // a group of the neighbouring tile
+		span[j] = (uint32_t)sx | ((uint32_t)(ex - sx) << 16);
+		uint64_t jj = (uint64_t)s_i[x] + h;
+		uint32_t k;
+		if (circular) { if (jj >= W) jj %= W; k = rank[jj]; }
+		else k = (jj < W) ? rank[jj] + 1u : 0u;
+		s_k[x] = k;
+	}
+	if (nb) atomicAdd(&s_big, nb);
+	__syncthreads();
+	#pragma unroll
+	for (int j = 0; j < DT_PER; ++j) {
+		if (!span[j]) continue;
+		int const x = DT_GMAX + j * DT_THREADS + (int)threadIdx.x;
+		int const sx = (int)(span[j] & 0xffffu), n = (int)(span[j] >> 16);
+		uint32_t const k = s_k[x];
+		uint32_t less = 0, eqb = 0, eq = 0;
+		#pragma unroll 4
+		for (int y = sx; y < sx + n; ++y) {
+			uint32_t const o = s_k[y];
+			less += o < k ? 1u : 0u;
+			eq += o == k ? 1u : 0u;
+			eqb += (o == k && y < x) ? 1u : 0u;
+		}
+		uint32_t const g = s_g[x], i = s_i[x];
+		uint32_t const a2 = abase + (uint32_t)sx + less + eqb;
+		sa[g + less + eqb] = i;
+		og[a2] = g + less;
+		oi[a2] = i;
+		of[a2] = (uint8_t)((eq > 1 ? 1u : 0u) | (less ? 4u : 0u));
+	}
+	if (threadIdx.x == 0 && s_big) atomicAdd(nbig, s_big);
+}
+
 void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W, int circular, int text_wraps,
                     DevBuf<uint32_t> & sa_buf, uint32_t * rank, SortStats * stats, const FusedOut * fo, StreamOut * so) {
 	if (W == 0) return;
@@ -1081,24 +1193,27 @@ void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W,
 		// roles: bufs[0]=grp, bufs[1]=idx, bufs[2]=key2, bufs[3..5]=ping-pong partners
 		uint64_t h = hstart;
 		int const bw = (int)ceil_log2_u64(W + 2);
-		while (na) {
-			if (circular && h >= W) break; // non-primitive text: ties stay in current order (unpinned, DESIGN.md)
-			unsigned const grid = (unsigned)div_up(na, 256);
-			B3M_LAUNCH_T(st, "gather_ahead", na * 40ull, k_gather_ahead, grid, 256, 0, (const uint32_t *)bufs[1], na, (const uint32_t *)rank, h, W, circular, bufs[2]);
-			S.other_bytes += na * (4ull + 32ull + 4ull);
+		// one round of the radix path on the list b[0] = group, b[1] = suffix (n entries; b[2] = key if key_ready): gather the
+		// rank ahead, sort by (group, rank ahead), split the groups; returns the entries still active, left in b[0], b[1]
+		auto radix_round = [&](uint32_t ** b, uint64_t n, bool key_ready) -> uint64_t {
+			unsigned const grid = (unsigned)div_up(n, 256);
+			if (!key_ready) {
+				B3M_LAUNCH_T(st, "gather_ahead", n * 40ull, k_gather_ahead, grid, 256, 0, (const uint32_t *)b[1], n, (const uint32_t *)rank, h, W, circular, b[2]);
+				S.other_bytes += n * (4ull + 32ull + 4ull);
+			}
 			TRACE("rN gather");
-			RadixRec<3> cur{{bufs[0], bufs[2], bufs[1]}}, alt{{bufs[3], bufs[4], bufs[5]}};
+			RadixRec<3> cur{{b[0], b[2], b[1]}}, alt{{b[3], b[4], b[5]}};
 			RadixStats rs;
-			radix_sort_bits<3>(st, cur, alt, 1, na, 0, bw, &rs); // rank ahead (minor key)
-			radix_sort_bits<3>(st, cur, alt, 0, na, 0, bw, &rs); // group (major key)
-			S.radix_passes += rs.passes; S.radix_bytes += rs.bytes; S.active_sum += na; S.rounds++;
+			radix_sort_bits<3>(st, cur, alt, 1, n, 0, bw, &rs); // rank ahead (minor key)
+			radix_sort_bits<3>(st, cur, alt, 0, n, 0, bw, &rs); // group (major key)
+			S.radix_passes += rs.passes; S.radix_bytes += rs.bytes;
 			TRACE("rN radix");
 			const uint32_t * sg = cur.a[0];
 			const uint32_t * sk = cur.a[1];
 			const uint32_t * si = cur.a[2];
 			uint32_t * ngrp = alt.a[0];
-			uint64_t const nam = na;
-			scan_apply<OpMaxMax>(st, na,
+			uint64_t const nam = n;
+			scan_apply<OpMaxMax>(st, n,
 				[=] __device__(uint64_t a) -> uint2 {
 					if (a == 0) return make_uint2(0u, 0u);
 					bool const seg = sg[a] != sg[a - 1];
@@ -1114,8 +1229,8 @@ void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W,
 					sa[g + ((uint32_t)a - segstart)] = i;
 					rank[i] = ng;
 					ngrp[a] = ng;
-				}, "split_scatter", na * 92ull);
-			S.other_bytes += na * (2 * 12ull + 4ull + 32ull + 32ull);
+				}, "split_scatter", n * 92ull);
+			S.other_bytes += n * (2 * 12ull + 4ull + 32ull + 32ull);
 			auto active = [=] __device__(uint64_t a) -> uint32_t {
 				bool const hk = (a == 0) || (ngrp[a] != ngrp[a - 1]);
 				bool const hn = (a + 1 == nam) || (ngrp[a + 1] != ngrp[a]);
@@ -1123,18 +1238,75 @@ void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W,
 			};
 			uint32_t * ogrp = alt.a[1];
 			uint32_t * oidx = alt.a[2];
-			scan_apply<OpSum>(st, na, active,
+			scan_apply<OpSum>(st, n, active,
 				[=] __device__(uint64_t a, uint32_t excl, uint32_t v0) {
 					if (v0) { ogrp[excl] = ngrp[a]; oidx[excl] = si[a]; }
 					if (a + 1 == nam) *d_total = excl + v0;
 				});
-			S.other_bytes += na * (2 * 8ull + 8ull);
+			S.other_bytes += n * (2 * 8ull + 8ull);
 			uint64_t const nn = fetch_u32(st, d_total);
 			TRACE("rN split+compact");
 			// next round: grp = alt[1], idx = alt[2]; everything else is free
-			uint32_t * nb[6] = {alt.a[1], alt.a[2], cur.a[0], cur.a[1], cur.a[2], alt.a[0]};
-			for (int b = 0; b < 6; ++b) bufs[b] = nb[b];
-			na = nn;
+			uint32_t * nbuf[6] = {alt.a[1], alt.a[2], cur.a[0], cur.a[1], cur.a[2], alt.a[0]};
+			for (int q = 0; q < 6; ++q) b[q] = nbuf[q];
+			return nn;
+		};
+		bool const tile_rounds = st.sortpath != B3M_SORT_LSD; // B3M_SORT_LSD keeps the plain radix rounds (tests compare the two)
+		while (na) {
+			if (circular && h >= W) break; // non-primitive text: ties stay in current order (unpinned, DESIGN.md)
+			S.active_sum += na; S.rounds++;
+			if (tile_rounds) {
+				// groups of at most DT_GMAX members are sorted inside a CTA; the members of larger ones are passed through
+				uint32_t * cg = bufs[0], * ci = bufs[1], * og = bufs[2], * oi = bufs[3];
+				uint8_t * of = reinterpret_cast<uint8_t *>(bufs[4]);
+				B3M_CUDA(cudaMemsetAsync(d_total + 1, 0, 4, st.s));
+				B3M_LAUNCH_T(st, "dbl_tile", na * 59ull, k_dbl_tile, (unsigned)div_up(na, DT_TILE), DT_THREADS, 0, (const uint32_t *)cg, (const uint32_t *)ci, (uint32_t)na,
+				             (const uint32_t *)rank, sa, h, W, circular, og, oi, of, d_total + 1);
+				S.other_bytes += na * (8ull + 32ull + 4ull + 9ull);
+				uint64_t const nbig = fetch_u32(st, d_total + 1);
+				TRACE("rN tile");
+				if (nbig <= na / 4) {
+					DevBuf<uint32_t> bpool[6];
+					uint32_t * bb[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+					uint64_t const nam = na;
+					if (nbig) {
+						// the larger groups: their members, in list order, and the ranks ahead of them (before any rank of this round is written)
+						for (int q = 0; q < 6; ++q) { bpool[q].alloc(st, nbig); bb[q] = bpool[q].get(); }
+						uint32_t * bg = bb[0], * bi = bb[1];
+						scan_apply<OpSum>(st, na,
+							[=] __device__(uint64_t k) -> uint32_t { return (of[k] >> 1) & 1u; },
+							[=] __device__(uint64_t k, uint32_t excl, uint32_t v0) { if (v0) { bg[excl] = og[k]; bi[excl] = oi[k]; } });
+						B3M_LAUNCH_T(st, "gather_ahead", nbig * 40ull, k_gather_ahead, (unsigned)div_up(nbig, 256), 256, 0, (const uint32_t *)bi, nbig, (const uint32_t *)rank, h, W, circular, bb[2]);
+						S.other_bytes += na * 9ull + nbig * 48ull;
+					}
+					// the changed ranks are written now; members of groups still tied make the next list
+					scan_apply<OpSum>(st, na,
+						[=] __device__(uint64_t k) -> uint32_t { return of[k] & 1u; },
+						[=] __device__(uint64_t k, uint32_t excl, uint32_t v0) {
+							uint32_t const f = of[k];
+							if (f & 4u) rank[oi[k]] = og[k];
+							if (v0) { cg[excl] = og[k]; ci[excl] = oi[k]; }
+							if (k + 1 == nam) *d_total = excl + v0;
+						}, "dbl_compact", na * 50ull);
+					S.other_bytes += na * (2 * 9ull + 32ull);
+					uint64_t nn = fetch_u32(st, d_total);
+					TRACE("rN compact");
+					if (nbig) {
+						uint64_t const nn2 = radix_round(bb, nbig, true);
+						if (nn2) {
+							B3M_CUDA(cudaMemcpyAsync(cg + nn, bb[0], nn2 * 4, cudaMemcpyDeviceToDevice, st.s));
+							B3M_CUDA(cudaMemcpyAsync(ci + nn, bb[1], nn2 * 4, cudaMemcpyDeviceToDevice, st.s));
+							B3M_CUDA(cudaStreamSynchronize(st.s)); // bpool is released below
+						}
+						nn += nn2;
+					}
+					na = nn;
+					h *= 2;
+					continue;
+				}
+				// mostly large groups: the radix round redoes the whole list (the tile kernel wrote nothing that round reads)
+			}
+			na = radix_round(bufs, na, false);
 			h *= 2;
 		}
 		if (fo) {

@@ -101,6 +101,39 @@ def test_mutated_copies(eng, oracle):
     check_all(oracle, res, t, 64, 32, 64)
 
 
+@pytest.mark.parametrize("copies,base_len,rate", [(300, 3_000, 1e-3), (257, 2_500, 3e-3), (40, 20_000, 1e-4), (600, 1_200, 2e-2)])
+def test_doubling_rounds_tile_and_radix(eng, oracle, copies, base_len, rate):
+    """Prefix-doubling rounds (sufsort.cu k_dbl_tile): groups of up to 256 tied suffixes are split inside a CTA,
+    larger ones go through the radix round; texts whose groups lie on both sides of that limit and cross it as the
+    rounds split them.  The order must equal the oracle's and the one of the radix-only rounds (sortpath="lsd")."""
+    from bwtb3m_b200 import workloads
+    data = workloads.repetitive_pac(copies, base_len, copies + 1, rate=rate)
+    t = oracle.decode_pac(data.tobytes(), term=True)
+    res, info = run(eng, data, "pacterm", preisarate=64, sasamplingrate=32, isasamplingrate=64, sortpath="msd")
+    assert info["sort_unresolved0"] > t.size // 2 and info["sort_rounds"] > 2
+    check_all(oracle, res, t, 64, 32, 64)
+    res2, info2 = run(eng, data, "pacterm", preisarate=64, sasamplingrate=32, isasamplingrate=64, sortpath="lsd")
+    for k in ("bwt", "preisa", "sa", "isa"):
+        assert np.array_equal(res[k], res2[k])
+
+
+def test_doubling_rounds_circular_bytes(eng, oracle):
+    """The same rounds on a circular text (bytestream ACGT codes): ranks ahead wrap around the end."""
+    rng = np.random.default_rng(5)
+    base = rng.integers(0, 4, size=9_000, dtype=np.uint8)
+    parts = []
+    for c in range(70):
+        x = base.copy()
+        pos = rng.integers(0, base.size, size=12)
+        x[pos] = (x[pos] + 1) & 3
+        parts.append(x)
+    parts.append(rng.integers(0, 4, size=777, dtype=np.uint8))  # makes the circular text primitive
+    data, t = make(oracle, "bytestream", np.concatenate(parts))
+    res, info = run(eng, data, "bytestream", preisarate=64, sasamplingrate=32, isasamplingrate=64, sortpath="msd")
+    assert info["sort_rounds"] > 2
+    check_all(oracle, res, t, 64, 32, 64)
+
+
 def test_tail_compares_by_length(eng, oracle):
     """pacterm: suffixes that reach the terminator inside the record's bits or the second key."""
     for l in (64, 65, 79, 80, 81, 95, 96, 97, 128, 200):

@@ -101,5 +101,5 @@ def test_cli_ngpus(tmp_path, oracle):
             assert "%d GPUs" % n in r.stderr and "xshard" in r.stderr, r.stderr
         outs[tag] = {suf: open(str(out)[:-4] + suf, "rb").read() for suf in (".bwt", ".hist", ".sa", ".isa")}
     assert outs["one"] == outs["multi"]
-    r = subprocess.run([os.path.join(ROOT, "bin", "bwtb3m"), "inputtype=pacterm", "ngpus=99", str(fn)], capture_output=True, text=True)
+    r = subprocess.run([os.path.join(ROOT, "bin", "bwtb3m"), "inputtype=pacterm", "ngpus=16", str(fn)], capture_output=True, text=True)  # a box has at most 8
     assert r.returncode != 0 and "does not exist" in r.stderr
