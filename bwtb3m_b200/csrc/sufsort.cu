@@ -879,24 +879,31 @@ uint64_t k2_xshard_finish(Stream & st, DevText const & T, int circular, XShard &
 }
 
 // ------------------------------------------------------------------------------------------
-// Prefix doubling, one round on the groups that fit a CTA (k_dbl_tile).  The active list holds the
-// suffixes of all groups of two or more, group after group: (g, i) = (place of the group's first member
+// Prefix doubling, one round on the groups that fit a CTA (k_dbl_tile + k_dbl_compact).  The active list holds
+// the suffixes of all groups of two or more, group after group: (g, i) = (place of the group's first member
 // in the suffix array, suffix).  A CTA owns the groups that START in its tile of the list and have at
 // most DT_GMAX members (it sees DT_GMAX elements on either side of the tile, so it knows).  It reads the
 // rank of the suffix h symbols ahead of every member (the only scattered access), and every member counts
 // the members of its group with a smaller key: that is its new place, and the new group id of all members
-// with an equal key.  Outputs, at the member's new place in the list: new group id, suffix, flags
-// (1: its new group still has two or more members, 2: member of a larger group -- passed through for the
-// radix round, 4: the group id changed).  The suffix array is updated in place (a group owns its range);
-// the rank array is NOT written here: other CTAs read it in the same round, and a mixture of old and new
-// ranks inside one comparison would order two suffixes of one old group wrongly.  The compaction pass that
-// follows writes the changed ranks.
+// with an equal key.  Most members of a group of near-identical copies carry the key of the group's first
+// member: those get their place from three group totals (members below that key, members off that key in
+// front of them -- a bitmap and its prefix counts) without looking at any other member; the others
+// ("deviants") are queued and counted against the whole group by consecutive threads afterwards, so that no
+// warp walks a group for one lane.  Outputs, at the member's new place in the list: new group id, suffix,
+// flags (1: its new group still has two or more members, 2: member of a larger group -- passed through for
+// the radix round, 4: the group id changed); and, per tile of list places, how many entries carry flag 1
+// (tcount; a CTA's groups reach into the next tile at most).  The suffix array is updated in place (a group
+// owns its range); the rank array is NOT written here: other CTAs read it in the same round, and a mixture
+// of old and new ranks inside one comparison would order two suffixes of one old group wrongly.
+// k_dbl_compact, after a scan of tcount, writes the changed ranks and the next list.
 // ------------------------------------------------------------------------------------------
 constexpr int DT_THREADS = 512;
 constexpr int DT_TILE = 2048;
 constexpr int DT_GMAX = 256;
 constexpr int DT_REG = DT_TILE + 2 * DT_GMAX;
 constexpr int DT_PER = (DT_REG - DT_GMAX + DT_THREADS - 1) / DT_THREADS;
+constexpr int DT_WORDS = DT_REG / 32;
+static_assert(DT_REG % 32 == 0 && DT_GMAX % 32 == 0 && DT_TILE % DT_THREADS == 0, "tile geometry");
 
 // highest head at or below x, not below lo (-1: none)
 __device__ __forceinline__ int dbl_prev_head(const uint32_t * hb, int x, int lo) {
@@ -923,22 +930,28 @@ __device__ __forceinline__ int dbl_next_head(const uint32_t * hb, int x, int hi)
 __global__ void __launch_bounds__(DT_THREADS)
 k_dbl_tile(const uint32_t * __restrict__ cg, const uint32_t * __restrict__ ci, uint32_t na, const uint32_t * __restrict__ rank,
            uint32_t * __restrict__ sa, uint64_t h, uint64_t W, int circular, uint32_t * __restrict__ og, uint32_t * __restrict__ oi,
-           uint8_t * __restrict__ of, uint32_t * __restrict__ nbig) {
+           uint8_t * __restrict__ of, uint32_t * __restrict__ nbig, uint32_t * __restrict__ tcount) {
 	__shared__ uint32_t s_g[DT_REG], s_i[DT_REG], s_k[DT_REG];
-	__shared__ uint32_t s_hb[DT_REG / 32 + 1];
-	__shared__ uint32_t s_big;
+	__shared__ uint32_t s_nlt[DT_REG];      // at a group's first member: members with a key below that member's
+	__shared__ uint16_t s_q[DT_REG];        // queue of deviants
+	__shared__ uint32_t s_hb[DT_WORDS + 1]; // heads
+	__shared__ uint32_t s_db[DT_WORDS + 1]; // deviants
+	__shared__ uint32_t s_dpre[DT_WORDS + 1];
+	__shared__ uint32_t s_big, s_nq, s_cnt[2];
 	uint32_t const t0 = blockIdx.x * (uint32_t)DT_TILE;
 	uint32_t const abase = t0 - (uint32_t)DT_GMAX; // region index x <-> list index abase + x; places before the list wrap to huge values
 	unsigned const lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-	if (threadIdx.x == 0) s_big = 0;
+	if (threadIdx.x == 0) { s_big = 0; s_nq = 0; s_cnt[0] = 0; s_cnt[1] = 0; }
 	for (int x = threadIdx.x; x < DT_REG; x += DT_THREADS) {
 		uint32_t const a = abase + (uint32_t)x;
 		bool const valid = a < na;
 		s_g[x] = valid ? cg[a] : 0xffffffffu;
 		s_i[x] = (valid && x >= DT_GMAX) ? ci[a] : 0u;
+		s_nlt[x] = 0;
 	}
+	if (threadIdx.x <= DT_WORDS) s_db[threadIdx.x] = 0;
 	__syncthreads();
-	for (int q = w; q < DT_REG / 32; q += DT_THREADS / 32) {
+	for (int q = w; q < DT_WORDS; q += DT_THREADS / 32) {
 		int const x = q * 32 + (int)lane;
 		uint32_t const a = abase + (uint32_t)x;
 		bool const valid = a < na;
@@ -946,7 +959,7 @@ k_dbl_tile(const uint32_t * __restrict__ cg, const uint32_t * __restrict__ ci, u
 		uint32_t const hb = __ballot_sync(0xffffffffu, head);
 		if (lane == 0) s_hb[q] = hb;
 	}
-	if (threadIdx.x == 0) s_hb[DT_REG / 32] = 0xffffffffu;
+	if (threadIdx.x == 0) s_hb[DT_WORDS] = 0xffffffffu;
 	__syncthreads();
 	// group of every element of the tile and of the DT_GMAX elements behind it; the key of the members of my groups
 	uint32_t span[DT_PER]; // (first member) | (members << 16); 0: not mine
@@ -976,28 +989,131 @@ k_dbl_tile(const uint32_t * __restrict__ cg, const uint32_t * __restrict__ ci, u
 	}
 	if (nb) atomicAdd(&s_big, nb);
 	__syncthreads();
+	// deviants: members whose key is not the one of their group's first member
 	#pragma unroll
 	for (int j = 0; j < DT_PER; ++j) {
-		if (!span[j]) continue;
-		int const x = DT_GMAX + j * DT_THREADS + (int)threadIdx.x;
-		int const sx = (int)(span[j] & 0xffffu), n = (int)(span[j] >> 16);
-		uint32_t const k = s_k[x];
-		uint32_t less = 0, eqb = 0, eq = 0;
-		#pragma unroll 4
-		for (int y = sx; y < sx + n; ++y) {
-			uint32_t const o = s_k[y];
-			less += o < k ? 1u : 0u;
-			eq += o == k ? 1u : 0u;
-			eqb += (o == k && y < x) ? 1u : 0u;
+		int const x = DT_GMAX + j * DT_THREADS + (int)threadIdx.x; // a warp covers the 32 places of one bitmap word
+		bool dev = false;
+		if (span[j]) {
+			int const sx = (int)(span[j] & 0xffffu);
+			uint32_t const k = s_k[x], k0 = s_k[sx];
+			dev = k != k0;
+			if (k < k0) atomicAdd(&s_nlt[sx], 1u);
 		}
+		uint32_t const b = __ballot_sync(0xffffffffu, dev);
+		if (x < DT_REG) {
+			uint32_t qb = 0;
+			if (lane == 0) { s_db[x >> 5] = b; if (b) qb = atomicAdd(&s_nq, (uint32_t)__popc(b)); }
+			qb = __shfl_sync(0xffffffffu, qb, 0);
+			if (dev) s_q[qb + __popc(b & lanemask_lt())] = (uint16_t)x;
+		}
+	}
+	__syncthreads();
+	if (w == 0) { // prefix counts of the deviant bitmap, word by word
+		uint32_t run = 0;
+		for (int q0 = 0; q0 < DT_WORDS + 1; q0 += 32) {
+			int const q = q0 + (int)lane;
+			uint32_t const c = q < DT_WORDS ? (uint32_t)__popc(s_db[q]) : 0u;
+			uint32_t incl = c;
+			#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { uint32_t const t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += t; }
+			if (q <= DT_WORDS) s_dpre[q] = run + incl - c;
+			run += __shfl_sync(0xffffffffu, incl, 31);
+		}
+	}
+	__syncthreads();
+	uint32_t n_own = 0, n_next = 0; // entries still tied, by the tile of the list they land in
+	auto emit = [&](int x, int sx, uint32_t less, uint32_t eqb, uint32_t eq) {
 		uint32_t const g = s_g[x], i = s_i[x];
 		uint32_t const a2 = abase + (uint32_t)sx + less + eqb;
 		sa[g + less + eqb] = i;
 		og[a2] = g + less;
 		oi[a2] = i;
 		of[a2] = (uint8_t)((eq > 1 ? 1u : 0u) | (less ? 4u : 0u));
+		if (eq > 1) { if (a2 - t0 < (uint32_t)DT_TILE) ++n_own; else ++n_next; }
+	};
+	auto devs_before = [&](int x) -> uint32_t { return s_dpre[x >> 5] + (uint32_t)__popc(s_db[x >> 5] & ((1u << (x & 31)) - 1u)); };
+	#pragma unroll
+	for (int j = 0; j < DT_PER; ++j) {
+		if (!span[j]) continue;
+		int const x = DT_GMAX + j * DT_THREADS + (int)threadIdx.x;
+		int const sx = (int)(span[j] & 0xffffu), n = (int)(span[j] >> 16);
+		if (s_k[x] != s_k[sx]) continue; // queued
+		uint32_t const d0 = devs_before(sx);
+		emit(x, sx, s_nlt[sx], (uint32_t)(x - sx) - (devs_before(x) - d0), (uint32_t)n - (devs_before(sx + n) - d0));
 	}
-	if (threadIdx.x == 0 && s_big) atomicAdd(nbig, s_big);
+	uint32_t const nq = s_nq;
+	for (uint32_t q = threadIdx.x; q < nq; q += DT_THREADS) {
+		int const x = (int)s_q[q];
+		int const sx = dbl_prev_head(s_hb, x, x - DT_GMAX + 1);
+		int const ex = dbl_next_head(s_hb, x, sx + DT_GMAX);
+		uint32_t const k = s_k[x];
+		uint32_t less = 0, eqb = 0, eq = 0;
+		#pragma unroll 4
+		for (int y = sx; y < ex; ++y) {
+			uint32_t const o = s_k[y];
+			less += o < k ? 1u : 0u;
+			eq += o == k ? 1u : 0u;
+			eqb += (o == k && y < x) ? 1u : 0u;
+		}
+		emit(x, sx, less, eqb, eq);
+	}
+	n_own = __reduce_add_sync(0xffffffffu, n_own);
+	n_next = __reduce_add_sync(0xffffffffu, n_next);
+	if (lane == 0) { if (n_own) atomicAdd(&s_cnt[0], n_own); if (n_next) atomicAdd(&s_cnt[1], n_next); }
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		if (s_big) atomicAdd(nbig, s_big);
+		if (s_cnt[0]) atomicAdd(&tcount[blockIdx.x], s_cnt[0]);
+		if (s_cnt[1]) atomicAdd(&tcount[blockIdx.x + 1], s_cnt[1]);
+	}
+}
+
+// The pass behind k_dbl_tile: list places in order, DT_TILE per CTA.  Writes the ranks that changed in this round
+// (now that every CTA has read the old ones) and moves the entries still tied to the front: tbase = exclusive scan
+// of k_dbl_tile's per-tile counts, the place inside the tile from ballots (warp w handles places w*32.. of every
+// DT_THREADS-wide row, all accesses coalesced).
+__global__ void __launch_bounds__(DT_THREADS)
+k_dbl_compact(const uint32_t * __restrict__ og, const uint32_t * __restrict__ oi, const uint8_t * __restrict__ of, uint32_t na,
+              const uint32_t * __restrict__ tbase, uint32_t * __restrict__ rank, uint32_t * __restrict__ cg, uint32_t * __restrict__ ci) {
+	constexpr int ROWS = DT_TILE / DT_THREADS, WARPS = DT_THREADS / 32;
+	__shared__ uint32_t s_pre[ROWS * WARPS];
+	uint32_t const t0 = blockIdx.x * (uint32_t)DT_TILE;
+	unsigned const lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	uint32_t f[ROWS], bal[ROWS];
+	#pragma unroll
+	for (int j = 0; j < ROWS; ++j) {
+		uint32_t const a = t0 + (uint32_t)(j * DT_THREADS) + threadIdx.x;
+		f[j] = a < na ? (uint32_t)of[a] : 0u;
+		bal[j] = __ballot_sync(0xffffffffu, f[j] & 1u);
+		if (lane == 0) s_pre[j * WARPS + w] = (uint32_t)__popc(bal[j]);
+	}
+	__syncthreads();
+	if (w == 0) {
+		uint32_t run = 0;
+		#pragma unroll
+		for (int q0 = 0; q0 < ROWS * WARPS; q0 += 32) {
+			uint32_t const c = s_pre[q0 + lane];
+			uint32_t incl = c;
+			#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { uint32_t const t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (unsigned)o) incl += t; }
+			s_pre[q0 + lane] = run + incl - c;
+			run += __shfl_sync(0xffffffffu, incl, 31);
+		}
+	}
+	__syncthreads();
+	uint32_t const base = tbase[blockIdx.x];
+	#pragma unroll
+	for (int j = 0; j < ROWS; ++j) {
+		if (!(f[j] & 5u)) continue;
+		uint32_t const a = t0 + (uint32_t)(j * DT_THREADS) + threadIdx.x;
+		uint32_t const g = og[a], i = oi[a];
+		if (f[j] & 4u) rank[i] = g;
+		if (f[j] & 1u) {
+			uint32_t const dst = base + s_pre[j * WARPS + w] + (uint32_t)__popc(bal[j] & lanemask_lt());
+			cg[dst] = g; ci[dst] = i;
+		}
+	}
 }
 
 void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W, int circular, int text_wraps,
@@ -1259,16 +1375,18 @@ void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W,
 				// groups of at most DT_GMAX members are sorted inside a CTA; the members of larger ones are passed through
 				uint32_t * cg = bufs[0], * ci = bufs[1], * og = bufs[2], * oi = bufs[3];
 				uint8_t * of = reinterpret_cast<uint8_t *>(bufs[4]);
+				uint32_t const ntiles = (uint32_t)div_up(na, DT_TILE);
+				DevBuf<uint32_t> tcount(st, (uint64_t)ntiles + 1);
+				B3M_CUDA(cudaMemsetAsync(tcount.get(), 0, tcount.bytes(), st.s));
 				B3M_CUDA(cudaMemsetAsync(d_total + 1, 0, 4, st.s));
-				B3M_LAUNCH_T(st, "dbl_tile", na * 59ull, k_dbl_tile, (unsigned)div_up(na, DT_TILE), DT_THREADS, 0, (const uint32_t *)cg, (const uint32_t *)ci, (uint32_t)na,
-				             (const uint32_t *)rank, sa, h, W, circular, og, oi, of, d_total + 1);
+				B3M_LAUNCH_T(st, "dbl_tile", na * 59ull, k_dbl_tile, ntiles, DT_THREADS, 0, (const uint32_t *)cg, (const uint32_t *)ci, (uint32_t)na,
+				             (const uint32_t *)rank, sa, h, W, circular, og, oi, of, d_total + 1, tcount.get());
 				S.other_bytes += na * (8ull + 32ull + 4ull + 9ull);
 				uint64_t const nbig = fetch_u32(st, d_total + 1);
 				TRACE("rN tile");
 				if (nbig <= na / 4) {
 					DevBuf<uint32_t> bpool[6];
 					uint32_t * bb[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-					uint64_t const nam = na;
 					if (nbig) {
 						// the larger groups: their members, in list order, and the ranks ahead of them (before any rank of this round is written)
 						for (int q = 0; q < 6; ++q) { bpool[q].alloc(st, nbig); bb[q] = bpool[q].get(); }
@@ -1280,15 +1398,11 @@ void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W,
 						S.other_bytes += na * 9ull + nbig * 48ull;
 					}
 					// the changed ranks are written now; members of groups still tied make the next list
-					scan_apply<OpSum>(st, na,
-						[=] __device__(uint64_t k) -> uint32_t { return of[k] & 1u; },
-						[=] __device__(uint64_t k, uint32_t excl, uint32_t v0) {
-							uint32_t const f = of[k];
-							if (f & 4u) rank[oi[k]] = og[k];
-							if (v0) { cg[excl] = og[k]; ci[excl] = oi[k]; }
-							if (k + 1 == nam) *d_total = excl + v0;
-						}, "dbl_compact", na * 50ull);
-					S.other_bytes += na * (2 * 9ull + 32ull);
+					scan_exclusive_inplace<OpSum>(st, tcount.get(), (uint64_t)ntiles + 1);
+					B3M_LAUNCH_T(st, "dbl_compact", na * 49ull, k_dbl_compact, ntiles, DT_THREADS, 0, (const uint32_t *)og, (const uint32_t *)oi, (const uint8_t *)of, (uint32_t)na,
+					             (const uint32_t *)tcount.get(), rank, cg, ci);
+					S.other_bytes += na * (9ull + 8ull + 32ull);
+					B3M_CUDA(cudaMemcpyAsync(d_total, tcount.get() + ntiles, 4, cudaMemcpyDeviceToDevice, st.s));
 					uint64_t nn = fetch_u32(st, d_total);
 					TRACE("rN compact");
 					if (nbig) {
