@@ -66,7 +66,7 @@ EXPORTS = [
     "b3m_engine_blk_merge", "b3m_engine_blk_merge_samples", "b3m_engine_blk_finish",
     "b3m_engine_default_preisarate", "b3m_engine_fetch_bwa",
     "b3m_engine_shard_build", "b3m_engine_shard_finish", "b3m_engine_shard_rows", "b3m_engine_pack_rows", "b3m_engine_unpack_rows",
-    "b3m_engine_shard_adopt", "b3m_engine_xshard_count", "b3m_engine_xshard_scatter", "b3m_engine_xshard_finish", "b3m_dev_alloc", "b3m_dev_free", "b3m_ipc_export", "b3m_ipc_open", "b3m_ipc_close",
+    "b3m_engine_shard_adopt", "b3m_engine_xshard_count", "b3m_engine_xshard_scatter", "b3m_engine_xshard_finish", "b3m_dev_alloc", "b3m_dev_free", "b3m_ipc_export", "b3m_ipc_open", "b3m_ipc_close", "b3m_dev_copy", "b3m_engine_pack_bwa",
     "b3m_multi_create", "b3m_multi_destroy", "b3m_multi_last_error", "b3m_multi_load_host", "b3m_multi_build", "b3m_multi_engine", "b3m_multi_stats",
 ]
 
@@ -113,6 +113,8 @@ def lib():
     L.b3m_ipc_export.argtypes = [C.c_int, vp, C.c_char_p, C.c_char_p, C.c_size_t]
     L.b3m_ipc_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(vp), C.c_char_p, C.c_size_t]
     L.b3m_ipc_close.argtypes = [C.c_int, vp, C.c_char_p, C.c_size_t]
+    L.b3m_dev_copy.argtypes = [C.c_int, vp, vp, u64, vp, C.c_char_p, C.c_size_t]
+    L.b3m_engine_pack_bwa.argtypes = [vp, vp, u64, u64]
     L.b3m_multi_create.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(vp), C.c_char_p, C.c_size_t]
     L.b3m_multi_destroy.argtypes = [vp]
     L.b3m_multi_destroy.restype = None

@@ -502,6 +502,7 @@ void Engine::kr_finish(const void * d_bwt, const void * d_prerank, const void * 
 	if (nsa) { sa.alloc(st, nsa); B3M_CUDA(cudaMemcpyAsync(sa.get(), d_sa, 8 * nsa, cudaMemcpyDeviceToDevice, st.s)); }
 	if (nisa) { isa.alloc(st, nisa); B3M_CUDA(cudaMemcpyAsync(isa.get(), d_isa, 8 * nisa, cudaMemcpyDeviceToDevice, st.s)); }
 	}
+	if (!this->d_special.get()) this->d_special.alloc(st, 8); // scratch words of the output stages (K8 counts its runs there)
 	uint32_t exc_pos = 0xffffffffu;
 	if (T.has_term) {
 		B3M_CUDA(cudaMemcpyAsync(pinned, d_special, 16, cudaMemcpyDeviceToHost, st.s));
@@ -975,6 +976,17 @@ int b3m_ipc_open(int device, const void * handle64, void ** dptr, char * err, si
 }
 int b3m_ipc_close(int device, void * dptr, char * err, size_t errlen) {
 	B3M_PLAIN({ B3M_CUDA(cudaSetDevice(device)); B3M_CUDA(cudaIpcCloseMemHandle(dptr)); });
+}
+
+int b3m_dev_copy(int device, void * dst, const void * src, uint64_t bytes, void * cuda_stream, char * err, size_t errlen) {
+	B3M_PLAIN({
+		if (bytes && (!dst || !src)) throw b3m::Error("null argument");
+		B3M_CUDA(cudaSetDevice(device));
+		if (bytes) B3M_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)cuda_stream));
+	});
+}
+int b3m_engine_pack_bwa(b3m_engine * h, void * d_words, uint64_t w_lo, uint64_t w_hi) {
+	B3M_GUARD(h, h->e->pack_bwa_device((uint32_t *)d_words, w_lo, w_hi));
 }
 
 int b3m_engine_sync(b3m_engine * h) {

@@ -132,6 +132,7 @@ struct Engine {
 	void write_bwt(const char * fn);
 	void fetch_runs(uint8_t * h_sym, uint64_t * h_len, uint64_t cap, uint64_t * nruns_out);
 	void fetch_bwa(uint32_t * h_words, uint64_t cap, uint64_t * primary, uint64_t * L2, uint64_t * seq_len_out);
+	void pack_bwa_device(uint32_t * d_words, uint64_t w_lo, uint64_t w_hi);
 	// sampled SA/ISA from an existing BWT and (rank,pos) anchors (bwtcomputessa path)
 	void install_bwt_symbols(const uint8_t * h_bwt, uint64_t n, uint64_t extra_bytes);
 	void lf_speed(const uint64_t * h_start, uint64_t nstart, uint64_t nchains, uint64_t steps, float * ms);

@@ -237,6 +237,17 @@ void Engine::fetch_bwa(uint32_t * h_words, uint64_t cap, uint64_t * primary, uin
 	B3M_CUDA(cudaStreamSynchronize(st.s));
 }
 
+void Engine::pack_bwa_device(uint32_t * d_words, uint64_t w_lo, uint64_t w_hi) {
+	B3M_CUDA(cudaSetDevice(device));
+	B3M_REQUIRE(have_results && !ssa_only, "no BWT to export");
+	B3M_REQUIRE(T.has_term && T.sigma <= 4, "the BWA export needs a pacterm build (bases A,C,G,T and one terminator)");
+	uint64_t const seq_len = T.n - 1;
+	uint64_t const nwords = (seq_len + 15) >> 4;
+	B3M_REQUIRE(d_words && w_lo <= w_hi && w_hi <= nwords, "bad word range");
+	if (w_hi > w_lo) k9_pack_bwa_range(st.s, bwt.get(), seq_len, (uint64_t)root_exc_pos, d_words, w_lo, w_hi);
+	++st.launches;
+}
+
 // runs of the BWT: start positions (device) and their number
 uint64_t Engine::rl_runs(const uint8_t * s, DevBuf<uint32_t> & start) {
 	uint64_t const n = T.n;

@@ -271,7 +271,10 @@ struct MsdGeom { unsigned b1 = 0, b2 = 0; };
 
 // bits of the two global levels: sub-buckets of 3200..6400 suffixes on average (a finish CTA holds MSD_CAP = 8192
 // records including the padding of its runs)
-static bool msd_geometry(Stream const & st, DevText const & T, uint64_t W, MsdGeom & g) {
+// nparts > 1 (position-sharded build): the level-1 runs of a tile cross NVLink as they are stored, and 64-byte runs use
+// a third of the link; one bit less doubles them (measured on 2 GPUs at 3.1 Gbp: scatter 21.1 -> 16.2 ms, finish -- twice
+// the runs to gather -- 15.8 -> 18.9 ms; profiles/r2s_*)
+static bool msd_geometry(Stream const & st, DevText const & T, uint64_t W, MsdGeom & g, uint32_t nparts = 1) {
 	if (st.sortpath == B3M_SORT_LSD) return false;
 	if (T.keybits != 2 || !T.packed || W < 64 || W >= 0xFFFFFF00ull) return false;
 	if (st.sortpath != B3M_SORT_MSD && W < (1u << 16)) return false;
@@ -279,6 +282,7 @@ static bool msd_geometry(Stream const & st, DevText const & T, uint64_t W, MsdGe
 	while (tb < 21 && (W >> tb) > 6400) ++tb;
 	g.b1 = 2 * ((tb + 3) / 4);
 	if (g.b1 > 10) g.b1 = 10;
+	if (nparts > 1 && g.b1 > 9 && tb - 9 <= 11) g.b1 = 9;
 	g.b2 = tb - g.b1;
 	if (g.b2 < 1) g.b2 = 1;
 	if (g.b2 > 11) g.b2 = 11;
@@ -795,7 +799,7 @@ bool k2_xshard_count(Stream & st, DevText const & T, int circular, uint32_t part
 	B3M_REQUIRE(nparts >= 1 && nparts <= (uint32_t)MSD_MAXPARTS && part < nparts, "bad part index");
 	MsdGeom g;
 	*nbins = 0;
-	if (!msd_geometry(st, T, T.ntext, g)) return false;
+	if (!msd_geometry(st, T, T.ntext, g, nparts)) return false;
 	TextView v{T.codes, T.packed, T.ntext, 0, T.ntext, circular, 0, T.has_term};
 	uint32_t const nt1 = (uint32_t)div_up(T.ntext, MSD_TILE);
 	X = XShard();

@@ -185,6 +185,10 @@ class Engine:
             self._check(self._lib.b3m_engine_fetch_bwa(self._h, _ptr(words), words.size, None, None, None))
         return words, int(primary.value), [int(x) for x in l2], int(seq_len.value)
 
+    def pack_bwa(self, d_words_ptr, w_lo, w_hi):
+        """K9 into a caller-owned device buffer: BWA's words [w_lo, w_hi) of the last pacterm build (no host copy)."""
+        self._check(self._lib.b3m_engine_pack_bwa(self._h, C.c_void_p(d_words_ptr), w_lo, w_hi))
+
     def ssa_from_bwt(self, bwt, preisa_pairs, sasamplingrate=32, isasamplingrate=32):
         """K4 + K7 on an existing BWT (bwtcomputessa path); returns (sa, isa) samples."""
         b = np.ascontiguousarray(bwt, dtype=np.uint8)
@@ -258,6 +262,10 @@ class DeviceMemory:
 
     def close(self, ptr):
         self._call(self._lib.b3m_ipc_close, self.device, C.c_void_p(ptr))
+
+    def copy(self, dst, src, nbytes, stream_ptr=0):
+        """cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDefault) on `stream_ptr` of this device."""
+        self._call(self._lib.b3m_dev_copy, self.device, C.c_void_p(dst), C.c_void_p(src), nbytes, C.c_void_p(stream_ptr) if stream_ptr else None)
 
 
 class MultiEngine:

@@ -375,6 +375,21 @@ class DirectResults:
         g = lambda k: self.p.get(k, 0)
         return g("bwt"), g("prerank"), g("sa"), g("isa"), g("special")
 
+    def extra(self, name, nbytes):
+        """One more buffer owned by rank 0 and mapped by all (collective on first use)."""
+        if name in self.p:
+            return self.p[name]
+        box = [None]
+        if self.rank == 0:
+            self.p[name] = self.mem.alloc(nbytes)
+            box[0] = self.mem.export(self.p[name])
+        if self.world > 1:
+            dist.broadcast_object_list(box, src=0)
+            if self.rank != 0:
+                self.p[name] = self.mem.open(box[0])
+        self.sizes[name] = nbytes
+        return self.p[name]
+
     def close(self):
         for v in self.p.values():
             (self.mem.free if self.rank == 0 else self.mem.close)(v)
@@ -462,6 +477,109 @@ def build_xsharded(engine, results, xrecs, sasamplingrate=32, isasamplingrate=26
     if rank == 0:
         engine.shard_adopt(world, *results.ptrs())
     return True
+
+
+class SharedHost:
+    """A host buffer that every process of the job maps and page-locks: rank 0 creates a file under /dev/shm, all
+    ranks map it (torch.from_file, shared) and register the mapping with CUDA, so that each rank's copy engine
+    can write its slice of the results into the same host memory over its own PCIe link."""
+
+    def __init__(self, nbytes, tag, rank, world, directory="/dev/shm"):
+        self.nbytes = max(int(nbytes), 1)
+        box = [None]
+        if rank == 0:
+            box[0] = os.path.join(directory if os.path.isdir(directory) else "/tmp", "b3m_%d_%s" % (os.getpid(), tag))
+            with open(box[0], "wb") as f:
+                f.truncate(self.nbytes)
+        if world > 1:
+            dist.broadcast_object_list(box, src=0)
+        self.path = box[0]
+        self.t = torch.from_file(self.path, shared=True, size=self.nbytes, dtype=torch.uint8)
+        rc = torch.cuda.cudart().cudaHostRegister(self.t.data_ptr(), self.nbytes, 0)
+        if int(rc) != 0:
+            raise RuntimeError("cudaHostRegister failed (%s)" % rc)
+        if world > 1:
+            dist.barrier()
+        if rank == 0:
+            os.unlink(self.path)  # the mappings keep the memory alive
+
+    def ptr(self):
+        return self.t.data_ptr()
+
+    def close(self):
+        if self.t is not None:
+            torch.cuda.cudart().cudaHostUnregister(self.t.data_ptr())
+            self.t = None
+
+
+def load_distributed(engine, host, inputtype, state):
+    """The input file reaches the GPUs over ALL their PCIe links: rank r copies bytes [r*chunk, (r+1)*chunk) of the
+    page-locked file image `host` (a uint8 tensor every rank holds or maps) into its slice of a device buffer, one
+    all-gather over NVLink completes the buffer on every rank, and every rank decodes the text (K1).  Runs on
+    torch's current stream, which must be the engine's.  `state` (a dict) keeps the device buffer between calls."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    n = host.numel()
+    chunk = ((n + world - 1) // world + 255) // 256 * 256
+    buf = state.get("in")
+    if buf is None or buf.numel() != chunk * world:
+        buf = state["in"] = torch.empty(chunk * world, dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
+    lo, hi = min(rank * chunk, n), min((rank + 1) * chunk, n)
+    if hi > lo:
+        buf[lo:hi].copy_(host[lo:hi], non_blocking=True)
+    if world > 1:
+        dist.all_gather_into_tensor(buf, buf[rank * chunk:(rank + 1) * chunk])
+    engine.load_device(buf.data_ptr(), n, inputtype)
+    return hi - lo
+
+
+def fetch_distributed(engine, state, host_words_ptr, host_sa_ptr, host_preisa_ptr=0, host_isa_ptr=0):
+    """Results of a sharded pacterm build (build_distributed, strategy "shard") to the host over ALL PCIe links:
+    rank 0 packs BWA's BWT words (K9) into a buffer the other ranks map, every rank pulls its slice of the words
+    and of the sampled SA out of rank 0's HBM over NVLink (cudaMemcpyAsync on peer-mapped memory) and copies it to
+    its place in the page-locked host buffers (SharedHost: the same memory in every process).  Anchors and ISA
+    samples (n / 8192 and n / 262144 entries) leave through rank 0.  Two one-element all-reduces on the stream:
+    "the words are packed" and "every slice has left rank 0's buffers" (the next build may overwrite them).
+    Returns the bytes this rank sent to the host."""
+    res = state.get("direct")
+    if res is None:
+        raise RuntimeError("fetch_distributed follows a sharded build_distributed with the same driver state")
+    rank, world = res.rank, res.world
+    dev = torch.device("cuda", torch.cuda.current_device())
+    stream_ptr = engine.stream_ptr
+    n = res.n
+    nwords = (n - 1 + 15) >> 4
+    nsa = res.sizes.get("sa", 0) // 8
+    res.extra("bwa", 4 * nwords)
+    fence = state.get("fence")
+    if fence is None:
+        fence = state["fence"] = torch.zeros(1, dtype=torch.int64, device=dev)
+    if rank == 0:
+        engine.pack_bwa(res.p["bwa"], 0, nwords)
+    if world > 1:
+        dist.all_reduce(fence, op=dist.ReduceOp.SUM)
+    sent = 0
+    for key, count, width, hptr in (("bwa", nwords, 4, host_words_ptr), ("sa", nsa, 8, host_sa_ptr)):
+        if not count or not hptr:
+            continue
+        per = ((count + world - 1) // world + 63) // 64 * 64
+        lo, hi = min(rank * per, count), min((rank + 1) * per, count)
+        if hi <= lo:
+            continue
+        nb = (hi - lo) * width
+        src = res.p[key] + lo * width
+        if rank != 0:
+            stage = state.get("stage_" + key)
+            if stage is None or stage.numel() < nb:
+                stage = state["stage_" + key] = torch.empty(per * width, dtype=torch.uint8, device=dev)
+            res.mem.copy(stage.data_ptr(), src, nb, stream_ptr)  # NVLink: rank 0's HBM -> mine
+            src = stage.data_ptr()
+        res.mem.copy(hptr + lo * width, src, nb, stream_ptr)       # my PCIe link
+        sent += nb
+    if rank == 0 and (host_preisa_ptr or host_isa_ptr):
+        engine.fetch_ptrs(0, host_preisa_ptr, 0, host_isa_ptr)
+    if world > 1:
+        dist.all_reduce(fence, op=dist.ReduceOp.SUM)
+    return sent
 
 
 def build_distributed(engine, local_blocks=1, preisarate=0, sasamplingrate=32, isasamplingrate=262144, bwtonly=False,

@@ -225,6 +225,9 @@ int b3m_engine_fetch_runs(b3m_engine * e, uint8_t * syms, uint64_t * lens, uint6
  * primary = rank of the suffix at text position 0; L2[0..4] = cumulative base counts; seq_len = n-1.
  * BWA's .sa payload is sa[1..] of b3m_engine_fetch.  With bwt_words NULL only the scalars are returned. */
 int b3m_engine_fetch_bwa(b3m_engine * e, uint32_t * bwt_words, uint64_t cap_words, uint64_t * primary, uint64_t * L2, uint64_t * seq_len);
+/* K9 into a caller-owned device buffer (cudaMalloc'ed, possibly shared through CUDA IPC): BWA's words
+ * [w_lo, w_hi) of the last pacterm build, on the engine's stream, no host copy. */
+int b3m_engine_pack_bwa(b3m_engine * e, void * d_words, uint64_t w_lo, uint64_t w_hi);
 /* K4 + K7 on an existing BWT: sampled SA/ISA from n symbols and npairs (rank,pos) anchors
  * (engine half of b3m_compute_ssa); fetch with b3m_engine_fetch(e, NULL, NULL, sa, isa). */
 int b3m_engine_ssa_from_bwt(b3m_engine * e, const uint8_t * bwt, uint64_t n, const uint64_t * preisa_pairs, uint64_t npairs,
@@ -320,6 +323,11 @@ int b3m_dev_free(int device, void * dptr, char * err, size_t errlen);
 int b3m_ipc_export(int device, const void * dptr, void * handle64, char * err, size_t errlen);
 int b3m_ipc_open(int device, const void * handle64, void ** dptr, char * err, size_t errlen);
 int b3m_ipc_close(int device, void * dptr, char * err, size_t errlen);
+/* cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault) on `cuda_stream` (NULL: the default stream) of `device`.
+ * With it every rank of a multi-GPU build pulls ITS slice of the owner's result buffers over NVLink and sends
+ * it to the host over its own PCIe link (bwtb3m_b200/multigpu.py fetch_distributed), instead of all results
+ * leaving through the owner's link. */
+int b3m_dev_copy(int device, void * dst, const void * src, uint64_t bytes, void * cuda_stream, char * err, size_t errlen);
 
 /* ---- multi-GPU build inside ONE process (what `ngpus` of b3m_options / of the bwtb3m command line selects) ----
  * ngpus engines, one host thread per GPU, peer access between all of them; no NCCL and no second process.

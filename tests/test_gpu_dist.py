@@ -20,6 +20,8 @@ def ngpus():
                                   ["--nsym", "200003", "--itype", "pacterm", "--strategy", "merge"],
                                   ["--nsym", "250001", "--itype", "pac", "--strategy", "shard"],
                                   ["--nsym", "20000003", "--itype", "pacterm", "--strategy", "shard"],
+                                  ["--nsym", "20000003", "--itype", "pacterm", "--strategy", "shard", "--io"],
+                                  ["--nsym", "100003", "--itype", "pacterm", "--strategy", "shard", "--io"],
                                   ["--workload", "cfg3", "--strategy", "shard"]])
 def test_nccl_build_equals_single(args):
     if ngpus() < 2:

@@ -25,6 +25,7 @@ ap.add_argument("--itype", default="pacterm")
 ap.add_argument("--local-blocks", type=int, default=1)
 ap.add_argument("--seed", type=int, default=7)
 ap.add_argument("--strategy", default="auto", choices=["auto", "shard", "merge"])
+ap.add_argument("--io", action="store_true", help="input and results over every rank's PCIe link (multigpu.load_distributed / fetch_distributed; pacterm, sharded)")
 a = ap.parse_args()
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -39,13 +40,27 @@ else:
 
 stream = torch.cuda.Stream()
 eng = Engine(local, stream.cuda_stream)
-eng.load_host(data, itype)
+io_state, shared = {}, None
+host = torch.from_numpy(data).pin_memory()
+if not a.io:
+    eng.load_host(data, itype)
 drv = None
 for it in range(2):
     torch.cuda.synchronize()
     dist.barrier()
     t0 = time.perf_counter()
-    drv, res = multigpu.build_distributed(eng, local_blocks=a.local_blocks, sasamplingrate=32, isasamplingrate=1024, driver=drv, strategy=a.strategy)
+    with torch.cuda.stream(stream):
+        if a.io:
+            multigpu.load_distributed(eng, host, itype, io_state)
+        drv, res = multigpu.build_distributed(eng, local_blocks=a.local_blocks, sasamplingrate=32, isasamplingrate=1024, driver=drv, strategy=a.strategy)
+        if a.io:
+            i0 = eng.info()
+            if shared is None:
+                nw = (i0["n"] - 1 + 15) >> 4
+                shared = {"bwa": multigpu.SharedHost(4 * nw, "bwa", rank, world), "sa": multigpu.SharedHost(8 * i0["nsa"], "sa", rank, world)}
+                shared["bwa"].t.fill_(0xEE)
+                shared["sa"].t.fill_(0xEE)
+            multigpu.fetch_distributed(eng, drv, shared["bwa"].ptr(), shared["sa"].ptr())
     torch.cuda.synchronize()
     dist.barrier()
     dt = time.perf_counter() - t0
@@ -61,6 +76,14 @@ if rank == 0:
         same = np.array_equal(multi[k], one[k])
         ok = ok and same
         print("%s: %s" % (k, "equal" if same else "DIFFERENT"))
+    if a.io:
+        words, primary, l2, seq_len = ref.fetch_bwa()
+        same = np.array_equal(shared["bwa"].t.numpy().view(np.uint32)[:words.size], words)
+        ok = ok and same
+        print("shared host BWA words: %s" % ("equal" if same else "DIFFERENT"))
+        same = np.array_equal(shared["sa"].t.numpy().view(np.uint64)[:one["sa"].size], one["sa"])
+        ok = ok and same
+        print("shared host SA samples: %s" % ("equal" if same else "DIFFERENT"))
     print("strategy used: %s" % res["strategy"])
     print("world=%d n=%d second build %.1f ms; phases ms sort=%.1f gap=%.1f merge=%.1f walk=%.1f  %s" %
           (world, info["n"], dt * 1e3, info["ms_sort"], info["ms_gap"], info["ms_merge"], info["ms_walk"], "DIST_CHECK_OK" if ok else "DIST_CHECK_FAILED"))
