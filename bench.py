@@ -341,6 +341,22 @@ def run_ours(args):
             dist.all_reduce(mx, op=dist.ReduceOp.MAX)
             e2e_s = float(mx[0].item())
         h2d = int(host_in.numel())  # N > 1: the sum over the ranks' slices
+        # where the end-to-end time goes: one more step with a device synchronisation and a barrier behind every phase (untimed above)
+        e2e_phases = None
+        if world > 1:
+            def phase(fn):
+                sync_all()
+                t = time.perf_counter()
+                fn()
+                sync_all()
+                return 1e3 * (time.perf_counter() - t)
+            ph = [phase(lambda: multigpu.load_distributed(eng, host_in, itype, io_state)), phase(lambda: build())]
+            if shared is not None and state["strategy"] == "shard":
+                ph.append(phase(lambda: multigpu.fetch_distributed(eng, state["drv"], shared["bwt"].ptr(), shared["sa"].ptr() if info["nsa"] else 0,
+                                                                   out["preisa"].data_ptr() if rank == 0 else 0, out["isa"].data_ptr() if (rank == 0 and info["nisa"]) else 0)))
+            mx = torch.tensor(ph, dtype=torch.float64, device="cuda")
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            e2e_phases = dict(zip(("load", "build", "fetch"), [round(float(x), 3) for x in mx.tolist()]))
         e2e_check = None
         if shared is not None and state["strategy"] == "shard":
             # what landed in the shared host buffers equals what rank 0's engine returns through the plain fetch calls
@@ -490,7 +506,7 @@ def run_ours(args):
                 "path": ("single GPU: results stream out during the last sorting kernel" if world == 1 else
                          "every rank uploads 1/N of the input and sends 1/N of the BWA words and SA samples to ONE shared page-locked host buffer over its own PCIe link" if e2e_check is not None else
                          "every rank uploads 1/N of the input; results leave through rank 0"),
-                "check": e2e_check},
+                "check": e2e_check, "phases_ms": e2e_phases},
         "gpu_launches": launches,
         "roofline": roof,
         "cpu_baseline": cpu,
