@@ -380,6 +380,26 @@ def run_ours(args):
         sync_all()
         kt = eng.kernel_times()
         eng.set_profile(False)
+        # N > 1: the slowest rank per kernel, and the phases of one position-sharded build on every rank (CUDA events)
+        kt_max, build_timeline = None, None
+        if world > 1:
+            allkt = [None] * world
+            dist.all_gather_object(allkt, {k: v["ms"] / nprof for k, v in kt.items()})
+            kt_max = {k: round(max(d.get(k, 0.0) for d in allkt), 4) for k in sorted(set().union(*allkt))}
+            direct = state["drv"].get("direct") if isinstance(state["drv"], dict) else None
+            if direct is not None and state["strategy"] == "shard":
+                direct.timeline = []
+                sync_all()
+                step_device()
+                sync_all()
+                tl = direct.timeline
+                direct.timeline = None
+                mine = {tl[i][0]: tl[i - 1][1].elapsed_time(tl[i][1]) for i in range(1, len(tl))}
+                alltl = [None] * world
+                dist.all_gather_object(alltl, mine)
+                if mine:
+                    build_timeline = {k: {"rank0": round(alltl[0].get(k, 0.0), 3), "max": round(max(d.get(k, 0.0) for d in alltl), 3),
+                                          "min": round(min(d.get(k, 0.0) for d in alltl), 3)} for k in mine}
         lf_ms = None
         k8 = None
         if rank == 0:
@@ -516,6 +536,10 @@ def run_ours(args):
         "kernels_ms_per_step": {k: round(v["ms"] / nprof, 4) for k, v in kt.items()},
         "lf_steps_per_s": (1 << 20) * 256 / (lf_ms * 1e-3),
     }
+    if kt_max is not None:
+        line["kernels_ms_per_step_max_over_ranks"] = kt_max
+    if build_timeline is not None:
+        line["build_timeline_ms"] = build_timeline
     if file_level is not None:
         line["file_level"] = file_level
     if k8 is not None:

@@ -464,6 +464,7 @@ void Engine::build_blocks(PhaseTimer & pt, uint32_t * exc_pos) {
 	uint64_t const bs = div_up(T.n, numblocks);
 	numblocks = div_up(T.n, bs);
 	B3M_REQUIRE(numblocks >= 2, "internal: build_blocks needs at least two blocks");
+	ensure_codes(); // the block kernels read one byte per symbol
 	gt.alloc(st, T.n);
 	rsamp.alloc(st, npre);
 	gtp = gt.get(); prep = prerank.get(); rsp = rsamp.get();
@@ -496,6 +497,7 @@ void Engine::blk_begin(uint64_t preisarate, uint64_t largelcpthres, void * d_gt,
 	B3M_CUDA(cudaSetDevice(device));
 	B3M_REQUIRE(loaded, "no input loaded");
 	B3M_REQUIRE(d_gt && d_prerank && d_rsamp, "null block buffers");
+	ensure_codes(); // the block kernels read one byte per symbol
 	reset_results();
 	params = b3m_build_params();
 	params.largelcpthres = largelcpthres ? largelcpthres : 16384;

@@ -49,7 +49,7 @@ void Engine::load(const void * input, uint64_t nbytes, int itype, bool on_device
 	B3M_CUDA(cudaSetDevice(device));
 	B3M_REQUIRE(itype >= 0 && itype <= 3, "unknown input type");
 	reset_results();
-	codes.release(); packed.release(); raw.release(); d_hist.release(); d_special.release();
+	codes.release(); packed.release(); raw.release(); d_hist.release(); d_special.release(); lastcode.release();
 	kr_plan = KeyRangePlan();
 	xs = XShard();
 	inputtype = itype;
@@ -88,8 +88,10 @@ void Engine::load(const void * input, uint64_t nbytes, int itype, bool on_device
 		uint64_t const l = (nbytes - 2) * 4 + last; // BWA fa2pac layout
 		B3M_REQUIRE(l > 0, "empty input");
 		if (on_device) d_in = (const uint8_t *)input; else stage(0, nbytes, 0);
-		codes.alloc(st, l + 16);
-		k1_unpack_pac(st, d_in, l, codes.get(), d_hist.get());
+		// straight to the packed text; the byte codes are made when a path asks for them (ensure_codes)
+		packed.alloc(st, l / 32 + 3);
+		lastcode.alloc(st, 16);
+		k1_pac_to_packed(st, d_in, l, packed.get(), d_hist.get(), lastcode.get());
 		B3M_CUDA(cudaMemcpyAsync(pinned, d_hist.get(), 256 * 8, cudaMemcpyDeviceToHost, st.s));
 		B3M_CUDA(cudaStreamSynchronize(st.s));
 		memcpy(hcodes, pinned, sizeof(hcodes));
@@ -103,7 +105,7 @@ void Engine::load(const void * input, uint64_t nbytes, int itype, bool on_device
 			for (int c = 0; c < 4; ++c) { hist[c] = hcodes[c]; code2sym[c] = (uint8_t)c; }
 		}
 		for (int c = 0; c < 4; ++c) codehist[c] = hcodes[c];
-		decode_bytes = nbytes + l;
+		decode_bytes = nbytes + l / 4;
 	} else {
 		uint64_t nsym;
 		if (itype == B3M_INPUT_COMPACTSTREAM) {
@@ -113,15 +115,23 @@ void Engine::load(const void * input, uint64_t nbytes, int itype, bool on_device
 			// Serialize<uint64_t> writes) or big-endian numbers with a big-endian bit stream; bits per
 			// symbol is 1..8 in exactly one of the two readings.
 			B3M_REQUIRE(nbytes >= 32, "compact file too short");
-			uint8_t hdr[16];
-			peek(0, 16, hdr);
-			uint64_t bb = 0, nb = 0, bl = 0, nl = 0;
-			for (int i = 0; i < 8; ++i) {
-				bb = (bb << 8) | hdr[i]; nb = (nb << 8) | hdr[8 + i];
-				bl = (bl << 8) | hdr[7 - i]; nl = (nl << 8) | hdr[15 - i];
+			uint8_t hdr[32];
+			peek(0, 32, hdr);
+			// the four numbers in both readings; a reading is plausible when bits is 1..8 and both word counts equal ceil(n*bits/64)
+			uint64_t be[4], le[4];
+			for (int f = 0; f < 4; ++f) {
+				be[f] = le[f] = 0;
+				for (int i = 0; i < 8; ++i) { be[f] = (be[f] << 8) | hdr[8 * f + i]; le[f] = (le[f] << 8) | hdr[8 * f + 7 - i]; }
 			}
-			bool const le_words = !(bb >= 1 && bb <= 8);
-			uint64_t const b = le_words ? bl : bb, n = le_words ? nl : nb;
+			auto plausible = [](const uint64_t * h) {
+				if (h[0] < 1 || h[0] > 8 || h[1] > (~0ull >> 4)) return false;
+				uint64_t const w = (h[1] * h[0] + 63) / 64;
+				return h[2] == w && h[3] == w;
+			};
+			bool const ok_be = plausible(be), ok_le = plausible(le);
+			// both or neither plausible (e.g. word counts written differently): fall back to "bits in 1..8", big-endian first
+			bool const le_words = (ok_be != ok_le) ? ok_le : !(be[0] >= 1 && be[0] <= 8);
+			uint64_t const b = le_words ? le[0] : be[0], n = le_words ? le[1] : be[1];
 			B3M_REQUIRE(b >= 1 && b <= 8, "compact file: unsupported bits per symbol");
 			B3M_REQUIRE(n <= (nbytes - 32) * 8 / b && (!le_words || (n * b + 63) / 64 * 8 <= nbytes - 32), "compact file: truncated");
 			B3M_REQUIRE(n > 0, "empty input");
@@ -155,18 +165,32 @@ void Engine::load(const void * input, uint64_t nbytes, int itype, bool on_device
 		decode_bytes = 3 * nsym;
 	}
 	B3M_REQUIRE(T.n < 0xFFFFFF00ull, "inputs of 2^32 - 256 symbols or more are not supported yet");
-	T.codes = codes.get();
-	raw.release();
-	if (T.keybits == 2) {
-		packed.alloc(st, T.ntext / 32 + 3);
-		k1_pack2(st, T.codes, T.ntext, packed.get());
-		T.packed = packed.get();
-		decode_bytes += T.ntext + T.ntext / 4;
+	T.codes = codes.get(); // nullptr for pac / pacterm until ensure_codes()
+	if (packed.get()) T.packed = packed.get();
+	else {
+		lastcode.alloc(st, 16);
+		B3M_CUDA(cudaMemcpyAsync(lastcode.get(), T.codes + T.ntext - 1, 1, cudaMemcpyDeviceToDevice, st.s));
+		if (T.keybits == 2) {
+			packed.alloc(st, T.ntext / 32 + 3);
+			k1_pack2(st, T.codes, T.ntext, packed.get());
+			T.packed = packed.get();
+			decode_bytes += T.ntext + T.ntext / 4;
+		}
 	}
+	raw.release();
 	pt.mark();
 	B3M_CUDA(cudaStreamSynchronize(st.s));
 	ms_decode = pt.ms(0, 1);
 	loaded = true;
+}
+
+void Engine::ensure_codes() {
+	if (T.codes) return;
+	B3M_CUDA(cudaSetDevice(device));
+	B3M_REQUIRE(loaded && T.packed, "internal: no packed text to expand");
+	codes.alloc(st, T.ntext + 16);
+	k1_unpack_packed(st, T.packed, T.ntext, codes.get());
+	T.codes = codes.get();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -272,7 +296,7 @@ void Engine::build(b3m_build_params const & p) {
 		StreamOut so;
 		if (direct && p.host_sa) { so.host_sa = (unsigned long long *)p.host_sa; so.nsa = nsa; }
 		if (T.has_term) // rank 0 is the terminator suffix (text position ntext); its predecessor is the last base
-			B3M_CUDA(cudaMemcpyAsync(bwt.get(), T.codes + T.ntext - 1, 1, cudaMemcpyDeviceToDevice, st.s));
+			B3M_CUDA(cudaMemcpyAsync(bwt.get(), lastcode.get(), 1, cudaMemcpyDeviceToDevice, st.s));
 		if (p.host_bwa && T.has_term && T.sigma <= 4) {
 			bwa_words.alloc(st, (T.ntext + 15) / 16 + 1);
 			so.host_bwa = p.host_bwa; so.d_bwa = bwa_words.get();
@@ -372,7 +396,7 @@ void Engine::kr_build_part(uint32_t part, uint32_t nparts, b3m_build_params cons
 	if (part == 0 && T.has_term) {
 		// rank 0 is the terminator suffix (text position ntext): its predecessor is the last base; its
 		// anchor / ISA entries are rank 0 (written explicitly: the buffers may be another GPU's, not zeroed)
-		B3M_CUDA(cudaMemcpyAsync(d_bwt, T.codes + T.ntext - 1, 1, cudaMemcpyDeviceToDevice, st.s));
+		B3M_CUDA(cudaMemcpyAsync(d_bwt, lastcode.get(), 1, cudaMemcpyDeviceToDevice, st.s));
 		uint64_t const pos = T.ntext;
 		if ((T.ntext & (prerate - 1)) == 0) B3M_CUDA(cudaMemsetAsync((uint32_t *)d_prerank + T.ntext / prerate, 0, 4, st.s));
 		if (!p.bwtonly) {
@@ -444,7 +468,7 @@ void Engine::xs_finish(void * d_recs_own, void * d_bwt, void * d_prerank, void *
 	*unresolved = k2_xshard_finish(st, T, T.has_term ? 0 : 1, xs, (unsigned long long *)d_recs_own, fo, &sortstats);
 	if (xs.part == 0 && T.has_term) {
 		// rank 0 is the terminator suffix (text position ntext): written explicitly, the buffers are not zeroed
-		B3M_CUDA(cudaMemcpyAsync(d_bwt, T.codes + T.ntext - 1, 1, cudaMemcpyDeviceToDevice, st.s));
+		B3M_CUDA(cudaMemcpyAsync(d_bwt, lastcode.get(), 1, cudaMemcpyDeviceToDevice, st.s));
 		uint64_t const pos = T.ntext;
 		if ((T.ntext & (prerate - 1)) == 0) B3M_CUDA(cudaMemsetAsync((uint32_t *)d_prerank + T.ntext / prerate, 0, 4, st.s));
 		if (!p.bwtonly) {
@@ -731,6 +755,7 @@ uint64_t Engine::check_bwt(const uint8_t * h_bwt, uint64_t n, const uint64_t * h
 	B3M_CUDA(cudaMemsetAsync(dres.get(), 0, 16, st.s));
 	PhaseTimer pt(st);
 	pt.mark();
+	ensure_codes();
 	k7_check_walk(st, D, T.codes, T.ntext, T.has_term, dar.get(), dap.get(), das.get(), npairs, n, dres.get());
 	pt.mark();
 	uint64_t res[2];

@@ -48,7 +48,8 @@ struct Engine {
 	// input
 	bool loaded = false;
 	int inputtype = 0;
-	DevBuf<uint8_t> raw, codes;
+	DevBuf<uint8_t> raw, codes;  // codes: pac / pacterm inputs create them on demand (ensure_codes)
+	DevBuf<uint8_t> lastcode;    // code of the last stored symbol (the seam of a circular text, the row behind the terminator)
 	DevBuf<uint64_t> packed;   // 2-bit packed text when sigma <= 4 (textview.cuh)
 	DevBuf<uint64_t> d_hist;
 	DevText T;
@@ -132,6 +133,7 @@ struct Engine {
 	void write_bwt(const char * fn);
 	void fetch_runs(uint8_t * h_sym, uint64_t * h_len, uint64_t cap, uint64_t * nruns_out);
 	void fetch_bwa(uint32_t * h_words, uint64_t cap, uint64_t * primary, uint64_t * L2, uint64_t * seq_len_out);
+	void ensure_codes();       // T.codes for the paths that read one byte per symbol (block merge tree, checkbwt)
 	void pack_bwa_device(uint32_t * d_words, uint64_t w_lo, uint64_t w_hi);
 	// sampled SA/ISA from an existing BWT and (rank,pos) anchors (bwtcomputessa path)
 	void install_bwt_symbols(const uint8_t * h_bwt, uint64_t n, uint64_t extra_bytes);

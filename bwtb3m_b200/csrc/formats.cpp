@@ -311,7 +311,7 @@ struct RlFile {
 		File f(fn, "rb");
 		uint8_t fix[40];
 		f.read(fix, 40);
-		if (memcmp(fix, RL_MAGIC, 8)) throw IoError(fn + " is not a b3m run-length container (bad magic)");
+		if (memcmp(fix, RL_MAGIC, 8)) throw IoError(fn + " is not a b3m run-length container (bad magic); files written by libmaus2's RLEncoder are not readable by this library and vice versa -- see README.md, file formats");
 		h.n = get_be64(fix + 8); h.nruns = get_be64(fix + 16); h.runs_per_block = get_be64(fix + 24); h.nblocks = get_be64(fix + 32);
 		f.seek(sz - 8);
 		uint8_t t8[8]; f.read(t8, 8);

@@ -283,6 +283,9 @@ int b3m_lf_speed(const char * bwtfn, uint64_t nchains, uint64_t steps, uint64_t 
 		uint64_t rate = 0; std::vector<uint64_t> isa;
 		read_sampled(isafn, &rate, &isa);
 		if (isa.empty()) throw Error("empty sampled ISA");
+		if (nchains < 1) throw Error("nchains must be at least 1");
+		if (L.empty()) throw Error("empty BWT");
+		for (auto v : isa) if (v >= L.size()) throw Error(isafn + " holds a rank outside the BWT (" + std::to_string(v) + " >= " + std::to_string(L.size()) + "): not the sampled ISA of this .bwt");
 		Engine e(device, nullptr);
 		e.install_bwt_symbols(L.data(), L.size(), 16 * nchains);
 		if (!steps) steps = std::min<uint64_t>(div_up(L.size(), nchains), 128ull << 20); // bwttestdecodespeed.cpp:84

@@ -36,6 +36,10 @@ void k1_unpack_pac(Stream & st, const uint8_t * d_pac, uint64_t l, uint8_t * d_o
 void k1_unpack_compact(Stream & st, const uint8_t * d_words, uint64_t n, unsigned b, bool le_words, uint8_t * d_out, uint64_t * d_hist256);
 // packed copy of n codes < 4; d_out holds n/32 + 3 words, the tail is zero
 void k1_pack2(Stream & st, const uint8_t * d_codes, uint64_t n, uint64_t * d_out);
+// pac payload (l bases, BWA layout) -> packed text (l/32 + 3 words, zero tail), histogram of the four codes, code of the last base
+void k1_pac_to_packed(Stream & st, const uint8_t * d_pac, uint64_t l, uint64_t * d_out, uint64_t * d_hist256, uint8_t * d_lastcode);
+// packed text -> one byte per symbol (n codes + 16 zero bytes)
+void k1_unpack_packed(Stream & st, const uint64_t * d_packed, uint64_t n, uint8_t * d_out);
 
 // ---- K2 ---------------------------------------------------------------------------------
 struct SortStats {

@@ -127,6 +127,81 @@ void k1_unpack_pac(Stream & st, const uint8_t * d_pac, uint64_t l, uint8_t * d_o
 	B3M_LAUNCH(st, k_unpack_pac, grid, 256, 0, d_pac, l, d_out, (unsigned long long *)d_hist256);
 }
 
+// pac -> the packed text directly: 8 pac bytes, read big-endian, ARE one word of the packed text (32 symbols, first
+// symbol in the top bits); the histogram of the codes comes from popcounts of the word.  The byte codes are not
+// written: the MSD sorter, the key-range sorter and the resolve kernels read the packed text only, and the paths that
+// want one byte per symbol (block merge tree, checkbwt) expand it on demand (k1_unpack_packed).
+__global__ void __launch_bounds__(256) k_pac_to_packed(const uint8_t * __restrict__ pac, uint64_t l, uint64_t * __restrict__ out, uint64_t nwords,
+                                                       int aligned, unsigned long long * __restrict__ hist, uint8_t * __restrict__ lastcode) {
+	__shared__ uint32_t sh[4];
+	if (threadIdx.x < 4) sh[threadIdx.x] = 0;
+	__syncthreads();
+	uint64_t const nbytes = (l + 3) >> 2;
+	uint32_t c1 = 0, c2 = 0, c3 = 0, cv = 0;
+	for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (uint64_t)gridDim.x * blockDim.x) {
+		uint64_t const first = w * 32;
+		uint32_t const valid = first >= l ? 0u : (l - first < 32 ? (uint32_t)(l - first) : 32u);
+		uint64_t x = 0;
+		if (valid) {
+			if (aligned && 8 * w + 8 <= nbytes) {
+				uint64_t const v = __ldg(reinterpret_cast<const uint64_t *>(pac) + w);
+				x = ((uint64_t)__byte_perm((uint32_t)v, 0u, 0x0123) << 32) | __byte_perm((uint32_t)(v >> 32), 0u, 0x0123);
+			} else {
+				for (uint32_t b = 0; b < 8; ++b) x = (x << 8) | (8 * w + b < nbytes ? (uint64_t)pac[8 * w + b] : 0ull);
+			}
+			if (valid < 32) x &= ~0ull << (64u - 2u * valid);
+			uint64_t const lo = x & 0x5555555555555555ull, hi = (x >> 1) & 0x5555555555555555ull;
+			c3 += (uint32_t)__popcll(lo & hi); c1 += (uint32_t)__popcll(lo & ~hi); c2 += (uint32_t)__popcll(hi & ~lo);
+			cv += valid;
+			if (l - 1 - first < 32) *lastcode = (uint8_t)((x >> (62u - 2u * (uint32_t)(l - 1 - first))) & 3u);
+		}
+		out[w] = x;
+	}
+	uint32_t const c0 = cv - c1 - c2 - c3;
+	if (c0) atomicAdd(&sh[0], c0);
+	if (c1) atomicAdd(&sh[1], c1);
+	if (c2) atomicAdd(&sh[2], c2);
+	if (c3) atomicAdd(&sh[3], c3);
+	__syncthreads();
+	if (threadIdx.x < 4 && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}
+
+void k1_pac_to_packed(Stream & st, const uint8_t * d_pac, uint64_t l, uint64_t * d_out, uint64_t * d_hist256, uint8_t * d_lastcode) {
+	B3M_CUDA(cudaMemsetAsync(d_hist256, 0, 256 * sizeof(uint64_t), st.s));
+	if (!l) return;
+	uint64_t const nwords = l / 32 + 3;
+	uint64_t const want = div_up(nwords, 256 * 4);
+	unsigned const grid = (unsigned)(want < (uint64_t)st.sms * 16 ? (want ? want : 1) : (uint64_t)st.sms * 16);
+	B3M_LAUNCH(st, k_pac_to_packed, grid, 256, 0, d_pac, l, d_out, nwords, ((uintptr_t)d_pac & 7u) == 0 ? 1 : 0, (unsigned long long *)d_hist256, d_lastcode);
+}
+
+// one byte per symbol out of the packed text: a thread expands one word into 32 codes (two 128-bit stores); the 16
+// bytes behind the last code are cleared (readers of 16-byte blocks may touch them)
+__global__ void __launch_bounds__(256) k_unpack_packed(const uint64_t * __restrict__ packed, uint64_t n, uint8_t * __restrict__ out) {
+	uint64_t const w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	uint64_t const first = w * 32;
+	if (first >= n + 16) return;
+	uint64_t const x = first < n ? __ldg(packed + w) : 0ull;
+	if (first + 32 <= n) {
+		uint32_t o[8];
+		#pragma unroll
+		for (int q = 0; q < 8; ++q) {
+			uint32_t const y = (uint32_t)(x >> (56 - 8 * q)) & 255u; // four symbols, first in the top bits
+			o[q] = ((y >> 6) & 3u) | (((y >> 4) & 3u) << 8) | (((y >> 2) & 3u) << 16) | ((y & 3u) << 24);
+		}
+		uint4 * dst = reinterpret_cast<uint4 *>(out + first);
+		dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+		dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+	} else {
+		for (uint32_t j = 0; j < 32 && first + j < n + 16; ++j) out[first + j] = first + j < n ? (uint8_t)((x >> (62u - 2u * j)) & 3u) : (uint8_t)0;
+	}
+}
+
+void k1_unpack_packed(Stream & st, const uint64_t * d_packed, uint64_t n, uint8_t * d_out) {
+	uint64_t const nwords = (n + 16 + 31) / 32;
+	B3M_LAUNCH(st, k_unpack_packed, (unsigned)div_up(nwords, 256), 256, 0, d_packed, n, d_out);
+}
+
 // compactstream payload: b-bit symbols, MSB first, in 64-bit words [layout unpinned, SURVEY 8c].  The words lie
 // either as a big-endian byte stream (flip = 0) or as native little-endian uint64 (flip = 7: byte k of the bit
 // stream is byte k ^ 7 of the file, what libmaus2's native Serialize<uint64_t> writes); one thread per symbol (b <= 8).

@@ -71,7 +71,7 @@ k_rank_scatter(const uint32_t * __restrict__ sa, uint64_t W, uint32_t * __restri
 // fused outputs of one suffix in its final place (K3 + sampling)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t fo_pred(TextView const & v, FusedOut const & fo, uint32_t i) {
-	if (i == 0) return fo.has_term ? 0u : (uint32_t)v.codes[v.ntext - 1];
+	if (i == 0) return fo.has_term ? 0u : tv_code(v, v.ntext - 1);
 	return tv_code_before(v, i);
 }
 

@@ -28,16 +28,22 @@ struct TextView {
 	int has_term;            // the text ends in an implicit unique terminator (pacterm)
 };
 
+// code at text position p: out of the packed text when there is one (the byte codes of a pac input exist only on demand)
+__device__ __forceinline__ uint32_t tv_code(TextView const & v, uint64_t p) {
+	if (v.packed) return (uint32_t)(__ldg(v.packed + (p >> 5)) >> (62u - 2u * (unsigned)(p & 31u))) & 3u;
+	return v.codes[p];
+}
+
 // symbol at window index i (any i >= 0)
 __device__ __forceinline__ uint32_t tv_symbol(TextView const & v, uint64_t i) {
 	if (v.circular) {
 		if (i >= v.W) { i -= v.W; if (i >= v.W) i %= v.W; }
-		return v.codes[i];
+		return tv_code(v, i);
 	}
 	if (i >= v.W) return 0u;
 	uint64_t p = v.wstart + i;
 	if (v.text_wraps && p >= v.ntext) p %= v.ntext;
-	return v.codes[p];
+	return tv_code(v, p);
 }
 
 // 32 symbols starting at text position p, no wrap: needs p + 32 <= 32 * (words of the packed array)
@@ -86,17 +92,11 @@ __device__ __forceinline__ uint64_t tv_symbols(TextView const & v, uint64_t i, u
 __device__ __forceinline__ uint32_t tv_pred(TextView const & v, uint64_t i) {
 	uint64_t p = v.wstart + i;
 	if (p >= v.ntext) p %= v.ntext;
-	if (p == 0) return v.has_term ? 0u : (uint32_t)v.codes[v.ntext - 1];
-	return v.codes[p - 1];
+	if (p == 0) return v.has_term ? 0u : tv_code(v, v.ntext - 1);
+	return tv_code(v, p - 1);
 }
 
 // code preceding text position p (p >= 1)
-__device__ __forceinline__ uint32_t tv_code_before(TextView const & v, uint64_t p) {
-	if (v.packed) {
-		uint64_t const q = p - 1;
-		return (uint32_t)(__ldg(v.packed + (q >> 5)) >> (62u - 2u * (unsigned)(q & 31u))) & 3u;
-	}
-	return v.codes[p - 1];
-}
+__device__ __forceinline__ uint32_t tv_code_before(TextView const & v, uint64_t p) { return tv_code(v, p - 1); }
 
 } // namespace b3m

@@ -449,29 +449,44 @@ def build_xsharded(engine, results, xrecs, sasamplingrate=32, isasamplingrate=26
     from .engine import B3MError
     rank, world = results.rank, results.world
     device = device or torch.device("cuda", torch.cuda.current_device())
+    marks = getattr(results, "timeline", None)  # bench.py: a list that receives (phase, CUDA event) pairs of this build
+
+    def mark(name):
+        if marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((name, ev))
+
+    mark("start")
     tot = torch.zeros(2048, dtype=torch.int64, device=device)
     nb = engine.xshard_count(rank, world, tot.data_ptr(), preisarate=results.prerate, sasamplingrate=sasamplingrate,
                              isasamplingrate=isasamplingrate, bwtonly=bwtonly)
     if nb == 0:
         return None
+    mark("count")
     allt = torch.empty(world * 2048, dtype=torch.int64, device=device)
     if world > 1:
         dist.all_gather_into_tensor(allt, tot)
     else:
         allt.copy_(tot)
     h = allt.cpu().numpy().view(np.uint64).reshape(world, 2048)[:, :nb]
+    mark("totals all-gather")
     try:
         engine.xshard_scatter(h, xrecs.ptrs, [xrecs.cap] * world)
     except B3MError:
         return None  # a key range too large for its array: decided from the same counts on every rank
+    mark("scatter")
     fence = torch.zeros(1, dtype=torch.int64, device=device)
     if world > 1:
         dist.all_reduce(fence, op=dist.ReduceOp.SUM)  # every rank's records have landed before anyone sorts
+    mark("fence")
     unres = engine.xshard_finish(xrecs.own, *results.ptrs())
+    mark("local+finish")
     if world > 1:
         flag = torch.tensor([unres], dtype=torch.int64, device=device)
         dist.all_reduce(flag, op=dist.ReduceOp.SUM)
         unres = int(flag.item())
+    mark("vote")
     if unres != 0:
         return False
     if rank == 0:

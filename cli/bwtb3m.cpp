@@ -51,6 +51,9 @@ int main(int argc, char ** argv) {
 			str << "device=[0] (CUDA device)\n";
 			str << "numblocks=[0] (0: derive from mem; >0: force the number of blocks)\n";
 			str << "ngpus=[1] (GPUs of this box sharing the build: devices device .. device+ngpus-1)\n";
+			str << "\nfile formats: .sa / .isa / .preisa are the reference's native uint64 layouts; the .bwt / .hist containers are this\n";
+			str << "library's own (same content, different bytes than libmaus2's RLEncoder / NumberMapSerialisation): read them with\n";
+			str << "the tools built from this tree (bwtb3mdecoderl, bwtb3mtobwa, bwtcomputessa, checkbwt), see README.md\n";
 			throw std::runtime_error(str.str());
 		}
 		std::string const fn = arg.rest[0];
