@@ -311,7 +311,7 @@ def run_ours(args):
         io_state = {}
         shared = None
         if world > 1 and as_bwa:
-            shared = {"bwt": multigpu.SharedHost(4 * nwords, "bwa", rank, world), "sa": multigpu.SharedHost(8 * max(info["nsa"], 1), "sa", rank, world)}
+            shared = {"bwt": multigpu.SharedHost(4 * nwords, "bwa", rank, world, width=4), "sa": multigpu.SharedHost(8 * max(info["nsa"], 1), "sa", rank, world, width=8)}
 
         def step_e2e():
             if world == 1:
@@ -357,6 +357,16 @@ def run_ours(args):
             mx = torch.tensor(ph, dtype=torch.float64, device="cuda")
             dist.all_reduce(mx, op=dist.ReduceOp.MAX)
             e2e_phases = dict(zip(("load", "build", "fetch"), [round(float(x), 3) for x in mx.tolist()]))
+            if len(ph) == 3:
+                # inside the fetch: CUDA events on every rank's stream
+                state["drv"]["fetch_timeline"] = []
+                ph.append(phase(lambda: multigpu.fetch_distributed(eng, state["drv"], shared["bwt"].ptr(), shared["sa"].ptr() if info["nsa"] else 0,
+                                                                   out["preisa"].data_ptr() if rank == 0 else 0, out["isa"].data_ptr() if (rank == 0 and info["nisa"]) else 0)))
+                tl = state["drv"].pop("fetch_timeline")
+                mine = {tl[i][0]: tl[i - 1][1].elapsed_time(tl[i][1]) for i in range(1, len(tl))}
+                alltl = [None] * world
+                dist.all_gather_object(alltl, mine)
+                e2e_phases["fetch_timeline"] = {k: {"rank0": round(alltl[0].get(k, 0.0), 3), "max": round(max(d.get(k, 0.0) for d in alltl), 3)} for k in mine}
         e2e_check = None
         if shared is not None and state["strategy"] == "shard":
             # what landed in the shared host buffers equals what rank 0's engine returns through the plain fetch calls
@@ -526,7 +536,8 @@ def run_ours(args):
                 "path": ("single GPU: results stream out during the last sorting kernel" if world == 1 else
                          "every rank uploads 1/N of the input and sends 1/N of the BWA words and SA samples to ONE shared page-locked host buffer over its own PCIe link" if e2e_check is not None else
                          "every rank uploads 1/N of the input; results leave through rank 0"),
-                "check": e2e_check, "phases_ms": e2e_phases},
+                "check": e2e_check, "phases_ms": e2e_phases,
+                "numa": ({"gpu_node_rank0": shared["bwt"].node, "policy_set_rank0": bool(shared["bwt"].policy)} if shared is not None else None)},
         "gpu_launches": launches,
         "roofline": roof,
         "cpu_baseline": cpu,

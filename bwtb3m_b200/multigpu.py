@@ -494,12 +494,46 @@ def build_xsharded(engine, results, xrecs, sasamplingrate=32, isasamplingrate=26
     return True
 
 
+def gpu_numa_node(device_index):
+    """NUMA node the GPU hangs off (sysfs numa_node of its PCI function), or -1 when the box does not say."""
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            return int(f.read().strip())
+    except Exception:
+        return -1
+
+
+def _set_mempolicy(node):
+    """Memory policy of the calling thread: pages it touches first are taken from `node` (MPOL_PREFERRED), or the
+    default policy again for node < 0.  Returns False where the kernel / container does not allow the call."""
+    try:
+        libc = C.CDLL(None, use_errno=True)
+        SYS_set_mempolicy = 238  # x86_64
+        if node < 0:
+            return libc.syscall(SYS_set_mempolicy, 0, None, 0) == 0
+        mask = (C.c_ulong * 16)()
+        mask[node // 64] = 1 << (node % 64)
+        return libc.syscall(SYS_set_mempolicy, 1, mask, 16 * 64 + 1) == 0
+    except Exception:
+        return False
+
+
+def rank_slice(count, rank, world):
+    """[lo, hi) of `count` result elements that rank `rank` sends to the host (fetch_distributed)."""
+    per = ((count + world - 1) // world + 63) // 64 * 64
+    return min(rank * per, count), min((rank + 1) * per, count)
+
+
 class SharedHost:
     """A host buffer that every process of the job maps and page-locks: rank 0 creates a file under /dev/shm, all
-    ranks map it (torch.from_file, shared) and register the mapping with CUDA, so that each rank's copy engine
-    can write its slice of the results into the same host memory over its own PCIe link."""
+    ranks map it (torch.from_file, shared), touch THEIR slice of it first -- with the memory policy set to the NUMA
+    node of their GPU, so that the pages a rank's copy engine will write lie behind its own PCIe root and not across
+    the socket interconnect -- and register the mapping with CUDA.  `width` = bytes per result element (the slices
+    are those of fetch_distributed)."""
 
-    def __init__(self, nbytes, tag, rank, world, directory="/dev/shm"):
+    def __init__(self, nbytes, tag, rank, world, width=1, device=None, directory="/dev/shm"):
         self.nbytes = max(int(nbytes), 1)
         box = [None]
         if rank == 0:
@@ -510,6 +544,15 @@ class SharedHost:
             dist.broadcast_object_list(box, src=0)
         self.path = box[0]
         self.t = torch.from_file(self.path, shared=True, size=self.nbytes, dtype=torch.uint8)
+        lo, hi = rank_slice(self.nbytes // width, rank, world)
+        self.node = gpu_numa_node(torch.cuda.current_device() if device is None else device)
+        self.policy = self.node >= 0 and _set_mempolicy(self.node)
+        if hi > lo:
+            self.t[lo * width:hi * width].zero_()  # first touch: these pages now exist, on this rank's node if the policy took
+        if self.policy:
+            _set_mempolicy(-1)
+        if world > 1:
+            dist.barrier()
         rc = torch.cuda.cudart().cudaHostRegister(self.t.data_ptr(), self.nbytes, 0)
         if int(rc) != 0:
             raise RuntimeError("cudaHostRegister failed (%s)" % rc)
@@ -565,21 +608,33 @@ def fetch_distributed(engine, state, host_words_ptr, host_sa_ptr, host_preisa_pt
     nwords = (n - 1 + 15) >> 4
     nsa = res.sizes.get("sa", 0) // 8
     res.extra("bwa", 4 * nwords)
+    marks = state.get("fetch_timeline")  # bench.py: a list that receives (phase, CUDA event) pairs
+
+    def mark(name):
+        if marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((name, ev))
+
+    mark("start")
     fence = state.get("fence")
     if fence is None:
         fence = state["fence"] = torch.zeros(1, dtype=torch.int64, device=dev)
     if rank == 0:
         engine.pack_bwa(res.p["bwa"], 0, nwords)
+    mark("pack words (rank 0)")
     if world > 1:
         dist.all_reduce(fence, op=dist.ReduceOp.SUM)
+    mark("fence")
     sent = 0
+    todo = []
     for key, count, width, hptr in (("bwa", nwords, 4, host_words_ptr), ("sa", nsa, 8, host_sa_ptr)):
         if not count or not hptr:
             continue
-        per = ((count + world - 1) // world + 63) // 64 * 64
-        lo, hi = min(rank * per, count), min((rank + 1) * per, count)
+        lo, hi = rank_slice(count, rank, world)
         if hi <= lo:
             continue
+        per = rank_slice(count, 0, world)[1]
         nb = (hi - lo) * width
         src = res.p[key] + lo * width
         if rank != 0:
@@ -588,12 +643,18 @@ def fetch_distributed(engine, state, host_words_ptr, host_sa_ptr, host_preisa_pt
                 stage = state["stage_" + key] = torch.empty(per * width, dtype=torch.uint8, device=dev)
             res.mem.copy(stage.data_ptr(), src, nb, stream_ptr)  # NVLink: rank 0's HBM -> mine
             src = stage.data_ptr()
-        res.mem.copy(hptr + lo * width, src, nb, stream_ptr)       # my PCIe link
+        todo.append((hptr + lo * width, src, nb))
+    mark("pull slices over NVLink")
+    for dst, src, nb in todo:
+        res.mem.copy(dst, src, nb, stream_ptr)                     # my PCIe link
         sent += nb
+    mark("slices to the host")
     if rank == 0 and (host_preisa_ptr or host_isa_ptr):
         engine.fetch_ptrs(0, host_preisa_ptr, 0, host_isa_ptr)
+    mark("anchors + ISA (rank 0)")
     if world > 1:
         dist.all_reduce(fence, op=dist.ReduceOp.SUM)
+    mark("fence 2")
     return sent
 
 

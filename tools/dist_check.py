@@ -57,7 +57,7 @@ for it in range(2):
             i0 = eng.info()
             if shared is None:
                 nw = (i0["n"] - 1 + 15) >> 4
-                shared = {"bwa": multigpu.SharedHost(4 * nw, "bwa", rank, world), "sa": multigpu.SharedHost(8 * i0["nsa"], "sa", rank, world)}
+                shared = {"bwa": multigpu.SharedHost(4 * nw, "bwa", rank, world, width=4), "sa": multigpu.SharedHost(8 * i0["nsa"], "sa", rank, world, width=8)}
                 shared["bwa"].t.fill_(0xEE)
                 shared["sa"].t.fill_(0xEE)
             multigpu.fetch_distributed(eng, drv, shared["bwa"].ptr(), shared["sa"].ptr())
