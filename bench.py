@@ -244,7 +244,7 @@ def run_ours(args):
     def build(host_sa_ptr=0, host_bwa_ptr=0):
         if world == 1:
             # e2e leg: the sampled SA and BWA's packed BWT land in the caller's pinned buffers while the last sorting step still runs
-            eng.build(numblocks=args.numblocks, host_sa_ptr=host_sa_ptr, host_bwa_ptr=host_bwa_ptr, **params)
+            eng.build(numblocks=args.numblocks, host_sa_ptr=host_sa_ptr, host_bwa_ptr=host_bwa_ptr, gapmode=args.gapmode, **params)
         else:
             state["drv"], res = multigpu.build_distributed(eng, local_blocks=args.numblocks, driver=state["drv"], strategy=args.strategy, **params)
             state["strategy"] = res["strategy"]
@@ -571,6 +571,7 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debugging only; invalid as a bench value)")
     ap.add_argument("--numblocks", type=int, default=1)
+    ap.add_argument("--gapmode", default="auto", choices=["auto", "atomic", "list"], help="how K5 counts gap arrays (multi-block builds; include/b3m.h B3M_GAP_*)")
     ap.add_argument("--strategy", default="auto", choices=["auto", "shard", "merge"], help="multi-GPU decomposition (bwtb3m_b200.multigpu)")
     ap.add_argument("--cpu-sample", type=int, default=256_000_000, help="symbols of the workload the cpu_baseline leg processes")
     ap.add_argument("--ref-sample", type=int, default=128_000_000, help="symbols per step of --impl reference (about 7 s of CPU work per step)")

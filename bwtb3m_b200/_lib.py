@@ -21,6 +21,7 @@ class BuildParams(C.Structure):
         ("host_sa", C.c_void_p),
         ("host_bwa", C.c_void_p),
         ("sortpath", C.c_int),
+        ("gapmode", C.c_int),
     ]
 
 

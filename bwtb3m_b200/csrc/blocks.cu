@@ -8,6 +8,7 @@
 #include "rankdict.cuh"
 #include "scan.cuh"
 #include "textview.cuh"
+#include "radix.cuh"
 #include <string.h>
 #include <algorithm>
 #include <string>
@@ -172,7 +173,8 @@ __global__ void __launch_bounds__(256)
 k_gap(DictView D, CTab C, TextRef t, uint64_t a1, uint64_t r1, uint64_t chl, uint64_t c_lo, uint64_t c_hi, const uint32_t * __restrict__ r0,
       const uint8_t * __restrict__ gt_in /* indexed by text position */, uint8_t * __restrict__ gt_out /* indexed by position - a1 */,
       const uint32_t * __restrict__ special, uint32_t isa_a0, uint64_t ratemask, uint32_t rateshift,
-      uint32_t * __restrict__ G, uint32_t * __restrict__ rsamp /* indexed by position / rate */) {
+      uint32_t * __restrict__ G, uint32_t * __restrict__ rsamp /* indexed by position / rate */,
+      uint32_t * __restrict__ rlist /* nullptr: count in G at once; else step k of chain c writes rlist[k * rl_stride + (c - c_lo)] */, uint64_t rl_stride) {
 	uint64_t const c = c_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (c >= c_hi) return;
 	uint64_t const zlo = a1 + c * chl;
@@ -203,7 +205,8 @@ k_gap(DictView D, CTab C, TextRef t, uint64_t a1, uint64_t r1, uint64_t chl, uin
 			uint32_t const c0 = byte_of(cb, (uint32_t)(p & 15u));
 			r = C.c[c0] + dict_rank(D, c0, r) + ((c0 == lastA && g) ? 1u : 0u);
 		}
-		atomicAdd(&G[r], 1u);
+		if (rlist) rlist[(zhi - j) * rl_stride + (c - c_lo)] = r; // coalesced: the threads of a warp are consecutive chains
+		else atomicAdd(&G[r], 1u);
 		uint64_t const q = p - a1;
 		if ((q >> 4) != oblk) { if (omask) flush(); oblk = q >> 4; ob = make_uint4(0, 0, 0, 0); omask = 0; }
 		or_byte(ob, (uint32_t)(q & 15u), r > isa_a0 ? 1u : 0u); // Appendix A.3
@@ -211,6 +214,22 @@ k_gap(DictView D, CTab C, TextRef t, uint64_t a1, uint64_t r1, uint64_t chl, uin
 		if ((p & ratemask) == 0) rsamp[p >> rateshift] = r;
 	}
 	if (omask) flush();
+}
+
+// G[r]++ for the ranks of a list (0xffffffff: no entry).  The list has been partitioned by the top 8 bits of the rank
+// (one radix pass), and CTAs run in list order, so the counters touched at any time span 1/256 of G: they stay in L2
+// and the read-modify-write of a counter never reaches DRAM one sector at a time.
+__global__ void __launch_bounds__(256)
+k_gap_hist(const uint32_t * __restrict__ list, uint64_t n, uint32_t * __restrict__ G) {
+	uint64_t const i0 = ((uint64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+	if (i0 + 4 <= n) {
+		uint4 const v = ld_stream_u4(reinterpret_cast<const uint4 *>(list + i0));
+		if (v.x != 0xffffffffu) atomicAdd(&G[v.x], 1u);
+		if (v.y != 0xffffffffu) atomicAdd(&G[v.y], 1u);
+		if (v.z != 0xffffffffu) atomicAdd(&G[v.z], 1u);
+		if (v.w != 0xffffffffu) atomicAdd(&G[v.w], 1u);
+	} else
+		for (uint64_t i = i0; i < n; ++i) { uint32_t const r = list[i]; if (r != 0xffffffffu) atomicAdd(&G[r], 1u); }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -331,6 +350,7 @@ void Engine::leaf_build(BlockLeaf & leaf, uint64_t s, uint64_t m, uint8_t * L, u
 // dictionary over L_A (the placeholder of A's block-start row excluded) and C_A over A's text
 void Engine::gap_prepare(GapCtx & ctx, const uint8_t * LA, uint64_t a0, uint64_t na, uint32_t termA) {
 	int const flavour = T.sigma <= 4 ? 2 : 8;
+	ctx.na = na;
 	ctx.lines.alloc(st, dict_bytes(flavour, na, T.sigma));
 	k4_build_dict(st, LA, na, flavour, T.sigma, ctx.lines.get());
 	DictView & D = ctx.D;
@@ -371,8 +391,34 @@ void Engine::gap_run(GapCtx & ctx, uint64_t a1, uint64_t r1, uint64_t chl, uint6
 	if (c_lo >= c_hi) return;
 	if (!(T.has_term && r1 == T.n)) B3M_LAUNCH(st, k_gt_top, 1, 1, 0, t, r1, a1, d_special.get());
 	uint64_t const steps = std::min(a1 + c_hi * chl, r1) - (a1 + c_lo * chl);
-	B3M_LAUNCH_T(st, "gap_chains", steps * 128ull, k_gap, (unsigned)div_up(c_hi - c_lo, 256), 256, 0, ctx.D, ctx.C, t, a1, r1, chl, c_lo, c_hi, r0,
-	             gt_in, gtnew, (const uint32_t *)d_special.get(), termA, prerate - 1, ilog2u(prerate), G, rs);
+	// Counting in G straight from the chains is a random read-modify-write of one 32-byte sector per LF step; once G
+	// outgrows the L2 that is what bounds K5 (16 G steps/s against 59 G of the same walk without counters, K7).  Then the
+	// chains write their ranks as a list (coalesced, 4 B per step), one radix pass partitions the list by the top 8 bits
+	// of the rank, and k_gap_hist counts partition after partition with its counters resident in L2.
+	uint64_t const gbytes = 4 * (ctx.na + 1);
+	bool const use_list = params.gapmode == B3M_GAP_LIST || (params.gapmode != B3M_GAP_ATOMIC && gbytes > (48ull << 20));
+	if (!use_list) {
+		B3M_LAUNCH_T(st, "gap_chains", steps * 128ull, k_gap, (unsigned)div_up(c_hi - c_lo, 256), 256, 0, ctx.D, ctx.C, t, a1, r1, chl, c_lo, c_hi, r0,
+		             gt_in, gtnew, (const uint32_t *)d_special.get(), termA, prerate - 1, ilog2u(prerate), G, rs, (uint32_t *)nullptr, (uint64_t)0);
+	} else {
+		uint64_t const nl = c_hi - c_lo, len = chl * nl;
+		B3M_REQUIRE(len < 0xFFFFFF00ull, "internal: gap list too long");
+		int const bw = (int)ceil_log2_u64(ctx.na + 2);
+		bool const part = bw > 8 && (gbytes > (32ull << 20) || params.gapmode == B3M_GAP_LIST);
+		DevBuf<uint32_t> rl(st, len + 4), rl2;
+		if (part) rl2.alloc(st, len + 4);
+		B3M_CUDA(cudaMemsetAsync(rl.get(), 0xff, 4 * (len + 4), st.s)); // the last chain may be shorter than the others
+		B3M_LAUNCH_T(st, "gap_chains", steps * 68ull, k_gap, (unsigned)div_up(nl, 256), 256, 0, ctx.D, ctx.C, t, a1, r1, chl, c_lo, c_hi, r0,
+		             gt_in, gtnew, (const uint32_t *)d_special.get(), termA, prerate - 1, ilog2u(prerate), G, rs, rl.get(), nl);
+		const uint32_t * list = rl.get();
+		if (part) {
+			RadixRec<1> cur{{rl.get()}}, alt{{rl2.get()}};
+			radix_sort_bits<1>(st, cur, alt, 0, len, bw - 8, bw, nullptr);
+			list = cur.a[0];
+		}
+		B3M_LAUNCH_T(st, "gap_hist", len * 4ull + steps * 8ull, k_gap_hist, (unsigned)div_up(div_up(len, 4), 256), 256, 0, list, len, G);
+		B3M_CUDA(cudaStreamSynchronize(st.s)); // rl / rl2 are released here
+	}
 	gap_lf_steps += steps; gap_chains += c_hi - c_lo;
 }
 

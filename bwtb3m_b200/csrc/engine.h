@@ -19,6 +19,7 @@ struct EventAccum;
 
 // what K5 needs from the left part of a merge: rank dictionary over L_A and C_A
 struct GapCtx {
+	uint64_t na = 0;           // |A|: the gap array has na + 1 counters
 	DevBuf<uint8_t> lines;
 	DictView D;
 	CTab C;

@@ -56,7 +56,7 @@ __device__ __forceinline__ unsigned warp_peers8(uint32_t d) {
 }
 
 // ---- digit histograms of one key array: up to 4 digits in one read -----------------------
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_radix_hist(const uint32_t * __restrict__ key, uint64_t n, int bit_lo, int ndig, uint32_t lastmask,
              unsigned long long * __restrict__ ghist /* [ndig][256] */) {
 	__shared__ uint32_t sh[RADIX_MAXDIG][RADIX_BINS];
@@ -83,7 +83,7 @@ k_radix_hist(const uint32_t * __restrict__ key, uint64_t n, int bit_lo, int ndig
 }
 
 // exclusive scan of each digit's histogram; skip[d] = 1 when one bin holds every record
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_radix_hist_scan(const unsigned long long * __restrict__ ghist, int ndig, uint64_t n, uint32_t * __restrict__ base /* [ndig][256] */,
                   uint32_t * __restrict__ skip) {
 	for (int d = 0; d < ndig; ++d) {
@@ -544,7 +544,7 @@ void radix_sort_bits(Stream & st, RadixRec<NA> & cur, RadixRec<NA> & alt, int ka
 			B3M_CUDA(cudaMemsetAsync(status.get(), 0, status.bytes(), st.s));
 			RadixPassArgs<NA> A;
 			A.in[0] = cur.a[ka]; A.out[0] = alt.a[ka];
-			for (int a = 0, o = 1; a < NA; ++a) if (a != ka) { A.in[o] = cur.a[a]; A.out[o] = alt.a[a]; ++o; }
+			for (int a = 0, o = 1; a < NA; ++a) if (a != ka && o < NA) { A.in[o] = cur.a[a]; A.out[o] = alt.a[a]; ++o; }
 			A.aux_in = cur.aux; A.aux_out = alt.aux;
 			uint64_t const pbytes = n * (8ull * NA + (cur.aux ? 2ull : 0ull));
 			if (cur.aux)
@@ -563,7 +563,7 @@ void radix_sort_bits(Stream & st, RadixRec<NA> & cur, RadixRec<NA> & alt, int ka
 // Digit d of the key of suffix i is the 4-mer at window index i + 4*(3-d), so all four digit
 // histograms come from ONE histogram of the window's 4-mers plus at most 12 corrections at
 // either end (exactly equal for a circular window).
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 k_hist_4mers(TextView v, unsigned long long * __restrict__ ghist /* [256] */) {
 	__shared__ uint32_t sh[RADIX_WARPS][RADIX_BINS];
 	for (int i = threadIdx.x; i < RADIX_WARPS * RADIX_BINS; i += blockDim.x) (&sh[0][0])[i] = 0;
@@ -594,7 +594,7 @@ k_hist_4mers(TextView v, unsigned long long * __restrict__ ghist /* [256] */) {
 
 // ghist[0][*] = histogram of the 4-mers at window indices [0, W)  ->  ghist[d][*], d = 0..3:
 // digit d counts the 4-mers at indices [off, off + W), off = 4*(3-d)
-__global__ void __launch_bounds__(256) k_hist_4mers_fix(TextView v, unsigned long long * __restrict__ ghist) {
+static __global__ void __launch_bounds__(256) k_hist_4mers_fix(TextView v, unsigned long long * __restrict__ ghist) {
 	unsigned long long const h0 = ghist[threadIdx.x];
 	for (int d = 0; d < 3; ++d) ghist[d * RADIX_BINS + threadIdx.x] = h0;
 	ghist[3 * RADIX_BINS + threadIdx.x] = h0;

@@ -60,11 +60,13 @@ class Engine:
         self._check(self._lib.b3m_engine_load_device(self._h, C.c_void_p(dptr), nbytes, INPUT_TYPES[inputtype]))
 
     def build(self, numblocks=1, preisarate=0, sasamplingrate=32, isasamplingrate=262144, bwtonly=False,
-              largelcpthres=16384, sampling="auto", host_sa_ptr=0, host_bwa_ptr=0, sortpath="auto"):
+              largelcpthres=16384, sampling="auto", host_sa_ptr=0, host_bwa_ptr=0, sortpath="auto", gapmode="auto"):
         """sampling: "auto" (sampled SA/ISA straight from the suffix array when one block holds the whole
-        text, LF walk otherwise) or "walk" (always the reference's LF walk from the anchors)."""
+        text, LF walk otherwise) or "walk" (always the reference's LF walk from the anchors).
+        gapmode: how K5 counts a gap array: "auto" (by its size), "atomic" or "list" (include/b3m.h B3M_GAP_*)."""
         p = BuildParams(numblocks, preisarate, sasamplingrate, isasamplingrate, 1 if bwtonly else 0, largelcpthres,
-                        {"auto": 0, "walk": 1}[sampling], host_sa_ptr or None, host_bwa_ptr or None, SORTPATHS[sortpath])
+                        {"auto": 0, "walk": 1}[sampling], host_sa_ptr or None, host_bwa_ptr or None, SORTPATHS[sortpath],
+                        {"auto": 0, "atomic": 1, "list": 2}[gapmode])
         self._check(self._lib.b3m_engine_build(self._h, C.byref(p)))
 
     def info(self):

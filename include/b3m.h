@@ -161,7 +161,14 @@ typedef struct b3m_build_params {
 	uint32_t * host_bwa;       /* likewise (pacterm, one block): PINNED host buffer of ceil((n-1)/16) words that receives
 	                            * BWA's packed BWT (see b3m_engine_fetch_bwa) while the build runs.  NULL: off */
 	int sortpath;              /* B3M_SORT_*: suffix sorter of a one-block build over an alphabet of at most four codes */
+	int gapmode;               /* B3M_GAP_*: how K5 counts the gap array of a merge (builds of two or more blocks) */
 } b3m_build_params;
+/* AUTO: gap arrays that fit the L2 cache are counted by the chains themselves (atomic adds), larger ones from a
+ * list of the chains' ranks partitioned by one radix pass, so that the counters in use stay in L2.  ATOMIC / LIST
+ * force one of them (tests, measurements).  Same results. */
+#define B3M_GAP_AUTO 0
+#define B3M_GAP_ATOMIC 1
+#define B3M_GAP_LIST 2
 /* AUTO: the MSD bucket sort (two global levels + a finish in shared memory) for texts of 2^16 symbols or more,
  * the LSD radix sort otherwise.  LSD / MSD force one of them (tests, measurements).  Same results. */
 #define B3M_SORT_AUTO 0

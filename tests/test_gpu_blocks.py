@@ -15,12 +15,12 @@ def eng():
     e.close()
 
 
-def check(eng, oracle, data, itype, text, numblocks, rates=(16, 4, 8)):
+def check(eng, oracle, data, itype, text, numblocks, rates=(16, 4, 8), gapmode="auto"):
     sa = oracle.sa_circular(text)
     bwt, isa = oracle.bwt_from_sa(text, sa)
     pre, sar, isar = rates
     eng.load_host(data, itype)
-    eng.build(numblocks=numblocks, preisarate=pre, sasamplingrate=sar, isasamplingrate=isar)
+    eng.build(numblocks=numblocks, preisarate=pre, sasamplingrate=sar, isasamplingrate=isar, gapmode=gapmode)
     res, info = eng.fetch(), eng.info()
     assert info["n"] == text.size
     assert np.array_equal(res["bwt"], bwt), "BWT differs (numblocks=%d)" % numblocks
@@ -50,6 +50,25 @@ def test_blocks_pac(eng, oracle, seed, l, itype, numblocks):
     pac = oracle.encode_pac(bases)
     t = oracle.decode_pac(pac.tobytes(), term=(itype == "pacterm"))
     check(eng, oracle, pac, itype, t, numblocks)
+
+
+@pytest.mark.parametrize("gapmode", ["list", "atomic"])
+@pytest.mark.parametrize("numblocks", [2, 3, 5, 16])
+@pytest.mark.parametrize("case", ["pacterm-300007", "pac-65537", "bytes256-40001", "bytes3-9000", "pacterm-777", "pacterm-5"])
+def test_blocks_gap_counting_modes(eng, oracle, case, numblocks, gapmode):
+    """K5 counts the gap array either by atomic adds from the chains or from a list of the chains' ranks partitioned by
+    one radix pass (what gap arrays beyond the L2 size take): forced on small texts, both equal the oracle."""
+    kind, n = case.split("-")
+    n = int(n)
+    rng = np.random.default_rng(n + numblocks)
+    if kind.startswith("bytes"):
+        t = rng.integers(0, int(kind[5:]), size=n, dtype=np.uint8)
+        data, itype = t, "bytestream"
+    else:
+        data, itype = oracle.encode_pac(rng.integers(0, 4, size=n, dtype=np.uint8)), kind
+        t = oracle.decode_pac(data.tobytes(), term=(kind == "pacterm"))
+    info = check(eng, oracle, data, itype, t, numblocks, gapmode=gapmode)
+    assert info["gap_lf_steps"] > 0
 
 
 def test_blocks_terminator_alone_in_last_block(eng, oracle):
