@@ -941,11 +941,11 @@ k_dbl_tile(const uint32_t * __restrict__ cg, const uint32_t * __restrict__ ci, u
 	__shared__ uint32_t s_hb[DT_WORDS + 1]; // heads
 	__shared__ uint32_t s_db[DT_WORDS + 1]; // deviants
 	__shared__ uint32_t s_dpre[DT_WORDS + 1];
-	__shared__ uint32_t s_big, s_nq, s_cnt[2];
+	__shared__ uint32_t s_big, s_nq, s_cnt[3];
 	uint32_t const t0 = blockIdx.x * (uint32_t)DT_TILE;
 	uint32_t const abase = t0 - (uint32_t)DT_GMAX; // region index x <-> list index abase + x; places before the list wrap to huge values
 	unsigned const lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-	if (threadIdx.x == 0) { s_big = 0; s_nq = 0; s_cnt[0] = 0; s_cnt[1] = 0; }
+	if (threadIdx.x == 0) { s_big = 0; s_nq = 0; s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0; }
 	for (int x = threadIdx.x; x < DT_REG; x += DT_THREADS) {
 		uint32_t const a = abase + (uint32_t)x;
 		bool const valid = a < na;
@@ -1027,6 +1027,7 @@ k_dbl_tile(const uint32_t * __restrict__ cg, const uint32_t * __restrict__ ci, u
 	}
 	__syncthreads();
 	uint32_t n_own = 0, n_next = 0; // entries still tied, by the tile of the list they land in
+	uint32_t n_chg = 0;             // entries whose rank changes
 	auto emit = [&](int x, int sx, uint32_t less, uint32_t eqb, uint32_t eq) {
 		uint32_t const g = s_g[x], i = s_i[x];
 		uint32_t const a2 = abase + (uint32_t)sx + less + eqb;
@@ -1035,6 +1036,7 @@ k_dbl_tile(const uint32_t * __restrict__ cg, const uint32_t * __restrict__ ci, u
 		oi[a2] = i;
 		of[a2] = (uint8_t)((eq > 1 ? 1u : 0u) | (less ? 4u : 0u));
 		if (eq > 1) { if (a2 - t0 < (uint32_t)DT_TILE) ++n_own; else ++n_next; }
+		if (less) ++n_chg;
 	};
 	auto devs_before = [&](int x) -> uint32_t { return s_dpre[x >> 5] + (uint32_t)__popc(s_db[x >> 5] & ((1u << (x & 31)) - 1u)); };
 	#pragma unroll
@@ -1064,10 +1066,12 @@ k_dbl_tile(const uint32_t * __restrict__ cg, const uint32_t * __restrict__ ci, u
 	}
 	n_own = __reduce_add_sync(0xffffffffu, n_own);
 	n_next = __reduce_add_sync(0xffffffffu, n_next);
-	if (lane == 0) { if (n_own) atomicAdd(&s_cnt[0], n_own); if (n_next) atomicAdd(&s_cnt[1], n_next); }
+	n_chg = __reduce_add_sync(0xffffffffu, n_chg);
+	if (lane == 0) { if (n_own) atomicAdd(&s_cnt[0], n_own); if (n_next) atomicAdd(&s_cnt[1], n_next); if (n_chg) atomicAdd(&s_cnt[2], n_chg); }
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		if (s_big) atomicAdd(nbig, s_big);
+		if (s_cnt[2]) atomicAdd(nbig + 1, s_cnt[2]); // nbig[1]: ranks that change in this round
 		if (s_cnt[0]) atomicAdd(&tcount[blockIdx.x], s_cnt[0]);
 		if (s_cnt[1]) atomicAdd(&tcount[blockIdx.x + 1], s_cnt[1]);
 	}
@@ -1077,8 +1081,11 @@ k_dbl_tile(const uint32_t * __restrict__ cg, const uint32_t * __restrict__ ci, u
 // (now that every CTA has read the old ones) and moves the entries still tied to the front: tbase = exclusive scan
 // of k_dbl_tile's per-tile counts, the place inside the tile from ballots (warp w handles places w*32.. of every
 // DT_THREADS-wide row, all accesses coalesced).
+// DIRECT = false: the changed ranks are not written here; oi[a] is replaced by the suffix whose rank changed (or
+// 0xffffffff), so that (oi, og) are the pairs rank_write_partitioned takes.
+template <bool DIRECT>
 __global__ void __launch_bounds__(DT_THREADS)
-k_dbl_compact(const uint32_t * __restrict__ og, const uint32_t * __restrict__ oi, const uint8_t * __restrict__ of, uint32_t na,
+k_dbl_compact(const uint32_t * __restrict__ og, uint32_t * __restrict__ oi, const uint8_t * __restrict__ of, uint32_t na,
               const uint32_t * __restrict__ tbase, uint32_t * __restrict__ rank, uint32_t * __restrict__ cg, uint32_t * __restrict__ ci) {
 	constexpr int ROWS = DT_TILE / DT_THREADS, WARPS = DT_THREADS / 32;
 	__shared__ uint32_t s_pre[ROWS * WARPS];
@@ -1109,15 +1116,49 @@ k_dbl_compact(const uint32_t * __restrict__ og, const uint32_t * __restrict__ oi
 	uint32_t const base = tbase[blockIdx.x];
 	#pragma unroll
 	for (int j = 0; j < ROWS; ++j) {
-		if (!(f[j] & 5u)) continue;
 		uint32_t const a = t0 + (uint32_t)(j * DT_THREADS) + threadIdx.x;
+		if (!(f[j] & 5u)) { if (!DIRECT && a < na) oi[a] = 0xffffffffu; continue; }
 		uint32_t const g = og[a], i = oi[a];
-		if (f[j] & 4u) rank[i] = g;
+		if (DIRECT) { if (f[j] & 4u) rank[i] = g; }
+		else if (!(f[j] & 4u)) oi[a] = 0xffffffffu;
 		if (f[j] & 1u) {
 			uint32_t const dst = base + s_pre[j * WARPS + w] + (uint32_t)__popc(bal[j] & lanemask_lt());
 			cg[dst] = g; ci[dst] = i;
 		}
 	}
+}
+
+// rank[pi[k]] = pg[k] for the pairs of a list (pi = 0xffffffff: no pair).  A rank array beyond the L2 size takes one
+// 4-byte store at a random place as a read-modify-write of a 32-byte sector (27 G stores/s measured on cfg4); with the
+// pairs partitioned by the top 8 bits of their target (one radix pass, rank_write_partitioned) the stores in flight fall
+// into 1/256 of the array, merge in L2 and leave as whole sectors.
+__global__ void __launch_bounds__(256)
+k_rank_write(const uint32_t * __restrict__ pi, const uint32_t * __restrict__ pg, uint64_t n, uint32_t * __restrict__ rank) {
+	uint64_t const i0 = ((uint64_t)blockIdx.x * 256 + threadIdx.x) * 4;
+	if (i0 + 4 <= n) {
+		uint4 const a = ld_stream_u4(reinterpret_cast<const uint4 *>(pi + i0)), g = ld_stream_u4(reinterpret_cast<const uint4 *>(pg + i0));
+		if (a.x != 0xffffffffu) rank[a.x] = g.x;
+		if (a.y != 0xffffffffu) rank[a.y] = g.y;
+		if (a.z != 0xffffffffu) rank[a.z] = g.z;
+		if (a.w != 0xffffffffu) rank[a.w] = g.w;
+	} else
+		for (uint64_t i = i0; i < n; ++i) if (pi[i] != 0xffffffffu) rank[pi[i]] = pg[i];
+}
+
+// pairs (pi, pg) in list order -> rank; t0 / t1 = scratch of n words each (16-byte aligned, like pi / pg); pi / pg are kept
+static void rank_write_partitioned(Stream & st, uint32_t * pi, uint32_t * pg, uint64_t n, uint32_t * t0, uint32_t * t1, uint64_t W, uint32_t * rank,
+                                   const char * label, SortStats & S) {
+	int const bw = (int)ceil_log2_u64(W + 1);
+	const uint32_t * qi = pi, * qg = pg;
+	if (bw > 8) {
+		RadixRec<2> cur{{pi, pg}}, alt{{t0, t1}};
+		RadixStats rs;
+		radix_sort_bits<2>(st, cur, alt, 0, n, bw - 8, bw, &rs); // one pass: the result lies in t0 / t1 (or in place when every target shares the digit)
+		S.radix_passes += rs.passes; S.radix_bytes += rs.bytes;
+		qi = cur.a[0]; qg = cur.a[1];
+	}
+	B3M_LAUNCH_T(st, label, n * 12ull, k_rank_write, (unsigned)div_up(div_up(n, 4), 256), 256, 0, qi, qg, n, rank);
+	S.other_bytes += n * 12ull;
 }
 
 void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W, int circular, int text_wraps,
@@ -1276,14 +1317,26 @@ void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W,
 			const uint8_t * hf = hflag.get();
 			uint64_t const Wm = W;
 			// head flags -> group head position (max-scan); rank of every suffix = head of its group
-			scan_apply<OpMax>(st, W,
-				[=] __device__(uint64_t k) -> uint32_t { return (k && hf[k]) ? (uint32_t)k : 0u; },
-				[=] __device__(uint64_t k, uint32_t excl, uint32_t v0) {
-					uint32_t const head = excl > v0 ? excl : v0;
-					grp[k] = head;
-					rank[sa[k]] = head;
-				}, "heads_rank_scatter", W * 42ull);
-			S.other_bytes += W * (2ull + 4ull + 4ull + 32ull);
+			// rank array beyond the L2 size: see k_rank_write (sortpath=msd forces it on small texts, for the tests)
+			bool const part_ranks = W * 4ull > (64ull << 20) ? st.sortpath != B3M_SORT_LSD : st.sortpath == B3M_SORT_MSD;
+			if (!part_ranks) {
+				scan_apply<OpMax>(st, W,
+					[=] __device__(uint64_t k) -> uint32_t { return (k && hf[k]) ? (uint32_t)k : 0u; },
+					[=] __device__(uint64_t k, uint32_t excl, uint32_t v0) {
+						uint32_t const head = excl > v0 ? excl : v0;
+						grp[k] = head;
+						rank[sa[k]] = head;
+					}, "heads_rank_scatter", W * 42ull);
+				S.other_bytes += W * (2ull + 4ull + 4ull + 32ull);
+			} else {
+				scan_apply<OpMax>(st, W,
+					[=] __device__(uint64_t k) -> uint32_t { return (k && hf[k]) ? (uint32_t)k : 0u; },
+					[=] __device__(uint64_t k, uint32_t excl, uint32_t v0) { grp[k] = excl > v0 ? excl : v0; }, "heads", W * 6ull);
+				S.other_bytes += W * 6ull;
+				DevBuf<uint32_t> t0(st, W + 4), t1(st, W + 4);
+				rank_write_partitioned(st, sa, grp, W, t0.get(), t1.get(), W, rank, "heads_rank_write", S);
+				B3M_CUDA(cudaStreamSynchronize(st.s)); // t0 / t1 are released here
+			}
 			TRACE("heads+rank scatter");
 			auto active = [=] __device__(uint64_t k) -> uint32_t {
 				bool const hk = grp[k] == (uint32_t)k;
@@ -1382,11 +1435,11 @@ void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W,
 				uint32_t const ntiles = (uint32_t)div_up(na, DT_TILE);
 				DevBuf<uint32_t> tcount(st, (uint64_t)ntiles + 1);
 				B3M_CUDA(cudaMemsetAsync(tcount.get(), 0, tcount.bytes(), st.s));
-				B3M_CUDA(cudaMemsetAsync(d_total + 1, 0, 4, st.s));
+				B3M_CUDA(cudaMemsetAsync(d_total + 1, 0, 8, st.s));
 				B3M_LAUNCH_T(st, "dbl_tile", na * 59ull, k_dbl_tile, ntiles, DT_THREADS, 0, (const uint32_t *)cg, (const uint32_t *)ci, (uint32_t)na,
 				             (const uint32_t *)rank, sa, h, W, circular, og, oi, of, d_total + 1, tcount.get());
 				S.other_bytes += na * (8ull + 32ull + 4ull + 9ull);
-				uint64_t const nbig = fetch_u32(st, d_total + 1);
+				uint64_t const nbig = fetch_u32(st, d_total + 1), nchg = fetch_u32(st, d_total + 2);
 				TRACE("rN tile");
 				if (nbig <= na / 4) {
 					DevBuf<uint32_t> bpool[6];
@@ -1403,9 +1456,20 @@ void k2_suffix_sort(Stream & st, DevText const & T, uint64_t wstart, uint64_t W,
 					}
 					// the changed ranks are written now; members of groups still tied make the next list
 					scan_exclusive_inplace<OpSum>(st, tcount.get(), (uint64_t)ntiles + 1);
-					B3M_LAUNCH_T(st, "dbl_compact", na * 49ull, k_dbl_compact, ntiles, DT_THREADS, 0, (const uint32_t *)og, (const uint32_t *)oi, (const uint8_t *)of, (uint32_t)na,
-					             (const uint32_t *)tcount.get(), rank, cg, ci);
-					S.other_bytes += na * (9ull + 8ull + 32ull);
+					// scattered rank stores cost a 64-byte read-modify-write each once the rank array outgrows the L2 (27 G stores/s);
+					// partitioning the (suffix, rank) pairs of the round streams 53 B per list entry: taken when a quarter of the
+					// list or more changes its rank (cfg4: compaction + rank stores 697 -> 507 ms over the 11 rounds)
+					bool const part = (W * 4ull > (64ull << 20) || st.sortpath == B3M_SORT_MSD) && nchg * 4ull > na;
+					if (!part) {
+						B3M_LAUNCH_T(st, "dbl_compact", na * 49ull, k_dbl_compact<true>, ntiles, DT_THREADS, 0, (const uint32_t *)og, oi, (const uint8_t *)of, (uint32_t)na,
+						             (const uint32_t *)tcount.get(), rank, cg, ci);
+						S.other_bytes += na * (9ull + 8ull) + nchg * 32ull;
+					} else {
+						B3M_LAUNCH_T(st, "dbl_compact", na * 21ull, k_dbl_compact<false>, ntiles, DT_THREADS, 0, (const uint32_t *)og, oi, (const uint8_t *)of, (uint32_t)na,
+						             (const uint32_t *)tcount.get(), rank, cg, ci);
+						S.other_bytes += na * (9ull + 8ull + 4ull);
+						rank_write_partitioned(st, oi, og, na, bufs[4], bufs[5], W, rank, "dbl_rank_write", S); // `of` (bufs[4]) is dead by now
+					}
 					B3M_CUDA(cudaMemcpyAsync(d_total, tcount.get() + ntiles, 4, cudaMemcpyDeviceToDevice, st.s));
 					uint64_t nn = fetch_u32(st, d_total);
 					TRACE("rN compact");
