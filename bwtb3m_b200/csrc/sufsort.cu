@@ -273,7 +273,8 @@ struct MsdGeom { unsigned b1 = 0, b2 = 0; };
 // records including the padding of its runs)
 // nparts > 1 (position-sharded build): the level-1 runs of a tile cross NVLink as they are stored, and 64-byte runs use
 // a third of the link; one bit less doubles them (measured on 2 GPUs at 3.1 Gbp: scatter 21.1 -> 16.2 ms, finish -- twice
-// the runs to gather -- 15.8 -> 18.9 ms; profiles/r2s_*)
+// the runs to gather -- 15.8 -> 18.9 ms).  8 bits do not work: a finish CTA holds its sub-bucket plus two padding
+// records per tile of the parent bucket, and a bucket of 1/256 of a 3.1 Gbp text has 1478 tiles (MSD_CAP)
 static bool msd_geometry(Stream const & st, DevText const & T, uint64_t W, MsdGeom & g, uint32_t nparts = 1) {
 	if (st.sortpath == B3M_SORT_LSD) return false;
 	if (T.keybits != 2 || !T.packed || W < 64 || W >= 0xFFFFFF00ull) return false;

@@ -535,13 +535,25 @@ class SharedHost:
 
     def __init__(self, nbytes, tag, rank, world, width=1, device=None, directory="/dev/shm"):
         self.nbytes = max(int(nbytes), 1)
+        self.t = None
         box = [None]
         if rank == 0:
-            box[0] = os.path.join(directory if os.path.isdir(directory) else "/tmp", "b3m_%d_%s" % (os.getpid(), tag))
-            with open(box[0], "wb") as f:
-                f.truncate(self.nbytes)
+            # a sparse file on a tmpfs without room would fault (SIGBUS) at the first touch: check before creating it
+            import shutil
+            import tempfile
+            for d in (directory, tempfile.gettempdir()):
+                try:
+                    if os.path.isdir(d) and shutil.disk_usage(d).free > self.nbytes + (64 << 20):
+                        box[0] = os.path.join(d, "b3m_%d_%s" % (os.getpid(), tag))
+                        with open(box[0], "wb") as f:
+                            f.truncate(self.nbytes)
+                        break
+                except OSError:
+                    box[0] = None
         if world > 1:
             dist.broadcast_object_list(box, src=0)
+        if box[0] is None:
+            raise RuntimeError("no room for a shared host buffer of %d bytes under %s" % (self.nbytes, directory))  # on every rank alike
         self.path = box[0]
         self.t = torch.from_file(self.path, shared=True, size=self.nbytes, dtype=torch.uint8)
         lo, hi = rank_slice(self.nbytes // width, rank, world)

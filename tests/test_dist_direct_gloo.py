@@ -97,3 +97,19 @@ def test_direct_sharded_driver_gloo(world, force):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert good
+
+
+def test_rank_slices_cover_the_results_exactly_once():
+    """fetch_distributed / SharedHost: the slices the ranks send to the host partition [0, count), start on multiples of
+    64 elements, and the slice length of rank 0 bounds every other one (it sizes the staging buffers)."""
+    from bwtb3m_b200 import multigpu
+    for count in (0, 1, 63, 64, 65, 6251, 1 << 20, 193_750_001):
+        for world in (1, 2, 3, 4, 8):
+            cover = 0
+            per = multigpu.rank_slice(count, 0, world)[1]
+            for r in range(world):
+                lo, hi = multigpu.rank_slice(count, r, world)
+                assert lo == min(cover, count) and lo % 64 == 0 or lo == count
+                assert hi - lo <= max(per, 0)
+                cover = max(cover, hi)
+            assert cover == count
