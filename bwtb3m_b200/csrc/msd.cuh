@@ -236,6 +236,7 @@ struct MsdP1 {
 	unsigned b1;
 	uint32_t d_lo, nkeep;           // bins [d_lo, d_lo + nkeep) are kept (one key range of a bin-sharded build, or all)
 	uint32_t t_lo;                  // first tile of the text this launch covers (position-sharded builds: one range of tiles per GPU)
+	uint32_t nt;                    // tiles of the launch
 	const uint32_t * base;          // [nkeep] where this launch's first record of kept bin b goes in its destination array
 	const uint32_t * toff;          // [tiles of the launch][nkeep] records of bin b in the earlier tiles of the launch
 	// destination arrays: bin b belongs to part p with bnd[p] <= b < bnd[p+1]; out[p] may be another GPU's memory
@@ -245,36 +246,48 @@ struct MsdP1 {
 	unsigned long long * out[MSD_MAXPARTS];
 };
 
-__global__ void __launch_bounds__(MSD_THREADS, 2)
+// SUB = 1: one tile per CTA of 512 threads (two CTAs per SM).  SUB = 2: two consecutive tiles per CTA of 1024 threads:
+// the column scan puts the records of consecutive tiles next to each other inside a bin, so the CTA stores runs of
+// twice the length -- what a position-sharded build wants, whose runs cross NVLink (A.nt = tiles of the launch).
+template <int SUB>
+__global__ void __launch_bounds__(MSD_THREADS * SUB, 2 / SUB)
 k_msd_scatter(MsdP1 A) {
+	constexpr int THREADS = MSD_THREADS * SUB;
 	extern __shared__ __align__(16) uint8_t msd_dyn[];
-	unsigned long long * const stage = reinterpret_cast<unsigned long long *>(msd_dyn);
+	unsigned long long * const stage = reinterpret_cast<unsigned long long *>(msd_dyn); // SUB * MSD_TILE records
 	__shared__ uint32_t cnt[MSD_MAXBINS];
 	__shared__ uint32_t gdel[MSD_MAXBINS];
 	__shared__ uint8_t gown[MSD_MAXBINS];
 	__shared__ unsigned long long * s_out[MSD_MAXPARTS];
-	__shared__ uint32_t wsum[MSD_THREADS / 32];
+	__shared__ uint32_t wsum[THREADS / 32];
 	unsigned const nkeep = A.nkeep;
-	for (unsigned i = threadIdx.x; i < nkeep; i += MSD_THREADS) cnt[i] = 0;
+	for (unsigned i = threadIdx.x; i < nkeep; i += THREADS) cnt[i] = 0;
 	if (threadIdx.x < A.nparts) s_out[threadIdx.x] = A.out[threadIdx.x];
 	__syncthreads();
-	uint32_t const tile = blockIdx.x;
+	uint32_t const tile = blockIdx.x * SUB;                 // first tile of this CTA
+	uint32_t const sub = threadIdx.x / MSD_THREADS, ltid = threadIdx.x % MSD_THREADS;
 	uint64_t const t0 = (uint64_t)(tile + A.t_lo) * MSD_TILE;
+	uint32_t const lpos = sub * (uint32_t)MSD_TILE + (uint32_t)MSD_ITEMS * ltid; // first position of this thread, relative to t0
 
-	uint32_t hi32[MSD_ITEMS], dr[MSD_ITEMS]; // dr = (kept bin << 16) | rank inside the tile's bin; ~0: not kept
-	msd_records16<true>(A.v, A.b1, t0 + (uint64_t)MSD_ITEMS * threadIdx.x, dr, hi32);
+	uint32_t hi32[MSD_ITEMS], dr[MSD_ITEMS]; // dr = (kept bin << 16) | rank inside the CTA's bin; ~0: not kept
+	if (tile + sub < A.nt) msd_records16<true>(A.v, A.b1, t0 + lpos, dr, hi32);
+	else {
+		#pragma unroll
+		for (int j = 0; j < MSD_ITEMS; ++j) { dr[j] = 0xffffffffu; hi32[j] = 0; }
+	}
 	#pragma unroll
 	for (int j = 0; j < MSD_ITEMS; ++j) {
 		uint32_t const d = dr[j] - A.d_lo;
-		dr[j] = d < nkeep ? ((d << 16) | atomicAdd(&cnt[d], 1u)) : 0xffffffffu;
+		dr[j] = (dr[j] != 0xffffffffu && d < nkeep) ? ((d << 16) | atomicAdd(&cnt[d], 1u)) : 0xffffffffu;
 	}
 	__syncthreads();
-	uint32_t mine[4];
+	constexpr int PERMAX = MSD_MAXBINS / THREADS;
+	uint32_t mine[PERMAX];
 	unsigned b0, per;
-	uint32_t const nvalid = msd_scan_bins<MSD_THREADS, 4>(cnt, nkeep, wsum, mine, b0, per);
+	uint32_t const nvalid = msd_scan_bins<THREADS, PERMAX>(cnt, nkeep, wsum, mine, b0, per);
 	const uint32_t * const orow = A.toff + (uint64_t)tile * nkeep;
 	#pragma unroll
-	for (unsigned q = 0; q < 4; ++q)
+	for (unsigned q = 0; q < (unsigned)PERMAX; ++q)
 		if (q < per && b0 + q < nkeep) {
 			unsigned const b = b0 + q;
 			gdel[b] = __ldg(A.base + b) + __ldg(orow + b) - cnt[b];
@@ -287,17 +300,17 @@ k_msd_scatter(MsdP1 A) {
 		if (dr[j] != 0xffffffffu) {
 			uint32_t const d = dr[j] >> 16;
 			uint32_t const slot = cnt[d] + (dr[j] & 0xffffu);
-			stage[slot] = ((unsigned long long)hi32[j] << 32) | (d << 14) | (uint32_t)(MSD_ITEMS * threadIdx.x + j);
+			stage[slot] = ((unsigned long long)hi32[j] << 32) | (d << 15) | (lpos + (uint32_t)j);
 		}
 	}
 	__syncthreads();
 	#pragma unroll
 	for (int j = 0; j < MSD_ITEMS; ++j) {
-		uint32_t const s = j * MSD_THREADS + threadIdx.x;
+		uint32_t const s = j * THREADS + threadIdx.x;
 		if (s < nvalid) {
 			unsigned long long const w = stage[s];
-			uint32_t const lo = (uint32_t)w, d = lo >> 14;
-			s_out[gown[d]][gdel[d] + s] = (w & 0xffffffff00000000ull) | (uint32_t)(t0 + (lo & 0x3fffu));
+			uint32_t const lo = (uint32_t)w, d = lo >> 15;
+			s_out[gown[d]][gdel[d] + s] = (w & 0xffffffff00000000ull) | (uint32_t)(t0 + (lo & 0x7fffu));
 		}
 	}
 }

@@ -307,7 +307,8 @@ static void msd_hist(Stream & st, TextView const & v, unsigned b1, std::vector<u
 static void msd_configure() {
 	static std::atomic<uint64_t> seen{0};
 	if (!first_on_device(seen)) return;
-	B3M_CUDA(cudaFuncSetAttribute(k_msd_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, MSD_TILE * 8));
+	B3M_CUDA(cudaFuncSetAttribute(k_msd_scatter<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, MSD_TILE * 8));
+	B3M_CUDA(cudaFuncSetAttribute(k_msd_scatter<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * MSD_TILE * 8));
 	B3M_CUDA(cudaFuncSetAttribute(k_msd_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (MSD_TILE + 2) * 8));
 	B3M_CUDA(cudaFuncSetAttribute(k_msd_finish<true, false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, MSD_FIN_SMEM));
 	B3M_CUDA(cudaFuncSetAttribute(k_msd_finish<false, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, MSD_FIN_SMEM));
@@ -349,11 +350,13 @@ static void msd_scatter_phase(Stream & st, TextView const & v, MsdGeom const & g
 	DevBuf<uint32_t> dbase(st, nkeep);
 	B3M_CUDA(cudaMemcpyAsync(dbase.get(), destbase.data(), nkeep * 4, cudaMemcpyHostToDevice, st.s));
 	MsdP1 A;
-	A.v = v; A.b1 = g.b1; A.d_lo = d_lo; A.nkeep = nkeep; A.t_lo = C.t_lo; A.base = dbase.get(); A.toff = C.toff.get(); A.nparts = nparts;
+	A.v = v; A.b1 = g.b1; A.d_lo = d_lo; A.nkeep = nkeep; A.t_lo = C.t_lo; A.nt = nt; A.base = dbase.get(); A.toff = C.toff.get(); A.nparts = nparts;
 	for (unsigned p = 0; p <= nparts; ++p) A.bnd[p] = bnd[p];
 	for (unsigned p = 0; p < nparts; ++p) A.out[p] = out[p];
 	uint64_t const npos = std::min<uint64_t>((uint64_t)nt * MSD_TILE, v.W - (uint64_t)C.t_lo * MSD_TILE);
-	B3M_LAUNCH_T(st, "msd_scatter", npos / 4 + 4ull * nt * nkeep + 8 * nrec, k_msd_scatter, nt, MSD_THREADS, MSD_TILE * 8, A);
+	// several destinations: the runs cross NVLink, two tiles per CTA double their length
+	if (nparts > 1) B3M_LAUNCH_T(st, "msd_scatter", npos / 4 + 4ull * nt * nkeep + 8 * nrec, k_msd_scatter<2>, (nt + 1) / 2, 2 * MSD_THREADS, 2 * MSD_TILE * 8, A);
+	else B3M_LAUNCH_T(st, "msd_scatter", npos / 4 + 4ull * nt * nkeep + 8 * nrec, k_msd_scatter<1>, nt, MSD_THREADS, MSD_TILE * 8, A);
 	S.radix_passes++; S.radix_bytes += npos / 4 + 4ull * nt * nkeep + 8 * nrec;
 	C.toff.release();
 }
