@@ -278,7 +278,7 @@ k_msd_scatter(MsdP1 A) {
 	#pragma unroll
 	for (int j = 0; j < MSD_ITEMS; ++j) {
 		uint32_t const d = dr[j] - A.d_lo;
-		dr[j] = (dr[j] != 0xffffffffu && d < nkeep) ? ((d << 16) | atomicAdd(&cnt[d], 1u)) : 0xffffffffu;
+		dr[j] = d < nkeep ? ((d << 16) | atomicAdd(&cnt[d], 1u)) : 0xffffffffu; // "no position" (~0) minus d_lo (< 2048) is no bin either
 	}
 	__syncthreads();
 	constexpr int PERMAX = MSD_MAXBINS / THREADS;
