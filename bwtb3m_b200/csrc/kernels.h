@@ -32,7 +32,6 @@ struct CTab { uint32_t c[257]; }; // C[code] passed to kernels by value
 // ---- K1 ---------------------------------------------------------------------------------
 void k1_hist_bytes(Stream & st, const uint8_t * d_in, uint64_t nbytes, uint64_t * d_hist256);
 void k1_map_bytes(Stream & st, const uint8_t * d_in, uint64_t n, const uint8_t * d_lut256, uint8_t * d_out);
-void k1_unpack_pac(Stream & st, const uint8_t * d_pac, uint64_t l, uint8_t * d_out, uint64_t * d_hist256);
 void k1_unpack_compact(Stream & st, const uint8_t * d_words, uint64_t n, unsigned b, bool le_words, uint8_t * d_out, uint64_t * d_hist256);
 // packed copy of n codes < 4; d_out holds n/32 + 3 words, the tail is zero
 void k1_pack2(Stream & st, const uint8_t * d_codes, uint64_t n, uint64_t * d_out);

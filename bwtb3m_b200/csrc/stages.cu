@@ -70,63 +70,6 @@ void k1_map_bytes(Stream & st, const uint8_t * d_in, uint64_t n, const uint8_t *
 }
 
 // pac: 2 bit/symbol, MSB first inside each byte (BWA fa2pac layout).
-// One thread expands 4 pac bytes into 16 one-byte codes (one 128-bit store).
-__global__ void __launch_bounds__(256) k_unpack_pac(const uint8_t * __restrict__ pac, uint64_t l, uint8_t * __restrict__ out,
-                                                    unsigned long long * __restrict__ hist) {
-	__shared__ uint32_t sh[4];
-	if (threadIdx.x < 4) sh[threadIdx.x] = 0;
-	__syncthreads();
-	uint64_t const ngroups = div_up(l, 16);
-	uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-	for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += (uint64_t)gridDim.x * blockDim.x) {
-		uint64_t const first = g * 16;
-		uint32_t const cnt = (l - first) < 16 ? (uint32_t)(l - first) : 16u;
-		uint32_t const nb = (cnt + 3) / 4;
-		uint32_t bytes[4] = {0, 0, 0, 0};
-		if (nb == 4) {
-			uint32_t const w = *reinterpret_cast<const uint32_t *>(pac + g * 4);
-			bytes[0] = w & 255u; bytes[1] = (w >> 8) & 255u; bytes[2] = (w >> 16) & 255u; bytes[3] = w >> 24;
-		} else {
-			for (uint32_t b = 0; b < nb; ++b) bytes[b] = pac[g * 4 + b];
-		}
-		uint32_t w[4];
-		#pragma unroll
-		for (int b = 0; b < 4; ++b) {
-			uint32_t const x = bytes[b];
-			w[b] = ((x >> 6) & 3u) | (((x >> 4) & 3u) << 8) | (((x >> 2) & 3u) << 16) | ((x & 3u) << 24);
-		}
-		if (cnt == 16) {
-			*reinterpret_cast<uint4 *>(out + first) = make_uint4(w[0], w[1], w[2], w[3]);
-			#pragma unroll
-			for (int b = 0; b < 4; ++b) {
-				// count codes 1,2,3 via bit tricks on the four bytes; code 0 = 4 - others
-				uint32_t const lo = w[b] & 0x01010101u, hi = (w[b] >> 1) & 0x01010101u;
-				uint32_t const n3 = __popc(lo & hi), n1 = __popc(lo & ~hi), n2 = __popc(hi & ~lo);
-				c1 += n1; c2 += n2; c3 += n3; c0 += 4 - n1 - n2 - n3;
-			}
-		} else {
-			for (uint32_t k = 0; k < cnt; ++k) {
-				uint32_t const c = (w[k >> 2] >> (8 * (k & 3))) & 3u;
-				out[first + k] = (uint8_t)c;
-				c0 += (c == 0); c1 += (c == 1); c2 += (c == 2); c3 += (c == 3);
-			}
-		}
-	}
-	c0 = __reduce_add_sync(0xffffffffu, c0); c1 = __reduce_add_sync(0xffffffffu, c1);
-	c2 = __reduce_add_sync(0xffffffffu, c2); c3 = __reduce_add_sync(0xffffffffu, c3);
-	if ((threadIdx.x & 31) == 0) { atomicAdd(&sh[0], c0); atomicAdd(&sh[1], c1); atomicAdd(&sh[2], c2); atomicAdd(&sh[3], c3); }
-	__syncthreads();
-	if (threadIdx.x < 4 && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
-}
-
-void k1_unpack_pac(Stream & st, const uint8_t * d_pac, uint64_t l, uint8_t * d_out, uint64_t * d_hist256) {
-	B3M_CUDA(cudaMemsetAsync(d_hist256, 0, 256 * sizeof(uint64_t), st.s));
-	if (!l) return;
-	uint64_t want = div_up(div_up(l, 16), 256 * 8);
-	unsigned grid = (unsigned)(want < (uint64_t)st.sms * 16 ? (want ? want : 1) : (uint64_t)st.sms * 16);
-	B3M_LAUNCH(st, k_unpack_pac, grid, 256, 0, d_pac, l, d_out, (unsigned long long *)d_hist256);
-}
-
 // pac -> the packed text directly: 8 pac bytes, read big-endian, ARE one word of the packed text (32 symbols, first
 // symbol in the top bits); the histogram of the codes comes from popcounts of the word.  The byte codes are not
 // written: the MSD sorter, the key-range sorter and the resolve kernels read the packed text only, and the paths that

@@ -683,7 +683,7 @@ def build_distributed(engine, local_blocks=1, preisarate=0, sasamplingrate=32, i
         raise ValueError("build_distributed needs an Engine created on a torch stream: Engine(device, torch.cuda.Stream().cuda_stream)")
     if strategy in ("auto", "shard"):
         with torch.cuda.stream(torch.cuda.ExternalStream(engine.stream_ptr)) if engine.stream_ptr else _null():
-            if hasattr(engine, "shard_adopt") and os.environ.get("B3M_SHARD_EXCHANGE", "0") != "1":
+            if hasattr(engine, "shard_adopt"):
                 # every rank stores straight into rank 0's buffers (CUDA IPC)
                 res = state.get("direct")
                 key = (engine.info()["n"], sasamplingrate, isasamplingrate, bool(bwtonly))
@@ -694,7 +694,7 @@ def build_distributed(engine, local_blocks=1, preisarate=0, sasamplingrate=32, i
                     res = DirectResults(engine, preisarate, sasamplingrate, isasamplingrate, bwtonly, dist.get_rank(), dist.get_world_size())
                 state["direct"] = res
                 ok = None
-                if hasattr(engine, "xshard_count") and dist.get_world_size() <= 16 and os.environ.get("B3M_SHARD_BINS", "0") != "1":
+                if hasattr(engine, "xshard_count") and dist.get_world_size() <= 16:
                     xr = state.get("xrecs")
                     if xr is not None and xr.n != key[0]:
                         xr.close()
