@@ -67,7 +67,7 @@ EXPORTS = [
     "b3m_engine_blk_merge", "b3m_engine_blk_merge_samples", "b3m_engine_blk_finish",
     "b3m_engine_default_preisarate", "b3m_engine_fetch_bwa",
     "b3m_engine_shard_build", "b3m_engine_shard_finish", "b3m_engine_shard_rows", "b3m_engine_pack_rows", "b3m_engine_unpack_rows",
-    "b3m_engine_shard_adopt", "b3m_engine_xshard_count", "b3m_engine_xshard_scatter", "b3m_engine_xshard_finish", "b3m_dev_alloc", "b3m_dev_free", "b3m_ipc_export", "b3m_ipc_open", "b3m_ipc_close", "b3m_dev_copy", "b3m_engine_pack_bwa",
+    "b3m_engine_shard_adopt", "b3m_engine_xshard_count", "b3m_engine_xshard_scatter", "b3m_engine_xshard_finish", "b3m_engine_xshard_stream_sa", "b3m_engine_xshard_sa_delivered", "b3m_dev_alloc", "b3m_dev_free", "b3m_ipc_export", "b3m_ipc_open", "b3m_ipc_close", "b3m_dev_copy", "b3m_engine_pack_bwa",
     "b3m_multi_create", "b3m_multi_destroy", "b3m_multi_last_error", "b3m_multi_load_host", "b3m_multi_build", "b3m_multi_engine", "b3m_multi_stats",
 ]
 
@@ -109,6 +109,8 @@ def lib():
     L.b3m_engine_xshard_count.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(BuildParams), vp, C.POINTER(C.c_uint32)]
     L.b3m_engine_xshard_scatter.argtypes = [vp, vp, vp, vp]
     L.b3m_engine_xshard_finish.argtypes = [vp, vp, vp, vp, vp, vp, vp, u64p]
+    L.b3m_engine_xshard_stream_sa.argtypes = [vp, vp, vp]
+    L.b3m_engine_xshard_sa_delivered.argtypes = [vp, C.POINTER(C.c_int)]
     L.b3m_dev_alloc.argtypes = [C.c_int, u64, C.POINTER(vp), C.c_char_p, C.c_size_t]
     L.b3m_dev_free.argtypes = [C.c_int, vp, C.c_char_p, C.c_size_t]
     L.b3m_ipc_export.argtypes = [C.c_int, vp, C.c_char_p, C.c_char_p, C.c_size_t]

@@ -452,6 +452,11 @@ void Engine::xs_scatter(const uint64_t * h_alltot, void * const * d_recs, const 
 	k2_xshard_scatter(st, T, T.has_term ? 0 : 1, xs, (const unsigned long long *)h_alltot, (unsigned long long * const *)d_recs, caps, &sortstats);
 }
 
+void Engine::xs_stream_sa(void * d_sa_local, uint64_t * host_sa) {
+	xs_sa_local = (unsigned long long *)d_sa_local;
+	xs_sa_host = (unsigned long long *)host_sa;
+}
+
 void Engine::xs_finish(void * d_recs_own, void * d_bwt, void * d_prerank, void * d_sa, void * d_isa, void * d_special, uint64_t * unresolved) {
 	B3M_CUDA(cudaSetDevice(device));
 	B3M_REQUIRE(loaded && xs.nparts && xs_pt, "xshard_count was not called");
@@ -465,7 +470,13 @@ void Engine::xs_finish(void * d_recs_own, void * d_bwt, void * d_prerank, void *
 		fo.sa_s = (unsigned long long *)d_sa; fo.salog = ceil_log2_u64(p.sasamplingrate);
 		fo.isa_s = (unsigned long long *)d_isa; fo.isalog = ceil_log2_u64(p.isasamplingrate);
 	}
-	*unresolved = k2_xshard_finish(st, T, T.has_term ? 0 : 1, xs, (unsigned long long *)d_recs_own, fo, &sortstats);
+	StreamOut so;
+	bool const stream = !p.bwtonly && xs_sa_local && xs_sa_host;
+	if (stream) { fo.sa_s2 = xs_sa_local; so.host_sa = xs_sa_host; so.nsa = nsa; }
+	xs_sa_local = nullptr; xs_sa_host = nullptr; // one build
+	*unresolved = k2_xshard_finish(st, T, T.has_term ? 0 : 1, xs, (unsigned long long *)d_recs_own, fo, &sortstats, stream ? &so : nullptr);
+	if (stream) B3M_CUDA(cudaStreamSynchronize(st.copy)); // this rank's samples are in the host buffer (all but sample 0 of a terminated text)
+	xs_sa_delivered = stream && so.delivered;
 	if (xs.part == 0 && T.has_term) {
 		// rank 0 is the terminator suffix (text position ntext): written explicitly, the buffers are not zeroed
 		B3M_CUDA(cudaMemcpyAsync(d_bwt, lastcode.get(), 1, cudaMemcpyDeviceToDevice, st.s));
@@ -923,6 +934,12 @@ int b3m_engine_xshard_count(b3m_engine * h, uint32_t part, uint32_t nparts, cons
 }
 int b3m_engine_xshard_scatter(b3m_engine * h, const uint64_t * all_totals, void * const * d_recs, const uint64_t * caps) {
 	B3M_GUARD(h, h->e->xs_scatter(all_totals, d_recs, caps));
+}
+int b3m_engine_xshard_stream_sa(b3m_engine * h, void * d_sa_local, uint64_t * host_sa) {
+	B3M_GUARD(h, h->e->xs_stream_sa(d_sa_local, host_sa));
+}
+int b3m_engine_xshard_sa_delivered(b3m_engine * h, int * delivered) {
+	B3M_GUARD(h, { if (!delivered) throw b3m::Error("null argument"); *delivered = h->e->xs_sa_delivered ? 1 : 0; });
 }
 int b3m_engine_xshard_finish(b3m_engine * h, void * d_recs_own, void * d_bwt, void * d_prerank, void * d_sa, void * d_isa, void * d_special, uint64_t * unresolved) {
 	B3M_GUARD(h, h->e->xs_finish(d_recs_own, d_bwt, d_prerank, d_sa, d_isa, d_special, unresolved));

@@ -125,6 +125,10 @@ struct Engine {
 	void xs_scatter(const uint64_t * h_alltot, void * const * d_recs, const uint64_t * caps);
 	void xs_finish(void * d_recs_own, void * d_bwt, void * d_prerank, void * d_sa, void * d_isa, void * d_special, uint64_t * unresolved);
 	PhaseTimer * xs_pt = nullptr;
+	unsigned long long * xs_sa_local = nullptr; // armed by xs_stream_sa for the next xs_finish: this GPU's copy of the sampled SA ..
+	unsigned long long * xs_sa_host = nullptr;  // .. and the page-locked host buffer its part of the samples is sent to while the finish runs
+	bool xs_sa_delivered = false;               // the last xs_finish did send its samples (the path needs 64 sub-buckets or more)
+	void xs_stream_sa(void * d_sa_local, uint64_t * host_sa);
 	void pack_rows(const void * d_rows, uint64_t nrows, void * d_packed, bool unpack);
 	void kr_finish(const void * d_bwt, const void * d_prerank, const void * d_sa, const void * d_isa, const void * d_special, uint32_t nparts, bool adopt);
 	// K8 / output side

@@ -62,6 +62,7 @@ struct FusedOut {
 	uint32_t * prerank = nullptr;  // prerank[p >> prelog] = rank of position p, p multiple of 2^prelog
 	uint32_t prelog = 0;
 	unsigned long long * sa_s = nullptr;  // sa_s[r >> salog] = position, r multiple of 2^salog (nullptr: bwtonly)
+	unsigned long long * sa_s2 = nullptr; // optional second copy (a sharded build: sa_s is another GPU's memory, sa_s2 this GPU's, from where the samples are sent to the host)
 	uint32_t salog = 0;
 	unsigned long long * isa_s = nullptr; // isa_s[p >> isalog] = rank
 	uint32_t isalog = 0;
@@ -128,7 +129,8 @@ bool k2_xshard_count(Stream & st, DevText const & T, int circular, uint32_t part
 void k2_xshard_scatter(Stream & st, DevText const & T, int circular, XShard & X, const unsigned long long * h_alltot, unsigned long long * const * recs,
                        const uint64_t * cap, SortStats * stats);
 // after every part has scattered: level 2 + finish on this part's bins; returns the number of suffixes left unresolved
-uint64_t k2_xshard_finish(Stream & st, DevText const & T, int circular, XShard & X, unsigned long long * recs_own, FusedOut const & fo0, SortStats * stats);
+uint64_t k2_xshard_finish(Stream & st, DevText const & T, int circular, XShard & X, unsigned long long * recs_own, FusedOut const & fo0, SortStats * stats,
+                          StreamOut * so = nullptr);
 
 // ---- K4 / K7 ----------------------------------------------------------------------------
 // Rank dictionary, 2-bit flavour: 64-byte lines = 4 x uint32 cumulative counts + 48 bytes

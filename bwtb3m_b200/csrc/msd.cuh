@@ -782,7 +782,10 @@ k_msd_finish(const __grid_constant__ MsdFin A) {
 		if (stage_sa) {
 			uint32_t const r_end = rshift + m;
 			uint32_t const ns = r_first < r_end ? ((r_end - 1u - r_first) >> A.fo.salog) + 1u : 0u;
-			for (uint32_t x = threadIdx.x; x < ns; x += THREADS) A.fo.sa_s[(r_first >> A.fo.salog) + x] = s_sa[x];
+			for (uint32_t x = threadIdx.x; x < ns; x += THREADS) {
+				A.fo.sa_s[(r_first >> A.fo.salog) + x] = s_sa[x];
+				if (A.fo.sa_s2) A.fo.sa_s2[(r_first >> A.fo.salog) + x] = s_sa[x];
+			}
 		}
 		uint8_t * const out = A.fo.bwt + A.fo.shift + o0;
 		// head bytes up to a 4-byte boundary, words, tail bytes

@@ -471,7 +471,9 @@ static bool msd_finish_phase(Stream & st, TextView const & v, int lin, MsdGeom c
 		for (int q = 0; q < MSD_CSLOTS; ++q) { for (int c = 0; c < 3; ++c) hc[c] += hcs[4 * q + c]; hc[3] |= hcs[4 * q + 3]; }
 	};
 	// early delivery (StreamOut): rows below a finished range of sub-buckets are final
-	bool const stream_sa = so && so->host_sa && fo.sa_s && st.copy && nsb >= 64 && whole;
+	// (a key range of a sharded build: only with a local copy of the samples, and through the kernel's staged path)
+	bool const stream_sa = so && so->host_sa && fo.sa_s && st.copy && nsb >= 64 && (whole || (fo.sa_s2 && fo.salog >= 5 && fo.salog < 32));
+	const unsigned long long * const sa_src = fo.sa_s2 ? fo.sa_s2 : fo.sa_s;
 	bool stream_bwa = so && so->host_bwa && so->d_bwa && fo.has_term && st.copy && nsb >= 64 && whole;
 	uint64_t primary = 0;
 	if (stream_bwa) {
@@ -504,7 +506,7 @@ static bool msd_finish_phase(Stream & st, TextView const & v, int lin, MsdGeom c
 		uint64_t const cm = nchunks > 1 ? (c + 1 == nchunks ? m : rows[c + 1]) - rows[c] : m;
 		launch_fin(false, "msd_finish", cm * fbytes_per + cm / 4, s_hi - s_lo);
 		if (stream_sa || stream_bwa) {
-			uint64_t const rows_lo = c ? rows[c] + fo.shift : 0, rows_hi = (c + 1 == nchunks) ? W + fo.shift : rows[c + 1] + fo.shift;
+			uint64_t const rows_lo = c ? rows[c] + fo.shift : (whole ? 0 : fo.shift), rows_hi = (c + 1 == nchunks) ? m + fo.shift : rows[c + 1] + fo.shift;
 			cudaEvent_t ev;
 			B3M_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
 			B3M_CUDA(cudaEventRecord(ev, st.s));
@@ -512,7 +514,7 @@ static bool msd_finish_phase(Stream & st, TextView const & v, int lin, MsdGeom c
 			B3M_CUDA(cudaEventDestroy(ev));
 			if (stream_sa) {
 				uint64_t const k_lo = div_up(rows_lo, 1ull << fo.salog), k_hi = std::min<uint64_t>(div_up(rows_hi, 1ull << fo.salog), so->nsa);
-				if (k_hi > k_lo) B3M_CUDA(cudaMemcpyAsync(so->host_sa + k_lo, fo.sa_s + k_lo, (k_hi - k_lo) * 8, cudaMemcpyDeviceToHost, st.copy));
+				if (k_hi > k_lo) B3M_CUDA(cudaMemcpyAsync(so->host_sa + k_lo, sa_src + k_lo, (k_hi - k_lo) * 8, cudaMemcpyDeviceToHost, st.copy));
 			}
 			if (stream_bwa) {
 				// word w reads the rows 16w .. 16w+16 (one further behind the primary)
@@ -863,7 +865,8 @@ void k2_xshard_scatter(Stream & st, DevText const & T, int circular, XShard & X,
 	if (stats) { stats->radix_passes += S.radix_passes; stats->radix_bytes += S.radix_bytes; stats->other_bytes += S.other_bytes; }
 }
 
-uint64_t k2_xshard_finish(Stream & st, DevText const & T, int circular, XShard & X, unsigned long long * recs_own, FusedOut const & fo0, SortStats * stats) {
+uint64_t k2_xshard_finish(Stream & st, DevText const & T, int circular, XShard & X, unsigned long long * recs_own, FusedOut const & fo0, SortStats * stats,
+                          StreamOut * so) {
 	B3M_REQUIRE(X.nparts && !X.bnd.empty(), "xshard_scatter was not called");
 	MsdGeom g; g.b1 = X.b1; g.b2 = X.b2;
 	TextView v{T.codes, T.packed, T.ntext, 0, T.ntext, circular, 0, T.has_term};
@@ -874,7 +877,7 @@ uint64_t k2_xshard_finish(Stream & st, DevText const & T, int circular, XShard &
 	S.rounds = 1; S.active_sum = X.records;
 	uint64_t unresolved = 0, hstart = 0;
 	if (nkeep && X.records) {
-		bool const ok = msd_finish_phase(st, v, !circular, g, d_lo, nkeep, X.total.data() + d_lo, recs_own, false, fo, nullptr, nullptr, nullptr, S, unresolved, hstart);
+		bool const ok = msd_finish_phase(st, v, !circular, g, d_lo, nkeep, X.total.data() + d_lo, recs_own, false, fo, so, nullptr, nullptr, S, unresolved, hstart);
 		B3M_REQUIRE(ok, "internal: xshard finish does not apply");
 	}
 	if (stats) {

@@ -158,6 +158,16 @@ class Engine:
         ca = (C.c_uint64 * n)(*caps)
         self._check(self._lib.b3m_engine_xshard_scatter(self._h, C.c_void_p(t.ctypes.data), pa, ca))
 
+    def xshard_stream_sa(self, d_sa_local_ptr, host_sa_ptr):
+        """Arms the next xshard_finish: this rank's SA samples also go to `d_sa_local_ptr` (this GPU) and from there
+        into the page-locked host buffer `host_sa_ptr` while the finish kernel runs (b3m_engine_xshard_stream_sa)."""
+        self._check(self._lib.b3m_engine_xshard_stream_sa(self._h, C.c_void_p(d_sa_local_ptr), C.c_void_p(host_sa_ptr)))
+
+    def xshard_sa_delivered(self):
+        d = C.c_int(0)
+        self._check(self._lib.b3m_engine_xshard_sa_delivered(self._h, C.byref(d)))
+        return bool(d.value)
+
     def xshard_finish(self, recs_own_ptr, bwt_ptr, prerank_ptr, sa_ptr, isa_ptr, special_ptr):
         """Step 3 (after every part has scattered): sorts this part's key range, outputs at their global places; returns the
         number of suffixes left unresolved."""

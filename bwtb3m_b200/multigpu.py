@@ -480,15 +480,25 @@ def build_xsharded(engine, results, xrecs, sasamplingrate=32, isasamplingrate=26
     if world > 1:
         dist.all_reduce(fence, op=dist.ReduceOp.SUM)  # every rank's records have landed before anyone sorts
     mark("fence")
+    # end to end: this rank's SA samples leave for the host while its finish kernel runs (fetch_distributed skips them then)
+    host_sa = getattr(results, "stream_sa_host", 0)
+    streamed = bool(host_sa) and not bwtonly and sasamplingrate >= 32 and hasattr(engine, "xshard_stream_sa")
+    if streamed:
+        if getattr(results, "sa_local", None) is None:
+            results.sa_local = results.mem.alloc(results.sizes["sa"])
+        engine.xshard_stream_sa(results.sa_local, host_sa)
+    results.sa_streamed = False
     unres = engine.xshard_finish(xrecs.own, *results.ptrs())
     mark("local+finish")
+    missed = 1 if (streamed and not engine.xshard_sa_delivered()) else 0  # a key range of too few sub-buckets does not stream
     if world > 1:
-        flag = torch.tensor([unres], dtype=torch.int64, device=device)
+        flag = torch.tensor([unres, missed], dtype=torch.int64, device=device)
         dist.all_reduce(flag, op=dist.ReduceOp.SUM)
-        unres = int(flag.item())
+        unres, missed = (int(x) for x in flag.tolist())
     mark("vote")
     if unres != 0:
         return False
+    results.sa_streamed = streamed and missed == 0
     if rank == 0:
         engine.shard_adopt(world, *results.ptrs())
     return True
@@ -640,8 +650,11 @@ def fetch_distributed(engine, state, host_words_ptr, host_sa_ptr, host_preisa_pt
     mark("fence")
     sent = 0
     todo = []
+    sa_there = bool(getattr(res, "sa_streamed", False)) and host_sa_ptr and host_sa_ptr == getattr(res, "stream_sa_host", 0)
+    if sa_there and rank == 0 and nsa:
+        res.mem.copy(host_sa_ptr, res.p["sa"], 8, stream_ptr)  # sample 0 of a terminated text is written by rank 0's engine, not by a finish kernel
     for key, count, width, hptr in (("bwa", nwords, 4, host_words_ptr), ("sa", nsa, 8, host_sa_ptr)):
-        if not count or not hptr:
+        if not count or not hptr or (key == "sa" and sa_there):
             continue
         lo, hi = rank_slice(count, rank, world)
         if hi <= lo:
@@ -702,6 +715,7 @@ def build_distributed(engine, local_blocks=1, preisarate=0, sasamplingrate=32, i
                     if xr is None:
                         xr = XRecs(engine, dist.get_rank(), dist.get_world_size())
                     state["xrecs"] = xr
+                    res.stream_sa_host = state.get("stream_sa_host", 0)  # set by the caller between builds (a SharedHost pointer)
                     ok = build_xsharded(engine, res, xr, sasamplingrate, isasamplingrate, bwtonly)
                 if ok is None:
                     ok = build_sharded_direct(engine, res, sasamplingrate, isasamplingrate, bwtonly)

@@ -312,6 +312,15 @@ int b3m_engine_shard_finish(b3m_engine * e, const void * d_bwt, const void * d_p
  * b3m_engine_shard_rows / _shard_finish / _shard_adopt apply afterwards.  Build parameters are those of step 1. */
 int b3m_engine_xshard_count(b3m_engine * e, uint32_t part, uint32_t nparts, const b3m_build_params * p, void * d_totals, uint32_t * nbins);
 int b3m_engine_xshard_scatter(b3m_engine * e, const uint64_t * all_totals, void * const * d_recs, const uint64_t * caps);
+/* Optional, before b3m_engine_xshard_finish: the samples of the rank-sampled SA that this rank produces are also
+ * stored into d_sa_local (this GPU's memory, ceil(n/sasamplingrate) uint64 like d_sa) and copied from there into the
+ * page-locked host buffer host_sa -- at their global places, chunk by chunk while the finish kernel still runs, over
+ * THIS GPU's PCIe link.  When the call returns they are in host memory (sample 0 of a terminated text excepted: the
+ * owner of d_sa holds it).  Applies to the next b3m_engine_xshard_finish only; needs sasamplingrate >= 32. */
+int b3m_engine_xshard_stream_sa(b3m_engine * e, void * d_sa_local, uint64_t * host_sa);
+/* after b3m_engine_xshard_finish: 1 if this rank's samples were sent that way (key ranges of fewer than 64 sub-buckets
+ * are not: the caller then copies the samples out of d_sa as usual) */
+int b3m_engine_xshard_sa_delivered(b3m_engine * e, int * delivered);
 int b3m_engine_xshard_finish(b3m_engine * e, void * d_recs_own, void * d_bwt, void * d_prerank, void * d_sa, void * d_isa, void * d_special,
                              uint64_t * unresolved);
 

@@ -52,6 +52,13 @@ for it in range(2):
     with torch.cuda.stream(stream):
         if a.io:
             multigpu.load_distributed(eng, host, itype, io_state)
+            if shared is not None and isinstance(drv, dict):
+                drv["stream_sa_host"] = shared["sa"].ptr()  # second build: the SA samples leave during the finish kernels
+                torch.cuda.synchronize()
+                if rank == 0:
+                    shared["sa"].t.fill_(0xEE)  # what the first round's fetch left must not pass for this round's delivery
+                    shared["bwa"].t.fill_(0xEE)
+                dist.barrier()
         drv, res = multigpu.build_distributed(eng, local_blocks=a.local_blocks, sasamplingrate=32, isasamplingrate=1024, driver=drv, strategy=a.strategy)
         if a.io:
             i0 = eng.info()
