@@ -61,7 +61,7 @@ EXPORTS = [
     "b3m_engine_load_device", "b3m_engine_build", "b3m_engine_info", "b3m_engine_fetch",
     "b3m_engine_device_results", "b3m_engine_lf_bench", "b3m_engine_sync", "b3m_engine_set_profile",
     "b3m_engine_kernel_times", "b3m_engine_write_bwt", "b3m_engine_fetch_runs", "b3m_engine_ssa_from_bwt",
-    "b3m_bwt_length", "b3m_bwt_decode", "b3m_bwt_encode_host",
+    "b3m_bwt_length", "b3m_bwt_decode", "b3m_bwt_encode_host", "b3m_bwt_block_sym_histograms", "b3m_bwt_rank",
     "b3m_compact_write", "b3m_compact_info", "b3m_compact_read",
     "b3m_engine_blk_begin", "b3m_engine_blk_build_range", "b3m_engine_blk_chains", "b3m_engine_blk_zranks", "b3m_engine_blk_gap",
     "b3m_engine_blk_merge", "b3m_engine_blk_merge_samples", "b3m_engine_blk_finish",
@@ -134,6 +134,8 @@ def lib():
     L.b3m_bwt_length.argtypes = [C.c_char_p, u64p, C.c_char_p, C.c_size_t]
     L.b3m_bwt_decode.argtypes = [C.c_char_p, vp, u64, u64, C.c_char_p, C.c_size_t]
     L.b3m_bwt_encode_host.argtypes = [C.c_char_p, vp, u64, C.c_char_p, C.c_size_t]
+    L.b3m_bwt_block_sym_histograms.argtypes = [C.c_char_p, C.c_char_p, C.c_int64, C.c_int64, u64, u64p, C.c_char_p, C.c_size_t]
+    L.b3m_bwt_rank.argtypes = [C.c_char_p, C.c_char_p, C.c_int64, C.c_int64, C.c_int64, u64, u64p, C.c_char_p, C.c_size_t]
     L.b3m_compact_write.argtypes = [C.c_char_p, C.c_uint, vp, u64, C.c_char_p, C.c_size_t]
     L.b3m_compact_info.argtypes = [C.c_char_p, C.POINTER(C.c_uint), u64p, C.c_char_p, C.c_size_t]
     L.b3m_compact_read.argtypes = [C.c_char_p, vp, u64, C.c_char_p, C.c_size_t]

@@ -460,6 +460,65 @@ std::vector<uint8_t> RlDecoder::decodeAll(std::vector<std::string> const & fns, 
 	return out;
 }
 
+uint64_t RlDecoder::getBlockSymHistograms(std::string const & bwtfn, std::string const & outfn, int64_t minsym, int64_t maxsym, uint64_t numthreads) {
+	if (maxsym < minsym || minsym < 0 || maxsym > 255) throw IoError("getBlockSymHistograms: symbol range must lie in 0..255");
+	RlFile const F(bwtfn);
+	uint64_t const nb = F.h.nblocks, ns = (uint64_t)(maxsym - minsym + 1);
+	std::vector<uint64_t> H(nb * ns, 0); // first the counts of the block itself
+	uint64_t const nt = std::max<uint64_t>(1, std::min<uint64_t>(numthreads ? numthreads : 1, nb));
+	std::vector<std::thread> th;
+	std::vector<std::string> errs(nt);
+	for (uint64_t t = 0; t < nt; ++t) th.emplace_back([&, t]() {
+		try {
+			File f(F.fn, "rb");
+			std::vector<uint8_t> buf; std::vector<std::pair<uint8_t, uint64_t>> runs;
+			for (uint64_t b = nb * t / nt; b < nb * (t + 1) / nt; ++b) {
+				F.decode_block(f, b, buf, runs);
+				for (auto const & r : runs) {
+					if ((int64_t)r.first < minsym || (int64_t)r.first > maxsym) throw IoError("getBlockSymHistograms: symbol outside [minsym,maxsym] in " + F.fn);
+					H[b * ns + (uint64_t)(r.first - minsym)] += r.second;
+				}
+			}
+		} catch (std::exception const & ex) { errs[t] = ex.what(); }
+	});
+	for (auto & x : th) x.join();
+	for (auto const & e : errs) if (!e.empty()) throw IoError(e);
+	// exclusive prefix sums down the blocks, written big-endian
+	std::vector<uint64_t> run(ns, 0);
+	std::vector<uint8_t> o;
+	o.reserve(8 * nb * ns);
+	for (uint64_t b = 0; b < nb; ++b)
+		for (uint64_t c = 0; c < ns; ++c) { put_be64(o, run[c]); run[c] += H[b * ns + c]; }
+	write_file(outfn, o.data(), o.size());
+	return nb;
+}
+
+uint64_t RlDecoder::rankm(std::string const & bwtfn, std::string const & sparserankfn, int64_t minsym, int64_t maxsym, int64_t sym, uint64_t i) {
+	if (sym < minsym || sym > maxsym) throw IoError("rankm: symbol outside [minsym,maxsym]");
+	RlFile const F(bwtfn);
+	if (i > F.h.n) throw IoError("rankm: position behind the end of the sequence");
+	if (F.h.nblocks == 0) return 0;
+	uint64_t const ns = (uint64_t)(maxsym - minsym + 1);
+	uint64_t b = (uint64_t)(std::upper_bound(F.soff.begin(), F.soff.end(), i) - F.soff.begin());
+	b = b ? b - 1 : 0;
+	File sr(sparserankfn, "rb");
+	sr.seek(8 * (b * ns + (uint64_t)(sym - minsym)));
+	uint8_t v8[8];
+	sr.read(v8, 8);
+	uint64_t r = get_be64(v8);
+	File f(F.fn, "rb");
+	std::vector<uint8_t> buf; std::vector<std::pair<uint8_t, uint64_t>> runs;
+	F.decode_block(f, b, buf, runs);
+	uint64_t left = i - F.soff[b];
+	for (auto const & q : runs) {
+		if (!left) break;
+		uint64_t const use = std::min<uint64_t>(left, q.second);
+		if ((int64_t)q.first == sym) r += use;
+		left -= use;
+	}
+	return r;
+}
+
 // ---- compactstream container [layout unpinned] ---------------------------------------------
 static void put_le64(std::vector<uint8_t> & o, uint64_t v) { for (int i = 0; i < 8; ++i) o.push_back((uint8_t)(v >> (8 * i))); }
 static uint64_t get_le64(const uint8_t * p) { uint64_t v = 0; for (int i = 7; i >= 0; --i) v = (v << 8) | p[i]; return v; }

@@ -106,6 +106,14 @@ public:
 	static uint64_t getLength(std::string const & file, uint64_t numthreads = 1) { return getLength(std::vector<std::string>(1, file), numthreads); }
 	// whole sequence into memory, blocks decoded by numthreads threads
 	static std::vector<uint8_t> decodeAll(std::vector<std::string> const & files, uint64_t numthreads);
+	// RLDecoder::getBlockSymHistograms(bwt, out, tmp, minsym, maxsym, numthreads, log)
+	// (/root/reference/src/bwtdecodeblock.cpp:216-223,356-365): for every block of the run-length container the number of
+	// occurrences of each symbol minsym..maxsym in the blocks BEFORE it, (maxsym - minsym + 1) big-endian uint64 per block
+	// -- the `.sparserank` file that SparseRank::rankm seeks into.  Returns the number of blocks.
+	static uint64_t getBlockSymHistograms(std::string const & bwtfn, std::string const & outfn, int64_t minsym, int64_t maxsym, uint64_t numthreads);
+	// rank_sym(L, i) = occurrences of sym in L[0..i): one seek into the .sparserank file plus the runs of one block
+	// (what SparseRank::rankm does, /root/reference/src/bwtdecodeblock.cpp:210-242)
+	static uint64_t rankm(std::string const & bwtfn, std::string const & sparserankfn, int64_t minsym, int64_t maxsym, int64_t sym, uint64_t i);
 private:
 	struct Impl;
 	std::unique_ptr<Impl> impl;

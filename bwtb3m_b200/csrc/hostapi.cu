@@ -362,6 +362,26 @@ int b3m_to_bwa(const char * inbwt, const char * outbwt, const char * outsa, char
 	catch (...) { set_err(err, errlen, "unknown error"); return 3; }
 }
 
+int b3m_bwt_block_sym_histograms(const char * bwtfn, const char * outfn, int64_t minsym, int64_t maxsym, uint64_t numthreads, uint64_t * nblocks,
+                                 char * err, size_t errlen) {
+	try {
+		if (!bwtfn || !outfn) throw Error("null argument");
+		uint64_t const nb = RlDecoder::getBlockSymHistograms(bwtfn, outfn, minsym, maxsym, numthreads);
+		if (nblocks) *nblocks = nb;
+		return 0;
+	} catch (std::exception const & ex) { set_err(err, errlen, ex.what()); return 2; }
+	catch (...) { set_err(err, errlen, "unknown error"); return 3; }
+}
+int b3m_bwt_rank(const char * bwtfn, const char * sparserankfn, int64_t minsym, int64_t maxsym, int64_t sym, uint64_t i, uint64_t * rank,
+                 char * err, size_t errlen) {
+	try {
+		if (!bwtfn || !sparserankfn || !rank) throw Error("null argument");
+		*rank = RlDecoder::rankm(bwtfn, sparserankfn, minsym, maxsym, sym, i);
+		return 0;
+	} catch (std::exception const & ex) { set_err(err, errlen, ex.what()); return 2; }
+	catch (...) { set_err(err, errlen, "unknown error"); return 3; }
+}
+
 // reader entry points for bindings that do not want to link C++: decode a .bwt into memory
 int b3m_bwt_length(const char * bwtfn, uint64_t * n, char * err, size_t errlen) {
 	try {

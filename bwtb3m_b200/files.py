@@ -80,6 +80,25 @@ def write_bwt_host(bwtfn, syms):
         raise B3MError(err.value.decode(errors="replace"))
 
 
+def block_sym_histograms(bwtfn, outfn, minsym, maxsym, numthreads=0):
+    """Writes the `.sparserank` file of a .bwt (RLDecoder::getBlockSymHistograms, bwtdecodeblock.cpp:356-365); returns
+    the number of blocks."""
+    nb = C.c_uint64(0)
+    err = C.create_string_buffer(2048)
+    if lib().b3m_bwt_block_sym_histograms(_b(bwtfn), _b(outfn), minsym, maxsym, numthreads or (os.cpu_count() or 1), C.byref(nb), err, len(err)) != 0:
+        raise B3MError(err.value.decode(errors="replace"))
+    return int(nb.value)
+
+
+def bwt_rank(bwtfn, sparserankfn, minsym, maxsym, sym, i):
+    """rank_sym(L, i) from the .bwt and its .sparserank file (SparseRank::rankm, bwtdecodeblock.cpp:210-242)."""
+    r = C.c_uint64(0)
+    err = C.create_string_buffer(2048)
+    if lib().b3m_bwt_rank(_b(bwtfn), _b(sparserankfn), minsym, maxsym, sym, i, C.byref(r), err, len(err)) != 0:
+        raise B3MError(err.value.decode(errors="replace"))
+    return int(r.value)
+
+
 def write_compact(fn, syms, bits):
     """Compact container for inputtype=compactstream (CompactArrayWriterFile, fagzToCompact4.cpp:105,232,265)."""
     a = np.ascontiguousarray(syms, dtype=np.uint8)

@@ -118,6 +118,14 @@ int b3m_bwt_decode(const char * bwtfn, uint8_t * out, uint64_t cap, uint64_t num
 /* Host writer of the same container from a symbol array (replaces RLEncoderStd::encode + flush,
  * /root/reference/src/lcpbit.cpp:3677-3681); a tool for tests and converters -- the build path
  * b3m_compute_bwt encodes on the device and never calls it. */
+/* RLDecoder::getBlockSymHistograms (/root/reference/src/bwtdecodeblock.cpp:356-365): writes the `.sparserank` file of a
+ * .bwt -- per block of the container the occurrences of the symbols minsym..maxsym BEFORE the block, big-endian uint64
+ * -- and b3m_bwt_rank answers rank_sym(L, i) from it with one seek and the runs of one block
+ * (SparseRank::rankm, /root/reference/src/bwtdecodeblock.cpp:210-242).  Host only. */
+int b3m_bwt_block_sym_histograms(const char * bwtfn, const char * outfn, int64_t minsym, int64_t maxsym, uint64_t numthreads, uint64_t * nblocks,
+                                 char * err, size_t errlen);
+int b3m_bwt_rank(const char * bwtfn, const char * sparserankfn, int64_t minsym, int64_t maxsym, int64_t sym, uint64_t i, uint64_t * rank,
+                 char * err, size_t errlen);
 int b3m_bwt_encode_host(const char * bwtfn, const uint8_t * syms, uint64_t n, char * err, size_t errlen);
 
 /* The compactstream container (`inputtype=compactstream`) for bindings that cannot link C++: replaces

@@ -73,6 +73,33 @@ def test_rl_container_roundtrip(tmp_path, kind):
     assert out2 == s.tobytes() * 2
 
 
+def test_block_sym_histograms_and_rank(tmp_path):
+    """getBlockSymHistograms / SparseRank::rankm of the reference's random-access consumer
+    (/root/reference/src/bwtdecodeblock.cpp:210-242,356-365): the `.sparserank` file holds, per block of the container,
+    the occurrences of every symbol before the block (big-endian uint64), and rank queries from it equal a prefix count."""
+    from bwtb3m_b200 import files
+    rng = np.random.default_rng(12)
+    # runs of uneven length over symbols 1..4 plus one 0, long enough for several blocks of 4096 runs
+    lens = rng.integers(1, 9, size=30_000)
+    syms = rng.integers(1, 5, size=lens.size).astype(np.uint8)
+    L = np.repeat(syms, lens)
+    L[L.size // 3] = 0
+    fn = str(tmp_path / "x.bwt")
+    files.write_bwt_host(fn, L)
+    nb = files.block_sym_histograms(fn, fn + ".sparserank", 0, 4, numthreads=3)
+    raw = np.fromfile(fn + ".sparserank", dtype=">u8").reshape(nb, 5)
+    assert nb >= 2 and np.all(raw[0] == 0) and np.all(np.diff(raw.astype(np.int64), axis=0) >= 0)
+    assert raw[-1].sum() < L.size  # counts BEFORE the last block
+    cum = np.zeros((5, L.size + 1), dtype=np.int64)
+    for c in range(5):
+        cum[c, 1:] = np.cumsum(L == c)
+    for i in [0, 1, 2, L.size // 3, L.size // 3 + 1, L.size - 1, L.size] + [int(x) for x in rng.integers(0, L.size, size=40)]:
+        for c in range(5):
+            assert files.bwt_rank(fn, fn + ".sparserank", 0, 4, c, i) == cum[c, i], (c, i)
+    with pytest.raises(Exception):
+        files.block_sym_histograms(fn, fn + ".bad", 1, 4)  # symbol 0 occurs: outside the stated range
+
+
 def test_rl_container_rejects_garbage(tmp_path):
     from bwtb3m_b200 import files
     from bwtb3m_b200.engine import B3MError
