@@ -10,6 +10,7 @@
 #include <unistd.h>
 #include <algorithm>
 #include <thread>
+#include <array>
 #include <memory>
 
 using namespace b3m;
@@ -317,11 +318,27 @@ int b3m_to_bwa(const char * inbwt, const char * outbwt, const char * outsa, char
 		uint64_t sarate = 0; std::vector<uint64_t> sa;
 		read_sampled(safn, &sarate, &sa);
 		uint64_t const seq_len = n - 1;
+		// symbol counts and the terminator row, one slice of the BWT per thread
 		uint64_t primary = ~0ull, cnt[5] = {0, 0, 0, 0, 0};
-		for (uint64_t i = 0; i < n; ++i) {
-			if (L[i] > 4) throw Error("bwtb3mtobwa needs a pacterm BWT (symbols 0..4)");
-			cnt[L[i]]++;
-			if (L[i] == 0) primary = i;
+		{
+			std::vector<std::array<uint64_t, 8>> part(nthreads); // cnt[0..4], position of a terminator, bad symbol seen
+			std::vector<std::thread> th;
+			for (unsigned t = 0; t < nthreads; ++t) th.emplace_back([&, t]() {
+				std::array<uint64_t, 8> a{}; a[5] = ~0ull;
+				uint64_t c[256] = {0};
+				uint64_t const i0 = n * t / nthreads, i1 = n * (t + 1) / nthreads;
+				for (uint64_t i = i0; i < i1; ++i) c[L[i]]++;
+				for (int s = 0; s < 5; ++s) a[s] = c[s];
+				for (int s = 5; s < 256; ++s) if (c[s]) a[6] = 1;
+				if (c[0]) for (uint64_t i = i0; i < i1; ++i) if (L[i] == 0) a[5] = i; // the last one, as a scan would leave it
+				part[t] = a;
+			});
+			for (auto & x : th) x.join();
+			for (auto const & a : part) {
+				if (a[6]) throw Error("bwtb3mtobwa needs a pacterm BWT (symbols 0..4)");
+				for (int s = 0; s < 5; ++s) cnt[s] += a[s];
+				if (a[5] != ~0ull) primary = a[5];
+			}
 		}
 		if (cnt[0] != 1) throw Error("bwtb3mtobwa needs exactly one terminator symbol in the BWT");
 		uint64_t L2[5]; L2[0] = 0;

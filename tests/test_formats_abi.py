@@ -100,6 +100,32 @@ def test_block_sym_histograms_and_rank(tmp_path):
         files.block_sym_histograms(fn, fn + ".bad", 1, 4)  # symbol 0 occurs: outside the stated range
 
 
+def test_to_bwa_host_tool_against_oracle(tmp_path, oracle):
+    """bwtb3mtobwa is a host tool (files in, files out, no GPU): .bwt + .sa of a pacterm text -> BWA's .bwt / .sa,
+    byte for byte what the restated MausFmToBwaConversion gives; texts without exactly one terminator are refused."""
+    from bwtb3m_b200 import files
+    rng = np.random.default_rng(21)
+    for l, sarate in ((5, 1), (1000, 4), (70_001, 32)):
+        t = np.concatenate([rng.integers(1, 5, size=l, dtype=np.uint8), np.zeros(1, dtype=np.uint8)])
+        sa = oracle.sa_circular(t)
+        bwt, isa = oracle.bwt_from_sa(t, sa)
+        fn = str(tmp_path / ("t%d.bwt" % l))
+        files.write_bwt_host(fn, bwt)
+        samples = sa[::sarate].astype(np.uint64)
+        with open(fn[:-4] + ".sa", "wb") as f:
+            f.write(np.array([sarate, samples.size], dtype=np.uint64).tobytes())
+            f.write(samples.tobytes())
+        files.to_bwa(fn, fn + ".bwa", fn + ".bwasa")
+        ob, osa = oracle.to_bwa(bwt, samples, sarate)
+        assert open(fn + ".bwa", "rb").read() == ob
+        assert open(fn + ".bwasa", "rb").read() == osa
+    bad = str(tmp_path / "bad.bwt")
+    files.write_bwt_host(bad, rng.integers(1, 5, size=100, dtype=np.uint8))  # no terminator
+    open(bad[:-4] + ".sa", "wb").write(np.array([4, 25] + [0] * 25, dtype=np.uint64).tobytes())
+    with pytest.raises(Exception):
+        files.to_bwa(bad, bad + ".bwa", bad + ".bwasa")
+
+
 def test_rl_container_rejects_garbage(tmp_path):
     from bwtb3m_b200 import files
     from bwtb3m_b200.engine import B3MError
