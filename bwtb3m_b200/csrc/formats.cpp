@@ -161,10 +161,12 @@ void huff_assign(HuffCode & h) {
 
 // canonical decoder: first code and first index per length
 struct HuffDecoder {
+	static constexpr unsigned LUT_BITS = 12; // codes of up to 12 bits decode with one table look-up
 	uint32_t first_code[RL_MAXCODELEN + 2];
 	uint32_t first_idx[RL_MAXCODELEN + 2];
 	uint32_t count[RL_MAXCODELEN + 2];
 	std::vector<uint16_t> sorted; // symbols by (length, symbol)
+	std::vector<uint32_t> lut;    // [next LUT_BITS bits] -> (symbol << 8) | code length, 0: a longer code
 	explicit HuffDecoder(HuffCode const & h) {
 		memset(count, 0, sizeof(count));
 		for (auto l : h.len) if (l) count[l]++;
@@ -176,22 +178,42 @@ struct HuffDecoder {
 		sorted.resize(idx);
 		std::vector<uint32_t> fill(first_idx, first_idx + RL_MAXCODELEN + 2);
 		for (size_t s = 0; s < h.len.size(); ++s) if (h.len[s]) sorted[fill[h.len[s]]++] = (uint16_t)s;
+		lut.assign((size_t)1 << LUT_BITS, 0);
+		for (unsigned l = 1; l <= LUT_BITS; ++l)
+			for (uint32_t k = 0; k < count[l]; ++k) {
+				uint32_t const c = first_code[l] + k, sym = sorted[first_idx[l] + k];
+				uint32_t const lo = c << (LUT_BITS - l), hi = (c + 1) << (LUT_BITS - l);
+				for (uint32_t x = lo; x < hi && x < lut.size(); ++x) lut[x] = (sym << 8) | l;
+			}
 	}
 };
 
+// MSB-first bit stream with a 64-bit window
 struct BitReader {
-	const uint8_t * p; uint64_t nbits; uint64_t pos = 0;
-	BitReader(const uint8_t * d, uint64_t bytes) : p(d), nbits(bytes * 8) {}
-	inline uint32_t bit() {
-		if (pos >= nbits) throw IoError("run-length stream: read past the end of a block");
-		uint32_t const b = (p[pos >> 3] >> (7 - (pos & 7))) & 1u; ++pos; return b;
+	const uint8_t * p; uint64_t nbytes; uint64_t next = 0; // next byte to load
+	uint64_t acc = 0; unsigned have = 0;                    // `have` valid bits at the top of acc
+	uint64_t used = 0;                                      // bits consumed
+	BitReader(const uint8_t * d, uint64_t bytes) : p(d), nbytes(bytes) {}
+	inline void refill() { while (have <= 56 && next < nbytes) { acc |= (uint64_t)p[next++] << (56 - have); have += 8; } }
+	// the next n <= 32 bits, zero padded behind the end of the block (consuming them there is the error)
+	inline uint32_t peek(unsigned n) { if (have < n) refill(); return n ? (uint32_t)(acc >> (64 - n)) : 0u; }
+	inline void skip(unsigned n) {
+		if (have < n) { refill(); if (have < n) throw IoError("run-length stream: read past the end of a block"); }
+		acc <<= n; have -= n; used += n;
 	}
-	inline uint64_t bits(unsigned n) { uint64_t v = 0; while (n--) v = (v << 1) | bit(); return v; }
+	inline uint64_t bits(unsigned n) { // n <= 64
+		uint64_t v = 0;
+		while (n > 32) { v = (v << 32) | peek(32); skip(32); n -= 32; }
+		if (n) { v = (v << n) | peek(n); skip(n); }
+		return v;
+	}
 	inline uint32_t huff(HuffDecoder const & d) {
-		uint32_t code = 0;
-		for (unsigned l = 1; l <= RL_MAXCODELEN; ++l) {
-			code = (code << 1) | bit();
-			if (d.count[l] && code >= d.first_code[l] && code - d.first_code[l] < d.count[l]) return d.sorted[d.first_idx[l] + (code - d.first_code[l])];
+		uint32_t const e = d.lut[peek(HuffDecoder::LUT_BITS)];
+		if (e) { skip(e & 255u); return e >> 8; }
+		uint32_t const w = peek(RL_MAXCODELEN);
+		for (unsigned l = HuffDecoder::LUT_BITS + 1; l <= RL_MAXCODELEN; ++l) {
+			uint32_t const code = w >> (RL_MAXCODELEN - l);
+			if (d.count[l] && code >= d.first_code[l] && code - d.first_code[l] < d.count[l]) { skip(l); return d.sorted[d.first_idx[l] + (code - d.first_code[l])]; }
 		}
 		throw IoError("run-length stream: invalid Huffman code");
 	}
@@ -449,7 +471,8 @@ std::vector<uint8_t> RlDecoder::decodeAll(std::vector<std::string> const & fns, 
 					uint64_t o = base[fi] + F.soff[b];
 					for (auto const & r : runs) {
 						if (o + r.second > n) throw IoError("run-length stream longer than its header says: " + F.fn);
-						memset(out.data() + o, r.first, r.second); o += r.second;
+						if (r.second < 8) { for (uint64_t x = 0; x < r.second; ++x) out[o + x] = r.first; } else memset(out.data() + o, r.first, r.second);
+						o += r.second;
 					}
 				}
 			} catch (std::exception const & ex) { errs[t] = ex.what(); }
