@@ -394,6 +394,9 @@ class DirectResults:
         for v in self.p.values():
             (self.mem.free if self.rank == 0 else self.mem.close)(v)
         self.p = {}
+        if getattr(self, "sa_local", None):
+            self.mem.free(self.sa_local)  # this rank's own copy of the sampled SA (build_xsharded, streamed samples)
+            self.sa_local = None
 
 
 def build_sharded_direct(engine, results, sasamplingrate=32, isasamplingrate=262144, bwtonly=False, device=None):
