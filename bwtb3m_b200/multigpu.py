@@ -595,7 +595,7 @@ class SharedHost:
             self.t = None
 
 
-def load_distributed(engine, host, inputtype, state):
+def load_distributed(engine, host, inputtype, state, device=None):
     """The input file reaches the GPUs over ALL their PCIe links: rank r copies bytes [r*chunk, (r+1)*chunk) of the
     page-locked file image `host` (a uint8 tensor every rank holds or maps) into its slice of a device buffer, one
     all-gather over NVLink completes the buffer on every rank, and every rank decodes the text (K1).  Runs on
@@ -605,7 +605,7 @@ def load_distributed(engine, host, inputtype, state):
     chunk = ((n + world - 1) // world + 255) // 256 * 256
     buf = state.get("in")
     if buf is None or buf.numel() != chunk * world:
-        buf = state["in"] = torch.empty(chunk * world, dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
+        buf = state["in"] = torch.empty(chunk * world, dtype=torch.uint8, device=device or torch.device("cuda", torch.cuda.current_device()))
     lo, hi = min(rank * chunk, n), min((rank + 1) * chunk, n)
     if hi > lo:
         buf[lo:hi].copy_(host[lo:hi], non_blocking=True)
@@ -615,7 +615,7 @@ def load_distributed(engine, host, inputtype, state):
     return hi - lo
 
 
-def fetch_distributed(engine, state, host_words_ptr, host_sa_ptr, host_preisa_ptr=0, host_isa_ptr=0):
+def fetch_distributed(engine, state, host_words_ptr, host_sa_ptr, host_preisa_ptr=0, host_isa_ptr=0, device=None):
     """Results of a sharded pacterm build (build_distributed, strategy "shard") to the host over ALL PCIe links:
     rank 0 packs BWA's BWT words (K9) into a buffer the other ranks map, every rank pulls its slice of the words
     and of the sampled SA out of rank 0's HBM over NVLink (cudaMemcpyAsync on peer-mapped memory) and copies it to
@@ -627,7 +627,7 @@ def fetch_distributed(engine, state, host_words_ptr, host_sa_ptr, host_preisa_pt
     if res is None:
         raise RuntimeError("fetch_distributed follows a sharded build_distributed with the same driver state")
     rank, world = res.rank, res.world
-    dev = torch.device("cuda", torch.cuda.current_device())
+    dev = device or torch.device("cuda", torch.cuda.current_device())  # (a CPU device only in the gloo tests of the schedule)
     stream_ptr = engine.stream_ptr
     n = res.n
     nwords = (n - 1 + 15) >> 4

@@ -45,6 +45,9 @@ class ShmMemory:
     def close(self, ptr):
         self.seg.pop(ptr).close()
 
+    def copy(self, dst, src, nbytes, stream_ptr=0):
+        C.memmove(dst, src, nbytes)
+
     def free(self, ptr):
         shm = self.seg.pop(ptr)
         shm.close()

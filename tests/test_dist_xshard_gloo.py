@@ -120,6 +120,16 @@ class XModelEngine:
                     host[r // sr] = p
         return 7 if self.force == self.part else 0
 
+    # ---- what load_distributed / fetch_distributed call ----
+    def load_device(self, ptr, n, inputtype):
+        self.loaded = self._view(ptr, n, C.c_uint8).copy()
+
+    def pack_bwa(self, words_ptr, w_lo, w_hi):
+        self._view(words_ptr, len(self.words), C.c_uint32)[w_lo:w_hi] = self.words[w_lo:w_hi]
+
+    def fetch_ptrs(self, bwt_p, pre_p, sa_p, isa_p):
+        self.small_fetch = (pre_p, isa_p)
+
     def shard_adopt(self, nparts, bwt_p, pre_p, sa_p, isa_p, spec_p):
         n = self.t.size
         pr, sr, ir = self.rates
@@ -161,6 +171,32 @@ def _worker(rank, world, port, force, no_stream_on, q):
                     hs = XModelEngine._view(host, -(-t.size // 32), C.c_int64)
                     good = good and np.array_equal(hs, sa[::32].astype(np.int64))
         dist.barrier()
+    # ---- the input over every rank's link, the two large results back the same way (CPU stand-ins for the copies) ----
+    if force is None:
+        src = np.random.default_rng(9).integers(0, 256, size=10_007, dtype=np.uint8)
+        io = {}
+        sent = multigpu.load_distributed(eng, torch.from_numpy(src), "pacterm", io, device=torch.device("cpu"))
+        good = good and np.array_equal(eng.loaded, src) and 0 < sent <= -(-src.size // world) + 256
+        nw = (t.size - 1 + 15) >> 4
+        eng.words = np.random.default_rng(10).integers(0, 1 << 32, size=nw, dtype=np.uint64).astype(np.uint32)
+        state = {"direct": res}
+        hw = res.extra("host_words_model", 4 * nw)
+        hs = res.extra("host_sa_model2", 8 * (-(-t.size // 32)))
+        for streamed in (False, True):
+            XModelEngine._view(hw, nw, C.c_uint32)[:] = 0
+            XModelEngine._view(hs, -(-t.size // 32), C.c_int64)[:] = -1
+            dist.barrier()
+            res.sa_streamed, res.stream_sa_host = streamed, hs
+            multigpu.fetch_distributed(eng, state, hw, hs, 1, 1, device=torch.device("cpu"))
+            dist.barrier()
+            if rank == 0:
+                good = good and np.array_equal(XModelEngine._view(hw, nw, C.c_uint32), eng.words) and eng.small_fetch == (1, 1)
+                got = XModelEngine._view(hs, -(-t.size // 32), C.c_int64)
+                if streamed:  # only sample 0 is written by the fetch, the rest is the finish kernels' business
+                    good = good and got[0] == sa[0] and np.all(got[1:] == -1)
+                else:
+                    good = good and np.array_equal(got, sa[::32].astype(np.int64))
+            dist.barrier()  # the other ranks clear the buffers for the next round only after rank 0 has looked
     flags = [None] * world
     dist.all_gather_object(flags, bool(good))
     if rank == 0:
